@@ -1,0 +1,1103 @@
+// engine.cpp — adjustment context and the C-ABI (include/gadj.h).
+//
+// Host orchestration of one Gauss–Newton iteration on the device:
+//   assemble (N, w)  ->  equilibrate + scatter into front panels  ->  supernodal
+//   Cholesky  ->  forward/backward solve  ->  x += delta  ->  [selected inverse]
+// mirroring dna_adjust::PrepareAdjustment / AdjustSimultaneous / Solve /
+// GenerateStatistics (ADJ:258, ADJ:2413-2511, ADJ:6586-6667, ADJ:6802-6841).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/gadj.h"
+#include "dev.h"
+#include "geodesy.h"
+#include "kernels.h"
+#include "plan.h"
+#include "symbolic.h"
+
+using namespace gadj;
+
+namespace {
+
+std::string g_create_error;
+
+template <class F>
+void parallel_for(uint64_t n, F&& fn)
+{
+    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (n < 65536 || nt == 1) {
+        fn(0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    uint64_t chunk = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+        uint64_t b = t * chunk, e = std::min(n, b + chunk);
+        if (b >= e)
+            break;
+        th.emplace_back([=, &fn] { fn(b, e); });
+    }
+    for (auto& t : th)
+        t.join();
+}
+
+// acklam + one Halley step; stands in for boost::math::quantile(normal) (ADJ:203-206)
+double norm_quantile(double p)
+{
+    static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
+                               1.383577518672690e+02,  -3.066479806614716e+01, 2.506628277459239e+00};
+    static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
+                               6.680131188771972e+01,  -1.328068155288572e+01};
+    static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
+                               -2.549732539343734e+00, 4.374664141464968e+00,  2.938163982698783e+00};
+    static const double d[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00,
+                               3.754408661907416e+00};
+    double q, r, x;
+    if (p < 0.02425) {
+        q = std::sqrt(-2 * std::log(p));
+        x = (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+            ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+    } else if (p <= 1 - 0.02425) {
+        q = p - 0.5;
+        r = q * q;
+        x = (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
+            (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1);
+    } else {
+        q = std::sqrt(-2 * std::log(1 - p));
+        x = -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+            ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+    }
+    double e = 0.5 * std::erfc(-x / std::sqrt(2.0)) - p;
+    double u = e * std::sqrt(2 * kPi) * std::exp(x * x / 2);
+    return x - u / (1 + x * u / 2);
+}
+
+void mat3_mul(const double* A, bool tA, const double* B, bool tB, double* C)  // row-major
+{
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k)
+                s += (tA ? A[k * 3 + i] : A[i * 3 + k]) * (tB ? B[j * 3 + k] : B[k * 3 + j]);
+            C[i * 3 + j] = s;
+        }
+}
+
+bool mat3_inverse(const double* A, double* B)
+{
+    double det = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
+    if (det == 0.0 || std::isnan(det))
+        return false;
+    double id = 1.0 / det;
+    B[0] = (A[4] * A[8] - A[5] * A[7]) * id;
+    B[1] = (A[2] * A[7] - A[1] * A[8]) * id;
+    B[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+    B[3] = (A[5] * A[6] - A[3] * A[8]) * id;
+    B[4] = (A[0] * A[8] - A[2] * A[6]) * id;
+    B[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+    B[6] = (A[3] * A[7] - A[4] * A[6]) * id;
+    B[7] = (A[1] * A[6] - A[0] * A[7]) * id;
+    B[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+    return true;
+}
+
+// geographic -> Cartesian Jacobian (dnatemplatematrixfuncs.hpp:204-232), row-major
+void cart_geo_jacobian(const Ellipsoid& e, double lat, double lon, double h, double* R)
+{
+    double cl = std::cos(lat), sl = std::sin(lat), co = std::cos(lon), so = std::sin(lon);
+    double t1a = e.a * e.e2;
+    double ome = 1. - e.e2;
+    double nu = prime_vertical(e, lat);
+    double nuh = nu + h;
+    double nu1h = nu * ome + h;
+    double t1b = t1a * sl * cl;
+    double t1c = std::pow((1. - e.e2 * sl * sl), 1.5);
+    R[0] = (t1b * cl * co / t1c) - (nuh * sl * co);
+    R[1] = -nuh * cl * so;
+    R[2] = cl * co;
+    R[3] = (t1b * cl * so / t1c) - (nuh * sl * so);
+    R[4] = nuh * cl * co;
+    R[5] = cl * so;
+    R[6] = (t1b * ome * sl / t1c) + (nu1h * cl);
+    R[7] = 0.;
+    R[8] = sl;
+}
+
+template <class T>
+struct DevArray {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevArray() { release(); }
+    void release()
+    {
+        if (p)
+            dev::free_(p);
+        p = nullptr;
+        n = 0;
+    }
+    bool resize(size_t count)
+    {
+        release();
+        if (count == 0)
+            return true;
+        p = (T*)dev::alloc(count * sizeof(T));
+        n = p ? count : 0;
+        return p != nullptr;
+    }
+    bool upload(const std::vector<T>& v)
+    {
+        if (!resize(v.size()))
+            return false;
+        if (!v.empty())
+            dev::h2d(p, v.data(), v.size() * sizeof(T));
+        return true;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+}  // namespace
+
+struct gadj_ctx {
+    gadj_opts o{};
+    std::string err;
+    Ellipsoid ell{};
+    // borrowed host data
+    dna_stn_t* stn = nullptr;
+    uint32_t nstn = 0;
+    dna_msr_t* msr = nullptr;
+    uint64_t nmsr = 0;
+    int reduced = 0;
+    std::vector<uint32_t> isl_off, isl;
+    // measurement plan
+    std::vector<uint32_t> first, edge_word;
+    std::vector<uint32_t> edge_hi, edge_lo;
+    bool contiguous = false;
+    uint64_t nbsl = 0, nedge = 0;
+    uint32_t constrained_components = 0;
+    // structure
+    Symbolic sym;
+    Plan plan;
+    bool prepared = false, factor_valid = false, inverse_valid = false, normals_valid = false;
+    uint32_t iteration = 0;
+    double critical = 0;
+    // device state
+    DevArray<dna_msr_t> d_msr;
+    DevArray<uint32_t> d_first, d_edge, d_edge_hi, d_edge_lo, d_pos, d_diag_ld, d_off_ld;
+    DevArray<uint64_t> d_diag_dest, d_off_dest;
+    DevArray<double> d_est, d_est0, d_llh, d_cblock, d_ndiag, d_noff, d_w, d_dscale, d_panels, d_pool, d_x, d_corr, d_vcvd,
+        d_vcvo, d_sums;
+    DevArray<int32_t> d_rowmap, d_rowidx, d_info;
+    DevArray<GemmOp> d_gemm;
+    DevArray<DiagOp> d_diag;
+    DevArray<TriOp> d_tri;
+    DevArray<GemvOp> d_gemv;
+    DevArray<TransposeOp> d_tr;
+    DevArray<GatherOp> d_gather;
+    std::vector<double> h_corr;
+    void* ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint64_t device_bytes = 0;
+
+    int fail(const std::string& m)
+    {
+        err = m;
+        return 1;
+    }
+};
+
+namespace {
+
+void run_launches(gadj_ctx* c, const std::vector<Launch>& list)
+{
+    void* st = dev::stream();
+    for (const Launch& L : list) {
+        switch (L.kind) {
+        case L_GEMM:
+            launch_gemm(c->d_gemm.p + L.op_begin, L.op_count, L.total_tiles, st);
+            break;
+        case L_DIAG:
+            launch_diag(c->d_diag.p + L.op_begin, L.op_count, c->d_info.p, st);
+            break;
+        case L_TRI_FWD:
+            launch_tri(c->d_tri.p + L.op_begin, L.op_count, 0, st);
+            break;
+        case L_TRI_BWD:
+            launch_tri(c->d_tri.p + L.op_begin, L.op_count, 1, st);
+            break;
+        case L_GEMV_FWD:
+            launch_gemv(c->d_gemv.p + L.op_begin, L.op_count, c->d_x.p, c->d_x.p, 0, st);
+            break;
+        case L_GEMV_BWD:
+            launch_gemv(c->d_gemv.p + L.op_begin, L.op_count, c->d_x.p, c->d_x.p, 1, st);
+            break;
+        case L_TRANSPOSE:
+            launch_transpose(c->d_tr.p + L.op_begin, L.op_count, st);
+            break;
+        case L_GATHER:
+            launch_gather(c->d_gather.p + L.op_begin, L.op_count, st);
+            break;
+        case L_ZERO:
+            dev::zero(L.zero_ptr, L.zero_bytes);
+            break;
+        }
+    }
+}
+
+// FormConstraintStationVarianceMatrix (ADJ:2041-2137): inverse-variance block, row-major
+bool constraint_block(const gadj_ctx* c, const dna_stn_t& s, double* out)
+{
+    double varC = c->o.fixed_std_dev * c->o.fixed_std_dev;
+    double varF = c->o.free_std_dev * c->o.free_std_dev;
+    const char* k = s.stationConst;
+    std::memset(out, 0, 9 * sizeof(double));
+    if (k[0] == 'C' && k[1] == 'C' && k[2] == 'C') {
+        out[0] = out[4] = out[8] = 1. / varC;
+        return true;
+    }
+    if (k[0] == 'F' && k[1] == 'F' && k[2] == 'F') {
+        out[0] = out[4] = out[8] = 1. / varF;
+        return true;
+    }
+    double L[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    bool llh = (s.suppliedStationType == DNA_LLH_TYPE || s.suppliedStationType == DNA_LLh_TYPE);
+    double v0 = (k[0] == 'F') ? varF : varC;
+    double v1 = (k[1] == 'F') ? varF : varC;
+    if (llh) {
+        L[4] = v0;  // latitude  -> north
+        L[0] = v1;  // longitude -> east
+    } else {
+        L[0] = v0;
+        L[4] = v1;
+    }
+    L[8] = (k[2] == 'F') ? varF : varC;
+    double V[9];
+    if (s.suppliedStationType == DNA_XYZ_TYPE)
+        std::memcpy(V, L, sizeof(V));
+    else {
+        double R[9], T[9];
+        local_to_cart_rotation(s.currentLatitude, s.currentLongitude, R);
+        mat3_mul(R, false, L, false, T);
+        mat3_mul(T, false, R, true, V);
+    }
+    double up[6] = {V[0], V[1], V[2], V[4], V[5], V[8]}, inv[6];
+    if (!spd3_inverse(up, inv))
+        return false;
+    out[0] = inv[0];
+    out[1] = out[3] = inv[1];
+    out[2] = out[6] = inv[2];
+    out[4] = inv[3];
+    out[5] = out[7] = inv[4];
+    out[8] = inv[5];
+    return true;
+}
+
+// LoadVarianceScaling + the scaling half of LoadVarianceMatrix_G (ADJ:4214-4282, 4453-4491):
+// applied once, on the host, when the records are raw; the scaled variances are written back
+// into the records so that every later consumer (device assembly, chi-square) reads them as-is.
+void first_run_reduction(gadj_ctx* c)
+{
+    const double lim = std::fmin(1.0e-5, c->o.fixed_std_dev);
+    dna_msr_t* msr = c->msr;
+    const dna_stn_t* stn = c->stn;
+    const Ellipsoid ell = c->ell;
+    const std::vector<uint32_t>& first = c->first;
+    const int reduced = c->reduced;
+    parallel_for(first.size(), [&](uint64_t b0, uint64_t b1) {
+        for (uint64_t b = b0; b < b1; ++b) {
+            dna_msr_t* m = msr + first[b];
+            if (reduced) {
+                for (int r = 0; r < 3; ++r)
+                    m[r].term1 = m[r].preAdjMeas;  // InitialiseMeasurement (ADJ:3913-3935)
+                continue;
+            }
+            for (int r = 0; r < 3; ++r)
+                m[r].preAdjMeas = m[r].term1;
+            double vS = m[0].scale4, pS = m[0].scale1, lS = m[0].scale2, hS = m[0].scale3;
+            if (vS < lim)
+                vS = 1.0;
+            if (pS < lim)
+                pS = 1.0;
+            if (lS < lim)
+                lS = 1.0;
+            if (hS < lim)
+                hS = 1.0;
+            bool scaleMatrix = std::fabs(vS - 1.0) > 1.0e-5;
+            bool scalePartial =
+                std::fabs(pS - 1.0) > 1.0e-5 || std::fabs(lS - 1.0) > 1.0e-5 || std::fabs(hS - 1.0) > 1.0e-5;
+            if (!scaleMatrix && !scalePartial)
+                continue;
+            if (scalePartial && scaleMatrix) {
+                pS *= vS;
+                lS *= vS;
+                hS *= vS;
+            }
+            double V[9];
+            double s = scaleMatrix ? vS : 1.0;
+            V[0] = m[0].term2 * s;
+            V[1] = V[3] = m[1].term2 * s;
+            V[4] = m[1].term3 * s;
+            V[2] = V[6] = m[2].term2 * s;
+            V[5] = V[7] = m[2].term3 * s;
+            V[8] = m[2].term4 * s;
+            if (scalePartial) {
+                // ScaleGPSVCV (dnatemplatematrixfuncs.hpp:372-399) at station 1
+                const dna_stn_t& s1 = stn[m[2].station1];
+                double R[9], Ri[9], T[9], Vg[9];
+                cart_geo_jacobian(ell, s1.currentLatitude, s1.currentLongitude, s1.currentHeight, R);
+                if (mat3_inverse(R, Ri)) {
+                    mat3_mul(Ri, false, V, false, T);
+                    mat3_mul(T, false, Ri, true, Vg);
+                    double sc[3] = {std::sqrt(pS), std::sqrt(lS), std::sqrt(hS)};
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j)
+                            Vg[i * 3 + j] *= sc[i] * sc[j];
+                    mat3_mul(R, false, Vg, false, T);
+                    mat3_mul(T, false, R, true, V);
+                }
+            }
+            m[0].term2 = V[0];
+            m[1].term2 = V[1];
+            m[1].term3 = V[4];
+            m[2].term2 = V[2];
+            m[2].term3 = V[5];
+            m[2].term4 = V[8];
+        }
+    });
+}
+
+int scan_measurements(gadj_ctx* c)
+{
+    c->first.clear();
+    uint64_t i = 0;
+    while (i < c->nmsr) {
+        const dna_msr_t& m = c->msr[i];
+        uint64_t step = 1;
+        switch (m.measType) {
+        case 'G':
+            step = 3;
+            break;
+        case 'X':
+        case 'Y': {
+            uint64_t j = i;
+            for (uint32_t k = 0; k < m.vectorCount1 && j < c->nmsr; ++k)
+                j += 3 + 3ull * c->msr[j].vectorCount2;
+            step = j - i;
+            break;
+        }
+        case 'D':
+            step = 1ull + m.vectorCount1;
+            break;
+        default:
+            step = 1;
+        }
+        if (step == 0)
+            step = 1;
+        if (!m.ignore) {
+            if (m.measType != 'G')
+                return c->fail(std::string("measurement type '") + m.measType +
+                               "' is not handled by the device assembly yet (GNSS baselines 'G' only)");
+            if (i + 3 > c->nmsr)
+                return c->fail("truncated GNSS baseline at the end of the measurement list");
+            if (i > 0xFFFFFFF0ull)
+                return c->fail("measurement index exceeds 32 bits");
+            c->first.push_back((uint32_t)i);
+        }
+        i += step;
+    }
+    c->nbsl = c->first.size();
+    if (c->nbsl == 0)
+        return c->fail("no measurements to adjust");
+    c->contiguous = true;
+    for (uint64_t b = 0; b < c->nbsl; ++b)
+        if (c->first[b] != c->first[0] + 3 * b) {
+            c->contiguous = false;
+            break;
+        }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void gadj_default_opts(gadj_opts* o)
+{
+    std::memset(o, 0, sizeof(*o));
+    o->fixed_std_dev = 1.0e-6;
+    o->free_std_dev = 10.0;
+    o->iteration_threshold = (double)0.0005f;
+    o->semi_major = 6378137.0;
+    o->inv_flattening = 298.257222101;
+    o->confidence_interval = 95.0;
+    o->workspace_gb = 0.0;
+    o->max_iterations = 10;
+    o->scale_normals_to_unity = 1;
+    o->ordering = GADJ_ORDER_AUTO;
+    o->leaf_stations = 96;
+    o->device = 0;
+}
+
+const char* gadj_last_error(const gadj_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int gadj_create(const gadj_opts* o, gadj_ctx** out)
+{
+    *out = nullptr;
+    gadj_opts d;
+    gadj_default_opts(&d);
+    if (o)
+        d = *o;
+    std::string e = dev::init(d.device);
+    if (!e.empty()) {
+        g_create_error = e;
+        return 1;
+    }
+    gadj_ctx* c = new gadj_ctx();
+    c->o = d;
+    if (c->o.leaf_stations == 0)
+        c->o.leaf_stations = 96;
+    c->ell = make_ellipsoid(c->o.semi_major, c->o.inv_flattening);
+    double conf = c->o.confidence_interval * 0.01;
+    conf += (1.0 - conf) / 2.0;
+    c->critical = norm_quantile(conf);
+    for (auto& e2 : c->ev)
+        e2 = dev::event_create();
+    *out = c;
+    return 0;
+}
+
+void gadj_destroy(gadj_ctx* c)
+{
+    if (!c)
+        return;
+    dev::sync();
+    for (auto& e : c->ev)
+        if (e)
+            dev::event_destroy(e);
+    delete c;
+}
+
+int gadj_set_stations(gadj_ctx* c, dna_stn_t* stn, uint32_t count)
+{
+    if (!stn || count == 0)
+        return c->fail("empty station list");
+    c->stn = stn;
+    c->nstn = count;
+    c->prepared = false;
+    return 0;
+}
+
+int gadj_set_measurements(gadj_ctx* c, dna_msr_t* msr, uint64_t count)
+{
+    if (!msr || count == 0)
+        return c->fail("empty measurement list");
+    c->msr = msr;
+    c->nmsr = count;
+    c->prepared = false;
+    return 0;
+}
+
+int gadj_set_blocks(gadj_ctx* c, uint32_t nblocks, const uint32_t* isl_off, const uint32_t* isl)
+{
+    c->isl_off.clear();
+    c->isl.clear();
+    if (nblocks > 1) {
+        if (!isl_off || !isl)
+            return c->fail("block lists missing");
+        c->isl_off.assign(isl_off, isl_off + nblocks + 1);
+        c->isl.assign(isl, isl + isl_off[nblocks]);
+    }
+    c->prepared = false;
+    return 0;
+}
+
+int gadj_prepare(gadj_ctx* c)
+{
+    c->prepared = false;
+    c->factor_valid = c->inverse_valid = c->normals_valid = false;
+    c->iteration = 0;
+    if (!c->stn || !c->msr)
+        return c->fail("stations and measurements must be set before gadj_prepare");
+    if (scan_measurements(c))
+        return 1;
+    for (uint64_t b = 0; b < c->nbsl; ++b) {
+        const dna_msr_t& m = c->msr[c->first[b]];
+        if (m.station1 >= c->nstn || m.station2 >= c->nstn)
+            return c->fail("measurement refers to a station index beyond the station list");
+        if (m.station1 == m.station2)
+            return c->fail("GNSS baseline with identical end stations");
+    }
+    first_run_reduction(c);
+
+    // unique station pairs -> edge slots
+    const uint64_t nb = c->nbsl;
+    std::vector<uint64_t> keys(nb);
+    for (uint64_t b = 0; b < nb; ++b) {
+        const dna_msr_t& m = c->msr[c->first[b]];
+        uint32_t lo = std::min(m.station1, m.station2), hi = std::max(m.station1, m.station2);
+        keys[b] = ((uint64_t)lo << 32) | hi;
+    }
+    std::vector<uint64_t> uniq(keys);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    c->nedge = uniq.size();
+    if (c->nedge >= (1ull << 31))
+        return c->fail("too many distinct station pairs");
+    std::vector<std::pair<uint32_t, uint32_t>> edges(c->nedge);
+    for (uint64_t e = 0; e < c->nedge; ++e)
+        edges[e] = {(uint32_t)(uniq[e] >> 32), (uint32_t)(uniq[e] & 0xFFFFFFFFu)};
+
+    std::vector<double> lat(c->nstn), lon(c->nstn);
+    c->constrained_components = 0;
+    for (uint32_t s = 0; s < c->nstn; ++s) {
+        lat[s] = c->stn[s].currentLatitude;
+        lon[s] = c->stn[s].currentLongitude;
+        for (int k = 0; k < 3; ++k)
+            c->constrained_components += c->stn[s].stationConst[k] == 'C';
+    }
+    OrderingOptions oo;
+    oo.leaf_stations = c->o.leaf_stations;
+    oo.dense = c->o.ordering == GADJ_ORDER_DENSE;
+    uint32_t nblocks = c->isl_off.empty() ? 1u : (uint32_t)c->isl_off.size() - 1;
+    std::string e = analyse(c->nstn, edges, lat.data(), lon.data(), oo, nblocks,
+                            c->isl_off.empty() ? nullptr : c->isl_off.data(), c->isl.empty() ? nullptr : c->isl.data(),
+                            c->sym);
+    if (!e.empty())
+        return c->fail(e);
+    const Symbolic& S = c->sym;
+
+    // per-edge orientation and destinations
+    c->edge_hi.resize(c->nedge);
+    c->edge_lo.resize(c->nedge);
+    std::vector<uint64_t> off_dest(c->nedge), diag_dest(c->nstn);
+    std::vector<uint32_t> off_ld(c->nedge), diag_ld(c->nstn);
+    bool bad = false;
+    parallel_for(c->nedge, [&](uint64_t e0, uint64_t e1) {
+        for (uint64_t ei = e0; ei < e1; ++ei) {
+            uint32_t a = edges[ei].first, b2 = edges[ei].second;
+            uint32_t pa = S.pos_of_stn[a], pb = S.pos_of_stn[b2];
+            uint32_t hi = pa > pb ? a : b2, lo = pa > pb ? b2 : a;
+            c->edge_hi[ei] = hi;
+            c->edge_lo[ei] = lo;
+            uint64_t slot = find_slot(S, std::max(pa, pb), std::min(pa, pb));
+            if (slot == UINT64_MAX) {
+                bad = true;
+                continue;
+            }
+            off_dest[ei] = S.ndest[slot];
+            off_ld[ei] = S.ndest_ld[slot];
+        }
+    });
+    if (bad)
+        return c->fail("internal: station pair missing from the normal-matrix pattern");
+    for (uint32_t s = 0; s < c->nstn; ++s) {
+        uint64_t slot = S.ncol_ptr[S.pos_of_stn[s]];
+        diag_dest[s] = S.ndest[slot];
+        diag_ld[s] = S.ndest_ld[slot];
+    }
+    c->edge_word.resize(nb);
+    parallel_for(nb, [&](uint64_t b0, uint64_t b1) {
+        for (uint64_t b = b0; b < b1; ++b) {
+            const dna_msr_t& m = c->msr[c->first[b]];
+            uint64_t ei = std::lower_bound(uniq.begin(), uniq.end(), keys[b]) - uniq.begin();
+            uint32_t flip = S.pos_of_stn[m.station1] > S.pos_of_stn[m.station2] ? 0x80000000u : 0u;
+            c->edge_word[b] = (uint32_t)ei | flip;
+        }
+    });
+
+    // a-priori Cartesian coordinates and constraint blocks
+    std::vector<double> est(3 * (size_t)c->nstn), cb(9 * (size_t)c->nstn);
+    for (uint32_t s = 0; s < c->nstn; ++s) {
+        geo_to_cart(c->ell, c->stn[s].currentLatitude, c->stn[s].currentLongitude, c->stn[s].currentHeight, &est[3 * s]);
+        if (!constraint_block(c, c->stn[s], &cb[9 * s]))
+            return c->fail("station constraint variance matrix is not positive definite");
+    }
+
+    // ---- device memory ---------------------------------------------------------
+    build_rowidx(S, c->plan);
+    std::vector<double> z;
+    bool ok = true;
+    ok &= c->d_msr.resize(c->nmsr);
+    ok &= c->d_first.upload(c->first);
+    ok &= c->d_edge.upload(c->edge_word);
+    ok &= c->d_edge_hi.upload(c->edge_hi);
+    ok &= c->d_edge_lo.upload(c->edge_lo);
+    ok &= c->d_pos.upload(S.pos_of_stn);
+    ok &= c->d_diag_dest.upload(diag_dest);
+    ok &= c->d_diag_ld.upload(diag_ld);
+    ok &= c->d_off_dest.upload(off_dest);
+    ok &= c->d_off_ld.upload(off_ld);
+    ok &= c->d_est.upload(est);
+    ok &= c->d_est0.upload(est);
+    ok &= c->d_cblock.upload(cb);
+    ok &= c->d_llh.resize(3 * (size_t)c->nstn);
+    ok &= c->d_ndiag.resize(9 * (size_t)c->nstn);
+    ok &= c->d_noff.resize(9 * (size_t)c->nedge);
+    ok &= c->d_w.resize(3 * (size_t)c->nstn);
+    ok &= c->d_dscale.resize(3 * (size_t)c->nstn);
+    ok &= c->d_x.resize(3 * (size_t)c->nstn);
+    ok &= c->d_corr.resize(3 * (size_t)c->nstn + 8);
+    ok &= c->d_vcvd.resize(9 * (size_t)c->nstn);
+    ok &= c->d_vcvo.resize(9 * (size_t)c->nedge);
+    ok &= c->d_sums.resize(8);
+    ok &= c->d_info.resize(4);
+    ok &= c->d_rowmap.upload(S.rowmap);
+    ok &= c->d_rowidx.upload(c->plan.rowidx);
+    ok &= c->d_panels.resize(S.panel_doubles);
+    if (!ok)
+        return c->fail("out of device memory while allocating the adjustment state");
+    dev::h2d(c->d_msr.p, c->msr, c->nmsr * sizeof(dna_msr_t));
+
+    size_t want = ideal_pool_doubles(S), least = min_pool_doubles(S);
+    size_t budget;
+    if (c->o.workspace_gb > 0)
+        budget = (size_t)(c->o.workspace_gb * 1e9 / 8);
+    else
+        budget = (size_t)(0.6 * (double)dev::mem_free() / 8);
+    size_t pool = std::max(least, std::min(want, budget));
+    if (!c->d_pool.resize(pool))
+        return c->fail("out of device memory while allocating the inverse workspace");
+
+    PlanBuffers pb;
+    pb.panels = c->d_panels.p;
+    pb.pool = c->d_pool.p;
+    pb.pool_doubles = pool;
+    pb.x = c->d_x.p;
+    pb.rowmap = c->d_rowmap.p;
+    pb.rowidx = c->d_rowidx.p;
+    e = build_plan(S, pb, c->plan);
+    if (!e.empty())
+        return c->fail(e);
+    ok = true;
+    ok &= c->d_gemm.upload(c->plan.gemm);
+    ok &= c->d_diag.upload(c->plan.diag);
+    ok &= c->d_tri.upload(c->plan.tri);
+    ok &= c->d_gemv.upload(c->plan.gemv);
+    ok &= c->d_tr.upload(c->plan.transpose);
+    ok &= c->d_gather.upload(c->plan.gather);
+    if (!ok)
+        return c->fail("out of device memory while uploading the launch plan");
+    e = dev::sync();
+    if (!e.empty())
+        return c->fail(e);
+    c->device_bytes = c->d_msr.bytes() + c->d_panels.bytes() + c->d_pool.bytes() + c->d_noff.bytes() + c->d_ndiag.bytes() +
+                      c->d_gemm.bytes() + c->d_gemv.bytes() + c->d_vcvo.bytes() + c->d_vcvd.bytes();
+    c->h_corr.assign(3 * (size_t)c->nstn, 0.0);
+    c->prepared = true;
+    return 0;
+}
+
+int gadj_get_info(const gadj_ctx* c, gadj_info* info)
+{
+    std::memset(info, 0, sizeof(*info));
+    if (!c->prepared)
+        return 1;
+    info->nstations = c->nstn;
+    info->nbaselines = c->nbsl;
+    info->nedges = c->nedge;
+    info->nfronts = c->sym.fronts.size();
+    info->nlevels = c->sym.levels.size();
+    info->panel_bytes = c->sym.panel_doubles * 8;
+    info->pool_bytes = c->d_pool.bytes();
+    info->device_bytes = c->device_bytes;
+    info->factor_flops = c->plan.factor_flops;
+    info->inverse_flops = c->plan.selinv_flops;
+    info->launches_factor = c->plan.factor.size();
+    info->launches_solve = c->plan.fwd.size() + c->plan.bwd.size();
+    info->launches_inverse = c->plan.selinv.size();
+    for (const Front& f : c->sym.fronts) {
+        info->max_front_rows = std::max(info->max_front_rows, f.m);
+        info->max_front_cols = std::max(info->max_front_cols, f.k);
+    }
+    return 0;
+}
+
+int gadj_upload_measurements(gadj_ctx* c)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    dev::h2d(c->d_msr.p, c->msr, c->nmsr * sizeof(dna_msr_t));
+    return 0;
+}
+
+int gadj_reset_estimates(gadj_ctx* c)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    dev::d2d(c->d_est.p, c->d_est0.p, c->d_est.bytes());
+    c->iteration = 0;
+    c->factor_valid = c->inverse_valid = false;
+    return 0;
+}
+
+static void fill_assemble(gadj_ctx* c, AssembleParams& ap, int normals)
+{
+    ap.msr = c->d_msr.p;
+    ap.first = c->d_first.p;
+    ap.edge = c->d_edge.p;
+    ap.est = c->d_est.p;
+    ap.ndiag = c->d_ndiag.p;
+    ap.noff = c->d_noff.p;
+    ap.w = c->d_w.p;
+    ap.chi2 = nullptr;
+    ap.nbaselines = c->nbsl;
+    ap.contiguous = c->contiguous ? 1 : 0;
+    ap.normals = normals;
+}
+
+static void fill_scatter(gadj_ctx* c, ScatterParams& sp)
+{
+    sp.ndiag = c->d_ndiag.p;
+    sp.noff = c->d_noff.p;
+    sp.diag_dest = c->d_diag_dest.p;
+    sp.diag_ld = c->d_diag_ld.p;
+    sp.off_dest = c->d_off_dest.p;
+    sp.off_ld = c->d_off_ld.p;
+    sp.edge_hi = c->d_edge_hi.p;
+    sp.edge_lo = c->d_edge_lo.p;
+    sp.panels = c->d_panels.p;
+    sp.dscale = c->d_dscale.p;
+    sp.nstn = c->nstn;
+    sp.nedge = c->nedge;
+    sp.scale = c->o.scale_normals_to_unity ? 1 : 0;
+}
+
+int gadj_iterate(gadj_ctx* c, int flags, gadj_iter_result* res)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    void* st = dev::stream();
+    bool normals = (flags & GADJ_ITER_NORMALS) || !c->factor_valid;
+    dev::event_record(c->ev[0]);
+    // ---- assembly (FillDesignNormalMeasurementsMatrices, ADJ:3888) --------------
+    launch_init_normals(normals ? c->d_cblock.p : nullptr, c->d_ndiag.p, c->d_noff.p, c->d_w.p, c->nstn,
+                        normals ? c->nedge : 0, st);
+    AssembleParams ap;
+    fill_assemble(c, ap, normals ? 1 : 0);
+    launch_assemble_g(ap, st);
+    dev::event_record(c->ev[1]);
+    // ---- factorisation (Solve: dpotrf, ADJ:6628) --------------------------------
+    if (normals) {
+        c->inverse_valid = false;
+        c->factor_valid = false;
+        ScatterParams sp;
+        fill_scatter(c, sp);
+        launch_compute_scale(sp, st);
+        dev::zero(c->d_panels.p, c->d_panels.bytes());
+        dev::zero(c->d_info.p, c->d_info.bytes());
+        launch_scatter_normals(sp, st);
+        run_launches(c, c->plan.factor);
+        c->normals_valid = true;
+    }
+    dev::event_record(c->ev[2]);
+    // ---- solve + estimates update (ADJ:6659-6667, ADJ:2463-2466) -----------------
+    launch_permute_rhs(c->d_w.p, c->d_dscale.p, c->d_pos.p, c->d_x.p, c->nstn, st);
+    run_launches(c, c->plan.fwd);
+    run_launches(c, c->plan.bwd);
+    launch_apply_corrections(c->d_x.p, c->d_dscale.p, c->d_pos.p, c->d_corr.p, c->d_est.p, c->nstn, st);
+    dev::event_record(c->ev[3]);
+    if (flags & GADJ_ITER_INVERSE) {
+        run_launches(c, c->plan.selinv);
+    }
+    dev::event_record(c->ev[4]);
+    int32_t info[4] = {0, 0, 0, 0};
+    double tail[8];
+    dev::d2h(info, c->d_info.p, sizeof(info));
+    dev::d2h(tail, c->d_corr.p + 3 * (size_t)c->nstn, sizeof(tail));
+    std::string e = dev::sync();
+    if (!e.empty())
+        return c->fail(e);
+    if (normals) {
+        if (info[0] != 0) {
+            c->factor_valid = false;
+            if (getenv("GADJ_DEBUG")) {
+                const Front& f = c->sym.fronts[info[0] - 1];
+                fprintf(stderr, "gadj: non-positive pivot in front %d (level %d, k=%u r=%u parent=%d)\n", info[0] - 1, f.level,
+                        f.k, f.r, f.parent);
+            }
+            return c->fail("Matrix inversion failed, the matrix is singular.");
+        }
+        c->factor_valid = true;
+    }
+    if (flags & GADJ_ITER_INVERSE) {
+        c->inverse_valid = true;
+        c->factor_valid = false;  // the panels now hold the inverse, not the factor
+    }
+    c->iteration++;
+    if (res) {
+        std::memset(res, 0, sizeof(*res));
+        res->max_corr = tail[0];
+        uint64_t row = (uint64_t)tail[1];
+        res->max_corr_station = (uint32_t)(row / 3);
+        res->max_corr_axis = (uint32_t)(row % 3);
+        res->iteration = c->iteration;
+        res->converged = std::fabs(tail[0]) <= c->o.iteration_threshold;
+        res->ms_assemble = dev::event_elapsed_ms(c->ev[0], c->ev[1]);
+        res->ms_factor = dev::event_elapsed_ms(c->ev[1], c->ev[2]);
+        res->ms_solve = dev::event_elapsed_ms(c->ev[2], c->ev[3]);
+        res->ms_inverse = dev::event_elapsed_ms(c->ev[3], c->ev[4]);
+        if (std::isnan(tail[0]) || std::isinf(tail[0]))
+            return c->fail("Solve(): Invalid variance matrix");
+    }
+    return 0;
+}
+
+int gadj_adjust(gadj_ctx* c, gadj_iter_result* last)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    gadj_iter_result r{};
+    // AdjustSimultaneous (ADJ:2413-2511): the normals of a GNSS-only network never change, so
+    // iterations >= 2 re-use the factorisation exactly as the reference re-uses its inverse.
+    float ms_inv = 0;
+    for (uint32_t i = 0; i < c->o.max_iterations; ++i) {
+        int flags = (c->iteration < 1) ? GADJ_ITER_NORMALS : 0;
+        if (gadj_iterate(c, flags, &r))
+            return 1;
+        if (std::fabs(r.max_corr) <= c->o.iteration_threshold)
+            break;
+    }
+    // rigorous variances (the reference carries them in v_normals_ after Solve)
+    if (!c->inverse_valid) {
+        dev::event_record(c->ev[3]);
+        run_launches(c, c->plan.selinv);
+        dev::event_record(c->ev[4]);
+        std::string e = dev::sync();
+        if (!e.empty())
+            return c->fail(e);
+        ms_inv = dev::event_elapsed_ms(c->ev[3], c->ev[4]);
+        c->inverse_valid = true;
+        c->factor_valid = false;
+    }
+    r.ms_inverse = ms_inv;
+    if (last)
+        *last = r;
+    return 0;
+}
+
+static int extract_vcv(gadj_ctx* c)
+{
+    if (!c->inverse_valid)
+        return c->fail("the rigorous inverse has not been formed (run gadj_adjust or iterate with GADJ_ITER_INVERSE)");
+    void* st = dev::stream();
+    launch_extract_station_vcv(c->d_panels.p, c->d_diag_dest.p, c->d_diag_ld.p, c->d_dscale.p, c->d_vcvd.p, c->nstn, st);
+    launch_extract_edge_vcv(c->d_panels.p, c->d_off_dest.p, c->d_off_ld.p, c->d_edge_hi.p, c->d_edge_lo.p, c->d_dscale.p,
+                            c->d_vcvo.p, c->nedge, st);
+    return 0;
+}
+
+int gadj_statistics(gadj_ctx* c, gadj_stats* stt, int write_back)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    if (extract_vcv(c))
+        return 1;
+    void* st = dev::stream();
+    // UpdateAdjustment(false): geographic coordinates + re-linearised l (ADJ:6807, ADJ:8734)
+    launch_cart_to_geo(c->d_est.p, c->d_llh.p, c->nstn, c->o.semi_major, c->o.inv_flattening, st);
+    dev::zero(c->d_sums.p, c->d_sums.bytes());
+    StatsParams sp;
+    sp.msr = c->d_msr.p;
+    sp.first = c->d_first.p;
+    sp.edge = c->d_edge.p;
+    sp.est = c->d_est.p;
+    sp.vcv_diag = c->d_vcvd.p;
+    sp.vcv_off = c->d_vcvo.p;
+    sp.sums = c->d_sums.p;
+    sp.nbaselines = c->nbsl;
+    sp.critical = c->critical;
+    launch_stats_g(sp, st);
+    double sums[8];
+    dev::d2h(sums, c->d_sums.p, sizeof(sums));
+    std::vector<double> llh;
+    if (write_back) {
+        dev::d2h(c->msr, c->d_msr.p, c->nmsr * sizeof(dna_msr_t));
+        llh.resize(3 * (size_t)c->nstn);
+        dev::d2h(llh.data(), c->d_llh.p, llh.size() * sizeof(double));
+    }
+    std::string e = dev::sync();
+    if (!e.empty())
+        return c->fail(e);
+    if (write_back)
+        for (uint32_t s = 0; s < c->nstn; ++s) {
+            c->stn[s].currentLatitude = llh[3 * s];
+            c->stn[s].currentLongitude = llh[3 * s + 1];
+            c->stn[s].currentHeight = llh[3 * s + 2];
+        }
+    std::memset(stt, 0, sizeof(*stt));
+    stt->chi_squared = sums[0];
+    stt->measurement_params = (uint32_t)(3 * c->nbsl);
+    stt->unknown_params = 3 * c->nstn - c->constrained_components;
+    stt->dof = (int64_t)stt->measurement_params - (int64_t)stt->unknown_params;   // ADJ:6856
+    stt->sigma_zero = stt->dof != 0 ? stt->chi_squared / (double)stt->dof : 0.0;
+    stt->outliers = (uint32_t)sums[3];
+    stt->global_pelzer = sums[2] > 0 ? std::sqrt(sums[1] / sums[2]) : 999.99;       // ADJ:8350-8354
+    stt->critical_value = c->critical;
+    return 0;
+}
+
+int gadj_get_estimates(gadj_ctx* c, double* xyz)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    dev::d2h(xyz, c->d_est.p, c->d_est.bytes());
+    std::string e = dev::sync();
+    return e.empty() ? 0 : c->fail(e);
+}
+
+int gadj_get_corrections(gadj_ctx* c, double* dxyz)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    dev::d2h(dxyz, c->d_corr.p, 3 * (size_t)c->nstn * sizeof(double));
+    std::string e = dev::sync();
+    return e.empty() ? 0 : c->fail(e);
+}
+
+int gadj_get_station_vcvs(gadj_ctx* c, double* q)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    if (extract_vcv(c))
+        return 1;
+    dev::d2h(q, c->d_vcvd.p, c->d_vcvd.bytes());
+    std::string e = dev::sync();
+    return e.empty() ? 0 : c->fail(e);
+}
+
+int gadj_get_station_vcv(gadj_ctx* c, uint32_t stn, double q[9])
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    if (stn >= c->nstn)
+        return c->fail("station index out of range");
+    if (extract_vcv(c))
+        return 1;
+    dev::d2h(q, c->d_vcvd.p + 9 * (size_t)stn, 9 * sizeof(double));
+    std::string e = dev::sync();
+    return e.empty() ? 0 : c->fail(e);
+}
+
+static int find_edge(gadj_ctx* c, uint32_t si, uint32_t sj, uint64_t* ei, bool* transposed)
+{
+    // edges are sorted by (min station, max station); edge_hi/edge_lo carry the elimination orientation
+    uint32_t lo = std::min(si, sj), hi = std::max(si, sj);
+    uint64_t b = 0, e = c->nedge;
+    while (b < e) {
+        uint64_t mid = (b + e) / 2;
+        uint32_t mlo = std::min(c->edge_hi[mid], c->edge_lo[mid]), mhi = std::max(c->edge_hi[mid], c->edge_lo[mid]);
+        if (mlo < lo || (mlo == lo && mhi < hi))
+            b = mid + 1;
+        else
+            e = mid;
+    }
+    if (b >= c->nedge)
+        return 1;
+    uint32_t mlo = std::min(c->edge_hi[b], c->edge_lo[b]), mhi = std::max(c->edge_hi[b], c->edge_lo[b]);
+    if (mlo != lo || mhi != hi)
+        return 1;
+    *ei = b;
+    *transposed = (c->edge_hi[b] != si);  // stored block is N[hi, lo]
+    return 0;
+}
+
+static int get_block(gadj_ctx* c, const double* diag, const double* off, uint32_t si, uint32_t sj, double q[9])
+{
+    if (si >= c->nstn || sj >= c->nstn)
+        return c->fail("station index out of range");
+    double t[9];
+    bool tr = false;
+    if (si == sj)
+        dev::d2h(t, diag + 9 * (size_t)si, sizeof(t));
+    else {
+        uint64_t ei;
+        if (find_edge(c, si, sj, &ei, &tr))
+            return c->fail("no measurement joins the two stations: block is outside the stored pattern");
+        dev::d2h(t, off + 9 * ei, sizeof(t));
+    }
+    std::string e = dev::sync();
+    if (!e.empty())
+        return c->fail(e);
+    for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 3; ++k)
+            q[r * 3 + k] = tr ? t[k * 3 + r] : t[r * 3 + k];
+    return 0;
+}
+
+int gadj_get_vcv_block(gadj_ctx* c, uint32_t si, uint32_t sj, double q[9])
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    if (extract_vcv(c))
+        return 1;
+    return get_block(c, c->d_vcvd.p, c->d_vcvo.p, si, sj, q);
+}
+
+int gadj_get_normals_block(gadj_ctx* c, uint32_t si, uint32_t sj, double n[9])
+{
+    if (!c->prepared || !c->normals_valid)
+        return c->fail("normals have not been assembled");
+    return get_block(c, c->d_ndiag.p, c->d_noff.p, si, sj, n);
+}
+
+int gadj_get_rhs(gadj_ctx* c, double* w)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    dev::d2h(w, c->d_w.p, c->d_w.bytes());
+    std::string e = dev::sync();
+    return e.empty() ? 0 : c->fail(e);
+}
+
+int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int M, int N, int K, int reps, float* ms)
+{
+    if (M <= 0 || N <= 0 || K <= 0 || (K & 1))
+        return c->fail("gadj_test_gemm: M, N, K must be positive and K even");
+    DevArray<double> dA, dB, dC;
+    DevArray<GemmOp> dop;
+    if (!dA.resize((size_t)M * K) || !dB.resize((size_t)N * K) || !dC.resize((size_t)M * N) || !dop.resize(1))
+        return c->fail("out of device memory");
+    dev::h2d(dA.p, A, dA.bytes());
+    dev::h2d(dB.p, B, dB.bytes());
+    dev::zero(dC.p, dC.bytes());
+    GemmOp op{};
+    op.A = dA.p;
+    op.B = dB.p;
+    op.C = dC.p;
+    op.lda = K;
+    op.ldb = K;
+    op.ldc = N;
+    op.M = M;
+    op.N = N;
+    op.K = K;
+    op.flags = 0;
+    op.tiles_m = (M + TILE_M - 1) / TILE_M;
+    op.tiles_n = (N + TILE_N - 1) / TILE_N;
+    op.tile_begin = 0;
+    if (!dev::encode_tma_2d(&op.tmA, op.A, M, K, K, TILE_M) || !dev::encode_tma_2d(&op.tmB, op.B, N, K, K, TILE_N))
+        return c->fail("tensor-map encoding failed");
+    dev::h2d(dop.p, &op, sizeof(op));
+    launch_gemm(dop.p, 1, op.tiles_m * op.tiles_n, dev::stream());
+    std::string e = dev::sync();
+    if (!e.empty())
+        return c->fail(e);
+    if (reps < 1)
+        reps = 1;
+    dev::event_record(c->ev[0]);
+    for (int i = 0; i < reps; ++i)
+        launch_gemm(dop.p, 1, op.tiles_m * op.tiles_n, dev::stream());
+    dev::event_record(c->ev[1]);
+    dev::d2h(C, dC.p, dC.bytes());
+    e = dev::sync();
+    if (!e.empty())
+        return c->fail(e);
+    if (ms)
+        *ms = dev::event_elapsed_ms(c->ev[0], c->ev[1]) / (float)reps;
+    return 0;
+}
+
+}  // extern "C"

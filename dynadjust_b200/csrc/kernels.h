@@ -1,0 +1,183 @@
+// kernels.h — device-side work descriptors and the launch interface.
+//
+// Every numeric phase of an iteration is a list of launches; each launch
+// consumes an array of small descriptors ("ops") that lives in device memory
+// and is built once by the planner (plan.cpp) after symbolic analysis.
+// The CUDA implementations are in kernels_*.cu.  tests/hostsim/ provides
+// plain-loop stand-ins with the same signatures so that the planner, the
+// index maps and the algorithm can be exercised on a machine without a GPU;
+// that build is test infrastructure and is never linked into libgadj.so.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/dna_records.h"
+
+namespace gadj {
+
+// ---- tile geometry of the FP64 tensor-core GEMM -------------------------------
+constexpr int TILE_M = 128;
+constexpr int TILE_N = 128;
+constexpr int TILE_K = 16;   // doubles per TMA box row (= 128 bytes, SWIZZLE_128B)
+constexpr int NB = 128;      // pivot block width of the blocked factorisation
+
+struct alignas(64) TmaDesc {
+    uint64_t opaque[16];     // CUtensorMap (128 bytes)
+};
+
+enum GemmFlags : int32_t {
+    GEMM_ACCUM = 1,     // C += alpha*A*B^T   (else C = alpha*A*B^T)
+    GEMM_NEG = 2,       // alpha = -1         (else +1)
+    GEMM_LOWER = 4,     // keep only elements with (i + tri_off) >= j; tiles wholly above are skipped
+    GEMM_SCATTER = 8,   // C is the base of a target panel; element (i, j) lands at row 3*rowmap[i/3]+i%3,
+                        // column 3*rowmap[j/3]+j%3 (station-level map), added atomically
+};
+
+// C[M x N] (row-major, ldc)  (+)= alpha * A[M x K] (row-major, lda) * B[N x K]^T (row-major, ldb)
+struct alignas(64) GemmOp {
+    TmaDesc tmA, tmB;
+    const double* A;
+    const double* B;
+    double* C;
+    const int32_t* rowmap;
+    int64_t lda, ldb, ldc;
+    int32_t M, N, K;
+    int32_t flags;
+    int32_t tri_off;
+    int32_t tile_begin;      // first linear tile id of this op inside its launch
+    int32_t tiles_m, tiles_n;
+};
+
+// One pivot tile (w <= NB).  factor: D (row-major, ldd) <- chol(D) lower, in place.
+// W  (optional): inverse of the lower factor, row-major, pitch ldw, zeros above the diagonal, rows/cols >= w untouched
+// Wt (optional): its transpose, row-major, pitch ldwt, zeros below the diagonal
+struct DiagOp {
+    double* D;
+    double* W;
+    double* Wt;
+    int64_t ldd, ldw, ldwt;
+    int32_t w;
+    int32_t factor;
+    int32_t front;           // for error reporting
+    int32_t pad;
+};
+
+// x_j <- L_jj^-1 x_j (forward) or L_jj^-T x_j (backward) on one pivot tile
+struct TriOp {
+    const double* D;
+    double* x;
+    int64_t ldd;
+    int32_t w;
+    int32_t pad;
+};
+
+// forward : x[rowidx[i]] -= sum_c P[i][c] * xj[c]         for i in [0, nrows)
+// backward: xj[c]        -= sum_i P[i][c] * x[rowidx[i]]
+struct GemvOp {
+    const double* P;         // first row of the chunk, first column of the pivot tile
+    const int32_t* rowidx;   // global unknown index of each row in the chunk
+    double* xj;              // the pivot tile's slice of the solution vector
+    int64_t ld;
+    int32_t nrows;
+    int32_t w;
+};
+
+// dst[c][r] = src[r][c]
+struct TransposeOp {
+    const double* src;
+    double* dst;
+    int64_t lds, ldd;
+    int32_t rows, cols;
+};
+
+// G[(i)][(j)] = Z entry of boundary pair (i, j) read from the owning ancestor panel
+// (station-level maps, 3x3 blocks): for boundary station range [jb, je) owned by
+// ancestor panel `Z` (pitch ld, first own column col0) and every i >= jb:
+//   block(i, j) = Z[3*rowmap[i-jb] .. +3][3*rowmap[j-jb] .. +3]; mirrored into (j, i).
+struct GatherOp {
+    const double* Z;
+    const int32_t* rowmap;
+    double* G;               // r x r row-major workspace, pitch ldg
+    int64_t ld, ldg;
+    int32_t jb, je, nb;      // nb = boundary station count of the front
+    int32_t col0;
+};
+
+// ---- launches -----------------------------------------------------------------
+// All pointers are device pointers; `stream` is the backend's stream handle.
+void launch_gemm(const GemmOp* ops, int nops, int total_tiles, void* stream);
+void launch_diag(const DiagOp* ops, int nops, int* info, void* stream);
+void launch_tri(const TriOp* ops, int nops, int backward, void* stream);
+void launch_gemv(const GemvOp* ops, int nops, const double* x_ro, double* x, int backward, void* stream);
+void launch_transpose(const TransposeOp* ops, int nops, void* stream);
+void launch_gather(const GatherOp* ops, int nops, void* stream);
+
+// ---- assembly -----------------------------------------------------------------
+struct AssembleParams {
+    const dna_msr_t* msr;        // device copy of the raw .bms records
+    const uint32_t* first;       // per GNSS baseline: index of its X record
+    const uint32_t* edge;        // per baseline: edge slot | (1u<<31 when station1 is eliminated after station2)
+    const double* est;           // 3 x nstn estimated Cartesian coordinates (station order)
+    double* ndiag;               // nstn x 9 diagonal blocks (station order, row-major 3x3)
+    double* noff;                // nedge x 9 off-diagonal blocks: N[later station, earlier station]
+    double* w;                   // 3 x nstn  A^T V^-1 l (station order)
+    double* chi2;                // optional: sum l^T V^-1 l accumulated here (statistics pass)
+    uint64_t nbaselines;
+    int32_t contiguous;          // first[b] == first[0] + 3b for all b
+    int32_t normals;             // 0: rhs (and chi2) only
+};
+void launch_assemble_g(const AssembleParams& p, void* stream);
+
+// diagonal blocks <- per-station constraint block (FormConstraintStationVarianceMatrix, ADJ:2041-2137)
+void launch_init_normals(const double* cblock, double* ndiag, double* noff, double* w, uint32_t nstn, uint64_t nedge,
+                         void* stream);
+
+struct ScatterParams {
+    const double* ndiag;
+    const double* noff;
+    const uint64_t* diag_dest;   // per station (station order)
+    const uint32_t* diag_ld;
+    const uint64_t* off_dest;    // per edge
+    const uint32_t* off_ld;
+    const uint32_t* edge_hi;     // per edge: station of the row block (eliminated later)
+    const uint32_t* edge_lo;
+    double* panels;
+    double* dscale;              // 3 x nstn, station order: 1/sqrt(N_ii) (or 1 when scaling is off)
+    uint32_t nstn;
+    uint64_t nedge;
+    int32_t scale;
+};
+void launch_compute_scale(const ScatterParams& p, void* stream);
+void launch_scatter_normals(const ScatterParams& p, void* stream);
+
+// b[3*pos[s]+c] = dscale[3s+c] * w[3s+c]
+void launch_permute_rhs(const double* w, const double* dscale, const uint32_t* pos_of_stn, double* b, uint32_t nstn,
+                        void* stream);
+// corr[3s+c] = dscale * x[3*pos[s]+c]; est += corr; tracks the largest |corr| (first in station order on ties)
+void launch_apply_corrections(const double* x, const double* dscale, const uint32_t* pos_of_stn, double* corr,
+                              double* est, uint32_t nstn, void* stream);
+// vcv[s] (9 doubles, row-major) = dscale_i * Z_ss * dscale_j read from the panels (lower triangle mirrored)
+void launch_extract_station_vcv(const double* panels, const uint64_t* diag_dest, const uint32_t* diag_ld,
+                                const double* dscale, double* vcv, uint32_t nstn, void* stream);
+// q (9 doubles) per edge: dscale-scaled off-diagonal block N^-1[hi station, lo station]
+void launch_extract_edge_vcv(const double* panels, const uint64_t* off_dest, const uint32_t* off_ld,
+                             const uint32_t* edge_hi, const uint32_t* edge_lo, const double* dscale, double* q,
+                             uint64_t nedge, void* stream);
+
+struct StatsParams {
+    dna_msr_t* msr;
+    const uint32_t* first;
+    const uint32_t* edge;
+    const double* est;
+    const double* vcv_diag;      // nstn x 9
+    const double* vcv_off;       // nedge x 9 : N^-1[hi, lo]
+    double* sums;                // [0] chi2, [1] pelzer sum, [2] pelzer count, [3] outliers
+    uint64_t nbaselines;
+    double critical;
+};
+void launch_stats_g(const StatsParams& p, void* stream);
+
+// geographic <- Cartesian for every station (CartToGeo, GEO:154-225)
+void launch_cart_to_geo(const double* est, double* llh, uint32_t nstn, double a, double invf, void* stream);
+
+}  // namespace gadj

@@ -1,0 +1,544 @@
+// plan.cpp — static launch lists for factorisation, triangular solves and the
+// selected inverse on the supernode tree.
+//
+// Numerically this is the block form of what the reference does per block with
+// dense LAPACK calls: Solve()'s dpotrf (ADJ:6628, MATC:982) becomes the blocked
+// right-looking Cholesky of each front's pivot block; the junction carry
+// N_next[JSL,JSL] += J^-1 (ADJ:1076-1126) becomes the Schur update
+// -L21 L21^T scattered into the ancestors' panels; dpotri (MATC:984) becomes the
+// top-down selected inverse Z11 = W^T W + Y^T Z22 Y, Z21 = -Z22 Y with
+// W = L11^-1, Y = L21 W  (the reverse/combine passes, ADJ:3461-3590).
+#include "plan.h"
+
+#include <algorithm>
+
+#include "dev.h"
+
+namespace gadj {
+namespace {
+
+inline size_t al16(size_t n) { return (n + 15) & ~(size_t)15; }
+inline uint32_t even(uint32_t n) { return n + (n & 1u); }
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+struct SelinvWs {
+    size_t W, Wt, wt_tiles, Tt, G, Yt, Z21t, total;
+    uint32_t ldw, ldt, ldg, ldr, ntiles;
+};
+
+SelinvWs ws_layout(const Front& f)
+{
+    SelinvWs w{};
+    w.ldw = even(f.k);
+    w.ldt = even(f.k);
+    w.ldg = even(f.r);
+    w.ldr = even(f.r);
+    w.ntiles = (uint32_t)cdiv((int)f.k, NB);
+    size_t o = 0;
+    w.W = o;
+    o += al16((size_t)f.k * w.ldw);
+    w.Wt = o;
+    o += al16((size_t)f.k * w.ldw);
+    w.wt_tiles = o;
+    o += al16((size_t)w.ntiles * NB * NB);
+    w.Tt = o;
+    o += al16((size_t)NB * w.ldt);
+    if (f.r > 0) {
+        w.G = o;
+        o += al16((size_t)f.r * w.ldg);
+        w.Yt = o;
+        o += al16((size_t)f.k * w.ldr);
+        w.Z21t = o;
+        o += al16((size_t)f.k * w.ldr);
+    }
+    w.total = o;
+    return w;
+}
+
+struct Builder {
+    const Symbolic& s;
+    const PlanBuffers& b;
+    Plan& p;
+    std::string err;
+
+    Builder(const Symbolic& S, const PlanBuffers& B, Plan& P) : s(S), b(B), p(P) {}
+
+    double* panel(const Front& f) const { return b.panels + f.panel_off; }
+
+    void add_gemm(std::vector<GemmOp>& batch, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                  int64_t ldc, int M, int N, int K, int flags, int tri_off = 0, const int32_t* rowmap = nullptr)
+    {
+        if (M <= 0 || N <= 0 || K <= 0)
+            return;
+        GemmOp op{};
+        op.A = A;
+        op.B = B;
+        op.C = C;
+        op.rowmap = rowmap;
+        op.lda = lda;
+        op.ldb = ldb;
+        op.ldc = ldc;
+        op.M = M;
+        op.N = N;
+        op.K = K;
+        op.flags = flags;
+        op.tri_off = tri_off;
+        op.tiles_m = cdiv(M, TILE_M);
+        op.tiles_n = cdiv(N, TILE_N);
+        batch.push_back(op);
+    }
+
+    // appends a batch as one launch; assigns tile ranges and encodes the tensor maps
+    void flush_gemm(std::vector<GemmOp>& batch, std::vector<Launch>& out, int level)
+    {
+        if (batch.empty())
+            return;
+        Launch L{};
+        L.kind = L_GEMM;
+        L.op_begin = (int64_t)p.gemm.size();
+        L.op_count = (int32_t)batch.size();
+        L.level = level;
+        int tiles = 0;
+        for (GemmOp& op : batch) {
+            op.tile_begin = tiles;
+            tiles += op.tiles_m * op.tiles_n;
+            double fl = 2.0 * op.M * (double)op.N * op.K;
+            if (op.flags & GEMM_LOWER)
+                fl *= 0.5;
+            L.flops += fl;
+            if (!dev::encode_tma_2d(&op.tmA, op.A, (uint64_t)op.M, (uint64_t)op.K, (uint64_t)op.lda, TILE_M) ||
+                !dev::encode_tma_2d(&op.tmB, op.B, (uint64_t)op.N, (uint64_t)op.K, (uint64_t)op.ldb, TILE_N))
+                err = "tensor-map encoding failed";
+            p.gemm.push_back(op);
+        }
+        L.total_tiles = tiles;
+        out.push_back(L);
+        batch.clear();
+    }
+
+    void flush_diag(std::vector<DiagOp>& batch, std::vector<Launch>& out, int level)
+    {
+        if (batch.empty())
+            return;
+        Launch L{};
+        L.kind = L_DIAG;
+        L.op_begin = (int64_t)p.diag.size();
+        L.op_count = (int32_t)batch.size();
+        L.level = level;
+        for (auto& op : batch) {
+            L.flops += (double)op.w * op.w * op.w * (op.factor ? 2.0 / 3.0 : 1.0 / 3.0);
+            p.diag.push_back(op);
+        }
+        out.push_back(L);
+        batch.clear();
+    }
+
+    template <class Op>
+    void flush_simple(std::vector<Op>& batch, std::vector<Op>& store, int kind, std::vector<Launch>& out, int level)
+    {
+        if (batch.empty())
+            return;
+        Launch L{};
+        L.kind = kind;
+        L.op_begin = (int64_t)store.size();
+        L.op_count = (int32_t)batch.size();
+        L.level = level;
+        store.insert(store.end(), batch.begin(), batch.end());
+        out.push_back(L);
+        batch.clear();
+    }
+
+    // ---- numeric factorisation ------------------------------------------------
+    void build_factor()
+    {
+        std::vector<GemmOp> gb;
+        std::vector<DiagOp> db;
+        for (size_t lv = 0; lv < s.levels.size(); ++lv) {
+            const auto& fl = s.levels[lv];
+            int nsteps = 0;
+            for (uint32_t f : fl)
+                nsteps = std::max(nsteps, cdiv((int)s.fronts[f].k, NB));
+            for (int j = 0; j < nsteps; ++j) {
+                const int jb = j * NB;
+                // pivot tiles
+                for (size_t i = 0; i < fl.size(); ++i) {
+                    const Front& f = s.fronts[fl[i]];
+                    if (jb >= (int)f.k)
+                        continue;
+                    DiagOp d{};
+                    d.D = panel(f) + (size_t)jb * f.ldk + jb;
+                    d.ldd = f.ldk;
+                    d.w = std::min<int>(NB, (int)f.k - jb);
+                    d.factor = 1;
+                    d.W = b.pool + i * (size_t)NB * NB;
+                    d.ldw = NB;
+                    d.front = (int32_t)fl[i];
+                    db.push_back(d);
+                }
+                flush_diag(db, p.factor, (int)lv);
+                // rows below the pivot tile: P <- P * W^T
+                for (size_t i = 0; i < fl.size(); ++i) {
+                    const Front& f = s.fronts[fl[i]];
+                    if (jb >= (int)f.k)
+                        continue;
+                    int w = std::min<int>(NB, (int)f.k - jb);
+                    double* A = panel(f) + (size_t)(jb + w) * f.ldk + jb;
+                    add_gemm(gb, A, f.ldk, b.pool + i * (size_t)NB * NB, NB, A, f.ldk, (int)f.m - (jb + w), w, w, 0);
+                }
+                flush_gemm(gb, p.factor, (int)lv);
+                // trailing update inside the panel (columns still to be factorised)
+                for (size_t i = 0; i < fl.size(); ++i) {
+                    const Front& f = s.fronts[fl[i]];
+                    if (jb >= (int)f.k)
+                        continue;
+                    int w = std::min<int>(NB, (int)f.k - jb);
+                    int nc = (int)f.k - (jb + w);
+                    double* A = panel(f) + (size_t)(jb + w) * f.ldk + jb;
+                    double* C = panel(f) + (size_t)(jb + w) * f.ldk + (jb + w);
+                    add_gemm(gb, A, f.ldk, A, f.ldk, C, f.ldk, (int)f.m - (jb + w), nc, w,
+                             GEMM_ACCUM | GEMM_NEG | GEMM_LOWER);
+                }
+                flush_gemm(gb, p.factor, (int)lv);
+            }
+            // Schur updates scattered into the ancestors' panels
+            for (uint32_t fi : fl) {
+                const Front& f = s.fronts[fi];
+                for (uint32_t t = 0; t < f.tgt_count; ++t) {
+                    const Target& tg = s.targets[f.tgt_begin + t];
+                    const Front& an = s.fronts[tg.anc];
+                    double* A = panel(f) + (size_t)(f.k + 3 * tg.jb) * f.ldk;
+                    double* C = panel(an);
+                    add_gemm(gb, A, f.ldk, A, f.ldk, C, an.ldk, (int)(f.r - 3 * tg.jb), (int)(3 * (tg.je - tg.jb)),
+                             (int)f.k, GEMM_SCATTER | GEMM_NEG | GEMM_LOWER, 0, b.rowmap + tg.rowmap_off);
+                }
+            }
+            flush_gemm(gb, p.factor, (int)lv);
+        }
+        for (auto& L : p.factor)
+            p.factor_flops += L.flops;
+    }
+
+    // ---- triangular solves ----------------------------------------------------
+    void build_solves()
+    {
+        const int CHUNK = 256;
+        std::vector<TriOp> tb;
+        std::vector<GemvOp> vb;
+        for (size_t lv = 0; lv < s.levels.size(); ++lv) {
+            const auto& fl = s.levels[lv];
+            int nsteps = 0;
+            for (uint32_t f : fl)
+                nsteps = std::max(nsteps, cdiv((int)s.fronts[f].k, NB));
+            for (int j = 0; j < nsteps; ++j) {
+                const int jb = j * NB;
+                for (uint32_t fi : fl) {
+                    const Front& f = s.fronts[fi];
+                    if (jb >= (int)f.k)
+                        continue;
+                    int w = std::min<int>(NB, (int)f.k - jb);
+                    TriOp t{};
+                    t.D = panel(f) + (size_t)jb * f.ldk + jb;
+                    t.ldd = f.ldk;
+                    t.w = w;
+                    t.x = b.x + 3 * (size_t)f.own_begin + jb;
+                    tb.push_back(t);
+                    for (int r0 = jb + w; r0 < (int)f.m; r0 += CHUNK) {
+                        GemvOp g{};
+                        g.P = panel(f) + (size_t)r0 * f.ldk + jb;
+                        g.rowidx = b.rowidx + p.rowidx_off[fi] + r0;
+                        g.xj = t.x;
+                        g.ld = f.ldk;
+                        g.nrows = std::min<int>(CHUNK, (int)f.m - r0);
+                        g.w = w;
+                        vb.push_back(g);
+                    }
+                }
+                flush_simple(tb, p.tri, L_TRI_FWD, p.fwd, (int)lv);
+                flush_simple(vb, p.gemv, L_GEMV_FWD, p.fwd, (int)lv);
+            }
+        }
+        for (size_t lvi = s.levels.size(); lvi-- > 0;) {
+            const auto& fl = s.levels[lvi];
+            int nsteps = 0;
+            for (uint32_t f : fl)
+                nsteps = std::max(nsteps, cdiv((int)s.fronts[f].k, NB));
+            for (int st = 0; st < nsteps; ++st) {
+                for (uint32_t fi : fl) {
+                    const Front& f = s.fronts[fi];
+                    int nt = cdiv((int)f.k, NB);
+                    int j = nt - 1 - st;
+                    if (j < 0)
+                        continue;
+                    int jb = j * NB;
+                    int w = std::min<int>(NB, (int)f.k - jb);
+                    TriOp t{};
+                    t.D = panel(f) + (size_t)jb * f.ldk + jb;
+                    t.ldd = f.ldk;
+                    t.w = w;
+                    t.x = b.x + 3 * (size_t)f.own_begin + jb;
+                    tb.push_back(t);
+                    for (int r0 = jb + w; r0 < (int)f.m; r0 += CHUNK) {
+                        GemvOp g{};
+                        g.P = panel(f) + (size_t)r0 * f.ldk + jb;
+                        g.rowidx = b.rowidx + p.rowidx_off[fi] + r0;
+                        g.xj = t.x;
+                        g.ld = f.ldk;
+                        g.nrows = std::min<int>(CHUNK, (int)f.m - r0);
+                        g.w = w;
+                        vb.push_back(g);
+                    }
+                }
+                flush_simple(vb, p.gemv, L_GEMV_BWD, p.bwd, (int)lvi);
+                flush_simple(tb, p.tri, L_TRI_BWD, p.bwd, (int)lvi);
+            }
+        }
+    }
+
+    // ---- selected inverse -------------------------------------------------------
+    void build_selinv_chunk(const std::vector<uint32_t>& chunk, const std::vector<size_t>& base, size_t used, int level)
+    {
+        std::vector<GemmOp> gb;
+        std::vector<DiagOp> db;
+        std::vector<TransposeOp> trb;
+        std::vector<GatherOp> gab;
+        {
+            Launch Z{};
+            Z.kind = L_ZERO;
+            Z.zero_ptr = b.pool;
+            Z.zero_bytes = used * sizeof(double);
+            Z.level = level;
+            p.selinv.push_back(Z);
+        }
+        int maxtiles = 0;
+        for (size_t i = 0; i < chunk.size(); ++i) {
+            const Front& f = s.fronts[chunk[i]];
+            SelinvWs w = ws_layout(f);
+            double* ws = b.pool + base[i];
+            maxtiles = std::max<int>(maxtiles, (int)w.ntiles);
+            for (uint32_t j = 0; j < w.ntiles; ++j) {
+                int jb = (int)j * NB;
+                DiagOp d{};
+                d.D = panel(f) + (size_t)jb * f.ldk + jb;
+                d.ldd = f.ldk;
+                d.w = std::min<int>(NB, (int)f.k - jb);
+                d.factor = 0;
+                d.W = ws + w.W + (size_t)jb * w.ldw + jb;
+                d.ldw = w.ldw;
+                d.Wt = ws + w.wt_tiles + (size_t)j * NB * NB;
+                d.ldwt = NB;
+                d.front = (int32_t)chunk[i];
+                db.push_back(d);
+            }
+        }
+        flush_diag(db, p.selinv, level);
+        // blocked inverse of the lower factor, block columns right to left
+        for (int st = 0; st + 1 < maxtiles; ++st) {
+            std::vector<GemmOp> ga, gbb;
+            for (size_t i = 0; i < chunk.size(); ++i) {
+                const Front& f = s.fronts[chunk[i]];
+                SelinvWs w = ws_layout(f);
+                double* ws = b.pool + base[i];
+                int j = (int)w.ntiles - 2 - st;
+                if (j < 0)
+                    continue;
+                int jb = j * NB, wj = NB;  // only the last tile can be narrower
+                int below = (int)f.k - (jb + wj);
+                // Tt = Wt_jj * L[below, jb:jb+wj]^T
+                add_gemm(ga, ws + w.wt_tiles + (size_t)j * NB * NB, NB, panel(f) + (size_t)(jb + wj) * f.ldk + jb, f.ldk,
+                         ws + w.Tt, w.ldt, wj, below, wj, 0);
+                // W[below, jb:jb+wj] = -W[below, below] * Tt^T
+                add_gemm(gbb, ws + w.W + (size_t)(jb + wj) * w.ldw + (jb + wj), w.ldw, ws + w.Tt, w.ldt,
+                         ws + w.W + (size_t)(jb + wj) * w.ldw + jb, w.ldw, below, wj, below, GEMM_NEG);
+            }
+            flush_gemm(ga, p.selinv, level);
+            flush_gemm(gbb, p.selinv, level);
+        }
+        for (size_t i = 0; i < chunk.size(); ++i) {
+            const Front& f = s.fronts[chunk[i]];
+            SelinvWs w = ws_layout(f);
+            double* ws = b.pool + base[i];
+            TransposeOp t{};
+            t.src = ws + w.W;
+            t.dst = ws + w.Wt;
+            t.lds = w.ldw;
+            t.ldd = w.ldw;
+            t.rows = (int32_t)f.k;
+            t.cols = (int32_t)f.k;
+            trb.push_back(t);
+            for (uint32_t ti = 0; ti < f.tgt_count; ++ti) {
+                const Target& tg = s.targets[f.tgt_begin + ti];
+                const Front& an = s.fronts[tg.anc];
+                GatherOp g{};
+                g.Z = panel(an);
+                g.ld = an.ldk;
+                g.rowmap = b.rowmap + tg.rowmap_off;
+                g.G = ws + w.G;
+                g.ldg = w.ldg;
+                g.jb = (int32_t)tg.jb;
+                g.je = (int32_t)tg.je;
+                g.nb = (int32_t)f.bnd_count;
+                g.col0 = (int32_t)tg.col0;
+                gab.push_back(g);
+            }
+        }
+        flush_simple(trb, p.transpose, L_TRANSPOSE, p.selinv, level);
+        flush_simple(gab, p.gather, L_GATHER, p.selinv, level);
+        // Yt = Wt * L21^T
+        for (size_t i = 0; i < chunk.size(); ++i) {
+            const Front& f = s.fronts[chunk[i]];
+            if (!f.r)
+                continue;
+            SelinvWs w = ws_layout(f);
+            double* ws = b.pool + base[i];
+            add_gemm(gb, ws + w.Wt, w.ldw, panel(f) + (size_t)f.k * f.ldk, f.ldk, ws + w.Yt, w.ldr, (int)f.k, (int)f.r,
+                     (int)f.k, 0);
+        }
+        flush_gemm(gb, p.selinv, level);
+        // Z21 = -G * Y   (overwrites L21)
+        for (size_t i = 0; i < chunk.size(); ++i) {
+            const Front& f = s.fronts[chunk[i]];
+            if (!f.r)
+                continue;
+            SelinvWs w = ws_layout(f);
+            double* ws = b.pool + base[i];
+            add_gemm(gb, ws + w.G, w.ldg, ws + w.Yt, w.ldr, panel(f) + (size_t)f.k * f.ldk, f.ldk, (int)f.r, (int)f.k,
+                     (int)f.r, GEMM_NEG);
+        }
+        flush_gemm(gb, p.selinv, level);
+        for (size_t i = 0; i < chunk.size(); ++i) {
+            const Front& f = s.fronts[chunk[i]];
+            if (!f.r)
+                continue;
+            SelinvWs w = ws_layout(f);
+            double* ws = b.pool + base[i];
+            TransposeOp t{};
+            t.src = panel(f) + (size_t)f.k * f.ldk;
+            t.dst = ws + w.Z21t;
+            t.lds = f.ldk;
+            t.ldd = w.ldr;
+            t.rows = (int32_t)f.r;
+            t.cols = (int32_t)f.k;
+            trb.push_back(t);
+        }
+        flush_simple(trb, p.transpose, L_TRANSPOSE, p.selinv, level);
+        // Z11 = Wt Wt^T   (overwrites L11, lower triangle)
+        for (size_t i = 0; i < chunk.size(); ++i) {
+            const Front& f = s.fronts[chunk[i]];
+            SelinvWs w = ws_layout(f);
+            double* ws = b.pool + base[i];
+            add_gemm(gb, ws + w.Wt, w.ldw, ws + w.Wt, w.ldw, panel(f), f.ldk, (int)f.k, (int)f.k, (int)f.k, GEMM_LOWER);
+        }
+        flush_gemm(gb, p.selinv, level);
+        // Z11 -= Yt * Z21t^T
+        for (size_t i = 0; i < chunk.size(); ++i) {
+            const Front& f = s.fronts[chunk[i]];
+            if (!f.r)
+                continue;
+            SelinvWs w = ws_layout(f);
+            double* ws = b.pool + base[i];
+            add_gemm(gb, ws + w.Yt, w.ldr, ws + w.Z21t, w.ldr, panel(f), f.ldk, (int)f.k, (int)f.k, (int)f.r,
+                     GEMM_ACCUM | GEMM_NEG | GEMM_LOWER);
+        }
+        flush_gemm(gb, p.selinv, level);
+    }
+
+    void build_selinv()
+    {
+        for (size_t lvi = s.levels.size(); lvi-- > 0;) {
+            const auto& fl = s.levels[lvi];
+            std::vector<uint32_t> chunk;
+            std::vector<size_t> base;
+            size_t used = 0;
+            for (uint32_t fi : fl) {
+                size_t need = ws_layout(s.fronts[fi]).total;
+                if (need > b.pool_doubles) {
+                    err = "workspace pool smaller than the largest front";
+                    return;
+                }
+                if (used + need > b.pool_doubles) {
+                    build_selinv_chunk(chunk, base, used, (int)lvi);
+                    chunk.clear();
+                    base.clear();
+                    used = 0;
+                }
+                chunk.push_back(fi);
+                base.push_back(used);
+                used += need;
+            }
+            if (!chunk.empty())
+                build_selinv_chunk(chunk, base, used, (int)lvi);
+        }
+        for (auto& L : p.selinv)
+            p.selinv_flops += L.flops;
+    }
+};
+
+}  // namespace
+
+size_t selinv_workspace(const Front& f) { return ws_layout(f).total; }
+
+size_t min_pool_doubles(const Symbolic& s)
+{
+    size_t need = 0, width = 0;
+    for (const Front& f : s.fronts)
+        need = std::max(need, ws_layout(f).total);
+    for (auto& lv : s.levels)
+        width = std::max(width, lv.size());
+    return std::max(need, width * (size_t)NB * NB);
+}
+
+size_t ideal_pool_doubles(const Symbolic& s)
+{
+    size_t best = min_pool_doubles(s);
+    for (auto& lv : s.levels) {
+        size_t t = 0;
+        for (uint32_t f : lv)
+            t += ws_layout(s.fronts[f]).total;
+        best = std::max(best, t);
+    }
+    return best;
+}
+
+void build_rowidx(const Symbolic& s, Plan& p)
+{
+    p.rowidx_off.assign(s.fronts.size(), 0);
+    size_t tot = 0;
+    for (size_t f = 0; f < s.fronts.size(); ++f) {
+        p.rowidx_off[f] = tot;
+        tot += s.fronts[f].m;
+    }
+    p.rowidx.resize(tot);
+    for (size_t fi = 0; fi < s.fronts.size(); ++fi) {
+        const Front& f = s.fronts[fi];
+        int32_t* r = p.rowidx.data() + p.rowidx_off[fi];
+        for (uint32_t i = 0; i < f.k; ++i)
+            r[i] = (int32_t)(3 * f.own_begin + i);
+        for (uint32_t i = 0; i < f.bnd_count; ++i)
+            for (int c = 0; c < 3; ++c)
+                r[f.k + 3 * i + c] = (int32_t)(3 * s.bnd[f.bnd_begin + i] + c);
+    }
+}
+
+std::string build_plan(const Symbolic& s, const PlanBuffers& b, Plan& p)
+{
+    p.gemm.clear();
+    p.diag.clear();
+    p.tri.clear();
+    p.gemv.clear();
+    p.transpose.clear();
+    p.gather.clear();
+    p.factor.clear();
+    p.fwd.clear();
+    p.bwd.clear();
+    p.selinv.clear();
+    p.factor_flops = p.selinv_flops = 0;
+    if (b.pool_doubles < min_pool_doubles(s))
+        return "workspace pool smaller than the largest front";
+    Builder B(s, b, p);
+    B.build_factor();
+    B.build_solves();
+    B.build_selinv();
+    return B.err;
+}
+
+}  // namespace gadj

@@ -1,0 +1,74 @@
+// plan.h — turns the symbolic structure into static launch lists (host).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "symbolic.h"
+
+namespace gadj {
+
+enum LaunchKind : int32_t {
+    L_GEMM = 0,
+    L_DIAG,
+    L_TRI_FWD,
+    L_TRI_BWD,
+    L_GEMV_FWD,
+    L_GEMV_BWD,
+    L_TRANSPOSE,
+    L_GATHER,
+    L_ZERO,
+};
+
+struct Launch {
+    int32_t kind;
+    int32_t op_count;
+    int64_t op_begin;     // index into the per-kind op array
+    int32_t total_tiles;  // L_GEMM
+    int32_t level;
+    double* zero_ptr;     // L_ZERO
+    size_t zero_bytes;
+    double flops;         // algorithmic flops of this launch (GEMM: 2MNK, halved for LOWER)
+};
+
+struct PlanBuffers {
+    double* panels = nullptr;     // device, Symbolic::panel_doubles
+    double* pool = nullptr;       // device workspace pool
+    size_t pool_doubles = 0;
+    double* x = nullptr;          // device, 3*nstn, elimination order
+    const int32_t* rowmap = nullptr;  // device copy of Symbolic::rowmap
+    const int32_t* rowidx = nullptr;  // device: global unknown index per front row (concatenated, Plan::rowidx_off)
+};
+
+struct Plan {
+    std::vector<GemmOp> gemm;
+    std::vector<DiagOp> diag;
+    std::vector<TriOp> tri;
+    std::vector<GemvOp> gemv;
+    std::vector<TransposeOp> transpose;
+    std::vector<GatherOp> gather;
+    std::vector<Launch> factor, fwd, bwd, selinv;
+    std::vector<int32_t> rowidx;            // host copy (uploaded by the caller before build_plan's pointers are used)
+    std::vector<uint64_t> rowidx_off;       // per front
+    double factor_flops = 0, selinv_flops = 0;
+    // device copies of the op arrays (owned by the context)
+    GemmOp* d_gemm = nullptr;
+    DiagOp* d_diag = nullptr;
+    TriOp* d_tri = nullptr;
+    GemvOp* d_gemv = nullptr;
+    TransposeOp* d_transpose = nullptr;
+    GatherOp* d_gather = nullptr;
+};
+
+// per-front selected-inverse workspace need (doubles)
+size_t selinv_workspace(const Front& f);
+// smallest usable pool (doubles): the largest single front + the factorisation's pivot-inverse tiles
+size_t min_pool_doubles(const Symbolic& s);
+// pool size that lets every level run as a single chunk
+size_t ideal_pool_doubles(const Symbolic& s);
+
+void build_rowidx(const Symbolic& s, Plan& p);
+// builds all four launch lists; encodes TMA descriptors through dev::encode_tma_2d
+std::string build_plan(const Symbolic& s, const PlanBuffers& b, Plan& p);
+
+}  // namespace gadj

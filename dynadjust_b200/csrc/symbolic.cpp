@@ -1,0 +1,377 @@
+// symbolic.cpp — ordering, supernode tree, front layout and scatter maps (host).
+#include "symbolic.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace gadj {
+namespace {
+
+struct Graph {
+    std::vector<uint64_t> ptr;
+    std::vector<uint32_t> adj;
+};
+
+Graph build_graph(uint32_t n, const std::vector<std::pair<uint32_t, uint32_t>>& edges)
+{
+    Graph g;
+    g.ptr.assign((size_t)n + 1, 0);
+    for (auto& e : edges) {
+        if (e.first == e.second)
+            continue;
+        g.ptr[e.first + 1]++;
+        g.ptr[e.second + 1]++;
+    }
+    for (uint32_t i = 0; i < n; ++i)
+        g.ptr[i + 1] += g.ptr[i];
+    std::vector<uint32_t> tmp(g.ptr[n]);
+    std::vector<uint64_t> fill(g.ptr.begin(), g.ptr.end() - 1);
+    for (auto& e : edges) {
+        if (e.first == e.second)
+            continue;
+        tmp[fill[e.first]++] = e.second;
+        tmp[fill[e.second]++] = e.first;
+    }
+    // sort + unique per vertex, then compact
+    std::vector<uint64_t> nptr((size_t)n + 1, 0);
+    g.adj.reserve(tmp.size());
+    for (uint32_t i = 0; i < n; ++i) {
+        auto b = tmp.begin() + g.ptr[i], e = tmp.begin() + g.ptr[i + 1];
+        std::sort(b, e);
+        e = std::unique(b, e);
+        g.adj.insert(g.adj.end(), b, e);
+        nptr[i + 1] = g.adj.size();
+    }
+    g.ptr.swap(nptr);
+    return g;
+}
+
+// ---- geometric nested dissection ------------------------------------------
+struct Dissector {
+    const Graph& g;
+    const double* lat;
+    const double* lon;
+    const OrderingOptions& opt;
+    std::vector<uint32_t> label;
+    uint32_t next_tag = 1;
+    std::vector<std::vector<uint32_t>> supernodes;  // in elimination order
+
+    Dissector(const Graph& G, const double* la, const double* lo, const OrderingOptions& o)
+        : g(G), lat(la), lon(lo), opt(o), label(G.ptr.size() - 1, 0)
+    {
+    }
+
+    void emit(std::vector<uint32_t>& v)
+    {
+        if (v.empty())
+            return;
+        std::sort(v.begin(), v.end());
+        supernodes.emplace_back(std::move(v));
+    }
+
+    void run(std::vector<uint32_t>& verts)
+    {
+        if (verts.size() <= opt.leaf_stations) {
+            emit(verts);
+            return;
+        }
+        // pick the wider axis (metres, roughly): x = lon * cos(mean lat), y = lat
+        double la0 = 1e300, la1 = -1e300, lo0 = 1e300, lo1 = -1e300, lam = 0;
+        for (uint32_t v : verts) {
+            la0 = std::min(la0, lat[v]);
+            la1 = std::max(la1, lat[v]);
+            lo0 = std::min(lo0, lon[v]);
+            lo1 = std::max(lo1, lon[v]);
+            lam += lat[v];
+        }
+        lam /= (double)verts.size();
+        bool split_lon = (lo1 - lo0) * std::cos(lam) > (la1 - la0);
+        const double* key = split_lon ? lon : lat;
+        size_t half = verts.size() / 2;
+        std::nth_element(verts.begin(), verts.begin() + half, verts.end(), [&](uint32_t a, uint32_t b) {
+            return key[a] < key[b] || (key[a] == key[b] && a < b);
+        });
+        uint32_t tagL = next_tag++, tagR = next_tag++, tagS = next_tag++;
+        for (size_t i = 0; i < verts.size(); ++i)
+            label[verts[i]] = i < half ? tagL : tagR;
+        // vertices with many cut edges (hubs) go straight into the separator
+        std::vector<uint32_t> S;
+        for (uint32_t v : verts) {
+            uint32_t other = label[v] == tagL ? tagR : tagL;
+            uint32_t cd = 0;
+            for (uint64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e)
+                cd += label[g.adj[e]] == other;
+            if (cd >= opt.cut_degree_to_sep)
+                S.push_back(v);
+        }
+        for (uint32_t v : S)
+            label[v] = tagS;
+        // one-sided boundary of the smaller side closes the remaining cut edges
+        std::vector<uint32_t> BL, BR;
+        for (uint32_t v : verts) {
+            if (label[v] == tagS)
+                continue;
+            uint32_t other = label[v] == tagL ? tagR : tagL;
+            for (uint64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e)
+                if (label[g.adj[e]] == other) {
+                    (label[v] == tagL ? BL : BR).push_back(v);
+                    break;
+                }
+        }
+        std::vector<uint32_t>& B = BL.size() <= BR.size() ? BL : BR;
+        for (uint32_t v : B) {
+            label[v] = tagS;
+            S.push_back(v);
+        }
+        std::vector<uint32_t> L, R;
+        L.reserve(half);
+        R.reserve(verts.size() - half);
+        for (uint32_t v : verts) {
+            if (label[v] == tagL)
+                L.push_back(v);
+            else if (label[v] == tagR)
+                R.push_back(v);
+        }
+        if (L.empty() || R.empty() || S.size() * 2 > verts.size()) {
+            // degenerate split (clique-like subgraph): keep it as one dense front
+            emit(verts);
+            return;
+        }
+        std::vector<uint32_t>().swap(verts);
+        run(L);
+        run(R);
+        emit(S);
+    }
+};
+
+}  // namespace
+
+uint64_t find_slot(const Symbolic& s, uint32_t q, uint32_t p)
+{
+    uint64_t b = s.ncol_ptr[p], e = s.ncol_ptr[p + 1];
+    if (q == p)
+        return b;
+    auto it = std::lower_bound(s.nrow.begin() + b + 1, s.nrow.begin() + e, q);
+    if (it == s.nrow.begin() + e || *it != q)
+        return UINT64_MAX;
+    return (uint64_t)(it - s.nrow.begin());
+}
+
+std::string analyse(uint32_t nstn, const std::vector<std::pair<uint32_t, uint32_t>>& edges, const double* lat,
+                    const double* lon, const OrderingOptions& opt, uint32_t nblocks, const uint32_t* isl_off,
+                    const uint32_t* isl, Symbolic& out)
+{
+    out = Symbolic();
+    out.nstn = nstn;
+    if (nstn == 0)
+        return "no stations";
+    for (auto& e : edges)
+        if (e.first >= nstn || e.second >= nstn)
+            return "measurement refers to a station index beyond the station list";
+    Graph g = build_graph(nstn, edges);
+
+    // ---- 1. partition into supernodes, in elimination order -----------------
+    std::vector<std::vector<uint32_t>> sn;
+    if (opt.dense) {
+        sn.emplace_back(nstn);
+        std::iota(sn[0].begin(), sn[0].end(), 0u);
+    } else if (nblocks > 1) {
+        std::vector<uint8_t> seen(nstn, 0);
+        for (uint32_t b = 0; b < nblocks; ++b) {
+            std::vector<uint32_t> v(isl + isl_off[b], isl + isl_off[b + 1]);
+            for (uint32_t s : v) {
+                if (s >= nstn)
+                    return "block list refers to a station index beyond the station list";
+                if (seen[s])
+                    return "station appears as an inner station of two blocks";
+                seen[s] = 1;
+            }
+            if (!v.empty())
+                sn.emplace_back(std::move(v));
+        }
+        for (uint32_t s = 0; s < nstn; ++s)
+            if (!seen[s])
+                return "station is not an inner station of any block";
+    } else {
+        Dissector d(g, lat, lon, opt);
+        std::vector<uint32_t> all(nstn);
+        std::iota(all.begin(), all.end(), 0u);
+        d.run(all);
+        sn.swap(d.supernodes);
+    }
+
+    const uint32_t F = (uint32_t)sn.size();
+    out.pos_of_stn.assign(nstn, 0);
+    out.stn_of_pos.assign(nstn, 0);
+    out.front_of_pos.assign(nstn, 0);
+    out.fronts.assign(F, Front());
+    {
+        uint32_t p = 0;
+        for (uint32_t f = 0; f < F; ++f) {
+            out.fronts[f].own_begin = p;
+            out.fronts[f].own_count = (uint32_t)sn[f].size();
+            for (uint32_t s : sn[f]) {
+                out.pos_of_stn[s] = p;
+                out.stn_of_pos[p] = s;
+                out.front_of_pos[p] = f;
+                ++p;
+            }
+        }
+        if (p != nstn)
+            return "internal: ordering does not cover every station";
+    }
+    std::vector<std::vector<uint32_t>>().swap(sn);
+
+    // ---- 2. supernodal symbolic factorisation --------------------------------
+    std::vector<uint32_t> mark(nstn, UINT32_MAX);
+    std::vector<std::vector<uint32_t>> children(F);
+    std::vector<uint32_t> st;
+    for (uint32_t f = 0; f < F; ++f) {
+        Front& fr = out.fronts[f];
+        const uint32_t own_end = fr.own_begin + fr.own_count;
+        st.clear();
+        for (uint32_t p = fr.own_begin; p < own_end; ++p) {
+            uint32_t v = out.stn_of_pos[p];
+            for (uint64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e) {
+                uint32_t q = out.pos_of_stn[g.adj[e]];
+                if (q >= own_end && mark[q] != f) {
+                    mark[q] = f;
+                    st.push_back(q);
+                }
+            }
+        }
+        for (uint32_t c : children[f]) {
+            const Front& ch = out.fronts[c];
+            for (uint32_t i = 0; i < ch.bnd_count; ++i) {
+                uint32_t q = out.bnd[ch.bnd_begin + i];
+                if (q >= own_end && mark[q] != f) {
+                    mark[q] = f;
+                    st.push_back(q);
+                }
+            }
+        }
+        std::sort(st.begin(), st.end());
+        fr.bnd_begin = (uint32_t)out.bnd.size();
+        fr.bnd_count = (uint32_t)st.size();
+        out.bnd.insert(out.bnd.end(), st.begin(), st.end());
+        if (!st.empty()) {
+            fr.parent = (int32_t)out.front_of_pos[st[0]];
+            children[fr.parent].push_back(f);
+        }
+    }
+
+    // ---- 3. levels, dimensions, storage --------------------------------------
+    int32_t maxlevel = 0;
+    for (uint32_t f = 0; f < F; ++f) {
+        Front& fr = out.fronts[f];
+        int32_t lv = 0;
+        for (uint32_t c : children[f])
+            lv = std::max(lv, out.fronts[c].level + 1);
+        fr.level = lv;
+        maxlevel = std::max(maxlevel, lv);
+        fr.k = 3 * fr.own_count;
+        fr.r = 3 * fr.bnd_count;
+        fr.m = fr.k + fr.r;
+        fr.ldk = fr.k + (fr.k & 1u);
+    }
+    out.levels.assign((size_t)maxlevel + 1, {});
+    uint64_t off = 0;
+    for (uint32_t f = 0; f < F; ++f) {
+        Front& fr = out.fronts[f];
+        out.levels[fr.level].push_back(f);
+        fr.panel_off = off;
+        uint64_t sz = (uint64_t)fr.m * fr.ldk;
+        off += (sz + 15) & ~(uint64_t)15;
+        double k = fr.k, r = fr.r;
+        out.factor_flops += k * k * k / 3.0 + k * k * r + k * r * r;
+        out.inverse_flops += 2.0 * k * k * k / 3.0 + 2.0 * k * k * r + 2.0 * k * r * r + 2.0 * k * k * r;
+        out.nnz_l_blocks += (uint64_t)fr.own_count * (fr.own_count + 1) / 2 + (uint64_t)fr.own_count * fr.bnd_count;
+    }
+    out.panel_doubles = off;
+
+    // ---- 4. update targets and row maps --------------------------------------
+    for (uint32_t f = 0; f < F; ++f) {
+        Front& fr = out.fronts[f];
+        fr.tgt_begin = (uint32_t)out.targets.size();
+        const uint32_t* b = out.bnd.data() + fr.bnd_begin;
+        uint32_t j = 0;
+        while (j < fr.bnd_count) {
+            uint32_t a = out.front_of_pos[b[j]];
+            const Front& an = out.fronts[a];
+            uint32_t a_end = an.own_begin + an.own_count;
+            uint32_t je = j;
+            while (je < fr.bnd_count && b[je] < a_end)
+                ++je;
+            Target t;
+            t.anc = a;
+            t.jb = j;
+            t.je = je;
+            t.col0 = b[j] - an.own_begin;
+            t.rowmap_off = out.rowmap.size();
+            const uint32_t* ab = out.bnd.data() + an.bnd_begin;
+            uint32_t w = 0;
+            for (uint32_t i = j; i < fr.bnd_count; ++i) {
+                uint32_t p = b[i];
+                if (p < a_end) {
+                    out.rowmap.push_back((int32_t)(p - an.own_begin));
+                } else {
+                    while (w < an.bnd_count && ab[w] < p)
+                        ++w;
+                    if (w >= an.bnd_count || ab[w] != p)
+                        return "internal: boundary station missing from an ancestor front";
+                    out.rowmap.push_back((int32_t)(an.own_count + w));
+                }
+            }
+            out.targets.push_back(t);
+            j = je;
+        }
+        fr.tgt_count = (uint32_t)out.targets.size() - fr.tgt_begin;
+    }
+
+    // ---- 5. block pattern of N in elimination order + panel destinations -----
+    out.ncol_ptr.assign((size_t)nstn + 1, 0);
+    for (uint32_t p = 0; p < nstn; ++p) {
+        uint32_t v = out.stn_of_pos[p];
+        uint64_t later = 0;
+        for (uint64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e)
+            later += out.pos_of_stn[g.adj[e]] > p;
+        out.ncol_ptr[p + 1] = out.ncol_ptr[p] + 1 + later;
+    }
+    out.nrow.resize(out.ncol_ptr[nstn]);
+    out.ndest.resize(out.ncol_ptr[nstn]);
+    out.ndest_ld.resize(out.ncol_ptr[nstn]);
+    for (uint32_t p = 0; p < nstn; ++p) {
+        uint32_t v = out.stn_of_pos[p];
+        uint64_t s = out.ncol_ptr[p];
+        out.nrow[s++] = p;
+        for (uint64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e) {
+            uint32_t q = out.pos_of_stn[g.adj[e]];
+            if (q > p)
+                out.nrow[s++] = q;
+        }
+        std::sort(out.nrow.begin() + out.ncol_ptr[p] + 1, out.nrow.begin() + out.ncol_ptr[p + 1]);
+        const uint32_t f = out.front_of_pos[p];
+        const Front& fr = out.fronts[f];
+        const uint32_t own_end = fr.own_begin + fr.own_count;
+        const uint32_t* b = out.bnd.data() + fr.bnd_begin;
+        const uint64_t col = 3ull * (p - fr.own_begin);
+        for (uint64_t t = out.ncol_ptr[p]; t < out.ncol_ptr[p + 1]; ++t) {
+            uint32_t q = out.nrow[t];
+            uint64_t row;
+            if (q < own_end)
+                row = 3ull * (q - fr.own_begin);
+            else {
+                const uint32_t* it = std::lower_bound(b, b + fr.bnd_count, q);
+                if (it == b + fr.bnd_count || *it != q)
+                    return "internal: neighbour missing from the front boundary";
+                row = 3ull * (fr.own_count + (uint32_t)(it - b));
+            }
+            out.ndest[t] = fr.panel_off + row * fr.ldk + col;
+            out.ndest_ld[t] = fr.ldk;
+        }
+    }
+    return std::string();
+}
+
+}  // namespace gadj

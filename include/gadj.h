@@ -1,0 +1,142 @@
+/*
+ * gadj.h — C-ABI of the B200-native least-squares adjustment engine (libgadj.so).
+ *
+ * This is the drop-in seam for the solve path of DynAdjust's `dnaadjust`: each
+ * entry point replaces a member of the reference's `dna_adjust` class
+ * (dynadjust/dynadjust/dnaadjust/dnaadjust.hpp:212-1362) that the reference
+ * wrapper drives (dnaadjustwrapper.cpp:1142, dnaadjustprogress.cpp:49-67).
+ * Plain pointers and sizes only; the caller owns every host array, the context
+ * owns all device memory.  All functions return 0 on success, non-zero on error
+ * (text from gadj_last_error); singular normals report the reference's message
+ * "Matrix inversion failed, the matrix is singular." (dnamatrix_contiguous.cpp:983).
+ * One host thread drives a context; streams and kernels are internal.
+ *
+ *   reference member (file:line)                               entry point here
+ *   ---------------------------------------------------------  ---------------------------
+ *   dna_adjust ctor + InitialiseAdjustment   ADJ:198-246        gadj_create
+ *   LoadNetworkFiles -> bstBinaryRecords_    ADJ:10107          gadj_set_stations
+ *   LoadNetworkFiles -> bmsBinaryRecords_    ADJ:10107          gadj_set_measurements
+ *   LoadSegmentationFile (v_ISL_/v_JSL_)     ADJ:10644-10664    gadj_set_blocks
+ *   PrepareAdjustment                        ADJ:258            gadj_prepare
+ *   Solve + estimates update (one iteration) ADJ:6586, 2457-63  gadj_iterate
+ *   AdjustNetwork / AdjustSimultaneous       ADJ:2140, 2413     gadj_adjust
+ *   GenerateStatistics / ComputeStatistics   ADJ:6802, 7116     gadj_statistics
+ *   v_estimatedStations_                     ADJH:1246-1270     gadj_get_estimates
+ *   v_corrections_                                              gadj_get_corrections
+ *   v_rigorousVariances_ (3x3 diagonal)      PRN:3917-4070      gadj_get_station_vcv(s)
+ *   v_rigorousVariances_ (pattern blocks)    ADJ:7784-8060      gadj_get_vcv_block
+ *   v_normals_ / At V^-1 l (before Solve)    ADJ:893-896        gadj_get_normals_block / gadj_get_rhs
+ */
+#ifndef GADJ_H_
+#define GADJ_H_
+
+#include <stdint.h>
+
+#include "dna_records.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gadj_ctx gadj_ctx;
+
+enum {
+    GADJ_ORDER_AUTO = 0,     /* blocks from gadj_set_blocks if given, else nested dissection */
+    GADJ_ORDER_DENSE = 1     /* one dense front (reference simultaneous mode on dense normals) */
+};
+
+enum {
+    GADJ_ITER_NORMALS = 1,   /* re-assemble N and refactorise (always done on the first call) */
+    GADJ_ITER_INVERSE = 2    /* also form the rigorous (selected) inverse in this call */
+};
+
+typedef struct gadj_opts {
+    double fixed_std_dev;          /* sigma of 'C' components, default 1e-6 m   (dnaoptions.hpp:432) */
+    double free_std_dev;           /* sigma of 'F' components, default 10 m */
+    double iteration_threshold;    /* default (double)(float)0.0005 m           (dnaoptions.hpp:432, ADJ:2477) */
+    double semi_major;             /* ellipsoid, default GRS80 */
+    double inv_flattening;
+    double confidence_interval;    /* default 95.0 */
+    double workspace_gb;           /* selected-inverse workspace budget; 0 = automatic */
+    uint32_t max_iterations;       /* default 10 */
+    int32_t scale_normals_to_unity;/* default 1: symmetric diagonal equilibration (ADJ:6614-6645), always safe */
+    int32_t ordering;              /* GADJ_ORDER_* */
+    uint32_t leaf_stations;        /* nested-dissection leaf size, default 96 */
+    int32_t device;                /* CUDA device ordinal */
+    int32_t reserved;
+} gadj_opts;
+
+typedef struct gadj_iter_result {
+    double max_corr;               /* signed largest-magnitude Cartesian correction (ADJ:2466) */
+    uint32_t max_corr_station;     /* station index it belongs to */
+    uint32_t max_corr_axis;        /* 0=X 1=Y 2=Z */
+    uint32_t iteration;            /* 1-based count of iterations run on this context */
+    int32_t converged;             /* |max_corr| <= iteration_threshold */
+    float ms_assemble, ms_factor, ms_solve, ms_inverse;   /* device time of each phase (CUDA events) */
+} gadj_iter_result;
+
+typedef struct gadj_stats {
+    double chi_squared;
+    double sigma_zero;             /* chi^2 / dof  (the reference's sigmaZero_) */
+    int64_t dof;
+    uint32_t measurement_params;
+    uint32_t unknown_params;
+    uint32_t outliers;
+    uint32_t reserved;
+    double global_pelzer;
+    double critical_value;
+} gadj_stats;
+
+typedef struct gadj_info {
+    uint64_t nstations, nbaselines, nedges;
+    uint64_t nfronts, nlevels;
+    uint64_t panel_bytes, pool_bytes, device_bytes;
+    double factor_flops, inverse_flops;    /* algorithmic, from the symbolic factorisation actually used */
+    uint64_t launches_factor, launches_solve, launches_inverse;
+    uint32_t max_front_rows, max_front_cols;
+} gadj_info;
+
+void gadj_default_opts(gadj_opts* o);
+int gadj_create(const gadj_opts* o, gadj_ctx** out);
+void gadj_destroy(gadj_ctx* c);
+const char* gadj_last_error(const gadj_ctx* c);   /* c may be NULL: error of the last failed gadj_create */
+
+/* borrowed: the arrays must outlive the context (or the next set_* call) */
+int gadj_set_stations(gadj_ctx* c, dna_stn_t* stn, uint32_t count);
+int gadj_set_measurements(gadj_ctx* c, dna_msr_t* msr, uint64_t count);
+/* optional chain segmentation (.seg): block b's inner stations are isl[isl_off[b] .. isl_off[b+1]) */
+int gadj_set_blocks(gadj_ctx* c, uint32_t nblocks, const uint32_t* isl_off, const uint32_t* isl);
+
+/* symbolic analysis, device allocation, upload, first-run variance scaling (written back to msr, ADJ:4281) */
+int gadj_prepare(gadj_ctx* c);
+int gadj_get_info(const gadj_ctx* c, gadj_info* info);
+
+/* re-send the host measurement records / a-priori station coordinates to the device */
+int gadj_upload_measurements(gadj_ctx* c);
+int gadj_reset_estimates(gadj_ctx* c);
+
+int gadj_iterate(gadj_ctx* c, int flags, gadj_iter_result* res);
+/* iterate to convergence with the reference's loop logic, then form the rigorous inverse */
+int gadj_adjust(gadj_ctx* c, gadj_iter_result* last);
+/* needs the rigorous inverse; write_back != 0 copies the statistics fields into the host msr records
+ * and the adjusted geographic coordinates into the host stn records */
+int gadj_statistics(gadj_ctx* c, gadj_stats* st, int write_back);
+
+int gadj_get_estimates(gadj_ctx* c, double* xyz /* 3*nstn */);
+int gadj_get_corrections(gadj_ctx* c, double* dxyz /* 3*nstn */);
+int gadj_get_station_vcvs(gadj_ctx* c, double* q /* 9*nstn, row-major 3x3 per station */);
+int gadj_get_station_vcv(gadj_ctx* c, uint32_t stn, double q[9]);
+/* N^-1 block (rows of station si, columns of station sj); only pairs joined by a measurement */
+int gadj_get_vcv_block(gadj_ctx* c, uint32_t si, uint32_t sj, double q[9]);
+/* assembled normals (constraints included) of the last iterate call that built them, and its right-hand side */
+int gadj_get_normals_block(gadj_ctx* c, uint32_t si, uint32_t sj, double n[9]);
+int gadj_get_rhs(gadj_ctx* c, double* w /* 3*nstn */);
+
+/* FP64 GEMM self-test / micro-benchmark of the tensor-core tile kernel: C = A * B^T (row-major host arrays).
+ * returns device milliseconds per call in *ms (averaged over reps) */
+int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int M, int N, int K, int reps, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GADJ_H_ */

@@ -1,0 +1,362 @@
+// tests/hostsim/kernels_host.cpp — TEST INFRASTRUCTURE.
+// Plain-loop stand-ins for every launch in csrc/kernels.h: an executable statement of what
+// each CUDA kernel must compute, used to validate the planner / index maps / control flow on
+// CPU.  Never linked into the product library.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../dynadjust_b200/csrc/geodesy.h"
+#include "../../dynadjust_b200/csrc/kernels.h"
+
+namespace gadj {
+
+void launch_gemm(const GemmOp* ops, int nops, int, void*)
+{
+    std::vector<double> row;
+    for (int o = 0; o < nops; ++o) {
+        const GemmOp& op = ops[o];
+        row.resize(op.N);
+        for (int i = 0; i < op.M; ++i) {
+            for (int j = 0; j < op.N; ++j) {
+                double acc = 0.0;
+                const double* a = op.A + (int64_t)i * op.lda;
+                const double* b = op.B + (int64_t)j * op.ldb;
+                for (int k = 0; k < op.K; ++k)
+                    acc += a[k] * b[k];
+                row[j] = (op.flags & GEMM_NEG) ? -acc : acc;
+            }
+            for (int j = 0; j < op.N; ++j) {
+                if ((op.flags & GEMM_LOWER) && i + op.tri_off < j)
+                    continue;
+                if (op.flags & GEMM_SCATTER) {
+                    int64_t r = 3ll * op.rowmap[i / 3] + i % 3;
+                    int64_t c = 3ll * op.rowmap[j / 3] + j % 3;
+                    op.C[r * op.ldc + c] += row[j];
+                } else if (op.flags & GEMM_ACCUM)
+                    op.C[(int64_t)i * op.ldc + j] += row[j];
+                else
+                    op.C[(int64_t)i * op.ldc + j] = row[j];
+            }
+        }
+    }
+}
+
+void launch_diag(const DiagOp* ops, int nops, int* info, void*)
+{
+    for (int o = 0; o < nops; ++o) {
+        const DiagOp& op = ops[o];
+        const int w = op.w;
+        double* D = op.D;
+        const int64_t ld = op.ldd;
+        if (op.factor) {
+            for (int j = 0; j < w; ++j) {
+                double d = D[j * ld + j];
+                for (int k = 0; k < j; ++k)
+                    d -= D[j * ld + k] * D[j * ld + k];
+                if (!(d > 0.0)) {
+                    if (info[0] == 0)
+                        info[0] = op.front + 1;
+                    d = 1.0;
+                }
+                d = std::sqrt(d);
+                D[j * ld + j] = d;
+                for (int i = j + 1; i < w; ++i) {
+                    double s = D[i * ld + j];
+                    for (int k = 0; k < j; ++k)
+                        s -= D[i * ld + k] * D[j * ld + k];
+                    D[i * ld + j] = s / d;
+                }
+            }
+        }
+        if (op.W || op.Wt) {
+            std::vector<double> W((size_t)w * w, 0.0);
+            for (int j = 0; j < w; ++j) {
+                W[(size_t)j * w + j] = 1.0 / D[j * ld + j];
+                for (int i = j + 1; i < w; ++i) {
+                    double s = 0.0;
+                    for (int k = j; k < i; ++k)
+                        s += D[i * ld + k] * W[(size_t)k * w + j];
+                    W[(size_t)i * w + j] = -s / D[i * ld + i];
+                }
+            }
+            for (int i = 0; i < w; ++i)
+                for (int j = 0; j < w; ++j) {
+                    if (op.W)
+                        op.W[i * op.ldw + j] = W[(size_t)i * w + j];
+                    if (op.Wt)
+                        op.Wt[j * op.ldwt + i] = W[(size_t)i * w + j];
+                }
+        }
+    }
+}
+
+void launch_tri(const TriOp* ops, int nops, int backward, void*)
+{
+    for (int o = 0; o < nops; ++o) {
+        const TriOp& op = ops[o];
+        const int w = op.w;
+        const double* D = op.D;
+        const int64_t ld = op.ldd;
+        double* x = op.x;
+        if (!backward) {
+            for (int i = 0; i < w; ++i) {
+                double s = x[i];
+                for (int k = 0; k < i; ++k)
+                    s -= D[i * ld + k] * x[k];
+                x[i] = s / D[i * ld + i];
+            }
+        } else {
+            for (int i = w - 1; i >= 0; --i) {
+                double s = x[i];
+                for (int k = i + 1; k < w; ++k)
+                    s -= D[k * ld + i] * x[k];
+                x[i] = s / D[i * ld + i];
+            }
+        }
+    }
+}
+
+void launch_gemv(const GemvOp* ops, int nops, const double* x_ro, double* x, int backward, void*)
+{
+    for (int o = 0; o < nops; ++o) {
+        const GemvOp& op = ops[o];
+        if (!backward) {
+            for (int i = 0; i < op.nrows; ++i) {
+                double s = 0.0;
+                for (int c = 0; c < op.w; ++c)
+                    s += op.P[(int64_t)i * op.ld + c] * op.xj[c];
+                x[op.rowidx[i]] -= s;
+            }
+        } else {
+            for (int c = 0; c < op.w; ++c) {
+                double s = 0.0;
+                for (int i = 0; i < op.nrows; ++i)
+                    s += op.P[(int64_t)i * op.ld + c] * x_ro[op.rowidx[i]];
+                op.xj[c] -= s;
+            }
+        }
+    }
+}
+
+void launch_transpose(const TransposeOp* ops, int nops, void*)
+{
+    for (int o = 0; o < nops; ++o) {
+        const TransposeOp& op = ops[o];
+        for (int r = 0; r < op.rows; ++r)
+            for (int c = 0; c < op.cols; ++c)
+                op.dst[(int64_t)c * op.ldd + r] = op.src[(int64_t)r * op.lds + c];
+    }
+}
+
+void launch_gather(const GatherOp* ops, int nops, void*)
+{
+    for (int o = 0; o < nops; ++o) {
+        const GatherOp& op = ops[o];
+        for (int i = op.jb; i < op.nb; ++i) {
+            const int64_t zr = 3ll * op.rowmap[i - op.jb];
+            for (int j = op.jb; j < op.je && j <= i; ++j) {
+                const int64_t zc = 3ll * op.rowmap[j - op.jb];
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b) {
+                        double v;
+                        if (i == j && a < b)
+                            v = op.Z[(zr + b) * op.ld + zc + a];
+                        else
+                            v = op.Z[(zr + a) * op.ld + zc + b];
+                        op.G[(3ll * i + a) * op.ldg + 3 * j + b] = v;
+                        op.G[(3ll * j + b) * op.ldg + 3 * i + a] = v;
+                    }
+            }
+        }
+    }
+}
+
+void launch_init_normals(const double* cblock, double* ndiag, double* noff, double* w, uint32_t nstn, uint64_t nedge, void*)
+{
+    if (cblock) {
+        std::memcpy(ndiag, cblock, 9 * (size_t)nstn * sizeof(double));
+        std::memset(noff, 0, 9 * (size_t)nedge * sizeof(double));
+    }
+    std::memset(w, 0, 3 * (size_t)nstn * sizeof(double));
+}
+
+void launch_assemble_g(const AssembleParams& p, void*)
+{
+    for (uint64_t b = 0; b < p.nbaselines; ++b) {
+        const dna_msr_t* m = p.msr + p.first[b];
+        const uint32_t s1 = m[0].station1, s2 = m[0].station2;
+        double l[3];
+        for (int r = 0; r < 3; ++r)
+            l[r] = m[r].term1 - (p.est[3 * (size_t)s2 + r] - p.est[3 * (size_t)s1 + r]);
+        const double up[6] = {m[0].term2, m[1].term2, m[2].term2, m[1].term3, m[2].term3, m[2].term4};
+        double q[6];
+        if (!spd3_inverse(up, q))
+            for (double& v : q)
+                v = NAN;
+        const double V[9] = {q[0], q[1], q[2], q[1], q[3], q[4], q[2], q[4], q[5]};
+        double t[3];
+        for (int r = 0; r < 3; ++r)
+            t[r] = V[3 * r] * l[0] + V[3 * r + 1] * l[1] + V[3 * r + 2] * l[2];
+        for (int r = 0; r < 3; ++r) {
+            p.w[3 * (size_t)s1 + r] -= t[r];
+            p.w[3 * (size_t)s2 + r] += t[r];
+        }
+        if (p.chi2)
+            *p.chi2 += l[0] * t[0] + l[1] * t[1] + l[2] * t[2];
+        if (p.normals) {
+            const uint32_t e = p.edge[b] & 0x7FFFFFFFu;
+            for (int k = 0; k < 9; ++k) {
+                p.ndiag[9 * (size_t)s1 + k] += V[k];
+                p.ndiag[9 * (size_t)s2 + k] += V[k];
+                p.noff[9 * (size_t)e + k] -= V[k];
+            }
+        }
+    }
+}
+
+void launch_compute_scale(const ScatterParams& p, void*)
+{
+    for (uint32_t s = 0; s < p.nstn; ++s)
+        for (int c = 0; c < 3; ++c)
+            p.dscale[3 * (size_t)s + c] = p.scale ? 1.0 / std::sqrt(p.ndiag[9 * (size_t)s + 4 * c]) : 1.0;
+}
+
+void launch_scatter_normals(const ScatterParams& p, void*)
+{
+    for (uint32_t s = 0; s < p.nstn; ++s) {
+        double* d = p.panels + p.diag_dest[s];
+        const uint32_t ld = p.diag_ld[s];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                d[(size_t)r * ld + c] = p.ndiag[9 * (size_t)s + 3 * r + c] * p.dscale[3 * (size_t)s + r] * p.dscale[3 * (size_t)s + c];
+    }
+    for (uint64_t e = 0; e < p.nedge; ++e) {
+        double* d = p.panels + p.off_dest[e];
+        const uint32_t ld = p.off_ld[e];
+        const uint32_t hi = p.edge_hi[e], lo = p.edge_lo[e];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                d[(size_t)r * ld + c] = p.noff[9 * e + 3 * r + c] * p.dscale[3 * (size_t)hi + r] * p.dscale[3 * (size_t)lo + c];
+    }
+}
+
+void launch_permute_rhs(const double* w, const double* dscale, const uint32_t* pos, double* b, uint32_t nstn, void*)
+{
+    for (uint32_t s = 0; s < nstn; ++s)
+        for (int c = 0; c < 3; ++c)
+            b[3 * (size_t)pos[s] + c] = dscale[3 * (size_t)s + c] * w[3 * (size_t)s + c];
+}
+
+void launch_apply_corrections(const double* x, const double* dscale, const uint32_t* pos, double* corr, double* est,
+                              uint32_t nstn, void*)
+{
+    size_t best = 0;
+    for (uint32_t s = 0; s < nstn; ++s)
+        for (int c = 0; c < 3; ++c) {
+            size_t i = 3 * (size_t)s + c;
+            corr[i] = dscale[i] * x[3 * (size_t)pos[s] + c];
+            est[i] += corr[i];
+            if (std::fabs(corr[i]) > std::fabs(corr[best]))
+                best = i;
+        }
+    corr[3 * (size_t)nstn] = corr[best];
+    corr[3 * (size_t)nstn + 1] = (double)best;
+}
+
+void launch_extract_station_vcv(const double* panels, const uint64_t* diag_dest, const uint32_t* diag_ld,
+                                const double* dscale, double* vcv, uint32_t nstn, void*)
+{
+    for (uint32_t s = 0; s < nstn; ++s) {
+        const double* z = panels + diag_dest[s];
+        const uint32_t ld = diag_ld[s];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+                int a = r > c ? r : c, b = r > c ? c : r;
+                vcv[9 * (size_t)s + 3 * r + c] = z[(size_t)a * ld + b] * dscale[3 * (size_t)s + r] * dscale[3 * (size_t)s + c];
+            }
+    }
+}
+
+void launch_extract_edge_vcv(const double* panels, const uint64_t* off_dest, const uint32_t* off_ld, const uint32_t* edge_hi,
+                             const uint32_t* edge_lo, const double* dscale, double* q, uint64_t nedge, void*)
+{
+    for (uint64_t e = 0; e < nedge; ++e) {
+        const double* z = panels + off_dest[e];
+        const uint32_t ld = off_ld[e];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                q[9 * e + 3 * r + c] = z[(size_t)r * ld + c] * dscale[3 * (size_t)edge_hi[e] + r] * dscale[3 * (size_t)edge_lo[e] + c];
+    }
+}
+
+void launch_stats_g(const StatsParams& p, void*)
+{
+    for (uint64_t b = 0; b < p.nbaselines; ++b) {
+        dna_msr_t* m = p.msr + p.first[b];
+        const uint32_t s1 = m[0].station1, s2 = m[0].station2;
+        double l[3];
+        for (int r = 0; r < 3; ++r)
+            l[r] = m[r].term1 - (p.est[3 * (size_t)s2 + r] - p.est[3 * (size_t)s1 + r]);
+        const uint32_t ew = p.edge[b];
+        const double* Qo = p.vcv_off + 9 * (size_t)(ew & 0x7FFFFFFFu);
+        const bool s1_is_hi = (ew & 0x80000000u) != 0;
+        const double* Q11 = p.vcv_diag + 9 * (size_t)s1;
+        const double* Q22 = p.vcv_diag + 9 * (size_t)s2;
+        // Q21(i,j) = N^-1[s2+i, s1+j]
+        auto Q21 = [&](int i, int j) { return s1_is_hi ? Qo[3 * j + i] : Qo[3 * i + j]; };
+        // Precision_Adjusted_GNSS_bsl (dnatemplatematrixfuncs.hpp:255-297): A Q A^T, A = [-I I]
+        double P[3][3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = i; j < 3; ++j) {
+                double t0 = -Q11[3 * i + j] + Q21(i, j);       // tmp[i][j]
+                double t1 = -Q21(j, i) + Q22[3 * i + j];       // tmp[i][j+3]: -Q(s1+i, s2+j) + Q(s2+i, s2+j)
+                P[i][j] = t1 - t0;
+            }
+        const double prec[3] = {P[0][0], P[1][1], P[2][2]};
+        const double mprec[3] = {m[0].term2, m[1].term3, m[2].term4};
+        for (int r = 0; r < 3; ++r) {
+            // UpdateMsrRecord / UpdateMsrRecordStats (ADJ:8187-8298)
+            m[r].measCorr = -l[r];
+            m[r].measAdj = m[r].term1 + m[r].measCorr;
+            m[r].measAdjPrec = prec[r];
+            double rp = mprec[r] - prec[r];
+            if (rp < 0.0)
+                rp = std::fabs(rp);
+            m[r].residualPrec = rp;
+            double pel = std::sqrt(mprec[r]) / std::sqrt(rp);
+            if (pel < 0. || pel > 700.)
+                pel = 999.99;
+            m[r].NStat = m[r].measCorr / std::sqrt(rp);
+            if (std::fabs(m[r].NStat) > p.critical)
+                p.sums[3] += 1.0;
+            // ComputeGlobalPelzer_GXY (ADJ:8396-8427)
+            if (pel > 0. && pel < 999.99) {
+                p.sums[1] += pel * pel - 1.;
+                p.sums[2] += 1.0;
+            } else
+                pel = 999.99;
+            m[r].PelzerRel = pel;
+        }
+        const double up[6] = {m[0].term2, m[1].term2, m[2].term2, m[1].term3, m[2].term3, m[2].term4};
+        double q[6];
+        if (!spd3_inverse(up, q))
+            for (double& v : q)
+                v = NAN;
+        const double V[9] = {q[0], q[1], q[2], q[1], q[3], q[4], q[2], q[4], q[5]};
+        double cs = 0.0;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                cs += V[3 * r + c] * l[r] * l[c];
+        p.sums[0] += cs;
+    }
+}
+
+void launch_cart_to_geo(const double* est, double* llh, uint32_t nstn, double a, double invf, void*)
+{
+    Ellipsoid e = make_ellipsoid(a, invf);
+    for (uint32_t s = 0; s < nstn; ++s)
+        cart_to_geo(e, est[3 * (size_t)s], est[3 * (size_t)s + 1], est[3 * (size_t)s + 2], llh + 3 * (size_t)s);
+}
+
+}  // namespace gadj
