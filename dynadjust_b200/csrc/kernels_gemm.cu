@@ -1,0 +1,279 @@
+// kernels_gemm.cu — batched FP64 tile GEMM on the DMMA tensor path, fed by TMA.
+//
+//   C[M x N] (+)= alpha * A[M x K] * B[N x K]^T        (all row-major, K contiguous)
+//
+// One CTA computes one 128 x 128 output tile of one op; a launch covers the tiles of many
+// ops (all the panel updates / Schur complements / inverse products of one tree level).
+//
+// Data path: a producer warp issues cp.async.bulk.tensor (TMA) loads of 128 x 16 FP64
+// boxes of A and B into a 4-stage shared-memory ring (SWIZZLE_128B, mbarrier full/empty
+// pairs); 8 consumer warps (2 along M x 4 along N, 64 x 32 each) read fragments with
+// bank-conflict-free LDS.64 and issue mma.sync.m8n8k4.f64 (DMMA).  The swizzle makes a
+// fragment's 8 rows conflict-free only when they are 2 apart, so fragment i of a warp
+// covers rows {16*(i/2) + 2g + (i&1)}: the same map is applied to A rows, B rows (= C
+// columns) and the accumulator addresses, so the product is unchanged.
+//
+// Roofline: FP64 tensor pipe.  Per tile and 16-deep K step: 2*128*128*16 = 524k flop against
+// 32 KB of TMA traffic (16 flop/B from L2; panels are read ~once from HBM per launch).
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdlib>
+
+#include "kernels.h"
+
+namespace gadj {
+namespace {
+
+constexpr int STAGES = 4;
+constexpr int A_TILE_BYTES = TILE_M * TILE_K * 8;   // 16 KB
+constexpr int B_TILE_BYTES = TILE_N * TILE_K * 8;   // 16 KB
+constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int CONSUMER_WARPS = 8;
+constexpr int GEMM_THREADS = (CONSUMER_WARPS + 1) * 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// LOADER 0: TMA producer warp + mbarrier ring (the product path).
+// LOADER 1: debug aid (GADJ_GEMM_LOADER=ldg) — the consumers fill one stage themselves with plain loads
+//           into the same swizzled layout; isolates tensor-map problems from fragment-layout problems.
+template <int LOADER>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp* __restrict__ ops, int nops)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const int tile = blockIdx.x;
+    // locate the op that owns this tile
+    int lo = 0, hi = nops - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (ops[mid].tile_begin <= tile)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const GemmOp* op = ops + lo;
+    const int local = tile - op->tile_begin;
+    const int tiles_n = op->tiles_n;
+    const int tm = local / tiles_n, tn = local - tm * tiles_n;
+    const int row0 = tm * TILE_M, col0 = tn * TILE_N;
+    const int M = op->M, N = op->N, K = op->K;
+    const int flags = op->flags, tri_off = op->tri_off;
+    if ((flags & GEMM_LOWER) && row0 + (TILE_M - 1) + tri_off < col0)
+        return;  // the whole tile lies above the diagonal
+    const int nk = (K + TILE_K - 1) / TILE_K;
+
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_full = base + STAGES * STAGE_BYTES;
+    const uint32_t bar_empty = bar_full + 8 * STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (LOADER == 0 && threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == CONSUMER_WARPS) {
+        // ---- TMA producer -------------------------------------------------------
+        if (LOADER == 0 && lane == 0) {
+            const void* tmA = &op->tmA;
+            const void* tmB = &op->tmB;
+            asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmA) : "memory");
+            asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmB) : "memory");
+            for (int kc = 0; kc < nk; ++kc) {
+                const int s = kc % STAGES;
+                if (kc >= STAGES)
+                    mbar_wait(bar_empty + 8 * s, ((kc / STAGES) - 1) & 1);
+                const uint32_t sa = base + s * STAGE_BYTES;
+                mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+                tma_load_2d(sa, tmA, kc * TILE_K, row0, bar_full + 8 * s);
+                tma_load_2d(sa + A_TILE_BYTES, tmB, kc * TILE_K, col0, bar_full + 8 * s);
+            }
+        }
+        return;
+    }
+
+    // ---- DMMA consumers ----------------------------------------------------------
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // per-thread constant parts of the swizzled fragment addresses
+    // element (r, k) of a 128 x 16 tile: r*128 + (((k>>1) ^ (r&7)) << 4) + ((k&1) << 3)
+    uint32_t a_row[8], b_row[4];
+    int a_x[2], b_x[2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        a_row[i] = (uint32_t)(wm + 16 * (i >> 1) + 2 * g + (i & 1)) * 128u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        b_row[j] = (uint32_t)(wn + 16 * (j >> 1) + 2 * g + (j & 1)) * 128u;
+    a_x[0] = b_x[0] = (2 * g) & 7;
+    a_x[1] = b_x[1] = (2 * g + 1) & 7;
+    const uint32_t khalf = (uint32_t)(t & 1) << 3;
+    const int kq = t >> 1;
+
+    for (int kc = 0; kc < nk; ++kc) {
+        const int s = LOADER == 0 ? kc % STAGES : 0;
+        const uint32_t sa = base + s * STAGE_BYTES;
+        const uint32_t sb = sa + A_TILE_BYTES;
+        if (LOADER == 0) {
+            mbar_wait(bar_full + 8 * s, (kc / STAGES) & 1);
+        } else {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const double* __restrict__ gA = op->A;
+            const double* __restrict__ gB = op->B;
+            for (int idx = threadIdx.x; idx < TILE_M * TILE_K; idx += CONSUMER_WARPS * 32) {
+                const int r = idx / TILE_K, k = idx - r * TILE_K;
+                const int gk = kc * TILE_K + k;
+                const uint32_t off = (uint32_t)r * 128u + ((uint32_t)((k >> 1) ^ (r & 7)) << 4) + ((uint32_t)(k & 1) << 3);
+                const double va = (row0 + r < M && gk < K) ? gA[(int64_t)(row0 + r) * op->lda + gk] : 0.0;
+                const double vb = (col0 + r < N && gk < K) ? gB[(int64_t)(col0 + r) * op->ldb + gk] : 0.0;
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"(sa + off), "d"(va) : "memory");
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"(sb + off), "d"(vb) : "memory");
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+#pragma unroll
+        for (int k4 = 0; k4 < TILE_K / 4; ++k4) {
+            const int chunk = 2 * k4 + kq;
+            const uint32_t o0 = ((uint32_t)(chunk ^ a_x[0]) << 4) + khalf;
+            const uint32_t o1 = ((uint32_t)(chunk ^ a_x[1]) << 4) + khalf;
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                a[i] = lds_f64(sa + a_row[i] + ((i & 1) ? o1 : o0));
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                b[j] = lds_f64(sb + b_row[j] + ((j & 1) ? o1 : o0));
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (LOADER == 0 && lane == 0)
+            mbar_arrive(bar_empty + 8 * s);
+    }
+
+    // ---- epilogue ------------------------------------------------------------------
+    const double alpha = (flags & GEMM_NEG) ? -1.0 : 1.0;
+    double* __restrict__ C = op->C;
+    const int64_t ldc = op->ldc;
+    const bool lower = (flags & GEMM_LOWER) != 0;
+    if (flags & GEMM_SCATTER) {
+        const int32_t* __restrict__ rowmap = op->rowmap;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = row0 + wm + 16 * (i >> 1) + 2 * g + (i & 1);
+            if (r >= M)
+                continue;
+            const int64_t dr = 3ll * rowmap[r / 3] + r % 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = col0 + wn + 16 * (j >> 1) + 2 * (2 * t + e) + (j & 1);
+                    if (c >= N || (lower && r + tri_off < c))
+                        continue;
+                    const int64_t dc = 3ll * rowmap[c / 3] + c % 3;
+                    atomicAdd(C + dr * ldc + dc, alpha * acc[i][j][e]);
+                }
+        }
+    } else {
+        const bool accum = (flags & GEMM_ACCUM) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = row0 + wm + 16 * (i >> 1) + 2 * g + (i & 1);
+            if (r >= M)
+                continue;
+            double* __restrict__ crow = C + (int64_t)r * ldc;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = col0 + wn + 16 * (j >> 1) + 2 * (2 * t + e) + (j & 1);
+                    if (c >= N || (lower && r + tri_off < c))
+                        continue;
+                    const double v = alpha * acc[i][j][e];
+                    crow[c] = accum ? crow[c] + v : v;
+                }
+        }
+    }
+}
+
+}  // namespace
+
+void launch_gemm(const GemmOp* ops, int nops, int total_tiles, void* stream)
+{
+    if (nops <= 0 || total_tiles <= 0)
+        return;
+    static int loader = -1;
+    if (loader < 0) {
+        const char* e = getenv("GADJ_GEMM_LOADER");
+        loader = (e && e[0] == 'l') ? 1 : 0;
+        cudaFuncSetAttribute(gemm_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        cudaFuncSetAttribute(gemm_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    }
+    if (loader == 0)
+        gemm_tile_kernel<0><<<total_tiles, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(ops, nops);
+    else
+        gemm_tile_kernel<1><<<total_tiles, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(ops, nops);
+}
+
+}  // namespace gadj

@@ -1,0 +1,109 @@
+"""GPU parity tests: the CUDA path, through the C-ABI, against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from dynadjust_b200 import engine, synth
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 16), (128, 128, 128), (1, 1, 2), (3, 5, 4), (64, 64, 64), (129, 127, 18),
+                                   (200, 72, 50), (300, 260, 130), (512, 384, 1000), (1000, 1000, 6)])
+def test_gemm_tile_kernel(gpu_lib, M, N, K):
+    """TMA-fed DMMA tile kernel: C = A B^T, ragged edges zero-filled by the tensor maps.  FP64: 1e-13 relative."""
+    rng = np.random.default_rng(M * 1000003 + N * 1009 + K)
+    A = rng.standard_normal((M, K))
+    B = rng.standard_normal((N, K))
+    adj = engine.Adjustment(lib_path=gpu_lib)
+    C, ms = adj.test_gemm(A, B)
+    ref = A @ B.T
+    assert np.abs(C - ref).max() <= 1e-13 * K * max(1.0, np.abs(ref).max())
+    adj.close()
+
+
+def test_normals_and_rhs(oracle, gpu_lib):
+    parity.check_normals(oracle, gpu_lib, 80, 240, 4, leaf_stations=12)
+
+
+@pytest.mark.parametrize("n,m,seed,leaf", [(100, 300, 1235, 16), (400, 1200, 5, 8), (1000, 3000, 7, 24), (2000, 6000, 13, 96)])
+def test_nested_dissection_matches_oracle(oracle, gpu_lib, n, m, seed, leaf):
+    info = parity.check_against_oracle(oracle, gpu_lib, n, m, seed, leaf_stations=leaf)
+    assert info.nfronts > 1
+
+
+def test_dense_front_matches_oracle(oracle, gpu_lib):
+    parity.check_against_oracle(oracle, gpu_lib, 60, 170, 21, ordering=engine.ORDER_DENSE)
+    parity.check_against_oracle(oracle, gpu_lib, 500, 1500, 22, ordering=engine.ORDER_DENSE)   # 12 pivot tiles
+
+
+def test_chain_blocks_match_oracle(oracle, gpu_lib):
+    parity.check_against_oracle(oracle, gpu_lib, 300, 900, 9, blocks=lambda n: parity.chain_blocks(n, 40))
+
+
+def test_degree_20_network(oracle, gpu_lib):
+    parity.check_against_oracle(oracle, gpu_lib, 400, 3600, 31, leaf_stations=32)
+
+
+def test_mixed_constraints(oracle, gpu_lib):
+    def mutate(stn, msr, truth):
+        for s, code in ((5, b"CCF"), (17, b"FFC"), (23, b"CFC")):
+            stn["stationConst"][s] = code
+            lat, lon, h = synth.cart_to_geo(truth[s])
+            stn["currentLatitude"][s], stn["currentLongitude"][s], stn["currentHeight"][s] = lat, lon, h
+    parity.check_against_oracle(oracle, gpu_lib, 120, 360, 77, mutate=mutate, leaf_stations=16)
+
+
+def test_variance_scaling(oracle, gpu_lib):
+    def mutate(stn, msr, truth):
+        msr["scale4"] = 2.5
+        rec = msr.reshape(-1, 3)
+        rec["scale1"][::3] = 1.5
+        rec["scale3"][::5] = 3.0
+    parity.check_against_oracle(oracle, gpu_lib, 100, 300, 8, mutate=mutate, leaf_stations=16)
+
+
+def test_small_workspace_forces_chunks(oracle, gpu_lib):
+    parity.check_against_oracle(oracle, gpu_lib, 400, 1200, 5, leaf_stations=8, workspace_gb=2.0e-4)
+
+
+def test_non_contiguous_measurement_list(oracle, gpu_lib):
+    """Ignored baselines break the contiguous-record fast path of the assembly kernel."""
+    def mutate(stn, msr, truth):
+        msr["ignore"][30:33] = 1
+        msr["ignore"][300:303] = 1
+    parity.check_against_oracle(oracle, gpu_lib, 150, 450, 19, mutate=mutate, leaf_stations=16)
+
+
+def test_singular_network_reports_reference_message(gpu_lib):
+    stn, msr, _, _ = synth.gnss_network(30, 80, 3)
+    msr["term2"] = 0.0
+    adj = engine.Adjustment(stn, msr, lib_path=gpu_lib)
+    adj.prepare()
+    with pytest.raises(engine.AdjustmentError) as e:
+        adj.adjust()
+    assert "Invalid variance matrix" in str(e.value) or "singular" in str(e.value)
+
+
+def test_scale_properties_config_c2(gpu_lib):
+    """BASELINE config C2 size (10k stations / 30k baselines), no oracle: size-independent properties.
+    Three independent elimination orders (two dissections, one chain of blocks) must agree; the converged
+    solution is a fixed point of the iteration; sigma-zero of a noise-consistent network is ~1."""
+    stn, msr, truth, _ = synth.config_network("C2")
+    results = []
+    for kw, blocks in ((dict(leaf_stations=96), None), (dict(leaf_stations=40), None),
+                       (dict(), parity.chain_blocks(len(stn), 500))):
+        s, m = stn.copy(), msr.copy()
+        adj, info, last, stats = parity.run_engine(gpu_lib, s, m, blocks=blocks, **kw)
+        est, q = adj.estimates(), adj.station_vcvs()
+        extra = adj.iterate(normals=True)          # one more full iteration from the converged estimates
+        assert abs(extra.max_corr) < 1e-7
+        results.append((est, q, stats))
+        adj.close()
+    e0, q0, s0 = results[0]
+    assert 0.95 < s0.sigma_zero < 1.05
+    assert np.sqrt(((e0 - truth) ** 2).mean()) < 0.05
+    for est, q, st in results[1:]:
+        assert np.abs(est - e0).max() < 1e-9
+        assert abs(st.sigma_zero - s0.sigma_zero) < 1e-12
+        assert np.abs(q - q0).max() < 1e-9 * np.abs(q0).max()

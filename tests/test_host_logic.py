@@ -1,0 +1,135 @@
+"""CPU tests of the engine's host logic (symbolic analysis, planner, control flow, C-ABI surface).
+
+These run the product's host code against plain-loop stand-ins for the CUDA kernels
+(tests/hostsim) — they validate indices, maps and the algorithm, not the kernels; the kernels
+themselves are checked by the `-m gpu` tests."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from dynadjust_b200 import engine, synth
+from tests import parity
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("n,m,seed,leaf", [(100, 300, 1235, 16), (400, 1200, 5, 8), (1000, 3000, 7, 24)])
+def test_nested_dissection_matches_oracle(oracle, hostsim_path, n, m, seed, leaf):
+    info = parity.check_against_oracle(oracle, hostsim_path, n, m, seed, leaf_stations=leaf)
+    assert info.nfronts > 1 and info.nlevels > 1
+
+
+def test_dense_front_matches_oracle(oracle, hostsim_path):
+    # one dense front wider than one pivot tile (k = 180 > NB = 128)
+    info = parity.check_against_oracle(oracle, hostsim_path, 60, 170, 21, ordering=engine.ORDER_DENSE)
+    assert info.nfronts == 1
+
+
+def test_chain_blocks_match_oracle(oracle, hostsim_path):
+    # a .seg-style chain of blocks (phased adjustment) is rigorous: same answer as simultaneous
+    info = parity.check_against_oracle(oracle, hostsim_path, 300, 900, 9, blocks=lambda n: parity.chain_blocks(n, 40))
+    assert info.nfronts == 8 and info.nlevels == 8
+
+
+def test_degree_20_network(oracle, hostsim_path):
+    # the C4 edge recipe (10 neighbour offsets per station) at a size the oracle finishes in seconds
+    parity.check_against_oracle(oracle, hostsim_path, 400, 3600, 31, leaf_stations=32)
+
+
+def test_mixed_constraints(oracle, hostsim_path):
+    def mutate(stn, msr, truth):
+        # partially constrained stations (held at their true position in the constrained components)
+        for s, code in ((5, b"CCF"), (17, b"FFC"), (23, b"CFC")):
+            stn["stationConst"][s] = code
+            lat, lon, h = synth.cart_to_geo(truth[s])
+            stn["currentLatitude"][s], stn["currentLongitude"][s], stn["currentHeight"][s] = lat, lon, h
+    parity.check_against_oracle(oracle, hostsim_path, 120, 360, 77, mutate=mutate, leaf_stations=16)
+
+
+def test_variance_scaling(oracle, hostsim_path):
+    def mutate(stn, msr, truth):
+        msr["scale4"] = 2.5                    # whole-matrix scalar
+        rec = msr.reshape(-1, 3)
+        rec["scale1"][::3] = 1.5               # phi
+        rec["scale3"][::5] = 3.0               # height
+    parity.check_against_oracle(oracle, hostsim_path, 100, 300, 8, mutate=mutate, leaf_stations=16)
+
+
+def test_normals_and_rhs(oracle, hostsim_path):
+    parity.check_normals(oracle, hostsim_path, 80, 240, 4, leaf_stations=12)
+
+
+def test_small_workspace_forces_chunks(oracle, hostsim_path):
+    # a tight inverse workspace makes every level run in several chunks; results must not change
+    parity.check_against_oracle(oracle, hostsim_path, 400, 1200, 5, leaf_stations=8, workspace_gb=2.0e-4)
+
+
+def test_singular_network_reports_reference_message(hostsim_path):
+    stn, msr, _, _ = synth.gnss_network(30, 80, 3)
+    msr["term2"] = 0.0  # zero variances -> V is not positive definite
+    adj = engine.Adjustment(stn, msr, lib_path=hostsim_path)
+    adj.prepare()
+    with pytest.raises(engine.AdjustmentError) as e:
+        adj.adjust()
+    assert "Invalid variance matrix" in str(e.value) or "singular" in str(e.value)
+
+
+def test_error_paths(hostsim_path):
+    stn, msr, _, _ = synth.gnss_network(30, 80, 3)
+    adj = engine.Adjustment(lib_path=hostsim_path)
+    with pytest.raises(engine.AdjustmentError):
+        adj.prepare()                           # nothing set
+    adj.set_stations(stn)
+    bad = msr.copy()
+    bad["station2"][0:3] = 1000                 # beyond the station list
+    adj.set_measurements(bad)
+    with pytest.raises(engine.AdjustmentError, match="beyond the station list"):
+        adj.prepare()
+    other = msr.copy()
+    other["measType"][0:3] = b"Q"
+    adj.set_measurements(other)
+    with pytest.raises(engine.AdjustmentError, match="not handled"):
+        adj.prepare()
+    ign = msr.copy()
+    ign["ignore"][0:3] = 1                      # ignored measurements are skipped like the reference's CML
+    adj.set_measurements(ign)
+    info = adj.prepare()
+    assert info.nbaselines == len(msr) // 3 - 1
+    with pytest.raises(engine.AdjustmentError):
+        adj.station_vcvs()                      # inverse not formed yet
+
+
+def test_header_declares_every_exported_symbol(hostsim_path):
+    """include/gadj.h, the Python mirror and the library agree on the entry points."""
+    hdr = open(os.path.join(ROOT, "include", "gadj.h")).read()
+    declared = set(re.findall(r"\b(gadj_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(engine.EXPORTS)
+    lib = ctypes.CDLL(hostsim_path)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_product_library_exports(tmp_path):
+    """The CUDA product library loads on a CPU-only box and exports the full C-ABI (no compute calls)."""
+    path = engine.LIB_PATH
+    if not os.path.exists(path):
+        pytest.skip("libgadj.so not built yet (run __graft_entry__.build())")
+    lib = ctypes.CDLL(path)
+    for name in engine.EXPORTS:
+        assert hasattr(lib, name), name
+    out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    assert "DMMA" in out and "UTMALDG" in out and "UBLKCP" in out
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    if not os.path.exists(engine.LIB_PATH):
+        pytest.skip("libgadj.so not built yet")
+    with pytest.raises(engine.AdjustmentError, match="no CPU fallback"):
+        engine.Adjustment()

@@ -1,0 +1,96 @@
+"""The oracle against the reference's own known-answer vectors and NumPy/SciPy cross-checks (CPU)."""
+import numpy as np
+import pytest
+
+from dynadjust_b200 import synth
+
+
+def test_cholesky_inverse_known_answer(oracle):
+    # reference tests/test_matrix.cpp:196-222 — 3x3 SPD inverse known answer (tolerance 1e-4 there)
+    a = np.array([[4.0, 2.0, 1.0], [2.0, 5.0, 3.0], [1.0, 3.0, 6.0]])
+    for use_ref in (False, True):
+        inv = oracle.spd_inverse(a, use_ref=use_ref)
+        assert np.allclose(inv @ a, np.eye(3), atol=1e-12)
+        assert np.allclose(inv, np.linalg.inv(a), atol=1e-12)
+
+
+def test_cholesky_inverse_packed_equals_full(oracle):
+    # reference tests/test_matrix.cpp:1006-1026, 1279-1309 — packed path == full path to 1e-10
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 7, 33, 130):
+        m = rng.standard_normal((n, n))
+        a = m @ m.T + n * np.eye(n)
+        ref = oracle.spd_inverse(a, use_ref=True)
+        port = oracle.spd_inverse(a, use_ref=False)
+        assert np.allclose(ref, np.linalg.inv(a), rtol=1e-10, atol=1e-12)
+        assert np.allclose(port, ref, rtol=1e-10, atol=1e-12)
+
+
+def test_cholesky_inverse_singular_throws(oracle):
+    # reference tests/test_matrix.cpp:535-568 — singular / indefinite input raises MatrixInversionFailure
+    a = np.array([[1.0, 2.0], [2.0, 4.0]])
+    b = np.array([[1.0, 2.0], [2.0, 1.0]])
+    for m in (a, b):
+        for use_ref in (False, True):
+            with pytest.raises(np.linalg.LinAlgError):
+                oracle.spd_inverse(m, use_ref=use_ref)
+
+
+def test_geodesy_round_trip(oracle):
+    # GEO:78-90 / GEO:154-225 and the worked example in the reference header comment (GEO:143-152):
+    # X,Y,Z = (-3563081.362, -2057145.984, -4870449.482) on GRS80 -> -50, -150 (=> 210-360), 10000 m
+    llh = oracle.cart_to_geo(-3563081.362, -2057145.984, -4870449.482)
+    assert abs(np.degrees(llh[0]) + 50.0) < 1e-7
+    assert abs(np.degrees(llh[1]) + 150.0) < 1e-7
+    assert abs(llh[2] - 10000.0) < 2e-3
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        lat, lon, h = np.radians(rng.uniform(-80, 80)), np.radians(rng.uniform(-179, 179)), rng.uniform(-100, 9000)
+        xyz = oracle.geo_to_cart(lat, lon, h)
+        back = oracle.cart_to_geo(*xyz)
+        assert abs(back[0] - lat) < 1e-11 and abs(back[1] - lon) < 1e-11 and abs(back[2] - h) < 2e-5  # Newton stop at |f|<1e-12 (GEO:190) leaves a few um in h
+        assert np.allclose(xyz, synth.geo_to_cart(np.array(lat), np.array(lon), np.array(h)), atol=1e-6)
+
+
+def test_adjustment_against_numpy(oracle):
+    """End-to-end oracle run on config C1 versus an independent dense NumPy solve of the same normals."""
+    stn, msr, truth, _ = synth.config_network("C1")
+    out = oracle.adjust_simultaneous(stn, msr, want_normals=True, want_vcv=True)
+    res = out["res"]
+    assert res.iterations == 2 and res.converged
+    assert res.measurement_params == 900 and res.dof == 900 - (300 - 9)
+    n, w = out["normals"], out["rhs"]
+    assert np.allclose(n, n.T)
+    d = np.linalg.solve(n, w)
+    assert np.allclose(d, out["first_corr"], atol=1e-9)
+    q = np.linalg.inv(n)
+    assert np.abs(q - out["vcv"]).max() / np.abs(q).max() < 1e-9
+    # the adjusted network is consistent with the truth at the level of the simulated noise
+    assert np.sqrt(((out["est"] - truth) ** 2).mean()) < 0.02
+    assert 0.7 < res.sigma_zero < 1.3
+
+
+def test_ref_and_port_agree(oracle):
+    if not oracle.ref_loaded():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    stn, msr, _, _ = synth.gnss_network(200, 600, 11)
+    a = oracle.adjust_simultaneous(stn.copy(), msr.copy(), opts=oracle.default_opts(use_ref=1), want_vcv=True)
+    b = oracle.adjust_simultaneous(stn.copy(), msr.copy(), opts=oracle.default_opts(use_ref=0), want_vcv=True)
+    assert a["res"].used_ref == 1 and b["res"].used_ref == 0
+    assert np.abs(a["est"] - b["est"]).max() < 1e-9
+    assert abs(a["res"].sigma_zero - b["res"].sigma_zero) < 1e-12
+    assert np.abs(a["vcv"] - b["vcv"]).max() / np.abs(a["vcv"]).max() < 1e-9
+
+
+def test_variance_scaling_write_back(oracle):
+    """vScale / p,l,h scaling is applied once and written back into the records (ADJ:4281)."""
+    stn, msr, _, _ = synth.gnss_network(30, 80, 3)
+    msr["scale4"] = 4.0
+    before = msr["term2"].copy()
+    out = oracle.adjust_simultaneous(stn, msr)
+    assert np.allclose(msr["term2"], 4.0 * before)
+    stn2, msr2, _, _ = synth.gnss_network(30, 80, 3)
+    out2 = oracle.adjust_simultaneous(stn2, msr2)
+    # scaling every VCV by 4 divides chi^2 by 4 and leaves the estimates unchanged (to solver accuracy)
+    assert abs(out["res"].chi_squared * 4.0 - out2["res"].chi_squared) / out2["res"].chi_squared < 1e-6
+    assert np.abs(out["est"] - out2["est"]).max() < 1e-5
