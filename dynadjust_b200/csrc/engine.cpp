@@ -202,6 +202,35 @@ struct gadj_ctx {
     std::vector<double> h_corr;
     void* ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint64_t device_bytes = 0;
+    // profiling
+    bool profiling = false;
+    struct ProfItem {
+        int kind;
+        double flops;
+        int tiles;
+    };
+    std::vector<void*> prof_ev;          // two events per item
+    std::vector<ProfItem> prof_items;
+    gadj_profile prof{};
+    uint64_t launch_count = 0;
+
+    void prof_begin(int kind, double flops = 0, int tiles = 0)
+    {
+        launch_count++;
+        if (!profiling)
+            return;
+        size_t i = prof_items.size();
+        while (prof_ev.size() < 2 * (i + 1))
+            prof_ev.push_back(dev::event_create());
+        prof_items.push_back({kind, flops, tiles});
+        dev::event_record(prof_ev[2 * i]);
+    }
+    void prof_end()
+    {
+        if (!profiling)
+            return;
+        dev::event_record(prof_ev[2 * (prof_items.size() - 1) + 1]);
+    }
 
     int fail(const std::string& m)
     {
@@ -216,6 +245,9 @@ void run_launches(gadj_ctx* c, const std::vector<Launch>& list)
 {
     void* st = dev::stream();
     for (const Launch& L : list) {
+        c->prof_begin(L.kind, L.flops, L.total_tiles);
+        if (L.kind == L_ZERO)
+            c->launch_count--;  // a memset, not one of our kernels
         switch (L.kind) {
         case L_GEMM:
             launch_gemm(c->d_gemm.p + L.op_begin, L.op_count, L.total_tiles, st);
@@ -245,8 +277,11 @@ void run_launches(gadj_ctx* c, const std::vector<Launch>& list)
             dev::zero(L.zero_ptr, L.zero_bytes);
             break;
         }
+        c->prof_end();
     }
 }
+
+enum { PK_ASSEMBLE = 100, PK_OTHER = 101 };
 
 // FormConstraintStationVarianceMatrix (ADJ:2041-2137): inverse-variance block, row-major
 bool constraint_block(const gadj_ctx* c, const dna_stn_t& s, double* out)
@@ -478,6 +513,8 @@ void gadj_destroy(gadj_ctx* c)
     for (auto& e : c->ev)
         if (e)
             dev::event_destroy(e);
+    for (auto& e : c->prof_ev)
+        dev::event_destroy(e);
     delete c;
 }
 
@@ -774,11 +811,15 @@ int gadj_iterate(gadj_ctx* c, int flags, gadj_iter_result* res)
     bool normals = (flags & GADJ_ITER_NORMALS) || !c->factor_valid;
     dev::event_record(c->ev[0]);
     // ---- assembly (FillDesignNormalMeasurementsMatrices, ADJ:3888) --------------
+    c->prof_begin(PK_ASSEMBLE);
     launch_init_normals(normals ? c->d_cblock.p : nullptr, c->d_ndiag.p, c->d_noff.p, c->d_w.p, c->nstn,
                         normals ? c->nedge : 0, st);
+    c->prof_end();
     AssembleParams ap;
     fill_assemble(c, ap, normals ? 1 : 0);
+    c->prof_begin(PK_ASSEMBLE);
     launch_assemble_g(ap, st);
+    c->prof_end();
     dev::event_record(c->ev[1]);
     // ---- factorisation (Solve: dpotrf, ADJ:6628) --------------------------------
     if (normals) {
@@ -786,19 +827,31 @@ int gadj_iterate(gadj_ctx* c, int flags, gadj_iter_result* res)
         c->factor_valid = false;
         ScatterParams sp;
         fill_scatter(c, sp);
+        c->prof_begin(PK_OTHER);
         launch_compute_scale(sp, st);
+        c->prof_end();
+        c->prof_begin(L_ZERO);
+        c->launch_count--;
         dev::zero(c->d_panels.p, c->d_panels.bytes());
         dev::zero(c->d_info.p, c->d_info.bytes());
+        c->prof_end();
+        c->prof_begin(PK_OTHER);
         launch_scatter_normals(sp, st);
+        c->prof_end();
         run_launches(c, c->plan.factor);
         c->normals_valid = true;
     }
     dev::event_record(c->ev[2]);
     // ---- solve + estimates update (ADJ:6659-6667, ADJ:2463-2466) -----------------
+    c->prof_begin(PK_OTHER);
     launch_permute_rhs(c->d_w.p, c->d_dscale.p, c->d_pos.p, c->d_x.p, c->nstn, st);
+    c->prof_end();
     run_launches(c, c->plan.fwd);
     run_launches(c, c->plan.bwd);
+    c->prof_begin(PK_OTHER);
+    c->launch_count++;  // two kernels: update + max reduction
     launch_apply_corrections(c->d_x.p, c->d_dscale.p, c->d_pos.p, c->d_corr.p, c->d_est.p, c->nstn, st);
+    c->prof_end();
     dev::event_record(c->ev[3]);
     if (flags & GADJ_ITER_INVERSE) {
         run_launches(c, c->plan.selinv);
@@ -1051,6 +1104,65 @@ int gadj_get_rhs(gadj_ctx* c, double* w)
     dev::d2h(w, c->d_w.p, c->d_w.bytes());
     std::string e = dev::sync();
     return e.empty() ? 0 : c->fail(e);
+}
+
+int gadj_profile_enable(gadj_ctx* c, int on)
+{
+    c->profiling = on != 0;
+    return 0;
+}
+
+int gadj_profile_read(gadj_ctx* c, gadj_profile* out, int reset)
+{
+    std::string e = dev::sync();
+    if (!e.empty())
+        return c->fail(e);
+    for (size_t i = 0; i < c->prof_items.size(); ++i) {
+        double ms = dev::event_elapsed_ms(c->prof_ev[2 * i], c->prof_ev[2 * i + 1]);
+        const auto& it = c->prof_items[i];
+        switch (it.kind) {
+        case L_GEMM:
+            c->prof.ms_gemm += ms;
+            c->prof.flops_gemm += it.flops;
+            c->prof.gemm_launches++;
+            c->prof.gemm_tiles += (uint64_t)it.tiles;
+            break;
+        case L_DIAG:
+            c->prof.ms_diag += ms;
+            break;
+        case L_TRI_FWD:
+        case L_TRI_BWD:
+            c->prof.ms_tri += ms;
+            break;
+        case L_GEMV_FWD:
+        case L_GEMV_BWD:
+            c->prof.ms_gemv += ms;
+            break;
+        case L_TRANSPOSE:
+            c->prof.ms_transpose += ms;
+            break;
+        case L_GATHER:
+            c->prof.ms_gather += ms;
+            break;
+        case L_ZERO:
+            c->prof.ms_zero += ms;
+            break;
+        case PK_ASSEMBLE:
+            c->prof.ms_assemble += ms;
+            break;
+        default:
+            c->prof.ms_other += ms;
+        }
+    }
+    c->prof_items.clear();
+    c->prof.launches = c->launch_count;
+    if (out)
+        *out = c->prof;
+    if (reset) {
+        c->prof = gadj_profile{};
+        c->launch_count = 0;
+    }
+    return 0;
 }
 
 int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int M, int N, int K, int reps, float* ms)

@@ -47,11 +47,18 @@ class GadjInfo(C.Structure):
                 ("launches_inverse", C.c_uint64), ("max_front_rows", C.c_uint32), ("max_front_cols", C.c_uint32)]
 
 
+class GadjProfile(C.Structure):
+    _fields_ = [("ms_gemm", C.c_double), ("ms_diag", C.c_double), ("ms_tri", C.c_double), ("ms_gemv", C.c_double),
+                ("ms_transpose", C.c_double), ("ms_gather", C.c_double), ("ms_zero", C.c_double),
+                ("ms_assemble", C.c_double), ("ms_other", C.c_double), ("flops_gemm", C.c_double),
+                ("launches", C.c_uint64), ("gemm_launches", C.c_uint64), ("gemm_tiles", C.c_uint64)]
+
+
 EXPORTS = ["gadj_default_opts", "gadj_create", "gadj_destroy", "gadj_last_error", "gadj_set_stations",
            "gadj_set_measurements", "gadj_set_blocks", "gadj_prepare", "gadj_get_info", "gadj_upload_measurements",
            "gadj_reset_estimates", "gadj_iterate", "gadj_adjust", "gadj_statistics", "gadj_get_estimates",
            "gadj_get_corrections", "gadj_get_station_vcvs", "gadj_get_station_vcv", "gadj_get_vcv_block",
-           "gadj_get_normals_block", "gadj_get_rhs", "gadj_test_gemm"]
+           "gadj_get_normals_block", "gadj_get_rhs", "gadj_profile_enable", "gadj_profile_read", "gadj_test_gemm"]
 
 _libs = {}
 
@@ -87,6 +94,8 @@ def load_library(path=None):
     L.gadj_get_vcv_block.argtypes = [vp, u32, u32, vp]
     L.gadj_get_normals_block.argtypes = [vp, u32, u32, vp]
     L.gadj_get_rhs.argtypes = [vp, vp]
+    L.gadj_profile_enable.argtypes = [vp, i32]
+    L.gadj_profile_read.argtypes = [vp, C.POINTER(GadjProfile), i32]
     L.gadj_test_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, C.POINTER(C.c_float)]
     _libs[path] = L
     return L
@@ -224,6 +233,14 @@ class Adjustment:
         out = np.zeros((len(self.stn), 3))
         self._check(self.L.gadj_get_rhs(self.h, self._p(out)))
         return out
+
+    def profile_enable(self, on=True):
+        self._check(self.L.gadj_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self, reset=True):
+        p = GadjProfile()
+        self._check(self.L.gadj_profile_read(self.h, C.byref(p), 1 if reset else 0))
+        return p
 
     def test_gemm(self, A, B, reps=1):
         A = np.ascontiguousarray(A, dtype=np.float64)

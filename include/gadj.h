@@ -96,6 +96,16 @@ typedef struct gadj_info {
     uint32_t max_front_rows, max_front_cols;
 } gadj_info;
 
+/* per-kernel-family device time (CUDA events around every launch) accumulated since the last reset */
+typedef struct gadj_profile {
+    double ms_gemm, ms_diag, ms_tri, ms_gemv, ms_transpose, ms_gather, ms_zero;
+    double ms_assemble;            /* init + assembly kernels */
+    double ms_other;               /* scale/scatter/permute/update kernels */
+    double flops_gemm;             /* algorithmic flops of the tile-GEMM launches */
+    uint64_t launches;             /* kernel launches of this library (memsets excluded) */
+    uint64_t gemm_launches, gemm_tiles;
+} gadj_profile;
+
 void gadj_default_opts(gadj_opts* o);
 int gadj_create(const gadj_opts* o, gadj_ctx** out);
 void gadj_destroy(gadj_ctx* c);
@@ -131,6 +141,10 @@ int gadj_get_vcv_block(gadj_ctx* c, uint32_t si, uint32_t sj, double q[9]);
 /* assembled normals (constraints included) of the last iterate call that built them, and its right-hand side */
 int gadj_get_normals_block(gadj_ctx* c, uint32_t si, uint32_t sj, double n[9]);
 int gadj_get_rhs(gadj_ctx* c, double* w /* 3*nstn */);
+
+/* optional per-launch timing; small overhead (two event records per launch) */
+int gadj_profile_enable(gadj_ctx* c, int on);
+int gadj_profile_read(gadj_ctx* c, gadj_profile* out, int reset);
 
 /* FP64 GEMM self-test / micro-benchmark of the tensor-core tile kernel: C = A * B^T (row-major host arrays).
  * returns device milliseconds per call in *ms (averaged over reps) */
