@@ -1117,9 +1117,14 @@ int gadj_profile_read(gadj_ctx* c, gadj_profile* out, int reset)
     std::string e = dev::sync();
     if (!e.empty())
         return c->fail(e);
+    FILE* dump = nullptr;
+    if (const char* dp = getenv("GADJ_PROFILE_DUMP"))
+        dump = fopen(dp, "a");
     for (size_t i = 0; i < c->prof_items.size(); ++i) {
         double ms = dev::event_elapsed_ms(c->prof_ev[2 * i], c->prof_ev[2 * i + 1]);
         const auto& it = c->prof_items[i];
+        if (dump)
+            fprintf(dump, "%zu,%d,%.6g,%d,%.6f\n", i, it.kind, it.flops, it.tiles, ms);
         switch (it.kind) {
         case L_GEMM:
             c->prof.ms_gemm += ms;
@@ -1154,6 +1159,8 @@ int gadj_profile_read(gadj_ctx* c, gadj_profile* out, int reset)
             c->prof.ms_other += ms;
         }
     }
+    if (dump)
+        fclose(dump);
     c->prof_items.clear();
     c->prof.launches = c->launch_count;
     if (out)
