@@ -268,10 +268,10 @@ void run_launches(gadj_ctx* c, const std::vector<Launch>& list)
             launch_gemv(c->d_gemv.p + L.op_begin, L.op_count, c->d_x.p, c->d_x.p, 1, st);
             break;
         case L_TRANSPOSE:
-            launch_transpose(c->d_tr.p + L.op_begin, L.op_count, st);
+            launch_transpose(c->d_tr.p + L.op_begin, L.op_count, L.total_tiles, st);
             break;
         case L_GATHER:
-            launch_gather(c->d_gather.p + L.op_begin, L.op_count, st);
+            launch_gather(c->d_gather.p + L.op_begin, L.op_count, L.total_tiles, st);
             break;
         case L_ZERO:
             dev::zero(L.zero_ptr, L.zero_bytes);
@@ -1178,7 +1178,8 @@ int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int
         return c->fail("gadj_test_gemm: M, N, K must be positive and K even");
     DevArray<double> dA, dB, dC;
     DevArray<GemmOp> dop;
-    if (!dA.resize((size_t)M * K) || !dB.resize((size_t)N * K) || !dC.resize((size_t)M * N) || !dop.resize(1))
+    const int ldc = N + (N & 1);
+    if (!dA.resize((size_t)M * K) || !dB.resize((size_t)N * K) || !dC.resize((size_t)M * ldc) || !dop.resize(1))
         return c->fail("out of device memory");
     dev::h2d(dA.p, A, dA.bytes());
     dev::h2d(dB.p, B, dB.bytes());
@@ -1189,7 +1190,7 @@ int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int
     op.C = dC.p;
     op.lda = K;
     op.ldb = K;
-    op.ldc = N;
+    op.ldc = ldc;
     op.M = M;
     op.N = N;
     op.K = K;
@@ -1210,10 +1211,13 @@ int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int
     for (int i = 0; i < reps; ++i)
         launch_gemm(dop.p, 1, op.tiles_m * op.tiles_n, dev::stream());
     dev::event_record(c->ev[1]);
-    dev::d2h(C, dC.p, dC.bytes());
+    std::vector<double> hc((size_t)M * ldc);
+    dev::d2h(hc.data(), dC.p, dC.bytes());
     e = dev::sync();
     if (!e.empty())
         return c->fail(e);
+    for (int i = 0; i < M; ++i)
+        std::memcpy(C + (size_t)i * N, hc.data() + (size_t)i * ldc, (size_t)N * sizeof(double));
     if (ms)
         *ms = dev::event_elapsed_ms(c->ev[0], c->ev[1]) / (float)reps;
     return 0;

@@ -29,6 +29,9 @@ enum GemmFlags : int32_t {
     GEMM_ACCUM = 1,     // C += alpha*A*B^T   (else C = alpha*A*B^T)
     GEMM_NEG = 2,       // alpha = -1         (else +1)
     GEMM_LOWER = 4,     // keep only elements with (i + tri_off) >= j; tiles wholly above are skipped
+    GEMM_KLO_ROW = 16,  // A is upper triangular (zero for k < row): start the K loop at the tile's first row
+    GEMM_KLO_MAX = 32,  // A and B upper triangular: start the K loop at max(first row, first column) of the tile
+    GEMM_KHI_ROW = 64,  // A is lower triangular (zero for k > row): end the K loop after the tile's last row
     GEMM_SCATTER = 8,   // C is the base of a target panel; element (i, j) lands at row 3*rowmap[i/3]+i%3,
                         // column 3*rowmap[j/3]+j%3 (station-level map), added atomically
 };
@@ -109,8 +112,9 @@ void launch_gemm(const GemmOp* ops, int nops, int total_tiles, void* stream);
 void launch_diag(const DiagOp* ops, int nops, int* info, void* stream);
 void launch_tri(const TriOp* ops, int nops, int backward, void* stream);
 void launch_gemv(const GemvOp* ops, int nops, const double* x_ro, double* x, int backward, void* stream);
-void launch_transpose(const TransposeOp* ops, int nops, void* stream);
-void launch_gather(const GatherOp* ops, int nops, void* stream);
+// grid_x: CTAs per op (each op loops over its tiles); the planner passes min(cap, largest tile count)
+void launch_transpose(const TransposeOp* ops, int nops, int grid_x, void* stream);
+void launch_gather(const GatherOp* ops, int nops, int grid_x, void* stream);
 
 // ---- assembly -----------------------------------------------------------------
 struct AssembleParams {

@@ -194,25 +194,52 @@ __global__ void __launch_bounds__(256) transpose_kernel(const TransposeOp* __res
 }
 
 // ---- selected-inverse gather ---------------------------------------------------------------
+// 16 x 16-station tiles (48 x 48 doubles) staged through shared memory so that both the lower block
+// and its mirror image are written with coalesced rows.
+constexpr int GT = 16;            // stations per tile edge
+constexpr int GE = 3 * GT;        // doubles per tile edge
 __global__ void __launch_bounds__(256) gather_kernel(const GatherOp* __restrict__ ops)
 {
+    __shared__ double T[GE][GE + 1];
     const GatherOp op = ops[blockIdx.y];
     const int ni = op.nb - op.jb, nj = op.je - op.jb;
-    const int64_t total = (int64_t)ni * nj;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int ii = (int)(idx / nj), jj = (int)(idx - (int64_t)ii * nj);
-        if (jj > ii)
-            continue;
-        const int i = op.jb + ii, j = op.jb + jj;
-        const int64_t zr = 3ll * op.rowmap[ii], zc = 3ll * op.rowmap[jj];
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                double v = (ii == jj && a < b) ? op.Z[(zr + b) * op.ld + zc + a] : op.Z[(zr + a) * op.ld + zc + b];
-                op.G[(3ll * i + a) * op.ldg + 3 * j + b] = v;
-                op.G[(3ll * j + b) * op.ldg + 3 * i + a] = v;
+    const int ti_n = (ni + GT - 1) / GT, tj_n = (nj + GT - 1) / GT;
+    for (int tl = blockIdx.x; tl < ti_n * tj_n; tl += gridDim.x) {
+        const int ti = tl / tj_n, tj = tl - ti * tj_n;
+        const int i0 = ti * GT, j0 = tj * GT;            // station offsets relative to jb
+        if (i0 + GT - 1 < j0)
+            continue;                                    // tile wholly above the diagonal (uniform per block)
+        for (int e = threadIdx.x; e < GE * GE; e += 256) {
+            const int ar = e / GE, bc = e - ar * GE;
+            const int ii = i0 + ar / 3, jj = j0 + bc / 3;
+            int a = ar % 3, b = bc % 3;
+            double v = 0.0;
+            if (ii < ni && jj < nj && jj <= ii) {
+                if (ii == jj && a < b) {
+                    const int t = a;
+                    a = b;
+                    b = t;
+                }
+                v = op.Z[(3ll * op.rowmap[ii] + a) * op.ld + 3ll * op.rowmap[jj] + b];
             }
+            T[ar][bc] = v;
+        }
+        __syncthreads();
+        // lower part: rows of G along i, contiguous along j
+        for (int e = threadIdx.x; e < GE * GE; e += 256) {
+            const int ar = e / GE, bc = e - ar * GE;
+            const int ii = i0 + ar / 3, jj = j0 + bc / 3;
+            if (ii < ni && jj < nj && jj <= ii)
+                op.G[(3ll * (op.jb + ii) + ar % 3) * op.ldg + 3 * (op.jb + jj) + bc % 3] = T[ar][bc];
+        }
+        // mirror: rows of G along j, contiguous along i
+        for (int e = threadIdx.x; e < GE * GE; e += 256) {
+            const int bc = e / GE, ar = e - bc * GE;
+            const int ii = i0 + ar / 3, jj = j0 + bc / 3;
+            if (ii < ni && jj < nj && jj <= ii)
+                op.G[(3ll * (op.jb + jj) + bc % 3) * op.ldg + 3 * (op.jb + ii) + ar % 3] = T[ar][bc];
+        }
+        __syncthreads();
     }
 }
 
@@ -256,23 +283,23 @@ void launch_gemv(const GemvOp* ops, int nops, const double* x_ro, double* x, int
         gemv_fwd_kernel<<<nops, 256, 0, (cudaStream_t)stream>>>(ops, x);
 }
 
-void launch_transpose(const TransposeOp* ops, int nops, void* stream)
+void launch_transpose(const TransposeOp* ops, int nops, int grid_x, void* stream)
 {
     if (nops <= 0)
         return;
     for (int o = 0; o < nops; o += 65535) {
         int n = nops - o < 65535 ? nops - o : 65535;
-        transpose_kernel<<<dim3(148, n), 256, 0, (cudaStream_t)stream>>>(ops + o);
+        transpose_kernel<<<dim3(grid_x < 1 ? 1 : (grid_x > 592 ? 592 : grid_x), n), 256, 0, (cudaStream_t)stream>>>(ops + o);
     }
 }
 
-void launch_gather(const GatherOp* ops, int nops, void* stream)
+void launch_gather(const GatherOp* ops, int nops, int grid_x, void* stream)
 {
     if (nops <= 0)
         return;
     for (int o = 0; o < nops; o += 65535) {
         int n = nops - o < 65535 ? nops - o : 65535;
-        gather_kernel<<<dim3(64, n), 256, 0, (cudaStream_t)stream>>>(ops + o);
+        gather_kernel<<<dim3(grid_x < 1 ? 1 : (grid_x > 592 ? 592 : grid_x), n), 256, 0, (cudaStream_t)stream>>>(ops + o);
     }
 }
 

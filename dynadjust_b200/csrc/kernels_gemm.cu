@@ -106,7 +106,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp
     const int flags = op->flags, tri_off = op->tri_off;
     if ((flags & GEMM_LOWER) && row0 + (TILE_M - 1) + tri_off < col0)
         return;  // the whole tile lies above the diagonal
-    const int nk = (K + TILE_K - 1) / TILE_K;
+    // K range of this tile (triangular operands carry explicit zeros outside it)
+    int k_lo = 0, k_hi = K;
+    if (flags & GEMM_KLO_ROW)
+        k_lo = row0;
+    if (flags & GEMM_KLO_MAX)
+        k_lo = row0 > col0 ? row0 : col0;
+    if (flags & GEMM_KHI_ROW)
+        k_hi = (row0 + TILE_M < K) ? row0 + TILE_M : K;
+    const int kc0 = k_lo / TILE_K;
+    const int nk = k_hi > k_lo ? (k_hi + TILE_K - 1) / TILE_K - kc0 : 0;
 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_full = base + STAGES * STAGE_BYTES;
@@ -135,8 +144,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp
                     mbar_wait(bar_empty + 8 * s, ((kc / STAGES) - 1) & 1);
                 const uint32_t sa = base + s * STAGE_BYTES;
                 mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
-                tma_load_2d(sa, tmA, kc * TILE_K, row0, bar_full + 8 * s);
-                tma_load_2d(sa + A_TILE_BYTES, tmB, kc * TILE_K, col0, bar_full + 8 * s);
+                tma_load_2d(sa, tmA, (kc0 + kc) * TILE_K, row0, bar_full + 8 * s);
+                tma_load_2d(sa + A_TILE_BYTES, tmB, (kc0 + kc) * TILE_K, col0, bar_full + 8 * s);
             }
         }
         return;
@@ -179,7 +188,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp
             const double* __restrict__ gB = op->B;
             for (int idx = threadIdx.x; idx < TILE_M * TILE_K; idx += CONSUMER_WARPS * 32) {
                 const int r = idx / TILE_K, k = idx - r * TILE_K;
-                const int gk = kc * TILE_K + k;
+                const int gk = (kc0 + kc) * TILE_K + k;
                 const uint32_t off = (uint32_t)r * 128u + ((uint32_t)((k >> 1) ^ (r & 7)) << 4) + ((uint32_t)(k & 1) << 3);
                 const double va = (row0 + r < M && gk < K) ? gA[(int64_t)(row0 + r) * op->lda + gk] : 0.0;
                 const double vb = (col0 + r < N && gk < K) ? gB[(int64_t)(col0 + r) * op->ldb + gk] : 0.0;
@@ -237,6 +246,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp
         }
     } else {
         const bool accum = (flags & GEMM_ACCUM) != 0;
+        // fragments j = 2p and 2p+1 interleave: together a thread owns 4 consecutive columns
+        // c0 .. c0+3 = {acc[i][2p][0], acc[i][2p+1][0], acc[i][2p][1], acc[i][2p+1][1]} -> two 16-byte accesses
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int r = row0 + wm + 16 * (i >> 1) + 2 * g + (i & 1);
@@ -244,15 +255,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp
                 continue;
             double* __restrict__ crow = C + (int64_t)r * ldc;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int p = 0; p < 2; ++p) {
+                const int c0 = col0 + wn + 16 * p + 4 * t;
+                double v[4] = {alpha * acc[i][2 * p][0], alpha * acc[i][2 * p + 1][0], alpha * acc[i][2 * p][1],
+                               alpha * acc[i][2 * p + 1][1]};
+                if (c0 + 3 < N && (!lower || r + tri_off >= c0 + 3)) {
+                    double2* q = reinterpret_cast<double2*>(crow + c0);
+                    if (accum) {
+                        const double2 o0 = q[0], o1 = q[1];
+                        v[0] += o0.x;
+                        v[1] += o0.y;
+                        v[2] += o1.x;
+                        v[3] += o1.y;
+                    }
+                    q[0] = make_double2(v[0], v[1]);
+                    q[1] = make_double2(v[2], v[3]);
+                } else {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int c = col0 + wn + 16 * (j >> 1) + 2 * (2 * t + e) + (j & 1);
-                    if (c >= N || (lower && r + tri_off < c))
-                        continue;
-                    const double v = alpha * acc[i][j][e];
-                    crow[c] = accum ? crow[c] + v : v;
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = c0 + e;
+                        if (c >= N || (lower && r + tri_off < c))
+                            continue;
+                        crow[c] = accum ? crow[c] + v[e] : v[e];
+                    }
                 }
+            }
         }
     }
 }

@@ -102,9 +102,18 @@ struct Builder {
         for (GemmOp& op : batch) {
             op.tile_begin = tiles;
             tiles += op.tiles_m * op.tiles_n;
-            double fl = 2.0 * op.M * (double)op.N * op.K;
-            if (op.flags & GEMM_LOWER)
+            // useful flops: lower-only outputs drop the strict upper triangle of the leading square;
+            // triangular operands halve the K range over that square
+            double M = op.M, N = op.N, K = op.K;
+            double fl = 2.0 * M * N * K;
+            if (op.flags & GEMM_LOWER) {
+                double sq = std::min(M, N);
+                fl -= sq * sq * K;
+            }
+            if (op.flags & (GEMM_KLO_ROW | GEMM_KHI_ROW))
                 fl *= 0.5;
+            if (op.flags & GEMM_KLO_MAX)
+                fl = 2.0 * M * M * M / 6.0 * (op.flags & GEMM_LOWER ? 1.0 : 2.0);
             L.flops += fl;
             if (!dev::encode_tma_2d(&op.tmA, op.A, (uint64_t)op.M, (uint64_t)op.K, (uint64_t)op.lda, TILE_M) ||
                 !dev::encode_tma_2d(&op.tmB, op.B, (uint64_t)op.N, (uint64_t)op.K, (uint64_t)op.ldb, TILE_N))
@@ -143,9 +152,31 @@ struct Builder {
         L.op_begin = (int64_t)store.size();
         L.op_count = (int32_t)batch.size();
         L.level = level;
+        L.total_tiles = tiles_hint(batch);
         store.insert(store.end(), batch.begin(), batch.end());
         out.push_back(L);
         batch.clear();
+    }
+
+    // CTAs per op for the looping helper kernels = the largest per-op tile count of the batch
+    static int tiles_hint(const std::vector<TransposeOp>& b)
+    {
+        int t = 1;
+        for (auto& o : b)
+            t = std::max(t, cdiv(o.rows, 32) * cdiv(o.cols, 32));
+        return t;
+    }
+    static int tiles_hint(const std::vector<GatherOp>& b)
+    {
+        int t = 1;
+        for (auto& o : b)
+            t = std::max(t, cdiv(o.nb - o.jb, 16) * cdiv(o.je - o.jb, 16));
+        return t;
+    }
+    template <class Op>
+    static int tiles_hint(const std::vector<Op>&)
+    {
+        return 0;
     }
 
     // ---- numeric factorisation ------------------------------------------------
@@ -158,8 +189,27 @@ struct Builder {
             int nsteps = 0;
             for (uint32_t f : fl)
                 nsteps = std::max(nsteps, cdiv((int)s.fronts[f].k, NB));
+            // Levels with enough fronts to fill the GPU from one block column per front run left-looking
+            // (each block column is updated once, from all columns to its left, K = jb: half the panel traffic
+            // and long K loops); sparse top levels run right-looking (2-D tile parallelism inside few big fronts).
+            size_t row_tiles = 0;
+            for (uint32_t f : fl)
+                row_tiles += (size_t)cdiv((int)s.fronts[f].m, TILE_M);
+            const bool left = row_tiles >= 2 * 148;
             for (int j = 0; j < nsteps; ++j) {
                 const int jb = j * NB;
+                if (left && jb > 0) {
+                    for (size_t i = 0; i < fl.size(); ++i) {
+                        const Front& f = s.fronts[fl[i]];
+                        if (jb >= (int)f.k)
+                            continue;
+                        int w = std::min<int>(NB, (int)f.k - jb);
+                        double* A = panel(f) + (size_t)jb * f.ldk;
+                        add_gemm(gb, A, f.ldk, A, f.ldk, A + jb, f.ldk, (int)f.m - jb, w, jb,
+                                 GEMM_ACCUM | GEMM_NEG | GEMM_LOWER);
+                    }
+                    flush_gemm(gb, p.factor, (int)lv);
+                }
                 // pivot tiles
                 for (size_t i = 0; i < fl.size(); ++i) {
                     const Front& f = s.fronts[fl[i]];
@@ -186,6 +236,8 @@ struct Builder {
                     add_gemm(gb, A, f.ldk, b.pool + i * (size_t)NB * NB, NB, A, f.ldk, (int)f.m - (jb + w), w, w, 0);
                 }
                 flush_gemm(gb, p.factor, (int)lv);
+                if (left)
+                    continue;
                 // trailing update inside the panel (columns still to be factorised)
                 for (size_t i = 0; i < fl.size(); ++i) {
                     const Front& f = s.fronts[fl[i]];
@@ -301,14 +353,9 @@ struct Builder {
         std::vector<DiagOp> db;
         std::vector<TransposeOp> trb;
         std::vector<GatherOp> gab;
-        {
-            Launch Z{};
-            Z.kind = L_ZERO;
-            Z.zero_ptr = b.pool;
-            Z.zero_bytes = used * sizeof(double);
-            Z.level = level;
-            p.selinv.push_back(Z);
-        }
+        // no clearing of the workspace: every tile that is read has been written before (the K-range
+        // flags keep the triangular products inside the written tiles)
+        (void)used;
         int maxtiles = 0;
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];
@@ -348,7 +395,7 @@ struct Builder {
                          ws + w.Tt, w.ldt, wj, below, wj, 0);
                 // W[below, jb:jb+wj] = -W[below, below] * Tt^T
                 add_gemm(gbb, ws + w.W + (size_t)(jb + wj) * w.ldw + (jb + wj), w.ldw, ws + w.Tt, w.ldt,
-                         ws + w.W + (size_t)(jb + wj) * w.ldw + jb, w.ldw, below, wj, below, GEMM_NEG);
+                         ws + w.W + (size_t)(jb + wj) * w.ldw + jb, w.ldw, below, wj, below, GEMM_NEG | GEMM_KHI_ROW);
             }
             flush_gemm(ga, p.selinv, level);
             flush_gemm(gbb, p.selinv, level);
@@ -391,7 +438,7 @@ struct Builder {
             SelinvWs w = ws_layout(f);
             double* ws = b.pool + base[i];
             add_gemm(gb, ws + w.Wt, w.ldw, panel(f) + (size_t)f.k * f.ldk, f.ldk, ws + w.Yt, w.ldr, (int)f.k, (int)f.r,
-                     (int)f.k, 0);
+                     (int)f.k, GEMM_KLO_ROW);
         }
         flush_gemm(gb, p.selinv, level);
         // Z21 = -G * Y   (overwrites L21)
@@ -426,7 +473,8 @@ struct Builder {
             const Front& f = s.fronts[chunk[i]];
             SelinvWs w = ws_layout(f);
             double* ws = b.pool + base[i];
-            add_gemm(gb, ws + w.Wt, w.ldw, ws + w.Wt, w.ldw, panel(f), f.ldk, (int)f.k, (int)f.k, (int)f.k, GEMM_LOWER);
+            add_gemm(gb, ws + w.Wt, w.ldw, ws + w.Wt, w.ldw, panel(f), f.ldk, (int)f.k, (int)f.k, (int)f.k,
+                     GEMM_LOWER | GEMM_KLO_MAX);
         }
         flush_gemm(gb, p.selinv, level);
         // Z11 -= Yt * Z21t^T

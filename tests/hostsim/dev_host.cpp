@@ -14,7 +14,14 @@ namespace dev {
 std::string init(int) { return std::string(); }
 bool is_cuda() { return false; }
 void* stream() { return nullptr; }
-void* alloc(size_t bytes) { return std::calloc(1, bytes ? bytes : 1); }
+void* alloc(size_t bytes)
+{
+    // poison fresh device memory with NaNs: a read of anything the engine has not written shows up in the results
+    void* p = std::malloc(bytes ? bytes : 1);
+    if (p)
+        std::memset(p, 0xFF, bytes ? bytes : 1);
+    return p;
+}
 void free_(void* p) { std::free(p); }
 void* alloc_host_pinned(size_t bytes) { return std::malloc(bytes); }
 void free_host_pinned(void* p) { std::free(p); }

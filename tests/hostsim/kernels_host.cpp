@@ -22,7 +22,17 @@ void launch_gemm(const GemmOp* ops, int nops, int, void*)
                 double acc = 0.0;
                 const double* a = op.A + (int64_t)i * op.lda;
                 const double* b = op.B + (int64_t)j * op.ldb;
-                for (int k = 0; k < op.K; ++k)
+                // the kernel's per-tile K range (triangular operands): nothing outside it may be read
+                const int row0 = (i / TILE_M) * TILE_M, col0 = (j / TILE_N) * TILE_N;
+                int k_lo = 0, k_hi = op.K;
+                if (op.flags & GEMM_KLO_ROW)
+                    k_lo = row0;
+                if (op.flags & GEMM_KLO_MAX)
+                    k_lo = row0 > col0 ? row0 : col0;
+                if (op.flags & GEMM_KHI_ROW)
+                    k_hi = row0 + TILE_M < op.K ? row0 + TILE_M : op.K;
+                k_lo = (k_lo / TILE_K) * TILE_K;
+                for (int k = k_lo; k < k_hi; ++k)
                     acc += a[k] * b[k];
                 row[j] = (op.flags & GEMM_NEG) ? -acc : acc;
             }
@@ -139,7 +149,7 @@ void launch_gemv(const GemvOp* ops, int nops, const double* x_ro, double* x, int
     }
 }
 
-void launch_transpose(const TransposeOp* ops, int nops, void*)
+void launch_transpose(const TransposeOp* ops, int nops, int, void*)
 {
     for (int o = 0; o < nops; ++o) {
         const TransposeOp& op = ops[o];
@@ -149,7 +159,7 @@ void launch_transpose(const TransposeOp* ops, int nops, void*)
     }
 }
 
-void launch_gather(const GatherOp* ops, int nops, void*)
+void launch_gather(const GatherOp* ops, int nops, int, void*)
 {
     for (int o = 0; o < nops; ++o) {
         const GatherOp& op = ops[o];
