@@ -208,13 +208,14 @@ struct gadj_ctx {
         int kind;
         double flops;
         int tiles;
+        int tag, level;
     };
     std::vector<void*> prof_ev;          // two events per item
     std::vector<ProfItem> prof_items;
     gadj_profile prof{};
     uint64_t launch_count = 0;
 
-    void prof_begin(int kind, double flops = 0, int tiles = 0)
+    void prof_begin(int kind, double flops = 0, int tiles = 0, int tag = 0, int level = -1)
     {
         launch_count++;
         if (!profiling)
@@ -222,7 +223,7 @@ struct gadj_ctx {
         size_t i = prof_items.size();
         while (prof_ev.size() < 2 * (i + 1))
             prof_ev.push_back(dev::event_create());
-        prof_items.push_back({kind, flops, tiles});
+        prof_items.push_back({kind, flops, tiles, tag, level});
         dev::event_record(prof_ev[2 * i]);
     }
     void prof_end()
@@ -245,7 +246,7 @@ void run_launches(gadj_ctx* c, const std::vector<Launch>& list)
 {
     void* st = dev::stream();
     for (const Launch& L : list) {
-        c->prof_begin(L.kind, L.flops, L.total_tiles);
+        c->prof_begin(L.kind, L.flops, L.total_tiles, L.tag, L.level);
         if (L.kind == L_ZERO)
             c->launch_count--;  // a memset, not one of our kernels
         switch (L.kind) {
@@ -1124,7 +1125,7 @@ int gadj_profile_read(gadj_ctx* c, gadj_profile* out, int reset)
         double ms = dev::event_elapsed_ms(c->prof_ev[2 * i], c->prof_ev[2 * i + 1]);
         const auto& it = c->prof_items[i];
         if (dump)
-            fprintf(dump, "%zu,%d,%.6g,%d,%.6f\n", i, it.kind, it.flops, it.tiles, ms);
+            fprintf(dump, "%zu,%d,%.6g,%d,%.6f,%d,%d\n", i, it.kind, it.flops, it.tiles, ms, it.tag, it.level);
         switch (it.kind) {
         case L_GEMM:
             c->prof.ms_gemm += ms;

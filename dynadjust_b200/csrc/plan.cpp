@@ -89,12 +89,13 @@ struct Builder {
     }
 
     // appends a batch as one launch; assigns tile ranges and encodes the tensor maps
-    void flush_gemm(std::vector<GemmOp>& batch, std::vector<Launch>& out, int level)
+    void flush_gemm(std::vector<GemmOp>& batch, std::vector<Launch>& out, int level, int tag = T_NONE)
     {
         if (batch.empty())
             return;
         Launch L{};
         L.kind = L_GEMM;
+        L.tag = tag;
         L.op_begin = (int64_t)p.gemm.size();
         L.op_count = (int32_t)batch.size();
         L.level = level;
@@ -208,7 +209,7 @@ struct Builder {
                         add_gemm(gb, A, f.ldk, A, f.ldk, A + jb, f.ldk, (int)f.m - jb, w, jb,
                                  GEMM_ACCUM | GEMM_NEG | GEMM_LOWER);
                     }
-                    flush_gemm(gb, p.factor, (int)lv);
+                    flush_gemm(gb, p.factor, (int)lv, T_LEFT_UPDATE);
                 }
                 // pivot tiles
                 for (size_t i = 0; i < fl.size(); ++i) {
@@ -235,7 +236,7 @@ struct Builder {
                     double* A = panel(f) + (size_t)(jb + w) * f.ldk + jb;
                     add_gemm(gb, A, f.ldk, b.pool + i * (size_t)NB * NB, NB, A, f.ldk, (int)f.m - (jb + w), w, w, 0);
                 }
-                flush_gemm(gb, p.factor, (int)lv);
+                flush_gemm(gb, p.factor, (int)lv, T_PANEL);
                 if (left)
                     continue;
                 // trailing update inside the panel (columns still to be factorised)
@@ -250,7 +251,7 @@ struct Builder {
                     add_gemm(gb, A, f.ldk, A, f.ldk, C, f.ldk, (int)f.m - (jb + w), nc, w,
                              GEMM_ACCUM | GEMM_NEG | GEMM_LOWER);
                 }
-                flush_gemm(gb, p.factor, (int)lv);
+                flush_gemm(gb, p.factor, (int)lv, T_RIGHT_UPDATE);
             }
             // Schur updates scattered into the ancestors' panels
             for (uint32_t fi : fl) {
@@ -264,7 +265,7 @@ struct Builder {
                              (int)f.k, GEMM_SCATTER | GEMM_NEG | GEMM_LOWER, 0, b.rowmap + tg.rowmap_off);
                 }
             }
-            flush_gemm(gb, p.factor, (int)lv);
+            flush_gemm(gb, p.factor, (int)lv, T_SCHUR);
         }
         for (auto& L : p.factor)
             p.factor_flops += L.flops;
@@ -397,8 +398,8 @@ struct Builder {
                 add_gemm(gbb, ws + w.W + (size_t)(jb + wj) * w.ldw + (jb + wj), w.ldw, ws + w.Tt, w.ldt,
                          ws + w.W + (size_t)(jb + wj) * w.ldw + jb, w.ldw, below, wj, below, GEMM_NEG | GEMM_KHI_ROW);
             }
-            flush_gemm(ga, p.selinv, level);
-            flush_gemm(gbb, p.selinv, level);
+            flush_gemm(ga, p.selinv, level, T_TRTRI_A);
+            flush_gemm(gbb, p.selinv, level, T_TRTRI_B);
         }
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];
@@ -440,7 +441,7 @@ struct Builder {
             add_gemm(gb, ws + w.Wt, w.ldw, panel(f) + (size_t)f.k * f.ldk, f.ldk, ws + w.Yt, w.ldr, (int)f.k, (int)f.r,
                      (int)f.k, GEMM_KLO_ROW);
         }
-        flush_gemm(gb, p.selinv, level);
+        flush_gemm(gb, p.selinv, level, T_YT);
         // Z21 = -G * Y   (overwrites L21)
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];
@@ -451,7 +452,7 @@ struct Builder {
             add_gemm(gb, ws + w.G, w.ldg, ws + w.Yt, w.ldr, panel(f) + (size_t)f.k * f.ldk, f.ldk, (int)f.r, (int)f.k,
                      (int)f.r, GEMM_NEG);
         }
-        flush_gemm(gb, p.selinv, level);
+        flush_gemm(gb, p.selinv, level, T_Z21);
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];
             if (!f.r)
@@ -476,7 +477,7 @@ struct Builder {
             add_gemm(gb, ws + w.Wt, w.ldw, ws + w.Wt, w.ldw, panel(f), f.ldk, (int)f.k, (int)f.k, (int)f.k,
                      GEMM_LOWER | GEMM_KLO_MAX);
         }
-        flush_gemm(gb, p.selinv, level);
+        flush_gemm(gb, p.selinv, level, T_Z11_WW);
         // Z11 -= Yt * Z21t^T
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];
@@ -487,7 +488,7 @@ struct Builder {
             add_gemm(gb, ws + w.Yt, w.ldr, ws + w.Z21t, w.ldr, panel(f), f.ldk, (int)f.k, (int)f.k, (int)f.r,
                      GEMM_ACCUM | GEMM_NEG | GEMM_LOWER);
         }
-        flush_gemm(gb, p.selinv, level);
+        flush_gemm(gb, p.selinv, level, T_Z11_YZ);
     }
 
     void build_selinv()

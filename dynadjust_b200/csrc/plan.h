@@ -29,6 +29,11 @@ struct Launch {
     double* zero_ptr;     // L_ZERO
     size_t zero_bytes;
     double flops;         // algorithmic flops of this launch (GEMM: 2MNK, halved for LOWER)
+    int32_t tag;          // which step of the algorithm (profiling label)
+};
+
+enum LaunchTag : int32_t {
+    T_NONE = 0, T_LEFT_UPDATE, T_PANEL, T_RIGHT_UPDATE, T_SCHUR, T_TRTRI_A, T_TRTRI_B, T_YT, T_Z21, T_Z11_WW, T_Z11_YZ,
 };
 
 struct PlanBuffers {
