@@ -32,7 +32,7 @@ BYTES_PER_BASELINE = 944   # 3*208 records + 8 plan words + 48 station XYZ + 27*
 
 WORKLOADS = {
     # name: (synth config, engine options)
-    "C4": ("C4", dict(leaf_stations=256)),
+    "C4": ("C4", dict(leaf_stations=128)),
     "C3g": ("C3g", dict(leaf_stations=96)),
     "C2": ("C2", dict(leaf_stations=96)),
     "C1": ("C1", dict(leaf_stations=16)),
@@ -270,13 +270,15 @@ def run_engine(args):
 
     if rank != 0:
         return
-    alg_flops = info.factor_flops + info.inverse_flops
+    alg_flops = info.factor_flops + info.inverse_flops            # whole network
+    rank_flops = info.rank_factor_flops + info.rank_inverse_flops   # this rank's fronts (== alg_flops on one GPU)
     gemm_ms = prof.ms_gemm / args.steps
     roofline = dict(bound="tensor", kernel="gemm_tile_kernel (TMA-fed DMMA, all panel/Schur/inverse products)",
-                    achieved=alg_flops / gemm_ms / 1e9 if gemm_ms > 0 else None, peak=peak_tf, unit="TFLOP/s",
-                    frac=(alg_flops / gemm_ms / 1e9 / peak_tf) if gemm_ms > 0 else None, traffic=None,
+                    achieved=rank_flops / gemm_ms / 1e9 if gemm_ms > 0 else None, peak=peak_tf, unit="TFLOP/s",
+                    frac=(rank_flops / gemm_ms / 1e9 / peak_tf) if gemm_ms > 0 else None, traffic=None,
                     peak_source="cuBLAS DGEMM 8192^3 best-of-5 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                    algorithmic_flops_per_step=alg_flops, executed_gemm_flops_per_step=prof.flops_gemm / args.steps,
+                    algorithmic_flops_per_step=alg_flops, rank0_algorithmic_flops_per_step=rank_flops,
+                    executed_gemm_flops_per_step=prof.flops_gemm / args.steps,
                     kernel_ms_per_step=gemm_ms, kernel_share_of_step=gemm_ms / ms_step,
                     launches_per_step=prof.gemm_launches / args.steps)
     asm_ms = prof.ms_assemble / args.steps
@@ -291,6 +293,8 @@ def run_engine(args):
                                      "one Gauss-Newton iteration = assemble + factorise + solve + rigorous (selected) inverse",
                             ordering=f"nested dissection, leaf {eng_opts.get('leaf_stations')} stations",
                             fronts=int(info.nfronts), levels=int(info.nlevels), l2_note="inputs larger than L2",
+                            sharding=(f"{world} ranks, subtrees of the dissection tree; {info.top_fronts} shared top fronts "
+                                      f"exchanged by NCCL reduce/broadcast (cut at level {info.cut_level})") if world > 1 else "none",
                             panel_gb=info.panel_bytes / 1e9, prepare_s=prepare_s),
                 e2e=dict(value=e2e_ms, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
                 gpu_launches=int(prof.launches), clocks=clocks, roofline=roofline, roofline_assembly=roofline_asm,

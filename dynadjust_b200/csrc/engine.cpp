@@ -184,6 +184,9 @@ struct gadj_ctx {
     Symbolic sym;
     Plan plan;
     bool prepared = false, factor_valid = false, inverse_valid = false, normals_valid = false;
+    bool stage_normals = false, vcv_extracted = false;
+    int32_t mg_rank = 0, mg_world = 1;
+    DevArray<uint8_t> d_pos_owned;
     uint32_t iteration = 0;
     double critical = 0;
     // device state
@@ -242,10 +245,12 @@ struct gadj_ctx {
 
 namespace {
 
-void run_launches(gadj_ctx* c, const std::vector<Launch>& list)
+void run_one(gadj_ctx* c, const Launch& L)
 {
     void* st = dev::stream();
-    for (const Launch& L : list) {
+    {
+        if (L.kind == L_SYNC)
+            return;
         c->prof_begin(L.kind, L.flops, L.total_tiles, L.tag, L.level);
         if (L.kind == L_ZERO)
             c->launch_count--;  // a memset, not one of our kernels
@@ -280,6 +285,12 @@ void run_launches(gadj_ctx* c, const std::vector<Launch>& list)
         }
         c->prof_end();
     }
+}
+
+void run_launches(gadj_ctx* c, const std::vector<Launch>& list)
+{
+    for (const Launch& L : list)
+        run_one(c, L);
 }
 
 enum { PK_ASSEMBLE = 100, PK_OTHER = 101 };
@@ -606,6 +617,8 @@ int gadj_prepare(gadj_ctx* c)
                             c->sym);
     if (!e.empty())
         return c->fail(e);
+    if (c->mg_world > 1)
+        finalize_layout(c->sym, c->mg_world, c->mg_rank);
     const Symbolic& S = c->sym;
 
     // per-edge orientation and destinations
@@ -665,6 +678,7 @@ int gadj_prepare(gadj_ctx* c)
     ok &= c->d_edge_hi.upload(c->edge_hi);
     ok &= c->d_edge_lo.upload(c->edge_lo);
     ok &= c->d_pos.upload(S.pos_of_stn);
+    ok &= c->d_pos_owned.upload(S.pos_owned);
     ok &= c->d_diag_dest.upload(diag_dest);
     ok &= c->d_diag_ld.upload(diag_ld);
     ok &= c->d_off_dest.upload(off_dest);
@@ -742,8 +756,14 @@ int gadj_get_info(const gadj_ctx* c, gadj_info* info)
     info->panel_bytes = c->sym.panel_doubles * 8;
     info->pool_bytes = c->d_pool.bytes();
     info->device_bytes = c->device_bytes;
-    info->factor_flops = c->plan.factor_flops;
-    info->inverse_flops = c->plan.selinv_flops;
+    info->factor_flops = c->sym.factor_flops;      // whole network, from the symbolic factorisation
+    info->inverse_flops = c->sym.inverse_flops;
+    info->rank_factor_flops = c->sym.world > 1 ? c->sym.my_factor_flops : c->sym.factor_flops;
+    info->rank_inverse_flops = c->sym.world > 1 ? c->sym.my_inverse_flops : c->sym.inverse_flops;
+    info->cut_level = c->sym.world > 1 ? c->sym.cut_level : -1;
+    info->top_fronts = 0;
+    for (const Front& f : c->sym.fronts)
+        info->top_fronts += f.top;
     info->launches_factor = c->plan.factor.size();
     info->launches_solve = c->plan.fwd.size() + c->plan.bwd.size();
     info->launches_inverse = c->plan.selinv.size();
@@ -804,12 +824,19 @@ static void fill_scatter(gadj_ctx* c, ScatterParams& sp)
     sp.scale = c->o.scale_normals_to_unity ? 1 : 0;
 }
 
-int gadj_iterate(gadj_ctx* c, int flags, gadj_iter_result* res)
+static int extract_vcv(gadj_ctx* c);
+
+// ---- staged execution -------------------------------------------------------------------------
+// gadj_iterate runs the stages back to back; a multi-GPU driver (dynadjust_b200/multigpu.py) calls them one by
+// one and exchanges the top fronts between stages where gadj_stage_run stops at a sync marker.
+
+int gadj_stage_begin(gadj_ctx* c, int flags)
 {
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     void* st = dev::stream();
-    bool normals = (flags & GADJ_ITER_NORMALS) || !c->factor_valid;
+    const bool normals = (flags & GADJ_ITER_NORMALS) || !c->factor_valid;
+    c->stage_normals = normals;
     dev::event_record(c->ev[0]);
     // ---- assembly (FillDesignNormalMeasurementsMatrices, ADJ:3888) --------------
     c->prof_begin(PK_ASSEMBLE);
@@ -822,10 +849,11 @@ int gadj_iterate(gadj_ctx* c, int flags, gadj_iter_result* res)
     launch_assemble_g(ap, st);
     c->prof_end();
     dev::event_record(c->ev[1]);
-    // ---- factorisation (Solve: dpotrf, ADJ:6628) --------------------------------
+    // ---- equilibrate + scatter into the front panels ------------------------------
     if (normals) {
         c->inverse_valid = false;
         c->factor_valid = false;
+        c->vcv_extracted = false;
         ScatterParams sp;
         fill_scatter(c, sp);
         c->prof_begin(PK_OTHER);
@@ -839,24 +867,78 @@ int gadj_iterate(gadj_ctx* c, int flags, gadj_iter_result* res)
         c->prof_begin(PK_OTHER);
         launch_scatter_normals(sp, st);
         c->prof_end();
-        run_launches(c, c->plan.factor);
         c->normals_valid = true;
     }
+    return 0;
+}
+
+int gadj_stage_run(gadj_ctx* c, int phase, int64_t* cursor, int32_t* sync_level)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    const std::vector<Launch>* list = nullptr;
+    switch (phase) {
+    case GADJ_PHASE_FACTOR:
+        list = &c->plan.factor;
+        break;
+    case GADJ_PHASE_FORWARD:
+        list = &c->plan.fwd;
+        break;
+    case GADJ_PHASE_BACKWARD:
+        list = &c->plan.bwd;
+        break;
+    case GADJ_PHASE_INVERSE:
+        list = &c->plan.selinv;
+        break;
+    default:
+        return c->fail("unknown phase");
+    }
+    int64_t i = cursor ? *cursor : 0;
+    int32_t lvl = -1;
+    for (; i < (int64_t)list->size(); ++i) {
+        if ((*list)[i].kind == L_SYNC) {
+            lvl = (*list)[i].level;
+            ++i;
+            break;
+        }
+        run_one(c, (*list)[i]);
+    }
+    if (cursor)
+        *cursor = i;
+    if (sync_level)
+        *sync_level = lvl;
+    return 0;
+}
+
+int gadj_stage_solve_begin(gadj_ctx* c)
+{
     dev::event_record(c->ev[2]);
-    // ---- solve + estimates update (ADJ:6659-6667, ADJ:2463-2466) -----------------
     c->prof_begin(PK_OTHER);
-    launch_permute_rhs(c->d_w.p, c->d_dscale.p, c->d_pos.p, c->d_x.p, c->nstn, st);
+    launch_permute_rhs(c->d_w.p, c->d_dscale.p, c->d_pos.p, c->mg_world > 1 ? c->d_pos_owned.p : nullptr, c->d_x.p, c->nstn,
+                       dev::stream());
     c->prof_end();
-    run_launches(c, c->plan.fwd);
-    run_launches(c, c->plan.bwd);
+    return 0;
+}
+
+int gadj_stage_solve_end(gadj_ctx* c)
+{
+    if (c->mg_world > 1)
+        launch_mask_positions(c->d_x.p, c->d_pos_owned.p, c->nstn, dev::stream());
+    return 0;
+}
+
+int gadj_stage_apply(gadj_ctx* c)
+{
     c->prof_begin(PK_OTHER);
     c->launch_count++;  // two kernels: update + max reduction
-    launch_apply_corrections(c->d_x.p, c->d_dscale.p, c->d_pos.p, c->d_corr.p, c->d_est.p, c->nstn, st);
+    launch_apply_corrections(c->d_x.p, c->d_dscale.p, c->d_pos.p, c->d_corr.p, c->d_est.p, c->nstn, dev::stream());
     c->prof_end();
     dev::event_record(c->ev[3]);
-    if (flags & GADJ_ITER_INVERSE) {
-        run_launches(c, c->plan.selinv);
-    }
+    return 0;
+}
+
+int gadj_stage_end(gadj_ctx* c, int flags, int32_t global_info, gadj_iter_result* res)
+{
     dev::event_record(c->ev[4]);
     int32_t info[4] = {0, 0, 0, 0};
     double tail[8];
@@ -865,10 +947,12 @@ int gadj_iterate(gadj_ctx* c, int flags, gadj_iter_result* res)
     std::string e = dev::sync();
     if (!e.empty())
         return c->fail(e);
-    if (normals) {
+    if (global_info > info[0])
+        info[0] = global_info;   // another rank met a non-positive pivot
+    if (c->stage_normals) {
         if (info[0] != 0) {
             c->factor_valid = false;
-            if (getenv("GADJ_DEBUG")) {
+            if (getenv("GADJ_DEBUG") && info[0] - 1 < (int)c->sym.fronts.size()) {
                 const Front& f = c->sym.fronts[info[0] - 1];
                 fprintf(stderr, "gadj: non-positive pivot in front %d (level %d, k=%u r=%u parent=%d)\n", info[0] - 1, f.level,
                         f.k, f.r, f.parent);
@@ -879,6 +963,7 @@ int gadj_iterate(gadj_ctx* c, int flags, gadj_iter_result* res)
     }
     if (flags & GADJ_ITER_INVERSE) {
         c->inverse_valid = true;
+        c->vcv_extracted = false;
         c->factor_valid = false;  // the panels now hold the inverse, not the factor
     }
     c->iteration++;
@@ -898,6 +983,117 @@ int gadj_iterate(gadj_ctx* c, int flags, gadj_iter_result* res)
             return c->fail("Solve(): Invalid variance matrix");
     }
     return 0;
+}
+
+int gadj_iterate(gadj_ctx* c, int flags, gadj_iter_result* res)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    if (c->mg_world > 1)
+        return c->fail("this context is one shard of a multi-GPU adjustment: drive it through the staged calls");
+    if (gadj_stage_begin(c, flags))
+        return 1;
+    if (c->stage_normals)
+        run_launches(c, c->plan.factor);
+    gadj_stage_solve_begin(c);
+    run_launches(c, c->plan.fwd);
+    run_launches(c, c->plan.bwd);
+    gadj_stage_apply(c);
+    if (flags & GADJ_ITER_INVERSE)
+        run_launches(c, c->plan.selinv);
+    return gadj_stage_end(c, flags, 0, res);
+}
+
+int gadj_stage_normals_pending(gadj_ctx* c) { return c->stage_normals ? 1 : 0; }
+
+int gadj_stage_mark_inverse(gadj_ctx* c)
+{
+    std::string e = dev::sync();
+    if (!e.empty())
+        return c->fail(e);
+    c->inverse_valid = true;
+    c->vcv_extracted = false;
+    c->factor_valid = false;
+    return 0;
+}
+
+int gadj_sync(gadj_ctx* c)
+{
+    std::string e = dev::sync();
+    return e.empty() ? 0 : c->fail(e);
+}
+
+int gadj_mg_init(gadj_ctx* c, int32_t rank, int32_t world)
+{
+    if (world < 1 || rank < 0 || rank >= world)
+        return c->fail("bad rank / world size");
+    c->mg_rank = rank;
+    c->mg_world = world;
+    c->prepared = false;
+    return 0;
+}
+
+int gadj_mg_buffer(gadj_ctx* c, int which, void** ptr, uint64_t* count)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    switch (which) {
+    case 0:
+        *ptr = c->d_x.p;
+        *count = c->d_x.n;
+        break;
+    case 1:
+        *ptr = c->d_panels.p;
+        *count = c->d_panels.n;
+        break;
+    case 2:
+        *ptr = c->d_vcvd.p;
+        *count = c->d_vcvd.n;
+        break;
+    case 3:
+        *ptr = c->d_vcvo.p;
+        *count = c->d_vcvo.n;
+        break;
+    case 4:
+        *ptr = c->d_info.p;
+        *count = c->d_info.n;
+        break;
+    default:
+        return c->fail("unknown buffer");
+    }
+    return 0;
+}
+
+int gadj_mg_top_fronts(gadj_ctx* c, int32_t level, uint32_t cap, uint32_t* n, uint64_t* panel_off, uint64_t* panel_len,
+                       uint64_t* x_off, uint64_t* x_len, int32_t* owner)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    uint32_t k = 0;
+    if (level >= 0 && level < (int32_t)c->sym.levels.size())
+        for (uint32_t fi : c->sym.levels[level]) {
+            const Front& f = c->sym.fronts[fi];
+            if (!f.top)
+                continue;
+            if (k < cap) {
+                panel_off[k] = f.panel_off;
+                panel_len[k] = (uint64_t)f.m * f.ldk;
+                x_off[k] = 3ull * f.own_begin;
+                x_len[k] = f.k;
+                owner[k] = f.owner;
+            }
+            ++k;
+        }
+    *n = k;
+    return 0;
+}
+
+int gadj_mg_extract_vcv(gadj_ctx* c)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    c->vcv_extracted = false;
+    return extract_vcv(c);
 }
 
 int gadj_adjust(gadj_ctx* c, gadj_iter_result* last)
@@ -925,6 +1121,7 @@ int gadj_adjust(gadj_ctx* c, gadj_iter_result* last)
             return c->fail(e);
         ms_inv = dev::event_elapsed_ms(c->ev[3], c->ev[4]);
         c->inverse_valid = true;
+        c->vcv_extracted = false;
         c->factor_valid = false;
     }
     r.ms_inverse = ms_inv;
@@ -937,6 +1134,9 @@ static int extract_vcv(gadj_ctx* c)
 {
     if (!c->inverse_valid)
         return c->fail("the rigorous inverse has not been formed (run gadj_adjust or iterate with GADJ_ITER_INVERSE)");
+    if (c->vcv_extracted)
+        return 0;   // (a multi-GPU driver has already summed the per-rank pieces in place)
+    c->vcv_extracted = true;
     void* st = dev::stream();
     launch_extract_station_vcv(c->d_panels.p, c->d_diag_dest.p, c->d_diag_ld.p, c->d_dscale.p, c->d_vcvd.p, c->nstn, st);
     launch_extract_edge_vcv(c->d_panels.p, c->d_off_dest.p, c->d_off_ld.p, c->d_edge_hi.p, c->d_edge_lo.p, c->d_dscale.p,

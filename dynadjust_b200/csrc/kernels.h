@@ -139,7 +139,7 @@ void launch_init_normals(const double* cblock, double* ndiag, double* noff, doub
 struct ScatterParams {
     const double* ndiag;
     const double* noff;
-    const uint64_t* diag_dest;   // per station (station order)
+    const uint64_t* diag_dest;   // per station (station order); ~0 = assembled by another rank
     const uint32_t* diag_ld;
     const uint64_t* off_dest;    // per edge
     const uint32_t* off_ld;
@@ -154,9 +154,11 @@ struct ScatterParams {
 void launch_compute_scale(const ScatterParams& p, void* stream);
 void launch_scatter_normals(const ScatterParams& p, void* stream);
 
-// b[3*pos[s]+c] = dscale[3s+c] * w[3s+c]
-void launch_permute_rhs(const double* w, const double* dscale, const uint32_t* pos_of_stn, double* b, uint32_t nstn,
-                        void* stream);
+// b[3*pos[s]+c] = dscale[3s+c] * w[3s+c]   (0 where pos_owned[pos[s]] == 0, when a mask is given)
+void launch_permute_rhs(const double* w, const double* dscale, const uint32_t* pos_of_stn, const uint8_t* pos_owned,
+                        double* b, uint32_t nstn, void* stream);
+// x[3p+c] = 0 for positions this rank does not own (before the cross-rank sum of the solution vector)
+void launch_mask_positions(double* x, const uint8_t* pos_owned, uint32_t nstn, void* stream);
 // corr[3s+c] = dscale * x[3*pos[s]+c]; est += corr; tracks the largest |corr| (first in station order on ties)
 void launch_apply_corrections(const double* x, const double* dscale, const uint32_t* pos_of_stn, double* corr,
                               double* est, uint32_t nstn, void* stream);

@@ -194,24 +194,38 @@ __global__ void scatter_normals_kernel(const ScatterParams p)
         if (i < nd) {
             const uint64_t s = i / 9;
             const int k = (int)(i - 9 * s), r = k / 3, c = k - 3 * r;
-            p.panels[p.diag_dest[s] + (uint64_t)r * p.diag_ld[s] + c] = p.ndiag[i] * p.dscale[3 * s + r] * p.dscale[3 * s + c];
+            const uint64_t d = p.diag_dest[s];
+            if (d != ~0ull)
+                p.panels[d + (uint64_t)r * p.diag_ld[s] + c] = p.ndiag[i] * p.dscale[3 * s + r] * p.dscale[3 * s + c];
         } else {
             const uint64_t j = i - nd, e = j / 9;
             const int k = (int)(j - 9 * e), r = k / 3, c = k - 3 * r;
-            p.panels[p.off_dest[e] + (uint64_t)r * p.off_ld[e] + c] =
-                p.noff[j] * p.dscale[3ull * p.edge_hi[e] + r] * p.dscale[3ull * p.edge_lo[e] + c];
+            const uint64_t d = p.off_dest[e];
+            if (d != ~0ull)
+                p.panels[d + (uint64_t)r * p.off_ld[e] + c] =
+                    p.noff[j] * p.dscale[3ull * p.edge_hi[e] + r] * p.dscale[3ull * p.edge_lo[e] + c];
         }
     }
 }
 
 __global__ void permute_rhs_kernel(const double* __restrict__ w, const double* __restrict__ dscale,
-                                   const uint32_t* __restrict__ pos, double* __restrict__ b, uint32_t nstn)
+                                   const uint32_t* __restrict__ pos, const uint8_t* __restrict__ pos_owned,
+                                   double* __restrict__ b, uint32_t nstn)
 {
     const uint64_t n = 3ull * nstn;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t s = i / 3;
-        b[3ull * pos[s] + (i - 3 * s)] = dscale[i] * w[i];
+        const uint32_t p = pos[s];
+        b[3ull * p + (i - 3 * s)] = (pos_owned == nullptr || pos_owned[p]) ? dscale[i] * w[i] : 0.0;
     }
+}
+
+__global__ void mask_positions_kernel(double* __restrict__ x, const uint8_t* __restrict__ pos_owned, uint32_t nstn)
+{
+    const uint64_t n = 3ull * nstn;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        if (!pos_owned[i / 3])
+            x[i] = 0.0;
 }
 
 // corrections + estimates + per-block (|max|, first index) partials
@@ -306,7 +320,8 @@ __global__ void extract_station_vcv_kernel(const double* __restrict__ panels, co
         const uint64_t s = i / 9;
         const int k = (int)(i - 9 * s), r = k / 3, c = k - 3 * r;
         const int a = r > c ? r : c, b = r > c ? c : r;
-        vcv[i] = panels[diag_dest[s] + (uint64_t)a * diag_ld[s] + b] * dscale[3 * s + r] * dscale[3 * s + c];
+        const uint64_t d = diag_dest[s];
+        vcv[i] = d != ~0ull ? panels[d + (uint64_t)a * diag_ld[s] + b] * dscale[3 * s + r] * dscale[3 * s + c] : 0.0;
     }
 }
 
@@ -319,7 +334,9 @@ __global__ void extract_edge_vcv_kernel(const double* __restrict__ panels, const
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t e = i / 9;
         const int k = (int)(i - 9 * e), r = k / 3, c = k - 3 * r;
-        q[i] = panels[off_dest[e] + (uint64_t)r * off_ld[e] + c] * dscale[3ull * edge_hi[e] + r] * dscale[3ull * edge_lo[e] + c];
+        const uint64_t d = off_dest[e];
+        q[i] = d != ~0ull ? panels[d + (uint64_t)r * off_ld[e] + c] * dscale[3ull * edge_hi[e] + r] * dscale[3ull * edge_lo[e] + c]
+                          : 0.0;
     }
 }
 
@@ -464,10 +481,15 @@ void launch_scatter_normals(const ScatterParams& p, void* stream)
     scatter_normals_kernel<<<grid_for(9ull * (p.nstn + p.nedge), 256), 256, 0, (cudaStream_t)stream>>>(p);
 }
 
-void launch_permute_rhs(const double* w, const double* dscale, const uint32_t* pos_of_stn, double* b, uint32_t nstn,
-                        void* stream)
+void launch_permute_rhs(const double* w, const double* dscale, const uint32_t* pos_of_stn, const uint8_t* pos_owned, double* b,
+                        uint32_t nstn, void* stream)
 {
-    permute_rhs_kernel<<<grid_for(3ull * nstn, 256), 256, 0, (cudaStream_t)stream>>>(w, dscale, pos_of_stn, b, nstn);
+    permute_rhs_kernel<<<grid_for(3ull * nstn, 256), 256, 0, (cudaStream_t)stream>>>(w, dscale, pos_of_stn, pos_owned, b, nstn);
+}
+
+void launch_mask_positions(double* x, const uint8_t* pos_owned, uint32_t nstn, void* stream)
+{
+    mask_positions_kernel<<<grid_for(3ull * nstn, 256), 256, 0, (cudaStream_t)stream>>>(x, pos_owned, nstn);
 }
 
 void launch_apply_corrections(const double* x, const double* dscale, const uint32_t* pos_of_stn, double* corr, double* est,

@@ -65,6 +65,25 @@ struct Builder {
 
     double* panel(const Front& f) const { return b.panels + f.panel_off; }
 
+    // fronts of a level that this rank factorises
+    std::vector<uint32_t> owned(size_t lv) const
+    {
+        std::vector<uint32_t> v;
+        for (uint32_t f : s.levels[lv])
+            if (s.fronts[f].owner == s.rank)
+                v.push_back(f);
+        return v;
+    }
+    void add_sync(std::vector<Launch>& out, size_t lv)
+    {
+        if (s.world <= 1 || (int)lv < s.cut_level)
+            return;
+        Launch L{};
+        L.kind = L_SYNC;
+        L.level = (int32_t)lv;
+        out.push_back(L);
+    }
+
     void add_gemm(std::vector<GemmOp>& batch, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                   int64_t ldc, int M, int N, int K, int flags, int tri_off = 0, const int32_t* rowmap = nullptr)
     {
@@ -186,7 +205,8 @@ struct Builder {
         std::vector<GemmOp> gb;
         std::vector<DiagOp> db;
         for (size_t lv = 0; lv < s.levels.size(); ++lv) {
-            const auto& fl = s.levels[lv];
+            const std::vector<uint32_t> fl = owned(lv);
+            add_sync(p.factor, lv);   // contributions to this level's top fronts are reduced to their owners first
             int nsteps = 0;
             for (uint32_t f : fl)
                 nsteps = std::max(nsteps, cdiv((int)s.fronts[f].k, NB));
@@ -278,7 +298,8 @@ struct Builder {
         std::vector<TriOp> tb;
         std::vector<GemvOp> vb;
         for (size_t lv = 0; lv < s.levels.size(); ++lv) {
-            const auto& fl = s.levels[lv];
+            const std::vector<uint32_t> fl = owned(lv);
+            add_sync(p.fwd, lv);      // right-hand-side contributions to this level's top fronts are summed first
             int nsteps = 0;
             for (uint32_t f : fl)
                 nsteps = std::max(nsteps, cdiv((int)s.fronts[f].k, NB));
@@ -311,7 +332,7 @@ struct Builder {
             }
         }
         for (size_t lvi = s.levels.size(); lvi-- > 0;) {
-            const auto& fl = s.levels[lvi];
+            const std::vector<uint32_t> fl = owned(lvi);
             int nsteps = 0;
             for (uint32_t f : fl)
                 nsteps = std::max(nsteps, cdiv((int)s.fronts[f].k, NB));
@@ -344,6 +365,7 @@ struct Builder {
                 flush_simple(vb, p.gemv, L_GEMV_BWD, p.bwd, (int)lvi);
                 flush_simple(tb, p.tri, L_TRI_BWD, p.bwd, (int)lvi);
             }
+            add_sync(p.bwd, lvi);     // the solved top fronts of this level are broadcast to every rank
         }
     }
 
@@ -494,7 +516,7 @@ struct Builder {
     void build_selinv()
     {
         for (size_t lvi = s.levels.size(); lvi-- > 0;) {
-            const auto& fl = s.levels[lvi];
+            const std::vector<uint32_t> fl = owned(lvi);
             std::vector<uint32_t> chunk;
             std::vector<size_t> base;
             size_t used = 0;
@@ -516,6 +538,7 @@ struct Builder {
             }
             if (!chunk.empty())
                 build_selinv_chunk(chunk, base, used, (int)lvi);
+            add_sync(p.selinv, lvi);  // the inverse panels of this level's top fronts are broadcast to every rank
         }
         for (auto& L : p.selinv)
             p.selinv_flops += L.flops;
@@ -530,10 +553,15 @@ size_t min_pool_doubles(const Symbolic& s)
 {
     size_t need = 0, width = 0;
     for (const Front& f : s.fronts)
-        need = std::max(need, ws_layout(f).total);
-    for (auto& lv : s.levels)
-        width = std::max(width, lv.size());
-    return std::max(need, width * (size_t)NB * NB);
+        if (f.owner == s.rank)
+            need = std::max(need, ws_layout(f).total);
+    for (auto& lv : s.levels) {
+        size_t n = 0;
+        for (uint32_t f : lv)
+            n += s.fronts[f].owner == s.rank;
+        width = std::max(width, n);
+    }
+    return std::max<size_t>(16, std::max(need, width * (size_t)NB * NB));
 }
 
 size_t ideal_pool_doubles(const Symbolic& s)
@@ -542,7 +570,8 @@ size_t ideal_pool_doubles(const Symbolic& s)
     for (auto& lv : s.levels) {
         size_t t = 0;
         for (uint32_t f : lv)
-            t += ws_layout(s.fronts[f]).total;
+            if (s.fronts[f].owner == s.rank)
+                t += ws_layout(s.fronts[f]).total;
         best = std::max(best, t);
     }
     return best;

@@ -18,6 +18,7 @@ enum LaunchKind : int32_t {
     L_TRANSPOSE,
     L_GATHER,
     L_ZERO,
+    L_SYNC,      // multi-GPU stage boundary: the host exchanges the top fronts of `level` before going on
 };
 
 struct Launch {

@@ -276,19 +276,17 @@ std::string analyse(uint32_t nstn, const std::vector<std::pair<uint32_t, uint32_
         fr.ldk = fr.k + (fr.k & 1u);
     }
     out.levels.assign((size_t)maxlevel + 1, {});
-    uint64_t off = 0;
     for (uint32_t f = 0; f < F; ++f) {
         Front& fr = out.fronts[f];
         out.levels[fr.level].push_back(f);
-        fr.panel_off = off;
-        uint64_t sz = (uint64_t)fr.m * fr.ldk;
-        off += (sz + 15) & ~(uint64_t)15;
         double k = fr.k, r = fr.r;
-        out.factor_flops += k * k * k / 3.0 + k * k * r + k * r * r;
-        out.inverse_flops += 2.0 * k * k * k / 3.0 + 2.0 * k * k * r + 2.0 * k * r * r + 2.0 * k * k * r;
+        double ff = k * k * k / 3.0 + k * k * r + k * r * r;
+        double fi = 2.0 * k * k * k / 3.0 + 2.0 * k * k * r + 2.0 * k * r * r + 2.0 * k * k * r;
+        fr.work = ff + fi;
+        out.factor_flops += ff;
+        out.inverse_flops += fi;
         out.nnz_l_blocks += (uint64_t)fr.own_count * (fr.own_count + 1) / 2 + (uint64_t)fr.own_count * fr.bnd_count;
     }
-    out.panel_doubles = off;
 
     // ---- 4. update targets and row maps --------------------------------------
     for (uint32_t f = 0; f < F; ++f) {
@@ -339,8 +337,6 @@ std::string analyse(uint32_t nstn, const std::vector<std::pair<uint32_t, uint32_
         out.ncol_ptr[p + 1] = out.ncol_ptr[p] + 1 + later;
     }
     out.nrow.resize(out.ncol_ptr[nstn]);
-    out.ndest.resize(out.ncol_ptr[nstn]);
-    out.ndest_ld.resize(out.ncol_ptr[nstn]);
     for (uint32_t p = 0; p < nstn; ++p) {
         uint32_t v = out.stn_of_pos[p];
         uint64_t s = out.ncol_ptr[p];
@@ -351,27 +347,133 @@ std::string analyse(uint32_t nstn, const std::vector<std::pair<uint32_t, uint32_
                 out.nrow[s++] = q;
         }
         std::sort(out.nrow.begin() + out.ncol_ptr[p] + 1, out.nrow.begin() + out.ncol_ptr[p + 1]);
-        const uint32_t f = out.front_of_pos[p];
-        const Front& fr = out.fronts[f];
+    }
+    finalize_layout(out, 1, 0);
+    return std::string();
+}
+
+void finalize_layout(Symbolic& s, int world, int rank)
+{
+    const uint32_t F = (uint32_t)s.fronts.size();
+    s.world = world;
+    s.rank = rank;
+    s.cut_level = 1 << 30;
+    std::vector<std::vector<uint32_t>> children(F);
+    std::vector<double> sub(F, 0.0);
+    for (uint32_t f = 0; f < F; ++f) {
+        sub[f] += s.fronts[f].work;
+        s.fronts[f].owner = 0;
+        s.fronts[f].top = 0;
+        if (s.fronts[f].parent >= 0) {
+            children[s.fronts[f].parent].push_back(f);
+            sub[s.fronts[f].parent] += sub[f];   // children precede parents in elimination order
+        }
+    }
+    if (world > 1) {
+        std::vector<uint32_t> cand;
+        double total = 0;
+        for (uint32_t f = 0; f < F; ++f)
+            if (s.fronts[f].parent < 0) {
+                cand.push_back(f);
+                total += sub[f];
+            }
+        // split the heaviest subtree while there are too few, or it alone exceeds a fair share
+        for (;;) {
+            size_t best = cand.size();
+            for (size_t i = 0; i < cand.size(); ++i)
+                if (!children[cand[i]].empty() && (best == cand.size() || sub[cand[i]] > sub[cand[best]]))
+                    best = i;
+            if (best == cand.size())
+                break;
+            bool heaviest_is_best = true;
+            for (uint32_t c : cand)
+                if (sub[c] > sub[cand[best]])
+                    heaviest_is_best = false;
+            if (cand.size() >= (size_t)world && !(heaviest_is_best && sub[cand[best]] > total / world))
+                break;
+            uint32_t f = cand[best];
+            s.fronts[f].top = 1;
+            cand.erase(cand.begin() + best);
+            for (uint32_t c : children[f])
+                cand.push_back(c);
+        }
+        // longest-processing-time packing of the subtrees
+        std::sort(cand.begin(), cand.end(), [&](uint32_t a, uint32_t b) { return sub[a] > sub[b] || (sub[a] == sub[b] && a < b); });
+        std::vector<double> load(world, 0.0);
+        std::vector<int32_t> root_owner(F, -1);
+        for (uint32_t c : cand) {
+            int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            load[r] += sub[c];
+            root_owner[c] = r;
+        }
+        // propagate subtree ownership downwards (parents have larger indices than children)
+        for (uint32_t fi = F; fi-- > 0;) {
+            Front& f = s.fronts[fi];
+            if (f.top)
+                continue;
+            if (root_owner[fi] >= 0)
+                f.owner = root_owner[fi];
+            else
+                f.owner = s.fronts[f.parent].owner;
+        }
+        // a top front is factorised by the owner of its heaviest child
+        for (uint32_t fi = 0; fi < F; ++fi) {
+            Front& f = s.fronts[fi];
+            if (!f.top)
+                continue;
+            double bw = -1;
+            for (uint32_t c : children[fi])
+                if (sub[c] > bw) {
+                    bw = sub[c];
+                    f.owner = s.fronts[c].owner;
+                }
+            s.cut_level = std::min(s.cut_level, f.level);
+        }
+    }
+    // storage: owned fronts + all top fronts
+    uint64_t off = 0;
+    s.my_factor_flops = s.my_inverse_flops = 0;
+    for (uint32_t fi = 0; fi < F; ++fi) {
+        Front& f = s.fronts[fi];
+        if (f.owner == rank || f.top) {
+            f.panel_off = off;
+            uint64_t sz = (uint64_t)f.m * f.ldk;
+            off += (sz + 15) & ~(uint64_t)15;
+        } else
+            f.panel_off = NO_DEST;
+        if (f.owner == rank) {
+            double k = f.k, r = f.r;
+            s.my_factor_flops += k * k * k / 3.0 + k * k * r + k * r * r;
+            s.my_inverse_flops += 2.0 * k * k * k / 3.0 + 2.0 * k * k * r + 2.0 * k * r * r + 2.0 * k * k * r;
+        }
+    }
+    s.panel_doubles = off;
+    s.pos_owned.assign(s.nstn, 0);
+    // destinations of N's blocks: assembled into a front only by its owner
+    const uint64_t nslots = s.ncol_ptr[s.nstn];
+    s.ndest.assign(nslots, NO_DEST);
+    s.ndest_ld.assign(nslots, 0);
+    for (uint32_t p = 0; p < s.nstn; ++p) {
+        const Front& fr = s.fronts[s.front_of_pos[p]];
+        if (fr.owner != rank)
+            continue;
+        s.pos_owned[p] = 1;
         const uint32_t own_end = fr.own_begin + fr.own_count;
-        const uint32_t* b = out.bnd.data() + fr.bnd_begin;
+        const uint32_t* b = s.bnd.data() + fr.bnd_begin;
         const uint64_t col = 3ull * (p - fr.own_begin);
-        for (uint64_t t = out.ncol_ptr[p]; t < out.ncol_ptr[p + 1]; ++t) {
-            uint32_t q = out.nrow[t];
+        for (uint64_t t = s.ncol_ptr[p]; t < s.ncol_ptr[p + 1]; ++t) {
+            uint32_t q = s.nrow[t];
             uint64_t row;
             if (q < own_end)
                 row = 3ull * (q - fr.own_begin);
             else {
                 const uint32_t* it = std::lower_bound(b, b + fr.bnd_count, q);
-                if (it == b + fr.bnd_count || *it != q)
-                    return "internal: neighbour missing from the front boundary";
                 row = 3ull * (fr.own_count + (uint32_t)(it - b));
             }
-            out.ndest[t] = fr.panel_off + row * fr.ldk + col;
-            out.ndest_ld[t] = fr.ldk;
+            s.ndest[t] = fr.panel_off + row * fr.ldk + col;
+            s.ndest_ld[t] = fr.ldk;
         }
     }
-    return std::string();
 }
 
 }  // namespace gadj

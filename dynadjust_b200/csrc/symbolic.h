@@ -24,7 +24,12 @@ struct Front {
     uint32_t ldk = 0;         // panel row pitch (doubles), even
     uint64_t panel_off = 0;   // offset (doubles) of the m x ldk row-major panel
     uint32_t tgt_begin = 0, tgt_count = 0;  // range into Symbolic::targets
+    int32_t owner = 0;        // rank that factorises this front (multi-GPU sharding by subtree)
+    uint8_t top = 0;          // 1: above the subtree cut — storage replicated on every rank, contributions reduced
+    double work = 0;          // factor + inverse flops of this front
 };
+
+constexpr uint64_t NO_DEST = ~0ull;
 
 // Update target: boundary stations [jb, je) of front `src` are owned by ancestor `anc`.
 struct Target {
@@ -53,6 +58,11 @@ struct Symbolic {
     std::vector<uint32_t> ndest_ld;     // row pitch at the destination
     double factor_flops = 0, inverse_flops = 0;
     uint64_t nnz_l_blocks = 0;
+    // sharding (world == 1: every front owned by rank 0, nothing is "top")
+    int32_t world = 1, rank = 0;
+    int32_t cut_level = 1 << 30;               // first level that holds a top front
+    std::vector<uint8_t> pos_owned;             // per elimination position: its front is owned by this rank
+    double my_factor_flops = 0, my_inverse_flops = 0;
 };
 
 struct OrderingOptions {
@@ -69,6 +79,11 @@ std::string analyse(uint32_t nstn, const std::vector<std::pair<uint32_t, uint32_
                     const double* lat, const double* lon, const OrderingOptions& opt,
                     uint32_t nblocks, const uint32_t* isl_off, const uint32_t* isl,
                     Symbolic& out);
+
+// Assign fronts to ranks by subtree (largest subtrees split until there are >= world of them, then
+// longest-processing-time packing), lay out this rank's panels (owned fronts + every top front) and compute
+// the normal-matrix destinations (NO_DEST for blocks whose front another rank assembles).
+void finalize_layout(Symbolic& s, int world, int rank);
 
 // slot of block (row position q, column position p), q >= p; UINT64_MAX when absent
 uint64_t find_slot(const Symbolic& s, uint32_t q, uint32_t p);

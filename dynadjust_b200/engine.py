@@ -44,7 +44,9 @@ class GadjInfo(C.Structure):
                 ("nfronts", C.c_uint64), ("nlevels", C.c_uint64), ("panel_bytes", C.c_uint64),
                 ("pool_bytes", C.c_uint64), ("device_bytes", C.c_uint64), ("factor_flops", C.c_double),
                 ("inverse_flops", C.c_double), ("launches_factor", C.c_uint64), ("launches_solve", C.c_uint64),
-                ("launches_inverse", C.c_uint64), ("max_front_rows", C.c_uint32), ("max_front_cols", C.c_uint32)]
+                ("launches_inverse", C.c_uint64), ("max_front_rows", C.c_uint32), ("max_front_cols", C.c_uint32),
+                ("rank_factor_flops", C.c_double), ("rank_inverse_flops", C.c_double), ("cut_level", C.c_int32),
+                ("top_fronts", C.c_uint32)]
 
 
 class GadjProfile(C.Structure):
@@ -58,7 +60,10 @@ EXPORTS = ["gadj_default_opts", "gadj_create", "gadj_destroy", "gadj_last_error"
            "gadj_set_measurements", "gadj_set_blocks", "gadj_prepare", "gadj_get_info", "gadj_upload_measurements",
            "gadj_reset_estimates", "gadj_iterate", "gadj_adjust", "gadj_statistics", "gadj_get_estimates",
            "gadj_get_corrections", "gadj_get_station_vcvs", "gadj_get_station_vcv", "gadj_get_vcv_block",
-           "gadj_get_normals_block", "gadj_get_rhs", "gadj_profile_enable", "gadj_profile_read", "gadj_test_gemm"]
+           "gadj_get_normals_block", "gadj_get_rhs", "gadj_profile_enable", "gadj_profile_read", "gadj_test_gemm",
+           "gadj_mg_init", "gadj_stage_begin", "gadj_stage_normals_pending", "gadj_stage_run", "gadj_stage_solve_begin",
+           "gadj_stage_solve_end", "gadj_stage_apply", "gadj_stage_end", "gadj_stage_mark_inverse", "gadj_sync", "gadj_mg_buffer",
+           "gadj_mg_top_fronts", "gadj_mg_extract_vcv"]
 
 _libs = {}
 
@@ -96,6 +101,19 @@ def load_library(path=None):
     L.gadj_get_rhs.argtypes = [vp, vp]
     L.gadj_profile_enable.argtypes = [vp, i32]
     L.gadj_profile_read.argtypes = [vp, C.POINTER(GadjProfile), i32]
+    L.gadj_mg_init.argtypes = [vp, C.c_int32, C.c_int32]
+    L.gadj_stage_begin.argtypes = [vp, i32]
+    L.gadj_stage_normals_pending.argtypes = [vp]
+    L.gadj_stage_run.argtypes = [vp, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    L.gadj_stage_solve_begin.argtypes = [vp]
+    L.gadj_stage_solve_end.argtypes = [vp]
+    L.gadj_stage_apply.argtypes = [vp]
+    L.gadj_stage_end.argtypes = [vp, i32, C.c_int32, C.POINTER(GadjIterResult)]
+    L.gadj_stage_mark_inverse.argtypes = [vp]
+    L.gadj_sync.argtypes = [vp]
+    L.gadj_mg_buffer.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]
+    L.gadj_mg_top_fronts.argtypes = [vp, C.c_int32, u32, C.POINTER(u32), vp, vp, vp, vp, vp]
+    L.gadj_mg_extract_vcv.argtypes = [vp]
     L.gadj_test_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, C.POINTER(C.c_float)]
     _libs[path] = L
     return L

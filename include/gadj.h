@@ -94,6 +94,9 @@ typedef struct gadj_info {
     double factor_flops, inverse_flops;    /* algorithmic, from the symbolic factorisation actually used */
     uint64_t launches_factor, launches_solve, launches_inverse;
     uint32_t max_front_rows, max_front_cols;
+    double rank_factor_flops, rank_inverse_flops;   /* the share of this rank (multi-GPU sharding) */
+    int32_t cut_level;                               /* first tree level holding a shared ("top") front; -1 single GPU */
+    uint32_t top_fronts;
 } gadj_info;
 
 /* per-kernel-family device time (CUDA events around every launch) accumulated since the last reset */
@@ -141,6 +144,34 @@ int gadj_get_vcv_block(gadj_ctx* c, uint32_t si, uint32_t sj, double q[9]);
 /* assembled normals (constraints included) of the last iterate call that built them, and its right-hand side */
 int gadj_get_normals_block(gadj_ctx* c, uint32_t si, uint32_t sj, double n[9]);
 int gadj_get_rhs(gadj_ctx* c, double* w /* 3*nstn */);
+
+/*
+ * Staged execution and multi-GPU sharding.  The dissection tree is cut into subtrees, one set per rank
+ * (one process per GPU); fronts above the cut ("top" fronts) have storage on every rank, are factorised by one
+ * owner, and are the only data exchanged: before an owner factorises a top front the ranks' partial Schur sums
+ * of its panel are reduced to it; before/after its triangular solves its slice of the solution vector is
+ * summed / broadcast; after its inverse panel is formed it is broadcast.  gadj_stage_run executes one phase's
+ * launches from *cursor up to the next exchange point and reports the tree level whose top fronts
+ * (gadj_mg_top_fronts) must be exchanged there (-1: phase finished).  The host driver does the collectives
+ * (torch.distributed / NCCL in dynadjust_b200/multigpu.py) on the buffers returned by gadj_mg_buffer.
+ * This is the sum form of the reference's junction-station carry between blocks (ADJ:998-1281, 3196-3333).
+ */
+enum { GADJ_PHASE_FACTOR = 0, GADJ_PHASE_FORWARD = 1, GADJ_PHASE_BACKWARD = 2, GADJ_PHASE_INVERSE = 3 };
+enum { GADJ_BUF_X = 0, GADJ_BUF_PANELS = 1, GADJ_BUF_STATION_VCV = 2, GADJ_BUF_EDGE_VCV = 3, GADJ_BUF_INFO = 4 };
+int gadj_mg_init(gadj_ctx* c, int32_t rank, int32_t world);          /* before gadj_prepare */
+int gadj_stage_begin(gadj_ctx* c, int flags);                         /* assembly, equilibration, scatter */
+int gadj_stage_normals_pending(gadj_ctx* c);                          /* 1 when this iteration refactorises */
+int gadj_stage_run(gadj_ctx* c, int phase, int64_t* cursor, int32_t* sync_level);
+int gadj_stage_solve_begin(gadj_ctx* c);                              /* right-hand side into the solution vector */
+int gadj_stage_solve_end(gadj_ctx* c);                                /* zero the entries other ranks own (then sum across ranks) */
+int gadj_stage_apply(gadj_ctx* c);                                    /* corrections, estimates, largest correction */
+int gadj_stage_end(gadj_ctx* c, int flags, int32_t global_info, gadj_iter_result* res);
+int gadj_stage_mark_inverse(gadj_ctx* c);                             /* after a stand-alone GADJ_PHASE_INVERSE run */
+int gadj_sync(gadj_ctx* c);                                           /* wait for the context's stream */
+int gadj_mg_buffer(gadj_ctx* c, int which, void** ptr, uint64_t* count);
+int gadj_mg_top_fronts(gadj_ctx* c, int32_t level, uint32_t cap, uint32_t* n, uint64_t* panel_off, uint64_t* panel_len,
+                       uint64_t* x_off, uint64_t* x_len, int32_t* owner);
+int gadj_mg_extract_vcv(gadj_ctx* c);                                 /* per-rank VCV pieces (zeros elsewhere), then sum across ranks */
 
 /* optional per-launch timing; small overhead (two event records per launch) */
 int gadj_profile_enable(gadj_ctx* c, int on);

@@ -235,6 +235,8 @@ void launch_compute_scale(const ScatterParams& p, void*)
 void launch_scatter_normals(const ScatterParams& p, void*)
 {
     for (uint32_t s = 0; s < p.nstn; ++s) {
+        if (p.diag_dest[s] == ~0ull)
+            continue;
         double* d = p.panels + p.diag_dest[s];
         const uint32_t ld = p.diag_ld[s];
         for (int r = 0; r < 3; ++r)
@@ -242,6 +244,8 @@ void launch_scatter_normals(const ScatterParams& p, void*)
                 d[(size_t)r * ld + c] = p.ndiag[9 * (size_t)s + 3 * r + c] * p.dscale[3 * (size_t)s + r] * p.dscale[3 * (size_t)s + c];
     }
     for (uint64_t e = 0; e < p.nedge; ++e) {
+        if (p.off_dest[e] == ~0ull)
+            continue;
         double* d = p.panels + p.off_dest[e];
         const uint32_t ld = p.off_ld[e];
         const uint32_t hi = p.edge_hi[e], lo = p.edge_lo[e];
@@ -251,11 +255,19 @@ void launch_scatter_normals(const ScatterParams& p, void*)
     }
 }
 
-void launch_permute_rhs(const double* w, const double* dscale, const uint32_t* pos, double* b, uint32_t nstn, void*)
+void launch_permute_rhs(const double* w, const double* dscale, const uint32_t* pos, const uint8_t* pos_owned, double* b,
+                        uint32_t nstn, void*)
 {
     for (uint32_t s = 0; s < nstn; ++s)
         for (int c = 0; c < 3; ++c)
-            b[3 * (size_t)pos[s] + c] = dscale[3 * (size_t)s + c] * w[3 * (size_t)s + c];
+            b[3 * (size_t)pos[s] + c] = (!pos_owned || pos_owned[pos[s]]) ? dscale[3 * (size_t)s + c] * w[3 * (size_t)s + c] : 0.0;
+}
+
+void launch_mask_positions(double* x, const uint8_t* pos_owned, uint32_t nstn, void*)
+{
+    for (size_t i = 0; i < 3 * (size_t)nstn; ++i)
+        if (!pos_owned[i / 3])
+            x[i] = 0.0;
 }
 
 void launch_apply_corrections(const double* x, const double* dscale, const uint32_t* pos, double* corr, double* est,
@@ -278,6 +290,11 @@ void launch_extract_station_vcv(const double* panels, const uint64_t* diag_dest,
                                 const double* dscale, double* vcv, uint32_t nstn, void*)
 {
     for (uint32_t s = 0; s < nstn; ++s) {
+        if (diag_dest[s] == ~0ull) {
+            for (int k = 0; k < 9; ++k)
+                vcv[9 * (size_t)s + k] = 0.0;
+            continue;
+        }
         const double* z = panels + diag_dest[s];
         const uint32_t ld = diag_ld[s];
         for (int r = 0; r < 3; ++r)
@@ -292,6 +309,11 @@ void launch_extract_edge_vcv(const double* panels, const uint64_t* off_dest, con
                              const uint32_t* edge_lo, const double* dscale, double* q, uint64_t nedge, void*)
 {
     for (uint64_t e = 0; e < nedge; ++e) {
+        if (off_dest[e] == ~0ull) {
+            for (int k = 0; k < 9; ++k)
+                q[9 * e + k] = 0.0;
+            continue;
+        }
         const double* z = panels + off_dest[e];
         const uint32_t ld = off_ld[e];
         for (int r = 0; r < 3; ++r)
