@@ -175,7 +175,10 @@ struct gadj_ctx {
     int reduced = 0;
     std::vector<uint32_t> isl_off, isl;
     // measurement plan
-    std::vector<uint32_t> first, edge_word;
+    std::vector<uint32_t> first, edge_word;          // GNSS baselines
+    std::vector<uint32_t> sfirst, sedge_word;        // scalar two-station rows ('S', 'L')
+    uint64_t nscalar = 0;
+    bool non_gps = false;
     std::vector<uint32_t> edge_hi, edge_lo;
     bool contiguous = false;
     uint64_t nbsl = 0, nedge = 0;
@@ -191,9 +194,9 @@ struct gadj_ctx {
     double critical = 0;
     // device state
     DevArray<dna_msr_t> d_msr;
-    DevArray<uint32_t> d_first, d_edge, d_edge_hi, d_edge_lo, d_pos, d_diag_ld, d_off_ld;
+    DevArray<uint32_t> d_first, d_edge, d_sfirst, d_sedge, d_edge_hi, d_edge_lo, d_pos, d_diag_ld, d_off_ld;
     DevArray<uint64_t> d_diag_dest, d_off_dest;
-    DevArray<double> d_est, d_est0, d_llh, d_cblock, d_ndiag, d_noff, d_w, d_dscale, d_panels, d_pool, d_x, d_corr, d_vcvd,
+    DevArray<double> d_est, d_est0, d_llh, d_llh0, d_cblock, d_ndiag, d_noff, d_w, d_dscale, d_panels, d_pool, d_x, d_corr, d_vcvd,
         d_vcvo, d_sums;
     DevArray<int32_t> d_rowmap, d_rowidx, d_info;
     DevArray<GemmOp> d_gemm;
@@ -417,9 +420,32 @@ void first_run_reduction(gadj_ctx* c)
     });
 }
 
+// first-run handling of the scalar rows: back up the raw value (InitialiseMeasurement, ADJ:3913-3935) and reduce
+// levelled height differences to ellipsoidal ones with the geoid separations (ADJ:5751-5757)
+void first_run_reduction_scalar(gadj_ctx* c)
+{
+    for (uint32_t fi : c->sfirst) {
+        dna_msr_t& m = c->msr[fi];
+        if (c->reduced) {
+            m.term1 = m.preAdjMeas;
+            continue;
+        }
+        m.preAdjMeas = m.term1;
+        if (m.measType == 'L') {
+            const dna_stn_t& s1 = c->stn[m.station1];
+            const dna_stn_t& s2 = c->stn[m.station2];
+            if (std::fabs(s1.geoidSep) > 1.0e-4 || std::fabs(s2.geoidSep) > 1.0e-4) {
+                m.preAdjCorr = s2.geoidSep - s1.geoidSep;
+                m.term1 += m.preAdjCorr;
+            }
+        }
+    }
+}
+
 int scan_measurements(gadj_ctx* c)
 {
     c->first.clear();
+    c->sfirst.clear();
     uint64_t i = 0;
     while (i < c->nmsr) {
         const dna_msr_t& m = c->msr[i];
@@ -445,19 +471,24 @@ int scan_measurements(gadj_ctx* c)
         if (step == 0)
             step = 1;
         if (!m.ignore) {
-            if (m.measType != 'G')
-                return c->fail(std::string("measurement type '") + m.measType +
-                               "' is not handled by the device assembly yet (GNSS baselines 'G' only)");
-            if (i + 3 > c->nmsr)
-                return c->fail("truncated GNSS baseline at the end of the measurement list");
             if (i > 0xFFFFFFF0ull)
                 return c->fail("measurement index exceeds 32 bits");
-            c->first.push_back((uint32_t)i);
+            if (m.measType == 'G') {
+                if (i + 3 > c->nmsr)
+                    return c->fail("truncated GNSS baseline at the end of the measurement list");
+                c->first.push_back((uint32_t)i);
+            } else if (m.measType == 'S' || m.measType == 'L') {
+                c->sfirst.push_back((uint32_t)i);
+            } else
+                return c->fail(std::string("measurement type '") + m.measType +
+                               "' is not handled by the device assembly yet (handled: G, S, L)");
         }
         i += step;
     }
     c->nbsl = c->first.size();
-    if (c->nbsl == 0)
+    c->nscalar = c->sfirst.size();
+    c->non_gps = c->nscalar > 0;   // v_msrTally_.ContainsNonGPS() (ADJ:2457)
+    if (c->nbsl + c->nscalar == 0)
         return c->fail("no measurements to adjust");
     c->contiguous = true;
     for (uint64_t b = 0; b < c->nbsl; ++b)
@@ -580,13 +611,23 @@ int gadj_prepare(gadj_ctx* c)
         if (m.station1 == m.station2)
             return c->fail("GNSS baseline with identical end stations");
     }
+    for (uint32_t fi : c->sfirst) {
+        const dna_msr_t& m = c->msr[fi];
+        if (m.station1 >= c->nstn || m.station2 >= c->nstn)
+            return c->fail("measurement refers to a station index beyond the station list");
+        if (m.station1 == m.station2)
+            return c->fail("two-station measurement with identical end stations");
+        if (!(m.term2 > 0.0))
+            return c->fail("Invalid variance matrix: non-positive measurement variance");
+    }
     first_run_reduction(c);
+    first_run_reduction_scalar(c);
 
-    // unique station pairs -> edge slots
-    const uint64_t nb = c->nbsl;
-    std::vector<uint64_t> keys(nb);
-    for (uint64_t b = 0; b < nb; ++b) {
-        const dna_msr_t& m = c->msr[c->first[b]];
+    // unique station pairs -> edge slots (baselines first, then scalar rows)
+    const uint64_t nb = c->nbsl, ns = c->nscalar;
+    std::vector<uint64_t> keys(nb + ns);
+    for (uint64_t b = 0; b < nb + ns; ++b) {
+        const dna_msr_t& m = c->msr[b < nb ? c->first[b] : c->sfirst[b - nb]];
         uint32_t lo = std::min(m.station1, m.station2), hi = std::max(m.station1, m.station2);
         keys[b] = ((uint64_t)lo << 32) | hi;
     }
@@ -651,18 +692,22 @@ int gadj_prepare(gadj_ctx* c)
         diag_ld[s] = S.ndest_ld[slot];
     }
     c->edge_word.resize(nb);
-    parallel_for(nb, [&](uint64_t b0, uint64_t b1) {
+    c->sedge_word.resize(ns);
+    parallel_for(nb + ns, [&](uint64_t b0, uint64_t b1) {
         for (uint64_t b = b0; b < b1; ++b) {
-            const dna_msr_t& m = c->msr[c->first[b]];
+            const dna_msr_t& m = c->msr[b < nb ? c->first[b] : c->sfirst[b - nb]];
             uint64_t ei = std::lower_bound(uniq.begin(), uniq.end(), keys[b]) - uniq.begin();
             uint32_t flip = S.pos_of_stn[m.station1] > S.pos_of_stn[m.station2] ? 0x80000000u : 0u;
-            c->edge_word[b] = (uint32_t)ei | flip;
+            (b < nb ? c->edge_word[b] : c->sedge_word[b - nb]) = (uint32_t)ei | flip;
         }
     });
 
     // a-priori Cartesian coordinates and constraint blocks
-    std::vector<double> est(3 * (size_t)c->nstn), cb(9 * (size_t)c->nstn);
+    std::vector<double> est(3 * (size_t)c->nstn), cb(9 * (size_t)c->nstn), llh0(3 * (size_t)c->nstn);
     for (uint32_t s = 0; s < c->nstn; ++s) {
+        llh0[3 * s] = c->stn[s].currentLatitude;
+        llh0[3 * s + 1] = c->stn[s].currentLongitude;
+        llh0[3 * s + 2] = c->stn[s].currentHeight;
         geo_to_cart(c->ell, c->stn[s].currentLatitude, c->stn[s].currentLongitude, c->stn[s].currentHeight, &est[3 * s]);
         if (!constraint_block(c, c->stn[s], &cb[9 * s]))
             return c->fail("station constraint variance matrix is not positive definite");
@@ -675,6 +720,8 @@ int gadj_prepare(gadj_ctx* c)
     ok &= c->d_msr.resize(c->nmsr);
     ok &= c->d_first.upload(c->first);
     ok &= c->d_edge.upload(c->edge_word);
+    ok &= c->d_sfirst.upload(c->sfirst);
+    ok &= c->d_sedge.upload(c->sedge_word);
     ok &= c->d_edge_hi.upload(c->edge_hi);
     ok &= c->d_edge_lo.upload(c->edge_lo);
     ok &= c->d_pos.upload(S.pos_of_stn);
@@ -686,7 +733,8 @@ int gadj_prepare(gadj_ctx* c)
     ok &= c->d_est.upload(est);
     ok &= c->d_est0.upload(est);
     ok &= c->d_cblock.upload(cb);
-    ok &= c->d_llh.resize(3 * (size_t)c->nstn);
+    ok &= c->d_llh.upload(llh0);
+    ok &= c->d_llh0.upload(llh0);
     ok &= c->d_ndiag.resize(9 * (size_t)c->nstn);
     ok &= c->d_noff.resize(9 * (size_t)c->nedge);
     ok &= c->d_w.resize(3 * (size_t)c->nstn);
@@ -787,6 +835,7 @@ int gadj_reset_estimates(gadj_ctx* c)
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     dev::d2d(c->d_est.p, c->d_est0.p, c->d_est.bytes());
+    dev::d2d(c->d_llh.p, c->d_llh0.p, c->d_llh.bytes());
     c->iteration = 0;
     c->factor_valid = c->inverse_valid = false;
     return 0;
@@ -805,6 +854,26 @@ static void fill_assemble(gadj_ctx* c, AssembleParams& ap, int normals)
     ap.nbaselines = c->nbsl;
     ap.contiguous = c->contiguous ? 1 : 0;
     ap.normals = normals;
+}
+
+static void fill_scalar(gadj_ctx* c, ScalarParams& sp, int normals)
+{
+    sp.msr = c->d_msr.p;
+    sp.first = c->d_sfirst.p;
+    sp.edge = c->d_sedge.p;
+    sp.est = c->d_est.p;
+    sp.llh = c->d_llh.p;
+    sp.ndiag = c->d_ndiag.p;
+    sp.noff = c->d_noff.p;
+    sp.w = c->d_w.p;
+    sp.vcv_diag = c->d_vcvd.p;
+    sp.vcv_off = c->d_vcvo.p;
+    sp.sums = c->d_sums.p;
+    sp.nrows = c->nscalar;
+    sp.semi_major = c->o.semi_major;
+    sp.inv_flattening = c->o.inv_flattening;
+    sp.critical = c->critical;
+    sp.normals = normals;
 }
 
 static void fill_scatter(gadj_ctx* c, ScatterParams& sp)
@@ -835,9 +904,13 @@ int gadj_stage_begin(gadj_ctx* c, int flags)
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     void* st = dev::stream();
-    const bool normals = (flags & GADJ_ITER_NORMALS) || !c->factor_valid;
+    // non-GNSS rows: the partials move with the estimates, so the normals are rebuilt on every iteration and the
+    // geographic coordinates are refreshed first (UpdateAdjustment, ADJ:543-545, 583-589)
+    const bool normals = (flags & GADJ_ITER_NORMALS) || !c->factor_valid || c->non_gps;
     c->stage_normals = normals;
     dev::event_record(c->ev[0]);
+    if (c->non_gps && c->iteration > 0)
+        launch_cart_to_geo(c->d_est.p, c->d_llh.p, c->nstn, c->o.semi_major, c->o.inv_flattening, st);
     // ---- assembly (FillDesignNormalMeasurementsMatrices, ADJ:3888) --------------
     c->prof_begin(PK_ASSEMBLE);
     launch_init_normals(normals ? c->d_cblock.p : nullptr, c->d_ndiag.p, c->d_noff.p, c->d_w.p, c->nstn,
@@ -848,6 +921,13 @@ int gadj_stage_begin(gadj_ctx* c, int flags)
     c->prof_begin(PK_ASSEMBLE);
     launch_assemble_g(ap, st);
     c->prof_end();
+    if (c->nscalar) {
+        ScalarParams sp;
+        fill_scalar(c, sp, normals ? 1 : 0);
+        c->prof_begin(PK_ASSEMBLE);
+        launch_assemble_scalar(sp, st);
+        c->prof_end();
+    }
     dev::event_record(c->ev[1]);
     // ---- equilibrate + scatter into the front panels ------------------------------
     if (normals) {
@@ -1165,6 +1245,11 @@ int gadj_statistics(gadj_ctx* c, gadj_stats* stt, int write_back)
     sp.nbaselines = c->nbsl;
     sp.critical = c->critical;
     launch_stats_g(sp, st);
+    if (c->nscalar) {
+        ScalarParams scp;
+        fill_scalar(c, scp, 0);
+        launch_stats_scalar(scp, st);
+    }
     double sums[8];
     dev::d2h(sums, c->d_sums.p, sizeof(sums));
     std::vector<double> llh;
@@ -1184,7 +1269,7 @@ int gadj_statistics(gadj_ctx* c, gadj_stats* stt, int write_back)
         }
     std::memset(stt, 0, sizeof(*stt));
     stt->chi_squared = sums[0];
-    stt->measurement_params = (uint32_t)(3 * c->nbsl);
+    stt->measurement_params = (uint32_t)(3 * c->nbsl + c->nscalar);
     stt->unknown_params = 3 * c->nstn - c->constrained_components;
     stt->dof = (int64_t)stt->measurement_params - (int64_t)stt->unknown_params;   // ADJ:6856
     stt->sigma_zero = stt->dof != 0 ? stt->chi_squared / (double)stt->dof : 0.0;

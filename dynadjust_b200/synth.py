@@ -191,6 +191,64 @@ def gnss_network(n_stations, n_baselines, seed, hub_fraction=0.0, n_hubs=0, apri
     return stn, msr, truth, edges
 
 
+def mixed_network(n_stations, n_baselines, seed, n_distances=0, n_levels=0, **kw):
+    """GNSS network plus terrestrial rows between grid neighbours: slope distances 'S' (sigma 2 mm + 2 ppm,
+    instrument / target heights ~1.5 m) and levelled height differences 'L' (sigma 1 mm * sqrt(km), orthometric,
+    reduced by adjust with the stations' geoid separations).  The terrestrial records follow the baselines."""
+    stn, gmsr, truth, edges = gnss_network(n_stations, n_baselines, seed, **kw)
+    rng = np.random.default_rng(seed + 7919)
+    a, invf = kw.get("a", GRS80_A), kw.get("invf", GRS80_INVF)
+    _, _, e2 = ellipsoid(a, invf)
+    tlat, tlon, th = cart_to_geo(truth, a, invf)
+    pairs = grid_edges(n_stations, max(n_distances, n_levels, 1), rng)
+    recs = []
+    if n_distances:
+        pr = pairs[rng.choice(len(pairs), size=n_distances, replace=False)]
+        s1, s2 = pr[:, 0], pr[:, 1]
+        ih = rng.uniform(1.2, 1.8, n_distances)
+        tg = rng.uniform(1.2, 1.8, n_distances)
+        # the adjustment model rotates both heights at station 1 (CartesianElementsFromInstrumentHeight)
+        up1 = np.stack([np.cos(tlat[s1]) * np.cos(tlon[s1]), np.cos(tlat[s1]) * np.sin(tlon[s1]), np.sin(tlat[s1])], axis=1)
+        d = np.linalg.norm(truth[s2] - truth[s1] + up1 * (tg - ih)[:, None], axis=1)
+        sig = 0.002 + 2.0e-6 * d
+        m = new_msr(n_distances)
+        m["measType"] = b"S"
+        m["measurementStations"] = 2
+        m["station1"], m["station2"] = s1, s2
+        m["term1"] = d + sig * rng.standard_normal(n_distances)
+        m["term2"] = sig ** 2
+        m["term3"], m["term4"] = ih, tg
+        recs.append(m)
+    if n_levels:
+        pr = pairs[rng.choice(len(pairs), size=n_levels, replace=False)]
+        s1, s2 = pr[:, 0], pr[:, 1]
+
+        def ell_height(i):
+            nu = a / np.sqrt(1.0 - e2 * np.sin(tlat[i]) ** 2)
+            zn = e2 * nu * np.sin(tlat[i])
+            return np.sqrt(truth[i, 0] ** 2 + truth[i, 1] ** 2 + (truth[i, 2] + zn) ** 2) - nu
+        dh = ell_height(s2) - ell_height(s1)
+        dist_km = np.linalg.norm(truth[s2] - truth[s1], axis=1) / 1000.0
+        sig = 0.001 * np.sqrt(np.maximum(dist_km, 0.05))
+        geoid = stn["geoidSep"].astype(np.float64)      # float32 in the record: use exactly what adjust will read
+        m = new_msr(n_levels)
+        m["measType"] = b"L"
+        m["measurementStations"] = 2
+        m["station1"], m["station2"] = s1, s2
+        m["term1"] = dh - (geoid[s2] - geoid[s1]) + sig * rng.standard_normal(n_levels)
+        m["term2"] = sig ** 2
+        recs.append(m)
+    # (np.concatenate would repack the padded record dtype: copy into a fresh array of the exact layout instead)
+    msr = new_msr(len(gmsr) + sum(len(r) for r in recs))
+    msr[:len(gmsr)] = gmsr
+    o = len(gmsr)
+    for r in recs:
+        msr[o:o + len(r)] = r
+        o += len(r)
+    msr["fileOrder"] = np.arange(len(msr), dtype=np.uint32)
+    return stn, msr, truth, edges
+
+
 # BASELINE.json configurations (SURVEY.md §8d): seeds 1234 + config index
 CONFIGS = {
     "C1": dict(n_stations=100, n_baselines=300, seed=1235),

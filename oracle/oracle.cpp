@@ -332,6 +332,7 @@ struct Ctx {
     std::vector<double> est;       // estimated stations (3S)
     std::vector<double> ell_rows;  // measured - computed, one per design row
     std::vector<double> vinv;      // per GNSS baseline: 3x3 V^-1 (column-major), in CML order
+    std::vector<double> apart;     // per scalar row: partials wrt station 1 (3) and station 2 (3)
     std::vector<double> N;         // packed normals / after Solve: packed inverse
     std::vector<double> corr;      // corrections
     std::vector<double> w;         // At V^-1 l
@@ -455,10 +456,12 @@ int build_cml(Ctx& c)
             step = 1;
         }
         if (!m.ignore) {
-            if (m.measType != 'G') {
+            if (m.measType != 'G' && m.measType != 'S' && m.measType != 'L') {
                 g_err = std::string("oracle: measurement type '") + m.measType + "' not restated yet";
                 return 3;
             }
+            if (m.measType != 'G')
+                c.non_gps = true;
             c.cml.push_back(i);
         }
         i += step;
@@ -466,13 +469,21 @@ int build_cml(Ctx& c)
     return 0;
 }
 
+// EllipsoidHeight (GEO:909-920)
+double ellipsoid_height(const Ellipsoid& e, double X, double Y, double Z, double lat, double* nu, double* Zn)
+{
+    *nu = prime_vertical(e, lat);
+    *Zn = e.e2 * (*nu) * std::sin(lat);
+    return std::sqrt(X * X + Y * Y + std::pow(Z + (*Zn), 2)) - (*nu);
+}
+
 // FillDesignNormalMeasurementsMatrices (ADJ:3888-4055) for the types restated.
-//   build=true : first pass — l, V^-1 (with variance scaling write-back), N
-//   build=false: re-linearise — l only (GNSS design never changes, ADJ:5294-5301)
+//   build=true : first pass — l, partials, V^-1 (with variance scaling write-back), first-run reductions
+//   build=false: re-linearise — l (and the partials of the non-GNSS rows; GNSS design never changes, ADJ:5294-5301)
 int fill_design_normals(Ctx& c, bool build)
 {
     uint32_t row = 0;
-    size_t g = 0;
+    size_t g = 0, sc = 0;
     for (uint64_t first : c.cml) {
         dna_msr_t* m = &c.msr[first];
         switch (m->measType) {
@@ -492,23 +503,64 @@ int fill_design_normals(Ctx& c, bool build)
                     return rc;
                 }
                 std::memcpy(&c.vinv[g * 9], Vinv.v, sizeof(Vinv.v));
-                // UpdateNormals_G (ADJ:1664-1684) through add_normal_3x3_from_atvinv_columns (ADJ:1478-1491):
-                // AtVinv[s1.., rows] = -V^-1 ; AtVinv[s2.., rows] = +V^-1
-                for (int col = 0; col < 3; ++col)
-                    for (int r = 0; r < 3; ++r)
-                        lower_add(c, s2 + r, s2 + col, 1. * Vinv(r, col));
-                for (int col = 0; col < 3; ++col)
-                    for (int r = 0; r < 3; ++r)
-                        lower_add(c, s1 + r, s1 + col, -1. * (-Vinv(r, col)));
-                for (int col = 0; col < 3; ++col)
-                    for (int r = 0; r < 3; ++r)
-                        lower_add(c, s1 + r, s2 + col, 1. * (-Vinv(r, col)));
-                for (int col = 0; col < 3; ++col)
-                    for (int r = 0; r < 3; ++r)
-                        lower_add(c, s2 + r, s1 + col, -1. * Vinv(r, col));
             }
             row += 3;
             ++g;
+            break;
+        }
+        case 'S': {
+            // UpdateDesignNormalMeasMatrices_S (ADJ:5437-5493)
+            if (build)
+                m->preAdjMeas = m->term1;
+            uint32_t s1 = m->station1 * 3, s2 = m->station2 * 3;
+            const dna_stn_t& st1 = c.stn[m->station1];
+            double cl = std::cos(st1.currentLatitude), sl = std::sin(st1.currentLatitude);
+            double co = std::cos(st1.currentLongitude), so = std::sin(st1.currentLongitude);
+            // CartesianElementsFromInstrumentHeight (GEO:763-771): both heights are rotated at station 1
+            double dXih = cl * co * m->term3, dYih = cl * so * m->term3, dZih = sl * m->term3;
+            double dXth = cl * co * m->term4, dYth = cl * so * m->term4, dZth = sl * m->term4;
+            double dX = c.est[s2] - c.est[s1] + dXth - dXih;
+            double dY = c.est[s2 + 1] - c.est[s1 + 1] + dYth - dYih;
+            double dZ = c.est[s2 + 2] - c.est[s1 + 2] + dZth - dZih;
+            double comp = std::sqrt(dX * dX + dY * dY + dZ * dZ);
+            c.ell_rows[row] = m->term1 - comp;
+            double* a = &c.apart[sc * 6];
+            a[0] = -dX / comp;
+            a[1] = -dY / comp;
+            a[2] = -dZ / comp;
+            a[3] = -a[0];
+            a[4] = -a[1];
+            a[5] = -a[2];
+            row += 1;
+            ++sc;
+            break;
+        }
+        case 'L': {
+            // UpdateDesignNormalMeasMatrices_L (ADJ:5717-5784)
+            uint32_t s1 = m->station1 * 3, s2 = m->station2 * 3;
+            const dna_stn_t& st1 = c.stn[m->station1];
+            const dna_stn_t& st2 = c.stn[m->station2];
+            double nu1, nu2, Zn1, Zn2;
+            double h1 = ellipsoid_height(c.ell, c.est[s1], c.est[s1 + 1], c.est[s1 + 2], st1.currentLatitude, &nu1, &Zn1);
+            double h2 = ellipsoid_height(c.ell, c.est[s2], c.est[s2 + 1], c.est[s2 + 2], st2.currentLatitude, &nu2, &Zn2);
+            double comp = h2 - h1;
+            if (build) {
+                m->preAdjMeas = m->term1;   // InitialiseMeasurement (ADJ:3913-3935)
+                if (std::fabs(st1.geoidSep) > 1.0e-4 || std::fabs(st2.geoidSep) > 1.0e-4) {
+                    m->preAdjCorr = st2.geoidSep - st1.geoidSep;
+                    m->term1 += m->preAdjCorr;
+                }
+            }
+            c.ell_rows[row] = m->term1 - comp;
+            double* a = &c.apart[sc * 6];
+            a[0] = -c.est[s1] / (nu1 + h1);
+            a[1] = -c.est[s1 + 1] / (nu1 + h1);
+            a[2] = -(c.est[s1 + 2] + Zn1) / (nu1 + h1);
+            a[3] = c.est[s2] / (nu2 + h2);
+            a[4] = c.est[s2 + 1] / (nu2 + h2);
+            a[5] = (c.est[s2 + 2] + Zn2) / (nu2 + h2);
+            row += 1;
+            ++sc;
             break;
         }
         default:
@@ -516,6 +568,41 @@ int fill_design_normals(Ctx& c, bool build)
         }
     }
     return 0;
+}
+
+// UpdateNormals (ADJ:1364-1455): N from the stored At V^-1 / design of every measurement
+void update_normals(Ctx& c)
+{
+    size_t g = 0, sc = 0;
+    for (uint64_t first : c.cml) {
+        const dna_msr_t* m = &c.msr[first];
+        uint32_t s1 = m->station1 * 3, s2 = m->station2 * 3;
+        if (m->measType == 'G') {
+            // UpdateNormals_G (ADJ:1664-1684) through add_normal_3x3_from_atvinv_columns (ADJ:1478-1491):
+            // AtVinv[s1.., rows] = -V^-1 ; AtVinv[s2.., rows] = +V^-1
+            M3 Vinv;
+            std::memcpy(Vinv.v, &c.vinv[g * 9], sizeof(Vinv.v));
+            for (int col = 0; col < 3; ++col)
+                for (int r = 0; r < 3; ++r) {
+                    lower_add(c, s2 + r, s2 + col, 1. * Vinv(r, col));
+                    lower_add(c, s1 + r, s1 + col, -1. * (-Vinv(r, col)));
+                    lower_add(c, s1 + r, s2 + col, 1. * (-Vinv(r, col)));
+                    lower_add(c, s2 + r, s1 + col, -1. * Vinv(r, col));
+                }
+            ++g;
+        } else {
+            // UpdateNormals_BCEKLMSVZ (ADJ:1640-1651): At V^-1 = a / term2 (UpdateAtVinv, ADJ:1285-1320)
+            const double* a = &c.apart[sc * 6];
+            const double p = 1. / m->term2;
+            const uint32_t st[2] = {s1, s2};
+            for (int bi = 0; bi < 2; ++bi)
+                for (int bj = 0; bj < 2; ++bj)
+                    for (int col = 0; col < 3; ++col)
+                        for (int r = 0; r < 3; ++r)
+                            lower_add(c, st[bi] + r, st[bj] + col, (p * a[3 * bi + r]) * a[3 * bj + col]);
+            ++sc;
+        }
+    }
 }
 
 // FormConstraintStationVarianceMatrix (ADJ:2041-2137) -> inverse variance block
@@ -576,7 +663,7 @@ void weighted_rhs(Ctx& c)
 {
     std::fill(c.w.begin(), c.w.end(), 0.0);
     uint32_t row = 0;
-    size_t g = 0;
+    size_t g = 0, sc = 0;
     for (uint64_t first : c.cml) {
         const dna_msr_t* m = &c.msr[first];
         if (m->measType == 'G') {
@@ -591,6 +678,16 @@ void weighted_rhs(Ctx& c)
             }
             row += 3;
             ++g;
+        } else {
+            uint32_t s1 = m->station1 * 3, s2 = m->station2 * 3;
+            const double* a = &c.apart[sc * 6];
+            const double p = 1. / m->term2;
+            for (int r = 0; r < 3; ++r) {
+                c.w[s1 + r] += (p * a[r]) * c.ell_rows[row];
+                c.w[s2 + r] += (p * a[3 + r]) * c.ell_rows[row];
+            }
+            row += 1;
+            ++sc;
         }
     }
 }
@@ -825,12 +922,14 @@ int oracle_adjust_simultaneous(const oracle_opts* opts, dna_stn_t* stn, uint32_t
     c.N.assign(psize(c.n), 0.0);
     c.ell_rows.assign(c.rows, 0.0);
     c.vinv.assign(c.cml.size() * 9, 0.0);
+    c.apart.assign(c.cml.size() * 6, 0.0);
     c.corr.assign(c.n, 0.0);
     c.w.assign(c.n, 0.0);
 
     rc = fill_design_normals(c, true);
     if (rc)
         return rc;
+    update_normals(c);
     rc = add_constraints(c);
     if (rc)
         return rc;
@@ -870,11 +969,22 @@ int oracle_adjust_simultaneous(const oracle_opts* opts, dna_stn_t* stn, uint32_t
         if (!iterate)
             break;
         bool lastIteration = (i + 1 >= opts->max_iterations);
-        // UpdateAdjustment(!lastIteration) (ADJ:473-627), simultaneous GNSS-only: l only
+        // UpdateAdjustment(!lastIteration) (ADJ:473-627)
+        if (c.non_gps || lastIteration)   // UpdateGeographicCoords (ADJ:543-545, ADJ:8734)
+            for (uint32_t s = 0; s < nstn; ++s)
+                cart_to_geo(c.ell, c.est[3 * s], c.est[3 * s + 1], c.est[3 * s + 2], &stn[s].currentLatitude,
+                            &stn[s].currentLongitude, &stn[s].currentHeight);
         rc = fill_design_normals(c, false);
         if (rc)
             return rc;
-        (void)lastIteration;
+        if (!lastIteration && c.non_gps) {
+            // partials changed: rebuild the normals (ADJ:583-589)
+            std::fill(c.N.begin(), c.N.end(), 0.0);
+            update_normals(c);
+            rc = add_constraints(c);
+            if (rc)
+                return rc;
+        }
     }
     res->iterations = iter;
     res->max_corr = maxCorr;
@@ -894,11 +1004,32 @@ int oracle_adjust_simultaneous(const oracle_opts* opts, dna_stn_t* stn, uint32_t
     double chi = 0.;
     {
         uint32_t row = 0;
+        size_t sc = 0;
+        auto Q = [&](uint32_t i, uint32_t j) { return i >= j ? c.N[pidx(c.n, i, j)] : c.N[pidx(c.n, j, i)]; };
         for (uint64_t first : c.cml) {
             dna_msr_t* m = &msr[first];
-            if (m->measType != 'G')
-                continue;
             uint32_t s1 = m->station1 * 3, s2 = m->station2 * 3;
+            if (m->measType != 'G') {
+                // ComputePrecisionAdjMsrs_BCEKLMSVZ (ADJ:7949-7982): a Q a^T over the two stations
+                const double* a = &c.apart[sc * 6];
+                const uint32_t st[2] = {s1, s2};
+                double prec = 0.;
+                for (int bs = 0; bs < 2; ++bs)
+                    for (int i = 0; i < 3; ++i) {
+                        double part = 0.;
+                        for (int bj = 0; bj < 2; ++bj)
+                            for (int k = 0; k < 3; ++k)
+                                part += a[3 * bj + k] * Q(st[bj] + k, st[bs] + i);
+                        prec += part * a[3 * bs + i];
+                    }
+                update_msr_record(*m, c.ell_rows[row], prec, m->term2, critical, outliers);
+                if (m->measType == 'L')
+                    m->measAdj -= m->preAdjCorr;   // ADJ:8241-8244
+                chi += c.ell_rows[row] * c.ell_rows[row] / m->term2;   // ADJ:8430-8437
+                row += 1;
+                ++sc;
+                continue;
+            }
             // ComputePrecisionAdjMsrs_GX (ADJ:8006-8032)
             double p6[6];
             precision_adjusted_gnss_bsl(c, s1, s2, p6);
@@ -931,8 +1062,14 @@ int oracle_adjust_simultaneous(const oracle_opts* opts, dna_stn_t* stn, uint32_t
         uint32_t num = 0;
         for (uint64_t first : c.cml) {
             dna_msr_t* m = &msr[first];
-            if (m->measType != 'G')
+            if (m->measType != 'G') {
+                if (m->PelzerRel > 0. && m->PelzerRel < STABLE_LIMIT) {   // ADJ:8339-8345
+                    sum += (m->PelzerRel * m->PelzerRel - 1.);
+                    num++;
+                } else
+                    m->PelzerRel = UNRELIABLE;
                 continue;
+            }
             for (int k = 0; k < 3; ++k) {
                 if (m[k].PelzerRel > 0. && m[k].PelzerRel < UNRELIABLE) {
                     sum += (m[k].PelzerRel * m[k].PelzerRel - 1.);

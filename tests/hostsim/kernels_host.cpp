@@ -225,6 +225,83 @@ void launch_assemble_g(const AssembleParams& p, void*)
     }
 }
 
+void launch_assemble_scalar(const ScalarParams& p, void*)
+{
+    const Ellipsoid ell = make_ellipsoid(p.semi_major, p.inv_flattening);
+    for (uint64_t i = 0; i < p.nrows; ++i) {
+        const dna_msr_t* m = p.msr + p.first[i];
+        const uint32_t s1 = m->station1, s2 = m->station2;
+        ScalarRow r;
+        if (!scalar_row(m->measType, m->term1, m->term2, m->term3, m->term4, p.est + 3 * (size_t)s1, p.est + 3 * (size_t)s2,
+                        p.llh + 3 * (size_t)s1, p.llh + 3 * (size_t)s2, ell, r))
+            continue;
+        for (int k = 0; k < 3; ++k) {
+            p.w[3 * (size_t)s1 + k] += r.p * r.a[k] * r.l;
+            p.w[3 * (size_t)s2 + k] += r.p * r.a[3 + k] * r.l;
+        }
+        if (p.normals) {
+            const uint32_t ew = p.edge[i];
+            const double* ahi = (ew & 0x80000000u) ? r.a : r.a + 3;
+            const double* alo = (ew & 0x80000000u) ? r.a + 3 : r.a;
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) {
+                    p.ndiag[9 * (size_t)s1 + 3 * a + b] += r.p * r.a[a] * r.a[b];
+                    p.ndiag[9 * (size_t)s2 + 3 * a + b] += r.p * r.a[3 + a] * r.a[3 + b];
+                    p.noff[9 * (size_t)(ew & 0x7FFFFFFFu) + 3 * a + b] += r.p * ahi[a] * alo[b];
+                }
+        }
+    }
+}
+
+void launch_stats_scalar(const ScalarParams& p, void*)
+{
+    const Ellipsoid ell = make_ellipsoid(p.semi_major, p.inv_flattening);
+    for (uint64_t i = 0; i < p.nrows; ++i) {
+        dna_msr_t* m = p.msr + p.first[i];
+        const uint32_t s1 = m->station1, s2 = m->station2;
+        ScalarRow r;
+        if (!scalar_row(m->measType, m->term1, m->term2, m->term3, m->term4, p.est + 3 * (size_t)s1, p.est + 3 * (size_t)s2,
+                        p.llh + 3 * (size_t)s1, p.llh + 3 * (size_t)s2, ell, r))
+            continue;
+        const uint32_t ew = p.edge[i];
+        const double* Qo = p.vcv_off + 9 * (size_t)(ew & 0x7FFFFFFFu);
+        const bool s1_is_hi = (ew & 0x80000000u) != 0;
+        const double* Q11 = p.vcv_diag + 9 * (size_t)s1;
+        const double* Q22 = p.vcv_diag + 9 * (size_t)s2;
+        double prec = 0.0;
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+                const double q21 = s1_is_hi ? Qo[3 * b + a] : Qo[3 * a + b];
+                prec += r.a[a] * Q11[3 * a + b] * r.a[b] + r.a[3 + a] * Q22[3 * a + b] * r.a[3 + b] + 2.0 * r.a[3 + a] * q21 * r.a[b];
+            }
+        const double corr = -r.l;
+        double rp = m->term2 - prec;
+        if (rp < 0.0)
+            rp = std::fabs(rp);
+        double pel = std::sqrt(m->term2) / std::sqrt(rp);
+        if (pel < 0. || pel > 700.)
+            pel = 999.99;
+        const double nstat = corr / std::sqrt(rp);
+        if (std::fabs(nstat) > p.critical)
+            p.sums[3] += 1.0;
+        if (pel > 0. && pel < 700.) {
+            p.sums[1] += pel * pel - 1.;
+            p.sums[2] += 1.0;
+        } else
+            pel = 999.99;
+        double adj = m->term1 + corr;
+        if (m->measType == 'L')
+            adj -= m->preAdjCorr;
+        m->measCorr = corr;
+        m->measAdj = adj;
+        m->measAdjPrec = prec;
+        m->residualPrec = rp;
+        m->NStat = nstat;
+        m->PelzerRel = pel;
+        p.sums[0] += r.l * r.l / m->term2;
+    }
+}
+
 void launch_compute_scale(const ScatterParams& p, void*)
 {
     for (uint32_t s = 0; s < p.nstn; ++s)

@@ -23,8 +23,12 @@ def run_engine(lib_path, stn, msr, blocks=None, **opts):
     return adj, info, last, stats
 
 
-def check_against_oracle(oracle, lib_path, n_stations, n_baselines, seed, blocks=None, mutate=None, **opts):
-    stn, msr, truth, edges = synth.gnss_network(n_stations, n_baselines, seed)
+def check_against_oracle(oracle, lib_path, n_stations, n_baselines, seed, blocks=None, mutate=None, n_distances=0,
+                         n_levels=0, **opts):
+    if n_distances or n_levels:
+        stn, msr, truth, edges = synth.mixed_network(n_stations, n_baselines, seed, n_distances=n_distances, n_levels=n_levels)
+    else:
+        stn, msr, truth, edges = synth.gnss_network(n_stations, n_baselines, seed)
     if mutate:
         mutate(stn, msr, truth)
     stn_o, msr_o = stn.copy(), msr.copy()
@@ -46,7 +50,7 @@ def check_against_oracle(oracle, lib_path, n_stations, n_baselines, seed, blocks
     q = adj.station_vcvs()
     qd = np.stack([V[3 * s:3 * s + 3, 3 * s:3 * s + 3] for s in range(S)])
     assert np.abs(q - qd).max() < TOL_VCV_REL * vscale
-    rec = msr.reshape(-1, 3)
+    rec = msr[:3 * n_baselines].reshape(-1, 3)
     step = max(1, len(rec) // 64)
     for b in range(0, len(rec), step):
         s1, s2 = int(rec["station1"][b, 0]), int(rec["station2"][b, 0])
@@ -56,8 +60,8 @@ def check_against_oracle(oracle, lib_path, n_stations, n_baselines, seed, blocks
     # statistics written back into the measurement records (ADJ:8187-8298)
     for f, tol in [("measCorr", 1e-9), ("measAdj", 1e-9), ("measAdjPrec", 4 * TOL_VCV_REL * vscale),
                    ("residualPrec", 4 * TOL_VCV_REL * vscale),
-                   ("NStat", 1e-6), ("PelzerRel", 1e-6)]:
-        assert np.abs(msr[f] - msr_o[f]).max() < tol, f
+                   ("NStat", 1e-6), ("PelzerRel", 1e-6), ("preAdjCorr", 0.0), ("term1", 0.0), ("preAdjMeas", 0.0)]:
+        assert np.abs(msr[f] - msr_o[f]).max() <= tol, f
     assert np.abs(stn["currentLatitude"] - stn_o["currentLatitude"]).max() < 1e-15
     assert np.abs(stn["currentHeight"] - stn_o["currentHeight"]).max() < 1e-8
     adj.close()

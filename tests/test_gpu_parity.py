@@ -22,6 +22,13 @@ def test_gemm_tile_kernel(gpu_lib, M, N, K):
     adj.close()
 
 
+def test_mixed_terrestrial_rows(oracle, gpu_lib):
+    """GNSS baselines + slope distances 'S' + levelled height differences 'L' (geoid-reduced on the first run):
+    the partials move with the estimates, so the normals are rebuilt and refactorised on every iteration."""
+    parity.check_against_oracle(oracle, gpu_lib, 200, 600, 17, n_distances=150, n_levels=120, leaf_stations=16)
+    parity.check_against_oracle(oracle, gpu_lib, 300, 500, 23, n_distances=400, n_levels=300, leaf_stations=24)
+
+
 def test_normals_and_rhs(oracle, gpu_lib):
     parity.check_normals(oracle, gpu_lib, 80, 240, 4, leaf_stations=12)
 

@@ -59,6 +59,13 @@ def test_variance_scaling(oracle, hostsim_path):
     parity.check_against_oracle(oracle, hostsim_path, 100, 300, 8, mutate=mutate, leaf_stations=16)
 
 
+def test_mixed_terrestrial_rows(oracle, hostsim_path):
+    """GNSS baselines + slope distances 'S' + levelled height differences 'L' (geoid-reduced on the first run):
+    the partials move with the estimates, so the normals are rebuilt and refactorised on every iteration."""
+    parity.check_against_oracle(oracle, hostsim_path, 200, 600, 17, n_distances=150, n_levels=120, leaf_stations=16)
+    parity.check_against_oracle(oracle, hostsim_path, 300, 500, 23, n_distances=400, n_levels=300, leaf_stations=24)
+
+
 def test_normals_and_rhs(oracle, hostsim_path):
     parity.check_normals(oracle, hostsim_path, 80, 240, 4, leaf_stations=12)
 
