@@ -1059,6 +1059,9 @@ int gadj_stage_end(gadj_ctx* c, int flags, int32_t global_info, gadj_iter_result
         res->ms_factor = dev::event_elapsed_ms(c->ev[1], c->ev[2]);
         res->ms_solve = dev::event_elapsed_ms(c->ev[2], c->ev[3]);
         res->ms_inverse = dev::event_elapsed_ms(c->ev[3], c->ev[4]);
+        res->max_corr_xyz[0] = tail[2];
+        res->max_corr_xyz[1] = tail[3];
+        res->max_corr_xyz[2] = tail[4];
         if (std::isnan(tail[0]) || std::isinf(tail[0]))
             return c->fail("Solve(): Invalid variance matrix");
     }
@@ -1176,6 +1179,28 @@ int gadj_mg_extract_vcv(gadj_ctx* c)
     return extract_vcv(c);
 }
 
+int gadj_form_inverse(gadj_ctx* c)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    if (c->inverse_valid)
+        return 0;
+    if (!c->factor_valid)
+        return c->fail("no valid factorisation to invert (run gadj_iterate first)");
+    if (c->mg_world > 1)
+        return c->fail("this context is one shard of a multi-GPU adjustment: drive it through the staged calls");
+    dev::event_record(c->ev[3]);
+    run_launches(c, c->plan.selinv);
+    dev::event_record(c->ev[4]);
+    std::string e = dev::sync();
+    if (!e.empty())
+        return c->fail(e);
+    c->inverse_valid = true;
+    c->vcv_extracted = false;
+    c->factor_valid = false;
+    return 0;
+}
+
 int gadj_adjust(gadj_ctx* c, gadj_iter_result* last)
 {
     if (!c->prepared)
@@ -1193,16 +1218,9 @@ int gadj_adjust(gadj_ctx* c, gadj_iter_result* last)
     }
     // rigorous variances (the reference carries them in v_normals_ after Solve)
     if (!c->inverse_valid) {
-        dev::event_record(c->ev[3]);
-        run_launches(c, c->plan.selinv);
-        dev::event_record(c->ev[4]);
-        std::string e = dev::sync();
-        if (!e.empty())
-            return c->fail(e);
+        if (gadj_form_inverse(c))
+            return 1;
         ms_inv = dev::event_elapsed_ms(c->ev[3], c->ev[4]);
-        c->inverse_valid = true;
-        c->vcv_extracted = false;
-        c->factor_valid = false;
     }
     r.ms_inverse = ms_inv;
     if (last)

@@ -1,0 +1,474 @@
+// dna_adjust_host.hpp — host-side C++ mirror of the reference's `dna_adjust` interface for the solve path,
+// implemented on the C-ABI (include/gadj.h).  Member names, argument meaning and error behaviour follow
+// dynadjust/dynadjust/dnaadjust/dnaadjust.hpp:212-1362 (PrepareAdjustment :260, AdjustNetwork :405,
+// GenerateStatistics :259, getters :336-354) and the wrapper's call order (dnaadjustwrapper.cpp:1142-1432);
+// the text outputs follow dnaadjust_printer.cpp (header :3436-3599, iteration block :70-92, statistics :660-719,
+// adjusted measurements, adjusted stations :3917-4070).
+#pragma once
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <iomanip>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/gadj.h"
+#include "dna_files.hpp"
+
+namespace dynadjust_b200 {
+
+enum ADJUST_MODE { SimultaneousMode = 0, PhasedMode = 1, Phased_Block_1Mode = 2 };
+enum ADJUST_STATUS { ADJUST_SUCCESS = 0, ADJUST_MAX_ITERATIONS_EXCEEDED = 2, ADJUST_EXCEPTION_RAISED = 4 };
+
+struct adjust_settings {            // the fields of project_settings.a / .g / .o the solve path reads
+    std::string network_name;
+    std::string input_folder = ".", output_folder = ".";
+    int adjust_mode = SimultaneousMode;
+    double iteration_threshold = (double)0.0005f;   // float in the reference (dnaoptions.hpp:432)
+    uint32_t max_iterations = 10;
+    double free_std_dev = 10.0, fixed_std_dev = 1.0e-6, confidence_interval = 95.0;
+    bool scale_normals_to_unity = false;
+    bool output_adj_msr = false;
+    bool update_binary_files = true;
+    std::string command_line;
+};
+
+class dna_adjust {
+  public:
+    ~dna_adjust()
+    {
+        if (ctx_)
+            gadj_destroy(ctx_);
+    }
+
+    // ---- PrepareAdjustment (ADJ:258): load .bst/.bms(/.seg), initialise, symbolic analysis, upload --------
+    void PrepareAdjustment(const adjust_settings& s)
+    {
+        a_ = s;
+        const std::string base = a_.input_folder + "/" + a_.network_name;
+        bst_file_ = base + ".bst";
+        bms_file_ = base + ".bms";
+        dnafiles::load_binary(bst_file_, stn_, bst_meta_);
+        dnafiles::load_binary(bms_file_, msr_, bms_meta_);
+        gadj_opts o;
+        gadj_default_opts(&o);
+        o.fixed_std_dev = a_.fixed_std_dev;
+        o.free_std_dev = a_.free_std_dev;
+        o.iteration_threshold = a_.iteration_threshold;
+        o.max_iterations = a_.max_iterations;
+        o.confidence_interval = a_.confidence_interval;
+        o.scale_normals_to_unity = 1;   // internal equilibration is always safe; the flag is accepted for compatibility
+        if (gadj_create(&o, &ctx_))
+            SignalExceptionAdjustment(gadj_last_error(nullptr));
+        check(gadj_set_stations(ctx_, stn_.data(), (uint32_t)stn_.size()));
+        check(gadj_set_measurements(ctx_, msr_.data(), msr_.size()));
+        if (a_.adjust_mode != SimultaneousMode) {
+            dnafiles::load_seg(base + ".seg", seg_);
+            std::vector<uint32_t> off{0}, isl;
+            for (auto& b : seg_.isl) {
+                isl.insert(isl.end(), b.begin(), b.end());
+                off.push_back((uint32_t)isl.size());
+            }
+            check(gadj_set_blocks(ctx_, (uint32_t)seg_.isl.size(), off.data(), isl.data()));
+        }
+        check(gadj_prepare(ctx_));
+        gadj_get_info(ctx_, &info_);
+        apriori_llh_.resize(3 * stn_.size());
+        for (size_t i = 0; i < stn_.size(); ++i) {
+            apriori_llh_[3 * i] = stn_[i].currentLatitude;
+            apriori_llh_[3 * i + 1] = stn_[i].currentLongitude;
+            apriori_llh_[3 * i + 2] = stn_[i].currentHeight;
+        }
+    }
+
+    // ---- AdjustNetwork (ADJ:2140) -> AdjustSimultaneous loop (ADJ:2413-2511) -------------------------------
+    ADJUST_STATUS AdjustNetwork()
+    {
+        auto t0 = std::chrono::steady_clock::now();
+        iterations_.clear();
+        adjustStatus_ = ADJUST_SUCCESS;
+        for (uint32_t i = 0; i < a_.max_iterations; ++i) {
+            auto ti = std::chrono::steady_clock::now();
+            gadj_iter_result r;
+            check(gadj_iterate(ctx_, i == 0 ? GADJ_ITER_NORMALS : 0, &r));
+            r.ms_inverse = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - ti).count();  // wall
+            iterations_.push_back(r);
+            maxCorr_ = r.max_corr;
+            if (std::fabs(r.max_corr) <= a_.iteration_threshold)
+                break;
+        }
+        if (iterations_.size() == a_.max_iterations && std::fabs(maxCorr_) > a_.iteration_threshold)
+            adjustStatus_ = ADJUST_MAX_ITERATIONS_EXCEEDED;   // ADJ:2523-2525
+        check(gadj_form_inverse(ctx_));                        // rigorous variances (v_rigorousVariances_)
+        total_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return adjustStatus_;
+    }
+
+    // ---- GenerateStatistics (ADJ:6802) ------------------------------------------------------------------------
+    void GenerateStatistics()
+    {
+        check(gadj_statistics(ctx_, &stats_, 1));   // also refreshes the records: adjusted lat/lon/h and measurement statistics
+        est_.resize(3 * stn_.size());
+        vcv_.resize(9 * stn_.size());
+        check(gadj_get_estimates(ctx_, est_.data()));
+        check(gadj_get_station_vcvs(ctx_, vcv_.data()));
+        ComputeTestStat();
+    }
+
+    // getters (ADJH:336-354)
+    double GetChiSquared() const { return stats_.chi_squared; }
+    double GetSigmaZero() const { return stats_.sigma_zero; }
+    int64_t GetDegreesOfFreedom() const { return stats_.dof; }
+    uint32_t GetMeasurementCount() const { return stats_.measurement_params; }
+    uint32_t GetUnknownsCount() const { return stats_.unknown_params; }
+    double GetGlobalPelzerRel() const { return stats_.global_pelzer; }
+    double GetChiSquaredUpperLimit() const { return chiUpper_; }
+    double GetChiSquaredLowerLimit() const { return chiLower_; }
+    uint32_t CurrentIteration() const { return (uint32_t)iterations_.size(); }
+    ADJUST_STATUS GetStatus() const { return adjustStatus_; }
+    const gadj_info& Info() const { return info_; }
+
+    std::string ModeSuffix() const
+    {   // output naming (WRAP:659-734)
+        switch (a_.adjust_mode) {
+        case PhasedMode: return "phased";
+        case Phased_Block_1Mode: return "phased-block1";
+        default: return "simult";
+        }
+    }
+
+    // ---- outputs (WRAP:1397-1432) --------------------------------------------------------------------------------
+    void PrintAdjustedNetwork()
+    {
+        const std::string stem = a_.output_folder + "/" + a_.network_name + "." + ModeSuffix();
+        std::ofstream adj(stem + ".adj");
+        PrintOutputFileHeaderInfo(adj, "DYNADJUST ADJUSTMENT OUTPUT FILE", stem + ".adj");
+        adj << "\n+ Initialising adjustment\n+ Loading network files\n+ Allocating memory\n\n+ Preparing for adjustment...  done.\n";
+        adj << "+ Commencing " << (a_.adjust_mode == SimultaneousMode ? "simultaneous" : "phased") << " adjustment\n\n";
+        for (size_t i = 0; i < iterations_.size(); ++i)
+            PrintIteration(adj, (uint32_t)i + 1, iterations_[i]);
+        PrintStatistics(adj);
+        if (a_.output_adj_msr)
+            PrintAdjMeasurements(adj);
+        PrintAdjStations(adj);
+        std::ofstream xyz(stem + ".xyz");
+        PrintOutputFileHeaderInfo(xyz, "DYNADJUST COORDINATE OUTPUT FILE", stem + ".xyz");
+        PrintAdjStations(xyz);
+    }
+
+    // UpdateBinaryFiles (ADJ:445-470): adjusted coordinates / statistics back to .bst/.bms with reduced = true
+    void UpdateBinaryFiles()
+    {
+        bst_meta_.reduced = true;
+        bms_meta_.reduced = true;
+        snprintf(bst_meta_.modifiedBy, sizeof(bst_meta_.modifiedBy), "%s", "adjust");
+        snprintf(bms_meta_.modifiedBy, sizeof(bms_meta_.modifiedBy), "%s", "adjust");
+        dnafiles::write_binary(bst_file_, stn_, bst_meta_);
+        dnafiles::write_binary(bms_file_, msr_, bms_meta_);
+    }
+
+  private:
+    void check(int rc)
+    {
+        if (rc)
+            SignalExceptionAdjustment(gadj_last_error(ctx_));
+    }
+    [[noreturn]] void SignalExceptionAdjustment(const std::string& msg)
+    {   // ADJ:10049-10069
+        adjustStatus_ = ADJUST_EXCEPTION_RAISED;
+        throw std::runtime_error(msg);
+    }
+
+    // regularised lower incomplete gamma P(a, x) (series / continued fraction) for the chi-square limits that the
+    // reference takes from boost::math (ADJ:6866-6911)
+    static double gamma_p(double a, double x)
+    {
+        if (x <= 0)
+            return 0;
+        const double gln = std::lgamma(a);
+        if (x < a + 1) {
+            double ap = a, sum = 1 / a, del = sum;
+            for (int n = 0; n < 100000; ++n) {
+                ap += 1;
+                del *= x / ap;
+                sum += del;
+                if (std::fabs(del) < std::fabs(sum) * 1e-16)
+                    break;
+            }
+            return sum * std::exp(-x + a * std::log(x) - gln);
+        }
+        double b = x + 1 - a, c = 1 / 1e-300, d = 1 / b, h = d;
+        for (int i = 1; i < 100000; ++i) {
+            double an = -i * (i - a);
+            b += 2;
+            d = an * d + b;
+            if (std::fabs(d) < 1e-300)
+                d = 1e-300;
+            c = b + an / c;
+            if (std::fabs(c) < 1e-300)
+                c = 1e-300;
+            d = 1 / d;
+            double del = d * c;
+            h *= del;
+            if (std::fabs(del - 1) < 1e-16)
+                break;
+        }
+        return 1 - std::exp(-x + a * std::log(x) - gln) * h;
+    }
+    static double chi2_quantile(double p, double dof)
+    {
+        // Wilson-Hilferty start, bisection/Newton polish on the CDF
+        double z = inv_norm(p);
+        double t = 1 - 2 / (9 * dof) + z * std::sqrt(2 / (9 * dof));
+        double x = dof * t * t * t;
+        double lo = 0, hi = std::max(4 * dof, x * 4 + 100);
+        for (int it = 0; it < 200; ++it) {
+            double f = gamma_p(dof / 2, x / 2) - p;
+            if (f > 0)
+                hi = x;
+            else
+                lo = x;
+            double pdf = std::exp((dof / 2 - 1) * std::log(x / 2) - x / 2 - std::lgamma(dof / 2)) / 2;
+            double xn = pdf > 0 ? x - f / pdf : 0.5 * (lo + hi);
+            if (!(xn > lo && xn < hi))
+                xn = 0.5 * (lo + hi);
+            if (std::fabs(xn - x) < 1e-12 * x)
+                return xn;
+            x = xn;
+        }
+        return x;
+    }
+    static double inv_norm(double p)
+    {
+        // Acklam
+        static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
+                                   1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
+        static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
+                                   6.680131188771972e+01, -1.328068155288572e+01};
+        static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
+                                   -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00};
+        static const double d[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00, 3.754408661907416e+00};
+        double q, r;
+        if (p < 0.02425) {
+            q = std::sqrt(-2 * std::log(p));
+            return (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+                   ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+        }
+        if (p <= 1 - 0.02425) {
+            q = p - 0.5;
+            r = q * q;
+            return (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
+                   (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1);
+        }
+        q = std::sqrt(-2 * std::log(1 - p));
+        return -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+               ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+    }
+
+    // ComputeTestStat (ADJ:6866-6911)
+    void ComputeTestStat()
+    {
+        double conf = (100. - a_.confidence_interval) * 0.01 * 0.5;
+        double dof = (double)stats_.dof;
+        if (dof <= 0) {
+            chiUpper_ = chiLower_ = 0;
+            passFail_ = 2;
+            return;
+        }
+        chiUpper_ = chi2_quantile(1 - conf, dof) / dof;
+        chiLower_ = chi2_quantile(conf, dof) / dof;
+        passFail_ = stats_.sigma_zero < chiLower_ ? 1 : (stats_.sigma_zero > chiUpper_ ? 2 : 0);
+    }
+
+    static std::string hp_dms(double rad)
+    {   // degrees.minutes-seconds "HP" notation, 9 decimals (FormatDmsString / RadtoDms)
+        double deg = rad * 180.0 / 3.14159265358979323846;
+        double sgn = deg < 0 ? -1 : 1;
+        deg = std::fabs(deg);
+        double d = std::floor(deg + 1e-13);
+        double m = std::floor((deg - d) * 60 + 1e-11);
+        double s = ((deg - d) * 60 - m) * 60;
+        if (s < 0)
+            s = 0;
+        if (s >= 59.999995) {
+            s = 0;
+            m += 1;
+        }
+        if (m >= 60) {
+            m -= 60;
+            d += 1;
+        }
+        char buf[64];
+        snprintf(buf, sizeof(buf), "%.9f", sgn * (d + m / 100.0 + s / 10000.0));
+        return buf;
+    }
+
+    void PrintOutputFileHeaderInfo(std::ostream& os, const char* title, const std::string& file) const
+    {   // PRN:3436-3599
+        const std::string dash(80, '-');
+        auto var = [&](const char* n, const std::string& v) { os << std::left << std::setw(35) << n << v << "\n"; };
+        os << dash << "\n" << title << "\n\n";
+        var("Version:", "b200-geodetic-adjust 0.1 (libgadj, sm_100a)");
+        var("Build:", std::string(__DATE__) + ", " + __TIME__);
+        var("File name:", file);
+        os << "\n";
+        var("Command line arguments:", a_.command_line);
+        os << "\n";
+        var("Stations file:", bst_file_);
+        var("Measurements file:", bms_file_);
+        var("Reference frame:", std::string("EPSG ") + bst_meta_.epsgCode);
+        var("Epoch:", bst_meta_.epoch);
+        std::ostringstream t;
+        t << a_.fixed_std_dev;
+        var("Constrained Station S.D. (m):", t.str());
+        t.str("");
+        t << a_.free_std_dev;
+        var("Free Station S.D. (m):", t.str());
+        t.str("");
+        t << (float)a_.iteration_threshold;
+        var("Iteration threshold:", t.str());
+        var("Maximum iterations:", std::to_string(a_.max_iterations));
+        t.str("");
+        t << std::fixed << std::setprecision(1) << a_.confidence_interval << "%";
+        var("Test confidence interval:", t.str());
+        var("Uncertainties SD(e,n,up):", "68.3% (1 sigma)");
+        var("Station coordinate types:", "PLHhXYZ");
+        var("Stations printed in blocks:", "No");
+        t.str("");
+        t << info_.nfronts << " fronts on " << info_.nlevels << " levels (supernodal Cholesky on B200)";
+        var("Elimination tree:", t.str());
+        os << dash << "\n";
+    }
+
+    void PrintIteration(std::ostream& os, uint32_t it, const gadj_iter_result& r) const
+    {   // PRN:70-92, OutputLargestCorrection ADJ:7357-7448
+        const std::string dash(80, '-');
+        os << "\n" << dash << "\n" << std::left << std::setw(35) << "ITERATION" << it << "\n\n";
+        char buf[64];
+        double sec = r.ms_inverse / 1e3;
+        snprintf(buf, sizeof(buf), "00:00:%09.6f", sec);
+        os << std::left << std::setw(35) << "Elapsed time" << buf << "\n";
+        const dna_stn_t& s = stn_[r.max_corr_station];
+        os << std::left << std::setw(35) << "Maximum station correction" << "Station " << s.stationName << "\n";
+        // Rotate_CartLocal at the station's a-priori geographic position
+        double lat = apriori_llh_[3 * r.max_corr_station], lon = apriori_llh_[3 * r.max_corr_station + 1];
+        const double* d = r.max_corr_xyz;
+        double e = -std::sin(lon) * d[0] + std::cos(lon) * d[1];
+        double n = -std::sin(lat) * std::cos(lon) * d[0] - std::sin(lat) * std::sin(lon) * d[1] + std::cos(lat) * d[2];
+        double u = std::cos(lat) * std::cos(lon) * d[0] + std::cos(lat) * std::sin(lon) * d[1] + std::sin(lat) * d[2];
+        double big = std::max(std::fabs(e), std::max(std::fabs(n), std::fabs(u)));
+        os << std::setw(35) << " ";
+        if (big > 0.000999)
+            os << std::fixed << std::setprecision(3) << e << ", " << n << ", " << u;
+        else if (big > 0.00009)
+            os << std::fixed << std::setprecision(4) << e << ", " << n << ", " << u;
+        else
+            os << std::scientific << std::setprecision(1) << e << ", " << n << ", " << u;
+        os << " (e, n, up)\n\n";
+        os.unsetf(std::ios::floatfield);
+    }
+
+    void PrintStatistics(std::ostream& os) const
+    {   // PRN:660-719
+        const std::string dash(80, '-');
+        auto var = [&](const char* n) -> std::ostream& { return os << std::left << std::setw(35) << n; };
+        os << "\n" << dash << "\n";
+        var("SOLUTION") << (adjustStatus_ == ADJUST_SUCCESS ? "Converged" : "Failed to converge after maximum iterations") << "\n";
+        char buf[64];
+        snprintf(buf, sizeof(buf), "00:00:%09.6f", total_ms_ / 1e3);
+        var("Total time") << buf << "\n\n";
+        var("Number of unknown parameters") << stats_.unknown_params << "\n";
+        var("Number of measurements") << stats_.measurement_params << "  (" << stats_.outliers << " potential outliers)\n";
+        var("Degrees of freedom") << stats_.dof << "\n";
+        var("Chi squared") << std::fixed << std::setprecision(2) << stats_.chi_squared << "\n";
+        var("Rigorous Sigma Zero") << std::fixed << std::setprecision(3) << stats_.sigma_zero << "\n";
+        var("Global (Pelzer) Reliability") << std::fixed << std::setprecision(3) << stats_.global_pelzer
+                                           << "   (excludes non redundant measurements)\n\n";
+        std::ostringstream t;
+        t << "Chi-Square test (" << std::fixed << std::setprecision(1) << a_.confidence_interval << "%)";
+        var(t.str().c_str()) << std::fixed << std::setprecision(3) << chiLower_ << " < " << stats_.sigma_zero << " < " << chiUpper_
+                             << "          *** " << (passFail_ == 0 ? "PASSED" : (passFail_ == 1 ? "WARNING" : "FAILED")) << " ***\n\n";
+    }
+
+    void PrintAdjMeasurements(std::ostream& os) const
+    {
+        os << "\nAdjusted Measurements\n------------------------------------------\n\n";
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%-2s%-20s%-20s%-20s%-3s%-2s%19s%19s%12s%13s%13s%13s%11s%12s%14s%7s", "M", "Station 1", "Station 2",
+                 "Station 3", "*", "C", "Measured", "Adjusted", "Correction", "Meas. SD", "Adj. SD", "Corr. SD", "N-stat", "Pelzer Rel",
+                 "Pre Adj Corr", "Out");
+        os << buf << "\n" << std::string(200, '-') << "\n";
+        const double crit = stats_.critical_value;
+        for (size_t i = 0; i < msr_.size(); ++i) {
+            const dna_msr_t& m = msr_[i];
+            if (m.ignore)
+                continue;
+            char comp = ' ';
+            double sd = 0;
+            if (m.measType == 'G') {
+                comp = "XYZ"[(int)m.measStart % 3];
+                sd = m.measStart == 0 ? m.term2 : (m.measStart == 1 ? m.term3 : m.term4);
+            } else
+                sd = m.term2;
+            const char* s1 = stn_[m.station1].stationName;
+            const char* s2 = m.measurementStations >= 2 ? stn_[m.station2].stationName : "";
+            snprintf(buf, sizeof(buf), "%-2c%-20s%-20s%-20s%-3s%-2c%19.4f%19.4f%12.4f%13.4f%13.4f%13.4f%11.2f%12.2f%14.4f%7s", m.measType, s1,
+                     s2, "", "", comp, m.preAdjMeas, m.measAdj, m.measCorr, std::sqrt(sd), std::sqrt(std::fabs(m.measAdjPrec)),
+                     std::sqrt(m.residualPrec), m.NStat, m.PelzerRel, m.preAdjCorr, std::fabs(m.NStat) > crit ? "*" : "");
+            os << buf << "\n";
+        }
+        os << "\n";
+    }
+
+    void PrintAdjStations(std::ostream& os) const
+    {   // PrintAdjStation (PRN:3917-4070): PLHhXYZ + SD(e,n,up) = sqrt diag(R^T Q R), geoid uncertainty added to up
+        os << "\nAdjusted Coordinates\n------------------------------------------\n\n";
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%-20s%-5s%14s%15s%11s%11s%15s%15s%15s%12s%10s%10s  %s", "Station", "Const", "Latitude", "Longitude",
+                 "H(Ortho)", "h(Ellipse)", "X", "Y", "Z", "SD(e)", "SD(n)", "SD(up)", "Description");
+        os << buf << "\n" << std::string(211, '-') << "\n";
+        for (size_t i = 0; i < stn_.size(); ++i) {
+            const dna_stn_t& s = stn_[i];
+            const double* q = &vcv_[9 * i];
+            double lat = s.currentLatitude, lon = s.currentLongitude, h = s.currentHeight;
+            double sl = std::sin(lat), cl = std::cos(lat), so = std::sin(lon), co = std::cos(lon);
+            double R[3][3] = {{-so, -sl * co, cl * co}, {co, -sl * so, cl * so}, {0, cl, sl}};  // local -> cart
+            double sd[3];
+            for (int k = 0; k < 3; ++k) {
+                double v = 0;
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b)
+                        v += R[a][k] * q[3 * a + b] * R[b][k];
+                if (k == 2)
+                    v += (double)s.geoidSepUnc * s.geoidSepUnc;
+                sd[k] = std::sqrt(std::fabs(v));
+            }
+            char cst[4] = {s.stationConst[0], s.stationConst[1], s.stationConst[2], 0};
+            snprintf(buf, sizeof(buf), "%-20s%-5s%14s%15s%11.4f%11.4f%15.4f%15.4f%15.4f%12.4f%10.4f%10.4f  %s", s.stationName, cst,
+                     hp_dms(lat).c_str(), hp_dms(lon).c_str(), h - (double)s.geoidSep, h, est_[3 * i], est_[3 * i + 1], est_[3 * i + 2],
+                     sd[0], sd[1], sd[2], s.description);
+            os << buf << "\n";
+        }
+        os << "\n";
+    }
+
+    adjust_settings a_;
+    gadj_ctx* ctx_ = nullptr;
+    gadj_info info_{};
+    gadj_stats stats_{};
+    std::vector<dna_stn_t> stn_;
+    std::vector<dna_msr_t> msr_;
+    dnafiles::BinaryMeta bst_meta_, bms_meta_;
+    dnafiles::Segmentation seg_;
+    std::string bst_file_, bms_file_;
+    std::vector<gadj_iter_result> iterations_;
+    std::vector<double> est_, vcv_, apriori_llh_;
+    double maxCorr_ = 0, total_ms_ = 0, chiUpper_ = 0, chiLower_ = 0;
+    int passFail_ = 0;
+    ADJUST_STATUS adjustStatus_ = ADJUST_SUCCESS;
+};
+
+}  // namespace dynadjust_b200

@@ -1,0 +1,162 @@
+// dnaadjust_main.cpp — `dnaadjust <network> [options]`: the reference's command line for the adjust step
+// (dnaadjustwrapper.cpp:799-1467; option strings config/dnaoptions-interface.hpp:96-158), driving the B200 engine.
+// Flags the solve path honours are parsed; flags that only select the reference's CPU execution strategy
+// (--multi-thread, --staged-adjustment, --create-stage-files, --purge-stage-files, --max-threads) are accepted and
+// ignored; unknown flags are a hard error, as in the reference (WRAP:1040-1046).
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "dna_adjust_host.hpp"
+
+using namespace dynadjust_b200;
+
+namespace {
+
+struct Flag {
+    const char* name;
+    bool takes_value;
+};
+
+const Flag kFlags[] = {
+    {"simultaneous-adjustment", false}, {"phased-adjustment", false}, {"block1-phased", false},
+    {"staged-adjustment", false}, {"multi-thread", false}, {"report-results", false},
+    {"conf-interval", true}, {"iteration-threshold", true}, {"max-iterations", true}, {"constraints", true},
+    {"free-stn-sd", true}, {"fixed-stn-sd", true}, {"scale-normals-to-unity", false},
+    {"create-stage-files", false}, {"purge-stage-files", false}, {"stage-path", true}, {"max-threads", true},
+    {"input-folder", true}, {"output-folder", true}, {"output-adj-msr", false}, {"output-pos-uncertainty", false},
+    {"output-all-covariances", false}, {"network-name", true}, {"quiet", false}, {"verbose-level", true},
+    {"no-binary-update", false}, {"help", false},
+};
+
+// Boost.program_options accepts unambiguous prefixes (CI uses --phased, --multi)
+const Flag* match(const std::string& key, std::string& err)
+{
+    const Flag* found = nullptr;
+    for (const Flag& f : kFlags) {
+        if (key == f.name)
+            return &f;
+        if (std::strncmp(f.name, key.c_str(), key.size()) == 0) {
+            if (found) {
+                err = "option '--" + key + "' is ambiguous";
+                return nullptr;
+            }
+            found = &f;
+        }
+    }
+    if (!found)
+        err = "unrecognised option '--" + key + "'";
+    return found;
+}
+
+}  // namespace
+
+int main(int argc, char** argv)
+{
+    adjust_settings s;
+    for (int i = 0; i < argc; ++i)
+        s.command_line += std::string(argv[i]) + " ";
+    bool quiet = false;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        if (a.rfind("--", 0) != 0) {
+            if (!s.network_name.empty()) {
+                std::cerr << "- Error: too many positional arguments ('" << a << "').\n";
+                return EXIT_FAILURE;
+            }
+            s.network_name = a;
+            continue;
+        }
+        std::string key = a.substr(2), value;
+        size_t eq = key.find('=');
+        bool has_eq = eq != std::string::npos;
+        if (has_eq) {
+            value = key.substr(eq + 1);
+            key = key.substr(0, eq);
+        }
+        std::string err;
+        const Flag* f = match(key, err);
+        if (!f) {
+            std::cerr << "- Error: " << err << "\n";   // WRAP:1040-1046
+            return EXIT_FAILURE;
+        }
+        if (f->takes_value && !has_eq) {
+            if (i + 1 >= argc) {
+                std::cerr << "- Error: the required argument for option '--" << f->name << "' is missing\n";
+                return EXIT_FAILURE;
+            }
+            value = argv[++i];
+        }
+        const std::string n = f->name;
+        if (n == "help") {
+            std::cout << "usage: dnaadjust <network> [--simultaneous-adjustment | --phased-adjustment] [--iteration-threshold x]\n"
+                         "       [--max-iterations n] [--free-stn-sd m] [--fixed-stn-sd m] [--conf-interval pct]\n"
+                         "       [--input-folder d] [--output-folder d] [--output-adj-msr] [--scale-normals-to-unity]\n";
+            return EXIT_SUCCESS;
+        } else if (n == "phased-adjustment" || n == "staged-adjustment" || n == "multi-thread")
+            s.adjust_mode = (n == "phased-adjustment") ? PhasedMode : s.adjust_mode;
+        else if (n == "block1-phased")
+            s.adjust_mode = Phased_Block_1Mode;
+        else if (n == "simultaneous-adjustment")
+            s.adjust_mode = SimultaneousMode;
+        else if (n == "conf-interval")
+            s.confidence_interval = std::atof(value.c_str());
+        else if (n == "iteration-threshold")
+            s.iteration_threshold = (double)(float)std::atof(value.c_str());
+        else if (n == "max-iterations")
+            s.max_iterations = (uint32_t)std::atoi(value.c_str());
+        else if (n == "free-stn-sd")
+            s.free_std_dev = std::atof(value.c_str());
+        else if (n == "fixed-stn-sd")
+            s.fixed_std_dev = std::atof(value.c_str());
+        else if (n == "scale-normals-to-unity")
+            s.scale_normals_to_unity = true;
+        else if (n == "input-folder")
+            s.input_folder = value;
+        else if (n == "output-folder")
+            s.output_folder = value;
+        else if (n == "output-adj-msr")
+            s.output_adj_msr = true;
+        else if (n == "network-name")
+            s.network_name = value;
+        else if (n == "quiet")
+            quiet = true;
+        else if (n == "no-binary-update")
+            s.update_binary_files = false;
+        else if (n == "constraints") {
+            std::cerr << "- Error: --constraints is not supported by this build (edit the station constraints upstream).\n";
+            return EXIT_FAILURE;
+        }
+        // remaining accepted flags select CPU execution strategies or extra reports: no effect here
+    }
+    if (s.network_name.empty()) {
+        std::cerr << "- Error: no network name was given.\n";
+        return EXIT_FAILURE;
+    }
+    try {
+        dna_adjust adj;
+        if (!quiet)
+            std::cout << "+ Preparing for adjustment... " << std::flush;
+        adj.PrepareAdjustment(s);
+        if (!quiet)
+            std::cout << "done.\n+ Adjusting network (" << adj.Info().nstations << " stations, " << adj.Info().nfronts
+                      << " fronts)...\n";
+        ADJUST_STATUS st = adj.AdjustNetwork();
+        adj.GenerateStatistics();
+        adj.PrintAdjustedNetwork();
+        if (s.update_binary_files)
+            adj.UpdateBinaryFiles();
+        if (!quiet) {
+            std::cout << "+ Solution " << (st == ADJUST_SUCCESS ? "converged" : "failed to converge") << " after "
+                      << adj.CurrentIteration() << " iteration(s).\n";
+            std::cout << "+ Chi squared " << adj.GetChiSquared() << ", degrees of freedom " << adj.GetDegreesOfFreedom()
+                      << ", rigorous sigma zero " << adj.GetSigmaZero() << "\n";
+        }
+        return EXIT_SUCCESS;   // ADJUST_SUCCESS even when not converged: the status is reported in the text (WRAP:133-147)
+    } catch (const std::exception& e) {
+        std::cerr << "\n- Error: " << e.what() << "\n";
+        return EXIT_FAILURE;
+    }
+}

@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(256) apply_corrections_kernel(const double* __
 
 __global__ void __launch_bounds__(256) finish_max_kernel(const double* __restrict__ part_val,
                                                          const unsigned long long* __restrict__ part_idx, int nparts,
-                                                         double* __restrict__ tail)
+                                                         const double* __restrict__ corr, double* __restrict__ tail)
 {
     __shared__ double sv[256];
     __shared__ unsigned long long si[256];
@@ -409,6 +409,10 @@ __global__ void __launch_bounds__(256) finish_max_kernel(const double* __restric
     if (threadIdx.x == 0) {
         tail[0] = sv[0];
         tail[1] = (double)si[0];
+        const unsigned long long s3 = (si[0] / 3) * 3;   // the station's three Cartesian corrections
+        tail[2] = corr[s3];
+        tail[3] = corr[s3 + 1];
+        tail[4] = corr[s3 + 2];
     }
 }
 
@@ -617,7 +621,7 @@ void launch_apply_corrections(const double* x, const double* dscale, const uint3
     const int grid = grid_for(3ull * nstn, 256, MAX_PARTS);
     apply_corrections_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, dscale, pos_of_stn, corr, est, nstn, g_part_val,
                                                                      g_part_idx);
-    finish_max_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(g_part_val, g_part_idx, grid, corr + 3ull * nstn);
+    finish_max_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(g_part_val, g_part_idx, grid, corr, corr + 3ull * nstn);
 }
 
 void launch_extract_station_vcv(const double* panels, const uint64_t* diag_dest, const uint32_t* diag_ld, const double* dscale,

@@ -30,7 +30,8 @@ class GadjOpts(C.Structure):
 class GadjIterResult(C.Structure):
     _fields_ = [("max_corr", C.c_double), ("max_corr_station", C.c_uint32), ("max_corr_axis", C.c_uint32),
                 ("iteration", C.c_uint32), ("converged", C.c_int32), ("ms_assemble", C.c_float),
-                ("ms_factor", C.c_float), ("ms_solve", C.c_float), ("ms_inverse", C.c_float)]
+                ("ms_factor", C.c_float), ("ms_solve", C.c_float), ("ms_inverse", C.c_float),
+                ("max_corr_xyz", C.c_double * 3)]
 
 
 class GadjStats(C.Structure):
@@ -58,7 +59,7 @@ class GadjProfile(C.Structure):
 
 EXPORTS = ["gadj_default_opts", "gadj_create", "gadj_destroy", "gadj_last_error", "gadj_set_stations",
            "gadj_set_measurements", "gadj_set_blocks", "gadj_prepare", "gadj_get_info", "gadj_upload_measurements",
-           "gadj_reset_estimates", "gadj_iterate", "gadj_adjust", "gadj_statistics", "gadj_get_estimates",
+           "gadj_reset_estimates", "gadj_iterate", "gadj_form_inverse", "gadj_adjust", "gadj_statistics", "gadj_get_estimates",
            "gadj_get_corrections", "gadj_get_station_vcvs", "gadj_get_station_vcv", "gadj_get_vcv_block",
            "gadj_get_normals_block", "gadj_get_rhs", "gadj_profile_enable", "gadj_profile_read", "gadj_test_gemm",
            "gadj_mg_init", "gadj_stage_begin", "gadj_stage_normals_pending", "gadj_stage_run", "gadj_stage_solve_begin",
@@ -91,6 +92,7 @@ def load_library(path=None):
     L.gadj_reset_estimates.argtypes = [vp]
     L.gadj_iterate.argtypes = [vp, i32, C.POINTER(GadjIterResult)]
     L.gadj_adjust.argtypes = [vp, C.POINTER(GadjIterResult)]
+    L.gadj_form_inverse.argtypes = [vp]
     L.gadj_statistics.argtypes = [vp, C.POINTER(GadjStats), i32]
     L.gadj_get_estimates.argtypes = [vp, vp]
     L.gadj_get_corrections.argtypes = [vp, vp]
@@ -209,6 +211,9 @@ class Adjustment:
         flags = (ITER_NORMALS if normals else 0) | (ITER_INVERSE if inverse else 0)
         self._check(self.L.gadj_iterate(self.h, flags, C.byref(r)))
         return r
+
+    def form_inverse(self):
+        self._check(self.L.gadj_form_inverse(self.h))
 
     # --- dna_adjust::AdjustNetwork (ADJ:2140)
     def adjust(self):

@@ -73,6 +73,7 @@ typedef struct gadj_iter_result {
     uint32_t iteration;            /* 1-based count of iterations run on this context */
     int32_t converged;             /* |max_corr| <= iteration_threshold */
     float ms_assemble, ms_factor, ms_solve, ms_inverse;   /* device time of each phase (CUDA events) */
+    double max_corr_xyz[3];        /* the three Cartesian corrections of that station (OutputLargestCorrection, ADJ:7357) */
 } gadj_iter_result;
 
 typedef struct gadj_stats {
@@ -129,6 +130,8 @@ int gadj_upload_measurements(gadj_ctx* c);
 int gadj_reset_estimates(gadj_ctx* c);
 
 int gadj_iterate(gadj_ctx* c, int flags, gadj_iter_result* res);
+/* rigorous (selected) inverse from the factorisation of the last iteration; the panels then hold N^-1 */
+int gadj_form_inverse(gadj_ctx* c);
 /* iterate to convergence with the reference's loop logic, then form the rigorous inverse */
 int gadj_adjust(gadj_ctx* c, gadj_iter_result* last);
 /* needs the rigorous inverse; write_back != 0 copies the statistics fields into the host msr records

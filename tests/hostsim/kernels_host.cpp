@@ -361,6 +361,8 @@ void launch_apply_corrections(const double* x, const double* dscale, const uint3
         }
     corr[3 * (size_t)nstn] = corr[best];
     corr[3 * (size_t)nstn + 1] = (double)best;
+    for (int c = 0; c < 3; ++c)
+        corr[3 * (size_t)nstn + 2 + c] = corr[(best / 3) * 3 + c];
 }
 
 void launch_extract_station_vcv(const double* panels, const uint64_t* diag_dest, const uint32_t* diag_ld,

@@ -1,0 +1,168 @@
+"""`dnaadjust <network> [options]` — the reference's process boundary (dnaadjustwrapper.cpp:799-1467).
+
+Network files (.bst/.bms/.seg in the reference's binary/ASCII layouts) are written by dynadjust_b200.dnafiles,
+the command line is run, and the text/binary outputs are compared with the CPU oracle at dnadiff's tolerance
+(0.001 on numeric fields; the tables print 4 decimals).  CPU: the command line linked against tests/hostsim;
+`-m gpu`: the product binary dynadjust_b200/bin/dnaadjust on the device."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from dynadjust_b200 import dnafiles, synth
+from dynadjust_b200.records import MSR_DTYPE, STN_DTYPE
+from tests import parity
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="session")
+def cli_hostsim(hostsim_path):
+    d = os.path.join(ROOT, "tests", "hostsim")
+    subprocess.run(["make", "-s", "-C", d, "all"], check=True)
+    return os.path.join(d, "_build", "dnaadjust_hostsim")
+
+
+@pytest.fixture(scope="session")
+def cli_gpu(gpu_lib):
+    exe = os.path.join(ROOT, "dynadjust_b200", "bin", "dnaadjust")
+    if not os.path.exists(exe):
+        raise RuntimeError("dynadjust_b200/bin/dnaadjust is missing on a GPU box: run __graft_entry__.build()")
+    return exe
+
+
+def _write_network(tmp, name, stn, msr):
+    dnafiles.write_bst(os.path.join(tmp, name + ".bst"), stn)
+    dnafiles.write_bms(os.path.join(tmp, name + ".bms"), msr)
+
+
+def _run(exe, tmp, *args):
+    return subprocess.run([exe, *args, "--input-folder", str(tmp), "--output-folder", str(tmp)], capture_output=True, text=True,
+                          timeout=600)
+
+
+def _solution_block(text):
+    def grab(label, cast=float):
+        m = re.search(r"^" + re.escape(label) + r"\s+(\S+)", text, re.M)
+        assert m, label
+        return cast(m.group(1))
+    return dict(unknowns=grab("Number of unknown parameters", int), measurements=grab("Number of measurements", int),
+                dof=grab("Degrees of freedom", int), chi=grab("Chi squared"), sigma0=grab("Rigorous Sigma Zero"),
+                pelzer=grab("Global (Pelzer) Reliability"), iterations=len(re.findall(r"^ITERATION\s+\d+", text, re.M)),
+                outliers=int(re.search(r"\((\d+) potential outliers\)", text).group(1)),
+                converged=bool(re.search(r"^SOLUTION\s+Converged", text, re.M)))
+
+
+def _station_table(text):
+    body = text.split("Adjusted Coordinates")[1]
+    rows = {}
+    for line in body.splitlines():
+        f = line.split()
+        if len(f) >= 12 and re.fullmatch(r"[CF]{3}", f[1]):
+            rows[f[0]] = [float(x) for x in f[2:12]]
+    return rows
+
+
+def _check_outputs(oracle, tmp, name, suffix, stn, msr, with_msr_table):
+    stn_o, msr_o = stn.copy(), msr.copy()
+    ref = oracle.adjust_simultaneous(stn_o, msr_o, want_vcv=True)
+    rr = ref["res"]
+    adj = open(os.path.join(tmp, f"{name}.{suffix}.adj")).read()
+    xyz = open(os.path.join(tmp, f"{name}.{suffix}.xyz")).read()
+    sol = _solution_block(adj)
+    assert sol["converged"] and sol["iterations"] == rr.iterations
+    assert sol["unknowns"] == rr.unknown_params and sol["measurements"] == rr.measurement_params and sol["dof"] == rr.dof
+    assert abs(sol["chi"] - rr.chi_squared) < 0.006 and abs(sol["sigma0"] - rr.sigma_zero) < 0.0006
+    assert abs(sol["pelzer"] - rr.global_pelzer) < 0.0006 and sol["outliers"] == rr.outliers
+    # adjusted coordinate table (.adj and .xyz carry the same table): X Y Z, h, SDs to the printed 4 decimals
+    V = ref["vcv"]
+    for text in (adj, xyz):
+        rows = _station_table(text)
+        assert len(rows) == len(stn)
+        for i in range(len(stn)):
+            r = rows[stn["stationName"][i].decode()]
+            assert np.abs(np.array(r[4:7]) - ref["est"].reshape(-1, 3)[i]).max() < 1e-3
+            assert abs(r[3] - stn_o["currentHeight"][i]) < 1e-3
+            lat, lon = stn_o["currentLatitude"][i], stn_o["currentLongitude"][i]
+            sl, cl, so, co = np.sin(lat), np.cos(lat), np.sin(lon), np.cos(lon)
+            R = np.array([[-so, -sl * co, cl * co], [co, -sl * so, cl * so], [0, cl, sl]])
+            q = R.T @ V[3 * i:3 * i + 3, 3 * i:3 * i + 3] @ R
+            sd = np.sqrt(np.abs(np.diag(q)) + np.array([0, 0, float(stn["geoidSepUnc"][i]) ** 2]))
+            assert np.abs(np.array(r[7:10]) - sd).max() < 1e-3
+    if with_msr_table:
+        body = adj.split("Adjusted Measurements")[1].split("Adjusted Coordinates")[0]
+        lines = [l for l in body.splitlines() if re.match(r"^[A-Z] \S", l) and not l.startswith("M Station 1")]
+        live = msr_o[msr_o["ignore"] == 0]
+        assert len(lines) == len(live)
+        for l, m in list(zip(lines, live))[::7]:
+            f = l.split()
+            nums = [float(x) for x in f if re.fullmatch(r"-?\d+\.\d+", x)]
+            assert abs(nums[1] - m["measAdj"]) < 1e-3 and abs(nums[2] - m["measCorr"]) < 1e-3
+    return stn_o, msr_o
+
+
+def _check_binary_update(tmp, name, stn_o, msr_o):
+    stn2, meta_s = dnafiles.read_binary(os.path.join(tmp, name + ".bst"), STN_DTYPE)
+    msr2, meta_m = dnafiles.read_binary(os.path.join(tmp, name + ".bms"), MSR_DTYPE)
+    assert meta_s["reduced"] and meta_m["reduced"]          # ADJ:445-470
+    assert np.abs(stn2["currentLatitude"] - stn_o["currentLatitude"]).max() < 1e-14
+    assert np.abs(stn2["currentHeight"] - stn_o["currentHeight"]).max() < 1e-7
+    for f in ("measAdj", "measCorr"):
+        assert np.abs(msr2[f] - msr_o[f]).max() < 5e-9
+
+
+def _simultaneous(exe, oracle, tmp_path):
+    stn, msr, _, _ = synth.config_network("C1")
+    _write_network(tmp_path, "c1", stn, msr)
+    r = _run(exe, tmp_path, "c1", "--output-adj-msr")
+    assert r.returncode == 0, r.stderr
+    stn_o, msr_o = _check_outputs(oracle, tmp_path, "c1", "simult", stn, msr, True)
+    _check_binary_update(tmp_path, "c1", stn_o, msr_o)
+
+
+def _phased(exe, oracle, tmp_path):
+    stn, msr, _, _ = synth.gnss_network(300, 900, 9)
+    _write_network(tmp_path, "net", stn, msr)
+    isl = parity.chain_blocks(300, 40)
+    dnafiles.write_seg(os.path.join(tmp_path, "net.seg"), isl, [[] for _ in isl], [[] for _ in isl])
+    r = _run(exe, tmp_path, "net", "--phased", "--no-binary-update")     # unambiguous prefix, as the reference's CI uses
+    assert r.returncode == 0, r.stderr
+    _check_outputs(oracle, tmp_path, "net", "phased", stn, msr, False)
+    stn2, meta = dnafiles.read_binary(os.path.join(tmp_path, "net.bst"), STN_DTYPE)
+    assert not meta["reduced"]
+
+
+def test_cli_simultaneous_hostsim(cli_hostsim, oracle, tmp_path):
+    _simultaneous(cli_hostsim, oracle, tmp_path)
+
+
+def test_cli_phased_seg_hostsim(cli_hostsim, oracle, tmp_path):
+    _phased(cli_hostsim, oracle, tmp_path)
+
+
+def test_cli_errors(cli_hostsim, tmp_path):
+    r = _run(cli_hostsim, tmp_path, "nonet")
+    assert r.returncode == 1 and "Error" in r.stderr                     # missing files: EXIT_FAILURE (WRAP:1377)
+    r = _run(cli_hostsim, tmp_path, "c1", "--no-such-flag")
+    assert r.returncode == 1 and "unrecognised option" in r.stderr       # WRAP:1040-1046
+    r = _run(cli_hostsim, tmp_path, "c1", "--output")                   # ambiguous prefix
+    assert r.returncode == 1 and "ambiguous" in r.stderr
+    stn, msr, _, _ = synth.config_network("C1")
+    _write_network(tmp_path, "old", stn, msr)
+    with open(os.path.join(tmp_path, "old.bms"), "r+b") as f:           # file version gate (io/bms_file.cpp:151)
+        f.seek(10)
+        f.write(b"       1.0")
+    r = _run(cli_hostsim, tmp_path, "old")
+    assert r.returncode == 1 and "predates" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_simultaneous_gpu(cli_gpu, oracle, tmp_path):
+    _simultaneous(cli_gpu, oracle, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_phased_seg_gpu(cli_gpu, oracle, tmp_path):
+    _phased(cli_gpu, oracle, tmp_path)
