@@ -39,6 +39,16 @@ WORKLOADS = {
 }
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture of this workload
+    (profiles/r1_ncu_dram_traffic_c4.json: dram__bytes_read.sum + dram__bytes_write.sum, C4 on one GPU)."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_dram_traffic_c4.json")
+    try:
+        return float(json.load(open(p))["kernels"][kernel]["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -275,7 +285,10 @@ def run_engine(args):
     gemm_ms = prof.ms_gemm / args.steps
     roofline = dict(bound="tensor", kernel="gemm_tile_kernel (TMA-fed DMMA, all panel/Schur/inverse products)",
                     achieved=rank_flops / gemm_ms / 1e9 if gemm_ms > 0 else None, peak=peak_tf, unit="TFLOP/s",
-                    frac=(rank_flops / gemm_ms / 1e9 / peak_tf) if gemm_ms > 0 else None, traffic=None,
+                    frac=(rank_flops / gemm_ms / 1e9 / peak_tf) if gemm_ms > 0 else None,
+                    traffic=ncu_traffic("gemm_tile_kernel") if (world == 1 and args.workload == "C4") else None,
+                    traffic_note="DRAM bytes per launch (avg over the iteration's launches) from profiles/r1_ncu_dram_traffic_c4.json",
+                    algorithmic_flops_per_launch=(rank_flops / (prof.gemm_launches / args.steps)) if prof.gemm_launches else None,
                     peak_source="cuBLAS DGEMM 8192^3 best-of-5 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                     algorithmic_flops_per_step=alg_flops, rank0_algorithmic_flops_per_step=rank_flops,
                     executed_gemm_flops_per_step=prof.flops_gemm / args.steps,
@@ -285,7 +298,8 @@ def run_engine(args):
     roofline_asm = dict(bound="hbm", kernel="assemble_g_kernel", achieved=info.nbaselines * BYTES_PER_BASELINE / asm_ms / 1e6,
                         peak=peaks["hbm_gbs"], unit="GB/s", peak_source=peaks_kind,
                         frac=info.nbaselines * BYTES_PER_BASELINE / asm_ms / 1e6 / peaks["hbm_gbs"],
-                        bytes_per_baseline=BYTES_PER_BASELINE, kernel_ms_per_step=asm_ms)
+                        bytes_per_baseline=BYTES_PER_BASELINE, kernel_ms_per_step=asm_ms,
+                        traffic=ncu_traffic("assemble_g_kernel") if args.workload == "C4" else None)
     line = dict(metric=METRIC, value=ms_step, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_step, higher_is_better=False, scaling="strong", vs_baseline=None, dtype="f64",
                 data="synthetic",

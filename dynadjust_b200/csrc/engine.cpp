@@ -661,6 +661,13 @@ int gadj_prepare(gadj_ctx* c)
     if (c->mg_world > 1)
         finalize_layout(c->sym, c->mg_world, c->mg_rank);
     const Symbolic& S = c->sym;
+    if (const char* fp = getenv("GADJ_DUMP_FRONTS")) {   // ordering studies: level, own unknowns, boundary unknowns, flops
+        if (FILE* f = fopen(fp, "w")) {
+            for (const Front& fr : S.fronts)
+                fprintf(f, "%d,%u,%u,%.6e\n", fr.level, fr.k, fr.r, fr.work);
+            fclose(f);
+        }
+    }
 
     // per-edge orientation and destinations
     c->edge_hi.resize(c->nedge);

@@ -320,6 +320,19 @@ M3 scale_gps_vcv(const Ellipsoid& e, const M3& V, double lat, double lon, double
     return mul(mul(R, false, Vs, false), false, R, true);
 }
 
+#include "oracle_types.h"
+
+// one entry of the CML (ADJH:1216-1218): a measurement or a cluster
+struct Meas {
+    uint64_t first = 0;
+    char type = 0;
+    uint32_t row0 = 0, nrows = 0;
+    size_t g = 0;                  // G: index into Ctx::vinv
+    std::vector<uint64_t> rec;     // D: direction record that stores each derived angle; X/Y: first record of each member
+    std::vector<uint64_t> base;    // D: record that supplies station1/station2/term3/term4 of each angle (RO, then the previous direction)
+    std::vector<double> vinv;      // D/X/Y: dense nrows x nrows V^-1, column-major, full
+};
+
 struct Ctx {
     const oracle_opts* o;
     Ellipsoid ell;
@@ -332,7 +345,8 @@ struct Ctx {
     std::vector<double> est;       // estimated stations (3S)
     std::vector<double> ell_rows;  // measured - computed, one per design row
     std::vector<double> vinv;      // per GNSS baseline: 3x3 V^-1 (column-major), in CML order
-    std::vector<double> apart;     // per scalar row: partials wrt station 1 (3) and station 2 (3)
+    std::vector<Meas> meas;        // parallel to cml
+    std::vector<Row> row;          // per design row of the non-G measurements: stations and partials
     std::vector<double> N;         // packed normals / after Solve: packed inverse
     std::vector<double> corr;      // corrections
     std::vector<double> w;         // At V^-1 l
@@ -428,41 +442,58 @@ inline void lower_add(Ctx& c, uint32_t r, uint32_t col, double v)  // MATH:405-4
     c.N[pidx(c.n, r, col)] += v;
 }
 
-// scan the record list into the CML (first record of each non-ignored measurement)
+// scan the record list into the CML (first record of each non-ignored measurement / cluster)
 int build_cml(Ctx& c)
 {
     uint64_t i = 0;
     while (i < c.nmsr) {
         const dna_msr_t& m = c.msr[i];
         uint64_t step = 1;
+        Meas me;
+        me.first = i;
+        me.type = m.measType;
         switch (m.measType) {
         case 'G':
             step = 3;
+            me.nrows = 3;
             break;
         case 'X':
         case 'Y': {
             // cluster: vectorCount1 members, each 3 records + 3 * vectorCount2(member) covariance records
             uint64_t j = i;
             uint32_t members = m.vectorCount1;
-            for (uint32_t k = 0; k < members; ++k)
+            for (uint32_t k = 0; k < members; ++k) {
+                me.rec.push_back(j);
                 j += 3 + 3ull * c.msr[j].vectorCount2;
+            }
             step = j - i;
+            me.nrows = 3 * members;
             break;
         }
-        case 'D':
-            step = 1ull + m.vectorCount1;
+        case 'D': {
+            // RO record + target directions: vectorCount1 records in all (dnadirectionset.cpp:430-466);
+            // vectorCount2 of them are not ignored -> vectorCount2 - 1 derived angles (ADJ:5088-5090)
+            step = m.vectorCount1 ? m.vectorCount1 : 1;
+            uint64_t prev = i;
+            for (uint64_t j = i + 1; j < i + step && me.rec.size() + 1 < m.vectorCount2; ++j) {
+                if (c.msr[j].ignore)
+                    continue;   // ADJ:5120-5129
+                me.rec.push_back(j);
+                me.base.push_back(prev);
+                prev = j;
+            }
+            me.nrows = (uint32_t)me.rec.size();
             break;
+        }
         default:
             step = 1;
+            me.nrows = 1;
         }
-        if (!m.ignore) {
-            if (m.measType != 'G' && m.measType != 'S' && m.measType != 'L') {
-                g_err = std::string("oracle: measurement type '") + m.measType + "' not restated yet";
-                return 3;
-            }
+        if (!m.ignore && me.nrows > 0) {
             if (m.measType != 'G')
-                c.non_gps = true;
+                c.non_gps = c.non_gps || (m.measType != 'X' && m.measType != 'Y');   // ContainsNonGPS (msr tally)
             c.cml.push_back(i);
+            c.meas.push_back(std::move(me));
         }
         i += step;
     }
@@ -477,16 +508,100 @@ double ellipsoid_height(const Ellipsoid& e, double X, double Y, double Z, double
     return std::sqrt(X * X + Y * Y + std::pow(Z + (*Zn), 2)) - (*nu);
 }
 
-// FillDesignNormalMeasurementsMatrices (ADJ:3888-4055) for the types restated.
+// LoadVarianceMatrix_D (ADJ:4059-4188): tridiagonal variance matrix of the angles derived from a round of
+// directions; first run stores variance / covariance in scale2 / scale3 of the direction records
+// (SetDirectionsVarianceMatrix, MFN:126-160), later runs read them back (GetDirectionsVarianceMatrix, MFN:53-82).
+int load_variance_matrix_D(Ctx& c, Meas& me, bool build)
+{
+    const uint32_t n = me.nrows;
+    std::vector<double> V((size_t)n * n, 0.0);
+    if (build) {
+        double previousVariance = c.msr[me.first].term2;
+        for (uint32_t a = 0; a < n; ++a) {
+            const double var = c.msr[me.rec[a]].term2;
+            // A = [-1 1] per angle; AV = [-prev, var]
+            V[(size_t)a * n + a] += (previousVariance * -1) * -1;
+            V[(size_t)a * n + a] += var * 1;
+            if (a + 1 < n) {
+                V[(size_t)(a + 1) * n + a] += var * -1;          // (a, a+1) = AV(a,a+1) * A(a+1,a+1)
+                V[(size_t)a * n + (a + 1)] = V[(size_t)(a + 1) * n + a];
+            }
+            previousVariance = var;
+        }
+        for (uint32_t a = 0; a < n; ++a) {
+            c.msr[me.rec[a]].scale2 = V[(size_t)a * n + a];
+            c.msr[me.rec[a]].scale3 = (a + 1 < n) ? V[(size_t)(a + 1) * n + a] : 0.0;
+        }
+    } else {
+        for (uint32_t a = 0; a < n; ++a) {
+            V[(size_t)a * n + a] = c.msr[me.rec[a]].scale2;
+            if (a + 1 < n)
+                V[(size_t)(a + 1) * n + a] = V[(size_t)a * n + (a + 1)] = c.msr[me.rec[a]].scale3;
+        }
+    }
+    me.vinv = V;
+    return inverse_variance(me.vinv.data(), n, false, c.use_ref);
+}
+
+// LoadVarianceMatrix_X / _Y (ADJ:4312-4450, ADJ:4494-4679) for Cartesian clusters: upper triangle from the records
+// (GetGPSVarianceMatrix, MFN:85-123), whole-matrix scalar applied and written back on the first run.
+int load_variance_matrix_XY(Ctx& c, Meas& me, bool build)
+{
+    const uint32_t n = me.nrows, members = (uint32_t)me.rec.size();
+    dna_msr_t* m0 = &c.msr[me.first];
+    double vS, pS, lS, hS;
+    bool scaleMatrix, scalePartial;
+    load_variance_scaling(c, *m0, vS, pS, lS, hS, scaleMatrix, scalePartial);
+    if (!build)
+        scaleMatrix = scalePartial = false;   // the records already hold the scaled matrix (ADJ:4281)
+    if (scalePartial) {
+        g_err = "oracle: phi/lambda/height variance scalars on X/Y clusters are not restated";
+        return 3;
+    }
+    if (me.type == 'Y' && std::strncmp(m0->coordType, "XYZ", 3) != 0) {
+        g_err = "oracle: Y clusters are restated for Cartesian (XYZ) coordinates only";
+        return 3;
+    }
+    std::vector<double> V((size_t)n * n, 0.0);
+    auto put = [&](uint32_t r, uint32_t col, double& field) {
+        if (scaleMatrix)
+            field *= vS;   // SetGPSVarianceMatrix writes the scaled value back
+        V[(size_t)col * n + r] = field;
+        V[(size_t)r * n + col] = field;
+    };
+    for (uint32_t k = 0; k < members; ++k) {
+        dna_msr_t* r = &c.msr[me.rec[k]];
+        const uint32_t v = 3 * k;
+        put(v, v, r[0].term2);
+        put(v, v + 1, r[1].term2);
+        put(v + 1, v + 1, r[1].term3);
+        put(v, v + 2, r[2].term2);
+        put(v + 1, v + 2, r[2].term3);
+        put(v + 2, v + 2, r[2].term4);
+        const uint32_t ncov = r[0].vectorCount2;
+        for (uint32_t q = 0; q < ncov; ++q) {
+            dna_msr_t* cv = r + 3 + 3 * q;
+            const uint32_t cc = v + 3 + 3 * q;
+            for (int i = 0; i < 3; ++i) {
+                put(v + i, cc, cv[i].term1);
+                put(v + i, cc + 1, cv[i].term2);
+                put(v + i, cc + 2, cv[i].term3);
+            }
+        }
+    }
+    me.vinv = V;
+    return inverse_variance(me.vinv.data(), n, false, c.use_ref);
+}
+
+// FillDesignNormalMeasurementsMatrices (ADJ:3888-4055).
 //   build=true : first pass — l, partials, V^-1 (with variance scaling write-back), first-run reductions
 //   build=false: re-linearise — l (and the partials of the non-GNSS rows; GNSS design never changes, ADJ:5294-5301)
 int fill_design_normals(Ctx& c, bool build)
 {
-    uint32_t row = 0;
-    size_t g = 0, sc = 0;
-    for (uint64_t first : c.cml) {
-        dna_msr_t* m = &c.msr[first];
-        switch (m->measType) {
+    for (Meas& me : c.meas) {
+        dna_msr_t* m = &c.msr[me.first];
+        uint32_t row = me.row0;
+        switch (me.type) {
         case 'G': {
             uint32_t s1 = m->station1 * 3, s2 = m->station2 * 3;
             // UpdateDesignMeasMatrices_GX (ADJ:5283-5350)
@@ -502,86 +617,162 @@ int fill_design_normals(Ctx& c, bool build)
                     g_err = "oracle: GNSS variance matrix inversion failed";
                     return rc;
                 }
-                std::memcpy(&c.vinv[g * 9], Vinv.v, sizeof(Vinv.v));
+                std::memcpy(&c.vinv[me.g * 9], Vinv.v, sizeof(Vinv.v));
             }
-            row += 3;
-            ++g;
             break;
         }
-        case 'S': {
-            // UpdateDesignNormalMeasMatrices_S (ADJ:5437-5493)
-            if (build)
-                m->preAdjMeas = m->term1;
-            uint32_t s1 = m->station1 * 3, s2 = m->station2 * 3;
-            const dna_stn_t& st1 = c.stn[m->station1];
-            double cl = std::cos(st1.currentLatitude), sl = std::sin(st1.currentLatitude);
-            double co = std::cos(st1.currentLongitude), so = std::sin(st1.currentLongitude);
-            // CartesianElementsFromInstrumentHeight (GEO:763-771): both heights are rotated at station 1
-            double dXih = cl * co * m->term3, dYih = cl * so * m->term3, dZih = sl * m->term3;
-            double dXth = cl * co * m->term4, dYth = cl * so * m->term4, dZth = sl * m->term4;
-            double dX = c.est[s2] - c.est[s1] + dXth - dXih;
-            double dY = c.est[s2 + 1] - c.est[s1 + 1] + dYth - dYih;
-            double dZ = c.est[s2 + 2] - c.est[s1 + 2] + dZth - dZih;
-            double comp = std::sqrt(dX * dX + dY * dY + dZ * dZ);
-            c.ell_rows[row] = m->term1 - comp;
-            double* a = &c.apart[sc * 6];
-            a[0] = -dX / comp;
-            a[1] = -dY / comp;
-            a[2] = -dZ / comp;
-            a[3] = -a[0];
-            a[4] = -a[1];
-            a[5] = -a[2];
-            row += 1;
-            ++sc;
-            break;
-        }
-        case 'L': {
-            // UpdateDesignNormalMeasMatrices_L (ADJ:5717-5784)
-            uint32_t s1 = m->station1 * 3, s2 = m->station2 * 3;
-            const dna_stn_t& st1 = c.stn[m->station1];
-            const dna_stn_t& st2 = c.stn[m->station2];
-            double nu1, nu2, Zn1, Zn2;
-            double h1 = ellipsoid_height(c.ell, c.est[s1], c.est[s1 + 1], c.est[s1 + 2], st1.currentLatitude, &nu1, &Zn1);
-            double h2 = ellipsoid_height(c.ell, c.est[s2], c.est[s2 + 1], c.est[s2 + 2], st2.currentLatitude, &nu2, &Zn2);
-            double comp = h2 - h1;
-            if (build) {
-                m->preAdjMeas = m->term1;   // InitialiseMeasurement (ADJ:3913-3935)
-                if (std::fabs(st1.geoidSep) > 1.0e-4 || std::fabs(st2.geoidSep) > 1.0e-4) {
-                    m->preAdjCorr = st2.geoidSep - st1.geoidSep;
-                    m->term1 += m->preAdjCorr;
+        case 'X':
+        case 'Y': {
+            // UpdateDesignNormalMeasMatrices_X (ADJ:6056-6246) / _Y (ADJ:6249-6566)
+            for (size_t k = 0; k < me.rec.size(); ++k) {
+                dna_msr_t* r = &c.msr[me.rec[k]];
+                uint32_t s1 = r->station1 * 3, s2 = r->station2 * 3;
+                Row& rw = c.row[row + 3 * k];
+                rw.st[0] = r->station1;
+                rw.st[1] = r->station2;
+                rw.nst = me.type == 'X' ? 2 : 1;
+                for (int q = 0; q < 3; ++q) {
+                    if (build)
+                        r[q].preAdjMeas = r[q].term1;
+                    c.ell_rows[row + 3 * k + q] =
+                        me.type == 'X' ? r[q].term1 - (c.est[s2 + q] - c.est[s1 + q]) : r[q].term1 - c.est[s1 + q];
                 }
             }
-            c.ell_rows[row] = m->term1 - comp;
-            double* a = &c.apart[sc * 6];
-            a[0] = -c.est[s1] / (nu1 + h1);
-            a[1] = -c.est[s1 + 1] / (nu1 + h1);
-            a[2] = -(c.est[s1 + 2] + Zn1) / (nu1 + h1);
-            a[3] = c.est[s2] / (nu2 + h2);
-            a[4] = c.est[s2 + 1] / (nu2 + h2);
-            a[5] = (c.est[s2 + 2] + Zn2) / (nu2 + h2);
-            row += 1;
-            ++sc;
+            if (build) {
+                int rc = load_variance_matrix_XY(c, me, true);
+                if (rc) {
+                    if (g_err.empty())
+                        g_err = "oracle: GNSS cluster variance matrix inversion failed";
+                    return rc;
+                }
+            }
             break;
         }
-        default:
+        case 'D': {
+            // UpdateDesignNormalMeasMatrices_D (ADJ:5082-5240)
+            double previousDirection = m->term1;
+            for (uint32_t a = 0; a < me.nrows; ++a) {
+                dna_msr_t* d = &c.msr[me.rec[a]];
+                dna_msr_t angle = c.msr[me.base[a]];   // scratch angle record (angleRec)
+                angle.station3 = d->station2;
+                if (build) {
+                    angle.term1 = d->term1 - previousDirection;
+                    if (angle.term1 < 0)
+                        angle.term1 += TWO_PI;
+                    if (angle.term1 > TWO_PI)
+                        angle.term1 -= TWO_PI;
+                    angle.preAdjMeas = angle.term1;   // InitialiseMeasurement inside _A
+                } else
+                    angle.term1 = d->scale1;
+                double l = angle_row(c.ell, &angle, c.stn, c.est.data(), angle.station1, angle.station2, angle.station3, build,
+                                     c.row[row + a]);
+                c.ell_rows[row + a] = l;
+                if (build) {
+                    d->scale1 = angle.term1;
+                    d->preAdjMeas = angle.preAdjMeas;
+                    d->preAdjCorr = angle.preAdjCorr;
+                    previousDirection = d->term1;
+                }
+            }
+            int rc = load_variance_matrix_D(c, me, build);
+            if (rc) {
+                g_err = "oracle: direction-set variance matrix inversion failed";
+                return rc;
+            }
             break;
+        }
+        default: {
+            if (!scalar_row_oracle(c.ell, m, c.stn, c.est.data(), build, c.row[row], &c.ell_rows[row])) {
+                g_err = std::string("oracle: measurement type '") + m->measType + "' not restated";
+                return 3;
+            }
+        }
         }
     }
     return 0;
 }
 
+// dense A (nrows x 3*|stations|) of one non-G measurement over its unique station list
+struct LocalDesign {
+    std::vector<uint32_t> stations;
+    std::vector<double> A;   // row-major nrows x 3*ns
+    uint32_t ns = 0;
+};
+void local_design(const Ctx& c, const Meas& me, LocalDesign& d)
+{
+    d.stations.clear();
+    auto add = [&](uint32_t s) {
+        for (uint32_t t : d.stations)
+            if (t == s)
+                return;
+        d.stations.push_back(s);
+    };
+    auto find = [&](uint32_t s) {
+        for (uint32_t i = 0; i < d.stations.size(); ++i)
+            if (d.stations[i] == s)
+                return i;
+        return 0u;
+    };
+    const bool cluster_gnss = me.type == 'X' || me.type == 'Y';
+    for (uint32_t r = 0; r < me.nrows; ++r) {
+        const Row& rw = c.row[me.row0 + (cluster_gnss ? 3 * (r / 3) : r)];
+        for (int k = 0; k < rw.nst; ++k)
+            add(rw.st[k]);
+    }
+    d.ns = (uint32_t)d.stations.size();
+    d.A.assign((size_t)me.nrows * 3 * d.ns, 0.0);
+    for (uint32_t r = 0; r < me.nrows; ++r) {
+        double* ar = &d.A[(size_t)r * 3 * d.ns];
+        if (cluster_gnss) {
+            const Row& rw = c.row[me.row0 + 3 * (r / 3)];
+            const int q = r % 3;
+            if (me.type == 'X') {
+                ar[3 * find(rw.st[0]) + q] += -1.;   // ADJ:5330-5344
+                ar[3 * find(rw.st[1]) + q] += 1.;
+            } else
+                ar[3 * find(rw.st[0]) + q] += 1.;
+        } else {
+            const Row& rw = c.row[me.row0 + r];
+            for (int k = 0; k < rw.nst; ++k)
+                for (int q = 0; q < 3; ++q)
+                    ar[3 * find(rw.st[k]) + q] += rw.a[3 * k + q];
+        }
+    }
+}
+// At V^-1 (3*ns x nrows, row-major) of one non-G measurement: UpdateAtVinv (ADJ:1285-1320), UpdateAtVinv_D
+// (ADJ:1328-1356), the X / Y blocks (ADJ:6125-6160, ADJ:6480-6512)
+void local_atvinv(const Ctx& c, const Meas& me, const LocalDesign& d, std::vector<double>& AtVinv)
+{
+    const uint32_t n = me.nrows, w = 3 * d.ns;
+    AtVinv.assign((size_t)w * n, 0.0);
+    if (me.vinv.empty()) {
+        const double variance = 1. / c.msr[me.first].term2;
+        for (uint32_t j = 0; j < w; ++j)
+            AtVinv[j] = variance * d.A[j];
+        return;
+    }
+    for (uint32_t j = 0; j < w; ++j)
+        for (uint32_t r = 0; r < n; ++r) {
+            double s = 0.;
+            for (uint32_t b = 0; b < n; ++b)
+                s += d.A[(size_t)b * w + j] * me.vinv[(size_t)r * n + b];
+            AtVinv[(size_t)j * n + r] = s;
+        }
+}
+
 // UpdateNormals (ADJ:1364-1455): N from the stored At V^-1 / design of every measurement
 void update_normals(Ctx& c)
 {
-    size_t g = 0, sc = 0;
-    for (uint64_t first : c.cml) {
-        const dna_msr_t* m = &c.msr[first];
-        uint32_t s1 = m->station1 * 3, s2 = m->station2 * 3;
-        if (m->measType == 'G') {
+    LocalDesign d;
+    std::vector<double> AtVinv;
+    for (const Meas& me : c.meas) {
+        const dna_msr_t* m = &c.msr[me.first];
+        if (me.type == 'G') {
+            uint32_t s1 = m->station1 * 3, s2 = m->station2 * 3;
             // UpdateNormals_G (ADJ:1664-1684) through add_normal_3x3_from_atvinv_columns (ADJ:1478-1491):
             // AtVinv[s1.., rows] = -V^-1 ; AtVinv[s2.., rows] = +V^-1
             M3 Vinv;
-            std::memcpy(Vinv.v, &c.vinv[g * 9], sizeof(Vinv.v));
+            std::memcpy(Vinv.v, &c.vinv[me.g * 9], sizeof(Vinv.v));
             for (int col = 0; col < 3; ++col)
                 for (int r = 0; r < 3; ++r) {
                     lower_add(c, s2 + r, s2 + col, 1. * Vinv(r, col));
@@ -589,19 +780,22 @@ void update_normals(Ctx& c)
                     lower_add(c, s1 + r, s2 + col, 1. * (-Vinv(r, col)));
                     lower_add(c, s2 + r, s1 + col, -1. * Vinv(r, col));
                 }
-            ++g;
-        } else {
-            // UpdateNormals_BCEKLMSVZ (ADJ:1640-1651): At V^-1 = a / term2 (UpdateAtVinv, ADJ:1285-1320)
-            const double* a = &c.apart[sc * 6];
-            const double p = 1. / m->term2;
-            const uint32_t st[2] = {s1, s2};
-            for (int bi = 0; bi < 2; ++bi)
-                for (int bj = 0; bj < 2; ++bj)
-                    for (int col = 0; col < 3; ++col)
-                        for (int r = 0; r < 3; ++r)
-                            lower_add(c, st[bi] + r, st[bj] + col, (p * a[3 * bi + r]) * a[3 * bj + col]);
-            ++sc;
+            continue;
         }
+        // UpdateNormals_A / _BCEKLMSVZ / _HIJPQR (ADJ:1510-1660), _D (ADJ:1540-1637), _X (ADJ:1687-1787), _Y:
+        // N[si, sj] += At V^-1[si, rows] . A[rows, sj] for every pair of the measurement's stations
+        local_design(c, me, d);
+        local_atvinv(c, me, d, AtVinv);
+        const uint32_t n = me.nrows, w = 3 * d.ns;
+        for (uint32_t bi = 0; bi < d.ns; ++bi)
+            for (uint32_t bj = 0; bj < d.ns; ++bj)
+                for (int col = 0; col < 3; ++col)
+                    for (int r = 0; r < 3; ++r) {
+                        double s = 0.;
+                        for (uint32_t q = 0; q < n; ++q)
+                            s += AtVinv[(size_t)(3 * bi + r) * n + q] * d.A[(size_t)q * w + 3 * bj + col];
+                        lower_add(c, 3 * d.stations[bi] + r, 3 * d.stations[bj] + col, s);
+                    }
     }
 }
 
@@ -662,13 +856,14 @@ int add_constraints(Ctx& c)
 void weighted_rhs(Ctx& c)
 {
     std::fill(c.w.begin(), c.w.end(), 0.0);
-    uint32_t row = 0;
-    size_t g = 0, sc = 0;
-    for (uint64_t first : c.cml) {
-        const dna_msr_t* m = &c.msr[first];
-        if (m->measType == 'G') {
+    LocalDesign d;
+    std::vector<double> AtVinv;
+    for (const Meas& me : c.meas) {
+        const dna_msr_t* m = &c.msr[me.first];
+        const uint32_t row = me.row0;
+        if (me.type == 'G') {
             uint32_t s1 = m->station1 * 3, s2 = m->station2 * 3;
-            const double* V = &c.vinv[g * 9];
+            const double* V = &c.vinv[me.g * 9];
             for (int r = 0; r < 3; ++r) {
                 double t = 0.;
                 for (int k = 0; k < 3; ++k)
@@ -676,19 +871,17 @@ void weighted_rhs(Ctx& c)
                 c.w[s1 + r] += -t;
                 c.w[s2 + r] += t;
             }
-            row += 3;
-            ++g;
-        } else {
-            uint32_t s1 = m->station1 * 3, s2 = m->station2 * 3;
-            const double* a = &c.apart[sc * 6];
-            const double p = 1. / m->term2;
-            for (int r = 0; r < 3; ++r) {
-                c.w[s1 + r] += (p * a[r]) * c.ell_rows[row];
-                c.w[s2 + r] += (p * a[3 + r]) * c.ell_rows[row];
-            }
-            row += 1;
-            ++sc;
+            continue;
         }
+        local_design(c, me, d);
+        local_atvinv(c, me, d, AtVinv);
+        for (uint32_t b = 0; b < d.ns; ++b)
+            for (int r = 0; r < 3; ++r) {
+                double t = 0.;
+                for (uint32_t q = 0; q < me.nrows; ++q)
+                    t += AtVinv[(size_t)(3 * b + r) * me.nrows + q] * c.ell_rows[row + q];
+                c.w[3 * d.stations[b] + r] += t;
+            }
     }
 }
 
@@ -906,8 +1099,15 @@ int oracle_adjust_simultaneous(const oracle_opts* opts, dna_stn_t* stn, uint32_t
     int rc = build_cml(c);
     if (rc)
         return rc;
-    for (uint64_t first : c.cml)
-        c.rows += (msr[first].measType == 'G') ? 3 : 1;
+    {
+        size_t g = 0;
+        for (Meas& me : c.meas) {
+            me.row0 = c.rows;
+            c.rows += me.nrows;
+            if (me.type == 'G')
+                me.g = g++;
+        }
+    }
 
     // PopulateEstimatedStationMatrix (ADJ:632-693)
     c.est.resize(c.n);
@@ -922,7 +1122,7 @@ int oracle_adjust_simultaneous(const oracle_opts* opts, dna_stn_t* stn, uint32_t
     c.N.assign(psize(c.n), 0.0);
     c.ell_rows.assign(c.rows, 0.0);
     c.vinv.assign(c.cml.size() * 9, 0.0);
-    c.apart.assign(c.cml.size() * 6, 0.0);
+    c.row.assign(c.rows, Row());
     c.corr.assign(c.n, 0.0);
     c.w.assign(c.n, 0.0);
 
@@ -1003,51 +1203,122 @@ int oracle_adjust_simultaneous(const oracle_opts* opts, dna_stn_t* stn, uint32_t
     uint32_t outliers = 0;
     double chi = 0.;
     {
-        uint32_t row = 0;
-        size_t sc = 0;
         auto Q = [&](uint32_t i, uint32_t j) { return i >= j ? c.N[pidx(c.n, i, j)] : c.N[pidx(c.n, j, i)]; };
-        for (uint64_t first : c.cml) {
-            dna_msr_t* m = &msr[first];
-            uint32_t s1 = m->station1 * 3, s2 = m->station2 * 3;
-            if (m->measType != 'G') {
-                // ComputePrecisionAdjMsrs_BCEKLMSVZ (ADJ:7949-7982): a Q a^T over the two stations
-                const double* a = &c.apart[sc * 6];
-                const uint32_t st[2] = {s1, s2};
-                double prec = 0.;
-                for (int bs = 0; bs < 2; ++bs)
-                    for (int i = 0; i < 3; ++i) {
-                        double part = 0.;
-                        for (int bj = 0; bj < 2; ++bj)
-                            for (int k = 0; k < 3; ++k)
-                                part += a[3 * bj + k] * Q(st[bj] + k, st[bs] + i);
-                        prec += part * a[3 * bs + i];
+        // ComputePrecisionAdjMsrs_A / _BCEKLMSVZ / _HIJPQR (ADJ:7880-8003): a Q a^T over the row's stations
+        auto row_precision = [&](const Row& rw) {
+            double prec = 0.;
+            for (int bs = 0; bs < rw.nst; ++bs)
+                for (int i = 0; i < 3; ++i) {
+                    double part = 0.;
+                    for (int bj = 0; bj < rw.nst; ++bj)
+                        for (int k = 0; k < 3; ++k)
+                            part += rw.a[3 * bj + k] * Q(3 * rw.st[bj] + k, 3 * rw.st[bs] + i);
+                    prec += part * rw.a[3 * bs + i];
+                }
+            return prec;
+        };
+        for (Meas& me : c.meas) {
+            dna_msr_t* m = &msr[me.first];
+            const uint32_t row = me.row0;
+            switch (me.type) {
+            case 'G':
+            case 'X':
+            case 'Y': {
+                const size_t members = me.type == 'G' ? 1 : me.rec.size();
+                for (size_t k = 0; k < members; ++k) {
+                    dna_msr_t* r = me.type == 'G' ? m : &msr[me.rec[k]];
+                    uint32_t s1 = r->station1 * 3, s2 = r->station2 * 3;
+                    double p6[6];
+                    if (me.type == 'Y') {
+                        // ComputePrecisionAdjMsrs_Y (ADJ:8035-8060)
+                        int q = 0;
+                        for (int i = 0; i < 3; ++i)
+                            for (int j = i; j < 3; ++j)
+                                p6[q++] = Q(s1 + i, s1 + j);
+                    } else
+                        precision_adjusted_gnss_bsl(c, s1, s2, p6);   // ComputePrecisionAdjMsrs_GX (ADJ:8006-8032)
+                    // UpdateMsrRecords_GXY (ADJ:8152-8184): XX row+0, YY row+3, ZZ row+5
+                    const uint32_t rr = row + 3 * (uint32_t)k;
+                    update_msr_record(r[0], c.ell_rows[rr + 0], p6[0], r[0].term2, critical, outliers);
+                    update_msr_record(r[1], c.ell_rows[rr + 1], p6[3], r[1].term3, critical, outliers);
+                    update_msr_record(r[2], c.ell_rows[rr + 2], p6[5], r[2].term4, critical, outliers);
+                }
+                if (me.type == 'G') {
+                    // ComputeChiSquare_G (ADJ:8530-8549)
+                    M3 Vinv;
+                    rc = inverse_gps_variance_G(c, m, Vinv);
+                    if (rc)
+                        return rc;
+                    double cs = 0.;
+                    for (int r = 0; r < 3; ++r)
+                        for (int col = 0; col < 3; ++col)
+                            cs += Vinv(r, col) * c.ell_rows[row + r] * c.ell_rows[row + col];
+                    chi += cs;
+                } else {
+                    // ComputeChiSquare_XY (ADJ:8552-8577): r^T V^-1 r with V^-1 from the records as they stand
+                    rc = load_variance_matrix_XY(c, me, false);
+                    if (rc)
+                        return rc;
+                    const uint32_t n = me.nrows;
+                    double cs = 0.;
+                    for (uint32_t j = 0; j < n; ++j) {
+                        double t = 0.;
+                        for (uint32_t i = 0; i < n; ++i)
+                            t += c.ell_rows[row + i] * me.vinv[(size_t)j * n + i];
+                        cs += t * c.ell_rows[row + j];
                     }
-                update_msr_record(*m, c.ell_rows[row], prec, m->term2, critical, outliers);
-                if (m->measType == 'L')
-                    m->measAdj -= m->preAdjCorr;   // ADJ:8241-8244
-                chi += c.ell_rows[row] * c.ell_rows[row] / m->term2;   // ADJ:8430-8437
-                row += 1;
-                ++sc;
-                continue;
+                    chi += cs;
+                }
+                break;
             }
-            // ComputePrecisionAdjMsrs_GX (ADJ:8006-8032)
-            double p6[6];
-            precision_adjusted_gnss_bsl(c, s1, s2, p6);
-            // UpdateMsrRecords_GXY (ADJ:8152-8184): XX row+0, YY row+3, ZZ row+5
-            update_msr_record(m[0], c.ell_rows[row + 0], p6[0], m[0].term2, critical, outliers);
-            update_msr_record(m[1], c.ell_rows[row + 1], p6[3], m[1].term3, critical, outliers);
-            update_msr_record(m[2], c.ell_rows[row + 2], p6[5], m[2].term4, critical, outliers);
-            // ComputeChiSquare_G (ADJ:8530-8549)
-            M3 Vinv;
-            rc = inverse_gps_variance_G(c, m, Vinv);
-            if (rc)
-                return rc;
-            double cs = 0.;
-            for (int r = 0; r < 3; ++r)
-                for (int col = 0; col < 3; ++col)
-                    cs += Vinv(r, col) * c.ell_rows[row + r] * c.ell_rows[row + col];
-            chi += cs;
-            row += 3;
+            case 'D': {
+                // ComputePrecisionAdjMsrs_D (ADJ:7912-7946), UpdateMsrRecords_D (ADJ:8120-8149), ComputeChiSquare_D (ADJ:8440-8469)
+                for (uint32_t a = 0; a < me.nrows; ++a) {
+                    dna_msr_t& d = msr[me.rec[a]];
+                    const double prec = row_precision(c.row[row + a]);
+                    update_msr_record(d, c.ell_rows[row + a], prec, d.scale2, critical, outliers);
+                    d.measAdj = d.scale1 + d.measCorr;   // ADJ:8194-8199
+                    if (d.measAdj > TWO_PI)
+                        d.measAdj -= TWO_PI;
+                    d.measAdj += d.preAdjCorr;           // ADJ:8259-8268
+                    chi += c.ell_rows[row + a] * c.ell_rows[row + a] / d.scale2;
+                }
+                break;
+            }
+            default: {
+                const Row& rw = c.row[row];
+                const double prec = row_precision(rw);
+                update_msr_record(*m, c.ell_rows[row], prec, m->term2, critical, outliers);
+                const double* p1 = &c.est[3 * (size_t)m->station1];
+                const double* p2 = &c.est[3 * (size_t)m->station2];
+                const dna_stn_t& st1 = stn[m->station1];
+                switch (m->measType) {   // ADJ:8205-8271
+                case 'E':
+                    m->measAdj = ell_chord_to_arc(c.ell, m->measAdj, p1, p2, st1.currentLatitude, st1.currentLongitude,
+                                                  stn[m->station2].currentLatitude);
+                    break;
+                case 'M':
+                    m->measAdj = ell_chord_to_msl_arc(c.ell, m->measAdj, st1.currentLatitude, stn[m->station2].currentLatitude,
+                                                      st1.geoidSep, stn[m->station2].geoidSep);
+                    break;
+                case 'H':
+                case 'L':
+                    m->measAdj -= m->preAdjCorr;
+                    break;
+                case 'A':
+                case 'I':
+                case 'J':
+                case 'K':
+                case 'Z':
+                    m->measAdj += m->preAdjCorr;
+                    break;
+                case 'V':
+                    m->measAdj -= m->preAdjCorr;
+                    break;
+                }
+                chi += c.ell_rows[row] * c.ell_rows[row] / m->term2;   // ADJ:8430-8437
+            }
+            }
         }
     }
     res->chi_squared = chi;
@@ -1060,22 +1331,32 @@ int oracle_adjust_simultaneous(const oracle_opts* opts, dna_stn_t* stn, uint32_t
     {
         double sum = 0.;
         uint32_t num = 0;
-        for (uint64_t first : c.cml) {
-            dna_msr_t* m = &msr[first];
-            if (m->measType != 'G') {
-                if (m->PelzerRel > 0. && m->PelzerRel < STABLE_LIMIT) {   // ADJ:8339-8345
-                    sum += (m->PelzerRel * m->PelzerRel - 1.);
-                    num++;
-                } else
-                    m->PelzerRel = UNRELIABLE;
-                continue;
-            }
-            for (int k = 0; k < 3; ++k) {
-                if (m[k].PelzerRel > 0. && m[k].PelzerRel < UNRELIABLE) {
-                    sum += (m[k].PelzerRel * m[k].PelzerRel - 1.);
-                    num++;
-                } else
-                    m[k].PelzerRel = UNRELIABLE;
+        auto tally = [&](dna_msr_t& r, double limit) {
+            if (r.PelzerRel > 0. && r.PelzerRel < limit) {
+                sum += (r.PelzerRel * r.PelzerRel - 1.);
+                num++;
+            } else
+                r.PelzerRel = UNRELIABLE;
+        };
+        for (Meas& me : c.meas) {
+            dna_msr_t* m = &msr[me.first];
+            switch (me.type) {
+            case 'G':
+                for (int k = 0; k < 3; ++k)
+                    tally(m[k], UNRELIABLE);
+                break;
+            case 'X':
+            case 'Y':
+                for (uint64_t r0 : me.rec)
+                    for (int k = 0; k < 3; ++k)
+                        tally(msr[r0 + k], UNRELIABLE);
+                break;
+            case 'D':
+                for (uint64_t r0 : me.rec)
+                    tally(msr[r0], UNRELIABLE);   // ComputeGlobalPelzer_D (ADJ:8362-8393)
+                break;
+            default:
+                tally(*m, STABLE_LIMIT);          // ADJ:8339-8345
             }
         }
         res->global_pelzer = num > 0 ? std::sqrt(sum / num) : UNRELIABLE;
