@@ -19,6 +19,7 @@
 #include "geodesy.h"
 #include "kernels.h"
 #include "plan.h"
+#include "rows.h"
 #include "symbolic.h"
 
 using namespace gadj;
@@ -176,8 +177,13 @@ struct gadj_ctx {
     std::vector<uint32_t> isl_off, isl;
     // measurement plan
     std::vector<uint32_t> first, edge_word;          // GNSS baselines
-    std::vector<uint32_t> sfirst, sedge_word;        // scalar two-station rows ('S', 'L')
-    uint64_t nscalar = 0;
+    // design rows of every other type (rows.h): terrestrial rows, derived angles of D sets, X / Y cluster rows
+    std::vector<RowDesc> rows;
+    std::vector<uint32_t> row_base;                  // D rows: record that supplies station2 / term3 / term4 of the angle
+    std::vector<ClusterDesc> clusters;
+    std::vector<uint32_t> cstn, inc_ptr, inc, pair_word;
+    std::vector<double> cvmat;                       // cluster variance matrices (host copy, inverted on the device)
+    uint64_t nrows = 0;
     bool non_gps = false;
     std::vector<uint32_t> edge_hi, edge_lo;
     bool contiguous = false;
@@ -194,7 +200,12 @@ struct gadj_ctx {
     double critical = 0;
     // device state
     DevArray<dna_msr_t> d_msr;
-    DevArray<uint32_t> d_first, d_edge, d_sfirst, d_sedge, d_edge_hi, d_edge_lo, d_pos, d_diag_ld, d_off_ld;
+    DevArray<uint32_t> d_first, d_edge, d_edge_hi, d_edge_lo, d_pos, d_diag_ld, d_off_ld;
+    DevArray<RowDesc> d_rows;
+    DevArray<ClusterDesc> d_clusters;
+    DevArray<uint32_t> d_cstn, d_inc_ptr, d_inc, d_pair_word;
+    DevArray<double> d_cvinv, d_row_l, d_row_a, d_row_t;
+    DevArray<float> d_geoid;
     DevArray<uint64_t> d_diag_dest, d_off_dest;
     DevArray<double> d_est, d_est0, d_llh, d_llh0, d_cblock, d_ndiag, d_noff, d_w, d_dscale, d_panels, d_pool, d_x, d_corr, d_vcvd,
         d_vcvo, d_sums;
@@ -420,33 +431,72 @@ void first_run_reduction(gadj_ctx* c)
     });
 }
 
-// first-run handling of the scalar rows: back up the raw value (InitialiseMeasurement, ADJ:3913-3935) and reduce
-// levelled height differences to ellipsoidal ones with the geoid separations (ADJ:5751-5757)
-void first_run_reduction_scalar(gadj_ctx* c)
+bool is_scalar_type(char t)
 {
-    for (uint32_t fi : c->sfirst) {
-        dna_msr_t& m = c->msr[fi];
-        if (c->reduced) {
-            m.term1 = m.preAdjMeas;
-            continue;
-        }
-        m.preAdjMeas = m.term1;
-        if (m.measType == 'L') {
-            const dna_stn_t& s1 = c->stn[m.station1];
-            const dna_stn_t& s2 = c->stn[m.station2];
-            if (std::fabs(s1.geoidSep) > 1.0e-4 || std::fabs(s2.geoidSep) > 1.0e-4) {
-                m.preAdjCorr = s2.geoidSep - s1.geoidSep;
-                m.term1 += m.preAdjCorr;
-            }
-        }
+    switch (t) {
+    case 'A': case 'B': case 'C': case 'E': case 'H': case 'I': case 'J': case 'K':
+    case 'L': case 'M': case 'P': case 'Q': case 'R': case 'S': case 'V': case 'Z':
+        return true;
+    default:
+        return false;
+    }
+}
+int stations_of_type(char t)
+{
+    switch (t) {
+    case 'A': case 'D':
+        return 3;
+    case 'H': case 'I': case 'J': case 'P': case 'Q': case 'R': case 'Y':
+        return 1;
+    default:
+        return 2;
     }
 }
 
+// Scan the record list (the reference's CML: first record of each non-ignored measurement, ADJH:1216-1218) into
+//   first[]      GNSS baselines 'G'
+//   rows[]       one RowDesc per design row of every other type
+//   clusters[]   D sets, X and Y clusters with their local station lists and station -> row incidence lists
 int scan_measurements(gadj_ctx* c)
 {
     c->first.clear();
-    c->sfirst.clear();
+    c->rows.clear();
+    c->row_base.clear();
+    c->clusters.clear();
+    c->cstn.clear();
+    c->inc_ptr.assign(1, 0u);
+    c->inc.clear();
+    c->non_gps = false;
     uint64_t i = 0;
+    auto bad_station = [&](uint32_t s) { return s >= c->nstn; };
+    // close a cluster: local stations + incidence lists from rows [row0, rows.size())
+    auto close_cluster = [&](char type, uint32_t row0) {
+        ClusterDesc cd;
+        std::memset(&cd, 0, sizeof(cd));
+        cd.type = (uint8_t)type;
+        cd.row0 = row0;
+        cd.n = (uint32_t)c->rows.size() - row0;
+        cd.st0 = (uint32_t)c->cstn.size();
+        std::vector<uint32_t> loc;
+        for (uint32_t r = row0; r < c->rows.size(); ++r)
+            for (int k = 0; k < c->rows[r].nst; ++k)
+                loc.push_back(c->rows[r].st[k]);
+        std::sort(loc.begin(), loc.end());
+        loc.erase(std::unique(loc.begin(), loc.end()), loc.end());
+        cd.ns = (uint32_t)loc.size();
+        std::vector<std::vector<uint32_t>> lists(loc.size());
+        for (uint32_t r = row0; r < c->rows.size(); ++r)
+            for (int k = 0; k < c->rows[r].nst; ++k) {
+                uint32_t j = (uint32_t)(std::lower_bound(loc.begin(), loc.end(), c->rows[r].st[k]) - loc.begin());
+                lists[j].push_back(((r - row0) << 2) | (uint32_t)k);
+            }
+        for (uint32_t j = 0; j < loc.size(); ++j) {
+            c->cstn.push_back(loc[j]);
+            c->inc.insert(c->inc.end(), lists[j].begin(), lists[j].end());
+            c->inc_ptr.push_back((uint32_t)c->inc.size());
+        }
+        c->clusters.push_back(cd);
+    };
     while (i < c->nmsr) {
         const dna_msr_t& m = c->msr[i];
         uint64_t step = 1;
@@ -463,32 +513,107 @@ int scan_measurements(gadj_ctx* c)
             break;
         }
         case 'D':
-            step = 1ull + m.vectorCount1;
+            step = m.vectorCount1;   // RO record + target directions (dnadirectionset.cpp:430-466)
             break;
         default:
             step = 1;
         }
         if (step == 0)
             step = 1;
+        if (i + step > c->nmsr)
+            return c->fail("truncated measurement at the end of the measurement list");
         if (!m.ignore) {
-            if (i > 0xFFFFFFF0ull)
+            if (i + step > 0xFFFFFFF0ull)
                 return c->fail("measurement index exceeds 32 bits");
             if (m.measType == 'G') {
-                if (i + 3 > c->nmsr)
-                    return c->fail("truncated GNSS baseline at the end of the measurement list");
                 c->first.push_back((uint32_t)i);
-            } else if (m.measType == 'S' || m.measType == 'L') {
-                c->sfirst.push_back((uint32_t)i);
+            } else if (is_scalar_type(m.measType)) {
+                RowDesc r;
+                std::memset(&r, 0, sizeof(r));
+                r.rec = (uint32_t)i;
+                r.type = (uint8_t)m.measType;
+                r.nst = (uint8_t)stations_of_type(m.measType);
+                r.st[0] = m.station1;
+                r.st[1] = r.nst > 1 ? m.station2 : m.station1;
+                r.st[2] = r.nst > 2 ? m.station3 : m.station1;
+                for (int k = 0; k < r.nst; ++k)
+                    if (bad_station(r.st[k]))
+                        return c->fail("measurement refers to a station index beyond the station list");
+                if ((r.nst > 1 && r.st[0] == r.st[1]) || (r.nst > 2 && (r.st[0] == r.st[2] || r.st[1] == r.st[2])))
+                    return c->fail(std::string("measurement of type '") + m.measType + "' with repeated stations");
+                if (!(m.term2 > 0.0))
+                    return c->fail("Invalid variance matrix: non-positive measurement variance");
+                c->rows.push_back(r);
+                c->row_base.push_back((uint32_t)i);
+                c->non_gps = true;   // v_msrTally_.ContainsNonGPS() (ADJ:2457)
+            } else if (m.measType == 'D') {
+                // derived angles between consecutive non-ignored directions (ADJ:5088-5129)
+                const uint32_t row0 = (uint32_t)c->rows.size();
+                uint64_t prev = i;
+                for (uint64_t j = i + 1; j < i + step && c->rows.size() - row0 + 1 < m.vectorCount2; ++j) {
+                    if (c->msr[j].ignore)
+                        continue;
+                    RowDesc r;
+                    std::memset(&r, 0, sizeof(r));
+                    r.rec = (uint32_t)j;
+                    r.type = 'D';
+                    r.nst = 3;
+                    r.clustered = 1;
+                    r.st[0] = c->msr[prev].station1;
+                    r.st[1] = c->msr[prev].station2;
+                    r.st[2] = c->msr[j].station2;
+                    for (int k = 0; k < 3; ++k)
+                        if (bad_station(r.st[k]))
+                            return c->fail("measurement refers to a station index beyond the station list");
+                    if (r.st[0] == r.st[1] || r.st[0] == r.st[2] || r.st[1] == r.st[2])
+                        return c->fail("direction set with repeated stations in one derived angle");
+                    if (!(c->msr[j].term2 > 0.0) || !(c->msr[prev].term2 > 0.0))
+                        return c->fail("Invalid variance matrix: non-positive direction variance");
+                    c->rows.push_back(r);
+                    c->row_base.push_back((uint32_t)prev);
+                    prev = j;
+                }
+                if (c->rows.size() > row0) {
+                    close_cluster('D', row0);
+                    c->non_gps = true;
+                }
+            } else if (m.measType == 'X' || m.measType == 'Y') {
+                if (m.measType == 'Y' && std::strncmp(m.coordType, "XYZ", 3) != 0)
+                    return c->fail("GNSS point clusters 'Y' are handled in Cartesian (XYZ) form only");
+                const uint32_t row0 = (uint32_t)c->rows.size();
+                uint64_t j = i;
+                for (uint32_t k = 0; k < m.vectorCount1; ++k) {
+                    const dna_msr_t& b = c->msr[j];
+                    if (bad_station(b.station1) || (m.measType == 'X' && bad_station(b.station2)))
+                        return c->fail("measurement refers to a station index beyond the station list");
+                    if (m.measType == 'X' && b.station1 == b.station2)
+                        return c->fail("GNSS baseline with identical end stations");
+                    for (int q = 0; q < 3; ++q) {
+                        RowDesc r;
+                        std::memset(&r, 0, sizeof(r));
+                        r.rec = (uint32_t)(j + q);
+                        r.type = (uint8_t)m.measType;
+                        r.nst = m.measType == 'X' ? 2 : 1;
+                        r.comp = (uint8_t)q;
+                        r.clustered = 1;
+                        r.st[0] = b.station1;
+                        r.st[1] = m.measType == 'X' ? b.station2 : b.station1;
+                        r.st[2] = b.station1;
+                        c->rows.push_back(r);
+                        c->row_base.push_back((uint32_t)j);
+                    }
+                    j += 3 + 3ull * b.vectorCount2;
+                }
+                if (c->rows.size() > row0)
+                    close_cluster(m.measType, row0);
             } else
-                return c->fail(std::string("measurement type '") + m.measType +
-                               "' is not handled by the device assembly yet (handled: G, S, L)");
+                return c->fail(std::string("measurement type '") + m.measType + "' is not a DynAdjust measurement type");
         }
         i += step;
     }
     c->nbsl = c->first.size();
-    c->nscalar = c->sfirst.size();
-    c->non_gps = c->nscalar > 0;   // v_msrTally_.ContainsNonGPS() (ADJ:2457)
-    if (c->nbsl + c->nscalar == 0)
+    c->nrows = c->rows.size();
+    if (c->nbsl + c->nrows == 0)
         return c->fail("no measurements to adjust");
     c->contiguous = true;
     for (uint64_t b = 0; b < c->nbsl; ++b)
@@ -496,6 +621,130 @@ int scan_measurements(gadj_ctx* c)
             c->contiguous = false;
             break;
         }
+    return 0;
+}
+
+// First-run handling of the rows (host, once): back up / restore the raw value (InitialiseMeasurement, ADJ:3913-3935),
+// deflection / geoid reductions per type (rows.h first_run_reduce), derived angles and their tridiagonal variance
+// matrix for D sets (ADJ:5082-5193, ADJ:4059-4188), cluster variance matrices of X / Y with the whole-matrix scalar
+// (ADJ:4312-4450, ADJ:4494-4679).  est: a-priori Cartesian coordinates.  Fills c->cvmat (V, to be inverted on the device).
+int first_run_reduction_rows(gadj_ctx* c, const double* est)
+{
+    dna_msr_t* msr = c->msr;
+    for (uint64_t r = 0; r < c->nrows; ++r) {
+        const RowDesc& d = c->rows[r];
+        if (d.clustered)
+            continue;
+        dna_msr_t& m = msr[d.rec];
+        if (c->reduced)
+            m.term1 = m.preAdjMeas;
+        else
+            m.preAdjMeas = m.term1;
+        first_run_reduce((char)d.type, m, d.st, c->stn, est);
+    }
+    uint64_t pool = 0;
+    for (ClusterDesc& cd : c->clusters) {
+        cd.vinv_off = pool;
+        pool += (uint64_t)cd.n * cd.n;
+    }
+    c->cvmat.assign(pool, 0.0);
+    const double lim = std::fmin(1.0e-5, c->o.fixed_std_dev);
+    for (ClusterDesc& cd : c->clusters) {
+        double* V = c->cvmat.data() + cd.vinv_off;
+        const uint32_t n = cd.n;
+        if (cd.type == 'D') {
+            const uint32_t ro = c->row_base[cd.row0];
+            double previousDirection = msr[ro].term1;
+            for (uint32_t a = 0; a < n; ++a) {
+                const RowDesc& d = c->rows[cd.row0 + a];
+                dna_msr_t& dir = msr[d.rec];
+                dna_msr_t angle = msr[c->row_base[cd.row0 + a]];   // the reference's scratch angle record
+                if (c->reduced)
+                    angle.term1 = dir.preAdjMeas;
+                else {
+                    angle.term1 = dir.term1 - previousDirection;
+                    if (angle.term1 < 0)
+                        angle.term1 += kTwoPi;
+                    if (angle.term1 > kTwoPi)
+                        angle.term1 -= kTwoPi;
+                }
+                angle.preAdjMeas = angle.term1;
+                first_run_reduce('D', angle, d.st, c->stn, est);
+                dir.scale1 = angle.term1;
+                dir.preAdjMeas = angle.preAdjMeas;
+                dir.preAdjCorr = angle.preAdjCorr;
+                previousDirection = dir.term1;
+            }
+            if (!c->reduced) {
+                // angle = direction_a - direction_(a-1): V = A diag(var) A^T is tridiagonal
+                double prevVar = msr[ro].term2;
+                for (uint32_t a = 0; a < n; ++a) {
+                    dna_msr_t& dir = msr[c->rows[cd.row0 + a].rec];
+                    dir.scale2 = prevVar + dir.term2;
+                    dir.scale3 = (a + 1 < n) ? -dir.term2 : 0.0;
+                    prevVar = dir.term2;
+                }
+            }
+            for (uint32_t a = 0; a < n; ++a) {
+                const dna_msr_t& dir = msr[c->rows[cd.row0 + a].rec];
+                V[(size_t)a * n + a] = dir.scale2;
+                if (a + 1 < n)
+                    V[(size_t)a * n + a + 1] = V[(size_t)(a + 1) * n + a] = dir.scale3;
+            }
+            continue;
+        }
+        // X / Y
+        const uint32_t members = n / 3;
+        dna_msr_t* m0 = &msr[c->rows[cd.row0].rec];
+        double vS = m0->scale4, pS = m0->scale1, lS = m0->scale2, hS = m0->scale3;
+        if (vS < lim)
+            vS = 1.0;
+        if (pS < lim)
+            pS = 1.0;
+        if (lS < lim)
+            lS = 1.0;
+        if (hS < lim)
+            hS = 1.0;
+        bool scaleMatrix = std::fabs(vS - 1.0) > 1.0e-5;
+        const bool scalePartial = std::fabs(pS - 1.0) > 1.0e-5 || std::fabs(lS - 1.0) > 1.0e-5 || std::fabs(hS - 1.0) > 1.0e-5;
+        if (c->reduced)
+            scaleMatrix = false;
+        else if (scalePartial)
+            return c->fail("phi / lambda / height variance scalars on X / Y clusters are not handled yet (whole-matrix scalar only)");
+        auto put = [&](uint32_t r, uint32_t col, double& field) {
+            if (scaleMatrix)
+                field *= vS;   // written back: later consumers read the scaled matrix (SetGPSVarianceMatrix, ADJ:4425)
+            V[(size_t)r * n + col] = V[(size_t)col * n + r] = field;
+        };
+        for (uint32_t k = 0; k < members; ++k) {
+            dna_msr_t* r = &msr[c->rows[cd.row0 + 3 * k].rec];
+            for (int q = 0; q < 3; ++q) {
+                if (c->reduced)
+                    r[q].term1 = r[q].preAdjMeas;
+                else
+                    r[q].preAdjMeas = r[q].term1;
+            }
+            const uint32_t v = 3 * k;
+            put(v, v, r[0].term2);
+            put(v, v + 1, r[1].term2);
+            put(v + 1, v + 1, r[1].term3);
+            put(v, v + 2, r[2].term2);
+            put(v + 1, v + 2, r[2].term3);
+            put(v + 2, v + 2, r[2].term4);
+            const uint32_t ncov = r[0].vectorCount2;
+            if (v + 3 + 3 * ncov > n)
+                return c->fail("GNSS cluster covariance records exceed the cluster size");
+            for (uint32_t q = 0; q < ncov; ++q) {
+                dna_msr_t* cv = r + 3 + 3 * q;
+                const uint32_t cc = v + 3 + 3 * q;
+                for (uint32_t x = 0; x < 3; ++x) {
+                    put(v + x, cc, cv[x].term1);
+                    put(v + x, cc + 1, cv[x].term2);
+                    put(v + x, cc + 2, cv[x].term3);
+                }
+            }
+        }
+    }
     return 0;
 }
 
@@ -611,26 +860,33 @@ int gadj_prepare(gadj_ctx* c)
         if (m.station1 == m.station2)
             return c->fail("GNSS baseline with identical end stations");
     }
-    for (uint32_t fi : c->sfirst) {
-        const dna_msr_t& m = c->msr[fi];
-        if (m.station1 >= c->nstn || m.station2 >= c->nstn)
-            return c->fail("measurement refers to a station index beyond the station list");
-        if (m.station1 == m.station2)
-            return c->fail("two-station measurement with identical end stations");
-        if (!(m.term2 > 0.0))
-            return c->fail("Invalid variance matrix: non-positive measurement variance");
-    }
+    // a-priori Cartesian coordinates (PopulateEstimatedStationMatrix, ADJ:632-693): the first-run reductions need them
+    std::vector<double> est(3 * (size_t)c->nstn);
+    for (uint32_t s = 0; s < c->nstn; ++s)
+        geo_to_cart(c->ell, c->stn[s].currentLatitude, c->stn[s].currentLongitude, c->stn[s].currentHeight, &est[3 * s]);
     first_run_reduction(c);
-    first_run_reduction_scalar(c);
+    if (first_run_reduction_rows(c, est.data()))
+        return 1;
 
-    // unique station pairs -> edge slots (baselines first, then scalar rows)
-    const uint64_t nb = c->nbsl, ns = c->nscalar;
-    std::vector<uint64_t> keys(nb + ns);
-    for (uint64_t b = 0; b < nb + ns; ++b) {
-        const dna_msr_t& m = c->msr[b < nb ? c->first[b] : c->sfirst[b - nb]];
-        uint32_t lo = std::min(m.station1, m.station2), hi = std::max(m.station1, m.station2);
-        keys[b] = ((uint64_t)lo << 32) | hi;
+    // unique station pairs -> edge slots: baselines, the station pairs of every independent row, every pair of a cluster
+    const uint64_t nb = c->nbsl;
+    auto pair_key = [](uint32_t a, uint32_t b2) { return ((uint64_t)std::min(a, b2) << 32) | std::max(a, b2); };
+    std::vector<uint64_t> keys(nb);
+    for (uint64_t b = 0; b < nb; ++b) {
+        const dna_msr_t& m = c->msr[c->first[b]];
+        keys[b] = pair_key(m.station1, m.station2);
     }
+    for (const RowDesc& d : c->rows) {
+        if (d.clustered)
+            continue;
+        for (int x = 0; x < d.nst; ++x)
+            for (int y = x + 1; y < d.nst; ++y)
+                keys.push_back(pair_key(d.st[x], d.st[y]));
+    }
+    for (const ClusterDesc& cd : c->clusters)
+        for (uint32_t x = 0; x < cd.ns; ++x)
+            for (uint32_t y = x + 1; y < cd.ns; ++y)
+                keys.push_back(pair_key(c->cstn[cd.st0 + x], c->cstn[cd.st0 + y]));
     std::vector<uint64_t> uniq(keys);
     std::sort(uniq.begin(), uniq.end());
     uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
@@ -698,24 +954,42 @@ int gadj_prepare(gadj_ctx* c)
         diag_dest[s] = S.ndest[slot];
         diag_ld[s] = S.ndest_ld[slot];
     }
+    // edge word of the ordered pair (a, b): slot | bit31 when a is eliminated after b (a owns the rows of the stored block)
+    auto edge_word_of = [&](uint32_t a, uint32_t b2) {
+        uint64_t ei = std::lower_bound(uniq.begin(), uniq.end(), pair_key(a, b2)) - uniq.begin();
+        return (uint32_t)ei | (S.pos_of_stn[a] > S.pos_of_stn[b2] ? 0x80000000u : 0u);
+    };
     c->edge_word.resize(nb);
-    c->sedge_word.resize(ns);
-    parallel_for(nb + ns, [&](uint64_t b0, uint64_t b1) {
+    parallel_for(nb, [&](uint64_t b0, uint64_t b1) {
         for (uint64_t b = b0; b < b1; ++b) {
-            const dna_msr_t& m = c->msr[b < nb ? c->first[b] : c->sfirst[b - nb]];
-            uint64_t ei = std::lower_bound(uniq.begin(), uniq.end(), keys[b]) - uniq.begin();
-            uint32_t flip = S.pos_of_stn[m.station1] > S.pos_of_stn[m.station2] ? 0x80000000u : 0u;
-            (b < nb ? c->edge_word[b] : c->sedge_word[b - nb]) = (uint32_t)ei | flip;
+            const dna_msr_t& m = c->msr[c->first[b]];
+            c->edge_word[b] = edge_word_of(m.station1, m.station2);
         }
     });
+    for (RowDesc& d : c->rows) {
+        if (d.nst >= 2)
+            d.edge[0] = edge_word_of(d.st[0], d.st[1]);
+        if (d.nst >= 3) {
+            d.edge[1] = edge_word_of(d.st[0], d.st[2]);
+            d.edge[2] = edge_word_of(d.st[1], d.st[2]);
+        }
+    }
+    c->pair_word.clear();
+    for (ClusterDesc& cd : c->clusters) {
+        cd.pair_off = c->pair_word.size();
+        for (uint32_t x = 0; x < cd.ns; ++x)
+            for (uint32_t y = 0; y < cd.ns; ++y)
+                c->pair_word.push_back(x == y ? 0u : edge_word_of(c->cstn[cd.st0 + x], c->cstn[cd.st0 + y]));
+    }
 
-    // a-priori Cartesian coordinates and constraint blocks
-    std::vector<double> est(3 * (size_t)c->nstn), cb(9 * (size_t)c->nstn), llh0(3 * (size_t)c->nstn);
+    // geographic coordinates, geoid separations and constraint blocks
+    std::vector<double> cb(9 * (size_t)c->nstn), llh0(3 * (size_t)c->nstn);
+    std::vector<float> geoid(c->nstn);
     for (uint32_t s = 0; s < c->nstn; ++s) {
         llh0[3 * s] = c->stn[s].currentLatitude;
         llh0[3 * s + 1] = c->stn[s].currentLongitude;
         llh0[3 * s + 2] = c->stn[s].currentHeight;
-        geo_to_cart(c->ell, c->stn[s].currentLatitude, c->stn[s].currentLongitude, c->stn[s].currentHeight, &est[3 * s]);
+        geoid[s] = c->stn[s].geoidSep;
         if (!constraint_block(c, c->stn[s], &cb[9 * s]))
             return c->fail("station constraint variance matrix is not positive definite");
     }
@@ -727,8 +1001,17 @@ int gadj_prepare(gadj_ctx* c)
     ok &= c->d_msr.resize(c->nmsr);
     ok &= c->d_first.upload(c->first);
     ok &= c->d_edge.upload(c->edge_word);
-    ok &= c->d_sfirst.upload(c->sfirst);
-    ok &= c->d_sedge.upload(c->sedge_word);
+    ok &= c->d_rows.upload(c->rows);
+    ok &= c->d_clusters.upload(c->clusters);
+    ok &= c->d_cstn.upload(c->cstn);
+    ok &= c->d_inc_ptr.upload(c->inc_ptr);
+    ok &= c->d_inc.upload(c->inc);
+    ok &= c->d_pair_word.upload(c->pair_word);
+    ok &= c->d_geoid.upload(geoid);
+    ok &= c->d_row_l.resize(c->nrows);
+    ok &= c->d_row_a.resize(9 * (size_t)c->nrows);
+    ok &= c->d_row_t.resize(c->nrows);
+    ok &= c->d_cvinv.resize(c->cvmat.size());
     ok &= c->d_edge_hi.upload(c->edge_hi);
     ok &= c->d_edge_lo.upload(c->edge_lo);
     ok &= c->d_pos.upload(S.pos_of_stn);
@@ -758,6 +1041,26 @@ int gadj_prepare(gadj_ctx* c)
     if (!ok)
         return c->fail("out of device memory while allocating the adjustment state");
     dev::h2d(c->d_msr.p, c->msr, c->nmsr * sizeof(dna_msr_t));
+    if (!c->clusters.empty()) {
+        // FormInverseVarianceMatrix (ADJ:8472-8517) of every cluster matrix, on the device
+        DevArray<double> work;
+        if (!work.upload(c->cvmat))
+            return c->fail("out of device memory while inverting the cluster variance matrices");
+        dev::zero(c->d_info.p, c->d_info.bytes());
+        launch_cluster_inverse(c->d_clusters.p, (uint32_t)c->clusters.size(), work.p, c->d_cvinv.p, c->d_info.p, dev::stream());
+        int32_t info[4] = {0, 0, 0, 0};
+        dev::d2h(info, c->d_info.p, sizeof(info));
+        std::string e2 = dev::sync();
+        if (!e2.empty())
+            return c->fail(e2);
+        if (info[0] != 0) {
+            const ClusterDesc& cd = c->clusters[info[0] - 1];
+            return c->fail(std::string("Invalid variance matrix: the variance matrix of a '") + (char)cd.type +
+                           "' cluster is not positive definite (record " + std::to_string(c->rows[cd.row0].rec) + ")");
+        }
+        c->cvmat.clear();
+        c->cvmat.shrink_to_fit();
+    }
 
     size_t want = ideal_pool_doubles(S), least = min_pool_doubles(S);
     size_t budget;
@@ -863,24 +1166,46 @@ static void fill_assemble(gadj_ctx* c, AssembleParams& ap, int normals)
     ap.normals = normals;
 }
 
-static void fill_scalar(gadj_ctx* c, ScalarParams& sp, int normals)
+static void fill_rows(gadj_ctx* c, RowsParams& rp, int normals, int assemble)
 {
-    sp.msr = c->d_msr.p;
-    sp.first = c->d_sfirst.p;
-    sp.edge = c->d_sedge.p;
-    sp.est = c->d_est.p;
-    sp.llh = c->d_llh.p;
-    sp.ndiag = c->d_ndiag.p;
-    sp.noff = c->d_noff.p;
-    sp.w = c->d_w.p;
-    sp.vcv_diag = c->d_vcvd.p;
-    sp.vcv_off = c->d_vcvo.p;
-    sp.sums = c->d_sums.p;
-    sp.nrows = c->nscalar;
-    sp.semi_major = c->o.semi_major;
-    sp.inv_flattening = c->o.inv_flattening;
-    sp.critical = c->critical;
-    sp.normals = normals;
+    rp.msr = c->d_msr.p;
+    rp.rows = c->d_rows.p;
+    rp.nrows = c->nrows;
+    rp.est = c->d_est.p;
+    rp.llh = c->d_llh.p;
+    rp.geoid = c->d_geoid.p;
+    rp.row_l = c->d_row_l.p;
+    rp.row_a = c->d_row_a.p;
+    rp.ndiag = c->d_ndiag.p;
+    rp.noff = c->d_noff.p;
+    rp.w = c->d_w.p;
+    rp.vcv_diag = c->d_vcvd.p;
+    rp.vcv_off = c->d_vcvo.p;
+    rp.sums = c->d_sums.p;
+    rp.semi_major = c->o.semi_major;
+    rp.inv_flattening = c->o.inv_flattening;
+    rp.critical = c->critical;
+    rp.normals = normals;
+    rp.assemble = assemble;
+}
+
+static void fill_clusters(gadj_ctx* c, ClusterParams& cp, int normals)
+{
+    cp.clusters = c->d_clusters.p;
+    cp.nclusters = (uint32_t)c->clusters.size();
+    cp.row_l = c->d_row_l.p;
+    cp.row_a = c->d_row_a.p;
+    cp.row_t = c->d_row_t.p;
+    cp.cvinv = c->d_cvinv.p;
+    cp.cstn = c->d_cstn.p;
+    cp.inc_ptr = c->d_inc_ptr.p;
+    cp.inc = c->d_inc.p;
+    cp.pair_word = c->d_pair_word.p;
+    cp.ndiag = c->d_ndiag.p;
+    cp.noff = c->d_noff.p;
+    cp.w = c->d_w.p;
+    cp.sums = c->d_sums.p;
+    cp.normals = normals;
 }
 
 static void fill_scatter(gadj_ctx* c, ScatterParams& sp)
@@ -928,12 +1253,19 @@ int gadj_stage_begin(gadj_ctx* c, int flags)
     c->prof_begin(PK_ASSEMBLE);
     launch_assemble_g(ap, st);
     c->prof_end();
-    if (c->nscalar) {
-        ScalarParams sp;
-        fill_scalar(c, sp, normals ? 1 : 0);
+    if (c->nrows) {
+        RowsParams rp;
+        fill_rows(c, rp, normals ? 1 : 0, 1);
         c->prof_begin(PK_ASSEMBLE);
-        launch_assemble_scalar(sp, st);
+        launch_rows(rp, st);
         c->prof_end();
+        if (!c->clusters.empty()) {
+            ClusterParams cp;
+            fill_clusters(c, cp, normals ? 1 : 0);
+            c->prof_begin(PK_ASSEMBLE);
+            launch_clusters(cp, st);
+            c->prof_end();
+        }
     }
     dev::event_record(c->ev[1]);
     // ---- equilibrate + scatter into the front panels ------------------------------
@@ -1270,10 +1602,17 @@ int gadj_statistics(gadj_ctx* c, gadj_stats* stt, int write_back)
     sp.nbaselines = c->nbsl;
     sp.critical = c->critical;
     launch_stats_g(sp, st);
-    if (c->nscalar) {
-        ScalarParams scp;
-        fill_scalar(c, scp, 0);
-        launch_stats_scalar(scp, st);
+    if (c->nrows) {
+        // re-linearise the rows at the final estimates, then per-row statistics and the cluster chi-squares
+        RowsParams rp;
+        fill_rows(c, rp, 0, 0);
+        launch_rows(rp, st);
+        launch_rows_stats(rp, st);
+        if (!c->clusters.empty()) {
+            ClusterParams cp;
+            fill_clusters(c, cp, 0);
+            launch_cluster_chi(cp, st);
+        }
     }
     double sums[8];
     dev::d2h(sums, c->d_sums.p, sizeof(sums));
@@ -1294,7 +1633,7 @@ int gadj_statistics(gadj_ctx* c, gadj_stats* stt, int write_back)
         }
     std::memset(stt, 0, sizeof(*stt));
     stt->chi_squared = sums[0];
-    stt->measurement_params = (uint32_t)(3 * c->nbsl + c->nscalar);
+    stt->measurement_params = (uint32_t)(3 * c->nbsl + c->nrows);
     stt->unknown_params = 3 * c->nstn - c->constrained_components;
     stt->dof = (int64_t)stt->measurement_params - (int64_t)stt->unknown_params;   // ADJ:6856
     stt->sigma_zero = stt->dof != 0 ? stt->chi_squared / (double)stt->dof : 0.0;

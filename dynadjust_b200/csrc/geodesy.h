@@ -131,53 +131,4 @@ GADJ_HD bool spd3_inverse(const double* v, double* out6)
     return true;
 }
 
-// ---- scalar two-station measurements ---------------------------------------------------------
-// One design row: residual l = measured - computed, partials a[0..2] wrt station 1 and a[3..5] wrt station 2,
-// weight p = 1 / variance (UpdateAtVinv, dnaadjust.cpp:1285-1320).
-struct ScalarRow {
-    double l, p;
-    double a[6];
-};
-
-// 'S' slope distance  (UpdateDesignNormalMeasMatrices_S, dnaadjust.cpp:5437-5493; instrument/target heights are
-//                      both rotated at station 1, dnatemplategeodesyfuncs.hpp:763-771)
-// 'L' level difference (UpdateDesignNormalMeasMatrices_L, dnaadjust.cpp:5717-5784; EllipsoidHeight,
-//                      dnatemplategeodesyfuncs.hpp:909-930)
-// e1/e2: estimated XYZ; llh1/llh2: current geographic coordinates of the two stations.
-GADJ_HD bool scalar_row(char type, double term1, double term2, double term3, double term4, const double* e1, const double* e2,
-                        const double* llh1, const double* llh2, const Ellipsoid& ell, ScalarRow& r)
-{
-    r.p = 1.0 / term2;
-    if (type == 'S') {
-        const double cl = cos(llh1[0]), sl = sin(llh1[0]), co = cos(llh1[1]), so = sin(llh1[1]);
-        const double dX = e2[0] - e1[0] + cl * co * term4 - cl * co * term3;
-        const double dY = e2[1] - e1[1] + cl * so * term4 - cl * so * term3;
-        const double dZ = e2[2] - e1[2] + sl * term4 - sl * term3;
-        const double comp = sqrt(dX * dX + dY * dY + dZ * dZ);
-        r.l = term1 - comp;
-        r.a[0] = -dX / comp;
-        r.a[1] = -dY / comp;
-        r.a[2] = -dZ / comp;
-        r.a[3] = -r.a[0];
-        r.a[4] = -r.a[1];
-        r.a[5] = -r.a[2];
-        return true;
-    }
-    if (type == 'L') {
-        const double nu1 = prime_vertical(ell, llh1[0]), nu2 = prime_vertical(ell, llh2[0]);
-        const double Zn1 = ell.e2 * nu1 * sin(llh1[0]), Zn2 = ell.e2 * nu2 * sin(llh2[0]);
-        const double h1 = sqrt(e1[0] * e1[0] + e1[1] * e1[1] + (e1[2] + Zn1) * (e1[2] + Zn1)) - nu1;
-        const double h2 = sqrt(e2[0] * e2[0] + e2[1] * e2[1] + (e2[2] + Zn2) * (e2[2] + Zn2)) - nu2;
-        r.l = term1 - (h2 - h1);
-        r.a[0] = -e1[0] / (nu1 + h1);
-        r.a[1] = -e1[1] / (nu1 + h1);
-        r.a[2] = -(e1[2] + Zn1) / (nu1 + h1);
-        r.a[3] = e2[0] / (nu2 + h2);
-        r.a[4] = e2[1] / (nu2 + h2);
-        r.a[5] = (e2[2] + Zn2) / (nu2 + h2);
-        return true;
-    }
-    return false;
-}
-
 }  // namespace gadj

@@ -132,25 +132,16 @@ struct AssembleParams {
 };
 void launch_assemble_g(const AssembleParams& p, void* stream);
 
-// scalar two-station rows ('S' slope distance, 'L' level difference): one record, one design row each
-struct ScalarParams {
-    dna_msr_t* msr;              // device records (statistics write the result fields back)
-    const uint32_t* first;       // per row: record index
-    const uint32_t* edge;        // per row: edge slot | (1u<<31 when station1 is eliminated after station2)
-    const double* est;           // 3 x nstn estimated Cartesian coordinates
-    const double* llh;           // 3 x nstn current latitude, longitude, height
-    double* ndiag;
-    double* noff;
-    double* w;
-    const double* vcv_diag;      // statistics pass
-    const double* vcv_off;
-    double* sums;                // statistics pass: [0] chi2, [1] pelzer sum, [2] pelzer count, [3] outliers
-    uint64_t nrows;
-    double semi_major, inv_flattening, critical;
-    int32_t normals;
-};
-void launch_assemble_scalar(const ScalarParams& p, void* stream);
-void launch_stats_scalar(const ScalarParams& p, void* stream);
+// design rows of every other measurement type and the D / X / Y clusters: parameter blocks in rows.h
+struct RowsParams;
+struct ClusterParams;
+struct ClusterDesc;
+void launch_rows(const RowsParams& p, void* stream);
+void launch_rows_stats(const RowsParams& p, void* stream);
+void launch_clusters(const ClusterParams& p, void* stream);
+void launch_cluster_chi(const ClusterParams& p, void* stream);
+// V -> V^-1 for every cluster matrix of the pool (work is destroyed); info receives (first failing cluster + 1)
+void launch_cluster_inverse(const ClusterDesc* clusters, uint32_t nclusters, double* work, double* out, int* info, void* stream);
 
 // diagonal blocks <- per-station constraint block (FormConstraintStationVarianceMatrix, ADJ:2041-2137)
 void launch_init_normals(const double* cblock, double* ndiag, double* noff, double* w, uint32_t nstn, uint64_t nedge,

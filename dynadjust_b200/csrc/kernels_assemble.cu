@@ -161,107 +161,6 @@ __global__ void __launch_bounds__(ASM_TILE) assemble_g_kernel(const AssemblePara
     }
 }
 
-// ---- scalar rows ('S', 'L'): one thread per measurement, same block updates as a rank-1 term p a a^T ----------
-__global__ void __launch_bounds__(128) assemble_scalar_kernel(const ScalarParams p)
-{
-    const Ellipsoid ell = make_ellipsoid(p.semi_major, p.inv_flattening);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.nrows; i += (uint64_t)gridDim.x * blockDim.x) {
-        const dna_msr_t* m = p.msr + p.first[i];
-        const uint32_t s1 = m->station1, s2 = m->station2;
-        ScalarRow r;
-        if (!scalar_row(m->measType, m->term1, m->term2, m->term3, m->term4, p.est + 3 * (size_t)s1, p.est + 3 * (size_t)s2,
-                        p.llh + 3 * (size_t)s1, p.llh + 3 * (size_t)s2, ell, r))
-            continue;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            atomicAdd(p.w + 3 * (size_t)s1 + k, r.p * r.a[k] * r.l);
-            atomicAdd(p.w + 3 * (size_t)s2 + k, r.p * r.a[3 + k] * r.l);
-        }
-        if (p.normals) {
-            const uint32_t ew = p.edge[i];
-            double* __restrict__ d1 = p.ndiag + 9 * (size_t)s1;
-            double* __restrict__ d2 = p.ndiag + 9 * (size_t)s2;
-            double* __restrict__ o = p.noff + 9 * (size_t)(ew & 0x7FFFFFFFu);
-            const double* ahi = (ew & 0x80000000u) ? r.a : r.a + 3;   // partials of the later-eliminated station
-            const double* alo = (ew & 0x80000000u) ? r.a + 3 : r.a;
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    atomicAdd(d1 + 3 * a + b, r.p * r.a[a] * r.a[b]);
-                    atomicAdd(d2 + 3 * a + b, r.p * r.a[3 + a] * r.a[3 + b]);
-                    atomicAdd(o + 3 * a + b, r.p * ahi[a] * alo[b]);
-                }
-        }
-    }
-}
-
-// ComputePrecisionAdjMsrs_BCEKLMSVZ + UpdateMsrRecord + ComputeChiSquare_ABCEHIJKLMPQRSVZ (ADJ:7949-7982, 8187-8298, 8430-8437)
-__global__ void __launch_bounds__(128) stats_scalar_kernel(const ScalarParams p)
-{
-    const Ellipsoid ell = make_ellipsoid(p.semi_major, p.inv_flattening);
-    double s_chi = 0.0, s_pel = 0.0, s_cnt = 0.0, s_out = 0.0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.nrows; i += (uint64_t)gridDim.x * blockDim.x) {
-        dna_msr_t* m = p.msr + p.first[i];
-        const uint32_t s1 = m->station1, s2 = m->station2;
-        ScalarRow r;
-        if (!scalar_row(m->measType, m->term1, m->term2, m->term3, m->term4, p.est + 3 * (size_t)s1, p.est + 3 * (size_t)s2,
-                        p.llh + 3 * (size_t)s1, p.llh + 3 * (size_t)s2, ell, r))
-            continue;
-        const uint32_t ew = p.edge[i];
-        const double* __restrict__ Qo = p.vcv_off + 9 * (size_t)(ew & 0x7FFFFFFFu);
-        const bool s1_is_hi = (ew & 0x80000000u) != 0;
-        const double* __restrict__ Q11 = p.vcv_diag + 9 * (size_t)s1;
-        const double* __restrict__ Q22 = p.vcv_diag + 9 * (size_t)s2;
-        double prec = 0.0;
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                const double q21 = s1_is_hi ? Qo[3 * b + a] : Qo[3 * a + b];   // N^-1[s2+a, s1+b]
-                prec += r.a[a] * Q11[3 * a + b] * r.a[b] + r.a[3 + a] * Q22[3 * a + b] * r.a[3 + b] + 2.0 * r.a[3 + a] * q21 * r.a[b];
-            }
-        const double corr = -r.l;
-        double rp = m->term2 - prec;
-        if (rp < 0.0)
-            rp = fabs(rp);
-        double pel = sqrt(m->term2) / sqrt(rp);
-        if (pel < 0. || pel > 700.)
-            pel = 999.99;
-        const double nstat = corr / sqrt(rp);
-        if (fabs(nstat) > p.critical)
-            s_out += 1.0;
-        if (pel > 0. && pel < 700.) {
-            s_pel += pel * pel - 1.;
-            s_cnt += 1.0;
-        } else
-            pel = 999.99;
-        double adj = m->term1 + corr;
-        if (m->measType == 'L')
-            adj -= m->preAdjCorr;
-        m->measCorr = corr;
-        m->measAdj = adj;
-        m->measAdjPrec = prec;
-        m->residualPrec = rp;
-        m->NStat = nstat;
-        m->PelzerRel = pel;
-        s_chi += r.l * r.l / m->term2;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s_chi += __shfl_xor_sync(0xffffffffu, s_chi, o);
-        s_pel += __shfl_xor_sync(0xffffffffu, s_pel, o);
-        s_cnt += __shfl_xor_sync(0xffffffffu, s_cnt, o);
-        s_out += __shfl_xor_sync(0xffffffffu, s_out, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(p.sums + 0, s_chi);
-        atomicAdd(p.sums + 1, s_pel);
-        atomicAdd(p.sums + 2, s_cnt);
-        atomicAdd(p.sums + 3, s_out);
-    }
-}
-
 __global__ void init_normals_kernel(const double* __restrict__ cblock, double* __restrict__ ndiag, double* __restrict__ noff,
                                     double* __restrict__ w, uint64_t n_diag, uint64_t n_off, uint64_t n_w)
 {
@@ -566,20 +465,6 @@ void launch_assemble_g(const AssembleParams& p, void* stream)
         assemble_g_kernel<true><<<grid, ASM_TILE, ASM_SMEM, (cudaStream_t)stream>>>(p, ntiles);
     else
         assemble_g_kernel<false><<<grid * 4, ASM_TILE, 0, (cudaStream_t)stream>>>(p, ntiles);
-}
-
-void launch_assemble_scalar(const ScalarParams& p, void* stream)
-{
-    if (p.nrows == 0)
-        return;
-    assemble_scalar_kernel<<<grid_for(p.nrows, 128), 128, 0, (cudaStream_t)stream>>>(p);
-}
-
-void launch_stats_scalar(const ScalarParams& p, void* stream)
-{
-    if (p.nrows == 0)
-        return;
-    stats_scalar_kernel<<<grid_for(p.nrows, 128), 128, 0, (cudaStream_t)stream>>>(p);
 }
 
 void launch_init_normals(const double* cblock, double* ndiag, double* noff, double* w, uint32_t nstn, uint64_t nedge,

@@ -8,6 +8,7 @@
 
 #include "../../dynadjust_b200/csrc/geodesy.h"
 #include "../../dynadjust_b200/csrc/kernels.h"
+#include "../../dynadjust_b200/csrc/rows.h"
 
 namespace gadj {
 
@@ -225,80 +226,94 @@ void launch_assemble_g(const AssembleParams& p, void*)
     }
 }
 
-void launch_assemble_scalar(const ScalarParams& p, void*)
+// rows / clusters: the arithmetic is shared with the kernels (rows.h); only the thread loops differ
+void launch_rows(const RowsParams& p, void*)
 {
-    const Ellipsoid ell = make_ellipsoid(p.semi_major, p.inv_flattening);
-    for (uint64_t i = 0; i < p.nrows; ++i) {
-        const dna_msr_t* m = p.msr + p.first[i];
-        const uint32_t s1 = m->station1, s2 = m->station2;
-        ScalarRow r;
-        if (!scalar_row(m->measType, m->term1, m->term2, m->term3, m->term4, p.est + 3 * (size_t)s1, p.est + 3 * (size_t)s2,
-                        p.llh + 3 * (size_t)s1, p.llh + 3 * (size_t)s2, ell, r))
+    const Ellipsoid el = make_ellipsoid(p.semi_major, p.inv_flattening);
+    for (uint64_t i = 0; i < p.nrows; ++i)
+        row_body(p, i, el);
+}
+
+void launch_rows_stats(const RowsParams& p, void*)
+{
+    const Ellipsoid el = make_ellipsoid(p.semi_major, p.inv_flattening);
+    double acc[4] = {0, 0, 0, 0};
+    for (uint64_t i = 0; i < p.nrows; ++i)
+        row_stats_body(p, i, el, acc);
+    for (int k = 0; k < 4; ++k)
+        p.sums[k] += acc[k];
+}
+
+void launch_clusters(const ClusterParams& p, void*)
+{
+    for (uint32_t ci = 0; ci < p.nclusters; ++ci) {
+        const ClusterDesc c = p.clusters[ci];
+        for (uint32_t r = 0; r < c.n; ++r)
+            cluster_t_body(p, c, r);
+        for (uint32_t j = 0; j < c.ns; ++j)
+            cluster_rhs_body(p, c, j);
+        if (p.normals)
+            for (uint64_t q = 0; q < (uint64_t)c.ns * (c.ns + 1) / 2; ++q)
+                cluster_pair_body(p, c, q);
+    }
+}
+
+void launch_cluster_chi(const ClusterParams& p, void*)
+{
+    for (uint32_t ci = 0; ci < p.nclusters; ++ci) {
+        const ClusterDesc c = p.clusters[ci];
+        if (c.type == 'D')
             continue;
-        for (int k = 0; k < 3; ++k) {
-            p.w[3 * (size_t)s1 + k] += r.p * r.a[k] * r.l;
-            p.w[3 * (size_t)s2 + k] += r.p * r.a[3 + k] * r.l;
-        }
-        if (p.normals) {
-            const uint32_t ew = p.edge[i];
-            const double* ahi = (ew & 0x80000000u) ? r.a : r.a + 3;
-            const double* alo = (ew & 0x80000000u) ? r.a + 3 : r.a;
-            for (int a = 0; a < 3; ++a)
-                for (int b = 0; b < 3; ++b) {
-                    p.ndiag[9 * (size_t)s1 + 3 * a + b] += r.p * r.a[a] * r.a[b];
-                    p.ndiag[9 * (size_t)s2 + 3 * a + b] += r.p * r.a[3 + a] * r.a[3 + b];
-                    p.noff[9 * (size_t)(ew & 0x7FFFFFFFu) + 3 * a + b] += r.p * ahi[a] * alo[b];
-                }
+        for (uint32_t r = 0; r < c.n; ++r) {
+            cluster_t_body(p, c, r);
+            p.sums[0] += p.row_l[c.row0 + r] * p.row_t[c.row0 + r];
         }
     }
 }
 
-void launch_stats_scalar(const ScalarParams& p, void*)
+// plain Cholesky inverse (factor, invert the factor, W^T W) per cluster matrix
+void launch_cluster_inverse(const ClusterDesc* clusters, uint32_t nclusters, double* work, double* out, int* info, void*)
 {
-    const Ellipsoid ell = make_ellipsoid(p.semi_major, p.inv_flattening);
-    for (uint64_t i = 0; i < p.nrows; ++i) {
-        dna_msr_t* m = p.msr + p.first[i];
-        const uint32_t s1 = m->station1, s2 = m->station2;
-        ScalarRow r;
-        if (!scalar_row(m->measType, m->term1, m->term2, m->term3, m->term4, p.est + 3 * (size_t)s1, p.est + 3 * (size_t)s2,
-                        p.llh + 3 * (size_t)s1, p.llh + 3 * (size_t)s2, ell, r))
-            continue;
-        const uint32_t ew = p.edge[i];
-        const double* Qo = p.vcv_off + 9 * (size_t)(ew & 0x7FFFFFFFu);
-        const bool s1_is_hi = (ew & 0x80000000u) != 0;
-        const double* Q11 = p.vcv_diag + 9 * (size_t)s1;
-        const double* Q22 = p.vcv_diag + 9 * (size_t)s2;
-        double prec = 0.0;
-        for (int a = 0; a < 3; ++a)
-            for (int b = 0; b < 3; ++b) {
-                const double q21 = s1_is_hi ? Qo[3 * b + a] : Qo[3 * a + b];
-                prec += r.a[a] * Q11[3 * a + b] * r.a[b] + r.a[3 + a] * Q22[3 * a + b] * r.a[3 + b] + 2.0 * r.a[3 + a] * q21 * r.a[b];
+    for (uint32_t ci = 0; ci < nclusters; ++ci) {
+        const uint32_t n = clusters[ci].n;
+        double* A = work + clusters[ci].vinv_off;
+        double* O = out + clusters[ci].vinv_off;
+        std::vector<double> L((size_t)n * n, 0.0), W((size_t)n * n, 0.0);
+        bool bad = false;
+        for (uint32_t j = 0; j < n; ++j) {
+            double d = A[(size_t)j * n + j];
+            for (uint32_t k = 0; k < j; ++k)
+                d -= L[(size_t)j * n + k] * L[(size_t)j * n + k];
+            if (!(d > 0.0)) {
+                bad = true;
+                d = 1.0;
             }
-        const double corr = -r.l;
-        double rp = m->term2 - prec;
-        if (rp < 0.0)
-            rp = std::fabs(rp);
-        double pel = std::sqrt(m->term2) / std::sqrt(rp);
-        if (pel < 0. || pel > 700.)
-            pel = 999.99;
-        const double nstat = corr / std::sqrt(rp);
-        if (std::fabs(nstat) > p.critical)
-            p.sums[3] += 1.0;
-        if (pel > 0. && pel < 700.) {
-            p.sums[1] += pel * pel - 1.;
-            p.sums[2] += 1.0;
-        } else
-            pel = 999.99;
-        double adj = m->term1 + corr;
-        if (m->measType == 'L')
-            adj -= m->preAdjCorr;
-        m->measCorr = corr;
-        m->measAdj = adj;
-        m->measAdjPrec = prec;
-        m->residualPrec = rp;
-        m->NStat = nstat;
-        m->PelzerRel = pel;
-        p.sums[0] += r.l * r.l / m->term2;
+            L[(size_t)j * n + j] = std::sqrt(d);
+            for (uint32_t i = j + 1; i < n; ++i) {
+                double s = A[(size_t)i * n + j];
+                for (uint32_t k = 0; k < j; ++k)
+                    s -= L[(size_t)i * n + k] * L[(size_t)j * n + k];
+                L[(size_t)i * n + j] = s / L[(size_t)j * n + j];
+            }
+        }
+        for (uint32_t c = 0; c < n; ++c) {
+            W[(size_t)c * n + c] = 1.0 / L[(size_t)c * n + c];
+            for (uint32_t i = c + 1; i < n; ++i) {
+                double s = 0.0;
+                for (uint32_t k = c; k < i; ++k)
+                    s += L[(size_t)i * n + k] * W[(size_t)k * n + c];
+                W[(size_t)i * n + c] = -s / L[(size_t)i * n + i];
+            }
+        }
+        for (uint32_t i = 0; i < n; ++i)
+            for (uint32_t j = 0; j <= i; ++j) {
+                double s = 0.0;
+                for (uint32_t k = i; k < n; ++k)
+                    s += W[(size_t)k * n + i] * W[(size_t)k * n + j];
+                O[(size_t)i * n + j] = O[(size_t)j * n + i] = s;
+            }
+        if (bad && info[0] == 0)
+            info[0] = (int)ci + 1;
     }
 }
 

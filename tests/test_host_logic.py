@@ -66,6 +66,35 @@ def test_mixed_terrestrial_rows(oracle, hostsim_path):
     parity.check_against_oracle(oracle, hostsim_path, 300, 500, 23, n_distances=400, n_levels=300, leaf_stations=24)
 
 
+@pytest.mark.parametrize("kind", list("ABKCEMSVZLHRIJPQ"))
+def test_every_scalar_type(oracle, hostsim_path, kind):
+    """One-, two- and three-station rows of each terrestrial type with deflections of the vertical
+    on half of the stations: first-run reductions, per-iteration re-linearisation, statistics written to the records."""
+    parity.check_against_oracle(oracle, hostsim_path, 120, 260, 31 + ord(kind), terrestrial=dict(scalars={kind: 260}),
+                                leaf_stations=16)
+
+
+def test_direction_sets(oracle, hostsim_path):
+    """D sets: derived angles, tridiagonal angle VCV inverted on the device stand-in, ignored directions inside a set."""
+    parity.check_against_oracle(oracle, hostsim_path, 150, 300, 41, terrestrial=dict(n_dir_sets=90), leaf_stations=16)
+    parity.check_against_oracle(oracle, hostsim_path, 150, 300, 42, terrestrial=dict(n_dir_sets=90, ignore_some=True),
+                                leaf_stations=24)
+
+
+def test_gnss_clusters(oracle, hostsim_path):
+    """X baseline clusters and Y point clusters with full VCVs (covariance records), with and without the v-scale."""
+    parity.check_against_oracle(oracle, hostsim_path, 150, 300, 43, terrestrial=dict(n_x=50, n_y=30), leaf_stations=16)
+    parity.check_against_oracle(oracle, hostsim_path, 150, 300, 44, terrestrial=dict(n_x=40, n_y=40, v_scale=2.5),
+                                leaf_stations=16)
+
+
+def test_all_types_together(oracle, hostsim_path):
+    """BASELINE config C3's mix and more: every type in one network, nested dissection and a chain of blocks."""
+    mix = dict(scalars={k: 50 for k in "ABKCEMSVZLHRIJPQ"}, n_dir_sets=40, n_x=20, n_y=20, ignore_some=True)
+    parity.check_against_oracle(oracle, hostsim_path, 300, 800, 45, terrestrial=mix, leaf_stations=24)
+    parity.check_against_oracle(oracle, hostsim_path, 300, 800, 46, terrestrial=mix, blocks=lambda n: parity.chain_blocks(n, 50))
+
+
 def test_normals_and_rhs(oracle, hostsim_path):
     parity.check_normals(oracle, hostsim_path, 80, 240, 4, leaf_stations=12)
 
@@ -97,10 +126,22 @@ def test_error_paths(hostsim_path):
     with pytest.raises(engine.AdjustmentError, match="beyond the station list"):
         adj.prepare()
     other = msr.copy()
-    other["measType"][0:3] = b"Q"
+    other["measType"][0:3] = b"?"
     adj.set_measurements(other)
-    with pytest.raises(engine.AdjustmentError, match="not handled"):
+    with pytest.raises(engine.AdjustmentError, match="not a DynAdjust measurement type"):
         adj.prepare()
+    from dynadjust_b200 import synth_terrestrial
+    s2, m2, _, _ = synth_terrestrial.terrestrial_network(40, 100, 3, n_x=4)
+    m2["scale1"][m2["measType"] == b"X"] = 2.0     # phi scalar on a cluster: refused, not silently ignored
+    a2 = engine.Adjustment(s2, m2, lib_path=hostsim_path)
+    with pytest.raises(engine.AdjustmentError, match="not handled yet"):
+        a2.prepare()
+    s3, m3, _, _ = synth_terrestrial.terrestrial_network(40, 100, 3, n_y=4)
+    ycl = np.where(m3["measType"] == b"Y")[0]
+    m3["term2"][ycl[0]] = -1.0                      # indefinite cluster VCV -> the reference's message
+    a3 = engine.Adjustment(s3, m3, lib_path=hostsim_path)
+    with pytest.raises(engine.AdjustmentError, match="Invalid variance matrix"):
+        a3.prepare()
     ign = msr.copy()
     ign["ignore"][0:3] = 1                      # ignored measurements are skipped like the reference's CML
     adj.set_measurements(ign)
