@@ -233,6 +233,8 @@ def run_engine(args):
         step()
     runner.profile_enable(True)
     runner.profile_read(reset=True)
+    if getattr(runner, "_trace", None) is not None:
+        runner._trace.clear()
     phase = dict(assemble=0.0, factor=0.0, solve=0.0, inverse=0.0)
     with ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank) as clk:
         barrier()
@@ -247,6 +249,9 @@ def run_engine(args):
         t1 = time.perf_counter()
     prof = runner.profile_read(reset=True)
     runner.profile_enable(False)
+    if getattr(runner, "_trace", None) is not None:     # GADJ_MG_TRACE=<path prefix>: per-rank stage / exchange wall times
+        with open(f"{os.environ['GADJ_MG_TRACE']}.rank{rank}.json", "w") as f:
+            json.dump(dict(steps=args.steps, records=runner._trace), f)
     clocks = clk.summary()
     ms_step = (t1 - t0) * 1e3 / args.steps
     if world > 1:

@@ -1768,8 +1768,12 @@ int gadj_profile_read(gadj_ctx* c, gadj_profile* out, int reset)
     if (!e.empty())
         return c->fail(e);
     FILE* dump = nullptr;
-    if (const char* dp = getenv("GADJ_PROFILE_DUMP"))
-        dump = fopen(dp, "a");
+    if (const char* dp = getenv("GADJ_PROFILE_DUMP")) {
+        std::string path = dp;
+        if (c->mg_world > 1)
+            path += ".rank" + std::to_string(c->mg_rank);
+        dump = fopen(path.c_str(), "a");
+    }
     for (size_t i = 0; i < c->prof_items.size(); ++i) {
         double ms = dev::event_elapsed_ms(c->prof_ev[2 * i], c->prof_ev[2 * i + 1]);
         const auto& it = c->prof_items[i];

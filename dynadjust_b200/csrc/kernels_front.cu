@@ -13,72 +13,208 @@ namespace {
 constexpr int DP = NB + 1;  // shared-memory pitch (doubles): conflict-free for row- and column-wise walks
 
 // ---- pivot tile: L = chol(D), W = L^-1 ----------------------------------------------
-// One CTA (NB threads) per tile.  Left-looking column Cholesky in shared memory: thread i owns
-// row i.  The inverse is formed column-by-column (thread c solves L x = e_c) into the strictly
-// upper triangle of the same buffer (x_k stored at S[c][k]), so one 128 x 129 FP64 tile suffices.
-__global__ void __launch_bounds__(NB, 1) diag_kernel(const DiagOp* __restrict__ ops, int* __restrict__ info)
+// One CTA (256 threads) per tile, the tile held in shared memory (pitch 129: conflict-free row and column walks)
+// and padded to 128 x 128 with an identity so that every step runs on full blocks.
+//   factor : blocked right-looking Cholesky, panel width 16.  Panel: one thread per row keeps its 16 panel
+//            entries in registers (two barriers per column); trailing update: 4 x 4 register tiles over all
+//            256 threads, rank-16 per step.
+//   inverse: in place in the lower triangle (L has been stored to global memory by then): 16 x 16 diagonal
+//            blocks by forward substitution in registers, then block doubling 16 -> 32 -> 64 -> 128 with
+//            W21 = -W22 (L21 W11) as two register-tiled products per level.
+constexpr int DIAG_THREADS = 256;
+constexpr int PBW = 16;
+
+// acc[x][y] += sum_k P[(pr + ti + tstride x) * DP + pc + k] * Q[(qr + k) * DP + qc + tj + tstride y],  k in [0, kn)
+__device__ __forceinline__ void tile_mm(const double* __restrict__ S, int prow, int pcol, int qrow, int qcol, int ti, int tj,
+                                        int tstride, int kn, double acc[4][4])
+{
+#pragma unroll 4
+    for (int k = 0; k < kn; ++k) {
+        double a[4], b[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+            a[x] = S[(prow + ti + tstride * x) * DP + pcol + k];
+#pragma unroll
+        for (int y = 0; y < 4; ++y)
+            b[y] = S[(qrow + k) * DP + qcol + tj + tstride * y];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y)
+                acc[x][y] += a[x] * b[y];
+    }
+}
+
+__global__ void __launch_bounds__(DIAG_THREADS, 1) diag_kernel(const DiagOp* __restrict__ ops, int* __restrict__ info)
 {
     extern __shared__ double S[];
-    __shared__ double dinv[NB];
+    __shared__ double colbuf[PBW];
+    __shared__ double piv;
     const DiagOp op = ops[blockIdx.x];
     const int w = op.w, tid = threadIdx.x;
     const int64_t ld = op.ldd;
-    // coalesced load of the lower triangle (row-major source)
-    for (int idx = tid; idx < w * w; idx += NB) {
-        int i = idx / w, j = idx - i * w;
-        S[i * DP + j] = (j <= i) ? op.D[i * ld + j] : 0.0;
+    const int wpad = (w + PBW - 1) & ~(PBW - 1);
+    // coalesced load of the lower triangle (row-major source); identity padding
+    for (int idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
+        const int i = idx >> 7, j = idx & (NB - 1);
+        double v = (i == j) ? 1.0 : 0.0;
+        if (i < w && j <= i)
+            v = op.D[i * ld + j];
+        S[i * DP + j] = v;
     }
     __syncthreads();
     if (op.factor) {
-        for (int j = 0; j < w; ++j) {
-            double s = 0.0;
-            if (tid >= j && tid < w) {
-                s = S[tid * DP + j];
-                for (int k = 0; k < j; ++k)
-                    s -= S[tid * DP + k] * S[j * DP + k];
+        for (int p0 = 0; p0 < wpad; p0 += PBW) {
+            // ---- panel: rows p0 .. wpad-1, columns p0 .. p0+15
+            const int i = tid;
+            const bool act = tid < wpad && i >= p0;
+            double r[PBW];
+            if (act) {
+#pragma unroll
+                for (int kk = 0; kk < PBW; ++kk)
+                    r[kk] = S[i * DP + p0 + kk];
             }
-            if (tid == j) {
-                if (!(s > 0.0)) {
-                    atomicCAS(info, 0, op.front + 1);
-                    s = 1.0;
+#pragma unroll
+            for (int jj = 0; jj < PBW; ++jj) {
+                if (tid == p0 + jj) {
+                    double d = r[jj];
+                    if (!(d > 0.0)) {
+                        atomicCAS(info, 0, op.front + 1);
+                        d = 1.0;
+                    }
+                    d = sqrt(d);
+                    r[jj] = d;
+                    piv = 1.0 / d;      // one division per column; the rows below multiply
                 }
-                s = sqrt(s);
-                S[j * DP + j] = s;
+                __syncthreads();
+                const bool below = act && i > p0 + jj;
+                if (below) {
+                    r[jj] = r[jj] * piv;
+                    if (i < p0 + PBW)
+                        colbuf[i - p0] = r[jj];
+                }
+                __syncthreads();
+                if (below) {
+                    const double l = r[jj];
+#pragma unroll
+                    for (int kk = jj + 1; kk < PBW; ++kk)
+                        r[kk] -= l * colbuf[kk];
+                }
+            }
+            if (act) {
+#pragma unroll
+                for (int kk = 0; kk < PBW; ++kk)
+                    if (p0 + kk <= i)
+                        S[i * DP + p0 + kk] = r[kk];
             }
             __syncthreads();
-            if (tid > j && tid < w)
-                S[tid * DP + j] = s / S[j * DP + j];
+            // ---- trailing update: S[i][k] -= sum_jj S[i][p0+jj] S[k][p0+jj] for rows / columns >= p0 + 16
+            const int t0 = p0 + PBW, tn = wpad - t0;
+            if (tn > 0) {
+                const int nt = tn >> 2;               // threads per dimension; each owns rows ti + nt x, columns tj + nt y
+                for (int t = tid; t < nt * nt; t += DIAG_THREADS) {
+                    const int ti = t / nt, tj = t - ti * nt;
+                    double acc[4][4] = {};
+#pragma unroll 4
+                    for (int k = 0; k < PBW; ++k) {
+                        double a[4], b[4];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+                            a[x] = S[(t0 + ti + nt * x) * DP + p0 + k];
+#pragma unroll
+                        for (int y = 0; y < 4; ++y)
+                            b[y] = S[(t0 + tj + nt * y) * DP + p0 + k];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int y = 0; y < 4; ++y)
+                                acc[x][y] += a[x] * b[y];
+                    }
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) {
+                            const int ii = t0 + ti + nt * x, kk = t0 + tj + nt * y;
+                            if (kk <= ii)
+                                S[ii * DP + kk] -= acc[x][y];
+                        }
+                }
+            }
             __syncthreads();
         }
-        for (int idx = tid; idx < w * w; idx += NB) {
-            int i = idx / w, j = idx - i * w;
+        for (int idx = tid; idx < w * w; idx += DIAG_THREADS) {
+            const int i = idx / w, j = idx - i * w;
             if (j <= i)
                 op.D[i * ld + j] = S[i * DP + j];
         }
     }
     if (op.W == nullptr && op.Wt == nullptr)
         return;
-    // W = L^-1: thread c owns column c; x_k (k > c) lives at S[c][k]
-    if (tid < w) {
-        const int c = tid;
-        const double xc = 1.0 / S[c * DP + c];
-        dinv[c] = xc;
-        for (int i = c + 1; i < w; ++i) {
-            double s = S[i * DP + c] * xc;
-            for (int k = c + 1; k < i; ++k)
-                s += S[i * DP + k] * S[c * DP + k];
-            S[c * DP + i] = -s / S[i * DP + i];
-        }
-    }
     __syncthreads();
-    for (int idx = tid; idx < w * w; idx += NB) {
-        int i = idx / w, j = idx - i * w;
-        // W[i][j] (row-major, lower)
+    // ---- W = L^-1, in place in the lower triangle -------------------------------------------------
+    {   // 16 x 16 diagonal blocks: thread (block d, column c) solves L x = e_c in registers
+        const int d = tid >> 4, c = tid & 15, base = d * PBW;
+        double x[PBW];
+        const bool act = base < wpad;
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < PBW; ++i) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < i; ++k)
+                    s += S[(base + i) * DP + base + k] * x[k];
+                const double dii = S[(base + i) * DP + base + i];
+                x[i] = (i < c) ? 0.0 : (i == c ? 1.0 / dii : -s / dii);
+            }
+        }
+        __syncthreads();
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < PBW; ++i)
+                if (i >= c)
+                    S[(base + i) * DP + base + c] = x[i];
+        }
+        __syncthreads();
+    }
+    for (int b = PBW; b < wpad; b <<= 1) {
+        // pairs of finished b x b diagonal blocks: W21 = -W22 (L21 W11)
+        const int q4 = b >> 2, tpp = q4 * q4;
+        const int pair = tid / tpp, rem = tid - pair * tpp;
+        const int ti = rem / q4, tj = rem - ti * q4;
+        const int r0 = pair * 2 * b;
+        const bool act = r0 + b < wpad;
+        double acc[4][4] = {};
+        if (act)
+            tile_mm(S, r0 + b, r0, r0, r0, ti, tj, q4, b, acc);            // T = L21 W11
+        __syncthreads();
+        if (act) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    S[(r0 + b + ti + q4 * x) * DP + r0 + tj + q4 * y] = acc[x][y];
+                    acc[x][y] = 0.0;
+                }
+        }
+        __syncthreads();
+        if (act)
+            tile_mm(S, r0 + b, r0 + b, r0 + b, r0, ti, tj, q4, b, acc);    // W22 T
+        __syncthreads();
+        if (act) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+                    S[(r0 + b + ti + q4 * x) * DP + r0 + tj + q4 * y] = -acc[x][y];
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < w * w; idx += DIAG_THREADS) {
+        const int i = idx / w, j = idx - i * w;
         if (op.W)
-            op.W[i * op.ldw + j] = (j < i) ? S[j * DP + i] : (j == i ? dinv[i] : 0.0);
-        // Wt[i][j] = W[j][i] (upper)
+            op.W[i * op.ldw + j] = (j <= i) ? S[i * DP + j] : 0.0;     // W[i][j] (row-major, lower)
         if (op.Wt)
-            op.Wt[i * op.ldwt + j] = (j > i) ? S[i * DP + j] : (j == i ? dinv[i] : 0.0);
+            op.Wt[i * op.ldwt + j] = (j >= i) ? S[j * DP + i] : 0.0;   // Wt[i][j] = W[j][i] (upper)
     }
 }
 
@@ -257,7 +393,7 @@ void launch_diag(const DiagOp* ops, int nops, int* info, void* stream)
         cudaFuncSetAttribute(tri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM);
         configured = true;
     }
-    diag_kernel<<<nops, NB, TILE_SMEM, (cudaStream_t)stream>>>(ops, info);
+    diag_kernel<<<nops, DIAG_THREADS, TILE_SMEM, (cudaStream_t)stream>>>(ops, info);
 }
 
 void launch_tri(const TriOp* ops, int nops, int backward, void* stream)

@@ -16,6 +16,8 @@ This is the sum form of the reference's junction-station carry between phased bl
 junction stations = the stations of the top fronts.
 """
 import ctypes as C
+import os
+import time
 
 import numpy as np
 import torch
@@ -43,6 +45,8 @@ class ShardedAdjustment(engine.Adjustment):
         self.cuda = lib_path is None or "hostsim" not in str(lib_path)
         self._bufs = {}
         self._tops = {}
+        # GADJ_MG_TRACE=1: wall-clock (phase, level, kind, ms) records of every stage and exchange on this rank
+        self._trace = [] if os.environ.get("GADJ_MG_TRACE") else None
 
     # ---- buffers of the library as torch tensors --------------------------------------------
     def _buffer(self, which, dtype=torch.float64):
@@ -97,13 +101,23 @@ class ShardedAdjustment(engine.Adjustment):
         """Run one phase; `exchange(level)` is called at every sync marker.  `before`: the marker precedes the
         level's launches (factor / forward) — purely informational, the library places the markers."""
         cur, lvl = C.c_int64(0), C.c_int32(-1)
+        trace = self._trace
         while True:
+            t0 = time.perf_counter() if trace is not None else 0.0
             self._check(self.L.gadj_stage_run(self.h, phase, C.byref(cur), C.byref(lvl)))
             if lvl.value < 0:
+                if trace is not None:
+                    self._lib_sync()
+                    trace.append((phase, -1, "compute", (time.perf_counter() - t0) * 1e3))
                 break
             self._lib_sync()
+            t1 = time.perf_counter() if trace is not None else 0.0
             exchange(lvl.value)
             self._torch_sync()
+            if trace is not None:
+                t2 = time.perf_counter()
+                trace.append((phase, lvl.value, "compute", (t1 - t0) * 1e3))
+                trace.append((phase, lvl.value, "exchange", (t2 - t1) * 1e3))
 
     def _reduce_panels(self, level):
         panels = self._buffer(BUF_PANELS)

@@ -127,7 +127,7 @@ def scalar_measurements(stn, truth, kind, count, rng, noise=True):
             return _scalar(kind, s1, None, T.h[s1] - T.N[s1], 0.01 * ones, rng, nstn=1, noise=noise)
         if kind == "R":
             return _scalar(kind, s1, None, T.h[s1], 0.01 * ones, rng, nstn=1, noise=noise)
-        sig = 0.02 * SEC * ones      # ~0.6 m on the ground
+        sig = 0.3 * SEC * ones       # astronomic / geodetic positions: ~0.3 arc seconds (~10 m on the ground)
         if kind == "P":
             return _scalar(kind, s1, None, T.lat[s1], sig, rng, nstn=1, noise=noise)
         if kind == "Q":
