@@ -207,12 +207,12 @@ struct gadj_ctx {
     DevArray<double> d_cvinv, d_row_l, d_row_a, d_row_t;
     DevArray<float> d_geoid;
     DevArray<uint64_t> d_diag_dest, d_off_dest;
-    DevArray<double> d_est, d_est0, d_llh, d_llh0, d_cblock, d_ndiag, d_noff, d_w, d_dscale, d_panels, d_pool, d_x, d_corr, d_vcvd,
+    DevArray<double> d_est, d_est0, d_llh, d_llh0, d_cblock, d_ndiag, d_noff, d_w, d_dscale, d_panels, d_pool, d_wbuf, d_x, d_y, d_corr, d_vcvd,
         d_vcvo, d_sums;
     DevArray<int32_t> d_rowmap, d_rowidx, d_info;
     DevArray<GemmOp> d_gemm;
     DevArray<DiagOp> d_diag;
-    DevArray<TriOp> d_tri;
+    DevArray<TrimvOp> d_tri;
     DevArray<GemvOp> d_gemv;
     DevArray<TransposeOp> d_tr;
     DevArray<GatherOp> d_gather;
@@ -276,10 +276,8 @@ void run_one(gadj_ctx* c, const Launch& L)
             launch_diag(c->d_diag.p + L.op_begin, L.op_count, c->d_info.p, st);
             break;
         case L_TRI_FWD:
-            launch_tri(c->d_tri.p + L.op_begin, L.op_count, 0, st);
-            break;
         case L_TRI_BWD:
-            launch_tri(c->d_tri.p + L.op_begin, L.op_count, 1, st);
+            launch_trimv(c->d_tri.p + L.op_begin, L.op_count, st);
             break;
         case L_GEMV_FWD:
             launch_gemv(c->d_gemv.p + L.op_begin, L.op_count, c->d_x.p, c->d_x.p, 0, st);
@@ -1030,6 +1028,8 @@ int gadj_prepare(gadj_ctx* c)
     ok &= c->d_w.resize(3 * (size_t)c->nstn);
     ok &= c->d_dscale.resize(3 * (size_t)c->nstn);
     ok &= c->d_x.resize(3 * (size_t)c->nstn);
+    ok &= c->d_y.resize(3 * (size_t)c->nstn);
+    ok &= c->d_wbuf.resize(wbuf_doubles(S));
     ok &= c->d_corr.resize(3 * (size_t)c->nstn + 8);
     ok &= c->d_vcvd.resize(9 * (size_t)c->nstn);
     ok &= c->d_vcvo.resize(9 * (size_t)c->nedge);
@@ -1077,6 +1077,8 @@ int gadj_prepare(gadj_ctx* c)
     pb.pool = c->d_pool.p;
     pb.pool_doubles = pool;
     pb.x = c->d_x.p;
+    pb.y = c->d_y.p;
+    pb.wbuf = c->d_wbuf.p;
     pb.rowmap = c->d_rowmap.p;
     pb.rowidx = c->d_rowidx.p;
     e = build_plan(S, pb, c->plan);
@@ -1094,7 +1096,7 @@ int gadj_prepare(gadj_ctx* c)
     e = dev::sync();
     if (!e.empty())
         return c->fail(e);
-    c->device_bytes = c->d_msr.bytes() + c->d_panels.bytes() + c->d_pool.bytes() + c->d_noff.bytes() + c->d_ndiag.bytes() +
+    c->device_bytes = c->d_msr.bytes() + c->d_panels.bytes() + c->d_pool.bytes() + c->d_wbuf.bytes() + c->d_noff.bytes() + c->d_ndiag.bytes() +
                       c->d_gemm.bytes() + c->d_gemv.bytes() + c->d_vcvo.bytes() + c->d_vcvd.bytes();
     c->h_corr.assign(3 * (size_t)c->nstn, 0.0);
     c->prepared = true;

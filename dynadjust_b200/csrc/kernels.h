@@ -65,13 +65,17 @@ struct DiagOp {
     int32_t pad;
 };
 
-// x_j <- L_jj^-1 x_j (forward) or L_jj^-T x_j (backward) on one pivot tile
-struct TriOp {
-    const double* D;
-    double* x;
-    int64_t ldd;
-    int32_t w;
-    int32_t pad;
+// y[row0 + i] = sum_c A[i][c] * x[c]  for one chunk of rows of a k x k triangular matrix (W = L11^-1 in the forward
+// substitution, Wt = W^T in the backward one).  Only the triangle is read: c <= row (lower) or c >= row (upper) —
+// the other half of the buffer holds scratch.
+struct TrimvOp {
+    const double* A;         // first row of the chunk (row-major, pitch ld)
+    const double* x;         // the front's slice of the input vector (k entries)
+    double* y;               // the front's slice of the output vector (k entries)
+    int64_t ld;
+    int32_t row0, nrows;     // rows [row0, row0 + nrows) of the front
+    int32_t k;
+    int32_t upper;           // 0: lower triangular, 1: upper triangular
 };
 
 // forward : x[rowidx[i]] -= sum_c P[i][c] * xj[c]         for i in [0, nrows)
@@ -110,7 +114,7 @@ struct GatherOp {
 // All pointers are device pointers; `stream` is the backend's stream handle.
 void launch_gemm(const GemmOp* ops, int nops, int total_tiles, void* stream);
 void launch_diag(const DiagOp* ops, int nops, int* info, void* stream);
-void launch_tri(const TriOp* ops, int nops, int backward, void* stream);
+void launch_trimv(const TrimvOp* ops, int nops, void* stream);
 void launch_gemv(const GemvOp* ops, int nops, const double* x_ro, double* x, int backward, void* stream);
 // grid_x: CTAs per op (each op loops over its tiles); the planner passes min(cap, largest tile count)
 void launch_transpose(const TransposeOp* ops, int nops, int grid_x, void* stream);

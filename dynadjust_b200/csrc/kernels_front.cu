@@ -1,5 +1,5 @@
 // kernels_front.cu — per-front helper kernels around the tile GEMM:
-//   pivot-tile Cholesky + triangular inverse, triangular tile solves, panel GEMV updates for the
+//   pivot-tile Cholesky + triangular inverse, triangular matrix-vector products, panel GEMV updates for the
 //   forward/backward substitution, transposes and the selected-inverse gather.
 #include <cuda_runtime.h>
 
@@ -218,44 +218,43 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) diag_kernel(const DiagOp* __r
     }
 }
 
-// ---- triangular solve with one pivot tile ---------------------------------------------
-__global__ void __launch_bounds__(NB, 1) tri_kernel(const TriOp* __restrict__ ops, int backward)
+// ---- triangular matrix-vector product with the inverse pivot block ------------------------------
+// y[row0 + i] = sum_c A[i][c] x[c] over the triangle only (lower: c <= row, upper: c >= row).  One CTA per chunk of
+// up to 64 rows; each warp owns groups of 4 rows and walks the columns with coalesced 32-wide strides, so one load
+// of x feeds four rows.  HBM-bound: the triangle of W / Wt is read once per substitution.
+constexpr int TRIMV_THREADS = 256;
+__global__ void __launch_bounds__(TRIMV_THREADS) trimv_kernel(const TrimvOp* __restrict__ ops)
 {
-    extern __shared__ double S[];
-    __shared__ double xs[NB];
-    const TriOp op = ops[blockIdx.x];
-    const int w = op.w, tid = threadIdx.x;
-    const int64_t ld = op.ldd;
-    for (int idx = tid; idx < w * w; idx += NB) {
-        int i = idx / w, j = idx - i * w;
-        if (j <= i)
-            S[i * DP + j] = op.D[i * ld + j];
-    }
-    double x = tid < w ? op.x[tid] : 0.0;
-    __syncthreads();
-    if (!backward) {
-        for (int j = 0; j < w; ++j) {
-            if (tid == j) {
-                x = x / S[j * DP + j];
-                xs[j] = x;
+    const TrimvOp op = ops[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double* __restrict__ x = op.x;
+    for (int g0 = 4 * warp; g0 < op.nrows; g0 += 4 * (TRIMV_THREADS / 32)) {
+        const int gr = op.row0 + g0;                       // first row (front numbering) of the group
+        const int nr = op.nrows - g0 < 4 ? op.nrows - g0 : 4;
+        const int c_lo = op.upper ? gr : 0;
+        const int c_hi = op.upper ? op.k : gr + nr;        // exclusive
+        const double* __restrict__ a0 = op.A + (int64_t)g0 * op.ld;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int c = (c_lo & ~31) + lane; c < c_hi; c += 32) {
+            if (c < c_lo)
+                continue;
+            const double xv = x[c];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const bool in = r < nr && (op.upper ? c >= gr + r : c <= gr + r);
+                if (in)
+                    acc[r] += a0[(int64_t)r * op.ld + c] * xv;
             }
-            __syncthreads();
-            if (tid > j && tid < w)
-                x -= S[tid * DP + j] * xs[j];
         }
-    } else {
-        for (int j = w - 1; j >= 0; --j) {
-            if (tid == j) {
-                x = x / S[j * DP + j];
-                xs[j] = x;
-            }
-            __syncthreads();
-            if (tid < j)
-                x -= S[j * DP + tid] * xs[j];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
         }
+        if (lane < nr)
+            op.y[gr + lane] = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
     }
-    if (tid < w)
-        op.x[tid] = x;
 }
 
 // ---- panel GEMV updates of the substitution ---------------------------------------------
@@ -390,23 +389,16 @@ void launch_diag(const DiagOp* ops, int nops, int* info, void* stream)
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM);
-        cudaFuncSetAttribute(tri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM);
         configured = true;
     }
     diag_kernel<<<nops, DIAG_THREADS, TILE_SMEM, (cudaStream_t)stream>>>(ops, info);
 }
 
-void launch_tri(const TriOp* ops, int nops, int backward, void* stream)
+void launch_trimv(const TrimvOp* ops, int nops, void* stream)
 {
     if (nops <= 0)
         return;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM);
-        cudaFuncSetAttribute(tri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM);
-        configured = true;
-    }
-    tri_kernel<<<nops, NB, TILE_SMEM, (cudaStream_t)stream>>>(ops, backward);
+    trimv_kernel<<<nops, TRIMV_THREADS, 0, (cudaStream_t)stream>>>(ops);
 }
 
 void launch_gemv(const GemvOp* ops, int nops, const double* x_ro, double* x, int backward, void* stream)

@@ -8,6 +8,9 @@
 // -L21 L21^T scattered into the ancestors' panels; dpotri (MATC:984) becomes the
 // top-down selected inverse Z11 = W^T W + Y^T Z22 Y, Z21 = -Z22 Y with
 // W = L11^-1, Y = L21 W  (the reverse/combine passes, ADJ:3461-3590).
+// W (and its transpose) of every front is formed once, right after the front's pivot block is factorised, and
+// kept: the substitutions multiply by it (two launches per tree level and direction instead of two per
+// pivot tile) and the selected inverse starts from it.
 #include "plan.h"
 
 #include <algorithm>
@@ -22,27 +25,16 @@ inline uint32_t even(uint32_t n) { return n + (n & 1u); }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 struct SelinvWs {
-    size_t W, Wt, wt_tiles, Tt, G, Yt, Z21t, total;
-    uint32_t ldw, ldt, ldg, ldr, ntiles;
+    size_t G, Yt, Z21t, total;
+    uint32_t ldg, ldr;
 };
 
 SelinvWs ws_layout(const Front& f)
 {
     SelinvWs w{};
-    w.ldw = even(f.k);
-    w.ldt = even(f.k);
     w.ldg = even(f.r);
     w.ldr = even(f.r);
-    w.ntiles = (uint32_t)cdiv((int)f.k, NB);
     size_t o = 0;
-    w.W = o;
-    o += al16((size_t)f.k * w.ldw);
-    w.Wt = o;
-    o += al16((size_t)f.k * w.ldw);
-    w.wt_tiles = o;
-    o += al16((size_t)w.ntiles * NB * NB);
-    w.Tt = o;
-    o += al16((size_t)NB * w.ldt);
     if (f.r > 0) {
         w.G = o;
         o += al16((size_t)f.r * w.ldg);
@@ -55,15 +47,32 @@ SelinvWs ws_layout(const Front& f)
     return w;
 }
 
+// persistent inverse pivot blocks: W then Wt, each k x ldw row-major
+inline uint32_t ldw_of(const Front& f) { return even(f.k); }
+inline size_t wblock(const Front& f) { return al16((size_t)f.k * ldw_of(f)); }
+
 struct Builder {
     const Symbolic& s;
     const PlanBuffers& b;
     Plan& p;
     std::string err;
 
-    Builder(const Symbolic& S, const PlanBuffers& B, Plan& P) : s(S), b(B), p(P) {}
+    std::vector<size_t> woff;   // per front: offset of its W block in b.wbuf (Wt follows at + wblock)
+
+    Builder(const Symbolic& S, const PlanBuffers& B, Plan& P) : s(S), b(B), p(P)
+    {
+        woff.assign(s.fronts.size(), 0);
+        size_t o = 0;
+        for (size_t f = 0; f < s.fronts.size(); ++f)
+            if (s.fronts[f].owner == s.rank) {
+                woff[f] = o;
+                o += 2 * wblock(s.fronts[f]);
+            }
+    }
 
     double* panel(const Front& f) const { return b.panels + f.panel_off; }
+    double* Wof(uint32_t fi) const { return b.wbuf + woff[fi]; }
+    double* Wtof(uint32_t fi) const { return b.wbuf + woff[fi] + wblock(s.fronts[fi]); }
 
     // fronts of a level that this rank factorises
     std::vector<uint32_t> owned(size_t lv) const
@@ -199,6 +208,48 @@ struct Builder {
         return 0;
     }
 
+    // W = L11^-1 and Wt = W^T by block doubling, from the pivot-tile inverses the factorisation left on the
+    // diagonal: pairs of finished bw x bw diagonal blocks (the second one may be shorter) are joined,
+    // W21 = -W22 (L21 W11),  as  Tt = Wt11 L21^T  (parked in the unused upper part of W),  W21 = -W22 Tt^T,
+    // Wt12 = W21^T.  Every pair of every front of the level is in the same three launches: 3 log2(k / 128)
+    // launches per level.
+    void build_trtri(const std::vector<uint32_t>& fl, std::vector<Launch>& out, int level)
+    {
+        std::vector<TransposeOp> trb;
+        int maxk = 0;
+        for (uint32_t fi : fl)
+            maxk = std::max<int>(maxk, (int)s.fronts[fi].k);
+        for (int bw = NB; bw < maxk; bw <<= 1) {
+            std::vector<GemmOp> ga, gbb;
+            for (uint32_t fi : fl) {
+                const Front& f = s.fronts[fi];
+                const uint32_t ldw = ldw_of(f);
+                double* W = Wof(fi);
+                double* Wt = Wtof(fi);
+                for (int r0 = 0; r0 + bw < (int)f.k; r0 += 2 * bw) {
+                    const int r1 = r0 + bw;
+                    const int rows2 = std::min<int>(bw, (int)f.k - r1);
+                    double* Tt = W + (size_t)r0 * ldw + r1;                    // bw x rows2
+                    double* W21 = W + (size_t)r1 * ldw + r0;                   // rows2 x bw
+                    add_gemm(ga, Wt + (size_t)r0 * ldw + r0, ldw, panel(f) + (size_t)r1 * f.ldk + r0, f.ldk, Tt, ldw, bw, rows2,
+                             bw, GEMM_KLO_ROW);
+                    add_gemm(gbb, W + (size_t)r1 * ldw + r1, ldw, Tt, ldw, W21, ldw, rows2, bw, rows2, GEMM_NEG | GEMM_KHI_ROW);
+                    TransposeOp t{};
+                    t.src = W21;
+                    t.dst = Wt + (size_t)r0 * ldw + r1;
+                    t.lds = ldw;
+                    t.ldd = ldw;
+                    t.rows = rows2;
+                    t.cols = bw;
+                    trb.push_back(t);
+                }
+            }
+            flush_gemm(ga, out, level, T_TRTRI_A);
+            flush_gemm(gbb, out, level, T_TRTRI_B);
+            flush_simple(trb, p.transpose, L_TRANSPOSE, out, level);
+        }
+    }
+
     // ---- numeric factorisation ------------------------------------------------
     void build_factor()
     {
@@ -241,8 +292,9 @@ struct Builder {
                     d.ldd = f.ldk;
                     d.w = std::min<int>(NB, (int)f.k - jb);
                     d.factor = 1;
-                    d.W = b.pool + i * (size_t)NB * NB;
-                    d.ldw = NB;
+                    d.ldw = d.ldwt = ldw_of(f);
+                    d.W = Wof(fl[i]) + (size_t)jb * d.ldw + jb;
+                    d.Wt = Wtof(fl[i]) + (size_t)jb * d.ldw + jb;
                     d.front = (int32_t)fl[i];
                     db.push_back(d);
                 }
@@ -254,7 +306,8 @@ struct Builder {
                         continue;
                     int w = std::min<int>(NB, (int)f.k - jb);
                     double* A = panel(f) + (size_t)(jb + w) * f.ldk + jb;
-                    add_gemm(gb, A, f.ldk, b.pool + i * (size_t)NB * NB, NB, A, f.ldk, (int)f.m - (jb + w), w, w, 0);
+                    add_gemm(gb, A, f.ldk, Wof(fl[i]) + (size_t)jb * ldw_of(f) + jb, ldw_of(f), A, f.ldk, (int)f.m - (jb + w), w, w,
+                             0);
                 }
                 flush_gemm(gb, p.factor, (int)lv, T_PANEL);
                 if (left)
@@ -273,6 +326,7 @@ struct Builder {
                 }
                 flush_gemm(gb, p.factor, (int)lv, T_RIGHT_UPDATE);
             }
+            build_trtri(fl, p.factor, (int)lv);
             // Schur updates scattered into the ancestors' panels
             for (uint32_t fi : fl) {
                 const Front& f = s.fronts[fi];
@@ -292,79 +346,64 @@ struct Builder {
     }
 
     // ---- triangular solves ----------------------------------------------------
-    void build_solves()
+    // x holds the right-hand side and, at the end, the solution; y the forward-substituted vector.
+    //   forward  (bottom-up):  y1 = W x1;            x[boundary rows] -= L21 y1
+    //   backward (top-down):   y1 -= L21^T x[boundary rows];   x1 = Wt y1
+    void add_trimv(std::vector<TrimvOp>& tb, uint32_t fi, bool upper)
+    {
+        const int ROWS = 64;
+        const Front& f = s.fronts[fi];
+        const uint32_t ldw = ldw_of(f);
+        const double* A = upper ? Wtof(fi) : Wof(fi);
+        for (int r0 = 0; r0 < (int)f.k; r0 += ROWS) {
+            TrimvOp t{};
+            t.A = A + (size_t)r0 * ldw;
+            t.ld = ldw;
+            t.row0 = r0;
+            t.nrows = std::min<int>(ROWS, (int)f.k - r0);
+            t.k = (int32_t)f.k;
+            t.upper = upper ? 1 : 0;
+            t.x = (upper ? b.y : b.x) + 3 * (size_t)f.own_begin;
+            t.y = (upper ? b.x : b.y) + 3 * (size_t)f.own_begin;
+            tb.push_back(t);
+        }
+    }
+    void add_gemv(std::vector<GemvOp>& vb, uint32_t fi)
     {
         const int CHUNK = 256;
-        std::vector<TriOp> tb;
+        const Front& f = s.fronts[fi];
+        for (int jb = 0; jb < (int)f.k; jb += NB)
+            for (int r0 = (int)f.k; r0 < (int)f.m; r0 += CHUNK) {
+                GemvOp g{};
+                g.P = panel(f) + (size_t)r0 * f.ldk + jb;
+                g.rowidx = b.rowidx + p.rowidx_off[fi] + r0;
+                g.xj = b.y + 3 * (size_t)f.own_begin + jb;
+                g.ld = f.ldk;
+                g.nrows = std::min<int>(CHUNK, (int)f.m - r0);
+                g.w = std::min<int>(NB, (int)f.k - jb);
+                vb.push_back(g);
+            }
+    }
+    void build_solves()
+    {
+        std::vector<TrimvOp> tb;
         std::vector<GemvOp> vb;
         for (size_t lv = 0; lv < s.levels.size(); ++lv) {
-            const std::vector<uint32_t> fl = owned(lv);
             add_sync(p.fwd, lv);      // right-hand-side contributions to this level's top fronts are summed first
-            int nsteps = 0;
-            for (uint32_t f : fl)
-                nsteps = std::max(nsteps, cdiv((int)s.fronts[f].k, NB));
-            for (int j = 0; j < nsteps; ++j) {
-                const int jb = j * NB;
-                for (uint32_t fi : fl) {
-                    const Front& f = s.fronts[fi];
-                    if (jb >= (int)f.k)
-                        continue;
-                    int w = std::min<int>(NB, (int)f.k - jb);
-                    TriOp t{};
-                    t.D = panel(f) + (size_t)jb * f.ldk + jb;
-                    t.ldd = f.ldk;
-                    t.w = w;
-                    t.x = b.x + 3 * (size_t)f.own_begin + jb;
-                    tb.push_back(t);
-                    for (int r0 = jb + w; r0 < (int)f.m; r0 += CHUNK) {
-                        GemvOp g{};
-                        g.P = panel(f) + (size_t)r0 * f.ldk + jb;
-                        g.rowidx = b.rowidx + p.rowidx_off[fi] + r0;
-                        g.xj = t.x;
-                        g.ld = f.ldk;
-                        g.nrows = std::min<int>(CHUNK, (int)f.m - r0);
-                        g.w = w;
-                        vb.push_back(g);
-                    }
-                }
-                flush_simple(tb, p.tri, L_TRI_FWD, p.fwd, (int)lv);
-                flush_simple(vb, p.gemv, L_GEMV_FWD, p.fwd, (int)lv);
+            for (uint32_t fi : owned(lv)) {
+                add_trimv(tb, fi, false);
+                add_gemv(vb, fi);
             }
+            flush_simple(tb, p.tri, L_TRI_FWD, p.fwd, (int)lv);
+            flush_simple(vb, p.gemv, L_GEMV_FWD, p.fwd, (int)lv);
         }
         for (size_t lvi = s.levels.size(); lvi-- > 0;) {
-            const std::vector<uint32_t> fl = owned(lvi);
-            int nsteps = 0;
-            for (uint32_t f : fl)
-                nsteps = std::max(nsteps, cdiv((int)s.fronts[f].k, NB));
-            for (int st = 0; st < nsteps; ++st) {
-                for (uint32_t fi : fl) {
-                    const Front& f = s.fronts[fi];
-                    int nt = cdiv((int)f.k, NB);
-                    int j = nt - 1 - st;
-                    if (j < 0)
-                        continue;
-                    int jb = j * NB;
-                    int w = std::min<int>(NB, (int)f.k - jb);
-                    TriOp t{};
-                    t.D = panel(f) + (size_t)jb * f.ldk + jb;
-                    t.ldd = f.ldk;
-                    t.w = w;
-                    t.x = b.x + 3 * (size_t)f.own_begin + jb;
-                    tb.push_back(t);
-                    for (int r0 = jb + w; r0 < (int)f.m; r0 += CHUNK) {
-                        GemvOp g{};
-                        g.P = panel(f) + (size_t)r0 * f.ldk + jb;
-                        g.rowidx = b.rowidx + p.rowidx_off[fi] + r0;
-                        g.xj = t.x;
-                        g.ld = f.ldk;
-                        g.nrows = std::min<int>(CHUNK, (int)f.m - r0);
-                        g.w = w;
-                        vb.push_back(g);
-                    }
-                }
-                flush_simple(vb, p.gemv, L_GEMV_BWD, p.bwd, (int)lvi);
-                flush_simple(tb, p.tri, L_TRI_BWD, p.bwd, (int)lvi);
+            for (uint32_t fi : owned(lvi)) {
+                add_gemv(vb, fi);
+                add_trimv(tb, fi, true);
             }
+            flush_simple(vb, p.gemv, L_GEMV_BWD, p.bwd, (int)lvi);
+            flush_simple(tb, p.tri, L_TRI_BWD, p.bwd, (int)lvi);
             add_sync(p.bwd, lvi);     // the solved top fronts of this level are broadcast to every rank
         }
     }
@@ -373,68 +412,15 @@ struct Builder {
     void build_selinv_chunk(const std::vector<uint32_t>& chunk, const std::vector<size_t>& base, size_t used, int level)
     {
         std::vector<GemmOp> gb;
-        std::vector<DiagOp> db;
         std::vector<TransposeOp> trb;
         std::vector<GatherOp> gab;
         // no clearing of the workspace: every tile that is read has been written before (the K-range
         // flags keep the triangular products inside the written tiles)
         (void)used;
-        int maxtiles = 0;
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];
             SelinvWs w = ws_layout(f);
             double* ws = b.pool + base[i];
-            maxtiles = std::max<int>(maxtiles, (int)w.ntiles);
-            for (uint32_t j = 0; j < w.ntiles; ++j) {
-                int jb = (int)j * NB;
-                DiagOp d{};
-                d.D = panel(f) + (size_t)jb * f.ldk + jb;
-                d.ldd = f.ldk;
-                d.w = std::min<int>(NB, (int)f.k - jb);
-                d.factor = 0;
-                d.W = ws + w.W + (size_t)jb * w.ldw + jb;
-                d.ldw = w.ldw;
-                d.Wt = ws + w.wt_tiles + (size_t)j * NB * NB;
-                d.ldwt = NB;
-                d.front = (int32_t)chunk[i];
-                db.push_back(d);
-            }
-        }
-        flush_diag(db, p.selinv, level);
-        // blocked inverse of the lower factor, block columns right to left
-        for (int st = 0; st + 1 < maxtiles; ++st) {
-            std::vector<GemmOp> ga, gbb;
-            for (size_t i = 0; i < chunk.size(); ++i) {
-                const Front& f = s.fronts[chunk[i]];
-                SelinvWs w = ws_layout(f);
-                double* ws = b.pool + base[i];
-                int j = (int)w.ntiles - 2 - st;
-                if (j < 0)
-                    continue;
-                int jb = j * NB, wj = NB;  // only the last tile can be narrower
-                int below = (int)f.k - (jb + wj);
-                // Tt = Wt_jj * L[below, jb:jb+wj]^T
-                add_gemm(ga, ws + w.wt_tiles + (size_t)j * NB * NB, NB, panel(f) + (size_t)(jb + wj) * f.ldk + jb, f.ldk,
-                         ws + w.Tt, w.ldt, wj, below, wj, 0);
-                // W[below, jb:jb+wj] = -W[below, below] * Tt^T
-                add_gemm(gbb, ws + w.W + (size_t)(jb + wj) * w.ldw + (jb + wj), w.ldw, ws + w.Tt, w.ldt,
-                         ws + w.W + (size_t)(jb + wj) * w.ldw + jb, w.ldw, below, wj, below, GEMM_NEG | GEMM_KHI_ROW);
-            }
-            flush_gemm(ga, p.selinv, level, T_TRTRI_A);
-            flush_gemm(gbb, p.selinv, level, T_TRTRI_B);
-        }
-        for (size_t i = 0; i < chunk.size(); ++i) {
-            const Front& f = s.fronts[chunk[i]];
-            SelinvWs w = ws_layout(f);
-            double* ws = b.pool + base[i];
-            TransposeOp t{};
-            t.src = ws + w.W;
-            t.dst = ws + w.Wt;
-            t.lds = w.ldw;
-            t.ldd = w.ldw;
-            t.rows = (int32_t)f.k;
-            t.cols = (int32_t)f.k;
-            trb.push_back(t);
             for (uint32_t ti = 0; ti < f.tgt_count; ++ti) {
                 const Target& tg = s.targets[f.tgt_begin + ti];
                 const Front& an = s.fronts[tg.anc];
@@ -451,7 +437,6 @@ struct Builder {
                 gab.push_back(g);
             }
         }
-        flush_simple(trb, p.transpose, L_TRANSPOSE, p.selinv, level);
         flush_simple(gab, p.gather, L_GATHER, p.selinv, level);
         // Yt = Wt * L21^T
         for (size_t i = 0; i < chunk.size(); ++i) {
@@ -460,7 +445,7 @@ struct Builder {
                 continue;
             SelinvWs w = ws_layout(f);
             double* ws = b.pool + base[i];
-            add_gemm(gb, ws + w.Wt, w.ldw, panel(f) + (size_t)f.k * f.ldk, f.ldk, ws + w.Yt, w.ldr, (int)f.k, (int)f.r,
+            add_gemm(gb, Wtof(chunk[i]), ldw_of(f), panel(f) + (size_t)f.k * f.ldk, f.ldk, ws + w.Yt, w.ldr, (int)f.k, (int)f.r,
                      (int)f.k, GEMM_KLO_ROW);
         }
         flush_gemm(gb, p.selinv, level, T_YT);
@@ -494,9 +479,7 @@ struct Builder {
         // Z11 = Wt Wt^T   (overwrites L11, lower triangle)
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];
-            SelinvWs w = ws_layout(f);
-            double* ws = b.pool + base[i];
-            add_gemm(gb, ws + w.Wt, w.ldw, ws + w.Wt, w.ldw, panel(f), f.ldk, (int)f.k, (int)f.k, (int)f.k,
+            add_gemm(gb, Wtof(chunk[i]), ldw_of(f), Wtof(chunk[i]), ldw_of(f), panel(f), f.ldk, (int)f.k, (int)f.k, (int)f.k,
                      GEMM_LOWER | GEMM_KLO_MAX);
         }
         flush_gemm(gb, p.selinv, level, T_Z11_WW);
@@ -551,17 +534,20 @@ size_t selinv_workspace(const Front& f) { return ws_layout(f).total; }
 
 size_t min_pool_doubles(const Symbolic& s)
 {
-    size_t need = 0, width = 0;
+    size_t need = 0;
     for (const Front& f : s.fronts)
         if (f.owner == s.rank)
             need = std::max(need, ws_layout(f).total);
-    for (auto& lv : s.levels) {
-        size_t n = 0;
-        for (uint32_t f : lv)
-            n += s.fronts[f].owner == s.rank;
-        width = std::max(width, n);
-    }
-    return std::max<size_t>(16, std::max(need, width * (size_t)NB * NB));
+    return std::max<size_t>(16, need);
+}
+
+size_t wbuf_doubles(const Symbolic& s)
+{
+    size_t o = 0;
+    for (const Front& f : s.fronts)
+        if (f.owner == s.rank)
+            o += 2 * wblock(f);
+    return std::max<size_t>(16, o);
 }
 
 size_t ideal_pool_doubles(const Symbolic& s)

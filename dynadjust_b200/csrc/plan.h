@@ -41,7 +41,9 @@ struct PlanBuffers {
     double* panels = nullptr;     // device, Symbolic::panel_doubles
     double* pool = nullptr;       // device workspace pool
     size_t pool_doubles = 0;
-    double* x = nullptr;          // device, 3*nstn, elimination order
+    double* x = nullptr;          // device, 3*nstn, elimination order: right-hand side, then the solution
+    double* y = nullptr;          // device, 3*nstn: the forward-substituted vector (second vector of the solves)
+    double* wbuf = nullptr;       // device, wbuf_doubles(): W = L11^-1 and Wt = W^T of every front this rank owns
     const int32_t* rowmap = nullptr;  // device copy of Symbolic::rowmap
     const int32_t* rowidx = nullptr;  // device: global unknown index per front row (concatenated, Plan::rowidx_off)
 };
@@ -49,7 +51,7 @@ struct PlanBuffers {
 struct Plan {
     std::vector<GemmOp> gemm;
     std::vector<DiagOp> diag;
-    std::vector<TriOp> tri;
+    std::vector<TrimvOp> tri;
     std::vector<GemvOp> gemv;
     std::vector<TransposeOp> transpose;
     std::vector<GatherOp> gather;
@@ -60,15 +62,17 @@ struct Plan {
     // device copies of the op arrays (owned by the context)
     GemmOp* d_gemm = nullptr;
     DiagOp* d_diag = nullptr;
-    TriOp* d_tri = nullptr;
+    TrimvOp* d_tri = nullptr;
     GemvOp* d_gemv = nullptr;
     TransposeOp* d_transpose = nullptr;
     GatherOp* d_gather = nullptr;
 };
 
+// doubles needed for the persistent inverse pivot blocks (W and Wt of every owned front)
+size_t wbuf_doubles(const Symbolic& s);
 // per-front selected-inverse workspace need (doubles)
 size_t selinv_workspace(const Front& f);
-// smallest usable pool (doubles): the largest single front + the factorisation's pivot-inverse tiles
+// smallest usable pool (doubles): the largest single front
 size_t min_pool_doubles(const Symbolic& s);
 // pool size that lets every level run as a single chunk
 size_t ideal_pool_doubles(const Symbolic& s);

@@ -102,28 +102,17 @@ void launch_diag(const DiagOp* ops, int nops, int* info, void*)
     }
 }
 
-void launch_tri(const TriOp* ops, int nops, int backward, void*)
+void launch_trimv(const TrimvOp* ops, int nops, void*)
 {
     for (int o = 0; o < nops; ++o) {
-        const TriOp& op = ops[o];
-        const int w = op.w;
-        const double* D = op.D;
-        const int64_t ld = op.ldd;
-        double* x = op.x;
-        if (!backward) {
-            for (int i = 0; i < w; ++i) {
-                double s = x[i];
-                for (int k = 0; k < i; ++k)
-                    s -= D[i * ld + k] * x[k];
-                x[i] = s / D[i * ld + i];
-            }
-        } else {
-            for (int i = w - 1; i >= 0; --i) {
-                double s = x[i];
-                for (int k = i + 1; k < w; ++k)
-                    s -= D[k * ld + i] * x[k];
-                x[i] = s / D[i * ld + i];
-            }
+        const TrimvOp& op = ops[o];
+        for (int i = 0; i < op.nrows; ++i) {
+            const int row = op.row0 + i;
+            const int c_lo = op.upper ? row : 0, c_hi = op.upper ? op.k : row + 1;
+            double s = 0.0;
+            for (int c = c_lo; c < c_hi; ++c)
+                s += op.A[(int64_t)i * op.ld + c] * op.x[c];
+            op.y[row] = s;
         }
     }
 }

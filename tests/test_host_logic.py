@@ -29,6 +29,13 @@ def test_dense_front_matches_oracle(oracle, hostsim_path):
     assert info.nfronts == 1
 
 
+def test_dense_front_block_doubling(oracle, hostsim_path):
+    # k = 750 = 5 full pivot tiles + 110: the triangular inverse joins blocks of 128, 256 and 512 with short
+    # second halves (pairs (4,5), then (0-3, 4-5)) — every shape of the block-doubling step
+    info = parity.check_against_oracle(oracle, hostsim_path, 250, 750, 23, ordering=engine.ORDER_DENSE)
+    assert info.nfronts == 1
+
+
 def test_chain_blocks_match_oracle(oracle, hostsim_path):
     # a .seg-style chain of blocks (phased adjustment) is rigorous: same answer as simultaneous
     info = parity.check_against_oracle(oracle, hostsim_path, 300, 900, 9, blocks=lambda n: parity.chain_blocks(n, 40))
