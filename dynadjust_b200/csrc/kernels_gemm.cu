@@ -226,23 +226,52 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp
     const int64_t ldc = op->ldc;
     const bool lower = (flags & GEMM_LOWER) != 0;
     if (flags & GEMM_SCATTER) {
+        // Scatter through the station-level row map with FP64 RED.ADD.  The accumulators are first parked in the
+        // (now idle) pipeline stages as a 128 x 128 row-major tile, XOR-swizzled in groups of four columns so that
+        // the row-order loads are bank-conflict free; the atomics are then issued row by row with the 32 lanes on
+        // 32 consecutive source columns (consecutive boundary stations are mostly consecutive in the ancestor, so
+        // a warp instruction touches far fewer 32-byte sectors than in fragment order) and the column part of
+        // the map is looked up once per lane instead of once per element.
         const int32_t* __restrict__ rowmap = op->rowmap;
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // every consumer has finished reading the last stages
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int r = row0 + wm + 16 * (i >> 1) + 2 * g + (i & 1);
+            const int rr = wm + 16 * (i >> 1) + 2 * g + (i & 1);
+            const uint32_t rbase = base + (uint32_t)rr * (TILE_N * 8);
+            const int sw = (rr >> 1) & 7;
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const int cg = ((wn + 16 * p) >> 2) + t;            // group of four columns owned by this thread
+                const uint32_t addr = rbase + (uint32_t)((cg ^ sw) << 5);
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(acc[i][2 * p][0]), "d"(acc[i][2 * p + 1][0])
+                             : "memory");
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr + 16), "d"(acc[i][2 * p][1]),
+                             "d"(acc[i][2 * p + 1][1])
+                             : "memory");
+            }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        int64_t dcol[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int c = col0 + 32 * cc + lane;
+            dcol[cc] = c < N ? 3ll * rowmap[c / 3] + c % 3 : -1;
+        }
+        for (int rr = warp; rr < TILE_M; rr += CONSUMER_WARPS) {
+            const int r = row0 + rr;
             if (r >= M)
-                continue;
-            const int64_t dr = 3ll * rowmap[r / 3] + r % 3;
+                break;
+            double* __restrict__ crow = C + (3ll * rowmap[r / 3] + r % 3) * ldc;
+            const uint32_t rbase = base + (uint32_t)rr * (TILE_N * 8);
+            const int sw = (rr >> 1) & 7;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int c = col0 + wn + 16 * (j >> 1) + 2 * (2 * t + e) + (j & 1);
-                    if (c >= N || (lower && r + tri_off < c))
-                        continue;
-                    const int64_t dc = 3ll * rowmap[c / 3] + c % 3;
-                    atomicAdd(C + dr * ldc + dc, alpha * acc[i][j][e]);
-                }
+            for (int cc = 0; cc < 4; ++cc) {
+                const int cl = 32 * cc + lane;
+                if (dcol[cc] < 0 || (lower && r + tri_off < col0 + cl))
+                    continue;
+                const double v = lds_f64(rbase + (uint32_t)((((cl >> 2) ^ sw) << 5) + ((cl & 3) << 3)));
+                atomicAdd(crow + dcol[cc], alpha * v);
+            }
         }
     } else {
         const bool accum = (flags & GEMM_ACCUM) != 0;
