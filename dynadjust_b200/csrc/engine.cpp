@@ -209,8 +209,10 @@ struct gadj_ctx {
     DevArray<uint64_t> d_diag_dest, d_off_dest;
     DevArray<double> d_est, d_est0, d_llh, d_llh0, d_cblock, d_ndiag, d_noff, d_w, d_dscale, d_panels, d_pool, d_wbuf, d_x, d_y, d_corr, d_vcvd,
         d_vcvo, d_sums;
-    DevArray<int32_t> d_rowmap, d_rowidx, d_info;
+    DevArray<int32_t> d_rowmap, d_rowidx, d_info, d_coltgt;
+    DevArray<ScatterTarget> d_tgt;
     DevArray<GemmOp> d_gemm;
+    DevArray<GemmTile> d_tiles;
     DevArray<DiagOp> d_diag;
     DevArray<TrimvOp> d_tri;
     DevArray<GemvOp> d_gemv;
@@ -270,7 +272,7 @@ void run_one(gadj_ctx* c, const Launch& L)
             c->launch_count--;  // a memset, not one of our kernels
         switch (L.kind) {
         case L_GEMM:
-            launch_gemm(c->d_gemm.p + L.op_begin, L.op_count, L.total_tiles, st);
+            launch_gemm(c->d_gemm.p + L.op_begin, L.op_count, c->d_tiles.p + L.tile_begin, L.total_tiles, st);
             break;
         case L_DIAG:
             launch_diag(c->d_diag.p + L.op_begin, L.op_count, c->d_info.p, st);
@@ -1036,6 +1038,8 @@ int gadj_prepare(gadj_ctx* c)
     ok &= c->d_sums.resize(8);
     ok &= c->d_info.resize(4);
     ok &= c->d_rowmap.upload(S.rowmap);
+    ok &= c->d_tgt.resize(S.targets.size());
+    ok &= c->d_coltgt.resize(S.bnd.size());
     ok &= c->d_rowidx.upload(c->plan.rowidx);
     ok &= c->d_panels.resize(S.panel_doubles);
     if (!ok)
@@ -1081,11 +1085,19 @@ int gadj_prepare(gadj_ctx* c)
     pb.wbuf = c->d_wbuf.p;
     pb.rowmap = c->d_rowmap.p;
     pb.rowidx = c->d_rowidx.p;
+    pb.tgt = c->d_tgt.p;
+    pb.coltgt = c->d_coltgt.p;
     e = build_plan(S, pb, c->plan);
     if (!e.empty())
         return c->fail(e);
     ok = true;
     ok &= c->d_gemm.upload(c->plan.gemm);
+    ok &= c->d_tiles.upload(c->plan.tiles);
+    // the scatter tables were allocated before build_plan (the ops point into them): fill in place
+    if (!c->plan.tgt.empty())
+        dev::h2d(c->d_tgt.p, c->plan.tgt.data(), c->plan.tgt.size() * sizeof(ScatterTarget));
+    if (!c->plan.coltgt.empty())
+        dev::h2d(c->d_coltgt.p, c->plan.coltgt.data(), c->plan.coltgt.size() * sizeof(int32_t));
     ok &= c->d_diag.upload(c->plan.diag);
     ok &= c->d_tri.upload(c->plan.tri);
     ok &= c->d_gemv.upload(c->plan.gemv);
@@ -1834,6 +1846,7 @@ int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int
         return c->fail("gadj_test_gemm: M, N, K must be positive and K even");
     DevArray<double> dA, dB, dC;
     DevArray<GemmOp> dop;
+    DevArray<GemmTile> dtl;
     const int ldc = N + (N & 1);
     if (!dA.resize((size_t)M * K) || !dB.resize((size_t)N * K) || !dC.resize((size_t)M * ldc) || !dop.resize(1))
         return c->fail("out of device memory");
@@ -1853,11 +1866,16 @@ int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int
     op.flags = 0;
     op.tiles_m = (M + TILE_M - 1) / TILE_M;
     op.tiles_n = (N + TILE_N - 1) / TILE_N;
-    op.tile_begin = 0;
+    std::vector<GemmTile> tl;
+    for (int tm = 0; tm < op.tiles_m; ++tm)
+        for (int tn = 0; tn < op.tiles_n; ++tn)
+            tl.push_back(GemmTile{0, (uint16_t)tm, (uint16_t)tn});
+    if (!dtl.upload(tl))
+        return c->fail("out of device memory");
     if (!dev::encode_tma_2d(&op.tmA, op.A, M, K, K, TILE_M) || !dev::encode_tma_2d(&op.tmB, op.B, N, K, K, TILE_N))
         return c->fail("tensor-map encoding failed");
     dev::h2d(dop.p, &op, sizeof(op));
-    launch_gemm(dop.p, 1, op.tiles_m * op.tiles_n, dev::stream());
+    launch_gemm(dop.p, 1, dtl.p, (int)tl.size(), dev::stream());
     std::string e = dev::sync();
     if (!e.empty())
         return c->fail(e);
@@ -1865,7 +1883,7 @@ int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int
         reps = 1;
     dev::event_record(c->ev[0]);
     for (int i = 0; i < reps; ++i)
-        launch_gemm(dop.p, 1, op.tiles_m * op.tiles_n, dev::stream());
+        launch_gemm(dop.p, 1, dtl.p, (int)tl.size(), dev::stream());
     dev::event_record(c->ev[1]);
     std::vector<double> hc((size_t)M * ldc);
     dev::d2h(hc.data(), dC.p, dC.bytes());

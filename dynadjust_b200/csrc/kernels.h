@@ -32,8 +32,19 @@ enum GemmFlags : int32_t {
     GEMM_KLO_ROW = 16,  // A is upper triangular (zero for k < row): start the K loop at the tile's first row
     GEMM_KLO_MAX = 32,  // A and B upper triangular: start the K loop at max(first row, first column) of the tile
     GEMM_KHI_ROW = 64,  // A is lower triangular (zero for k > row): end the K loop after the tile's last row
-    GEMM_SCATTER = 8,   // C is the base of a target panel; element (i, j) lands at row 3*rowmap[i/3]+i%3,
-                        // column 3*rowmap[j/3]+j%3 (station-level map), added atomically
+    GEMM_SCATTER = 8,   // Schur update of a front, scattered into its ancestors' panels: column j belongs to boundary
+                        // station j/3, whose owning ancestor is target t = coltgt[j/3]; element (i, j) is added
+                        // atomically to tgt[t].C at row 3*tgt[t].rowmap[i/3 - tgt[t].jb] + i%3 and column
+                        // 3*tgt[t].rowmap[j/3 - tgt[t].jb] + j%3 (station-level maps)
+};
+
+// One update target of a front: the ancestor that owns boundary stations [jb, je) of the front.
+struct ScatterTarget {
+    double* C;               // the ancestor's panel
+    const int32_t* rowmap;   // entry i - jb: local station row in the ancestor of the front's boundary station i >= jb
+    int64_t ldc;
+    int32_t jb;
+    int32_t pad;
 };
 
 // C[M x N] (row-major, ldc)  (+)= alpha * A[M x K] (row-major, lda) * B[N x K]^T (row-major, ldb)
@@ -42,13 +53,22 @@ struct alignas(64) GemmOp {
     const double* A;
     const double* B;
     double* C;
-    const int32_t* rowmap;
+    const int32_t* coltgt;   // GEMM_SCATTER: per boundary station, index into tgt
+    const ScatterTarget* tgt;
     int64_t lda, ldb, ldc;
     int32_t M, N, K;
     int32_t flags;
     int32_t tri_off;
-    int32_t tile_begin;      // first linear tile id of this op inside its launch
+    int32_t pad0;
     int32_t tiles_m, tiles_n;
+};
+
+// One 128 x 128 output tile of one op.  The planner lists only the tiles that hold work (tiles wholly above the
+// diagonal of a lower-only output are left out); a launch is a contiguous run of this list and the persistent
+// GEMM CTAs stride through it.
+struct GemmTile {
+    int32_t op;              // index into the launch's op array
+    uint16_t tm, tn;         // tile row / column inside the op
 };
 
 // One pivot tile (w <= NB).  factor: D (row-major, ldd) <- chol(D) lower, in place.
@@ -112,7 +132,7 @@ struct GatherOp {
 
 // ---- launches -----------------------------------------------------------------
 // All pointers are device pointers; `stream` is the backend's stream handle.
-void launch_gemm(const GemmOp* ops, int nops, int total_tiles, void* stream);
+void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, void* stream);
 void launch_diag(const DiagOp* ops, int nops, int* info, void* stream);
 void launch_trimv(const TrimvOp* ops, int nops, void* stream);
 void launch_gemv(const GemvOp* ops, int nops, const double* x_ro, double* x, int backward, void* stream);

@@ -80,33 +80,9 @@ __device__ __forceinline__ double lds_f64(uint32_t addr)
     return v;
 }
 
-// LOADER 0: TMA producer warp + mbarrier ring (the product path).
-// LOADER 1: debug aid (GADJ_GEMM_LOADER=ldg) — the consumers fill one stage themselves with plain loads
-//           into the same swizzled layout; isolates tensor-map problems from fragment-layout problems.
-template <int LOADER>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp* __restrict__ ops, int nops)
+// K range (in 16-deep steps) of the tile at (row0, col0): triangular operands carry explicit zeros outside it
+__device__ __forceinline__ void tile_k_range(int flags, int row0, int col0, int K, int& kc0, int& nk)
 {
-    extern __shared__ uint8_t smem_raw[];
-    const int tile = blockIdx.x;
-    // locate the op that owns this tile
-    int lo = 0, hi = nops - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (ops[mid].tile_begin <= tile)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
-    const GemmOp* op = ops + lo;
-    const int local = tile - op->tile_begin;
-    const int tiles_n = op->tiles_n;
-    const int tm = local / tiles_n, tn = local - tm * tiles_n;
-    const int row0 = tm * TILE_M, col0 = tn * TILE_N;
-    const int M = op->M, N = op->N, K = op->K;
-    const int flags = op->flags, tri_off = op->tri_off;
-    if ((flags & GEMM_LOWER) && row0 + (TILE_M - 1) + tri_off < col0)
-        return;  // the whole tile lies above the diagonal
-    // K range of this tile (triangular operands carry explicit zeros outside it)
     int k_lo = 0, k_hi = K;
     if (flags & GEMM_KLO_ROW)
         k_lo = row0;
@@ -114,12 +90,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp
         k_lo = row0 > col0 ? row0 : col0;
     if (flags & GEMM_KHI_ROW)
         k_hi = (row0 + TILE_M < K) ? row0 + TILE_M : K;
-    const int kc0 = k_lo / TILE_K;
-    const int nk = k_hi > k_lo ? (k_hi + TILE_K - 1) / TILE_K - kc0 : 0;
+    kc0 = k_lo / TILE_K;
+    nk = k_hi > k_lo ? (k_hi + TILE_K - 1) / TILE_K - kc0 : 0;
+}
 
+// Persistent CTAs: the grid is one CTA per SM (or fewer), each CTA strides through the launch's tile list.  The
+// mbarrier ring runs on across tiles, so while the consumer warps store one tile the producer warp is already
+// fetching the first stages of the next one; the per-tile cost is the epilogue, not a CTA launch + pipeline fill.
+// LOADER 0: TMA producer warp + mbarrier ring (the product path).
+// LOADER 1: debug aid (GADJ_GEMM_LOADER=ldg) — the consumers fill one stage themselves with plain loads
+//           into the same swizzled layout; isolates tensor-map problems from fragment-layout problems.
+template <int LOADER>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    gemm_tile_kernel(const GemmOp* __restrict__ ops, const GemmTile* __restrict__ tiles, int ntiles)
+{
+    extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_full = base + STAGES * STAGE_BYTES;
     const uint32_t bar_empty = bar_full + 8 * STAGES;
+    const uint32_t bar_tile = bar_empty + 8 * STAGES;   // scatter tiles: the stages double as the epilogue's staging buffer
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (LOADER == 0 && threadIdx.x == 0) {
@@ -127,6 +116,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, CONSUMER_WARPS);
         }
+        mbar_init(bar_tile, CONSUMER_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -134,18 +124,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp
     if (warp == CONSUMER_WARPS) {
         // ---- TMA producer -------------------------------------------------------
         if (LOADER == 0 && lane == 0) {
-            const void* tmA = &op->tmA;
-            const void* tmB = &op->tmB;
-            asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmA) : "memory");
-            asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmB) : "memory");
-            for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % STAGES;
-                if (kc >= STAGES)
-                    mbar_wait(bar_empty + 8 * s, ((kc / STAGES) - 1) & 1);
-                const uint32_t sa = base + s * STAGE_BYTES;
-                mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
-                tma_load_2d(sa, tmA, (kc0 + kc) * TILE_K, row0, bar_full + 8 * s);
-                tma_load_2d(sa + A_TILE_BYTES, tmB, (kc0 + kc) * TILE_K, col0, bar_full + 8 * s);
+            uint32_t gk = 0, nscatter = 0;
+            for (int it = blockIdx.x; it < ntiles; it += gridDim.x) {
+                const GemmTile tl = tiles[it];
+                const GemmOp* op = ops + tl.op;
+                const int row0 = tl.tm * TILE_M, col0 = tl.tn * TILE_N;
+                const int flags = op->flags;
+                int kc0, nk;
+                tile_k_range(flags, row0, col0, op->K, kc0, nk);
+                const void* tmA = &op->tmA;
+                const void* tmB = &op->tmB;
+                asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmA) : "memory");
+                asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmB) : "memory");
+                for (int kc = 0; kc < nk; ++kc, ++gk) {
+                    const uint32_t s = gk % STAGES;
+                    if (gk >= STAGES)
+                        mbar_wait(bar_empty + 8 * s, ((gk / STAGES) - 1) & 1);
+                    const uint32_t sa = base + s * STAGE_BYTES;
+                    mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+                    tma_load_2d(sa, tmA, (kc0 + kc) * TILE_K, row0, bar_full + 8 * s);
+                    tma_load_2d(sa + A_TILE_BYTES, tmB, (kc0 + kc) * TILE_K, col0, bar_full + 8 * s);
+                }
+                if (flags & GEMM_SCATTER) {
+                    // no prefetch past a scatter tile: its epilogue parks the accumulators in the stages
+                    mbar_wait(bar_tile, nscatter & 1);
+                    ++nscatter;
+                }
             }
         }
         return;
@@ -154,6 +158,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp
     // ---- DMMA consumers ----------------------------------------------------------
     const int g = lane >> 2, t = lane & 3;
     const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+    // per-thread constant parts of the swizzled fragment addresses
+    // element (r, k) of a 128 x 16 tile: r*128 + (((k>>1) ^ (r&7)) << 4) + ((k&1) << 3)
+    // fragment i of A sits at row wm + 16*(i>>1) + 2g + (i&1): a per-thread base plus a compile-time offset; the
+    // swizzle term depends on (row & 7) = (2g + (i&1)) & 7 only.  Likewise B.
+    const uint32_t a_base = (uint32_t)(wm + 2 * g) * 128u, b_base = (uint32_t)(wn + 2 * g) * 128u;
+    const int x0 = (2 * g) & 7, x1 = (2 * g + 1) & 7;
+    const uint32_t khalf = (uint32_t)(t & 1) << 3;
+    const int kq = t >> 1;
+
+    uint32_t gk = 0;
+    GemmTile next = tiles[blockIdx.x];
+    for (int it = blockIdx.x; it < ntiles; it += gridDim.x) {
+    const GemmTile tl = next;
+    if (it + (int)gridDim.x < ntiles)
+        next = tiles[it + gridDim.x];   // in flight during this tile
+    const GemmOp* op = ops + tl.op;
+    const int row0 = tl.tm * TILE_M, col0 = tl.tn * TILE_N;
+    const int M = op->M, N = op->N, K = op->K;
+    const int flags = op->flags, tri_off = op->tri_off;
+    int kc0, nk;
+    tile_k_range(flags, row0, col0, K, kc0, nk);
+
     double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -161,37 +187,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp
         for (int j = 0; j < 4; ++j)
             acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    // per-thread constant parts of the swizzled fragment addresses
-    // element (r, k) of a 128 x 16 tile: r*128 + (((k>>1) ^ (r&7)) << 4) + ((k&1) << 3)
-    uint32_t a_row[8], b_row[4];
-    int a_x[2], b_x[2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        a_row[i] = (uint32_t)(wm + 16 * (i >> 1) + 2 * g + (i & 1)) * 128u;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        b_row[j] = (uint32_t)(wn + 16 * (j >> 1) + 2 * g + (j & 1)) * 128u;
-    a_x[0] = b_x[0] = (2 * g) & 7;
-    a_x[1] = b_x[1] = (2 * g + 1) & 7;
-    const uint32_t khalf = (uint32_t)(t & 1) << 3;
-    const int kq = t >> 1;
-
-    for (int kc = 0; kc < nk; ++kc) {
-        const int s = LOADER == 0 ? kc % STAGES : 0;
+    for (int kc = 0; kc < nk; ++kc, ++gk) {
+        const uint32_t s = LOADER == 0 ? gk % STAGES : 0;
         const uint32_t sa = base + s * STAGE_BYTES;
         const uint32_t sb = sa + A_TILE_BYTES;
         if (LOADER == 0) {
-            mbar_wait(bar_full + 8 * s, (kc / STAGES) & 1);
+            mbar_wait(bar_full + 8 * s, (gk / STAGES) & 1);
         } else {
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const double* __restrict__ gA = op->A;
             const double* __restrict__ gB = op->B;
             for (int idx = threadIdx.x; idx < TILE_M * TILE_K; idx += CONSUMER_WARPS * 32) {
                 const int r = idx / TILE_K, k = idx - r * TILE_K;
-                const int gk = (kc0 + kc) * TILE_K + k;
+                const int gkk = (kc0 + kc) * TILE_K + k;
                 const uint32_t off = (uint32_t)r * 128u + ((uint32_t)((k >> 1) ^ (r & 7)) << 4) + ((uint32_t)(k & 1) << 3);
-                const double va = (row0 + r < M && gk < K) ? gA[(int64_t)(row0 + r) * op->lda + gk] : 0.0;
-                const double vb = (col0 + r < N && gk < K) ? gB[(int64_t)(col0 + r) * op->ldb + gk] : 0.0;
+                const double va = (row0 + r < M && gkk < K) ? gA[(int64_t)(row0 + r) * op->lda + gkk] : 0.0;
+                const double vb = (col0 + r < N && gkk < K) ? gB[(int64_t)(col0 + r) * op->ldb + gkk] : 0.0;
                 asm volatile("st.shared.f64 [%0], %1;" ::"r"(sa + off), "d"(va) : "memory");
                 asm volatile("st.shared.f64 [%0], %1;" ::"r"(sb + off), "d"(vb) : "memory");
             }
@@ -200,15 +211,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp
 #pragma unroll
         for (int k4 = 0; k4 < TILE_K / 4; ++k4) {
             const int chunk = 2 * k4 + kq;
-            const uint32_t o0 = ((uint32_t)(chunk ^ a_x[0]) << 4) + khalf;
-            const uint32_t o1 = ((uint32_t)(chunk ^ a_x[1]) << 4) + khalf;
+            const uint32_t o0 = ((uint32_t)(chunk ^ x0) << 4) + khalf;
+            const uint32_t o1 = ((uint32_t)(chunk ^ x1) << 4) + khalf + 128u;
+            const uint32_t pa0 = sa + a_base + o0, pa1 = sa + a_base + o1;
+            const uint32_t pb0 = sb + b_base + o0, pb1 = sb + b_base + o1;
             double a[8], b[4];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                a[i] = lds_f64(sa + a_row[i] + ((i & 1) ? o1 : o0));
+                a[i] = lds_f64(((i & 1) ? pa1 : pa0) + (uint32_t)(i >> 1) * 2048u);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                b[j] = lds_f64(sb + b_row[j] + ((j & 1) ? o1 : o0));
+                b[j] = lds_f64(((j & 1) ? pb1 : pb0) + (uint32_t)(j >> 1) * 2048u);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -232,7 +245,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp
         // 32 consecutive source columns (consecutive boundary stations are mostly consecutive in the ancestor, so
         // a warp instruction touches far fewer 32-byte sectors than in fragment order) and the column part of
         // the map is looked up once per lane instead of once per element.
-        const int32_t* __restrict__ rowmap = op->rowmap;
         asm volatile("bar.sync 1, 256;" ::: "memory");   // every consumer has finished reading the last stages
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -251,28 +263,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp
             }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        int64_t dcol[4];
+        // per lane: its four columns' targets (ancestor panel, pitch, station row map) and column positions
+        double* cbase[4];
+        const int32_t* rmap[4];
+        int64_t cld[4];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
             const int c = col0 + 32 * cc + lane;
-            dcol[cc] = c < N ? 3ll * rowmap[c / 3] + c % 3 : -1;
+            cbase[cc] = nullptr;
+            if (c < N) {
+                const ScatterTarget tg = op->tgt[op->coltgt[c / 3]];
+                rmap[cc] = tg.rowmap - tg.jb;                                    // indexed by boundary station
+                cld[cc] = tg.ldc;
+                cbase[cc] = tg.C + 3ll * rmap[cc][c / 3] + c % 3;
+            }
         }
         for (int rr = warp; rr < TILE_M; rr += CONSUMER_WARPS) {
             const int r = row0 + rr;
             if (r >= M)
                 break;
-            double* __restrict__ crow = C + (3ll * rowmap[r / 3] + r % 3) * ldc;
+            const int si = r / 3, rc = r - 3 * si;
             const uint32_t rbase = base + (uint32_t)rr * (TILE_N * 8);
             const int sw = (rr >> 1) & 7;
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
                 const int cl = 32 * cc + lane;
-                if (dcol[cc] < 0 || (lower && r + tri_off < col0 + cl))
+                if (cbase[cc] == nullptr || (lower && r + tri_off < col0 + cl))
                     continue;
                 const double v = lds_f64(rbase + (uint32_t)((((cl >> 2) ^ sw) << 5) + ((cl & 3) << 3)));
-                atomicAdd(crow + dcol[cc], alpha * v);
+                atomicAdd(cbase[cc] + (3ll * rmap[cc][si] + rc) * cld[cc], alpha * v);
             }
         }
+        __syncwarp();
+        if (LOADER == 0 && lane == 0)
+            mbar_arrive(bar_tile);   // this warp no longer reads the staging area: the producer may refill the stages
     } else {
         const bool accum = (flags & GEMM_ACCUM) != 0;
         // fragments j = 2p and 2p+1 interleave: together a thread owns 4 consecutive columns
@@ -311,25 +335,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const GemmOp
             }
         }
     }
+    if (LOADER != 0)
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // debug loader: the next tile's self-loads reuse stage 0
+    }   // tile loop
 }
 
 }  // namespace
 
-void launch_gemm(const GemmOp* ops, int nops, int total_tiles, void* stream)
+void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, void* stream)
 {
-    if (nops <= 0 || total_tiles <= 0)
+    if (nops <= 0 || ntiles <= 0)
         return;
-    static int loader = -1;
+    static int loader = -1, sms = 148;
     if (loader < 0) {
         const char* e = getenv("GADJ_GEMM_LOADER");
         loader = (e && e[0] == 'l') ? 1 : 0;
         cudaFuncSetAttribute(gemm_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
         cudaFuncSetAttribute(gemm_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            sms = n;
     }
+    const int grid = ntiles < sms ? ntiles : sms;   // one persistent CTA per SM (the 132 KB ring allows no more)
     if (loader == 0)
-        gemm_tile_kernel<0><<<total_tiles, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(ops, nops);
+        gemm_tile_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(ops, tiles, ntiles);
     else
-        gemm_tile_kernel<1><<<total_tiles, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(ops, nops);
+        gemm_tile_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(ops, tiles, ntiles);
 }
 
 }  // namespace gadj

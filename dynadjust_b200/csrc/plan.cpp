@@ -94,7 +94,7 @@ struct Builder {
     }
 
     void add_gemm(std::vector<GemmOp>& batch, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
-                  int64_t ldc, int M, int N, int K, int flags, int tri_off = 0, const int32_t* rowmap = nullptr)
+                  int64_t ldc, int M, int N, int K, int flags, int tri_off = 0, const int32_t* coltgt = nullptr)
     {
         if (M <= 0 || N <= 0 || K <= 0)
             return;
@@ -102,7 +102,8 @@ struct Builder {
         op.A = A;
         op.B = B;
         op.C = C;
-        op.rowmap = rowmap;
+        op.coltgt = coltgt;
+        op.tgt = b.tgt;
         op.lda = lda;
         op.ldb = ldb;
         op.ldc = ldc;
@@ -127,10 +128,16 @@ struct Builder {
         L.op_begin = (int64_t)p.gemm.size();
         L.op_count = (int32_t)batch.size();
         L.level = level;
-        int tiles = 0;
+        L.tile_begin = (int64_t)p.tiles.size();
+        int32_t opi = 0;
         for (GemmOp& op : batch) {
-            op.tile_begin = tiles;
-            tiles += op.tiles_m * op.tiles_n;
+            for (int tm = 0; tm < op.tiles_m; ++tm)
+                for (int tn = 0; tn < op.tiles_n; ++tn) {
+                    if ((op.flags & GEMM_LOWER) && tm * TILE_M + (TILE_M - 1) + op.tri_off < tn * TILE_N)
+                        continue;   // wholly above the diagonal
+                    p.tiles.push_back(GemmTile{opi, (uint16_t)tm, (uint16_t)tn});
+                }
+            ++opi;
             // useful flops: lower-only outputs drop the strict upper triangle of the leading square;
             // triangular operands halve the K range over that square
             double M = op.M, N = op.N, K = op.K;
@@ -149,7 +156,7 @@ struct Builder {
                 err = "tensor-map encoding failed";
             p.gemm.push_back(op);
         }
-        L.total_tiles = tiles;
+        L.total_tiles = (int32_t)(p.tiles.size() - (size_t)L.tile_begin);
         out.push_back(L);
         batch.clear();
     }
@@ -327,17 +334,15 @@ struct Builder {
                 flush_gemm(gb, p.factor, (int)lv, T_RIGHT_UPDATE);
             }
             build_trtri(fl, p.factor, (int)lv);
-            // Schur updates scattered into the ancestors' panels
+            // Schur update -L21 L21^T of every front, one lower-triangular r x r product per front, scattered into the
+            // ancestors' panels through the per-column target table
             for (uint32_t fi : fl) {
                 const Front& f = s.fronts[fi];
-                for (uint32_t t = 0; t < f.tgt_count; ++t) {
-                    const Target& tg = s.targets[f.tgt_begin + t];
-                    const Front& an = s.fronts[tg.anc];
-                    double* A = panel(f) + (size_t)(f.k + 3 * tg.jb) * f.ldk;
-                    double* C = panel(an);
-                    add_gemm(gb, A, f.ldk, A, f.ldk, C, an.ldk, (int)(f.r - 3 * tg.jb), (int)(3 * (tg.je - tg.jb)),
-                             (int)f.k, GEMM_SCATTER | GEMM_NEG | GEMM_LOWER, 0, b.rowmap + tg.rowmap_off);
-                }
+                if (!f.r)
+                    continue;
+                double* A = panel(f) + (size_t)f.k * f.ldk;
+                add_gemm(gb, A, f.ldk, A, f.ldk, nullptr, 0, (int)f.r, (int)f.r, (int)f.k, GEMM_SCATTER | GEMM_NEG | GEMM_LOWER, 0,
+                         b.coltgt + f.bnd_begin);
             }
             flush_gemm(gb, p.factor, (int)lv, T_SCHUR);
         }
@@ -586,6 +591,7 @@ void build_rowidx(const Symbolic& s, Plan& p)
 std::string build_plan(const Symbolic& s, const PlanBuffers& b, Plan& p)
 {
     p.gemm.clear();
+    p.tiles.clear();
     p.diag.clear();
     p.tri.clear();
     p.gemv.clear();
@@ -598,6 +604,24 @@ std::string build_plan(const Symbolic& s, const PlanBuffers& b, Plan& p)
     p.factor_flops = p.selinv_flops = 0;
     if (b.pool_doubles < min_pool_doubles(s))
         return "workspace pool smaller than the largest front";
+    // scatter tables of the Schur updates
+    p.tgt.assign(s.targets.size(), ScatterTarget{});
+    p.coltgt.assign(s.bnd.size(), -1);
+    for (const Front& f : s.fronts) {
+        if (f.owner != s.rank)
+            continue;
+        for (uint32_t t = 0; t < f.tgt_count; ++t) {
+            const Target& tg = s.targets[f.tgt_begin + t];
+            const Front& an = s.fronts[tg.anc];
+            ScatterTarget& st = p.tgt[f.tgt_begin + t];
+            st.C = b.panels + an.panel_off;
+            st.rowmap = b.rowmap + tg.rowmap_off;
+            st.ldc = an.ldk;
+            st.jb = (int32_t)tg.jb;
+            for (uint32_t i = tg.jb; i < tg.je; ++i)
+                p.coltgt[f.bnd_begin + i] = (int32_t)(f.tgt_begin + t);
+        }
+    }
     Builder B(s, b, p);
     B.build_factor();
     B.build_solves();

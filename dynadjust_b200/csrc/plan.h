@@ -25,7 +25,8 @@ struct Launch {
     int32_t kind;
     int32_t op_count;
     int64_t op_begin;     // index into the per-kind op array
-    int32_t total_tiles;  // L_GEMM
+    int32_t total_tiles;  // L_GEMM: tiles with work (entries of Plan::tiles from tile_begin); transpose / gather: CTAs per op
+    int64_t tile_begin;   // L_GEMM
     int32_t level;
     double* zero_ptr;     // L_ZERO
     size_t zero_bytes;
@@ -46,10 +47,15 @@ struct PlanBuffers {
     double* wbuf = nullptr;       // device, wbuf_doubles(): W = L11^-1 and Wt = W^T of every front this rank owns
     const int32_t* rowmap = nullptr;  // device copy of Symbolic::rowmap
     const int32_t* rowidx = nullptr;  // device: global unknown index per front row (concatenated, Plan::rowidx_off)
+    const ScatterTarget* tgt = nullptr;   // device, Symbolic::targets.size() entries (filled from Plan::tgt)
+    const int32_t* coltgt = nullptr;      // device, Symbolic::bnd.size() entries (filled from Plan::coltgt)
 };
 
 struct Plan {
     std::vector<GemmOp> gemm;
+    std::vector<GemmTile> tiles;
+    std::vector<ScatterTarget> tgt;         // per Symbolic::targets entry (device pointers inside)
+    std::vector<int32_t> coltgt;            // per Symbolic::bnd entry: index into tgt of the ancestor owning that station
     std::vector<DiagOp> diag;
     std::vector<TrimvOp> tri;
     std::vector<GemvOp> gemv;

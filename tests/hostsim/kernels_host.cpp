@@ -12,44 +12,51 @@
 
 namespace gadj {
 
-void launch_gemm(const GemmOp* ops, int nops, int, void*)
+void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, void*)
 {
-    std::vector<double> row;
-    for (int o = 0; o < nops; ++o) {
-        const GemmOp& op = ops[o];
-        row.resize(op.N);
-        for (int i = 0; i < op.M; ++i) {
-            for (int j = 0; j < op.N; ++j) {
+    // tile by tile, exactly the work list the persistent CTAs stride through: a tile missing from the planner's
+    // list, or listed twice, changes the results
+    std::vector<double> out((size_t)TILE_M * TILE_N);
+    for (int t = 0; t < ntiles; ++t) {
+        const GemmTile& tl = tiles[t];
+        if (tl.op < 0 || tl.op >= nops)
+            continue;
+        const GemmOp& op = ops[tl.op];
+        const int row0 = tl.tm * TILE_M, col0 = tl.tn * TILE_N;
+        // the kernel's per-tile K range (triangular operands): nothing outside it may be read
+        int k_lo = 0, k_hi = op.K;
+        if (op.flags & GEMM_KLO_ROW)
+            k_lo = row0;
+        if (op.flags & GEMM_KLO_MAX)
+            k_lo = row0 > col0 ? row0 : col0;
+        if (op.flags & GEMM_KHI_ROW)
+            k_hi = row0 + TILE_M < op.K ? row0 + TILE_M : op.K;
+        k_lo = (k_lo / TILE_K) * TILE_K;
+        const int i1 = row0 + TILE_M < op.M ? row0 + TILE_M : op.M, j1 = col0 + TILE_N < op.N ? col0 + TILE_N : op.N;
+        for (int i = row0; i < i1; ++i)
+            for (int j = col0; j < j1; ++j) {
                 double acc = 0.0;
                 const double* a = op.A + (int64_t)i * op.lda;
                 const double* b = op.B + (int64_t)j * op.ldb;
-                // the kernel's per-tile K range (triangular operands): nothing outside it may be read
-                const int row0 = (i / TILE_M) * TILE_M, col0 = (j / TILE_N) * TILE_N;
-                int k_lo = 0, k_hi = op.K;
-                if (op.flags & GEMM_KLO_ROW)
-                    k_lo = row0;
-                if (op.flags & GEMM_KLO_MAX)
-                    k_lo = row0 > col0 ? row0 : col0;
-                if (op.flags & GEMM_KHI_ROW)
-                    k_hi = row0 + TILE_M < op.K ? row0 + TILE_M : op.K;
-                k_lo = (k_lo / TILE_K) * TILE_K;
                 for (int k = k_lo; k < k_hi; ++k)
                     acc += a[k] * b[k];
-                row[j] = (op.flags & GEMM_NEG) ? -acc : acc;
+                out[(size_t)(i - row0) * TILE_N + (j - col0)] = (op.flags & GEMM_NEG) ? -acc : acc;
             }
-            for (int j = 0; j < op.N; ++j) {
+        for (int i = row0; i < i1; ++i)
+            for (int j = col0; j < j1; ++j) {
                 if ((op.flags & GEMM_LOWER) && i + op.tri_off < j)
                     continue;
+                const double v = out[(size_t)(i - row0) * TILE_N + (j - col0)];
                 if (op.flags & GEMM_SCATTER) {
-                    int64_t r = 3ll * op.rowmap[i / 3] + i % 3;
-                    int64_t c = 3ll * op.rowmap[j / 3] + j % 3;
-                    op.C[r * op.ldc + c] += row[j];
+                    const ScatterTarget& tg = op.tgt[op.coltgt[j / 3]];
+                    int64_t r = 3ll * tg.rowmap[i / 3 - tg.jb] + i % 3;
+                    int64_t c = 3ll * tg.rowmap[j / 3 - tg.jb] + j % 3;
+                    tg.C[r * tg.ldc + c] += v;
                 } else if (op.flags & GEMM_ACCUM)
-                    op.C[(int64_t)i * op.ldc + j] += row[j];
+                    op.C[(int64_t)i * op.ldc + j] += v;
                 else
-                    op.C[(int64_t)i * op.ldc + j] = row[j];
+                    op.C[(int64_t)i * op.ldc + j] = v;
             }
-        }
     }
 }
 
