@@ -177,6 +177,8 @@ struct gadj_ctx {
     std::vector<uint32_t> isl_off, isl;
     // measurement plan
     std::vector<uint32_t> first, edge_word;          // GNSS baselines
+    std::vector<uint32_t> binc_ptr, binc;            // station -> incident GNSS baselines (bit 31: the station is station2)
+    std::vector<uint32_t> edge_bsl;                  // per edge: its only baseline (block read from the baseline's slot) or ~0u
     // design rows of every other type (rows.h): terrestrial rows, derived angles of D sets, X / Y cluster rows
     std::vector<RowDesc> rows;
     std::vector<uint32_t> row_base;                  // D rows: record that supplies station2 / term3 / term4 of the angle
@@ -200,7 +202,8 @@ struct gadj_ctx {
     double critical = 0;
     // device state
     DevArray<dna_msr_t> d_msr;
-    DevArray<uint32_t> d_first, d_edge, d_edge_hi, d_edge_lo, d_pos, d_diag_ld, d_off_ld;
+    DevArray<uint32_t> d_first, d_edge, d_edge_hi, d_edge_lo, d_pos, d_diag_ld, d_off_ld, d_binc_ptr, d_binc, d_edge_bsl;
+    DevArray<double> d_bq;
     DevArray<RowDesc> d_rows;
     DevArray<ClusterDesc> d_clusters;
     DevArray<uint32_t> d_cstn, d_inc_ptr, d_inc, d_pair_word;
@@ -887,11 +890,24 @@ int gadj_prepare(gadj_ctx* c)
         for (uint32_t x = 0; x < cd.ns; ++x)
             for (uint32_t y = x + 1; y < cd.ns; ++y)
                 keys.push_back(pair_key(c->cstn[cd.st0 + x], c->cstn[cd.st0 + y]));
+    // distinct pairs, and how many measurements contribute to each: a pair fed by a single GNSS baseline is stored, not added
     std::vector<uint64_t> uniq(keys);
     std::sort(uniq.begin(), uniq.end());
-    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    std::vector<uint32_t> pair_count;
+    {
+        size_t o = 0;
+        for (size_t i = 0; i < uniq.size();) {
+            size_t j = i;
+            while (j < uniq.size() && uniq[j] == uniq[i])
+                ++j;
+            uniq[o++] = uniq[i];
+            pair_count.push_back((uint32_t)(j - i));
+            i = j;
+        }
+        uniq.resize(o);
+    }
     c->nedge = uniq.size();
-    if (c->nedge >= (1ull << 31))
+    if (c->nedge >= (1ull << 30))
         return c->fail("too many distinct station pairs");
     std::vector<std::pair<uint32_t, uint32_t>> edges(c->nedge);
     for (uint64_t e = 0; e < c->nedge; ++e)
@@ -963,9 +979,34 @@ int gadj_prepare(gadj_ctx* c)
     parallel_for(nb, [&](uint64_t b0, uint64_t b1) {
         for (uint64_t b = b0; b < b1; ++b) {
             const dna_msr_t& m = c->msr[c->first[b]];
-            c->edge_word[b] = edge_word_of(m.station1, m.station2);
+            uint32_t w = edge_word_of(m.station1, m.station2);
+            if (pair_count[w & EDGE_SLOT_MASK] == 1)
+                w |= EDGE_EXCLUSIVE;
+            c->edge_word[b] = w;
         }
     });
+    c->edge_bsl.assign(c->nedge, ~0u);
+    for (uint64_t b = 0; b < nb; ++b)
+        if (c->edge_word[b] & EDGE_EXCLUSIVE)
+            c->edge_bsl[c->edge_word[b] & EDGE_SLOT_MASK] = (uint32_t)b;
+    // incidence lists of the stations over the GNSS baselines, ascending baseline index (fixed summation order)
+    c->binc_ptr.assign((size_t)c->nstn + 1, 0);
+    for (uint64_t b = 0; b < nb; ++b) {
+        const dna_msr_t& m = c->msr[c->first[b]];
+        ++c->binc_ptr[m.station1 + 1];
+        ++c->binc_ptr[m.station2 + 1];
+    }
+    for (uint32_t s2 = 0; s2 < c->nstn; ++s2)
+        c->binc_ptr[s2 + 1] += c->binc_ptr[s2];
+    c->binc.resize(2 * nb);
+    {
+        std::vector<uint32_t> cur(c->binc_ptr.begin(), c->binc_ptr.end() - 1);
+        for (uint64_t b = 0; b < nb; ++b) {
+            const dna_msr_t& m = c->msr[c->first[b]];
+            c->binc[cur[m.station1]++] = (uint32_t)b;
+            c->binc[cur[m.station2]++] = (uint32_t)b | 0x80000000u;
+        }
+    }
     for (RowDesc& d : c->rows) {
         if (d.nst >= 2)
             d.edge[0] = edge_word_of(d.st[0], d.st[1]);
@@ -1001,6 +1042,10 @@ int gadj_prepare(gadj_ctx* c)
     ok &= c->d_msr.resize(c->nmsr);
     ok &= c->d_first.upload(c->first);
     ok &= c->d_edge.upload(c->edge_word);
+    ok &= c->d_binc_ptr.upload(c->binc_ptr);
+    ok &= c->d_binc.upload(c->binc);
+    ok &= c->d_edge_bsl.upload(c->edge_bsl);
+    ok &= c->d_bq.resize(9 * (size_t)nb);
     ok &= c->d_rows.upload(c->rows);
     ok &= c->d_clusters.upload(c->clusters);
     ok &= c->d_cstn.upload(c->cstn);
@@ -1171,11 +1216,14 @@ static void fill_assemble(gadj_ctx* c, AssembleParams& ap, int normals)
     ap.first = c->d_first.p;
     ap.edge = c->d_edge.p;
     ap.est = c->d_est.p;
+    ap.bq = c->d_bq.p;
+    ap.inc_ptr = c->d_binc_ptr.p;
+    ap.inc = c->d_binc.p;
     ap.ndiag = c->d_ndiag.p;
     ap.noff = c->d_noff.p;
     ap.w = c->d_w.p;
-    ap.chi2 = nullptr;
     ap.nbaselines = c->nbsl;
+    ap.nstn = c->nstn;
     ap.contiguous = c->contiguous ? 1 : 0;
     ap.normals = normals;
 }
@@ -1226,6 +1274,8 @@ static void fill_scatter(gadj_ctx* c, ScatterParams& sp)
 {
     sp.ndiag = c->d_ndiag.p;
     sp.noff = c->d_noff.p;
+    sp.bq = c->d_bq.p;
+    sp.edge_bsl = c->d_edge_bsl.p;
     sp.diag_dest = c->d_diag_dest.p;
     sp.diag_ld = c->d_diag_ld.p;
     sp.off_dest = c->d_off_dest.p;
@@ -1266,6 +1316,9 @@ int gadj_stage_begin(gadj_ctx* c, int flags)
     fill_assemble(c, ap, normals ? 1 : 0);
     c->prof_begin(PK_ASSEMBLE);
     launch_assemble_g(ap, st);
+    c->prof_end();
+    c->prof_begin(PK_ASSEMBLE);
+    launch_station_sum(ap, st);
     c->prof_end();
     if (c->nrows) {
         RowsParams rp;
@@ -1758,6 +1811,21 @@ int gadj_get_normals_block(gadj_ctx* c, uint32_t si, uint32_t sj, double n[9])
 {
     if (!c->prepared || !c->normals_valid)
         return c->fail("normals have not been assembled");
+    if (si != sj && si < c->nstn && sj < c->nstn) {
+        uint64_t ei;
+        bool tr = false;
+        if (!find_edge(c, si, sj, &ei, &tr) && c->edge_bsl[ei] != ~0u) {
+            // the pair is observed by a single GNSS baseline: its block -V^-1 lives in the baseline's slot
+            double q6[6];
+            dev::d2h(q6, c->d_bq.p + 9 * (size_t)c->edge_bsl[ei], sizeof(q6));
+            std::string e = dev::sync();
+            if (!e.empty())
+                return c->fail(e);
+            for (int k = 0; k < 9; ++k)
+                n[k] = -q6[GADJ_SYM3(k)];
+            return 0;
+        }
+    }
     return get_block(c, c->d_ndiag.p, c->d_noff.p, si, sj, n);
 }
 

@@ -141,20 +141,33 @@ void launch_transpose(const TransposeOp* ops, int nops, int grid_x, void* stream
 void launch_gather(const GatherOp* ops, int nops, int grid_x, void* stream);
 
 // ---- assembly -----------------------------------------------------------------
+// Edge word of a GNSS baseline: bits 0..29 edge slot, bit 31 = station1 is eliminated after station2, bit 30 = this
+// baseline is the only contribution to its off-diagonal block: the block is not stored at all, the scatter into the
+// panels reads it from the baseline's slot (ScatterParams::edge_bsl).
+constexpr uint32_t EDGE_SLOT_MASK = 0x3FFFFFFFu;
+constexpr uint32_t EDGE_EXCLUSIVE = 0x40000000u;
+// element k (row-major) of a symmetric 3x3 block -> index into its stored upper triangle {00 01 02 11 12 22}
+#define GADJ_SYM3(k) ((k) == 0 ? 0 : (k) == 1 || (k) == 3 ? 1 : (k) == 2 || (k) == 6 ? 2 : (k) == 4 ? 3 : (k) == 8 ? 5 : 4)
+
 struct AssembleParams {
     const dna_msr_t* msr;        // device copy of the raw .bms records
     const uint32_t* first;       // per GNSS baseline: index of its X record
-    const uint32_t* edge;        // per baseline: edge slot | (1u<<31 when station1 is eliminated after station2)
+    const uint32_t* edge;        // per baseline: edge word (above)
     const double* est;           // 3 x nstn estimated Cartesian coordinates (station order)
-    double* ndiag;               // nstn x 9 diagonal blocks (station order, row-major 3x3)
+    double* bq;                  // 9 x nbaselines: V^-1 (upper triangle, 6) and V^-1 l (3) of every baseline
+    const uint32_t* inc_ptr;     // nstn + 1: incidence lists of the stations ...
+    const uint32_t* inc;         // ... entries = baseline index | bit 31 when the station is the baseline's station2
+    double* ndiag;               // nstn x 9 diagonal blocks (station order, row-major 3x3), initialised by init_normals
     double* noff;                // nedge x 9 off-diagonal blocks: N[later station, earlier station]
     double* w;                   // 3 x nstn  A^T V^-1 l (station order)
-    double* chi2;                // optional: sum l^T V^-1 l accumulated here (statistics pass)
     uint64_t nbaselines;
+    uint32_t nstn;
     int32_t contiguous;          // first[b] == first[0] + 3b for all b
-    int32_t normals;             // 0: rhs (and chi2) only
+    int32_t normals;             // 0: rhs only
 };
+// two launches: per-baseline pass (records -> bq, off-diagonal blocks), per-station gather (bq -> ndiag, w)
 void launch_assemble_g(const AssembleParams& p, void* stream);
+void launch_station_sum(const AssembleParams& p, void* stream);
 
 // design rows of every other measurement type and the D / X / Y clusters: parameter blocks in rows.h
 struct RowsParams;
@@ -174,6 +187,8 @@ void launch_init_normals(const double* cblock, double* ndiag, double* noff, doub
 struct ScatterParams {
     const double* ndiag;
     const double* noff;
+    const double* bq;            // per-baseline slots of the assembly (V^-1 upper triangle + V^-1 l)
+    const uint32_t* edge_bsl;    // per edge: the one GNSS baseline that forms its block (N[hi,lo] = -V^-1, read from bq), or ~0u: block is in noff
     const uint64_t* diag_dest;   // per station (station order); ~0 = assembled by another rank
     const uint32_t* diag_ld;
     const uint64_t* off_dest;    // per edge

@@ -3,12 +3,15 @@
 //   front panels, right-hand-side permutation, estimate update, VCV extraction and statistics.
 //
 // Assembly follows UpdateDesignNormalMeasMatrices_G / LoadVarianceMatrix_G / UpdateNormals_G
-// (ADJ:5353-5397, ADJ:4214-4309, ADJ:1664-1684) for one GNSS baseline per thread:
-//   l = term1 - (X2 - X1);  V^-1 from the six variance terms of the three records;
-//   N[s1,s1] += V^-1, N[s2,s2] += V^-1, N[s2,s1] -= V^-1;  w[s1] -= V^-1 l, w[s2] += V^-1 l.
-// The raw 208-byte records are streamed into shared memory by 1-D bulk async copies
-// (cp.async.bulk + mbarrier, i.e. the TMA engine) one 64-baseline tile (39,936 B) at a time; several
-// CTAs per SM overlap one CTA's copy with the others' arithmetic and atomics.
+// (ADJ:5353-5397, ADJ:4214-4309, ADJ:1664-1684) in two passes without floating-point atomics on the diagonal:
+//   pass 1, one GNSS baseline per thread:  l = term1 - (X2 - X1);  V^-1 from the six variance terms of the three
+//           records;  V^-1 and V^-1 l are written to a 72-byte slot per baseline and  N[s2,s1] = -V^-1  goes straight
+//           to the baseline's off-diagonal block (plain store when no other measurement shares the station pair).
+//           The raw 208-byte records are streamed into shared memory by 1-D bulk async copies (cp.async.bulk +
+//           mbarrier, i.e. the TMA engine, L2 evict-first) one 64-baseline tile (39,936 B) at a time; several CTAs
+//           per SM overlap one CTA's copy with the others' arithmetic.
+//   pass 2, 16 lanes per station:  N[s,s] += sum of V^-1 over the station's incidence list,  w[s] += sum of -/+ V^-1 l
+//           — a gather in a fixed order, so the assembled normals are bit-reproducible from run to run.
 // Algorithmic traffic per baseline: 3*208 B records + 8 B plan words + 48 B station XYZ
 // + 27*8 B block updates + 48 B rhs updates = 944 B  (936 B in SURVEY.md §8d + the two plan words).
 #include <cuda_runtime.h>
@@ -28,11 +31,19 @@ constexpr int ASM_SMEM = ASM_TILE * ASM_BYTES_PER_BSL;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+// the records are read exactly once: evict-first keeps the station arrays and the 72-byte slots in L2 instead
+__device__ __forceinline__ uint64_t policy_evict_first()
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+        : "memory");
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
@@ -57,8 +68,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 }
 
 // arithmetic of one baseline given its three records
-__device__ __forceinline__ void baseline_contribution(const dna_msr_t* __restrict__ m, const AssembleParams& p, uint32_t edge_word,
-                                                      double& chi)
+__device__ __forceinline__ void baseline_contribution(const dna_msr_t* __restrict__ m, const AssembleParams& p, uint64_t b,
+                                                      uint32_t edge_word)
 {
     const uint32_t s1 = m[0].station1, s2 = m[0].station2;
     const double* __restrict__ e1 = p.est + 3 * (size_t)s1;
@@ -75,27 +86,19 @@ __device__ __forceinline__ void baseline_contribution(const dna_msr_t* __restric
             q[k] = __longlong_as_double(0x7ff8000000000000ll);
     }
     const double V[9] = {q[0], q[1], q[2], q[1], q[3], q[4], q[2], q[4], q[5]};
-    double t[3];
+    double* __restrict__ slot = p.bq + 9 * b;
 #pragma unroll
     for (int r = 0; r < 3; ++r)
-        t[r] = V[3 * r] * l[0] + V[3 * r + 1] * l[1] + V[3 * r + 2] * l[2];
-    double* __restrict__ w1 = p.w + 3 * (size_t)s1;
-    double* __restrict__ w2 = p.w + 3 * (size_t)s2;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        atomicAdd(w1 + r, -t[r]);
-        atomicAdd(w2 + r, t[r]);
-    }
-    chi = l[0] * t[0] + l[1] * t[1] + l[2] * t[2];
+        slot[6 + r] = V[3 * r] * l[0] + V[3 * r + 1] * l[1] + V[3 * r + 2] * l[2];
     if (p.normals) {
-        double* __restrict__ d1 = p.ndiag + 9 * (size_t)s1;
-        double* __restrict__ d2 = p.ndiag + 9 * (size_t)s2;
-        double* __restrict__ o = p.noff + 9 * (size_t)(edge_word & 0x7FFFFFFFu);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            atomicAdd(d1 + k, V[k]);
-            atomicAdd(d2 + k, V[k]);
-            atomicAdd(o + k, -V[k]);
+        for (int k = 0; k < 6; ++k)
+            slot[k] = q[k];
+        if (!(edge_word & EDGE_EXCLUSIVE)) {     // a station pair shared with other measurements: accumulate its block
+            double* __restrict__ o = p.noff + 9 * (size_t)(edge_word & EDGE_SLOT_MASK);
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                atomicAdd(o + k, -V[k]);
         }
     }
 }
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(ASM_TILE) assemble_g_kernel(const AssemblePara
         __syncthreads();
     }
     uint32_t phase = 0;
-    double chi_acc = 0.0;
+    const uint64_t pol = policy_evict_first();
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t b0 = tile * ASM_TILE;
         const int nb = (int)((p.nbaselines - b0 < (uint64_t)ASM_TILE) ? (p.nbaselines - b0) : ASM_TILE);
@@ -129,14 +132,14 @@ __global__ void __launch_bounds__(ASM_TILE) assemble_g_kernel(const AssemblePara
                 if (tid == 0) {
                     const uint32_t bytes = (uint32_t)nb * ASM_BYTES_PER_BSL;
                     mbar_expect_tx(bar, bytes);
-                    bulk_g2s(smem_u32(stage), p.msr + first, bytes, bar);
+                    bulk_g2s(smem_u32(stage), p.msr + first, bytes, bar, pol);
                 }
             } else {
                 if (tid == 0)
                     mbar_expect_tx(bar, (uint32_t)nb * ASM_BYTES_PER_BSL);
                 __syncthreads();  // the expectation is posted before any copy can complete
                 if (active)
-                    bulk_g2s(smem_u32(stage) + tid * ASM_BYTES_PER_BSL, p.msr + first, ASM_BYTES_PER_BSL, bar);
+                    bulk_g2s(smem_u32(stage) + tid * ASM_BYTES_PER_BSL, p.msr + first, ASM_BYTES_PER_BSL, bar, pol);
             }
             mbar_wait(bar, phase);
             phase ^= 1u;
@@ -144,21 +147,52 @@ __global__ void __launch_bounds__(ASM_TILE) assemble_g_kernel(const AssemblePara
         } else {
             m = p.msr + first;
         }
-        if (active) {
-            double chi;
-            baseline_contribution(m, p, ew, chi);
-            chi_acc += chi;
-        }
+        if (active)
+            baseline_contribution(m, p, b, ew);
         if (STAGED)
             __syncthreads();  // everyone is done with the stage before the next copy overwrites it
     }
-    if (p.chi2) {
+}
+
+// pass 2: 16 lanes per station (12 used: the 9 elements of the diagonal block and the 3 of the right-hand side);
+// every lane walks the station's incidence list and adds its element of each baseline's slot
+__global__ void __launch_bounds__(256) station_sum_kernel(const AssembleParams p)
+{
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t s = gid >> 4;
+    const int k = (int)(gid & 15);
+    if (s >= p.nstn || k >= 12 || (k < 9 && !p.normals))
+        return;
+    // element k of the 3x3 block -> index into the stored upper triangle {00 01 02 11 12 22}
+    const int sym = k < 9 ? GADJ_SYM3(k) : k - 3;
+    const uint32_t i0 = p.inc_ptr[s], i1 = p.inc_ptr[s + 1];
+    double acc = 0.0;
+    // four incidences per round: the index loads, then the four slot loads, are in flight together; the sum order
+    // (ascending list position) is the same for every run
+    const bool rhs = k >= 9;
+    uint32_t i = i0;
+    for (; i + 4 <= i1; i += 4) {
+        uint32_t e[4];
+        double v[4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-            chi_acc += __shfl_xor_sync(0xffffffffu, chi_acc, o);
-        if ((tid & 31) == 0)
-            atomicAdd(p.chi2, chi_acc);
+        for (int u = 0; u < 4; ++u)
+            e[u] = p.inc[i + u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            v[u] = p.bq[9ull * (e[u] & 0x7FFFFFFFu) + sym];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            acc += (rhs && !(e[u] & 0x80000000u)) ? -v[u] : v[u];      // w[s1] -= V^-1 l,  w[s2] += V^-1 l
     }
+    for (; i < i1; ++i) {
+        const uint32_t e = p.inc[i];
+        const double v = p.bq[9ull * (e & 0x7FFFFFFFu) + sym];
+        acc += (rhs && !(e & 0x80000000u)) ? -v : v;
+    }
+    if (rhs)
+        p.w[3 * s + (k - 9)] += acc;
+    else
+        p.ndiag[9 * s + k] += acc;
 }
 
 __global__ void init_normals_kernel(const double* __restrict__ cblock, double* __restrict__ ndiag, double* __restrict__ noff,
@@ -201,9 +235,11 @@ __global__ void scatter_normals_kernel(const ScatterParams p)
             const uint64_t j = i - nd, e = j / 9;
             const int k = (int)(j - 9 * e), r = k / 3, c = k - 3 * r;
             const uint64_t d = p.off_dest[e];
-            if (d != ~0ull)
-                p.panels[d + (uint64_t)r * p.off_ld[e] + c] =
-                    p.noff[j] * p.dscale[3ull * p.edge_hi[e] + r] * p.dscale[3ull * p.edge_lo[e] + c];
+            if (d != ~0ull) {
+                const uint32_t b = p.edge_bsl[e];
+                const double v = b != ~0u ? -p.bq[9ull * b + GADJ_SYM3(k)] : p.noff[j];
+                p.panels[d + (uint64_t)r * p.off_ld[e] + c] = v * p.dscale[3ull * p.edge_hi[e] + r] * p.dscale[3ull * p.edge_lo[e] + c];
+            }
         }
     }
 }
@@ -359,7 +395,7 @@ __global__ void __launch_bounds__(128) stats_g_kernel(const StatsParams p)
             l[r] = t1[r] - (p.est[3 * (size_t)s2 + r] - p.est[3 * (size_t)s1 + r]);
         }
         const uint32_t ew = p.edge[b];
-        const double* __restrict__ Qo = p.vcv_off + 9 * (size_t)(ew & 0x7FFFFFFFu);
+        const double* __restrict__ Qo = p.vcv_off + 9 * (size_t)(ew & EDGE_SLOT_MASK);
         const bool s1_is_hi = (ew & 0x80000000u) != 0;
         const double* __restrict__ Q11 = p.vcv_diag + 9 * (size_t)s1;
         const double* __restrict__ Q22 = p.vcv_diag + 9 * (size_t)s2;
@@ -451,20 +487,28 @@ constexpr int MAX_PARTS = 148 * 8;
 
 void launch_assemble_g(const AssembleParams& p, void* stream)
 {
-    if (p.nbaselines == 0)
-        return;
     static int mode = -1;  // 0 staged (bulk async copies), 1 direct loads (debug aid: GADJ_ASSEMBLE_DIRECT=1)
     if (mode < 0) {
         const char* e = getenv("GADJ_ASSEMBLE_DIRECT");
         mode = (e && e[0] == '1') ? 1 : 0;
         cudaFuncSetAttribute(assemble_g_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASM_SMEM);
     }
+    if (p.nbaselines == 0)
+        return;
     const uint64_t ntiles = (p.nbaselines + ASM_TILE - 1) / ASM_TILE;
     const int grid = (int)(ntiles < (uint64_t)(148 * 5) ? ntiles : (uint64_t)(148 * 5));
     if (mode == 0)
         assemble_g_kernel<true><<<grid, ASM_TILE, ASM_SMEM, (cudaStream_t)stream>>>(p, ntiles);
     else
         assemble_g_kernel<false><<<grid * 4, ASM_TILE, 0, (cudaStream_t)stream>>>(p, ntiles);
+}
+
+void launch_station_sum(const AssembleParams& p, void* stream)
+{
+    if (p.nbaselines == 0)
+        return;
+    const uint64_t threads = 16ull * p.nstn;
+    station_sum_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
 }
 
 void launch_init_normals(const double* cblock, double* ndiag, double* noff, double* w, uint32_t nstn, uint64_t nedge,

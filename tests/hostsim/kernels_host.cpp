@@ -190,6 +190,7 @@ void launch_init_normals(const double* cblock, double* ndiag, double* noff, doub
 
 void launch_assemble_g(const AssembleParams& p, void*)
 {
+    // pass 1: per baseline
     for (uint64_t b = 0; b < p.nbaselines; ++b) {
         const dna_msr_t* m = p.msr + p.first[b];
         const uint32_t s1 = m[0].station1, s2 = m[0].station2;
@@ -202,24 +203,38 @@ void launch_assemble_g(const AssembleParams& p, void*)
             for (double& v : q)
                 v = NAN;
         const double V[9] = {q[0], q[1], q[2], q[1], q[3], q[4], q[2], q[4], q[5]};
-        double t[3];
+        double* slot = p.bq + 9 * b;
         for (int r = 0; r < 3; ++r)
-            t[r] = V[3 * r] * l[0] + V[3 * r + 1] * l[1] + V[3 * r + 2] * l[2];
-        for (int r = 0; r < 3; ++r) {
-            p.w[3 * (size_t)s1 + r] -= t[r];
-            p.w[3 * (size_t)s2 + r] += t[r];
-        }
-        if (p.chi2)
-            *p.chi2 += l[0] * t[0] + l[1] * t[1] + l[2] * t[2];
+            slot[6 + r] = V[3 * r] * l[0] + V[3 * r + 1] * l[1] + V[3 * r + 2] * l[2];
         if (p.normals) {
-            const uint32_t e = p.edge[b] & 0x7FFFFFFFu;
-            for (int k = 0; k < 9; ++k) {
-                p.ndiag[9 * (size_t)s1 + k] += V[k];
-                p.ndiag[9 * (size_t)s2 + k] += V[k];
-                p.noff[9 * (size_t)e + k] -= V[k];
+            for (int k = 0; k < 6; ++k)
+                slot[k] = q[k];
+            const uint32_t ew = p.edge[b];
+            if (!(ew & EDGE_EXCLUSIVE)) {
+                double* o = p.noff + 9 * (size_t)(ew & EDGE_SLOT_MASK);
+                for (int k = 0; k < 9; ++k)
+                    o[k] -= V[k];
             }
         }
     }
+}
+
+void launch_station_sum(const AssembleParams& p, void*)
+{
+    if (p.nbaselines == 0)
+        return;
+    // pass 2: per station, over its incidence list
+    static const int sym[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
+    for (uint32_t s = 0; s < p.nstn; ++s)
+        for (uint32_t i = p.inc_ptr[s]; i < p.inc_ptr[s + 1]; ++i) {
+            const uint32_t e = p.inc[i];
+            const double* slot = p.bq + 9ull * (e & 0x7FFFFFFFu);
+            if (p.normals)
+                for (int k = 0; k < 9; ++k)
+                    p.ndiag[9 * (size_t)s + k] += slot[sym[k]];
+            for (int r = 0; r < 3; ++r)
+                p.w[3 * (size_t)s + r] += (e & 0x80000000u) ? slot[6 + r] : -slot[6 + r];
+        }
 }
 
 // rows / clusters: the arithmetic is shared with the kernels (rows.h); only the thread loops differ
@@ -339,7 +354,12 @@ void launch_scatter_normals(const ScatterParams& p, void*)
         const uint32_t hi = p.edge_hi[e], lo = p.edge_lo[e];
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c)
-                d[(size_t)r * ld + c] = p.noff[9 * e + 3 * r + c] * p.dscale[3 * (size_t)hi + r] * p.dscale[3 * (size_t)lo + c];
+            {
+                const uint32_t b = p.edge_bsl[e];
+                const int k = 3 * r + c;
+                const double v = b != ~0u ? -p.bq[9ull * b + GADJ_SYM3(k)] : p.noff[9 * e + k];
+                d[(size_t)r * ld + c] = v * p.dscale[3 * (size_t)hi + r] * p.dscale[3 * (size_t)lo + c];
+            }
     }
 }
 
@@ -421,7 +441,7 @@ void launch_stats_g(const StatsParams& p, void*)
         for (int r = 0; r < 3; ++r)
             l[r] = m[r].term1 - (p.est[3 * (size_t)s2 + r] - p.est[3 * (size_t)s1 + r]);
         const uint32_t ew = p.edge[b];
-        const double* Qo = p.vcv_off + 9 * (size_t)(ew & 0x7FFFFFFFu);
+        const double* Qo = p.vcv_off + 9 * (size_t)(ew & EDGE_SLOT_MASK);
         const bool s1_is_hi = (ew & 0x80000000u) != 0;
         const double* Q11 = p.vcv_diag + 9 * (size_t)s1;
         const double* Q22 = p.vcv_diag + 9 * (size_t)s2;

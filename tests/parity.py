@@ -82,9 +82,11 @@ def chain_blocks(n_stations, width):
     return [list(range(b, min(n_stations, b + width))) for b in range(0, n_stations, width)]
 
 
-def check_normals(oracle, lib_path, n_stations, n_baselines, seed, **opts):
+def check_normals(oracle, lib_path, n_stations, n_baselines, seed, mutate=None, **opts):
     """Assembled N (constraints included) and w of the first iteration, block by block."""
     stn, msr, _, _ = synth.gnss_network(n_stations, n_baselines, seed)
+    if mutate:
+        mutate(stn, msr)
     ref = oracle.adjust_simultaneous(stn.copy(), msr.copy(), want_normals=True)
     adj = engine.Adjustment(stn, msr, lib_path=lib_path, **opts)
     adj.prepare()

@@ -82,6 +82,18 @@ def test_normals_and_rhs(oracle, gpu_lib):
     parity.check_normals(oracle, gpu_lib, 80, 240, 4, leaf_stations=12)
 
 
+def test_repeated_station_pairs(oracle, gpu_lib):
+    # several baselines over the same station pair, in both directions: their off-diagonal block is accumulated
+    # (atomic adds), while pairs observed once are stored — both paths must give the reference's normals
+    def mutate(stn, msr):
+        rec = msr.reshape(-1, 3)
+        for dst, src, flip in ((5, 0, False), (9, 0, True), (30, 12, True)):
+            rec["station1"][dst] = rec["station2"][src] if flip else rec["station1"][src]
+            rec["station2"][dst] = rec["station1"][src] if flip else rec["station2"][src]
+            rec["term1"][dst] = -rec["term1"][src] if flip else rec["term1"][src]
+    parity.check_normals(oracle, gpu_lib, 80, 240, 6, mutate=mutate, leaf_stations=12)
+
+
 @pytest.mark.parametrize("n,m,seed,leaf", [(100, 300, 1235, 16), (400, 1200, 5, 8), (1000, 3000, 7, 24), (2000, 6000, 13, 96)])
 def test_nested_dissection_matches_oracle(oracle, gpu_lib, n, m, seed, leaf):
     info = parity.check_against_oracle(oracle, gpu_lib, n, m, seed, leaf_stations=leaf)

@@ -106,6 +106,18 @@ def test_normals_and_rhs(oracle, hostsim_path):
     parity.check_normals(oracle, hostsim_path, 80, 240, 4, leaf_stations=12)
 
 
+def test_repeated_station_pairs(oracle, hostsim_path):
+    # several baselines over the same station pair, in both directions: their off-diagonal block is accumulated
+    # (atomic adds), while pairs observed once are stored — both paths must give the reference's normals
+    def mutate(stn, msr):
+        rec = msr.reshape(-1, 3)
+        for dst, src, flip in ((5, 0, False), (9, 0, True), (30, 12, True)):
+            rec["station1"][dst] = rec["station2"][src] if flip else rec["station1"][src]
+            rec["station2"][dst] = rec["station1"][src] if flip else rec["station2"][src]
+            rec["term1"][dst] = -rec["term1"][src] if flip else rec["term1"][src]
+    parity.check_normals(oracle, hostsim_path, 80, 240, 6, mutate=mutate, leaf_stations=12)
+
+
 def test_small_workspace_forces_chunks(oracle, hostsim_path):
     # a tight inverse workspace makes every level run in several chunks; results must not change
     parity.check_against_oracle(oracle, hostsim_path, 400, 1200, 5, leaf_stations=8, workspace_gb=2.0e-4)
