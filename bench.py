@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "ms_per_lsq_iteration"
 UNIT = "ms"
-BYTES_PER_BASELINE = 944   # 3*208 records + 8 plan words + 48 station XYZ + 27*8 block updates + 48 rhs (DESIGN.md)
+BYTES_PER_BASELINE = 944   # 3*208 records + 8 plan words + 48 station XYZ + 27*8 block updates + 48 rhs (DESIGN.md §4)
 
 WORKLOADS = {
     # name: (synth config, engine options)
@@ -39,12 +39,13 @@ WORKLOADS = {
 }
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture of this workload
+def ncu_traffic(*kernels):
+    """DRAM bytes per launch of the named kernel(s), summed, from the committed ncu capture of this workload
     (profiles/r1_ncu_dram_traffic_c4.json: dram__bytes_read.sum + dram__bytes_write.sum, C4 on one GPU)."""
     p = os.path.join(ROOT, "profiles", "r1_ncu_dram_traffic_c4.json")
     try:
-        return float(json.load(open(p))["kernels"][kernel]["dram_bytes_per_launch"])
+        k = json.load(open(p))["kernels"]
+        return float(sum(k[name]["dram_bytes_per_launch"] for name in kernels))
     except (OSError, KeyError, ValueError):
         return None
 
@@ -300,11 +301,11 @@ def run_engine(args):
                     kernel_ms_per_step=gemm_ms, kernel_share_of_step=gemm_ms / ms_step,
                     launches_per_step=prof.gemm_launches / args.steps)
     asm_ms = prof.ms_assemble / args.steps
-    roofline_asm = dict(bound="hbm", kernel="assemble_g_kernel", achieved=info.nbaselines * BYTES_PER_BASELINE / asm_ms / 1e6,
+    roofline_asm = dict(bound="hbm", kernel="init_normals_kernel + assemble_g_kernel + station_sum_kernel (the assembly pass)", achieved=info.nbaselines * BYTES_PER_BASELINE / asm_ms / 1e6,
                         peak=peaks["hbm_gbs"], unit="GB/s", peak_source=peaks_kind,
                         frac=info.nbaselines * BYTES_PER_BASELINE / asm_ms / 1e6 / peaks["hbm_gbs"],
                         bytes_per_baseline=BYTES_PER_BASELINE, kernel_ms_per_step=asm_ms,
-                        traffic=ncu_traffic("assemble_g_kernel") if args.workload == "C4" else None)
+                        traffic=ncu_traffic("init_normals_kernel", "assemble_g_kernel", "station_sum_kernel") if args.workload == "C4" else None)
     line = dict(metric=METRIC, value=ms_step, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_step, higher_is_better=False, scaling="strong", vs_baseline=None, dtype="f64",
                 data="synthetic",
