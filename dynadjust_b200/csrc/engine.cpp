@@ -1039,7 +1039,7 @@ int gadj_prepare(gadj_ctx* c)
     build_rowidx(S, c->plan);
     std::vector<double> z;
     bool ok = true;
-    ok &= c->d_msr.resize(c->nmsr);
+    ok &= c->d_msr.resize(c->nmsr + 64);   // slack: sharded uploads gather equal chunks of ceil(nmsr / ranks) records
     ok &= c->d_first.upload(c->first);
     ok &= c->d_edge.upload(c->edge_word);
     ok &= c->d_binc_ptr.upload(c->binc_ptr);
@@ -1196,6 +1196,17 @@ int gadj_upload_measurements(gadj_ctx* c)
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     dev::h2d(c->d_msr.p, c->msr, c->nmsr * sizeof(dna_msr_t));
+    return 0;
+}
+
+int gadj_upload_measurements_range(gadj_ctx* c, uint64_t first, uint64_t count)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    if (first > c->nmsr || count > c->nmsr - first)
+        return c->fail("measurement record range out of bounds");
+    if (count)
+        dev::h2d(c->d_msr.p + first, c->msr + first, count * sizeof(dna_msr_t));
     return 0;
 }
 
@@ -1546,6 +1557,10 @@ int gadj_mg_buffer(gadj_ctx* c, int which, void** ptr, uint64_t* count)
     case 4:
         *ptr = c->d_info.p;
         *count = c->d_info.n;
+        break;
+    case 5:   // the device copy of the measurement records, in bytes
+        *ptr = c->d_msr.p;
+        *count = c->d_msr.n * sizeof(dna_msr_t);
         break;
     default:
         return c->fail("unknown buffer");

@@ -59,6 +59,7 @@ class GadjProfile(C.Structure):
 
 EXPORTS = ["gadj_default_opts", "gadj_create", "gadj_destroy", "gadj_last_error", "gadj_set_stations",
            "gadj_set_measurements", "gadj_set_blocks", "gadj_prepare", "gadj_get_info", "gadj_upload_measurements",
+           "gadj_upload_measurements_range",
            "gadj_reset_estimates", "gadj_iterate", "gadj_form_inverse", "gadj_adjust", "gadj_statistics", "gadj_get_estimates",
            "gadj_get_corrections", "gadj_get_station_vcvs", "gadj_get_station_vcv", "gadj_get_vcv_block",
            "gadj_get_normals_block", "gadj_get_rhs", "gadj_profile_enable", "gadj_profile_read", "gadj_test_gemm",
@@ -89,6 +90,7 @@ def load_library(path=None):
     L.gadj_prepare.argtypes = [vp]
     L.gadj_get_info.argtypes = [vp, C.POINTER(GadjInfo)]
     L.gadj_upload_measurements.argtypes = [vp]
+    L.gadj_upload_measurements_range.argtypes = [vp, C.c_uint64, C.c_uint64]
     L.gadj_reset_estimates.argtypes = [vp]
     L.gadj_iterate.argtypes = [vp, i32, C.POINTER(GadjIterResult)]
     L.gadj_adjust.argtypes = [vp, C.POINTER(GadjIterResult)]

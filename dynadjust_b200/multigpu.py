@@ -26,7 +26,7 @@ import torch.distributed as dist
 from . import engine
 
 PH_FACTOR, PH_FORWARD, PH_BACKWARD, PH_INVERSE = 0, 1, 2, 3
-BUF_X, BUF_PANELS, BUF_STATION_VCV, BUF_EDGE_VCV, BUF_INFO = 0, 1, 2, 3, 4
+BUF_X, BUF_PANELS, BUF_STATION_VCV, BUF_EDGE_VCV, BUF_INFO, BUF_MSR = 0, 1, 2, 3, 4, 5
 
 
 class _CudaView:
@@ -56,10 +56,10 @@ class ShardedAdjustment(engine.Adjustment):
         self._check(self.L.gadj_mg_buffer(self.h, which, C.byref(ptr), C.byref(cnt)))
         n = cnt.value
         if self.cuda:
-            ts = "<f8" if dtype == torch.float64 else "<i4"
+            ts = {torch.float64: "<f8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
             t = torch.as_tensor(_CudaView(ptr.value, n, ts), device=torch.device("cuda", torch.cuda.current_device()))
         else:
-            ct = C.c_double if dtype == torch.float64 else C.c_int32
+            ct = {torch.float64: C.c_double, torch.int32: C.c_int32, torch.uint8: C.c_uint8}[dtype]
             arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,))
             t = torch.from_numpy(arr)
         self._bufs[which] = t
@@ -96,6 +96,27 @@ class ShardedAdjustment(engine.Adjustment):
         self._bufs.clear()
         self._tops.clear()
         return info
+
+    def upload_measurements(self):
+        """Host -> device copy of the measurement records, sharded: every rank copies 1/world of the list over its own
+        PCIe link and the device copies are all-gathered over NVLink (each rank assembles from the whole list)."""
+        n = len(self.msr)
+        chunk = -(-n // self.world)
+        first = min(n, self.rank * chunk)
+        self._check(self.L.gadj_upload_measurements_range(self.h, first, min(chunk, n - first)))
+        self._lib_sync()
+        buf = self._buffer(BUF_MSR, torch.uint8)
+        rec = self.msr.dtype.itemsize
+        whole = buf[:self.world * chunk * rec]
+        mine = whole[self.rank * chunk * rec:(self.rank + 1) * chunk * rec]
+        if self.cuda:
+            dist.all_gather_into_tensor(whole, mine)
+        else:
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(parts, mine.clone())
+            for r, p in enumerate(parts):
+                whole[r * chunk * rec:(r + 1) * chunk * rec] = p
+        self._torch_sync()
 
     def _run_phase(self, phase, exchange, before):
         """Run one phase; `exchange(level)` is called at every sync marker.  `before`: the marker precedes the

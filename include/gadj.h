@@ -127,6 +127,8 @@ int gadj_get_info(const gadj_ctx* c, gadj_info* info);
 
 /* re-send the host measurement records / a-priori station coordinates to the device */
 int gadj_upload_measurements(gadj_ctx* c);
+/* same for records [first, first + count): one rank's share of a sharded upload (the ranks then all-gather the device copies) */
+int gadj_upload_measurements_range(gadj_ctx* c, uint64_t first, uint64_t count);
 int gadj_reset_estimates(gadj_ctx* c);
 
 int gadj_iterate(gadj_ctx* c, int flags, gadj_iter_result* res);

@@ -18,6 +18,11 @@ def main():
     stn, msr, _, _ = synth.gnss_network(n, m, seed)
     adj = multigpu.ShardedAdjustment(stn, msr, rank, world, lib_path=lib, leaf_stations=leaf)
     info = adj.prepare()
+    # wipe the device copy of the records, then restore it by the sharded upload (each rank copies 1/world of the list,
+    # the device copies are all-gathered): the adjustment below is only right if every rank got the whole list back
+    import torch
+    adj._buffer(multigpu.BUF_MSR, torch.uint8).zero_()
+    adj.upload_measurements()
     last = adj.adjust()
     st = adj.statistics(write_back=True)
     est = adj.estimates()
