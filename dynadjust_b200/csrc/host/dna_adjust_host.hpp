@@ -3,7 +3,8 @@
 // dynadjust/dynadjust/dnaadjust/dnaadjust.hpp:212-1362 (PrepareAdjustment :260, AdjustNetwork :405,
 // GenerateStatistics :259, getters :336-354) and the wrapper's call order (dnaadjustwrapper.cpp:1142-1432);
 // the text outputs follow dnaadjust_printer.cpp (header :3436-3599, iteration block :70-92, statistics :660-719,
-// adjusted measurements, adjusted stations :3917-4070).
+// adjusted measurements, adjusted stations :3917-4070, positional uncertainty :2665-2770 / :4290-4470, station
+// corrections :1349-1408 / :4146-4288).
 #pragma once
 #include <chrono>
 #include <cmath>
@@ -16,6 +17,7 @@
 #include <vector>
 
 #include "../../../include/gadj.h"
+#include "../geodesy.h"
 #include "dna_files.hpp"
 
 namespace dynadjust_b200 {
@@ -32,6 +34,10 @@ struct adjust_settings {            // the fields of project_settings.a / .g / .
     double free_std_dev = 10.0, fixed_std_dev = 1.0e-6, confidence_interval = 95.0;
     bool scale_normals_to_unity = false;
     bool output_adj_msr = false;
+    bool output_pos_uncertainty = false;   // --output-pos-uncertainty: <net>.<mode>.apu
+    bool output_corrections = false;       // --output-corrections-file: <net>.<mode>.cor
+    bool apu_vcv_enu = false;              // --output-apu-vcv-units ENU (default XYZ)
+    double hz_corr_threshold = 0.0, vt_corr_threshold = 0.0;   // dnaoptions.hpp:510
     bool update_binary_files = true;
     std::string command_line;
 };
@@ -77,10 +83,13 @@ class dna_adjust {
         check(gadj_prepare(ctx_));
         gadj_get_info(ctx_, &info_);
         apriori_llh_.resize(3 * stn_.size());
+        apriori_xyz_.resize(3 * stn_.size());   // v_originalStations_ (ADJ:632-693)
+        const gadj::Ellipsoid ell = gadj::make_ellipsoid(o.semi_major, o.inv_flattening);
         for (size_t i = 0; i < stn_.size(); ++i) {
             apriori_llh_[3 * i] = stn_[i].currentLatitude;
             apriori_llh_[3 * i + 1] = stn_[i].currentLongitude;
             apriori_llh_[3 * i + 2] = stn_[i].currentHeight;
+            gadj::geo_to_cart(ell, stn_[i].currentLatitude, stn_[i].currentLongitude, stn_[i].currentHeight, &apriori_xyz_[3 * i]);
         }
     }
 
@@ -157,6 +166,99 @@ class dna_adjust {
         std::ofstream xyz(stem + ".xyz");
         PrintOutputFileHeaderInfo(xyz, "DYNADJUST COORDINATE OUTPUT FILE", stem + ".xyz");
         PrintAdjStations(xyz);
+        if (a_.output_pos_uncertainty)
+            PrintPositionalUncertainty(stem + ".apu");
+        if (a_.output_corrections)
+            PrintNetworkStationCorrections(stem + ".cor");
+    }
+
+    // ---- .apu (PrintPositionalUncertainty PRN:2665-2770, PrintPosUncertainty PRN:4326-4432) -------------------------
+    // Per station: horizontal / vertical positional uncertainty at 95 %, 1-sigma error ellipse, and the upper triangle
+    // of its 3x3 variance block (XYZ or ENU).  Stations are listed as one block (the reference's layout for
+    // simultaneous adjustments and for phased ones without --output-stn-blocks).
+    void PrintPositionalUncertainty(const std::string& file) const
+    {
+        std::ofstream os(file);
+        PrintStationFileHeader(os, "POSITIONAL UNCERTAINTY", file);
+        auto var = [&](const char* n, const std::string& v) { os << std::left << std::setw(35) << n << v << "\n"; };
+        var("PU confidence interval:", "95.0%");
+        var("Error ellipse axes:", "68.3% (1 sigma)");
+        var("Variances:", "68.3% (1 sigma)");
+        var("Stations printed in blocks:", "No");
+        var("Variance matrix units:", a_.apu_vcv_enu ? "ENU" : "XYZ");
+        var("Full covariance matrix:", "No");
+        os << std::string(80, '-') << "\n\n";
+        os << "Positional uncertainty of adjusted station coordinates\n";
+        os << "------------------------------------------------------\n\n";
+        char buf[512];
+        const char* vn = a_.apu_vcv_enu ? "enu" : "XYZ";
+        char v1[16], v2[16], v3[16];
+        snprintf(v1, sizeof(v1), "Variance(%c)", vn[0]);
+        snprintf(v2, sizeof(v2), "Variance(%c)", vn[1]);
+        if (a_.apu_vcv_enu)
+            snprintf(v3, sizeof(v3), "Variance(up)");
+        else
+            snprintf(v3, sizeof(v3), "Variance(Z)");
+        snprintf(buf, sizeof(buf), "%-20s%2s%14s%15s%11s%11s%13s%13s%13s%19s%19s%19s", "Station", "", "Latitude", "Longitude", "Hz PosU",
+                 "Vt PosU", "Semi-major", "Semi-minor", "Orientation", v1, v2, v3);
+        os << buf << "\n" << std::string(20 + 2 + 14 + 15 + 11 + 11 + 13 + 13 + 13 + 19 + 19 + 19, '-') << "\n";
+        const int pad = 20 + 2 + 14 + 15 + 11 + 11 + 13 + 13 + 13;
+        for (size_t i = 0; i < stn_.size(); ++i) {
+            const dna_stn_t& s = stn_[i];
+            const double* q = &vcv_[9 * i];
+            double ql[9];
+            to_local(q, s.currentLatitude, s.currentLongitude, ql);
+            double smaj, smin, az, hz, vt;
+            ErrorEllipseParameters(ql, smaj, smin, az);
+            PositionalUncertainty(smaj, smin, std::sqrt(std::fabs(ql[8])), hz, vt);
+            const double* v = a_.apu_vcv_enu ? ql : q;
+            snprintf(buf, sizeof(buf), "%-20s%2s%14.9f%15.9f%11.4f%11.4f%13.4f%13.4f%13.4f%19.9e%19.9e%19.9e", s.stationName, "",
+                     rad_to_dms(s.currentLatitude), rad_to_dms(s.currentLongitude), hz, vt, smaj, smin, rad_to_dms(az), v[0], v[1], v[2]);
+            os << buf << "\n";
+            snprintf(buf, sizeof(buf), "%*s%19.9e%19.9e", pad + 19, "", v[4], v[5]);
+            os << buf << "\n";
+            snprintf(buf, sizeof(buf), "%*s%19.9e", pad + 38, "", v[8]);
+            os << buf << "\n";
+        }
+    }
+
+    // ---- .cor (PrintNetworkStationCorrections PRN:1349-1408, PrintCorStation PRN:4146-4230) -----------------------------
+    // Per station: azimuth, vertical angle, slope and horizontal distance of the shift a-priori -> adjusted position and
+    // its local e / n / up components; stations inside both thresholds are left out.
+    void PrintNetworkStationCorrections(const std::string& file) const
+    {
+        std::ofstream os(file);
+        PrintStationFileHeader(os, "CORRECTIONS", file);
+        os << std::left << std::setw(35) << "Stations printed in blocks:" << "No\n" << std::string(80, '-') << "\n\n";
+        os << "Corrections to stations\n------------------------------------------\n\n";
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%-20s%2s%19s%19s%19s%19s%11s%11s%11s", "Station", "", "Azimuth", "V. Angle", "S. Distance", "H. Distance",
+                 "east", "north", "up");
+        os << buf << "\n" << std::string(20 + 2 + 4 * 19 + 3 * 11, '-') << "\n";
+        for (size_t i = 0; i < stn_.size(); ++i) {
+            const dna_stn_t& s = stn_[i];
+            const double d[3] = {est_[3 * i] - apriori_xyz_[3 * i], est_[3 * i + 1] - apriori_xyz_[3 * i + 1],
+                                 est_[3 * i + 2] - apriori_xyz_[3 * i + 2]};
+            const double lat = s.currentLatitude, lon = s.currentLongitude;   // the adjusted position, as in the reference
+            const double e = -std::sin(lon) * d[0] + std::cos(lon) * d[1];
+            const double n = -std::sin(lat) * std::cos(lon) * d[0] - std::sin(lat) * std::sin(lon) * d[1] + std::cos(lat) * d[2];
+            const double u = std::cos(lat) * std::cos(lon) * d[0] + std::cos(lat) * std::sin(lon) * d[1] + std::sin(lat) * d[2];
+            const bool tiny = std::fabs(e) < 1e-5 && std::fabs(n) < 1e-5;
+            double va = std::atan2(u, std::sqrt(e * e + n * n));
+            if (tiny && std::fabs(u) < 1e-5)
+                va = 0.0;
+            if (std::fabs(u) < a_.vt_corr_threshold)
+                continue;
+            const double hd = std::sqrt(e * e + n * n);
+            if (hd < a_.hz_corr_threshold)
+                continue;
+            double az = tiny ? 0.0 : direction_en(e, n);
+            const double sd = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            snprintf(buf, sizeof(buf), "%-20s%2s%19s%19s%19.4f%19.4f%11.4f%11.4f%11.4f", s.stationName, "",
+                     FormatDmsString(rad_to_dms(az)).c_str(), FormatDmsString(rad_to_dms(va)).c_str(), sd, hd, e, n, u);
+            os << buf << "\n";
+        }
+        os << "\n";
     }
 
     // UpdateBinaryFiles (ADJ:445-470): adjusted coordinates / statistics back to .bst/.bms with reduced = true
@@ -281,6 +383,105 @@ class dna_adjust {
         chiUpper_ = chi2_quantile(1 - conf, dof) / dof;
         chiLower_ = chi2_quantile(conf, dof) / dof;
         passFail_ = stats_.sigma_zero < chiLower_ ? 1 : (stats_.sigma_zero > chiUpper_ ? 2 : 0);
+    }
+
+    // RadtoDms / DegtoDms (dnatemplatecalcfuncs.hpp:206-222, 283-288): ddd.mmssss as a number
+    static double rad_to_dms(double rad)
+    {
+        const double deg = rad * 180.0 / 3.14159265358979323846;
+        double v = std::fabs(deg);
+        const double d = std::floor(v);
+        double m = std::floor((v - d) * 60.0);
+        double s = (v - d - m / 60.0) * 3600.0;
+        if (std::fabs(s - 60.0) < 0.000000001) {
+            s = 0.0;
+            m += 1.0;
+        }
+        v = d + m / 100.0 + s / 10000.0;
+        return deg < 0.0 ? -v : v;
+    }
+    // FormatDmsString(dms, 4, withSpaces, no symbols) (dnatemplatefuncs.hpp:253-310): "ddd mm ss"
+    static std::string FormatDmsString(double dms)
+    {
+        char b[64];
+        snprintf(b, sizeof(b), "%.4f", dms);
+        std::string t(b);
+        size_t dot = t.find('.');
+        if (dot == std::string::npos)
+            return t;
+        t.replace(dot, 1, " ");
+        t.insert(dot + 3, " ");
+        return t;
+    }
+    // atan_2 / Direction (dnatemplatecalcfuncs.hpp:350-362, dnatemplategeodesyfuncs.hpp:679-693)
+    static double atan_2(double x, double y)
+    {
+        const double t = std::atan(x / y);
+        if (y < 0)
+            return t + 3.14159265358979323846;
+        return x > 0 ? t : t + 2 * 3.14159265358979323846;
+    }
+    static double direction_en(double e, double n)
+    {
+        double d = std::fabs(e) < std::fabs(n) ? atan_2(e, n) : 3.14159265358979323846 / 2 - atan_2(n, e);
+        if (d < 0)
+            d += 2 * 3.14159265358979323846;
+        return d;
+    }
+    // V_local = R^T V_cart R with R = local (e, n, up) -> Cartesian at (lat, lon)  (PropagateVariances_LocalCart, MFN:592-621)
+    static void to_local(const double* q, double lat, double lon, double* out)
+    {
+        const double sl = std::sin(lat), cl = std::cos(lat), so = std::sin(lon), co = std::cos(lon);
+        const double R[3][3] = {{-so, -sl * co, cl * co}, {co, -sl * so, cl * so}, {0, cl, sl}};
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+                double v = 0;
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j)
+                        v += R[i][a] * q[3 * i + j] * R[j][b];
+                out[3 * a + b] = v;
+            }
+    }
+    // ErrorEllipseParameters (MFN:840-891) on the local e / n block
+    static void ErrorEllipseParameters(const double* ql, double& smaj, double& smin, double& az)
+    {
+        smaj = smin = az = -1.;
+        const double e2 = ql[0], n2 = ql[4], en = ql[1];
+        double W = (e2 - n2) * (e2 - n2) + 4. * en * en;
+        if (W < 0.0) {
+            if (std::fabs(W) > 1e-15)
+                return;
+            W = 0.0;
+        }
+        const double a2 = 0.5 * (e2 + n2 + std::sqrt(W)), b2 = 0.5 * (e2 + n2 - std::sqrt(W));
+        if (a2 < 0.0 || b2 < 0.0)
+            return;
+        smaj = std::sqrt(a2);
+        smin = std::sqrt(b2);
+        if (std::fabs(e2 - n2) < 1e-25)
+            az = en < 1e-25 ? 0. : 3.14159265358979323846 / 4.;
+        else
+            az = 0.5 * atan_2(en + en, n2 - e2);
+    }
+    // PositionalUncertainty (MFN:808-826; coefficients dnaconsts.hpp:105-108)
+    static void PositionalUncertainty(double smaj, double smin, double sd_ht, double& hz, double& vt)
+    {
+        hz = vt = -1.;
+        if (smaj < 0.0 || smin < 0.0)
+            return;
+        const double c = smin / smaj;
+        hz = smaj * (1.96079 + 0.004071 * c + 0.114276 * c * c + 0.371625 * c * c * c);
+        vt = sd_ht * 1.96;
+    }
+    // print_file_header + file name (dnaiostreamfuncs.hpp:115-141, PRN:1156-1162)
+    void PrintStationFileHeader(std::ostream& os, const char* type, const std::string& file) const
+    {
+        auto var = [&](const char* n, const std::string& v) { os << std::left << std::setw(35) << n << v << "\n"; };
+        os << std::string(80, '-') << "\nDYNADJUST " << type << " OUTPUT FILE\n\n";
+        var("Version:", "b200-geodetic-adjust 0.1 (libgadj, sm_100a)");
+        var("Build:", std::string(__DATE__) + ", " + __TIME__);
+        var("File name:", file);
+        os << "\n";
     }
 
     static std::string hp_dms(double rad)
@@ -465,7 +666,7 @@ class dna_adjust {
     dnafiles::Segmentation seg_;
     std::string bst_file_, bms_file_;
     std::vector<gadj_iter_result> iterations_;
-    std::vector<double> est_, vcv_, apriori_llh_;
+    std::vector<double> est_, vcv_, apriori_llh_, apriori_xyz_;
     double maxCorr_ = 0, total_ms_ = 0, chiUpper_ = 0, chiLower_ = 0;
     int passFail_ = 0;
     ADJUST_STATUS adjustStatus_ = ADJUST_SUCCESS;

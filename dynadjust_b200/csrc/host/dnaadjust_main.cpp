@@ -27,7 +27,8 @@ const Flag kFlags[] = {
     {"free-stn-sd", true}, {"fixed-stn-sd", true}, {"scale-normals-to-unity", false},
     {"create-stage-files", false}, {"purge-stage-files", false}, {"stage-path", true}, {"max-threads", true},
     {"input-folder", true}, {"output-folder", true}, {"output-adj-msr", false}, {"output-pos-uncertainty", false},
-    {"output-all-covariances", false}, {"network-name", true}, {"quiet", false}, {"verbose-level", true},
+    {"output-all-covariances", false}, {"output-corrections-file", false}, {"output-apu-vcv-units", true},
+    {"hz-corr-threshold", true}, {"vt-corr-threshold", true}, {"network-name", true}, {"quiet", false}, {"verbose-level", true},
     {"no-binary-update", false}, {"help", false},
 };
 
@@ -119,6 +120,21 @@ int main(int argc, char** argv)
             s.output_folder = value;
         else if (n == "output-adj-msr")
             s.output_adj_msr = true;
+        else if (n == "output-pos-uncertainty")
+            s.output_pos_uncertainty = true;
+        else if (n == "output-corrections-file")
+            s.output_corrections = true;
+        else if (n == "output-apu-vcv-units")
+            s.apu_vcv_enu = value == "ENU" || value == "enu" || value == "1";
+        else if (n == "hz-corr-threshold")
+            s.hz_corr_threshold = std::atof(value.c_str());
+        else if (n == "vt-corr-threshold")
+            s.vt_corr_threshold = std::atof(value.c_str());
+        else if (n == "output-all-covariances") {
+            std::cerr << "- Error: --output-all-covariances needs the dense block variance matrix; this build keeps N^-1 on the "
+                         "sparsity pattern of the factor only (station blocks and measured pairs).\n";
+            return EXIT_FAILURE;
+        }
         else if (n == "network-name")
             s.network_name = value;
         else if (n == "quiet")

@@ -134,6 +134,80 @@ def _phased(exe, oracle, tmp_path):
     assert not meta["reduced"]
 
 
+def _dms_to_rad(v):
+    """ddd.mmssss (the reference's printed angle format) -> radians"""
+    a = abs(v)
+    d = np.floor(a + 1e-9)
+    m = np.floor((a - d) * 100 + 1e-7)
+    sec = ((a - d) * 100 - m) * 100
+    return np.sign(v) * np.radians(d + m / 60 + sec / 3600)
+
+
+def _apu_cor(exe, oracle, tmp_path):
+    """--output-pos-uncertainty / --output-corrections-file: the .apu and .cor tables against the
+    same quantities computed here from the oracle's VCV and estimates (PRN:4326-4432, PRN:4146-4230)."""
+    stn, msr, _, _ = synth.gnss_network(60, 170, 33)
+    _write_network(tmp_path, "pu", stn, msr)
+    r = _run(exe, tmp_path, "pu", "--output-pos-uncertainty", "--output-corrections-file", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    stn_o, msr_o = stn.copy(), msr.copy()
+    ref = oracle.adjust_simultaneous(stn_o, msr_o, want_vcv=True)
+    V, est = ref["vcv"], ref["est"].reshape(-1, 3)
+    apu = open(os.path.join(tmp_path, "pu.simult.apu")).read()
+    assert "DYNADJUST POSITIONAL UNCERTAINTY OUTPUT FILE" in apu and "Variance matrix units:" in apu
+    body = apu.split("Positional uncertainty of adjusted station coordinates")[1].splitlines()
+    rows = [l.split() for l in body if l[:1].isalnum() and not l.startswith("Station")]
+    assert len(rows) == len(stn)
+    x0 = synth.geo_to_cart(stn["currentLatitude"], stn["currentLongitude"], stn["currentHeight"])
+    for i, f in enumerate(rows):
+        assert f[0] == stn["stationName"][i].decode()
+        lat, lon = stn_o["currentLatitude"][i], stn_o["currentLongitude"][i]
+        assert abs(_dms_to_rad(float(f[1])) - lat) < 1e-9 and abs(_dms_to_rad(float(f[2])) - lon) < 1e-9
+        sl, cl, so, co = np.sin(lat), np.cos(lat), np.sin(lon), np.cos(lon)
+        R = np.array([[-so, -sl * co, cl * co], [co, -sl * so, cl * so], [0, cl, sl]])
+        q = V[3 * i:3 * i + 3, 3 * i:3 * i + 3]
+        ql = R.T @ q @ R
+        ev = np.linalg.eigvalsh(ql[:2, :2])
+        smaj, smin = np.sqrt(ev[1]), np.sqrt(ev[0])
+        c = smin / smaj
+        hz = smaj * (1.96079 + 0.004071 * c + 0.114276 * c * c + 0.371625 * c ** 3)
+        vt = 1.96 * np.sqrt(ql[2, 2])
+        got = [float(x) for x in f[3:7]]
+        assert np.abs(np.array(got) - [hz, vt, smaj, smin]).max() < 1e-4
+        # orientation of the semi-major axis: the eigenvector of the e/n block, as an azimuth from north
+        w, vec = np.linalg.eigh(ql[:2, :2])
+        az = np.arctan2(vec[0, 1], vec[1, 1]) % np.pi
+        assert min(abs(_dms_to_rad(float(f[7])) % np.pi - az), np.pi - abs(_dms_to_rad(float(f[7])) % np.pi - az)) < 2e-3 or c > 0.98
+        assert np.abs(np.array([float(x) for x in f[8:11]]) - q[0]).max() <= 1e-8 * np.abs(q).max()
+    cor = open(os.path.join(tmp_path, "pu.simult.cor")).read()
+    assert "DYNADJUST CORRECTIONS OUTPUT FILE" in cor
+    crows = [l.split() for l in cor.split("Corrections to stations")[1].splitlines() if l[:1].isalnum() and not l.startswith("Station")]
+    assert len(crows) == len(stn)
+    for i, f in enumerate(crows):
+        lat, lon = stn_o["currentLatitude"][i], stn_o["currentLongitude"][i]
+        sl, cl, so, co = np.sin(lat), np.cos(lat), np.sin(lon), np.cos(lon)
+        R = np.array([[-so, -sl * co, cl * co], [co, -sl * so, cl * so], [0, cl, sl]])
+        enu = R.T @ (est[i] - x0[i])
+        assert np.abs(np.array([float(x) for x in f[-3:]]) - enu).max() < 1e-4        # east north up
+        assert abs(float(f[-5]) - np.linalg.norm(enu)) < 1e-4                          # slope distance
+        assert abs(float(f[-4]) - np.hypot(enu[0], enu[1])) < 1e-4                     # horizontal distance
+        if np.hypot(enu[0], enu[1]) > 1e-3:
+            az = np.degrees(np.arctan2(enu[0], enu[1]) % (2 * np.pi))
+            d, m, sec = (float(x) for x in f[1:4])                                     # "ddd mm ss"
+            assert abs((d + m / 60 + sec / 3600) - az) < 1.5 / 3600 or abs((d + m / 60 + sec / 3600) - az) > 359.99
+    # thresholds drop the small corrections (PRN:4172-4181)
+    r = _run(exe, tmp_path, "pu", "--output-corrections-file", "--hz-corr-threshold", "1000", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    cor = open(os.path.join(tmp_path, "pu.simult.cor")).read()
+    assert not [l for l in cor.split("Corrections to stations")[1].splitlines() if l[:1].isalnum() and not l.startswith("Station")]
+    r = _run(exe, tmp_path, "pu", "--output-all-covariances")
+    assert r.returncode == 1 and "dense block variance matrix" in r.stderr
+
+
+def test_cli_apu_cor_hostsim(cli_hostsim, oracle, tmp_path):
+    _apu_cor(cli_hostsim, oracle, tmp_path)
+
+
 def test_cli_simultaneous_hostsim(cli_hostsim, oracle, tmp_path):
     _simultaneous(cli_hostsim, oracle, tmp_path)
 
@@ -166,3 +240,8 @@ def test_cli_simultaneous_gpu(cli_gpu, oracle, tmp_path):
 @pytest.mark.gpu
 def test_cli_phased_seg_gpu(cli_gpu, oracle, tmp_path):
     _phased(cli_gpu, oracle, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_apu_cor_gpu(cli_gpu, oracle, tmp_path):
+    _apu_cor(cli_gpu, oracle, tmp_path)
