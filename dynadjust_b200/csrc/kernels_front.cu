@@ -4,17 +4,18 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "kernels.h"
 
 namespace gadj {
 namespace {
 
-constexpr int DP = NB + 1;  // shared-memory pitch (doubles): conflict-free for row- and column-wise walks
-
 // ---- pivot tile: L = chol(D), W = L^-1 ----------------------------------------------
-// One CTA (256 threads) per tile, the tile held in shared memory (pitch 129: conflict-free row and column walks)
-// and padded to 128 x 128 with an identity so that every step runs on full blocks.
+// One CTA (256 threads) per tile.  Only the lower triangle is ever needed, so the tile lives in shared memory in
+// packed form (row i at offset i(i+1)/2: 66 KB instead of 132 KB) and three CTAs share an SM — the kernel is bound
+// by barrier and shared-memory latency, not by arithmetic, so co-resident tiles are what fills the SM.  The tile is
+// padded to 128 x 128 with an identity so that every step runs on full blocks.
 //   factor : blocked right-looking Cholesky, panel width 16.  Panel: one thread per row keeps its 16 panel
 //            entries in registers (two barriers per column); trailing update: 4 x 4 register tiles over all
 //            256 threads, rank-16 per step.
@@ -23,8 +24,17 @@ constexpr int DP = NB + 1;  // shared-memory pitch (doubles): conflict-free for 
 //            W21 = -W22 (L21 W11) as two register-tiled products per level.
 constexpr int DIAG_THREADS = 256;
 constexpr int PBW = 16;
+constexpr int TRI_DOUBLES = NB * (NB + 1) / 2;
 
-// acc[x][y] += sum_k P[(pr + ti + tstride x) * DP + pc + k] * Q[(qr + k) * DP + qc + tj + tstride y],  k in [0, kn)
+__device__ __forceinline__ int tri(int i, int j) { return ((i * (i + 1)) >> 1) + j; }            // j <= i
+__device__ __forceinline__ double tri_ld(const double* __restrict__ S, int i, int j)              // zero above the diagonal
+{
+    return j <= i ? S[tri(i, j)] : 0.0;
+}
+
+// acc[x][y] += sum_k P(prow + ti + tstride x, pcol + k) * Q(qrow + k, qcol + tj + tstride y),  k in [0, kn);
+// PTRI / QTRI: the operand block sits on the diagonal (lower triangular: entries above it read as zero)
+template <bool PTRI, bool QTRI>
 __device__ __forceinline__ void tile_mm(const double* __restrict__ S, int prow, int pcol, int qrow, int qcol, int ti, int tj,
                                         int tstride, int kn, double acc[4][4])
 {
@@ -33,10 +43,10 @@ __device__ __forceinline__ void tile_mm(const double* __restrict__ S, int prow, 
         double a[4], b[4];
 #pragma unroll
         for (int x = 0; x < 4; ++x)
-            a[x] = S[(prow + ti + tstride * x) * DP + pcol + k];
+            a[x] = PTRI ? tri_ld(S, prow + ti + tstride * x, pcol + k) : S[tri(prow + ti + tstride * x, pcol + k)];
 #pragma unroll
         for (int y = 0; y < 4; ++y)
-            b[y] = S[(qrow + k) * DP + qcol + tj + tstride * y];
+            b[y] = QTRI ? tri_ld(S, qrow + k, qcol + tj + tstride * y) : S[tri(qrow + k, qcol + tj + tstride * y)];
 #pragma unroll
         for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -45,7 +55,8 @@ __device__ __forceinline__ void tile_mm(const double* __restrict__ S, int prow, 
     }
 }
 
-__global__ void __launch_bounds__(DIAG_THREADS, 1) diag_kernel(const DiagOp* __restrict__ ops, int* __restrict__ info)
+template <int CTAS_PER_SM>
+__global__ void __launch_bounds__(DIAG_THREADS, CTAS_PER_SM) diag_kernel(const DiagOp* __restrict__ ops, int* __restrict__ info)
 {
     extern __shared__ double S[];
     __shared__ double colbuf[PBW];
@@ -57,10 +68,8 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) diag_kernel(const DiagOp* __r
     // coalesced load of the lower triangle (row-major source); identity padding
     for (int idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
         const int i = idx >> 7, j = idx & (NB - 1);
-        double v = (i == j) ? 1.0 : 0.0;
-        if (i < w && j <= i)
-            v = op.D[i * ld + j];
-        S[i * DP + j] = v;
+        if (j <= i)
+            S[tri(i, j)] = i < w ? op.D[i * ld + j] : (i == j ? 1.0 : 0.0);
     }
     __syncthreads();
     if (op.factor) {
@@ -72,7 +81,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) diag_kernel(const DiagOp* __r
             if (act) {
 #pragma unroll
                 for (int kk = 0; kk < PBW; ++kk)
-                    r[kk] = S[i * DP + p0 + kk];
+                    r[kk] = tri_ld(S, i, p0 + kk);
             }
 #pragma unroll
             for (int jj = 0; jj < PBW; ++jj) {
@@ -105,7 +114,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) diag_kernel(const DiagOp* __r
 #pragma unroll
                 for (int kk = 0; kk < PBW; ++kk)
                     if (p0 + kk <= i)
-                        S[i * DP + p0 + kk] = r[kk];
+                        S[tri(i, p0 + kk)] = r[kk];
             }
             __syncthreads();
             // ---- trailing update: S[i][k] -= sum_jj S[i][p0+jj] S[k][p0+jj] for rows / columns >= p0 + 16
@@ -120,10 +129,10 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) diag_kernel(const DiagOp* __r
                         double a[4], b[4];
 #pragma unroll
                         for (int x = 0; x < 4; ++x)
-                            a[x] = S[(t0 + ti + nt * x) * DP + p0 + k];
+                            a[x] = S[tri(t0 + ti + nt * x, p0 + k)];
 #pragma unroll
                         for (int y = 0; y < 4; ++y)
-                            b[y] = S[(t0 + tj + nt * y) * DP + p0 + k];
+                            b[y] = S[tri(t0 + tj + nt * y, p0 + k)];
 #pragma unroll
                         for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) diag_kernel(const DiagOp* __r
                         for (int y = 0; y < 4; ++y) {
                             const int ii = t0 + ti + nt * x, kk = t0 + tj + nt * y;
                             if (kk <= ii)
-                                S[ii * DP + kk] -= acc[x][y];
+                                S[tri(ii, kk)] -= acc[x][y];
                         }
                 }
             }
@@ -145,7 +154,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) diag_kernel(const DiagOp* __r
         for (int idx = tid; idx < w * w; idx += DIAG_THREADS) {
             const int i = idx / w, j = idx - i * w;
             if (j <= i)
-                op.D[i * ld + j] = S[i * DP + j];
+                op.D[i * ld + j] = S[tri(i, j)];
         }
     }
     if (op.W == nullptr && op.Wt == nullptr)
@@ -162,8 +171,8 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) diag_kernel(const DiagOp* __r
                 double s = 0.0;
 #pragma unroll
                 for (int k = 0; k < i; ++k)
-                    s += S[(base + i) * DP + base + k] * x[k];
-                const double dii = S[(base + i) * DP + base + i];
+                    s += S[tri(base + i, base + k)] * x[k];
+                const double dii = S[tri(base + i, base + i)];
                 x[i] = (i < c) ? 0.0 : (i == c ? 1.0 / dii : -s / dii);
             }
         }
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) diag_kernel(const DiagOp* __r
 #pragma unroll
             for (int i = 0; i < PBW; ++i)
                 if (i >= c)
-                    S[(base + i) * DP + base + c] = x[i];
+                    S[tri(base + i, base + c)] = x[i];
         }
         __syncthreads();
     }
@@ -185,36 +194,36 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) diag_kernel(const DiagOp* __r
         const bool act = r0 + b < wpad;
         double acc[4][4] = {};
         if (act)
-            tile_mm(S, r0 + b, r0, r0, r0, ti, tj, q4, b, acc);            // T = L21 W11
+            tile_mm<false, true>(S, r0 + b, r0, r0, r0, ti, tj, q4, b, acc);            // T = L21 W11
         __syncthreads();
         if (act) {
 #pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y) {
-                    S[(r0 + b + ti + q4 * x) * DP + r0 + tj + q4 * y] = acc[x][y];
+                    S[tri(r0 + b + ti + q4 * x, r0 + tj + q4 * y)] = acc[x][y];
                     acc[x][y] = 0.0;
                 }
         }
         __syncthreads();
         if (act)
-            tile_mm(S, r0 + b, r0 + b, r0 + b, r0, ti, tj, q4, b, acc);    // W22 T
+            tile_mm<true, false>(S, r0 + b, r0 + b, r0 + b, r0, ti, tj, q4, b, acc);    // W22 T
         __syncthreads();
         if (act) {
 #pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y)
-                    S[(r0 + b + ti + q4 * x) * DP + r0 + tj + q4 * y] = -acc[x][y];
+                    S[tri(r0 + b + ti + q4 * x, r0 + tj + q4 * y)] = -acc[x][y];
         }
         __syncthreads();
     }
     for (int idx = tid; idx < w * w; idx += DIAG_THREADS) {
         const int i = idx / w, j = idx - i * w;
         if (op.W)
-            op.W[i * op.ldw + j] = (j <= i) ? S[i * DP + j] : 0.0;     // W[i][j] (row-major, lower)
+            op.W[i * op.ldw + j] = (j <= i) ? S[tri(i, j)] : 0.0;     // W[i][j] (row-major, lower)
         if (op.Wt)
-            op.Wt[i * op.ldwt + j] = (j >= i) ? S[j * DP + i] : 0.0;   // Wt[i][j] = W[j][i] (upper)
+            op.Wt[i * op.ldwt + j] = (j >= i) ? S[tri(j, i)] : 0.0;   // Wt[i][j] = W[j][i] (upper)
     }
 }
 
@@ -378,7 +387,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherOp* __restrict_
     }
 }
 
-constexpr int TILE_SMEM = NB * DP * 8;
+constexpr int TILE_SMEM = TRI_DOUBLES * 8;
 
 }  // namespace
 
@@ -386,12 +395,17 @@ void launch_diag(const DiagOp* ops, int nops, int* info, void* stream)
 {
     if (nops <= 0)
         return;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM);
-        configured = true;
+    static int ctas = 0;
+    if (!ctas) {
+        cudaFuncSetAttribute(diag_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM);
+        cudaFuncSetAttribute(diag_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM);
+        const char* e = getenv("GADJ_DIAG_CTAS");   // register budget: 2 CTAs/SM without spills, 3 with a few spilled values
+        ctas = (e && e[0] == '3') ? 3 : 2;
     }
-    diag_kernel<<<nops, DIAG_THREADS, TILE_SMEM, (cudaStream_t)stream>>>(ops, info);
+    if (ctas == 3)
+        diag_kernel<3><<<nops, DIAG_THREADS, TILE_SMEM, (cudaStream_t)stream>>>(ops, info);
+    else
+        diag_kernel<2><<<nops, DIAG_THREADS, TILE_SMEM, (cudaStream_t)stream>>>(ops, info);
 }
 
 void launch_trimv(const TrimvOp* ops, int nops, void* stream)

@@ -254,10 +254,19 @@ CONFIGS = {
     "C1": dict(n_stations=100, n_baselines=300, seed=1235),
     "C2": dict(n_stations=10_000, n_baselines=30_000, seed=1236),
     "C3g": dict(n_stations=100_000, n_baselines=300_000, seed=1237),
+    # BASELINE config C3: ~3 GNSS baselines per station, direction sets of 4-6 targets on 30 % of the
+    # stations, slope distances and levelled height differences along neighbour lines
+    "C3": dict(n_stations=100_000, n_baselines=300_000, seed=1237,
+               terrestrial=dict(scalars={"S": 120_000, "L": 100_000}, n_dir_sets=30_000)),
     "C4": dict(n_stations=1_000_000, n_baselines=10_000_000, seed=1238, hub_fraction=0.02, n_hubs=200),
     "C5": dict(n_stations=100_000, n_baselines=300_000, seed=1239),
 }
 
 
 def config_network(name):
-    return gnss_network(**CONFIGS[name])
+    cfg = dict(CONFIGS[name])
+    terr = cfg.pop("terrestrial", None)
+    if terr is not None:
+        from . import synth_terrestrial
+        return synth_terrestrial.terrestrial_network(cfg.pop("n_stations"), cfg.pop("n_baselines"), cfg.pop("seed"), **terr, **cfg)
+    return gnss_network(**cfg)

@@ -175,3 +175,27 @@ def test_scale_properties_config_c2(gpu_lib):
         assert np.abs(est - e0).max() < 1e-9
         assert abs(st.sigma_zero - s0.sigma_zero) < 1e-12
         assert np.abs(q - q0).max() < 1e-9 * np.abs(q0).max()
+
+
+def test_scale_properties_config_c3(gpu_lib):
+    """BASELINE config C3 size (100k stations; GNSS baselines + direction sets + slope distances + levelling), no oracle:
+    nested dissection and a chain of 1000-station blocks (the phased mode of the reference) must agree, the iteration
+    converges, sigma-zero of the noise-consistent network is ~1 and the adjusted coordinates sit on the truth."""
+    stn, msr, truth, _ = synth.config_network("C3")
+    results = []
+    for kw, blocks in ((dict(leaf_stations=96), None), (dict(), parity.chain_blocks(len(stn), 1000))):
+        s, m = stn.copy(), msr.copy()
+        adj, info, last, stats = parity.run_engine(gpu_lib, s, m, blocks=blocks, **kw)
+        assert last.converged and last.iteration <= 6
+        results.append((adj.estimates(), adj.station_vcvs(), stats, m))
+        adj.close()
+    e0, q0, s0, m0 = results[0]
+    e1, q1, s1, m1 = results[1]
+    assert 0.97 < s0.sigma_zero < 1.03
+    assert np.sqrt(((e0 - truth) ** 2).mean()) < 0.05
+    assert np.abs(e1 - e0).max() < 1e-8
+    assert abs(s1.sigma_zero - s0.sigma_zero) < 1e-9
+    assert s1.dof == s0.dof and s1.measurement_params == s0.measurement_params
+    assert np.abs(q1 - q0).max() < 1e-8 * np.abs(q0).max()
+    # the per-record statistics written back by the two runs agree as well
+    assert np.abs(m1["measCorr"] - m0["measCorr"]).max() < 1e-7
