@@ -14,6 +14,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../../include/gadj.h"
@@ -39,6 +40,7 @@ struct adjust_settings {            // the fields of project_settings.a / .g / .
     bool apu_vcv_enu = false;              // --output-apu-vcv-units ENU (default XYZ)
     double hz_corr_threshold = 0.0, vt_corr_threshold = 0.0;   // dnaoptions.hpp:510
     bool update_binary_files = true;
+    std::string station_constraints;       // --constraints "STN1,CCC,STN2,FFC" (dnaoptions.hpp:481)
     std::string command_line;
 };
 
@@ -59,6 +61,7 @@ class dna_adjust {
         bms_file_ = base + ".bms";
         dnafiles::load_binary(bst_file_, stn_, bst_meta_);
         dnafiles::load_binary(bms_file_, msr_, bms_meta_);
+        ApplyConstraints();
         gadj_opts o;
         gadj_default_opts(&o);
         o.fixed_std_dev = a_.fixed_std_dev;
@@ -273,6 +276,35 @@ class dna_adjust {
     }
 
   private:
+    // NetworkDataLoader::ApplyConstraints (network_data_loader.cpp:211-263): user-supplied "station,constraint" pairs
+    // override the constraints in the .bst records.  The reference looks the names up in <net>.map (names sorted, binary
+    // search); the same names are in the station records, so they are indexed here directly.
+    void ApplyConstraints()
+    {
+        if (a_.station_constraints.empty())
+            return;
+        std::vector<std::string> tok;
+        std::stringstream ss(a_.station_constraints);
+        for (std::string t; std::getline(ss, t, ',');) {
+            size_t b = t.find_first_not_of(" \t"), e = t.find_last_not_of(" \t");
+            tok.push_back(b == std::string::npos ? std::string() : t.substr(b, e - b + 1));
+        }
+        std::unordered_map<std::string, uint32_t> by_name;
+        for (size_t i = 0; i < stn_.size(); ++i)
+            by_name.emplace(stn_[i].stationName, (uint32_t)i);
+        for (size_t k = 0; k + 1 < tok.size(); k += 2) {
+            std::string c = tok[k + 1];
+            for (char& ch : c)
+                ch = (char)std::toupper((unsigned char)ch);
+            auto it = by_name.find(tok[k]);
+            if (it == by_name.end())
+                SignalExceptionAdjustment("The supplied constraint station '" + tok[k] + "' is not in the stations map");
+            if (c.size() != 3 || c.find_first_not_of("CF") != std::string::npos)   // CDnaStation::IsValidConstraint
+                SignalExceptionAdjustment("Invalid station constraint: '" + tok[k + 1] + "'");
+            snprintf(stn_[it->second].stationConst, sizeof(stn_[it->second].stationConst), "%s", c.c_str());
+        }
+    }
+
     void check(int rc)
     {
         if (rc)
@@ -524,6 +556,8 @@ class dna_adjust {
         var("Epoch:", bst_meta_.epoch);
         std::ostringstream t;
         t << a_.fixed_std_dev;
+        if (!a_.station_constraints.empty())
+            var("Station constraints:", a_.station_constraints);   // PRN:3490
         var("Constrained Station S.D. (m):", t.str());
         t.str("");
         t << a_.free_std_dev;

@@ -141,10 +141,8 @@ int main(int argc, char** argv)
             quiet = true;
         else if (n == "no-binary-update")
             s.update_binary_files = false;
-        else if (n == "constraints") {
-            std::cerr << "- Error: --constraints is not supported by this build (edit the station constraints upstream).\n";
-            return EXIT_FAILURE;
-        }
+        else if (n == "constraints")
+            s.station_constraints = value;
         // remaining accepted flags select CPU execution strategies or extra reports: no effect here
     }
     if (s.network_name.empty()) {

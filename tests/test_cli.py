@@ -204,6 +204,27 @@ def _apu_cor(exe, oracle, tmp_path):
     assert r.returncode == 1 and "dense block variance matrix" in r.stderr
 
 
+def test_cli_constraints(cli_hostsim, oracle, tmp_path):
+    """--constraints "name,CCC,..." (network_data_loader.cpp:211-263): the override reaches the solve; bad names and
+    bad codes are errors with the reference's wording."""
+    stn, msr, _, _ = synth.gnss_network(60, 170, 35)
+    _write_network(tmp_path, "cn", stn, msr)
+    n1, n2 = stn["stationName"][7].decode(), stn["stationName"][11].decode()
+    r = _run(cli_hostsim, tmp_path, "cn", "--constraints", f"{n1},ccc,{n2},FFC", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    stn_c = stn.copy()
+    stn_c["stationConst"][7] = b"CCC"
+    stn_c["stationConst"][11] = b"FFC"
+    _check_outputs(oracle, tmp_path, "cn", "simult", stn_c, msr, False)
+    adj = open(os.path.join(tmp_path, "cn.simult.adj")).read()
+    assert "Station constraints:" in adj
+    rows = _station_table(adj)
+    r = _run(cli_hostsim, tmp_path, "cn", "--constraints", "NOSUCH,CCC")
+    assert r.returncode == 1 and "is not in the stations map" in r.stderr
+    r = _run(cli_hostsim, tmp_path, "cn", "--constraints", f"{n1},CXC")
+    assert r.returncode == 1 and "Invalid station constraint" in r.stderr
+
+
 def test_cli_apu_cor_hostsim(cli_hostsim, oracle, tmp_path):
     _apu_cor(cli_hostsim, oracle, tmp_path)
 
