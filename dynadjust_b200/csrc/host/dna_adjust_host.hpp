@@ -13,6 +13,8 @@
 #include <iomanip>
 #include <sstream>
 #include <stdexcept>
+#include <algorithm>
+#include <cctype>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -35,6 +37,7 @@ struct adjust_settings {            // the fields of project_settings.a / .g / .
     double free_std_dev = 10.0, fixed_std_dev = 1.0e-6, confidence_interval = 95.0;
     bool scale_normals_to_unity = false;
     bool output_adj_msr = false;
+    bool output_stn_blocks = false;        // --output-stn-blocks: phased modes print the station tables block by block
     bool output_pos_uncertainty = false;   // --output-pos-uncertainty: <net>.<mode>.apu
     bool output_corrections = false;       // --output-corrections-file: <net>.<mode>.cor
     bool apu_vcv_enu = false;              // --output-apu-vcv-units ENU (default XYZ)
@@ -165,14 +168,40 @@ class dna_adjust {
         PrintStatistics(adj);
         if (a_.output_adj_msr)
             PrintAdjMeasurements(adj);
-        PrintAdjStations(adj);
         std::ofstream xyz(stem + ".xyz");
         PrintOutputFileHeaderInfo(xyz, "DYNADJUST COORDINATE OUTPUT FILE", stem + ".xyz");
-        PrintAdjStations(xyz);
+        PrintAdjustedNetworkStations(adj, xyz);
         if (a_.output_pos_uncertainty)
             PrintPositionalUncertainty(stem + ".apu");
         if (a_.output_corrections)
             PrintNetworkStationCorrections(stem + ".cor");
+    }
+
+    // PrintAdjustedNetworkStations (PRN:535-595): one list of every station; in the phased modes with
+    // --output-stn-blocks one table per block (inner + junction stations); block-1 mode stops after the first block.
+    void PrintAdjustedNetworkStations(std::ostream& adj, std::ostream& xyz) const
+    {
+        const bool phased = a_.adjust_mode != SimultaneousMode && !seg_.isl.empty();
+        if (!phased || (!a_.output_stn_blocks && a_.adjust_mode != Phased_Block_1Mode)) {
+            PrintAdjStations(adj, nullptr);
+            PrintAdjStations(xyz, nullptr);
+            return;
+        }
+        for (size_t b = 0; b < seg_.isl.size(); ++b) {
+            std::vector<uint32_t> list(seg_.isl[b]);
+            if (b < seg_.jsl.size())
+                list.insert(list.end(), seg_.jsl[b].begin(), seg_.jsl[b].end());
+            std::sort(list.begin(), list.end());
+            list.erase(std::unique(list.begin(), list.end()), list.end());
+            if (a_.output_stn_blocks) {
+                adj << "\nBlock " << b + 1 << "\n";
+                xyz << "\nBlock " << b + 1 << "\n";
+            }
+            PrintAdjStations(adj, &list);
+            PrintAdjStations(xyz, &list);
+            if (a_.adjust_mode == Phased_Block_1Mode)
+                break;   // only the first block is reported (PRN:586-588)
+        }
     }
 
     // ---- .apu (PrintPositionalUncertainty PRN:2665-2770, PrintPosUncertainty PRN:4326-4432) -------------------------
@@ -622,6 +651,10 @@ class dna_adjust {
         var("Rigorous Sigma Zero") << std::fixed << std::setprecision(3) << stats_.sigma_zero << "\n";
         var("Global (Pelzer) Reliability") << std::fixed << std::setprecision(3) << stats_.global_pelzer
                                            << "   (excludes non redundant measurements)\n\n";
+        if (a_.adjust_mode == Phased_Block_1Mode) {   // no global test in block-1 mode (ADJ:7140-7147)
+            os << "\n";
+            return;
+        }
         std::ostringstream t;
         t << "Chi-Square test (" << std::fixed << std::setprecision(1) << a_.confidence_interval << "%)";
         var(t.str().c_str()) << std::fixed << std::setprecision(3) << chiLower_ << " < " << stats_.sigma_zero << " < " << chiUpper_
@@ -658,14 +691,16 @@ class dna_adjust {
         os << "\n";
     }
 
-    void PrintAdjStations(std::ostream& os) const
+    void PrintAdjStations(std::ostream& os, const std::vector<uint32_t>* subset) const
     {   // PrintAdjStation (PRN:3917-4070): PLHhXYZ + SD(e,n,up) = sqrt diag(R^T Q R), geoid uncertainty added to up
         os << "\nAdjusted Coordinates\n------------------------------------------\n\n";
         char buf[512];
         snprintf(buf, sizeof(buf), "%-20s%-5s%14s%15s%11s%11s%15s%15s%15s%12s%10s%10s  %s", "Station", "Const", "Latitude", "Longitude",
                  "H(Ortho)", "h(Ellipse)", "X", "Y", "Z", "SD(e)", "SD(n)", "SD(up)", "Description");
         os << buf << "\n" << std::string(211, '-') << "\n";
-        for (size_t i = 0; i < stn_.size(); ++i) {
+        const size_t count = subset ? subset->size() : stn_.size();
+        for (size_t n = 0; n < count; ++n) {
+            const size_t i = subset ? (*subset)[n] : n;
             const dna_stn_t& s = stn_[i];
             const double* q = &vcv_[9 * i];
             double lat = s.currentLatitude, lon = s.currentLongitude, h = s.currentHeight;

@@ -28,7 +28,8 @@ const Flag kFlags[] = {
     {"create-stage-files", false}, {"purge-stage-files", false}, {"stage-path", true}, {"max-threads", true},
     {"input-folder", true}, {"output-folder", true}, {"output-adj-msr", false}, {"output-pos-uncertainty", false},
     {"output-all-covariances", false}, {"output-corrections-file", false}, {"output-apu-vcv-units", true},
-    {"hz-corr-threshold", true}, {"vt-corr-threshold", true}, {"network-name", true}, {"quiet", false}, {"verbose-level", true},
+    {"hz-corr-threshold", true}, {"vt-corr-threshold", true}, {"output-stn-blocks", false}, {"output-msr-blocks", false},
+    {"network-name", true}, {"quiet", false}, {"verbose-level", true},
     {"no-binary-update", false}, {"help", false},
 };
 
@@ -120,6 +121,8 @@ int main(int argc, char** argv)
             s.output_folder = value;
         else if (n == "output-adj-msr")
             s.output_adj_msr = true;
+        else if (n == "output-stn-blocks")
+            s.output_stn_blocks = true;
         else if (n == "output-pos-uncertainty")
             s.output_pos_uncertainty = true;
         else if (n == "output-corrections-file")

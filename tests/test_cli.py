@@ -225,6 +225,40 @@ def test_cli_constraints(cli_hostsim, oracle, tmp_path):
     assert r.returncode == 1 and "Invalid station constraint" in r.stderr
 
 
+def test_cli_block_outputs(cli_hostsim, oracle, tmp_path):
+    """--output-stn-blocks (one station table per .seg block) and --block1-phased (only block 1 is reported, no global
+    test; PRN:535-595, ADJ:7140-7147).  Every block is rigorous here, so the printed values are the simultaneous ones."""
+    stn, msr, _, _ = synth.gnss_network(120, 360, 12)
+    _write_network(tmp_path, "blk", stn, msr)
+    isl = parity.chain_blocks(120, 30)
+    jsl = [list(range(b[-1] + 1, min(b[-1] + 4, 120))) for b in isl]      # a few stations of the next block as junctions
+    dnafiles.write_seg(os.path.join(tmp_path, "blk.seg"), isl, jsl, [[] for _ in isl])
+    ref = oracle.adjust_simultaneous(stn.copy(), msr.copy(), want_vcv=True)
+    est = ref["est"].reshape(-1, 3)
+    r = _run(cli_hostsim, tmp_path, "blk", "--phased", "--output-stn-blocks", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    adj = open(os.path.join(tmp_path, "blk.phased.adj")).read()
+    parts = re.split(r"^Block (\d+)$", adj.split("SOLUTION")[1], flags=re.M)
+    assert len(parts) == 2 * len(isl) + 1
+    for b in range(len(isl)):
+        assert int(parts[2 * b + 1]) == b + 1
+        rows = {}
+        for line in parts[2 * b + 2].splitlines():
+            f = line.split()
+            if len(f) >= 12 and re.fullmatch(r"[CF]{3}", f[1]):
+                rows[f[0]] = [float(x) for x in f[2:12]]
+        want = sorted(set(isl[b]) | set(jsl[b]))
+        assert sorted(rows) == sorted(stn["stationName"][i].decode() for i in want)
+        for i in want:
+            assert np.abs(np.array(rows[stn["stationName"][i].decode()][4:7]) - est[i]).max() < 1e-3
+    r = _run(cli_hostsim, tmp_path, "blk", "--block1-phased", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    adj = open(os.path.join(tmp_path, "blk.phased-block1.adj")).read()
+    assert "Chi-Square test" not in adj and "Rigorous Sigma Zero" in adj
+    rows = _station_table(adj)
+    assert sorted(rows) == sorted(stn["stationName"][i].decode() for i in set(isl[0]) | set(jsl[0]))
+
+
 def test_cli_apu_cor_hostsim(cli_hostsim, oracle, tmp_path):
     _apu_cor(cli_hostsim, oracle, tmp_path)
 
