@@ -2,8 +2,9 @@
 //
 //   C[M x N] (+)= alpha * A[M x K] * B[N x K]^T        (all row-major, K contiguous)
 //
-// One CTA computes one 128 x 128 output tile of one op; a launch covers the tiles of many
-// ops (all the panel updates / Schur complements / inverse products of one tree level).
+// The unit of work is one 128 x 128 output tile of one op; a launch covers the tiles of many ops (all the
+// panel updates / Schur complements / inverse products of one tree level), listed by the planner (only tiles
+// that hold work), and one persistent CTA per SM strides through the list.
 //
 // Data path: a producer warp issues cp.async.bulk.tensor (TMA) loads of 128 x 16 FP64
 // boxes of A and B into a 4-stage shared-memory ring (SWIZZLE_128B, mbarrier full/empty
@@ -15,6 +16,8 @@
 //
 // Roofline: FP64 tensor pipe.  Per tile and 16-deep K step: 2*128*128*16 = 524k flop against
 // 32 KB of TMA traffic (16 flop/B from L2; panels are read ~once from HBM per launch).
+// Measured DMMA issue ceiling from registers: 36.4 TFLOP/s (tools/probes/dmma_pred_probe.cu); cuBLAS DGEMM 35.4;
+// this kernel 35.5 at 4096^3 and 29.3 (algorithmic flops) over a whole C4 iteration.
 #include <cuda_runtime.h>
 
 #include <cstdint>
