@@ -434,6 +434,114 @@ void first_run_reduction(gadj_ctx* c)
     });
 }
 
+// GNSS point clusters 'Y' given as latitude / longitude / height become Cartesian on their first run
+// (UpdateDesignNormalMeasMatrices_Y ADJ:6281-6325, LoadVarianceMatrix_Y ADJ:4563-4644): the original values are kept
+// in preAdjMeas, orthometric heights are reduced with the station's geoid separation (kept in preAdjCorr), the
+// records are rewritten in place as XYZ (station3 remembers the original type) and the cluster variance matrix is
+// propagated with the Jacobians d(XYZ)/d(lat, lon, h) at the stations' current positions.  Written back into the
+// caller's records, as the reference does.
+int convert_llh_point_clusters(gadj_ctx* c)
+{
+    for (uint64_t i = 0; i < c->nmsr;) {
+        dna_msr_t* m = &c->msr[i];
+        if (m->measType != 'Y' || m->measStart != 0) {
+            ++i;
+            continue;
+        }
+        // members of this cluster
+        const uint32_t count = m->vectorCount1;
+        std::vector<uint64_t> rec;
+        uint64_t j = i;
+        for (uint32_t k = 0; k < count && j + 2 < c->nmsr; ++k) {
+            rec.push_back(j);
+            j += 3 + 3ull * c->msr[j].vectorCount2;
+        }
+        i = std::max<uint64_t>(j, i + 1);
+        const bool LLH = std::strncmp(m->coordType, "LLH", 3) == 0, LLh = std::strncmp(m->coordType, "LLh", 3) == 0;
+        if ((!LLH && !LLh) || m->ignore || rec.size() != count || j > c->nmsr)
+            continue;
+        const uint32_t n = 3 * count;
+        std::vector<double> V((size_t)n * n, 0.0), J((size_t)n * 3, 0.0);   // J: one 3x3 block per member
+        auto sym = [&](uint32_t r, uint32_t col, double v) { V[(size_t)r * n + col] = V[(size_t)col * n + r] = v; };
+        for (uint32_t k = 0; k < count; ++k) {
+            dna_msr_t* r = &c->msr[rec[k]];
+            if (r->station1 >= c->nstn)
+                return c->fail("measurement refers to a station index beyond the station list");
+            const dna_stn_t& st = c->stn[r->station1];
+            const uint32_t v = 3 * k;
+            sym(v, v, r[0].term2);
+            sym(v, v + 1, r[1].term2);
+            sym(v + 1, v + 1, r[1].term3);
+            sym(v, v + 2, r[2].term2);
+            sym(v + 1, v + 2, r[2].term3);
+            sym(v + 2, v + 2, r[2].term4);
+            for (uint32_t q = 0; q < r[0].vectorCount2 && v + 3 + 3 * q + 2 < n; ++q) {
+                const dna_msr_t* cv = r + 3 + 3 * q;
+                const uint32_t cc = v + 3 + 3 * q;
+                for (uint32_t x = 0; x < 3; ++x) {
+                    sym(v + x, cc, cv[x].term1);
+                    sym(v + x, cc + 1, cv[x].term2);
+                    sym(v + x, cc + 2, cv[x].term3);
+                }
+            }
+            cart_geo_jacobian(c->ell, st.currentLatitude, st.currentLongitude, st.currentHeight, &J[9 * (size_t)k]);
+            double h = r[2].term1;
+            for (int q = 0; q < 3; ++q)
+                r[q].preAdjMeas = r[q].term1;
+            if (LLH && std::fabs((double)st.geoidSep) > 1.0e-4) {
+                r[2].preAdjCorr = st.geoidSep;
+                h += r[2].preAdjCorr;
+            }
+            double xyz[3];
+            geo_to_cart(c->ell, r[0].term1, r[1].term1, h, xyz);
+            for (int q = 0; q < 3; ++q) {
+                r[q].term1 = xyz[q];
+                std::snprintf(r[q].coordType, sizeof(r[q].coordType), "%s", "XYZ");
+                r[q].station3 = LLH ? DNA_LLH_TYPE : DNA_LLh_TYPE;
+            }
+        }
+        // block (a, b) of J V J^T = J_a V_ab J_b^T
+        auto block = [&](uint32_t a, uint32_t b2, double* out) {
+            double T[9];
+            for (int x = 0; x < 3; ++x)
+                for (int y = 0; y < 3; ++y) {
+                    double sum = 0.0;
+                    for (int z = 0; z < 3; ++z)
+                        sum += J[9 * (size_t)a + 3 * x + z] * V[(size_t)(3 * a + z) * n + 3 * b2 + y];
+                    T[3 * x + y] = sum;
+                }
+            for (int x = 0; x < 3; ++x)
+                for (int y = 0; y < 3; ++y) {
+                    double sum = 0.0;
+                    for (int z = 0; z < 3; ++z)
+                        sum += T[3 * x + z] * J[9 * (size_t)b2 + 3 * y + z];
+                    out[3 * x + y] = sum;
+                }
+        };
+        for (uint32_t k = 0; k < count; ++k) {
+            dna_msr_t* r = &c->msr[rec[k]];
+            double B[9];
+            block(k, k, B);
+            r[0].term2 = B[0];
+            r[1].term2 = B[1];
+            r[1].term3 = B[4];
+            r[2].term2 = B[2];
+            r[2].term3 = B[5];
+            r[2].term4 = B[8];
+            for (uint32_t q = 0; q < r[0].vectorCount2 && k + 1 + q < count; ++q) {
+                dna_msr_t* cv = r + 3 + 3 * q;
+                block(k, k + 1 + q, B);
+                for (int x = 0; x < 3; ++x) {
+                    cv[x].term1 = B[3 * x];
+                    cv[x].term2 = B[3 * x + 1];
+                    cv[x].term3 = B[3 * x + 2];
+                }
+            }
+        }
+    }
+    return 0;
+}
+
 bool is_scalar_type(char t)
 {
     switch (t) {
@@ -722,6 +830,9 @@ int first_run_reduction_rows(gadj_ctx* c, const double* est)
         for (uint32_t k = 0; k < members; ++k) {
             dna_msr_t* r = &msr[c->rows[cd.row0 + 3 * k].rec];
             for (int q = 0; q < 3; ++q) {
+                // clusters that arrived as latitude / longitude / height keep the original values in preAdjMeas (ADJ:6353)
+                if (cd.type == 'Y' && (r[q].station3 == DNA_LLH_TYPE || r[q].station3 == DNA_LLh_TYPE))
+                    continue;
                 if (c->reduced)
                     r[q].term1 = r[q].preAdjMeas;
                 else
@@ -854,6 +965,8 @@ int gadj_prepare(gadj_ctx* c)
     c->iteration = 0;
     if (!c->stn || !c->msr)
         return c->fail("stations and measurements must be set before gadj_prepare");
+    if (!c->reduced && convert_llh_point_clusters(c))
+        return 1;
     if (scan_measurements(c))
         return 1;
     for (uint64_t b = 0; b < c->nbsl; ++b) {

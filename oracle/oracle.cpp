@@ -543,6 +543,120 @@ int load_variance_matrix_D(Ctx& c, Meas& me, bool build)
     return inverse_variance(me.vinv.data(), n, false, c.use_ref);
 }
 
+// FormCarttoGeoRotationMatrix (MFN:204-233): d(X,Y,Z)/d(phi,lambda,h) at one position, row-major 3x3
+void geo_to_cart_jacobian(const Ellipsoid& e, double lat, double lon, double h, double* R)
+{
+    const double coslat = std::cos(lat), sinlat = std::sin(lat), coslon = std::cos(lon), sinlon = std::sin(lon);
+    const double term1_a = e.a * e.e2, one_minus_esq = 1. - e.e2;
+    const double nu = prime_vertical(e, lat);
+    const double nu_plus_h = nu + h, nu_1minuse2_plus_h = nu * one_minus_esq + h;
+    const double term1_b = term1_a * sinlat * coslat;
+    const double term1_c = std::pow(1. - e.e2 * sinlat * sinlat, 1.5);
+    R[0] = (term1_b * coslat * coslon / term1_c) - (nu_plus_h * sinlat * coslon);
+    R[1] = -nu_plus_h * coslat * sinlon;
+    R[2] = coslat * coslon;
+    R[3] = (term1_b * coslat * sinlon / term1_c) - (nu_plus_h * sinlat * sinlon);
+    R[4] = nu_plus_h * coslat * coslon;
+    R[5] = coslat * sinlon;
+    R[6] = (term1_b * one_minus_esq * sinlat / term1_c) + (nu_1minuse2_plus_h * coslat);
+    R[7] = 0.;
+    R[8] = sinlat;
+}
+
+// First run of a Y cluster given in latitude / longitude / height (UpdateDesignNormalMeasMatrices_Y ADJ:6281-6325,
+// 6384-6420; LoadVarianceMatrix_Y ADJ:4563-4644): the original values go to preAdjMeas, orthometric heights are
+// reduced with the station's geoid separation (preAdjCorr), the point becomes Cartesian in place (coordType "XYZ",
+// station3 keeps the original type) and the whole variance matrix is propagated V_cart = J V_geo J^T with the
+// Jacobians taken at the stations' current positions, then written back (SetGPSVarianceMatrix).
+void convert_y_cluster_llh(Ctx& c, Meas& me)
+{
+    dna_msr_t* m0 = &c.msr[me.first];
+    const bool LLH = std::strncmp(m0->coordType, "LLH", 3) == 0, LLh = std::strncmp(m0->coordType, "LLh", 3) == 0;
+    if (!LLH && !LLh)
+        return;
+    const uint32_t n = me.nrows, members = (uint32_t)me.rec.size();
+    std::vector<double> V((size_t)n * n, 0.0), J((size_t)n * n, 0.0);
+    auto sym = [&](uint32_t r, uint32_t col, double v) { V[(size_t)r * n + col] = V[(size_t)col * n + r] = v; };
+    for (uint32_t k = 0; k < members; ++k) {
+        dna_msr_t* r = &c.msr[me.rec[k]];
+        const dna_stn_t& st = c.stn[r->station1];
+        const uint32_t v = 3 * k;
+        sym(v, v, r[0].term2);
+        sym(v, v + 1, r[1].term2);
+        sym(v + 1, v + 1, r[1].term3);
+        sym(v, v + 2, r[2].term2);
+        sym(v + 1, v + 2, r[2].term3);
+        sym(v + 2, v + 2, r[2].term4);
+        for (uint32_t q = 0; q < r[0].vectorCount2; ++q) {
+            dna_msr_t* cv = r + 3 + 3 * q;
+            const uint32_t cc = v + 3 + 3 * q;
+            for (int i = 0; i < 3; ++i) {
+                sym(v + i, cc, cv[i].term1);
+                sym(v + i, cc + 1, cv[i].term2);
+                sym(v + i, cc + 2, cv[i].term3);
+            }
+        }
+        double R[9];
+        geo_to_cart_jacobian(c.ell, st.currentLatitude, st.currentLongitude, st.currentHeight, R);
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b)
+                J[(size_t)(v + a) * n + v + b] = R[3 * a + b];
+        // the point itself
+        const double lat = r[0].term1, lon = r[1].term1;
+        double h = r[2].term1;
+        for (int q = 0; q < 3; ++q)
+            r[q].preAdjMeas = r[q].term1;
+        if (LLH && std::fabs(st.geoidSep) > 1.0e-4) {
+            r[2].preAdjCorr = st.geoidSep;
+            h += r[2].preAdjCorr;
+        }
+        double x, y, z;
+        geo_to_cart(c.ell, lat, lon, h, &x, &y, &z);
+        r[0].term1 = x;
+        r[1].term1 = y;
+        r[2].term1 = z;
+        for (int q = 0; q < 3; ++q) {
+            std::snprintf(r[q].coordType, sizeof(r[q].coordType), "%s", "XYZ");
+            r[q].station3 = LLH ? DNA_LLH_TYPE : DNA_LLh_TYPE;
+        }
+    }
+    // V_cart = J V J^T
+    std::vector<double> T((size_t)n * n, 0.0), W((size_t)n * n, 0.0);
+    for (uint32_t i = 0; i < n; ++i)
+        for (uint32_t k = 0; k < n; ++k) {
+            const double a = J[(size_t)i * n + k];
+            if (a != 0.0)
+                for (uint32_t j = 0; j < n; ++j)
+                    T[(size_t)i * n + j] += a * V[(size_t)k * n + j];
+        }
+    for (uint32_t i = 0; i < n; ++i)
+        for (uint32_t j = 0; j < n; ++j) {
+            double sum = 0.0;
+            for (uint32_t k = 0; k < n; ++k)
+                sum += T[(size_t)i * n + k] * J[(size_t)j * n + k];
+            W[(size_t)i * n + j] = sum;
+        }
+    for (uint32_t k = 0; k < members; ++k) {
+        dna_msr_t* r = &c.msr[me.rec[k]];
+        const uint32_t v = 3 * k;
+        r[0].term2 = W[(size_t)v * n + v];
+        r[1].term2 = W[(size_t)v * n + v + 1];
+        r[1].term3 = W[(size_t)(v + 1) * n + v + 1];
+        r[2].term2 = W[(size_t)v * n + v + 2];
+        r[2].term3 = W[(size_t)(v + 1) * n + v + 2];
+        r[2].term4 = W[(size_t)(v + 2) * n + v + 2];
+        for (uint32_t q = 0; q < r[0].vectorCount2; ++q) {
+            dna_msr_t* cv = r + 3 + 3 * q;
+            const uint32_t cc = v + 3 + 3 * q;
+            for (int i = 0; i < 3; ++i) {
+                cv[i].term1 = W[(size_t)(v + i) * n + cc];
+                cv[i].term2 = W[(size_t)(v + i) * n + cc + 1];
+                cv[i].term3 = W[(size_t)(v + i) * n + cc + 2];
+            }
+        }
+    }
+}
+
 // LoadVarianceMatrix_X / _Y (ADJ:4312-4450, ADJ:4494-4679) for Cartesian clusters: upper triangle from the records
 // (GetGPSVarianceMatrix, MFN:85-123), whole-matrix scalar applied and written back on the first run.
 int load_variance_matrix_XY(Ctx& c, Meas& me, bool build)
@@ -559,7 +673,7 @@ int load_variance_matrix_XY(Ctx& c, Meas& me, bool build)
         return 3;
     }
     if (me.type == 'Y' && std::strncmp(m0->coordType, "XYZ", 3) != 0) {
-        g_err = "oracle: Y clusters are restated for Cartesian (XYZ) coordinates only";
+        g_err = "oracle: Y cluster coordinates must be XYZ, LLH or LLh";
         return 3;
     }
     std::vector<double> V((size_t)n * n, 0.0);
@@ -624,6 +738,8 @@ int fill_design_normals(Ctx& c, bool build)
         case 'X':
         case 'Y': {
             // UpdateDesignNormalMeasMatrices_X (ADJ:6056-6246) / _Y (ADJ:6249-6566)
+            if (build && me.type == 'Y')
+                convert_y_cluster_llh(c, me);
             for (size_t k = 0; k < me.rec.size(); ++k) {
                 dna_msr_t* r = &c.msr[me.rec[k]];
                 uint32_t s1 = r->station1 * 3, s2 = r->station2 * 3;
@@ -632,7 +748,8 @@ int fill_design_normals(Ctx& c, bool build)
                 rw.st[1] = r->station2;
                 rw.nst = me.type == 'X' ? 2 : 1;
                 for (int q = 0; q < 3; ++q) {
-                    if (build)
+                    // clusters that arrived as latitude / longitude / height keep the original values (ADJ:6353-6356)
+                    if (build && !(me.type == 'Y' && (r[q].station3 == DNA_LLH_TYPE || r[q].station3 == DNA_LLh_TYPE)))
                         r[q].preAdjMeas = r[q].term1;
                     c.ell_rows[row + 3 * k + q] =
                         me.type == 'X' ? r[q].term1 - (c.est[s2 + q] - c.est[s1 + q]) : r[q].term1 - c.est[s1 + q];

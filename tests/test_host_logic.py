@@ -95,6 +95,80 @@ def test_gnss_clusters(oracle, hostsim_path):
                                 leaf_stations=16)
 
 
+def _y_clusters_as_llh(stn, msr):
+    """Rewrite every Cartesian Y cluster of `msr` in latitude / longitude / orthometric-height form (the layout of the
+    reference's urban sample): values through CartToGeo, variance matrix through the inverse Jacobians at the points."""
+    i = 0
+    while i < len(msr):
+        if msr["measType"][i] != b"Y" or msr["measStart"][i] != 0:
+            i += 1
+            continue
+        count = int(msr["vectorCount1"][i])
+        rec, j = [], i
+        for _ in range(count):
+            rec.append(j)
+            j += 3 + 3 * int(msr["vectorCount2"][j])
+        n = 3 * count
+        V = np.zeros((n, n))
+        for k, r in enumerate(rec):
+            v = 3 * k
+            V[v, v], V[v, v + 1], V[v + 1, v + 1] = msr["term2"][r], msr["term2"][r + 1], msr["term3"][r + 1]
+            V[v, v + 2], V[v + 1, v + 2], V[v + 2, v + 2] = msr["term2"][r + 2], msr["term3"][r + 2], msr["term4"][r + 2]
+            for q in range(int(msr["vectorCount2"][r])):
+                for x in range(3):
+                    cv = r + 3 + 3 * q + x
+                    V[v + x, v + 3 + 3 * q:v + 6 + 3 * q] = msr["term1"][cv], msr["term2"][cv], msr["term3"][cv]
+        V = np.triu(V) + np.triu(V, 1).T
+        J = np.zeros((n, n))
+        for k, r in enumerate(rec):
+            s = int(msr["station1"][r])
+            lat, lon, h = synth.cart_to_geo(np.array([[msr["term1"][r], msr["term1"][r + 1], msr["term1"][r + 2]]]))
+            # Jacobian at the station's a-priori position, as the engine / reference will use
+            la, lo, hh = stn["currentLatitude"][s], stn["currentLongitude"][s], stn["currentHeight"][s]
+            eps = 1e-7
+            f = lambda a, b, c: synth.geo_to_cart(np.array([a]), np.array([b]), np.array([c]))[0]
+            Jk = np.stack([(f(la + eps, lo, hh) - f(la - eps, lo, hh)) / (2 * eps), (f(la, lo + eps, hh) - f(la, lo - eps, hh)) / (2 * eps),
+                           (f(la, lo, hh + 1.0) - f(la, lo, hh - 1.0)) / 2.0], axis=1)
+            J[3 * k:3 * k + 3, 3 * k:3 * k + 3] = Jk
+            msr["term1"][r], msr["term1"][r + 1], msr["term1"][r + 2] = lat[0], lon[0], h[0] - float(stn["geoidSep"][s])
+            msr["coordType"][r:r + 3] = b"LLH"
+        Ji = np.linalg.inv(J)
+        G = Ji @ V @ Ji.T
+        for k, r in enumerate(rec):
+            v = 3 * k
+            msr["term2"][r], msr["term2"][r + 1], msr["term3"][r + 1] = G[v, v], G[v, v + 1], G[v + 1, v + 1]
+            msr["term2"][r + 2], msr["term3"][r + 2], msr["term4"][r + 2] = G[v, v + 2], G[v + 1, v + 2], G[v + 2, v + 2]
+            for q in range(int(msr["vectorCount2"][r])):
+                for x in range(3):
+                    cv = r + 3 + 3 * q + x
+                    msr["term1"][cv], msr["term2"][cv], msr["term3"][cv] = G[v + x, v + 3 + 3 * q:v + 6 + 3 * q]
+        i = j
+
+
+def test_point_clusters_in_geographic_form(oracle, hostsim_path):
+    """Y clusters supplied as latitude / longitude / orthometric height (ADJ:6281-6325, 4563-4644): converted to
+    Cartesian on the first run with geoid reduction and variance propagation, written back into the records.  The
+    engine must agree with the oracle, and both with the same network given in Cartesian form."""
+    from dynadjust_b200 import synth_terrestrial as st
+    stn, msr, truth, _ = st.terrestrial_network(120, 300, 47, n_y=25, deflections=False)
+    ref_xyz = oracle.adjust_simultaneous(stn.copy(), msr.copy(), want_vcv=False)
+    msr_llh = msr.copy()
+    _y_clusters_as_llh(stn, msr_llh)
+    assert (msr_llh["coordType"][msr_llh["measType"] == b"Y"] == b"LLH").any()
+    s_o, m_o = stn.copy(), msr_llh.copy()
+    ref = oracle.adjust_simultaneous(s_o, m_o, want_vcv=False)
+    assert np.abs(ref["est"] - ref_xyz["est"]).max() < 1e-5 and abs(ref["res"].sigma_zero - ref_xyz["res"].sigma_zero) < 1e-5
+    s_e, m_e = stn.copy(), msr_llh.copy()
+    adj, info, last, stats = parity.run_engine(hostsim_path, s_e, m_e, leaf_stations=16)
+    assert np.abs(adj.estimates() - ref["est"]).max() < parity.TOL_XYZ
+    assert abs(stats.sigma_zero - ref["res"].sigma_zero) < 1e-11 and stats.dof == ref["res"].dof
+    y = m_e["measType"] == b"Y"
+    for f in ("term1", "term2", "term3", "term4", "preAdjMeas", "preAdjCorr", "measAdj", "measCorr"):
+        assert np.abs(m_e[f][y] - m_o[f][y]).max() <= 1e-9 * max(1.0, np.abs(m_o[f][y]).max()), f
+    assert (m_e["coordType"][y] == b"XYZ").all() and (m_e["station3"][y & (m_e["measStart"] <= 2)] == 2).all()
+    adj.close()
+
+
 def test_all_types_together(oracle, hostsim_path):
     """BASELINE config C3's mix and more: every type in one network, nested dissection and a chain of blocks."""
     mix = dict(scalars={k: 50 for k in "ABKCEMSVZLHRIJPQ"}, n_dir_sets=40, n_x=20, n_y=20, ignore_some=True)
