@@ -13,7 +13,7 @@ ITRF2008 -> GDA2020 dnatransformationparameters.hpp:2413-2430, epoch arithmetic 
 import numpy as np
 
 from dynadjust_b200 import synth
-from dynadjust_b200.records import LLH_TYPE, XYZ_TYPE, new_msr, new_stn
+from dynadjust_b200.records import GRS80_A, GRS80_INVF, LLH_TYPE, UTM_TYPE, XYZ_TYPE, new_msr, new_stn
 
 # millimetres, ppb, milli-arc-seconds and their rates per year, reference epoch 2020.0
 ITRF2008_TO_GDA2020 = (13.790, 4.550, 15.220, 2.5500, 0.2808, 0.2677, -0.4638,
@@ -50,6 +50,63 @@ def helmert_to_gda2020(xyz, frame, epoch):
     return (R @ xyz) * (1.0 + sc) + t
 
 
+def grid_to_geo(easting, northing, zone, a=GRS80_A, invf=GRS80_INVF, false_e=500000.0, false_n=10000000.0, k0=0.9996,
+                lcm_z1=-177.0, zw=6.0):
+    """GridToGeo (dnatemplategeodesyfuncs.hpp:435-510): Redfearn's formulae, UTM / MGA grid -> latitude, longitude (radians)"""
+    f = 1.0 / invf
+    b = a * (1 - f)
+    e2 = 2 * f - f * f
+    n = (a - b) / (a + b)
+    n2, n3, n4 = n ** 2, n ** 3, n ** 4
+    G = a * (1 - n) * (1 - n2) * (1 + 9 * n2 / 4 + 225 * n4 / 64) * (np.pi / 180.0)
+    ep, npr = easting - false_e, northing - false_n
+    m = npr / k0
+    sigma = (m * np.pi) / (180 * G)
+    lp = sigma + ((3 * n / 2) - (27 * n3 / 32)) * np.sin(2 * sigma)
+    lp += ((21 * n2 / 16) - (55 * n4 / 32)) * np.sin(4 * sigma)
+    lp += (151 * n3 / 96) * np.sin(6 * sigma)
+    lp += (1097 * n4 / 512) * np.sin(8 * sigma)
+    rho = a * (1 - e2) / (1 - e2 * np.sin(lp) ** 2) ** 1.5
+    nu = a / (1 - e2 * np.sin(lp) ** 2) ** 0.5
+    t, psi = np.tan(lp), nu / rho
+    num1 = t / (k0 * rho)
+    x = ep / (k0 * nu)
+    t1 = num1 * x * ep / 2
+    t2 = num1 * ep * x ** 3 / 24 * (-4 * psi ** 2 + 9 * psi * (1 - t ** 2) + 12 * t ** 2)
+    t3 = num1 * ep * x ** 5 / 720 * (8 * psi ** 4 * (11 - 24 * t ** 2) - 12 * psi ** 3 * (21 - 71 * t ** 2) +
+                                       15 * psi ** 2 * (15 - 98 * t ** 2 + 15 * t ** 4) + 180 * psi * (5 * t ** 2 - 3 * t ** 4) + 360 * t ** 4)
+    t4 = num1 * ep * x ** 7 / 40320 * (1385 + 3633 * t ** 2 + 4095 * t ** 4 + 1575 * t ** 6)
+    lat = lp - t1 + t2 - t3 + t4
+    cm = np.radians(zone * zw + lcm_z1 - zw)
+    sec = 1.0 / np.cos(lp)
+    l1 = x * sec
+    l2 = x ** 3 / 6 * sec * (psi + 2 * t ** 2)
+    l3 = x ** 5 / 120 * sec * (-4 * psi ** 3 * (1 - 6 * t ** 2) + psi ** 2 * (9 - 68 * t ** 2) + 72 * psi * t ** 2 + 24 * t ** 4)
+    l4 = x ** 7 / 5040 * sec * (61 + 662 * t ** 2 + 1320 * t ** 4 + 720 * t ** 6)
+    return lat, cm + l1 - l2 + l3 - l4
+
+
+def apply_geoid(stn, path, convert_heights=True):
+    """dnageoid (dnageoid.cpp:165-176) from an exported DNA geoid file (name, N, meridian and prime-vertical deflections
+    in seconds): geoid separation and deflections into the station records; orthometric station heights become
+    ellipsoidal (--convert-stn-hts).  The exported file carries three decimals (the sample's .gsb grid does not
+    reproduce the values of the expected run — they differ by 2-4 mm — so the exported file is the record of what that
+    run used; its rounding, 0.5 mm in N, is the accuracy limit of the height-dependent rows of this fixture)."""
+    index = {n.decode(): i for i, n in enumerate(stn["stationName"])}
+    for l in open(path).read().splitlines():
+        if not l or l.startswith("#"):
+            continue
+        f = l.split()
+        i = index.get(f[0])
+        if i is None:
+            continue
+        stn["geoidSep"][i] = float(f[1])
+        stn["meridianDef"][i] = np.radians(float(f[2]) / 3600.0)
+        stn["verticalDef"][i] = np.radians(float(f[3]) / 3600.0)
+        if convert_heights:
+            stn["currentHeight"][i] = stn["initialHeight"][i] + float(stn["geoidSep"][i])
+
+
 def read_stations(path):
     rows = [l for l in open(path).read().splitlines() if l and not l.startswith(("!", "*"))]
     stn = new_stn(len(rows))
@@ -60,6 +117,11 @@ def read_stations(path):
             lat, lon, h = synth.cart_to_geo(np.array([c]))
             lat, lon, h = float(lat[0]), float(lon[0]), float(h[0])
             stn["suppliedStationType"][i] = XYZ_TYPE
+        elif ctype == "UTM":
+            zone = int(l[87:90])
+            lat, lon = grid_to_geo(c[0], c[1], zone)
+            h = c[2]
+            stn["suppliedStationType"][i] = UTM_TYPE
         else:
             lat, lon, h = dms_to_rad(c[0]), dms_to_rad(c[1]), c[2]
             stn["suppliedStationType"][i] = LLH_TYPE
@@ -69,7 +131,7 @@ def read_stations(path):
         stn["initialLatitude"][i] = stn["currentLatitude"][i] = lat
         stn["initialLongitude"][i] = stn["currentLongitude"][i] = lon
         stn["initialHeight"][i] = stn["currentHeight"][i] = h
-        stn["description"][i] = l[87:].strip().encode()[:127] if len(l) > 87 else b""
+        stn["description"][i] = l[90 if ctype == "UTM" else 87:].strip().encode()[:127] if len(l) > 87 else b""
         stn["fileOrder"][i] = stn["nameOrder"][i] = i
         stn["epoch"][i] = b"01.01.2020"
     return stn
@@ -86,8 +148,9 @@ def _terms(line):
 
 
 def read_measurements(path, stn, reftran=True):
-    """G baselines and Y clusters of a DNA measurement file -> binary records (dnaimport), optionally followed by the
-    reference-frame step (dnareftran) for baselines given in ITRF2008."""
+    """Measurements of a DNA file -> binary records (dnaimport): G baselines, X / Y clusters, the scalar types A B K V Z
+    (angles: radians, variances radians^2) and H L M S C E (metres), optionally followed by the reference-frame step
+    (dnareftran) for GNSS vectors given in ITRF2008 / ITRF2014."""
     index = {n.decode(): i for i, n in enumerate(stn["stationName"])}
     xyz0 = synth.geo_to_cart(stn["currentLatitude"], stn["currentLongitude"], stn["currentHeight"])
     L = [l for l in open(path).read().splitlines() if l and not l.startswith(("!", "*"))]
@@ -117,15 +180,43 @@ def read_measurements(path, stn, reftran=True):
             groups.append(m)
             cluster += 1
             i += 4
+        elif kind in "ABKVZ" or kind in "HLMSCE":
+            f = l[62:].split()
+            m = new_msr(1)
+            m["measType"], m["ignore"] = kind.encode(), ignore
+            m["station1"] = index[l[2:22].strip()]
+            nst = 1
+            if l[22:42].strip():
+                m["station2"], nst = index[l[22:42].strip()], 2
+            if l[42:62].strip():
+                m["station3"], nst = index[l[42:62].strip()], 3
+            m["measurementStations"] = nst
+            if kind in "ABKVZ":          # degrees minutes seconds, standard deviation in seconds
+                sign = -1.0 if f[0].startswith("-") else 1.0
+                m["term1"] = sign * np.radians(abs(float(f[0])) + float(f[1]) / 60.0 + float(f[2]) / 3600.0)
+                m["term2"] = np.radians(float(f[3]) / 3600.0) ** 2
+                rest = f[4:]
+            else:                        # metres
+                m["term1"] = float(f[0])
+                m["term2"] = float(f[1]) ** 2
+                rest = f[2:]
+            if len(rest) >= 2:
+                m["term3"], m["term4"] = float(rest[0]), float(rest[1])   # instrument and target heights
+            m["clusterID"] = cluster
+            m["epoch"] = b"01.01.2020"
+            groups.append(m)
+            cluster += 1
+            i += 1
         elif kind in "XY":
             count = int(l[42:62])
             v, p, lam, h = (float(l[62 + 10 * k:72 + 10 * k]) for k in range(4))
             frame, epoch = l[102:122].strip(), l[122:142].strip()
+            ctype = l[22:42].strip() if kind == "Y" else "XYZ"
             if kind == "Y":
-                assert l[22:42].strip() == "XYZ" and frame == "GDA2020", "only Cartesian GDA2020 point clusters are handled"
+                assert ctype in ("XYZ", "LLH", "LLh") and (not reftran or frame in ("GDA2020", "GDA94")), "point cluster form not handled"
             total = sum(3 + 3 * (count - 1 - k) for k in range(count))
             m = new_msr(total)
-            m["measType"], m["coordType"], m["clusterID"] = kind.encode(), b"XYZ", cluster
+            m["measType"], m["coordType"], m["clusterID"], m["ignore"] = kind.encode(), ctype.encode(), cluster, ignore
             m["measurementStations"] = 2 if kind == "X" else 1
             m["scale1"], m["scale2"], m["scale3"], m["scale4"] = p, lam, h, v
             m["epoch"] = b"01.01.2020"
@@ -136,6 +227,8 @@ def read_measurements(path, stn, reftran=True):
                 r = m[o:o + 3]
                 r["measStart"], r["station1"], r["vectorCount1"], r["vectorCount2"] = [0, 1, 2], s, count, count - 1 - k
                 d = np.array([x[0] for x in vals])
+                if ctype != "XYZ":
+                    d[0], d[1] = dms_to_rad(d[0]), dms_to_rad(d[1])     # latitude and longitude arrive as ddd.mmssss
                 if kind == "X":
                     r["station2"] = index[L[i][22:42].strip()]
                     if reftran and frame.upper() != "GDA2020":

@@ -1,4 +1,5 @@
-"""The reference's own end-to-end golden output pins the oracle and the engine.
+"""The reference's own end-to-end golden outputs pin the oracle and the engine (GNSS sample below; the urban sample
+with every terrestrial type at the end of the file).
 
 tests/golden/gnss_sample.npz (made by tests/golden/make_gnss_sample.py) holds the reference's sample GNSS network
 (43 stations; 129 G baselines, one X cluster of 4 baselines, one Y cluster of 6 points; 417 measurement rows) as binary
@@ -98,3 +99,90 @@ def test_engine_host_logic_reproduces_reference_expected_output(hostsim_path, go
 def test_cuda_path_reproduces_reference_expected_output(gpu_lib, golden):
     _engine(golden, gpu_lib, leaf_stations=8)
     _engine(golden, gpu_lib, ordering=engine.ORDER_DENSE)
+
+
+# ---- the reference's urban sample: terrestrial types against its expected phased adjustment ---------------------
+@pytest.fixture(scope="module")
+def urban():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "urban_sample.npz"))
+    return dict(stn=np.ascontiguousarray(z["stn"].astype(STN_DTYPE)), msr=np.ascontiguousarray(z["msr"].astype(MSR_DTYPE)),
+                sol=dict(zip(z["solution_keys"].tolist(), z["solution"].tolist())), msr_keys=z["msr_keys"].tolist(),
+                msr_rows=z["msr_rows"], stn_names=z["stn_names"].tolist(), stn_rows=z["stn_rows"])
+
+
+SEC = np.radians(1.0 / 3600.0)
+
+
+def _check_urban(g, stn, msr, est, vcv_of, stats):
+    """tests/golden/urban_sample.npz: 149 stations (UTM, mixed constraints CCC / CCF / CFF / FFC), 1182 rows of types
+    A B G H K L M S V Y Z, the Y cluster in latitude / longitude / orthometric height.  Every standard deviation the
+    reference prints (measurement, adjusted measurement, correction; SD e/n/up of the stations) is reproduced at print
+    resolution; values that depend on station heights carry the 0.5 mm rounding of the exported geoid file the fixture
+    is built from (heights to 0.5 mm, zenith angles over 10-100 m lines to 0.5", levelled differences to 1 mm)."""
+    sol = g["sol"]
+    assert stats["unknowns"] == sol["unknowns"] and stats["measurements"] == sol["measurements"] and stats["dof"] == sol["dof"]
+    assert stats["outliers"] == sol["outliers"]
+    assert abs(stats["chi_squared"] - sol["chi_squared"]) < 1.0            # 0.15 %
+    assert abs(stats["sigma_zero"] - sol["sigma_zero"]) < 0.0011 and abs(stats["pelzer"] - sol["pelzer"]) < 0.0011
+    names = [n.decode() for n in stn["stationName"]]
+    for name, row in zip(g["stn_names"], g["stn_rows"]):
+        i = names.index(name)
+        assert np.abs(est[i] - row[4:7]).max() < 5e-4 and abs(stn["currentHeight"][i] - row[3]) < 6e-4, name
+        lat, lon = stn["currentLatitude"][i], stn["currentLongitude"][i]
+        sl, cl, so, co = np.sin(lat), np.cos(lat), np.sin(lon), np.cos(lon)
+        R = np.array([[-so, -sl * co, cl * co], [co, -sl * so, cl * so], [0, cl, sl]])
+        sd = np.sqrt(np.abs(np.diag(R.T @ vcv_of(i) @ R)))
+        assert np.abs(sd - row[7:10]).max() < 0.51e-4, name
+    rows = msr[(msr["measStart"] <= 2) & (msr["ignore"] == 0)]
+    assert len(rows) == len(g["msr_rows"]) == 1182
+    seen = set()
+    for m, key, w in zip(rows, g["msr_keys"], g["msr_rows"]):
+        t = key[0]
+        assert t == chr(m["measType"][0]) and key.split()[1] == names[m["station1"]], key
+        seen.add(t)
+        if t == "Y":
+            continue   # printed back in geographic form (PrintAdjMeasurements_YLLH)
+        ang = t in "ABKVZ"
+        unit = SEC if ang else 1.0
+        var = (m["term2"], m["term3"], m["term4"])[m["measStart"]] if t == "G" else m["term2"]
+        sds = np.array([np.sqrt(var), np.sqrt(abs(m["measAdjPrec"])), np.sqrt(m["residualPrec"])]) / unit
+        assert np.abs(sds - w[3:6]).max() < 0.51e-4 + (1.5e-4 if ang else 0.0), (key, sds, w[3:6])
+        tol_adj = (0.6 if t in "VZ" else 0.05) if ang else 7e-4
+        assert abs(m["measAdj"] - w[1]) / unit < tol_adj and abs(m["measCorr"] / unit - w[2]) < tol_adj, key
+        assert abs(m["NStat"] - w[6]) < 0.07 and abs(m["PelzerRel"] - w[7]) < 0.011, key
+        assert abs(m["preAdjCorr"] / unit - w[8]) < (0.05 if ang else 1e-3), key
+    assert seen == set("ABGHKLMSVYZ")
+
+
+def test_oracle_reproduces_reference_urban_output(oracle, urban):
+    stn, msr = urban["stn"].copy(), urban["msr"].copy()
+    ref = oracle.adjust_simultaneous(stn, msr, want_vcv=True)
+    r, V = ref["res"], ref["vcv"]
+    _check_urban(urban, stn, msr, ref["est"].reshape(-1, 3), lambda i: V[3 * i:3 * i + 3, 3 * i:3 * i + 3],
+                 dict(unknowns=r.unknown_params, measurements=r.measurement_params, dof=r.dof, chi_squared=r.chi_squared,
+                      sigma_zero=r.sigma_zero, pelzer=r.global_pelzer, outliers=r.outliers))
+
+
+def _engine_urban(urban, oracle, lib, tol_sigma0, **kw):
+    stn, msr = urban["stn"].copy(), urban["msr"].copy()
+    adj, info, last, st = parity.run_engine(lib, stn, msr, **kw)
+    q = adj.station_vcvs().reshape(-1, 3, 3)
+    _check_urban(urban, stn, msr, adj.estimates().reshape(-1, 3), lambda i: q[i],
+                 dict(unknowns=st.unknown_params, measurements=st.measurement_params, dof=st.dof, chi_squared=st.chi_squared,
+                      sigma_zero=st.sigma_zero, pelzer=st.global_pelzer, outliers=st.outliers))
+    # and against the oracle at the parity bar: every terrestrial type on the reference's own network
+    s_o, m_o = urban["stn"].copy(), urban["msr"].copy()
+    ref = oracle.adjust_simultaneous(s_o, m_o, want_vcv=False)
+    assert np.abs(adj.estimates() - ref["est"]).max() < parity.TOL_XYZ
+    assert abs(st.sigma_zero - ref["res"].sigma_zero) < tol_sigma0 and last.iteration == ref["res"].iterations
+    adj.close()
+
+
+def test_engine_host_logic_reproduces_reference_urban_output(oracle, hostsim_path, urban):
+    _engine_urban(urban, oracle, hostsim_path, 1e-11, leaf_stations=12)
+
+
+@pytest.mark.gpu
+def test_cuda_path_reproduces_reference_urban_output(oracle, gpu_lib, urban):
+    # trigonometric rows: CUDA's and glibc's libm differ in the last ulp (see tests/test_gpu_parity.py)
+    _engine_urban(urban, oracle, gpu_lib, 1e-7, leaf_stations=12)
