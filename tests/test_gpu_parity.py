@@ -59,6 +59,20 @@ def test_gnss_clusters(oracle, gpu_lib):
                                 leaf_stations=16)
 
 
+def test_point_clusters_in_geographic_form(oracle, gpu_lib):
+    """Y clusters given as latitude / longitude / orthometric height: first-run conversion + variance propagation."""
+    from dynadjust_b200 import synth_terrestrial as st
+    from tests.test_host_logic import _y_clusters_as_llh
+    stn, msr, truth, _ = st.terrestrial_network(120, 300, 47, n_y=25, deflections=False)
+    _y_clusters_as_llh(stn, msr)
+    s_o, m_o = stn.copy(), msr.copy()
+    ref = oracle.adjust_simultaneous(s_o, m_o, want_vcv=False)
+    adj, info, last, stats = parity.run_engine(gpu_lib, stn, msr, leaf_stations=16)
+    assert np.abs(adj.estimates() - ref["est"]).max() < parity.TOL_XYZ
+    assert abs(stats.sigma_zero - ref["res"].sigma_zero) < 1e-11 and stats.dof == ref["res"].dof
+    adj.close()
+
+
 def test_large_gnss_cluster(oracle, gpu_lib):
     """One X cluster of 120 baselines (360 x 360 VCV): the per-cluster Cholesky inverse beyond a single tile."""
     from dynadjust_b200 import synth_terrestrial as st
