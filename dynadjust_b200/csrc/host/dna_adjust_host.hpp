@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 #include <iomanip>
 #include <sstream>
@@ -670,25 +671,48 @@ class dna_adjust {
                  "Pre Adj Corr", "Out");
         os << buf << "\n" << std::string(200, '-') << "\n";
         const double crit = stats_.critical_value;
+        const double SEC = 3.14159265358979323846 / 180.0 / 3600.0;
         for (size_t i = 0; i < msr_.size(); ++i) {
             const dna_msr_t& m = msr_[i];
-            if (m.ignore)
+            if (m.ignore || m.measStart > 2)   // covariance records of X / Y clusters carry no row
                 continue;
-            char comp = ' ';
-            double sd = 0;
-            if (m.measType == 'G') {
-                comp = "XYZ"[(int)m.measStart % 3];
-                sd = m.measStart == 0 ? m.term2 : (m.measStart == 1 ? m.term3 : m.term4);
-            } else
-                sd = m.term2;
+            const char t = m.measType;
+            const bool gnss = t == 'G' || t == 'X' || t == 'Y';
+            // angles (A B D K V Z) and astronomic / geodetic latitudes and longitudes (I J P Q) print as d m s, their
+            // corrections and standard deviations in seconds (PrintAdjMeasurementsAngular, PRN:195-201, 2302-2350)
+            const bool angular = std::strchr("ABDKVZIJPQ", t) != nullptr;
+            char comp = gnss ? "XYZ"[(int)m.measStart] : ' ';
+            const double var = !gnss ? m.term2 : (m.measStart == 0 ? m.term2 : (m.measStart == 1 ? m.term3 : m.term4));
             const char* s1 = stn_[m.station1].stationName;
-            const char* s2 = m.measurementStations >= 2 ? stn_[m.station2].stationName : "";
-            snprintf(buf, sizeof(buf), "%-2c%-20s%-20s%-20s%-3s%-2c%19.4f%19.4f%12.4f%13.4f%13.4f%13.4f%11.2f%12.2f%14.4f%7s", m.measType, s1,
-                     s2, "", "", comp, m.preAdjMeas, m.measAdj, m.measCorr, std::sqrt(sd), std::sqrt(std::fabs(m.measAdjPrec)),
-                     std::sqrt(m.residualPrec), m.NStat, m.PelzerRel, m.preAdjCorr, std::fabs(m.NStat) > crit ? "*" : "");
+            const char* s2 = (m.measurementStations >= 2 && t != 'Y') ? stn_[m.station2].stationName : "";
+            const char* s3 = (m.measurementStations >= 3 && t == 'A') ? stn_[m.station3].stationName : "";
+            const double unit = angular ? SEC : 1.0;
+            char meas[32], adjd[32];
+            if (angular) {
+                snprintf(meas, sizeof(meas), "%s", dms_spaced(m.preAdjMeas).c_str());
+                snprintf(adjd, sizeof(adjd), "%s", dms_spaced(m.measAdj).c_str());
+            } else {
+                snprintf(meas, sizeof(meas), "%.4f", m.preAdjMeas);
+                snprintf(adjd, sizeof(adjd), "%.4f", m.measAdj);
+            }
+            snprintf(buf, sizeof(buf), "%-2c%-20s%-20s%-20s%-3s%-2c%19s%19s%12.4f%13.4f%13.4f%13.4f%11.2f%12.2f%14.4f%7s", t, s1, s2, s3, "",
+                     comp, meas, adjd, m.measCorr / unit, std::sqrt(var) / unit, std::sqrt(std::fabs(m.measAdjPrec)) / unit,
+                     std::sqrt(m.residualPrec) / unit, m.NStat, m.PelzerRel, m.preAdjCorr / unit, std::fabs(m.NStat) > crit ? "*" : "");
             os << buf << "\n";
         }
         os << "\n";
+    }
+
+    // "ddd mm ss.ssss" (FormatDmsString with spaces on a RadtoDms value, 4 decimals of a second)
+    static std::string dms_spaced(double rad)
+    {
+        const double deg = std::fabs(rad) * 180.0 / 3.14159265358979323846;
+        long long units = std::llround(deg * 3600.0 * 10000.0);   // ten-thousandths of a second: carries are exact
+        const long long d = units / (3600LL * 10000), rem = units % (3600LL * 10000);
+        const long long mi = rem / (60LL * 10000), sec = rem % (60LL * 10000);
+        char b[48];
+        snprintf(b, sizeof(b), "%s%lld %02lld %02lld.%04lld", rad < 0 ? "-" : "", d, mi, sec / 10000, sec % 10000);
+        return b;
     }
 
     void PrintAdjStations(std::ostream& os, const std::vector<uint32_t>* subset) const

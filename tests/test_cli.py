@@ -259,6 +259,48 @@ def test_cli_block_outputs(cli_hostsim, oracle, tmp_path):
     assert sorted(rows) == sorted(stn["stationName"][i].decode() for i in set(isl[0]) | set(jsl[0]))
 
 
+def _golden_gnss_text(exe, tmp_path):
+    """The reference's CI check, on our command line: run `dnaadjust gnss --output-adj-msr` on the reference's sample
+    GNSS network (tests/golden/gnss_sample.npz) and compare the .adj text with the reference's expected file
+    (dnadiff compares numeric fields at 0.001; here 1.1e-4 = print rounding on both sides)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "gnss_sample.npz"))
+    stn, msr = np.ascontiguousarray(z["stn"].astype(STN_DTYPE)), np.ascontiguousarray(z["msr"].astype(MSR_DTYPE))
+    _write_network(tmp_path, "gnss", stn, msr)
+    r = _run(exe, tmp_path, "gnss", "--output-adj-msr", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    adj = open(os.path.join(tmp_path, "gnss.simult.adj")).read()
+    sol, want = _solution_block(adj), dict(zip(z["solution_keys"].tolist(), z["solution"].tolist()))
+    assert sol["unknowns"] == want["unknowns"] and sol["measurements"] == want["measurements"] and sol["dof"] == want["dof"]
+    assert sol["chi"] == want["chi_squared"] and sol["sigma0"] == want["sigma_zero"] and sol["pelzer"] == want["pelzer"]
+    assert sol["outliers"] == want["outliers"] and sol["iterations"] == want["iterations"] and sol["converged"]
+    m = re.search(r"Chi-Square test \(95.0%\)\s+(\S+) < \S+ < (\S+)", adj)
+    assert abs(float(m.group(1)) - want["chi_lower"]) < 0.0011 and abs(float(m.group(2)) - want["chi_upper"]) < 0.0011
+    body = adj.split("Adjusted Measurements")[1].split("Adjusted Coordinates")[0]
+    lines = [l for l in body.splitlines() if re.match(r"^[GXY] \S", l)]
+    assert len(lines) == len(z["msr_rows"]) == 417
+    for l, key, row in zip(lines, z["msr_keys"].tolist(), z["msr_rows"]):
+        f = l.split()
+        k = next(i for i in range(2, len(f)) if f[i] in ("X", "Y", "Z") and re.fullmatch(r"-?\d+\.\d+", f[i + 1]))
+        assert " ".join([f[0]] + f[1:k] + [f[k]]) == key
+        got = np.array([float(x) for x in f[k + 1:k + 10]])
+        assert np.abs(got[:6] - row[:6]).max() < 1.1e-4 and np.abs(got[6:8] - row[6:8]).max() < 0.0101, (key, got, row)
+        assert ("*" in f[k + 10:]) == (abs(row[6]) > 1.96)
+    rows = _station_table(adj)
+    for name, row in zip(z["stn_names"].tolist(), z["stn_rows"]):
+        got = np.array(rows[name])
+        assert np.abs(got[[0, 1]] - row[[0, 1]]).max() < 2e-9          # latitude, longitude as ddd.mmsssssss
+        assert np.abs(got[3:10] - row[3:10]).max() < 1.1e-4, name       # h, X Y Z, SD e n up
+
+
+def test_cli_reproduces_reference_expected_adj_hostsim(cli_hostsim, tmp_path):
+    _golden_gnss_text(cli_hostsim, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_reproduces_reference_expected_adj_gpu(cli_gpu, tmp_path):
+    _golden_gnss_text(cli_gpu, tmp_path)
+
+
 def test_cli_apu_cor_hostsim(cli_hostsim, oracle, tmp_path):
     _apu_cor(cli_hostsim, oracle, tmp_path)
 
