@@ -692,7 +692,10 @@ class dna_adjust {
                 snprintf(meas, sizeof(meas), "%s", dms_spaced(m.preAdjMeas).c_str());
                 snprintf(adjd, sizeof(adjd), "%s", dms_spaced(m.measAdj).c_str());
             } else {
-                snprintf(meas, sizeof(meas), "%.4f", m.preAdjMeas);
+                // point clusters that arrived as latitude / longitude / height are reported in the Cartesian form they were
+                // adjusted in (the reference converts these rows back to P / L / H for printing, PRN:2488-2660)
+                const bool from_llh = t == 'Y' && (m.station3 == DNA_LLH_TYPE || m.station3 == DNA_LLh_TYPE);
+                snprintf(meas, sizeof(meas), "%.4f", from_llh ? m.term1 : m.preAdjMeas);
                 snprintf(adjd, sizeof(adjd), "%.4f", m.measAdj);
             }
             snprintf(buf, sizeof(buf), "%-2c%-20s%-20s%-20s%-3s%-2c%19s%19s%12.4f%13.4f%13.4f%13.4f%11.2f%12.2f%14.4f%7s", t, s1, s2, s3, "",
