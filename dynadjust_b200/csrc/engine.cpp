@@ -690,7 +690,7 @@ int scan_measurements(gadj_ctx* c)
                 }
             } else if (m.measType == 'X' || m.measType == 'Y') {
                 if (m.measType == 'Y' && std::strncmp(m.coordType, "XYZ", 3) != 0)
-                    return c->fail("GNSS point clusters 'Y' are handled in Cartesian (XYZ) form only");
+                    return c->fail("GNSS point cluster 'Y': coordinates must be XYZ, LLH or LLh");
                 const uint32_t row0 = (uint32_t)c->rows.size();
                 uint64_t j = i;
                 for (uint32_t k = 0; k < m.vectorCount1; ++k) {
@@ -817,16 +817,18 @@ int first_run_reduction_rows(gadj_ctx* c, const double* est)
         if (hS < lim)
             hS = 1.0;
         bool scaleMatrix = std::fabs(vS - 1.0) > 1.0e-5;
-        const bool scalePartial = std::fabs(pS - 1.0) > 1.0e-5 || std::fabs(lS - 1.0) > 1.0e-5 || std::fabs(hS - 1.0) > 1.0e-5;
+        bool scalePartial = std::fabs(pS - 1.0) > 1.0e-5 || std::fabs(lS - 1.0) > 1.0e-5 || std::fabs(hS - 1.0) > 1.0e-5;
         if (c->reduced)
-            scaleMatrix = false;
-        else if (scalePartial)
-            return c->fail("phi / lambda / height variance scalars on X / Y clusters are not handled yet (whole-matrix scalar only)");
-        auto put = [&](uint32_t r, uint32_t col, double& field) {
-            if (scaleMatrix)
-                field *= vS;   // written back: later consumers read the scaled matrix (SetGPSVarianceMatrix, ADJ:4425)
-            V[(size_t)r * n + col] = V[(size_t)col * n + r] = field;
-        };
+            scaleMatrix = scalePartial = false;    // the records already hold the scaled matrix
+        if (scalePartial && scaleMatrix) {         // LoadVarianceScaling (ADJ:4484-4490)
+            pS *= vS;
+            lS *= vS;
+            hS *= vS;
+        }
+        // X clusters take the whole-matrix scalar while loading (ADJ:4358-4392) — also when partial scalars follow —
+        // Y clusters afterwards and only without partial scalars (ADJ:4646-4647)
+        const double onload = (cd.type == 'X' && scaleMatrix) ? vS : 1.0;
+        auto put = [&](uint32_t r, uint32_t col, double field) { V[(size_t)r * n + col] = V[(size_t)col * n + r] = field * onload; };
         for (uint32_t k = 0; k < members; ++k) {
             dna_msr_t* r = &msr[c->rows[cd.row0 + 3 * k].rec];
             for (int q = 0; q < 3; ++q) {
@@ -855,6 +857,61 @@ int first_run_reduction_rows(gadj_ctx* c, const double* est)
                     put(v + x, cc, cv[x].term1);
                     put(v + x, cc + 1, cv[x].term2);
                     put(v + x, cc + 2, cv[x].term3);
+                }
+            }
+        }
+        if (scalePartial) {
+            // ScaleGPSVCV_Cluster (MFN:401-438): V' = (J S J^-1) V (J S J^-1)^T block by block, J = d(XYZ)/d(lat, lon, h) at
+            // the member's first station, S = diag(sqrt p, sqrt l, sqrt h)
+            std::vector<double> M((size_t)members * 9), W((size_t)n * n);
+            for (uint32_t k = 0; k < members; ++k) {
+                const dna_stn_t& st = c->stn[msr[c->rows[cd.row0 + 3 * k].rec].station1];
+                double J[9], Ji[9];
+                cart_geo_jacobian(c->ell, st.currentLatitude, st.currentLongitude, st.currentHeight, J);
+                if (!mat3_inverse(J, Ji))
+                    return c->fail("variance scaling: singular geographic Jacobian");
+                const double sc[3] = {std::sqrt(pS), std::sqrt(lS), std::sqrt(hS)};
+                for (int a = 0; a < 3; ++a)
+                    for (int b2 = 0; b2 < 3; ++b2)
+                        M[9 * (size_t)k + 3 * a + b2] = J[3 * a] * sc[0] * Ji[b2] + J[3 * a + 1] * sc[1] * Ji[3 + b2] + J[3 * a + 2] * sc[2] * Ji[6 + b2];
+            }
+            for (uint32_t ka = 0; ka < members; ++ka)
+                for (uint32_t kb = 0; kb < members; ++kb) {
+                    double T[9];
+                    for (int x = 0; x < 3; ++x)
+                        for (int y = 0; y < 3; ++y)
+                            T[3 * x + y] = M[9 * (size_t)ka + 3 * x] * V[(size_t)(3 * ka) * n + 3 * kb + y] +
+                                           M[9 * (size_t)ka + 3 * x + 1] * V[(size_t)(3 * ka + 1) * n + 3 * kb + y] +
+                                           M[9 * (size_t)ka + 3 * x + 2] * V[(size_t)(3 * ka + 2) * n + 3 * kb + y];
+                    for (int x = 0; x < 3; ++x)
+                        for (int y = 0; y < 3; ++y)
+                            W[(size_t)(3 * ka + x) * n + 3 * kb + y] = T[3 * x] * M[9 * (size_t)kb + 3 * y] + T[3 * x + 1] * M[9 * (size_t)kb + 3 * y + 1] +
+                                                                   T[3 * x + 2] * M[9 * (size_t)kb + 3 * y + 2];
+                }
+            std::copy(W.begin(), W.end(), V);
+        } else if (cd.type == 'Y' && scaleMatrix) {
+            for (size_t x = 0; x < (size_t)n * n; ++x)
+                V[x] *= vS;
+        }
+        if (scaleMatrix || scalePartial) {
+            // written back: later consumers read the scaled matrix (SetGPSVarianceMatrix, ADJ:4425, 4654)
+            for (uint32_t k = 0; k < members; ++k) {
+                dna_msr_t* r = &msr[c->rows[cd.row0 + 3 * k].rec];
+                const uint32_t v = 3 * k;
+                r[0].term2 = V[(size_t)v * n + v];
+                r[1].term2 = V[(size_t)v * n + v + 1];
+                r[1].term3 = V[(size_t)(v + 1) * n + v + 1];
+                r[2].term2 = V[(size_t)v * n + v + 2];
+                r[2].term3 = V[(size_t)(v + 1) * n + v + 2];
+                r[2].term4 = V[(size_t)(v + 2) * n + v + 2];
+                for (uint32_t q = 0; q < r[0].vectorCount2; ++q) {
+                    dna_msr_t* cv = r + 3 + 3 * q;
+                    const uint32_t cc = v + 3 + 3 * q;
+                    for (uint32_t x = 0; x < 3; ++x) {
+                        cv[x].term1 = V[(size_t)(v + x) * n + cc];
+                        cv[x].term2 = V[(size_t)(v + x) * n + cc + 1];
+                        cv[x].term3 = V[(size_t)(v + x) * n + cc + 2];
+                    }
                 }
             }
         }

@@ -668,20 +668,16 @@ int load_variance_matrix_XY(Ctx& c, Meas& me, bool build)
     load_variance_scaling(c, *m0, vS, pS, lS, hS, scaleMatrix, scalePartial);
     if (!build)
         scaleMatrix = scalePartial = false;   // the records already hold the scaled matrix (ADJ:4281)
-    if (scalePartial) {
-        g_err = "oracle: phi/lambda/height variance scalars on X/Y clusters are not restated";
-        return 3;
-    }
     if (me.type == 'Y' && std::strncmp(m0->coordType, "XYZ", 3) != 0) {
         g_err = "oracle: Y cluster coordinates must be XYZ, LLH or LLh";
         return 3;
     }
     std::vector<double> V((size_t)n * n, 0.0);
-    auto put = [&](uint32_t r, uint32_t col, double& field) {
-        if (scaleMatrix)
-            field *= vS;   // SetGPSVarianceMatrix writes the scaled value back
-        V[(size_t)col * n + r] = field;
-        V[(size_t)r * n + col] = field;
+    // X clusters apply the whole-matrix scalar while loading (ADJ:4358-4392), Y clusters afterwards and only when no
+    // partial scalars are given (ADJ:4646-4647)
+    const double onload = (me.type == 'X' && scaleMatrix) ? vS : 1.0;
+    auto put = [&](uint32_t r, uint32_t col, double field) {
+        V[(size_t)col * n + r] = V[(size_t)r * n + col] = field * onload;
     };
     for (uint32_t k = 0; k < members; ++k) {
         dna_msr_t* r = &c.msr[me.rec[k]];
@@ -700,6 +696,80 @@ int load_variance_matrix_XY(Ctx& c, Meas& me, bool build)
                 put(v + i, cc, cv[i].term1);
                 put(v + i, cc + 1, cv[i].term2);
                 put(v + i, cc + 2, cv[i].term3);
+            }
+        }
+    }
+    if (scalePartial) {
+        // ScaleGPSVCV_Cluster (MFN:401-438): to the geographic frame with the Jacobians at the first stations' current
+        // positions, scale by sqrt(p), sqrt(l), sqrt(h) (already multiplied by the whole-matrix scalar when both are
+        // given, ADJ:4484-4490), back to Cartesian:  V' = (J S J^-1) V (J S J^-1)^T  block by block
+        std::vector<double> M((size_t)members * 9);
+        for (uint32_t k = 0; k < members; ++k) {
+            const dna_stn_t& st = c.stn[c.msr[me.rec[k]].station1];
+            double J[9], Ji[9];
+            geo_to_cart_jacobian(c.ell, st.currentLatitude, st.currentLongitude, st.currentHeight, J);
+            const double det = J[0] * (J[4] * J[8] - J[5] * J[7]) - J[1] * (J[3] * J[8] - J[5] * J[6]) + J[2] * (J[3] * J[7] - J[4] * J[6]);
+            Ji[0] = (J[4] * J[8] - J[5] * J[7]) / det;
+            Ji[1] = (J[2] * J[7] - J[1] * J[8]) / det;
+            Ji[2] = (J[1] * J[5] - J[2] * J[4]) / det;
+            Ji[3] = (J[5] * J[6] - J[3] * J[8]) / det;
+            Ji[4] = (J[0] * J[8] - J[2] * J[6]) / det;
+            Ji[5] = (J[2] * J[3] - J[0] * J[5]) / det;
+            Ji[6] = (J[3] * J[7] - J[4] * J[6]) / det;
+            Ji[7] = (J[1] * J[6] - J[0] * J[7]) / det;
+            Ji[8] = (J[0] * J[4] - J[1] * J[3]) / det;
+            const double sc[3] = {std::sqrt(pS), std::sqrt(lS), std::sqrt(hS)};
+            for (int a = 0; a < 3; ++a)
+                for (int b2 = 0; b2 < 3; ++b2) {
+                    double sum = 0.0;
+                    for (int z = 0; z < 3; ++z)
+                        sum += J[3 * a + z] * sc[z] * Ji[3 * z + b2];
+                    M[9 * (size_t)k + 3 * a + b2] = sum;
+                }
+        }
+        std::vector<double> W((size_t)n * n, 0.0);
+        for (uint32_t ka = 0; ka < members; ++ka)
+            for (uint32_t kb = 0; kb < members; ++kb) {
+                double T[9];
+                for (int x = 0; x < 3; ++x)
+                    for (int y = 0; y < 3; ++y) {
+                        double sum = 0.0;
+                        for (int z = 0; z < 3; ++z)
+                            sum += M[9 * (size_t)ka + 3 * x + z] * V[(size_t)(3 * ka + z) * n + 3 * kb + y];
+                        T[3 * x + y] = sum;
+                    }
+                for (int x = 0; x < 3; ++x)
+                    for (int y = 0; y < 3; ++y) {
+                        double sum = 0.0;
+                        for (int z = 0; z < 3; ++z)
+                            sum += T[3 * x + z] * M[9 * (size_t)kb + 3 * y + z];
+                        W[(size_t)(3 * ka + x) * n + 3 * kb + y] = sum;
+                    }
+            }
+        V.swap(W);
+    } else if (me.type == 'Y' && scaleMatrix) {
+        for (double& x : V)
+            x *= vS;
+    }
+    if (scaleMatrix || scalePartial) {
+        // SetGPSVarianceMatrix: the scaled matrix replaces the record values (ADJ:4425, 4654)
+        for (uint32_t k = 0; k < members; ++k) {
+            dna_msr_t* r = &c.msr[me.rec[k]];
+            const uint32_t v = 3 * k;
+            r[0].term2 = V[(size_t)v * n + v];
+            r[1].term2 = V[(size_t)v * n + v + 1];
+            r[1].term3 = V[(size_t)(v + 1) * n + v + 1];
+            r[2].term2 = V[(size_t)v * n + v + 2];
+            r[2].term3 = V[(size_t)(v + 1) * n + v + 2];
+            r[2].term4 = V[(size_t)(v + 2) * n + v + 2];
+            for (uint32_t q = 0; q < r[0].vectorCount2; ++q) {
+                dna_msr_t* cv = r + 3 + 3 * q;
+                const uint32_t cc = v + 3 + 3 * q;
+                for (int i = 0; i < 3; ++i) {
+                    cv[i].term1 = V[(size_t)(v + i) * n + cc];
+                    cv[i].term2 = V[(size_t)(v + i) * n + cc + 1];
+                    cv[i].term3 = V[(size_t)(v + i) * n + cc + 2];
+                }
             }
         }
     }

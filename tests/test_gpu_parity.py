@@ -73,6 +73,21 @@ def test_point_clusters_in_geographic_form(oracle, gpu_lib):
     adj.close()
 
 
+def test_cluster_partial_variance_scalars(oracle, gpu_lib):
+    """phi / lambda / height variance scalars on X and Y clusters, with and without the whole-matrix scalar."""
+    from dynadjust_b200 import synth_terrestrial as st
+    stn, msr, truth, _ = st.terrestrial_network(120, 300, 48, n_x=12, n_y=12, deflections=False)
+    c = np.isin(msr["measType"], (b"X", b"Y"))
+    msr["scale1"][c], msr["scale2"][c], msr["scale3"][c] = 1.7, 0.6, 2.5
+    msr["scale4"][c & (msr["clusterID"] % 2 == 1)] = 3.0
+    s_o, m_o = stn.copy(), msr.copy()
+    ref = oracle.adjust_simultaneous(s_o, m_o, want_vcv=False)
+    adj, info, last, stats = parity.run_engine(gpu_lib, stn, msr, leaf_stations=16)
+    assert np.abs(adj.estimates() - ref["est"]).max() < parity.TOL_XYZ
+    assert abs(stats.sigma_zero - ref["res"].sigma_zero) < 1e-11
+    adj.close()
+
+
 def test_large_gnss_cluster(oracle, gpu_lib):
     """One X cluster of 120 baselines (360 x 360 VCV): the per-cluster Cholesky inverse beyond a single tile."""
     from dynadjust_b200 import synth_terrestrial as st

@@ -169,6 +169,71 @@ def test_point_clusters_in_geographic_form(oracle, hostsim_path):
     adj.close()
 
 
+def _cluster_matrix(msr, first):
+    count = int(msr["vectorCount1"][first])
+    rec, j = [], first
+    for _ in range(count):
+        rec.append(j)
+        j += 3 + 3 * int(msr["vectorCount2"][j])
+    n = 3 * count
+    V = np.zeros((n, n))
+    for k, r in enumerate(rec):
+        v = 3 * k
+        V[v, v], V[v, v + 1], V[v + 1, v + 1] = msr["term2"][r], msr["term2"][r + 1], msr["term3"][r + 1]
+        V[v, v + 2], V[v + 1, v + 2], V[v + 2, v + 2] = msr["term2"][r + 2], msr["term3"][r + 2], msr["term4"][r + 2]
+        for q in range(int(msr["vectorCount2"][r])):
+            for x in range(3):
+                cv = r + 3 + 3 * q + x
+                V[v + x, v + 3 + 3 * q:v + 6 + 3 * q] = msr["term1"][cv], msr["term2"][cv], msr["term3"][cv]
+    return np.triu(V) + np.triu(V, 1).T, rec
+
+
+def test_cluster_partial_variance_scalars(oracle, hostsim_path):
+    """phi / lambda / height variance scalars on X and Y clusters (ScaleGPSVCV_Cluster, MFN:401-438), alone and together
+    with the whole-matrix scalar — for X clusters the reference then applies the whole-matrix scalar twice (while
+    loading, ADJ:4358, and inside the partial scalars, ADJ:4484-4490); restated as is.  The matrix written back into
+    the records is checked against a NumPy evaluation; the engine against the oracle."""
+    from dynadjust_b200 import synth_terrestrial as st
+    stn, msr, truth, _ = st.terrestrial_network(120, 300, 48, n_x=12, n_y=12, deflections=False)
+    firsts = [i for i in range(len(msr)) if msr["measType"][i] in (b"X", b"Y") and msr["measStart"][i] == 0 and
+              (i == 0 or msr["clusterID"][i] != msr["clusterID"][i - 1])]
+    for n_, i in enumerate(firsts):
+        cid = msr["clusterID"][i]
+        sel = (msr["clusterID"] == cid) & np.isin(msr["measType"], (b"X", b"Y"))
+        msr["scale1"][sel], msr["scale2"][sel], msr["scale3"][sel] = 1.7, 0.6, 2.5
+        msr["scale4"][sel] = 3.0 if n_ % 2 else 1.0
+    raw = msr.copy()
+    s_o, m_o = stn.copy(), msr.copy()
+    ref = oracle.adjust_simultaneous(s_o, m_o, want_vcv=False)
+    for i in firsts:
+        V, rec = _cluster_matrix(raw, i)
+        kind, vs = raw["measType"][i], float(raw["scale4"][i])
+        both = abs(vs - 1.0) > 1e-5
+        if kind == b"X" and both:
+            V = V * vs
+        sc = np.sqrt(np.array([1.7, 0.6, 2.5]) * (vs if both else 1.0))
+        M = np.zeros_like(V)
+        for k, r in enumerate(rec):
+            s = int(raw["station1"][r])
+            la, lo, hh = stn["currentLatitude"][s], stn["currentLongitude"][s], stn["currentHeight"][s]
+            f = lambda a, b, c: synth.geo_to_cart(np.array([a]), np.array([b]), np.array([c]))[0]
+            eps = 1e-7
+            J = np.stack([(f(la + eps, lo, hh) - f(la - eps, lo, hh)) / (2 * eps), (f(la, lo + eps, hh) - f(la, lo - eps, hh)) / (2 * eps),
+                          (f(la, lo, hh + 1.0) - f(la, lo, hh - 1.0)) / 2.0], axis=1)
+            M[3 * k:3 * k + 3, 3 * k:3 * k + 3] = J @ np.diag(sc) @ np.linalg.inv(J)
+        want = M @ V @ M.T
+        got, _ = _cluster_matrix(m_o, i)
+        assert np.abs(got - want).max() < 2e-7 * np.abs(want).max(), (kind, vs)
+    s_e, m_e = stn.copy(), msr.copy()
+    adj, info, last, stats = parity.run_engine(hostsim_path, s_e, m_e, leaf_stations=16)
+    assert np.abs(adj.estimates() - ref["est"]).max() < parity.TOL_XYZ
+    assert abs(stats.sigma_zero - ref["res"].sigma_zero) < 1e-11
+    c = np.isin(m_e["measType"], (b"X", b"Y"))
+    for fld in ("term1", "term2", "term3", "term4"):
+        assert np.abs(m_e[fld][c] - m_o[fld][c]).max() <= 1e-12 * max(1.0, np.abs(m_o[fld][c]).max()), fld
+    adj.close()
+
+
 def test_all_types_together(oracle, hostsim_path):
     """BASELINE config C3's mix and more: every type in one network, nested dissection and a chain of blocks."""
     mix = dict(scalars={k: 50 for k in "ABKCEMSVZLHRIJPQ"}, n_dir_sets=40, n_x=20, n_y=20, ignore_some=True)
@@ -224,10 +289,10 @@ def test_error_paths(hostsim_path):
     with pytest.raises(engine.AdjustmentError, match="not a DynAdjust measurement type"):
         adj.prepare()
     from dynadjust_b200 import synth_terrestrial
-    s2, m2, _, _ = synth_terrestrial.terrestrial_network(40, 100, 3, n_x=4)
-    m2["scale1"][m2["measType"] == b"X"] = 2.0     # phi scalar on a cluster: refused, not silently ignored
+    s2, m2, _, _ = synth_terrestrial.terrestrial_network(40, 100, 3, n_y=4)
+    m2["coordType"][m2["measType"] == b"Y"] = b"UTM"   # a coordinate form the reference's Y clusters do not have: refused
     a2 = engine.Adjustment(s2, m2, lib_path=hostsim_path)
-    with pytest.raises(engine.AdjustmentError, match="not handled yet"):
+    with pytest.raises(engine.AdjustmentError, match="XYZ, LLH or LLh"):
         a2.prepare()
     s3, m3, _, _ = synth_terrestrial.terrestrial_network(40, 100, 3, n_y=4)
     ycl = np.where(m3["measType"] == b"Y")[0]
