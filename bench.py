@@ -32,7 +32,7 @@ BYTES_PER_BASELINE = 944   # 3*208 records + 8 plan words + 48 station XYZ + 27*
 
 WORKLOADS = {
     # name: (synth config, engine options)
-    "C4": ("C4", dict(leaf_stations=128)),
+    "C4": ("C4", dict(leaf_stations=64)),      # leaf sweep on the current kernels: profiles/r1_leaf_sweep_c4.json
     "C3g": ("C3g", dict(leaf_stations=96)),
     "C2": ("C2", dict(leaf_stations=96)),
     "C1": ("C1", dict(leaf_stations=16)),
