@@ -32,6 +32,7 @@ enum GemmFlags : int32_t {
     GEMM_KLO_ROW = 16,  // A is upper triangular (zero for k < row): start the K loop at the tile's first row
     GEMM_KLO_MAX = 32,  // A and B upper triangular: start the K loop at max(first row, first column) of the tile
     GEMM_KHI_ROW = 64,  // A is lower triangular (zero for k > row): end the K loop after the tile's last row
+    GEMM_DUAL = 128,    // also store the transpose: Ct[j][i] = C[i][j] (row-major, pitch ldct); not with ACCUM / LOWER / SCATTER
     GEMM_SCATTER = 8,   // Schur update of a front, scattered into its ancestors' panels: column j belongs to boundary
                         // station j/3, whose owning ancestor is target t = coltgt[j/3]; element (i, j) is added
                         // atomically to tgt[t].C at row 3*tgt[t].rowmap[i/3 - tgt[t].jb] + i%3 and column
@@ -55,6 +56,8 @@ struct alignas(64) GemmOp {
     double* C;
     const int32_t* coltgt;   // GEMM_SCATTER: per boundary station, index into tgt
     const ScatterTarget* tgt;
+    double* Ct;              // GEMM_DUAL: transposed copy of the result
+    int64_t ldct;
     int64_t lda, ldb, ldc;
     int32_t M, N, K;
     int32_t flags;

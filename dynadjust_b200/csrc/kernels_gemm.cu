@@ -315,6 +315,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 const int c0 = col0 + wn + 16 * p + 4 * t;
                 double v[4] = {alpha * acc[i][2 * p][0], alpha * acc[i][2 * p + 1][0], alpha * acc[i][2 * p][1],
                                alpha * acc[i][2 * p + 1][1]};
+                if (flags & GEMM_DUAL) {
+                    // transposed copy (e.g. Z21^T next to Z21): lanes of a quad write four neighbouring rows of Ct, the
+                    // eight quads of the warp eight elements 2 apart along a row; the (i&1) partner instruction fills the gaps
+                    double* __restrict__ ct = op->Ct + (int64_t)c0 * op->ldct + r;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (c0 + e < N)
+                            ct[(int64_t)e * op->ldct] = v[e];
+                }
                 if (c0 + 3 < N && (!lower || r + tri_off >= c0 + 3)) {
                     double2* q = reinterpret_cast<double2*>(crow + c0);
                     if (accum) {

@@ -417,7 +417,6 @@ struct Builder {
     void build_selinv_chunk(const std::vector<uint32_t>& chunk, const std::vector<size_t>& base, size_t used, int level)
     {
         std::vector<GemmOp> gb;
-        std::vector<TransposeOp> trb;
         std::vector<GatherOp> gab;
         // no clearing of the workspace: every tile that is read has been written before (the K-range
         // flags keep the triangular products inside the written tiles)
@@ -454,7 +453,7 @@ struct Builder {
                      (int)f.k, GEMM_KLO_ROW);
         }
         flush_gemm(gb, p.selinv, level, T_YT);
-        // Z21 = -G * Y   (overwrites L21)
+        // Z21 = -G * Y   (overwrites L21), with its transpose Z21t stored by the same epilogue
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];
             if (!f.r)
@@ -462,25 +461,11 @@ struct Builder {
             SelinvWs w = ws_layout(f);
             double* ws = b.pool + base[i];
             add_gemm(gb, ws + w.G, w.ldg, ws + w.Yt, w.ldr, panel(f) + (size_t)f.k * f.ldk, f.ldk, (int)f.r, (int)f.k,
-                     (int)f.r, GEMM_NEG);
+                     (int)f.r, GEMM_NEG | GEMM_DUAL);
+            gb.back().Ct = ws + w.Z21t;
+            gb.back().ldct = w.ldr;
         }
         flush_gemm(gb, p.selinv, level, T_Z21);
-        for (size_t i = 0; i < chunk.size(); ++i) {
-            const Front& f = s.fronts[chunk[i]];
-            if (!f.r)
-                continue;
-            SelinvWs w = ws_layout(f);
-            double* ws = b.pool + base[i];
-            TransposeOp t{};
-            t.src = panel(f) + (size_t)f.k * f.ldk;
-            t.dst = ws + w.Z21t;
-            t.lds = f.ldk;
-            t.ldd = w.ldr;
-            t.rows = (int32_t)f.r;
-            t.cols = (int32_t)f.k;
-            trb.push_back(t);
-        }
-        flush_simple(trb, p.transpose, L_TRANSPOSE, p.selinv, level);
         // Z11 = Wt Wt^T   (overwrites L11, lower triangle)
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];

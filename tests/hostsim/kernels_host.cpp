@@ -54,8 +54,11 @@ void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles,
                     tg.C[r * tg.ldc + c] += v;
                 } else if (op.flags & GEMM_ACCUM)
                     op.C[(int64_t)i * op.ldc + j] += v;
-                else
+                else {
                     op.C[(int64_t)i * op.ldc + j] = v;
+                    if (op.flags & GEMM_DUAL)
+                        op.Ct[(int64_t)j * op.ldct + i] = v;
+                }
             }
     }
 }
