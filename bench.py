@@ -39,6 +39,11 @@ WORKLOADS = {
 }
 
 
+def workload_name(key, cfg):
+    return (f"{key}: {cfg['n_stations']} stations / {cfg['n_baselines']} GNSS baselines, "
+            "one Gauss-Newton iteration = assemble + factorise + solve + rigorous (selected) inverse")
+
+
 def ncu_traffic(*kernels):
     """DRAM bytes per launch of the named kernel(s), summed, from the committed ncu capture of this workload
     (profiles/r1_ncu_dram_traffic_c4.json: dram__bytes_read.sum + dram__bytes_write.sum, C4 on one GPU)."""
@@ -179,7 +184,9 @@ def run_reference(args):
     line = dict(metric=METRIC, value=base["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=base["value"], higher_is_better=False, scaling="strong", vs_baseline=None, dtype="f64",
                 data="synthetic", impl="reference",
-                config=dict(workload=f"{args.workload}: {cfg['n_stations']} stations / {cfg['n_baselines']} GNSS baselines"),
+                config=dict(workload=workload_name(args.workload, cfg),
+                            note="the reference's per-block dense CPU path (oracle + compiled reference matrix_2d) on a bounded sample "
+                                 "of dnasegment-size blocks, extrapolated to the network; forward pass only"),
                 cpu_baseline=base,
                 e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
@@ -309,8 +316,7 @@ def run_engine(args):
     line = dict(metric=METRIC, value=ms_step, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_step, higher_is_better=False, scaling="strong", vs_baseline=None, dtype="f64",
                 data="synthetic",
-                config=dict(workload=f"{args.workload}: {cfg['n_stations']} stations / {cfg['n_baselines']} GNSS baselines, "
-                                     "one Gauss-Newton iteration = assemble + factorise + solve + rigorous (selected) inverse",
+                config=dict(workload=workload_name(args.workload, cfg),
                             ordering=f"nested dissection, leaf {eng_opts.get('leaf_stations')} stations",
                             fronts=int(info.nfronts), levels=int(info.nlevels), l2_note="inputs larger than L2",
                             sharding=(f"{world} ranks, subtrees of the dissection tree; {info.top_fronts} shared top fronts "
