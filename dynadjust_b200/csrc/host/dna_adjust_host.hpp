@@ -39,6 +39,7 @@ struct adjust_settings {            // the fields of project_settings.a / .g / .
     bool scale_normals_to_unity = false;
     bool output_adj_msr = false;
     bool output_stn_blocks = false;        // --output-stn-blocks: phased modes print the station tables block by block
+    bool output_msr_blocks = false;        // --output-msr-blocks: likewise the adjusted measurements
     bool output_pos_uncertainty = false;   // --output-pos-uncertainty: <net>.<mode>.apu
     bool output_corrections = false;       // --output-corrections-file: <net>.<mode>.cor
     bool apu_vcv_enu = false;              // --output-apu-vcv-units ENU (default XYZ)
@@ -168,7 +169,7 @@ class dna_adjust {
             PrintIteration(adj, (uint32_t)i + 1, iterations_[i]);
         PrintStatistics(adj);
         if (a_.output_adj_msr)
-            PrintAdjMeasurements(adj);
+            PrintAdjustedNetworkMeasurements(adj);
         std::ofstream xyz(stem + ".xyz");
         PrintOutputFileHeaderInfo(xyz, "DYNADJUST COORDINATE OUTPUT FILE", stem + ".xyz");
         PrintAdjustedNetworkStations(adj, xyz);
@@ -662,7 +663,38 @@ class dna_adjust {
                              << "          *** " << (passFail_ == 0 ? "PASSED" : (passFail_ == 1 ? "WARNING" : "FAILED")) << " ***\n\n";
     }
 
-    void PrintAdjMeasurements(std::ostream& os) const
+    // PrintAdjustedNetworkMeasurements (PRN:494-533): every measurement; block-1 mode reports the measurements of the
+    // first block only; --output-msr-blocks prints one table per .seg block (the block's CML)
+    void PrintAdjustedNetworkMeasurements(std::ostream& os) const
+    {
+        const bool phased = a_.adjust_mode != SimultaneousMode && !seg_.cml.empty();
+        if (!phased || (!a_.output_msr_blocks && a_.adjust_mode != Phased_Block_1Mode)) {
+            PrintAdjMeasurements(os, nullptr, -1);
+            return;
+        }
+        // block of every record: a measurement spans the records from its first one (listed in a block's CML) up to the
+        // next listed first record
+        std::vector<int32_t> rec_block(msr_.size(), -1);
+        for (size_t b = 0; b < seg_.cml.size(); ++b)
+            for (uint32_t f : seg_.cml[b])
+                if (f < rec_block.size())
+                    rec_block[f] = (int32_t)b;
+        for (size_t i = 0, cur = (size_t)-1; i < rec_block.size(); ++i) {
+            if (rec_block[i] >= 0)
+                cur = (size_t)rec_block[i];
+            else if (cur != (size_t)-1)
+                rec_block[i] = (int32_t)cur;
+        }
+        for (size_t b = 0; b < seg_.cml.size(); ++b) {
+            if (a_.output_msr_blocks)
+                os << "\nBlock " << b + 1 << "\n";
+            PrintAdjMeasurements(os, &rec_block, (int32_t)b);
+            if (a_.adjust_mode == Phased_Block_1Mode)
+                break;
+        }
+    }
+
+    void PrintAdjMeasurements(std::ostream& os, const std::vector<int32_t>* rec_block, int32_t block) const
     {
         os << "\nAdjusted Measurements\n------------------------------------------\n\n";
         char buf[512];
@@ -675,6 +707,8 @@ class dna_adjust {
         for (size_t i = 0; i < msr_.size(); ++i) {
             const dna_msr_t& m = msr_[i];
             if (m.ignore || m.measStart > 2)   // covariance records of X / Y clusters carry no row
+                continue;
+            if (rec_block && (*rec_block)[i] != block)
                 continue;
             const char t = m.measType;
             const bool gnss = t == 'G' || t == 'X' || t == 'Y';

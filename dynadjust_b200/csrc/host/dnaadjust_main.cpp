@@ -123,6 +123,8 @@ int main(int argc, char** argv)
             s.output_adj_msr = true;
         else if (n == "output-stn-blocks")
             s.output_stn_blocks = true;
+        else if (n == "output-msr-blocks")
+            s.output_msr_blocks = true;
         else if (n == "output-pos-uncertainty")
             s.output_pos_uncertainty = true;
         else if (n == "output-corrections-file")

@@ -251,6 +251,23 @@ def test_cli_block_outputs(cli_hostsim, oracle, tmp_path):
         assert sorted(rows) == sorted(stn["stationName"][i].decode() for i in want)
         for i in want:
             assert np.abs(np.array(rows[stn["stationName"][i].decode()][4:7]) - est[i]).max() < 1e-3
+    # --output-msr-blocks: every measurement appears once, under the block whose CML lists it
+    rec = msr.reshape(-1, 3)
+    blk_of = lambda s: next(b for b, l in enumerate(isl) if s in l)
+    cml = [[] for _ in isl]
+    for b_ in range(len(rec)):
+        cml[max(blk_of(int(rec["station1"][b_, 0])), blk_of(int(rec["station2"][b_, 0])))].append(3 * b_)
+    dnafiles.write_seg(os.path.join(tmp_path, "blk.seg"), isl, jsl, cml)
+    r = _run(cli_hostsim, tmp_path, "blk", "--phased", "--output-adj-msr", "--output-msr-blocks", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    adj = open(os.path.join(tmp_path, "blk.phased.adj")).read()
+    parts = re.split(r"^Block (\d+)$", adj.split("SOLUTION")[1].split("Adjusted Coordinates")[0], flags=re.M)
+    counts = [len([l for l in parts[2 * b_ + 2].splitlines() if l.startswith("G ")]) for b_ in range(len(isl))]
+    assert counts == [3 * len(c) for c in cml] and sum(counts) == len(msr)
+    r = _run(cli_hostsim, tmp_path, "blk", "--block1-phased", "--output-adj-msr", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    adj = open(os.path.join(tmp_path, "blk.phased-block1.adj")).read()
+    assert len([l for l in adj.splitlines() if l.startswith("G ")]) == 3 * len(cml[0])
     r = _run(cli_hostsim, tmp_path, "blk", "--block1-phased", "--no-binary-update")
     assert r.returncode == 0, r.stderr
     adj = open(os.path.join(tmp_path, "blk.phased-block1.adj")).read()
