@@ -1992,6 +1992,79 @@ int gadj_get_vcv_block(gadj_ctx* c, uint32_t si, uint32_t sj, double q[9])
     return get_block(c, c->d_vcvd.p, c->d_vcvo.p, si, sj, q);
 }
 
+int gadj_get_block_vcv(gadj_ctx* c, uint32_t block, uint32_t* nstations, uint32_t* stations, uint32_t cap, double* packed_lower)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    if (!c->inverse_valid)
+        return c->fail("the rigorous variances have not been formed");
+    const Symbolic& S = c->sym;
+    if (block >= S.fronts.size())
+        return c->fail("block index out of range");
+    const Front& f = S.fronts[block];
+    if (f.owner != S.rank)
+        return c->fail("the block is held by another rank");
+    const uint32_t nst = f.own_count + f.bnd_count;
+    *nstations = nst;
+    if (!stations || !packed_lower)
+        return 0;
+    if (cap < nst)
+        return c->fail("station list capacity too small");
+    for (uint32_t i = 0; i < f.own_count; ++i)
+        stations[i] = S.stn_of_pos[f.own_begin + i];
+    for (uint32_t i = 0; i < f.bnd_count; ++i)
+        stations[f.own_count + i] = S.stn_of_pos[S.bnd[f.bnd_begin + i]];
+    const size_t k = f.k, r = f.r, m = f.m, n = m;
+    // the front's panel [Z11; Z21] and the junction block Z22, gathered from the ancestors' panels like the selected inverse does
+    std::vector<double> P(m * (size_t)f.ldk), G, d(3 * (size_t)c->nstn);
+    dev::d2h(P.data(), c->d_panels.p + f.panel_off, P.size() * sizeof(double));
+    dev::d2h(d.data(), c->d_dscale.p, d.size() * sizeof(double));
+    const size_t ldg = r + (r & 1);
+    DevArray<double> dG;
+    DevArray<GatherOp> dops;
+    if (r) {
+        std::vector<GatherOp> ops;
+        int grid = 1;
+        if (!dG.resize(r * ldg))
+            return c->fail("out of device memory");
+        for (uint32_t t = 0; t < f.tgt_count; ++t) {
+            const Target& tg = S.targets[f.tgt_begin + t];
+            const Front& an = S.fronts[tg.anc];
+            GatherOp g{};
+            g.Z = c->d_panels.p + an.panel_off;
+            g.ld = an.ldk;
+            g.rowmap = c->d_rowmap.p + tg.rowmap_off;
+            g.G = dG.p;
+            g.ldg = (int64_t)ldg;
+            g.jb = (int32_t)tg.jb;
+            g.je = (int32_t)tg.je;
+            g.nb = (int32_t)f.bnd_count;
+            g.col0 = (int32_t)tg.col0;
+            ops.push_back(g);
+            grid = std::max<int>(grid, (int)(((g.nb - g.jb + 15) / 16) * ((g.je - g.jb + 15) / 16)));
+        }
+        if (!dops.upload(ops))
+            return c->fail("out of device memory");
+        launch_gather(dops.p, (int)ops.size(), grid, dev::stream());
+        G.resize(r * ldg);
+        dev::d2h(G.data(), dG.p, G.size() * sizeof(double));
+    }
+    std::string e = dev::sync();
+    if (!e.empty())
+        return c->fail(e);
+    auto scale_of = [&](size_t row) { return d[3 * (size_t)stations[row / 3] + row % 3]; };
+    for (size_t j = 0; j < n; ++j)
+        for (size_t i = j; i < n; ++i) {
+            double z;
+            if (j < k)
+                z = P[i * f.ldk + j];                    // Z11 (lower triangle) and Z21
+            else
+                z = G[(i - k) * ldg + (j - k)];          // Z22
+            packed_lower[j * n - j * (j - 1) / 2 + (i - j)] = z * scale_of(i) * scale_of(j);
+        }
+    return 0;
+}
+
 int gadj_get_normals_block(gadj_ctx* c, uint32_t si, uint32_t sj, double n[9])
 {
     if (!c->prepared || !c->normals_valid)

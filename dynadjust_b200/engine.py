@@ -62,7 +62,7 @@ EXPORTS = ["gadj_default_opts", "gadj_create", "gadj_destroy", "gadj_last_error"
            "gadj_upload_measurements_range",
            "gadj_reset_estimates", "gadj_iterate", "gadj_form_inverse", "gadj_adjust", "gadj_statistics", "gadj_get_estimates",
            "gadj_get_corrections", "gadj_get_station_vcvs", "gadj_get_station_vcv", "gadj_get_vcv_block",
-           "gadj_get_normals_block", "gadj_get_rhs", "gadj_profile_enable", "gadj_profile_read", "gadj_test_gemm",
+           "gadj_get_normals_block", "gadj_get_rhs", "gadj_get_block_vcv", "gadj_profile_enable", "gadj_profile_read", "gadj_test_gemm",
            "gadj_mg_init", "gadj_stage_begin", "gadj_stage_normals_pending", "gadj_stage_run", "gadj_stage_solve_begin",
            "gadj_stage_solve_end", "gadj_stage_apply", "gadj_stage_end", "gadj_stage_mark_inverse", "gadj_sync", "gadj_mg_buffer",
            "gadj_mg_top_fronts", "gadj_mg_extract_vcv"]
@@ -101,6 +101,7 @@ def load_library(path=None):
     L.gadj_get_station_vcvs.argtypes = [vp, vp]
     L.gadj_get_station_vcv.argtypes = [vp, u32, vp]
     L.gadj_get_vcv_block.argtypes = [vp, u32, u32, vp]
+    L.gadj_get_block_vcv.argtypes = [vp, u32, vp, vp, u32, vp]
     L.gadj_get_normals_block.argtypes = [vp, u32, u32, vp]
     L.gadj_get_rhs.argtypes = [vp, vp]
     L.gadj_profile_enable.argtypes = [vp, i32]
@@ -266,6 +267,21 @@ class Adjustment:
         p = GadjProfile()
         self._check(self.L.gadj_profile_read(self.h, C.byref(p), 1 if reset else 0))
         return p
+
+    def block_vcv(self, block):
+        """(station indices, dense 3n x 3n variance matrix) of one block / front: inner stations, then junction stations."""
+        n = C.c_uint32()
+        self._check(self.L.gadj_get_block_vcv(self.h, block, C.byref(n), None, 0, None))
+        stations = np.zeros(n.value, np.uint32)
+        dim = 3 * n.value
+        packed = np.zeros(dim * (dim + 1) // 2)
+        self._check(self.L.gadj_get_block_vcv(self.h, block, C.byref(n), self._p(stations), n.value, self._p(packed)))
+        V = np.zeros((dim, dim))
+        o = 0
+        for j in range(dim):          # packed lower, column-major
+            V[j:, j] = packed[o:o + dim - j]
+            o += dim - j
+        return stations, V + np.tril(V, -1).T
 
     def test_gemm(self, A, B, reps=1):
         A = np.ascontiguousarray(A, dtype=np.float64)

@@ -25,6 +25,7 @@
  *   v_corrections_                                              gadj_get_corrections
  *   v_rigorousVariances_ (3x3 diagonal)      PRN:3917-4070      gadj_get_station_vcv(s)
  *   v_rigorousVariances_ (pattern blocks)    ADJ:7784-8060      gadj_get_vcv_block
+ *   v_rigorousVariances_.at(block) (dense)   ADJ:3805, PRN:2942   gadj_get_block_vcv
  *   v_normals_ / At V^-1 l (before Solve)    ADJ:893-896        gadj_get_normals_block / gadj_get_rhs
  */
 #ifndef GADJ_H_
@@ -146,6 +147,12 @@ int gadj_get_station_vcvs(gadj_ctx* c, double* q /* 9*nstn, row-major 3x3 per st
 int gadj_get_station_vcv(gadj_ctx* c, uint32_t stn, double q[9]);
 /* N^-1 block (rows of station si, columns of station sj); only pairs joined by a measurement */
 int gadj_get_vcv_block(gadj_ctx* c, uint32_t si, uint32_t sj, double q[9]);
+/* Dense rigorous variance matrix of one block = front of the elimination tree (block b of gadj_set_blocks, in order):
+ * its inner stations followed by its junction stations, as the reference keeps per block (v_rigorousVariances_.at(b),
+ * read by the SINEX / covariance printers).  *nstations receives the station count n; when `stations` (capacity cap >= n)
+ * and `packed_lower` (3n(3n+1)/2 doubles) are given they receive the station indices in matrix order and the matrix in
+ * the reference's packed-lower column-major layout, idx(i,j) = j*3n - j(j-1)/2 + (i-j), i >= j (MATH:363-369). */
+int gadj_get_block_vcv(gadj_ctx* c, uint32_t block, uint32_t* nstations, uint32_t* stations, uint32_t cap, double* packed_lower);
 /* assembled normals (constraints included) of the last iterate call that built them, and its right-hand side */
 int gadj_get_normals_block(gadj_ctx* c, uint32_t si, uint32_t sj, double n[9]);
 int gadj_get_rhs(gadj_ctx* c, double* w /* 3*nstn */);

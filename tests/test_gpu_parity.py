@@ -88,6 +88,13 @@ def test_cluster_partial_variance_scalars(oracle, gpu_lib):
     adj.close()
 
 
+def test_block_variance_matrices(oracle, gpu_lib):
+    from tests.test_host_logic import _check_block_vcvs
+    _check_block_vcvs(oracle, gpu_lib, leaf_stations=16)
+    _check_block_vcvs(oracle, gpu_lib, blocks=lambda n: parity.chain_blocks(n, 40))
+    _check_block_vcvs(oracle, gpu_lib, n=60, m=170, seed=21, ordering=engine.ORDER_DENSE)
+
+
 def test_large_gnss_cluster(oracle, gpu_lib):
     """One X cluster of 120 baselines (360 x 360 VCV): the per-cluster Cholesky inverse beyond a single tile."""
     from dynadjust_b200 import synth_terrestrial as st

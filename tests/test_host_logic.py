@@ -257,6 +257,35 @@ def test_repeated_station_pairs(oracle, hostsim_path):
     parity.check_normals(oracle, hostsim_path, 80, 240, 6, mutate=mutate, leaf_stations=12)
 
 
+def _check_block_vcvs(oracle, lib, **kw):
+    """gadj_get_block_vcv: the dense variance matrix of every block (inner + junction stations) against the same rows /
+    columns of the oracle's full inverse."""
+    blocks = kw.pop("blocks", None)
+    stn, msr, _, _ = synth.gnss_network(kw.pop("n", 200), kw.pop("m", 600), kw.pop("seed", 15))
+    ref = oracle.adjust_simultaneous(stn.copy(), msr.copy(), want_vcv=True)
+    V = ref["vcv"]
+    adj, info, last, stats = parity.run_engine(lib, stn, msr, blocks=blocks(len(stn)) if blocks else None, **kw)
+    seen = set()
+    for b in range(info.nfronts):
+        st, Q = adj.block_vcv(b)
+        idx = np.concatenate([[3 * s, 3 * s + 1, 3 * s + 2] for s in st]).astype(int)
+        want = V[np.ix_(idx, idx)]
+        assert Q.shape == want.shape and np.abs(Q - want).max() <= 2e-8 * np.abs(want).max(), b
+        seen.update(int(s) for s in st)
+    assert seen == set(range(len(stn)))
+    adj.close()
+    return info
+
+
+def test_block_variance_matrices(oracle, hostsim_path):
+    info = _check_block_vcvs(oracle, hostsim_path, leaf_stations=16)
+    assert info.nfronts > 8
+    info = _check_block_vcvs(oracle, hostsim_path, blocks=lambda n: parity.chain_blocks(n, 40))      # .seg chain: block = front
+    assert info.nfronts == 5
+    info = _check_block_vcvs(oracle, hostsim_path, n=60, m=170, seed=21, ordering=engine.ORDER_DENSE)  # the whole network
+    assert info.nfronts == 1
+
+
 def test_small_workspace_forces_chunks(oracle, hostsim_path):
     # a tight inverse workspace makes every level run in several chunks; results must not change
     parity.check_against_oracle(oracle, hostsim_path, 400, 1200, 5, leaf_stations=8, workspace_gb=2.0e-4)
