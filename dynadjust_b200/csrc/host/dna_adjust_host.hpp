@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <fstream>
 #include <iomanip>
 #include <sstream>
@@ -42,6 +43,7 @@ struct adjust_settings {            // the fields of project_settings.a / .g / .
     bool output_msr_blocks = false;        // --output-msr-blocks: likewise the adjusted measurements
     bool output_pos_uncertainty = false;   // --output-pos-uncertainty: <net>.<mode>.apu
     bool output_corrections = false;       // --output-corrections-file: <net>.<mode>.cor
+    bool export_sinex = false;             // --export-sinex-file: <net>[-block<k>].<frame>.snx with the dense block variance matrix
     bool apu_vcv_enu = false;              // --output-apu-vcv-units ENU (default XYZ)
     double hz_corr_threshold = 0.0, vt_corr_threshold = 0.0;   // dnaoptions.hpp:510
     bool update_binary_files = true;
@@ -75,6 +77,13 @@ class dna_adjust {
         o.max_iterations = a_.max_iterations;
         o.confidence_interval = a_.confidence_interval;
         o.scale_normals_to_unity = 1;   // internal equilibration is always safe; the flag is accepted for compatibility
+        if (a_.export_sinex && a_.adjust_mode == SimultaneousMode) {
+            // the SINEX file of a simultaneous adjustment carries the full variance matrix (PRN:2944-2946): one dense front
+            if (stn_.size() > 12000)
+                SignalExceptionAdjustment("--export-sinex-file in simultaneous mode needs the full variance matrix of the network "
+                                          "(dense); segment the network (dnasegment) and run --phased-adjustment for per-block files");
+            o.ordering = GADJ_ORDER_DENSE;
+        }
         if (gadj_create(&o, &ctx_))
             SignalExceptionAdjustment(gadj_last_error(nullptr));
         check(gadj_set_stations(ctx_, stn_.data(), (uint32_t)stn_.size()));
@@ -177,6 +186,105 @@ class dna_adjust {
             PrintPositionalUncertainty(stem + ".apu");
         if (a_.output_corrections)
             PrintNetworkStationCorrections(stem + ".cor");
+        if (a_.export_sinex)
+            PrintEstimatedStationCoordinatestoSNX();
+    }
+
+    // ---- .snx (PrintEstimatedStationCoordinatestoSNX PRN:2906-3010, DnaIoSnx::SerialiseSinex snx_file_writer.cpp) -----------
+    // One file per block, <net>-block<k>.<frame>.snx (phased; block-1 mode: the first only), or <net>.<frame>.snx
+    // (simultaneous): SITE/ID, SOLUTION/STATISTICS, SOLUTION/ESTIMATE and the lower triangle of the block's dense
+    // variance matrix, SOLUTION/MATRIX_ESTIMATE L COVA.
+    void PrintEstimatedStationCoordinatestoSNX()
+    {
+        const uint32_t nblocks = (uint32_t)info_.nfronts;
+        const bool phased = a_.adjust_mode != SimultaneousMode;
+        const std::string frame = frame_name();
+        for (uint32_t b = 0; b < nblocks; ++b) {
+            if (a_.adjust_mode == Phased_Block_1Mode && b > 0)
+                break;
+            uint32_t n = 0;
+            check(gadj_get_block_vcv(ctx_, b, &n, nullptr, 0, nullptr));
+            std::vector<uint32_t> st(n);
+            const size_t dim = 3 * (size_t)n;
+            std::vector<double> q(dim * (dim + 1) / 2);
+            check(gadj_get_block_vcv(ctx_, b, &n, st.data(), n, q.data()));
+            std::string file = a_.output_folder + "/" + a_.network_name;
+            if (phased)
+                file += "-block" + std::to_string(b + 1);
+            file += "." + frame + ".snx";
+            std::ofstream os(file);
+            auto at = [&](size_t i, size_t j) { return i >= j ? q[j * dim - j * (j - 1) / 2 + (i - j)] : q[i * dim - i * (i - 1) / 2 + (j - i)]; };
+            const std::string line = "*-------------------------------------------------------------------------------";
+            char buf[256];
+            const std::string epoch = sinex_date(bst_meta_.epoch, false), now = sinex_date("", true);
+            snprintf(buf, sizeof(buf), "%%=SNX 2.00 DNA %s DNA %s %s P %05u 0 S           ", now.c_str(), epoch.c_str(), epoch.c_str(),
+                     (unsigned)stats_.unknown_params);
+            os << buf << "\n" << line << "\n+FILE/REFERENCE\n"
+               << "*INFO_TYPE_________ INFO________________________________________________________\n"
+               << " DESCRIPTION        Network " << a_.network_name << "\n";
+            std::ostringstream what;
+            if (nblocks > 1)
+                what << "Phased adjustment results. Block " << b + 1 << " of " << nblocks;
+            else
+                what << "Simultaneous adjustment results.";
+            os << " OUTPUT             " << std::left << std::setw(60) << what.str() << "\n"
+               << " SOFTWARE           b200-geodetic-adjust 0.1 (libgadj, sm_100a)\n"
+               << " INPUT              " << std::left << std::setw(60) << bst_file_ << "\n"
+               << " INPUT              " << std::left << std::setw(60) << bms_file_ << "\n-FILE/REFERENCE\n" << line << "\n+FILE/COMMENT\n";
+            if (nblocks > 1)
+                os << " This file contains the rigorous estimates for block " << b + 1 << " of a segmented\n network comprised of " << nblocks
+                   << " blocks. Due to the way in which junction stations\n are carried through successive blocks, stations appearing in this "
+                      "file\n may also be found in other SINEX files relating to this network, such as\n "
+                   << a_.network_name << "-block1.snx, " << a_.network_name << "-block2.snx, etc.\n";
+            os << "-FILE/COMMENT\n" << line << "\n+SITE/ID\n"
+               << "*CODE PT __DOMES__ T _STATION DESCRIPTION__ APPROX_LON_ APPROX_LAT_ _APP_H_\n";
+            for (uint32_t i = 0; i < n; ++i) {
+                const dna_stn_t& s = stn_[st[i]];
+                const std::string name = s.stationName, desc = s.description;
+                snprintf(buf, sizeof(buf), " %-4s %2s %-9s %1s %-22s %11s %11s %7.1f", name.substr(0, 4).c_str(), "A", name.substr(0, 9).c_str(), "P",
+                         desc.substr(0, 22).c_str(), dms_spaced5(s.currentLongitude).c_str(), dms_spaced5(s.currentLatitude).c_str(),
+                         s.currentHeight);
+                os << buf << "\n";
+            }
+            os << "-SITE/ID\n" << line << "\n+SOLUTION/STATISTICS\n*_STATISTICAL PARAMETER________ __VALUE(S)____________\n";
+            snprintf(buf, sizeof(buf), " %-30s %22u\n %-30s %22u\n %-30s %22lld\n %-30s %22.6f\n", "NUMBER OF OBSERVATIONS",
+                     (unsigned)stats_.measurement_params, "NUMBER OF UNKNOWNS", (unsigned)stats_.unknown_params, "NUMBER OF DEGREES OF FREEDOM",
+                     (long long)stats_.measurement_params - (long long)stats_.unknown_params, "VARIANCE FACTOR", stats_.sigma_zero);
+            os << buf << "-SOLUTION/STATISTICS\n" << line << "\n+SOLUTION/ESTIMATE\n"
+               << "*INDEX TYPE__ CODE PT SOLN _REF_EPOCH__ UNIT S __ESTIMATED VALUE____ _STD_DEV___\n";
+            unsigned index = 1;
+            for (uint32_t i = 0; i < n; ++i)
+                for (int c = 0; c < 3; ++c) {
+                    const std::string name = stn_[st[i]].stationName;
+                    char val[40], sd[40];
+                    snprintf(val, sizeof(val), "%.14E", est_[3 * (size_t)st[i] + c]);
+                    snprintf(sd, sizeof(sd), "%.5E", std::sqrt(std::fabs(at(3 * i + c, 3 * i + c))));
+                    snprintf(buf, sizeof(buf), " %5u STA%c   %-4s %2s 0001 %s %-4s 0 %21s %11s", index++, "XYZ"[c], name.substr(0, 4).c_str(), "A",
+                             epoch.c_str(), "m", val, sd);
+                    os << buf << "\n";
+                }
+            os << "-SOLUTION/ESTIMATE\n" << line << "\n+SOLUTION/MATRIX_ESTIMATE L COVA\n"
+               << "*PARA1 PARA2 ____PARA2+0__________ ____PARA2+1__________ ____PARA2+2__________\n";
+            for (size_t row = 0; row < dim; ++row) {
+                int field = 1;
+                bool fresh = true;
+                for (size_t col = 0; col <= row; ++col) {
+                    if (fresh) {
+                        snprintf(buf, sizeof(buf), " %5zu %5zu ", row + 1, col + 1);
+                        os << buf;
+                        fresh = false;
+                    }
+                    snprintf(buf, sizeof(buf), "%21.14E ", at(row, col));
+                    os << buf;
+                    if (row == col || ++field > 3) {
+                        os << "\n";
+                        fresh = true;
+                        field = 1;
+                    }
+                }
+            }
+            os << "-SOLUTION/MATRIX_ESTIMATE L COVA\n%ENDSNX\n";
+        }
     }
 
     // PrintAdjustedNetworkStations (PRN:535-595): one list of every station; in the phased modes with
@@ -738,6 +846,50 @@ class dna_adjust {
             os << buf << "\n";
         }
         os << "\n";
+    }
+
+    // reference-frame name for file names: GDA2020 / GDA94 from the EPSG code of the station file, else "EPSG<code>"
+    std::string frame_name() const
+    {
+        const std::string e = bst_meta_.epsgCode;
+        if (e == "7843")
+            return "GDA2020";
+        if (e == "4283" || e == "4939")
+            return "GDA94";
+        return e.empty() ? "GDA2020" : "EPSG" + e;
+    }
+    // YY:DDD:SSSSS of a dd.mm.yyyy date (DateSINEXFormat, dnachronutils.hpp:98-123); today with seconds when `today`
+    static std::string sinex_date(const std::string& ddmmyyyy, bool today)
+    {
+        int d = 1, m = 1, y = 2020;
+        long sec = 0;
+        if (today) {
+            const std::time_t t = std::time(nullptr);
+            std::tm g{};
+            gmtime_r(&t, &g);
+            d = g.tm_mday;
+            m = g.tm_mon + 1;
+            y = g.tm_year + 1900;
+            sec = g.tm_hour * 3600L + g.tm_min * 60L + g.tm_sec;
+        } else if (sscanf(ddmmyyyy.c_str(), "%d.%d.%d", &d, &m, &y) != 3) {
+            d = m = 1;
+            y = 2020;
+        }
+        static const int cum[2][12] = {{0, 31, 59, 90, 120, 151, 181, 212, 243, 273, 304, 334}, {0, 31, 60, 91, 121, 152, 182, 213, 244, 274, 305, 335}};
+        const int leap = (y % 400 == 0 || (y % 100 != 0 && y % 4 == 0)) ? 1 : 0;
+        char b[32];
+        snprintf(b, sizeof(b), "%02d:%03d:%05ld", y % 100, cum[leap][(m - 1) % 12] + d, sec);
+        return b;
+    }
+    // FormatDmsString(RadtoDms(x), 5, spaces): "ddd mm ss.s"
+    static std::string dms_spaced5(double rad)
+    {
+        const double deg = std::fabs(rad) * 180.0 / 3.14159265358979323846;
+        const long long units = std::llround(deg * 3600.0 * 10.0);
+        const long long d = units / 36000, rem = units % 36000, mi = rem / 600, s10 = rem % 600;
+        char b[48];
+        snprintf(b, sizeof(b), "%s%lld %02lld %02lld.%lld", rad < 0 ? "-" : "", d, mi, s10 / 10, s10 % 10);
+        return b;
     }
 
     // "ddd mm ss.ssss" (FormatDmsString with spaces on a RadtoDms value, 4 decimals of a second)

@@ -318,6 +318,68 @@ def test_cli_reproduces_reference_expected_adj_gpu(cli_gpu, tmp_path):
     _golden_gnss_text(cli_gpu, tmp_path)
 
 
+def _read_snx(path):
+    text = open(path).read()
+    assert text.startswith("%=SNX 2.00 DNA") and text.rstrip().endswith("%ENDSNX")
+    sec = lambda name: text.split("+" + name)[1].split("-" + name)[0].splitlines()[1:]
+    sites = [l.split()[0] for l in sec("SITE/ID") if l.startswith(" ")]
+    est = [(l.split()[1], l.split()[2], float(l.split()[8]), float(l.split()[9])) for l in sec("SOLUTION/ESTIMATE") if l.startswith(" ")]
+    n = len(est)
+    Q = np.zeros((n, n))
+    for l in sec("SOLUTION/MATRIX_ESTIMATE L COVA"):
+        if not l.startswith(" "):
+            continue
+        f = l.split()
+        r, c0 = int(f[0]) - 1, int(f[1]) - 1
+        for k, v in enumerate(f[2:]):
+            Q[r, c0 + k] = Q[c0 + k, r] = float(v)
+    stats = {l[1:31].strip(): float(l[31:]) for l in sec("SOLUTION/STATISTICS") if l.startswith(" ")}
+    return sites, est, Q, stats
+
+
+def _sinex(exe, oracle, tmp_path):
+    """--export-sinex-file (PRN:2906-3010, snx_file_writer.cpp): estimates, standard deviations and the
+    lower triangle of the dense variance matrix, for the whole network (simultaneous) and per block (phased)."""
+    stn, msr, _, _ = synth.gnss_network(90, 260, 14)
+    stn["stationName"] = np.char.add("P", np.char.zfill(np.arange(90).astype(str), 3)).astype("S31")   # 4-character SINEX codes
+    _write_network(tmp_path, "sx", stn, msr)
+    ref = oracle.adjust_simultaneous(stn.copy(), msr.copy(), want_vcv=True)
+    V, est_ref = ref["vcv"], ref["est"].reshape(-1, 3)
+    names = [n.decode() for n in stn["stationName"]]
+
+    def check(path):
+        sites, est, Q, stats = _read_snx(path)
+        idx = np.concatenate([[3 * names.index(c), 3 * names.index(c) + 1, 3 * names.index(c) + 2] for c in sites])
+        assert [e[1] for e in est] == [c for c in sites for _ in range(3)] and [e[0] for e in est] == ["STAX", "STAY", "STAZ"] * len(sites)
+        assert np.abs(np.array([e[2] for e in est]) - est_ref.reshape(-1)[idx]).max() < 1e-8
+        want = V[np.ix_(idx, idx)]
+        assert np.abs(Q - want).max() <= 2e-8 * np.abs(want).max()
+        assert np.abs(np.array([e[3] for e in est]) - np.sqrt(np.diag(want))).max() <= 1e-5 * np.sqrt(np.diag(want)).max()
+        assert stats["NUMBER OF UNKNOWNS"] == ref["res"].unknown_params and abs(stats["VARIANCE FACTOR"] - ref["res"].sigma_zero) < 1e-6
+        return sites
+
+    r = _run(exe, tmp_path, "sx", "--export-sinex-file", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    assert len(check(os.path.join(tmp_path, "sx.GDA2020.snx"))) == 90
+    isl = parity.chain_blocks(90, 30)
+    dnafiles.write_seg(os.path.join(tmp_path, "sx.seg"), isl, [[] for _ in isl], [[] for _ in isl])
+    r = _run(exe, tmp_path, "sx", "--phased", "--export-sinex-file", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    seen = set()
+    for b in range(len(isl)):
+        seen.update(check(os.path.join(tmp_path, f"sx-block{b + 1}.GDA2020.snx")))
+    assert seen == set(names)
+
+
+def test_cli_sinex_hostsim(cli_hostsim, oracle, tmp_path):
+    _sinex(cli_hostsim, oracle, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_sinex_gpu(cli_gpu, oracle, tmp_path):
+    _sinex(cli_gpu, oracle, tmp_path)
+
+
 def test_cli_apu_cor_hostsim(cli_hostsim, oracle, tmp_path):
     _apu_cor(cli_hostsim, oracle, tmp_path)
 
