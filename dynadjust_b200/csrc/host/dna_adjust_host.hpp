@@ -47,6 +47,7 @@ struct adjust_settings {            // the fields of project_settings.a / .g / .
     bool apu_vcv_enu = false;              // --output-apu-vcv-units ENU (default XYZ)
     double hz_corr_threshold = 0.0, vt_corr_threshold = 0.0;   // dnaoptions.hpp:510
     bool update_binary_files = true;
+    std::string type_b_global, type_b_file; // --type-b-sd-global "e,n,up" (metres, 1 sigma), --type-b-sd-file <file> (dnaoptions-interface.hpp)
     std::string station_constraints;       // --constraints "STN1,CCC,STN2,FFC" (dnaoptions.hpp:481)
     std::string command_line;
 };
@@ -141,6 +142,7 @@ class dna_adjust {
         vcv_.resize(9 * stn_.size());
         check(gadj_get_estimates(ctx_, est_.data()));
         check(gadj_get_station_vcvs(ctx_, vcv_.data()));
+        ApplyTypeBUncertainties();
         ComputeTestStat();
     }
 
@@ -329,6 +331,10 @@ class dna_adjust {
         var("Stations printed in blocks:", "No");
         var("Variance matrix units:", a_.apu_vcv_enu ? "ENU" : "XYZ");
         var("Full covariance matrix:", "No");
+        if (!a_.type_b_global.empty())
+            var("Type B uncertainties:", a_.type_b_global);
+        if (!a_.type_b_file.empty())
+            var("Type B uncertainty file:", a_.type_b_file);
         os << std::string(80, '-') << "\n\n";
         os << "Positional uncertainty of adjusted station coordinates\n";
         os << "------------------------------------------------------\n\n";
@@ -415,6 +421,94 @@ class dna_adjust {
     }
 
   private:
+    // Type B uncertainties (LoadTypeBUncertainties ADJ:10231-10323, dnaiotbu.cpp, PrintAdjStation PRN:4000-4029): 1-sigma
+    // east / north / up values in metres — one set for every station on the command line, site-specific ones from a
+    // "!#=DNA 1.00 TBU" file (station name in the first 20 columns) taking precedence — are added, as variances rotated
+    // into the Cartesian frame at the station's estimated position, to the station variance blocks that every report
+    // (.adj, .xyz, .apu) reads.
+    void ApplyTypeBUncertainties()
+    {
+        if (a_.type_b_global.empty() && a_.type_b_file.empty())
+            return;
+        auto parse3 = [&](const std::vector<std::string>& t, const std::string& what, double* enu) {
+            std::vector<double> v;
+            for (const std::string& x : t) {
+                char* end = nullptr;
+                const double d = std::strtod(x.c_str(), &end);
+                if (x.empty() || end == x.c_str() || *end != 0)
+                    SignalExceptionAdjustment("  Type b uncertainty '" + x + "' is not a number:\n    " + what);
+                v.push_back(d);
+            }
+            enu[0] = enu[1] = enu[2] = 0.0;
+            if (v.size() >= 3) {
+                enu[0] = v[0] * v[0];
+                enu[1] = v[1] * v[1];
+                enu[2] = v[2] * v[2];
+            } else if (v.size() == 2) {       // east, north
+                enu[0] = v[0] * v[0];
+                enu[1] = v[1] * v[1];
+            } else if (v.size() == 1)         // up
+                enu[2] = v[0] * v[0];
+            else
+                SignalExceptionAdjustment("  No Type b uncertainties provided:\n    " + what);
+        };
+        std::vector<double> tb(3 * stn_.size(), 0.0);
+        std::vector<char> has(stn_.size(), 0);
+        if (!a_.type_b_global.empty()) {
+            std::vector<std::string> tok;
+            std::stringstream ss(a_.type_b_global);
+            for (std::string t; std::getline(ss, t, ',');)
+                tok.push_back(t);
+            double enu[3];
+            parse3(tok, a_.type_b_global, enu);
+            for (size_t i = 0; i < stn_.size(); ++i) {
+                std::copy(enu, enu + 3, &tb[3 * i]);
+                has[i] = 1;
+            }
+        }
+        if (!a_.type_b_file.empty()) {
+            std::ifstream f(a_.type_b_file);
+            std::string line;
+            if (!f || !std::getline(f, line))
+                SignalExceptionAdjustment("load_tbu_file(): An error was encountered when opening " + a_.type_b_file + ".");
+            if (line.size() < 15 || line.compare(0, 6, "!#=DNA") != 0 || (line.substr(12, 3) != "TBU" && line.substr(12, 3) != "tbu"))
+                SignalExceptionAdjustment("  The supplied filetype is not recognised:\n  " + line);
+            std::unordered_map<std::string, uint32_t> by_name;
+            for (size_t i = 0; i < stn_.size(); ++i)
+                by_name.emplace(stn_[i].stationName, (uint32_t)i);
+            while (std::getline(f, line)) {
+                if (line.empty() || line[0] == '*' || line.find_first_not_of(" \t\r") == std::string::npos)
+                    continue;
+                std::string name = line.substr(0, 20);
+                name.erase(name.find_last_not_of(" \t\r") + 1);
+                auto it = by_name.find(name);
+                if (it == by_name.end() || line.size() <= 20)
+                    continue;                 // stations outside the network are ignored (dnaiotbu.cpp:255-262)
+                std::vector<std::string> tok;
+                std::stringstream ss(line.substr(20));
+                for (std::string t; ss >> t;)
+                    tok.push_back(t);
+                if (tok.empty())
+                    continue;
+                tok.resize(3, "0");
+                double enu[3];
+                parse3(tok, line, enu);
+                std::copy(enu, enu + 3, &tb[3 * (size_t)it->second]);
+                has[it->second] = 1;
+            }
+        }
+        for (size_t i = 0; i < stn_.size(); ++i) {
+            if (!has[i])
+                continue;
+            const double lat = stn_[i].currentLatitude, lon = stn_[i].currentLongitude;
+            const double sl = std::sin(lat), cl = std::cos(lat), so = std::sin(lon), co = std::cos(lon);
+            const double R[3][3] = {{-so, -sl * co, cl * co}, {co, -sl * so, cl * so}, {0, cl, sl}};   // local -> Cartesian
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b)
+                    vcv_[9 * i + 3 * a + b] += R[a][0] * tb[3 * i] * R[b][0] + R[a][1] * tb[3 * i + 1] * R[b][1] + R[a][2] * tb[3 * i + 2] * R[b][2];
+        }
+    }
+
     // NetworkDataLoader::ApplyConstraints (network_data_loader.cpp:211-263): user-supplied "station,constraint" pairs
     // override the constraints in the .bst records.  The reference looks the names up in <net>.map (names sorted, binary
     // search); the same names are in the station records, so they are indexed here directly.

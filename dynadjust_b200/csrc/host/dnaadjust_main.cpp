@@ -29,7 +29,7 @@ const Flag kFlags[] = {
     {"input-folder", true}, {"output-folder", true}, {"output-adj-msr", false}, {"output-pos-uncertainty", false},
     {"output-all-covariances", false}, {"output-corrections-file", false}, {"output-apu-vcv-units", true},
     {"hz-corr-threshold", true}, {"vt-corr-threshold", true}, {"output-stn-blocks", false}, {"output-msr-blocks", false},
-    {"export-sinex-file", false}, {"network-name", true}, {"quiet", false}, {"verbose-level", true},
+    {"export-sinex-file", false}, {"type-b-sd-global", true}, {"type-b-sd-file", true}, {"network-name", true}, {"quiet", false}, {"verbose-level", true},
     {"no-binary-update", false}, {"help", false},
 };
 
@@ -125,6 +125,10 @@ int main(int argc, char** argv)
             s.output_stn_blocks = true;
         else if (n == "output-msr-blocks")
             s.output_msr_blocks = true;
+        else if (n == "type-b-sd-global")
+            s.type_b_global = value;
+        else if (n == "type-b-sd-file")
+            s.type_b_file = value;
         else if (n == "export-sinex-file")
             s.export_sinex = true;
         else if (n == "output-pos-uncertainty")

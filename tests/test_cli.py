@@ -380,6 +380,35 @@ def test_cli_sinex_gpu(cli_gpu, oracle, tmp_path):
     _sinex(cli_gpu, oracle, tmp_path)
 
 
+def test_cli_type_b_uncertainties(cli_hostsim, oracle, tmp_path):
+    """--type-b-sd-global / --type-b-sd-file (ADJ:10231-10323, PRN:4000-4029): type B variances (e, n, up) added to the
+    printed station uncertainties; site-specific values from the file override the global ones."""
+    stn, msr, _, _ = synth.gnss_network(40, 110, 52)
+    _write_network(tmp_path, "tb", stn, msr)
+    tbu = os.path.join(tmp_path, "sites.tbu")
+    s7 = stn["stationName"][7].decode()
+    with open(tbu, "w") as f:
+        f.write("!#=DNA 1.00 TBU\n* site-specific type B uncertainties\n%-20s%-13s%-13s%-13s\nNOTINNET            1.0 1.0 1.0\n" % (s7, "0.030", "0.040", "0.050"))
+    r = _run(cli_hostsim, tmp_path, "tb", "--type-b-sd-global", "0.010,0.010,0.020", "--type-b-sd-file", tbu, "--output-pos-uncertainty",
+             "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    stn_o = stn.copy()
+    ref = oracle.adjust_simultaneous(stn_o, msr.copy(), want_vcv=True)
+    V = ref["vcv"]
+    rows = _station_table(open(os.path.join(tmp_path, "tb.simult.xyz")).read())
+    for i in range(len(stn)):
+        lat, lon = stn_o["currentLatitude"][i], stn_o["currentLongitude"][i]
+        sl, cl, so, co = np.sin(lat), np.cos(lat), np.sin(lon), np.cos(lon)
+        R = np.array([[-so, -sl * co, cl * co], [co, -sl * so, cl * so], [0, cl, sl]])
+        tb = np.array([0.030, 0.040, 0.050]) if i == 7 else np.array([0.010, 0.010, 0.020])
+        q = R.T @ V[3 * i:3 * i + 3, 3 * i:3 * i + 3] @ R
+        sd = np.sqrt(np.diag(q) + tb ** 2 + np.array([0, 0, float(stn["geoidSepUnc"][i]) ** 2]))
+        assert np.abs(np.array(rows[stn["stationName"][i].decode()][7:10]) - sd).max() < 1e-4
+    assert "Type B uncertainties:" in open(os.path.join(tmp_path, "tb.simult.apu")).read()
+    r = _run(cli_hostsim, tmp_path, "tb", "--type-b-sd-global", "0.01,abc")
+    assert r.returncode == 1 and "is not a number" in r.stderr
+
+
 def test_cli_apu_cor_hostsim(cli_hostsim, oracle, tmp_path):
     _apu_cor(cli_hostsim, oracle, tmp_path)
 
