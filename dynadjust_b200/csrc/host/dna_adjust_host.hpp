@@ -905,7 +905,6 @@ class dna_adjust {
                  "Pre Adj Corr", "Out");
         os << buf << "\n" << std::string(200, '-') << "\n";
         const double crit = stats_.critical_value;
-        const double SEC = 3.14159265358979323846 / 180.0 / 3600.0;
         for (size_t i = 0; i < msr_.size(); ++i) {
             const dna_msr_t& m = msr_[i];
             if (m.ignore || m.measStart > 2)   // covariance records of X / Y clusters carry no row
@@ -914,6 +913,11 @@ class dna_adjust {
                 continue;
             const char t = m.measType;
             const bool gnss = t == 'G' || t == 'X' || t == 'Y';
+            if (t == 'Y' && m.measStart == 0 && (m.station3 == DNA_LLH_TYPE || m.station3 == DNA_LLh_TYPE) && i + 2 < msr_.size()) {
+                PrintAdjMeasurements_YLLH(os, i, crit);
+                i += 2;
+                continue;
+            }
             // angles (A B D K V Z) and astronomic / geodetic latitudes and longitudes (I J P Q) print as d m s, their
             // corrections and standard deviations in seconds (PrintAdjMeasurementsAngular, PRN:195-201, 2302-2350)
             const bool angular = std::strchr("ABDKVZIJPQ", t) != nullptr;
@@ -922,24 +926,86 @@ class dna_adjust {
             const char* s1 = stn_[m.station1].stationName;
             const char* s2 = (m.measurementStations >= 2 && t != 'Y') ? stn_[m.station2].stationName : "";
             const char* s3 = (m.measurementStations >= 3 && t == 'A') ? stn_[m.station3].stationName : "";
-            const double unit = angular ? SEC : 1.0;
-            char meas[32], adjd[32];
-            if (angular) {
-                snprintf(meas, sizeof(meas), "%s", dms_spaced(m.preAdjMeas).c_str());
-                snprintf(adjd, sizeof(adjd), "%s", dms_spaced(m.measAdj).c_str());
-            } else {
-                // point clusters that arrived as latitude / longitude / height are reported in the Cartesian form they were
-                // adjusted in (the reference converts these rows back to P / L / H for printing, PRN:2488-2660)
-                const bool from_llh = t == 'Y' && (m.station3 == DNA_LLH_TYPE || m.station3 == DNA_LLh_TYPE);
-                snprintf(meas, sizeof(meas), "%.4f", from_llh ? m.term1 : m.preAdjMeas);
-                snprintf(adjd, sizeof(adjd), "%.4f", m.measAdj);
-            }
-            snprintf(buf, sizeof(buf), "%-2c%-20s%-20s%-20s%-3s%-2c%19s%19s%12.4f%13.4f%13.4f%13.4f%11.2f%12.2f%14.4f%7s", t, s1, s2, s3, "",
-                     comp, meas, adjd, m.measCorr / unit, std::sqrt(var) / unit, std::sqrt(std::fabs(m.measAdjPrec)) / unit,
-                     std::sqrt(m.residualPrec) / unit, m.NStat, m.PelzerRel, m.preAdjCorr / unit, std::fabs(m.NStat) > crit ? "*" : "");
-            os << buf << "\n";
+            PrintMsrRow(os, t, s1, s2, s3, comp, angular, m.preAdjMeas, m.measAdj, m.measCorr, var, m.measAdjPrec, m.residualPrec, m.NStat,
+                        m.PelzerRel, m.preAdjCorr, crit);
         }
         os << "\n";
+    }
+
+    void PrintMsrRow(std::ostream& os, char t, const char* s1, const char* s2, const char* s3, char comp, bool angular, double measured,
+                     double adjusted, double corr, double var, double adj_prec, double res_prec, double nstat, double pelzer,
+                     double pre_adj_corr, double crit) const
+    {
+        const double SEC = 3.14159265358979323846 / 180.0 / 3600.0, unit = angular ? SEC : 1.0;
+        char meas[32], adjd[32], buf[512];
+        if (angular) {
+            snprintf(meas, sizeof(meas), "%s", dms_spaced(measured).c_str());
+            snprintf(adjd, sizeof(adjd), "%s", dms_spaced(adjusted).c_str());
+        } else {
+            snprintf(meas, sizeof(meas), "%.4f", measured);
+            snprintf(adjd, sizeof(adjd), "%.4f", adjusted);
+        }
+        snprintf(buf, sizeof(buf), "%-2c%-20s%-20s%-20s%-3s%-2c%19s%19s%12.4f%13.4f%13.4f%13.4f%11.2f%12.2f%14.4f%7s", t, s1, s2, s3, "", comp, meas,
+                 adjd, corr / unit, std::sqrt(var) / unit, std::sqrt(std::fabs(adj_prec)) / unit, std::sqrt(res_prec) / unit, nstat, pelzer,
+                 pre_adj_corr / unit, std::fabs(nstat) > crit ? "*" : "");
+        os << buf << "\n";
+    }
+
+    // A point of a Y cluster that was supplied as latitude / longitude / height is reported in that form
+    // (PrintAdjMeasurements_YLLH PRN:2488-2660, ReduceYLLHMeasurementsforPrinting ADJ:9981-10046): the adjusted Cartesian
+    // point goes back to geographic (orthometric height for LLH: minus the geoid separation), the corrections are taken
+    // against the original values kept in preAdjMeas, and the variances of the measurement (its 3x3 Cartesian block) and
+    // of the adjusted measurement (its three Cartesian variances) are propagated to geographic with the Jacobian at the
+    // adjusted position; N-stat and Pelzer reliability are then recomputed in that frame.
+    void PrintAdjMeasurements_YLLH(std::ostream& os, size_t i, double crit) const
+    {
+        const dna_msr_t* r = &msr_[i];
+        const dna_stn_t& st = stn_[r->station1];
+        gadj_opts o;
+        gadj_default_opts(&o);
+        const gadj::Ellipsoid ell = gadj::make_ellipsoid(o.semi_major, o.inv_flattening);
+        double llh[3];
+        gadj::cart_to_geo(ell, r[0].measAdj, r[1].measAdj, r[2].measAdj, llh);
+        // d(XYZ)/d(lat, lon, h) at the adjusted position (FormCarttoGeoRotationMatrix, MFN:204-233) and its inverse
+        const double lat = llh[0], lon = llh[1], h = llh[2];
+        const double sl = std::sin(lat), cl = std::cos(lat), so = std::sin(lon), co = std::cos(lon);
+        const double nu = gadj::prime_vertical(ell, lat), ome = 1.0 - ell.e2;
+        const double t1b = ell.a * ell.e2 * sl * cl, t1c = std::pow(1.0 - ell.e2 * sl * sl, 1.5);
+        const double J[9] = {t1b * cl * co / t1c - (nu + h) * sl * co, -(nu + h) * cl * so, cl * co,
+                             t1b * cl * so / t1c - (nu + h) * sl * so, (nu + h) * cl * co,  cl * so,
+                             t1b * ome * sl / t1c + (nu * ome + h) * cl, 0.0,               sl};
+        const double det = J[0] * (J[4] * J[8] - J[5] * J[7]) - J[1] * (J[3] * J[8] - J[5] * J[6]) + J[2] * (J[3] * J[7] - J[4] * J[6]);
+        const double Ji[9] = {(J[4] * J[8] - J[5] * J[7]) / det, (J[2] * J[7] - J[1] * J[8]) / det, (J[1] * J[5] - J[2] * J[4]) / det,
+                              (J[5] * J[6] - J[3] * J[8]) / det, (J[0] * J[8] - J[2] * J[6]) / det, (J[2] * J[3] - J[0] * J[5]) / det,
+                              (J[3] * J[7] - J[4] * J[6]) / det, (J[1] * J[6] - J[0] * J[7]) / det, (J[0] * J[4] - J[1] * J[3]) / det};
+        auto to_geo_diag = [&](const double* V, double* out) {     // diag(Ji V Ji^T)
+            for (int a = 0; a < 3; ++a) {
+                double s = 0.0;
+                for (int x = 0; x < 3; ++x)
+                    for (int y = 0; y < 3; ++y)
+                        s += Ji[3 * a + x] * V[3 * x + y] * Ji[3 * a + y];
+                out[a] = s;
+            }
+        };
+        const double Vm[9] = {r[0].term2, r[1].term2, r[2].term2, r[1].term2, r[1].term3, r[2].term3, r[2].term2, r[2].term3, r[2].term4};
+        const double Va[9] = {r[0].measAdjPrec, 0, 0, 0, r[1].measAdjPrec, 0, 0, 0, r[2].measAdjPrec};
+        double var[3], adjp[3];
+        to_geo_diag(Vm, var);
+        to_geo_diag(Va, adjp);
+        double adj[3] = {lat, lon, h};
+        const bool ortho = r->station3 == DNA_LLH_TYPE;
+        if (ortho && std::fabs((double)st.geoidSep) > 1.0e-4)
+            adj[2] -= st.geoidSep;
+        const char comp[3] = {'P', 'L', ortho ? 'H' : 'h'};
+        for (int q = 0; q < 3; ++q) {
+            const double corr = adj[q] - r[q].preAdjMeas;
+            const double resp = std::fabs(var[q] - adjp[q]);
+            double pelzer = std::sqrt(var[q]) / std::sqrt(resp);
+            if (!(pelzer >= 0.0) || pelzer > 700.0)
+                pelzer = 999.99;
+            PrintMsrRow(os, 'Y', st.stationName, "", "", comp[q], q < 2, r[q].preAdjMeas, adj[q], corr, var[q], adjp[q], resp, corr / std::sqrt(resp),
+                        pelzer, r[q].preAdjCorr, crit);
+        }
     }
 
     // reference-frame name for file names: GDA2020 / GDA94 from the EPSG code of the station file, else "EPSG<code>"

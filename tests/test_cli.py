@@ -318,6 +318,51 @@ def test_cli_reproduces_reference_expected_adj_gpu(cli_gpu, tmp_path):
     _golden_gnss_text(cli_gpu, tmp_path)
 
 
+def _golden_urban_text(exe, tmp_path):
+    """`dnaadjust urban --output-adj-msr` on the reference's urban sample (tests/golden/urban_sample.npz: types
+    A B G H K L M S V Y Z, the Y cluster given as latitude / longitude / orthometric height) against the rows of
+    sampleData/urban.phased.adj.expected, parsed from our file by the parser that made the fixture.  Printed standard
+    deviations agree to the last digit (2e-4" on the Y rows, whose Jacobian is taken at the adjusted point); values tied to
+    station heights carry the 0.5 mm rounding of the exported geoid file (see tests/test_golden.py)."""
+    from tests.golden.make_urban_sample import parse_expected
+    z = np.load(os.path.join(ROOT, "tests", "golden", "urban_sample.npz"))
+    stn, msr = np.ascontiguousarray(z["stn"].astype(STN_DTYPE)), np.ascontiguousarray(z["msr"].astype(MSR_DTYPE))
+    _write_network(tmp_path, "urban", stn, msr)
+    r = _run(exe, tmp_path, "urban", "--output-adj-msr", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    sol, keys, rows, stn_names, stn_rows = parse_expected(os.path.join(tmp_path, "urban.simult.adj"))
+    want = dict(zip(z["solution_keys"].tolist(), z["solution"].tolist()))
+    assert all(sol[k] == want[k] for k in ("unknowns", "measurements", "dof", "outliers"))
+    assert abs(sol["chi_squared"] - want["chi_squared"]) < 1.0 and abs(sol["sigma_zero"] - want["sigma_zero"]) < 0.0011
+    assert keys == z["msr_keys"].tolist() and len(keys) == 1182
+    sec = np.radians(1.0 / 3600.0)
+    for key, got, w in zip(keys, rows, z["msr_rows"]):
+        t, comp = key[0], key.split()[-1]
+        ang = t in "ABKVZ" or (t == "Y" and comp in "PL")
+        unit = sec if ang else 1.0
+        assert abs(got[0] - w[0]) / unit < 1.1e-4, key                                   # the measurement as given
+        assert np.abs(got[3:6] - w[3:6]).max() < (2.6e-4 if ang else 1.1e-4), (key, got, w)     # the three SD columns
+        tol = (0.6 if t in "VZ" else 0.05) if ang else 8e-4
+        assert abs(got[1] - w[1]) / unit < tol and abs(got[2] - w[2]) < tol, (key, got, w)
+        assert abs(got[6] - w[6]) < 0.08 and abs(got[7] - w[7]) < 0.011, (key, got, w)
+        assert abs(got[8] - w[8]) < (0.05 if ang else 1.1e-3), (key, got, w)
+    # dnaimport sorts the station file by name; the fixture keeps the order of the ASCII file — pair the rows by name
+    assert sorted(stn_names) == sorted(z["stn_names"].tolist())
+    stn_rows = stn_rows[[stn_names.index(n) for n in z["stn_names"].tolist()]]
+    assert np.abs(stn_rows[:, [0, 1]] - z["stn_rows"][:, [0, 1]]).max() < 2e-9          # latitude, longitude as ddd.mmsssssss
+    assert np.abs(stn_rows[:, 3:7] - z["stn_rows"][:, 3:7]).max() < 7e-4                # h, X Y Z
+    assert np.abs(stn_rows[:, 7:10] - z["stn_rows"][:, 7:10]).max() < 1.1e-4            # SD e n up
+
+
+def test_cli_reproduces_reference_expected_urban_adj_hostsim(cli_hostsim, tmp_path):
+    _golden_urban_text(cli_hostsim, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_reproduces_reference_expected_urban_adj_gpu(cli_gpu, tmp_path):
+    _golden_urban_text(cli_gpu, tmp_path)
+
+
 def _read_snx(path):
     text = open(path).read()
     assert text.startswith("%=SNX 2.00 DNA") and text.rstrip().endswith("%ENDSNX")
