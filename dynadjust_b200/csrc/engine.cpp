@@ -1895,6 +1895,177 @@ int gadj_statistics(gadj_ctx* c, gadj_stats* stt, int write_back)
     return 0;
 }
 
+// ---- ignored measurements, a posteriori (UpdateIgnoredMeasurements_* ADJ:8750-9980; reporting only, host side) -------
+// For every measurement flagged as ignored whose stations were adjusted: the value computed from the adjusted
+// coordinates, mapped back to the domain the measurement was observed in (deflection / geoid / arc reductions undone),
+// and its difference from the measured value.  Writes preAdjMeas, measAdj, measCorr, preAdjCorr of the ignored records
+// (direction sets: scale1 = derived angle, scale2 = its variance, on the direction records).  Call after gadj_statistics
+// with write_back (the stations' geographic coordinates are then the adjusted ones).
+static int compute_measurements_host(gadj_ctx* c, bool want_ignored)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    const uint32_t ns = c->nstn;
+    std::vector<double> est(3 * (size_t)ns), llh(3 * (size_t)ns);
+    std::vector<float> geoid(ns);
+    dev::d2h(est.data(), c->d_est.p, est.size() * sizeof(double));
+    std::string e = dev::sync();
+    if (!e.empty())
+        return c->fail(e);
+    for (uint32_t s = 0; s < ns; ++s) {
+        cart_to_geo(c->ell, est[3 * s], est[3 * s + 1], est[3 * s + 2], &llh[3 * (size_t)s]);
+        geoid[s] = c->stn[s].geoidSep;
+    }
+    auto bad = [&](uint32_t s) { return s >= ns; };
+    // one scalar row (also the derived angle of a direction set): geometric value -> observation domain (ADJ:8194-8271)
+    auto scalar = [&](dna_msr_t& m, char type, const uint32_t st[3], int nst) {
+        RowDesc d;
+        std::memset(&d, 0, sizeof(d));
+        d.type = (uint8_t)type;
+        d.nst = (uint8_t)nst;
+        for (int k = 0; k < 3; ++k)
+            d.st[k] = st[k];
+        if (want_ignored || !c->reduced || type == 'D')
+            m.preAdjMeas = m.term1;           // else: reduced by an earlier run, the measured value is kept in preAdjMeas
+        dna_msr_t w = m;                      // the reductions act on a copy: the record keeps its value
+        w.term1 = m.preAdjMeas;
+        first_run_reduce(type, w, d.st, c->stn, est.data());
+        RowOut o;
+        double reduced = 0.0;
+        if (!design_row(d, w.term1, w.term3, w.term4, w.preAdjMeas, est.data(), llh.data(), geoid.data(), c->ell, o, &reduced))
+            return;
+        if (type == 'E' || type == 'M') {
+            w.term1 = reduced;
+            w.preAdjCorr = reduced - w.preAdjMeas;
+        }
+        double adj = w.term1 - o.l;           // the value computed from the adjusted coordinates, as reduced
+        switch (type) {
+        case 'D':
+            if (adj > kTwoPi)
+                adj -= kTwoPi;
+            adj += w.preAdjCorr;
+            break;
+        case 'E': {
+            const double r = chord_radius(c->ell, &est[3 * (size_t)st[0]], &est[3 * (size_t)st[1]], &llh[3 * (size_t)st[0]], &llh[3 * (size_t)st[1]]);
+            adj = std::asin(adj / 2.0 / r) * 2.0 * r;
+            break;
+        }
+        case 'M':
+            adj = chord_to_msl_arc(c->ell, adj, llh[3 * (size_t)st[0]], llh[3 * (size_t)st[1]], (double)geoid[st[0]], (double)geoid[st[1]]);
+            break;
+        case 'H': case 'L': case 'V':
+            adj -= w.preAdjCorr;
+            break;
+        case 'A': case 'I': case 'J': case 'K': case 'Z':
+            adj += w.preAdjCorr;
+            break;
+        default:
+            break;
+        }
+        m.preAdjCorr = w.preAdjCorr;
+        m.measAdj = adj;
+        m.measCorr = adj - m.preAdjMeas;
+        if (std::strchr("ABDKVZ", type)) {   // angular differences stay within half a turn
+            if (m.measCorr > kPi)
+                m.measCorr -= kTwoPi;
+            if (m.measCorr < -kPi)
+                m.measCorr += kTwoPi;
+        }
+    };
+    uint64_t i = 0;
+    while (i < c->nmsr) {
+        dna_msr_t& m = c->msr[i];
+        uint64_t step = 1;
+        switch (m.measType) {
+        case 'G':
+            step = 3;
+            break;
+        case 'X': case 'Y': {
+            uint64_t j = i;
+            for (uint32_t k = 0; k < std::max<uint32_t>(1u, m.vectorCount1) && j < c->nmsr; ++k)
+                j += 3 + 3ull * c->msr[j].vectorCount2;
+            step = j - i;
+            break;
+        }
+        case 'D':
+            step = std::max<uint32_t>(1u, m.vectorCount1);
+            break;
+        default:
+            break;
+        }
+        if (i + step > c->nmsr)
+            break;
+        if ((m.ignore != 0) == want_ignored) {
+            if (m.measType == 'G' || m.measType == 'X' || m.measType == 'Y') {
+                const bool geographic = m.measType == 'Y' && (std::strncmp(m.coordType, "LLH", 3) == 0 || std::strncmp(m.coordType, "LLh", 3) == 0);
+                for (uint64_t j = i; j + 2 < i + step;) {
+                    dna_msr_t* r = &c->msr[j];
+                    const uint32_t s1 = r->station1, s2 = m.measType == 'Y' ? r->station1 : r->station2;
+                    if (!bad(s1) && !bad(s2)) {
+                        double v[3];
+                        for (int q = 0; q < 3; ++q)
+                            v[q] = m.measType == 'Y' ? est[3 * (size_t)s1 + q] : est[3 * (size_t)s2 + q] - est[3 * (size_t)s1 + q];
+                        if (geographic) {       // UpdateIgnoredMeasurements_Y (ADJ:9720-9830): latitude, longitude, height as supplied
+                            v[0] = llh[3 * (size_t)s1], v[1] = llh[3 * (size_t)s1 + 1], v[2] = llh[3 * (size_t)s1 + 2];
+                            if (std::strncmp(m.coordType, "LLH", 3) == 0 && std::fabs((double)geoid[s1]) > 1.0e-4) {
+                                r[2].preAdjCorr = geoid[s1];
+                                v[2] -= geoid[s1];
+                            }
+                        }
+                        for (int q = 0; q < 3; ++q) {
+                            if (want_ignored || !c->reduced)
+                                r[q].preAdjMeas = r[q].term1;
+                            r[q].measAdj = v[q];
+                            r[q].measCorr = v[q] - r[q].preAdjMeas;
+                        }
+                    }
+                    j += 3 + 3ull * r->vectorCount2;
+                }
+            } else if (m.measType == 'D') {
+                double prev_dir = m.term1, prev_var = m.term2;
+                uint64_t prev = i;
+                for (uint64_t j = i + 1; j < i + step; ++j) {
+                    dna_msr_t& dir = c->msr[j];
+                    if (!want_ignored && dir.ignore)
+                        continue;             // an ignored direction inside a set that is used (ADJ:5120-5129)
+                    const uint32_t st[3] = {c->msr[prev].station1, c->msr[prev].station2, dir.station2};
+                    if (!bad(st[0]) && !bad(st[1]) && !bad(st[2]) && st[0] != st[1] && st[0] != st[2] && st[1] != st[2]) {
+                        dna_msr_t angle = c->msr[prev];
+                        angle.term1 = dir.term1 - prev_dir;
+                        if (angle.term1 < 0)
+                            angle.term1 += kTwoPi;
+                        if (angle.term1 > kTwoPi)
+                            angle.term1 -= kTwoPi;
+                        scalar(angle, 'D', st, 3);
+                        dir.scale1 = angle.preAdjMeas;
+                        dir.scale2 = prev_var + dir.term2;
+                        dir.measCorr = angle.measCorr;
+                        dir.measAdj = angle.measAdj;
+                        dir.preAdjCorr = angle.preAdjCorr;
+                    }
+                    prev_dir = dir.term1;
+                    prev_var = dir.term2;
+                    prev = j;
+                }
+            } else if (is_scalar_type(m.measType)) {
+                const int nst = stations_of_type(m.measType);
+                const uint32_t st[3] = {m.station1, nst > 1 ? m.station2 : m.station1, nst > 2 ? m.station3 : m.station1};
+                if (!bad(st[0]) && !bad(st[1]) && !bad(st[2]) && (nst < 2 || st[0] != st[1]) && (nst < 3 || (st[0] != st[2] && st[1] != st[2])))
+                    scalar(m, m.measType, st, nst);
+            }
+        }
+        i += step;
+    }
+    return 0;
+}
+
+int gadj_update_ignored_measurements(gadj_ctx* c) { return compute_measurements_host(c, true); }
+
+// "Computed Measurements (a-priori)" of --output-iter-cmp-msr (PrintCompMeasurements PRN:1938-2023): the same evaluation
+// for the measurements that take part, at the current estimates.  Meant for the start of the first iteration — later
+// iterations read the re-linearised records of gadj_statistics.
+int gadj_compute_measurements(gadj_ctx* c) { return compute_measurements_host(c, false); }
+
 int gadj_get_estimates(gadj_ctx* c, double* xyz)
 {
     if (!c->prepared)

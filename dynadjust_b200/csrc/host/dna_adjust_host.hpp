@@ -16,6 +16,8 @@
 #include <sstream>
 #include <stdexcept>
 #include <algorithm>
+#include <array>
+#include <tuple>
 #include <cctype>
 #include <string>
 #include <unordered_map>
@@ -49,6 +51,20 @@ struct adjust_settings {            // the fields of project_settings.a / .g / .
     bool update_binary_files = true;
     std::string type_b_global, type_b_file; // --type-b-sd-global "e,n,up" (metres, 1 sigma), --type-b-sd-file <file> (dnaoptions-interface.hpp)
     std::string station_constraints;       // --constraints "STN1,CCC,STN2,FFC" (dnaoptions.hpp:481)
+    // report layout (output_settings, dnaoptions.hpp:496-516)
+    int sort_adj_msr = 0;                  // --sort-adj-msr-field 0 file order | 1 type | 2 inst | 3 targ | 4 value | 5 correction | 6 adj sd | 7 n-stat
+    int adj_gnss_units = 0;                // --output-adj-gnss-units 0 XYZ | 1 ENU | 2 AED | 3 ADU
+    bool adj_msr_tstat = false;            // --output-tstat-adj-msr
+    bool output_msr_to_stn = false;        // --output-msr-to-stn
+    int sort_msr_to_stn = 0;               // --sort-msr-to-stn-field 0 file order | 1 name | 2 count | 3 count descending
+    bool stn_corrections = false;          // --stn-corrections: Corr(e) Corr(n) Corr(up) columns in the station tables
+    std::string stn_coord_types = "PLHhXYZ";   // --stn-coord-types
+    bool sort_stn_orig_order = false;      // --sort-stn-orig-order
+    int angular_type_stn = 0, angular_type_msr = 0, dms_format_msr = 0;   // 0 dms | 1 decimal degrees; 0 "d m s" | 1 symbols | 2 d.mmsss
+    int precision_seconds_stn = 5, precision_metres_stn = 4, precision_seconds_msr = 4, precision_metres_msr = 4;
+    bool iter_adj_stn = false, iter_adj_stat = false, iter_adj_msr = false, iter_cmp_msr = false;   // --output-iter-*
+    bool output_ignored_msrs = false;      // --output-ignored-msrs
+    std::string comments;                  // --comments
     std::string command_line;
 };
 
@@ -117,15 +133,43 @@ class dna_adjust {
         auto t0 = std::chrono::steady_clock::now();
         iterations_.clear();
         adjustStatus_ = ADJUST_SUCCESS;
+        iter_pre_.clear();
+        iter_post_.clear();
+        const bool iter_reports = a_.iter_adj_stn || a_.iter_adj_stat || a_.iter_adj_msr || a_.iter_cmp_msr;
         for (uint32_t i = 0; i < a_.max_iterations; ++i) {
+            std::ostringstream pre, post;
+            if (a_.iter_cmp_msr) {
+                // computed measurements at the start of the iteration (ADJ:2443-2445): the a-priori evaluation before the
+                // first solve, afterwards the records re-linearised by the statistics of the previous iteration
+                if (i == 0)
+                    check(gadj_compute_measurements(ctx_));
+                PrintMsrTableHeader(pre, "Computed Measurements (a-priori)", 1);
+                PrintMeasurementRecords(pre, CollectMeasurements(nullptr, -1, false), 1);
+                pre << "\n";
+            }
             auto ti = std::chrono::steady_clock::now();
             gadj_iter_result r;
             check(gadj_iterate(ctx_, i == 0 ? GADJ_ITER_NORMALS : 0, &r));
             r.ms_inverse = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - ti).count();  // wall
             iterations_.push_back(r);
             maxCorr_ = r.max_corr;
+            iter_pre_.push_back(pre.str());
+            iter_post_.push_back(std::string());
             if (std::fabs(r.max_corr) <= a_.iteration_threshold)
                 break;
+            if (iter_reports && i + 1 < a_.max_iterations) {
+                // --output-iter-adj-stat / -msr / -stn: statistics, adjusted measurements and stations of an iteration that
+                // is followed by another (ADJ:2483-2502); needs the rigorous variances of this iteration
+                check(gadj_form_inverse(ctx_));
+                GenerateStatistics();
+                if (a_.iter_adj_stat)
+                    PrintStatisticsSummary(post, false);
+                if (a_.iter_adj_msr)
+                    PrintAdjMeasurements(post, nullptr, -1);
+                if (a_.iter_adj_stn)
+                    PrintAdjStations(post, nullptr);
+                iter_post_.back() = post.str();
+            }
         }
         if (iterations_.size() == a_.max_iterations && std::fabs(maxCorr_) > a_.iteration_threshold)
             adjustStatus_ = ADJUST_MAX_ITERATIONS_EXCEEDED;   // ADJ:2523-2525
@@ -142,8 +186,15 @@ class dna_adjust {
         vcv_.resize(9 * stn_.size());
         check(gadj_get_estimates(ctx_, est_.data()));
         check(gadj_get_station_vcvs(ctx_, vcv_.data()));
+        raw_vcv_ = vcv_;                              // before type B uncertainties: adjusted-measurement precisions use these
         ApplyTypeBUncertainties();
         ComputeTestStat();
+        if (a_.adj_msr_tstat) {                       // Student's t = n-stat / sqrt(sigma zero) (UpdateMsrTstatistic ADJ:6914-7092)
+            const double sz = std::sqrt(stats_.sigma_zero);
+            for (dna_msr_t& m : msr_)
+                if (!m.ignore && m.measStart <= 2)
+                    m.TStat = std::fabs(sz) < 1.0e-10 ? 0.0 : m.NStat / sz;
+        }
     }
 
     // getters (ADJH:336-354)
@@ -176,11 +227,17 @@ class dna_adjust {
         PrintOutputFileHeaderInfo(adj, "DYNADJUST ADJUSTMENT OUTPUT FILE", stem + ".adj");
         adj << "\n+ Initialising adjustment\n+ Loading network files\n+ Allocating memory\n\n+ Preparing for adjustment...  done.\n";
         adj << "+ Commencing " << (a_.adjust_mode == SimultaneousMode ? "simultaneous" : "phased") << " adjustment\n\n";
-        for (size_t i = 0; i < iterations_.size(); ++i)
+        for (size_t i = 0; i < iterations_.size(); ++i) {
             PrintIteration(adj, (uint32_t)i + 1, iterations_[i]);
+            adj << iter_pre_[i] << iter_post_[i];
+        }
         PrintStatistics(adj);
         if (a_.output_adj_msr)
             PrintAdjustedNetworkMeasurements(adj);
+        if (a_.output_adj_msr && a_.output_ignored_msrs)
+            PrintIgnoredAdjMeasurements(adj);
+        if (a_.output_msr_to_stn)
+            PrintMeasurementsToStation(adj);
         std::ofstream xyz(stem + ".xyz");
         PrintOutputFileHeaderInfo(xyz, "DYNADJUST COORDINATE OUTPUT FILE", stem + ".xyz");
         PrintAdjustedNetworkStations(adj, xyz);
@@ -385,8 +442,9 @@ class dna_adjust {
         os << buf << "\n" << std::string(20 + 2 + 4 * 19 + 3 * 11, '-') << "\n";
         for (size_t i = 0; i < stn_.size(); ++i) {
             const dna_stn_t& s = stn_[i];
-            const double d[3] = {est_[3 * i] - apriori_xyz_[3 * i], est_[3 * i + 1] - apriori_xyz_[3 * i + 1],
-                                 est_[3 * i + 2] - apriori_xyz_[3 * i + 2]};
+            double o[3];
+            OriginalXYZ(i, o);
+            const double d[3] = {est_[3 * i] - o[0], est_[3 * i + 1] - o[1], est_[3 * i + 2] - o[2]};
             const double lat = s.currentLatitude, lon = s.currentLongitude;   // the adjusted position, as in the reference
             const double e = -std::sin(lon) * d[0] + std::cos(lon) * d[1];
             const double n = -std::sin(lat) * std::cos(lon) * d[0] - std::sin(lat) * std::sin(lon) * d[1] + std::cos(lat) * d[2];
@@ -749,27 +807,23 @@ class dna_adjust {
         os << "\n";
     }
 
-    static std::string hp_dms(double rad)
-    {   // degrees.minutes-seconds "HP" notation, 9 decimals (FormatDmsString / RadtoDms)
-        double deg = rad * 180.0 / 3.14159265358979323846;
-        double sgn = deg < 0 ? -1 : 1;
-        deg = std::fabs(deg);
-        double d = std::floor(deg + 1e-13);
-        double m = std::floor((deg - d) * 60 + 1e-11);
-        double s = ((deg - d) * 60 - m) * 60;
-        if (s < 0)
-            s = 0;
-        if (s >= 59.999995) {
-            s = 0;
-            m += 1;
-        }
-        if (m >= 60) {
-            m -= 60;
-            d += 1;
-        }
-        char buf[64];
-        snprintf(buf, sizeof(buf), "%.9f", sgn * (d + m / 100.0 + s / 10000.0));
-        return buf;
+    // degrees.minutes-seconds "HP" notation ddd.mmsss.. with `decimals` places (RadtoDms + fixed, PRN:1632-1650); integer
+    // arithmetic on the last printed place of a second so that carries are exact
+    static std::string hp_dms(double rad, int decimals = 9)
+    {
+        const int sp = std::max(0, decimals - 4);
+        long long scale = 1;
+        for (int k = 0; k < sp; ++k)
+            scale *= 10;
+        const double deg = std::fabs(rad) * 180.0 / 3.14159265358979323846;
+        const long long units = std::llround(deg * 3600.0 * (double)scale);
+        const long long d = units / (3600LL * scale), rem = units % (3600LL * scale);
+        const long long mi = rem / (60LL * scale), sec = rem % (60LL * scale);
+        char b[64], frac[32] = "";
+        if (sp > 0)
+            snprintf(frac, sizeof(frac), "%0*lld", sp, sec % scale);
+        snprintf(b, sizeof(b), "%s%lld.%02lld%02lld%s", rad < 0 && units > 0 ? "-" : "", d, mi, sec / scale, frac);
+        return b;
     }
 
     void PrintOutputFileHeaderInfo(std::ostream& os, const char* title, const std::string& file) const
@@ -848,13 +902,24 @@ class dna_adjust {
         char buf[64];
         snprintf(buf, sizeof(buf), "00:00:%09.6f", total_ms_ / 1e3);
         var("Total time") << buf << "\n\n";
+        PrintStatisticsSummary(os, true);
+    }
+
+    void PrintStatisticsSummary(std::ostream& os, bool printPelzer) const
+    {
+        auto var = [&](const char* n) -> std::ostream& { return os << std::left << std::setw(35) << n; };
         var("Number of unknown parameters") << stats_.unknown_params << "\n";
-        var("Number of measurements") << stats_.measurement_params << "  (" << stats_.outliers << " potential outliers)\n";
+        var("Number of measurements") << stats_.measurement_params;
+        if (stats_.outliers > 0)
+            os << "  (" << stats_.outliers << " potential outlier" << (stats_.outliers > 1 ? "s" : "") << ")";
+        os << "\n";
         var("Degrees of freedom") << stats_.dof << "\n";
         var("Chi squared") << std::fixed << std::setprecision(2) << stats_.chi_squared << "\n";
         var("Rigorous Sigma Zero") << std::fixed << std::setprecision(3) << stats_.sigma_zero << "\n";
-        var("Global (Pelzer) Reliability") << std::fixed << std::setprecision(3) << stats_.global_pelzer
-                                           << "   (excludes non redundant measurements)\n\n";
+        if (printPelzer)
+            var("Global (Pelzer) Reliability") << std::fixed << std::setprecision(3) << stats_.global_pelzer
+                                               << "   (excludes non redundant measurements)\n";
+        os << "\n";
         if (a_.adjust_mode == Phased_Block_1Mode) {   // no global test in block-1 mode (ADJ:7140-7147)
             os << "\n";
             return;
@@ -862,7 +927,8 @@ class dna_adjust {
         std::ostringstream t;
         t << "Chi-Square test (" << std::fixed << std::setprecision(1) << a_.confidence_interval << "%)";
         var(t.str().c_str()) << std::fixed << std::setprecision(3) << chiLower_ << " < " << stats_.sigma_zero << " < " << chiUpper_
-                             << "          *** " << (passFail_ == 0 ? "PASSED" : (passFail_ == 1 ? "WARNING" : "FAILED")) << " ***\n\n";
+                             << "          " << (stats_.dof < 1 ? "NO REDUNDANCY" : (passFail_ == 0 ? "*** PASSED ***" : (passFail_ == 1 ? "*** WARNING ***" : "*** FAILED ***")))
+                             << "\n\n";
     }
 
     // PrintAdjustedNetworkMeasurements (PRN:494-533): every measurement; block-1 mode reports the measurements of the
@@ -896,59 +962,376 @@ class dna_adjust {
         }
     }
 
-    void PrintAdjMeasurements(std::ostream& os, const std::vector<int32_t>* rec_block, int32_t block) const
+    // ---- adjusted measurements table (PrintAdjMeasurements PRN:1682-1782, PrintMeasurementRecords PRN:2025-2117) ------
+    // Measurements are listed by their first record (a G baseline, an X / Y cluster, a direction set, a scalar row),
+    // sorted as --sort-adj-msr-field asks, and printed by type.
+    size_t MeasurementSpan(size_t i) const
     {
-        os << "\nAdjusted Measurements\n------------------------------------------\n\n";
-        char buf[512];
-        snprintf(buf, sizeof(buf), "%-2s%-20s%-20s%-20s%-3s%-2s%19s%19s%12s%13s%13s%13s%11s%12s%14s%7s", "M", "Station 1", "Station 2",
-                 "Station 3", "*", "C", "Measured", "Adjusted", "Correction", "Meas. SD", "Adj. SD", "Corr. SD", "N-stat", "Pelzer Rel",
-                 "Pre Adj Corr", "Out");
-        os << buf << "\n" << std::string(200, '-') << "\n";
-        const double crit = stats_.critical_value;
-        for (size_t i = 0; i < msr_.size(); ++i) {
-            const dna_msr_t& m = msr_[i];
-            if (m.ignore || m.measStart > 2)   // covariance records of X / Y clusters carry no row
-                continue;
-            if (rec_block && (*rec_block)[i] != block)
-                continue;
-            const char t = m.measType;
-            const bool gnss = t == 'G' || t == 'X' || t == 'Y';
-            if (t == 'Y' && m.measStart == 0 && (m.station3 == DNA_LLH_TYPE || m.station3 == DNA_LLh_TYPE) && i + 2 < msr_.size()) {
-                PrintAdjMeasurements_YLLH(os, i, crit);
-                i += 2;
-                continue;
-            }
-            // angles (A B D K V Z) and astronomic / geodetic latitudes and longitudes (I J P Q) print as d m s, their
-            // corrections and standard deviations in seconds (PrintAdjMeasurementsAngular, PRN:195-201, 2302-2350)
-            const bool angular = std::strchr("ABDKVZIJPQ", t) != nullptr;
-            char comp = gnss ? "XYZ"[(int)m.measStart] : ' ';
-            const double var = !gnss ? m.term2 : (m.measStart == 0 ? m.term2 : (m.measStart == 1 ? m.term3 : m.term4));
-            const char* s1 = stn_[m.station1].stationName;
-            const char* s2 = (m.measurementStations >= 2 && t != 'Y') ? stn_[m.station2].stationName : "";
-            const char* s3 = (m.measurementStations >= 3 && t == 'A') ? stn_[m.station3].stationName : "";
-            PrintMsrRow(os, t, s1, s2, s3, comp, angular, m.preAdjMeas, m.measAdj, m.measCorr, var, m.measAdjPrec, m.residualPrec, m.NStat,
-                        m.PelzerRel, m.preAdjCorr, crit);
+        const dna_msr_t& m = msr_[i];
+        switch (m.measType) {
+        case 'G': case 'X': case 'Y': {
+            size_t j = i;
+            const uint32_t count = std::max<uint32_t>(1u, m.vectorCount1);
+            for (uint32_t k = 0; k < count && j < msr_.size(); ++k)
+                j += 3 + 3 * (size_t)msr_[j].vectorCount2;
+            return std::min(j, msr_.size()) - i;
         }
+        case 'D':
+            return std::max<uint32_t>(1u, m.vectorCount1);
+        default:
+            return 1;
+        }
+    }
+
+    std::vector<uint32_t> CollectMeasurements(const std::vector<int32_t>* rec_block, int32_t block, bool ignored) const
+    {
+        std::vector<uint32_t> list;
+        for (size_t i = 0; i < msr_.size();) {
+            const size_t span = MeasurementSpan(i);
+            if ((msr_[i].ignore != 0) == ignored && (!rec_block || (*rec_block)[i] == block))
+                list.push_back((uint32_t)i);
+            i += span;
+        }
+        return list;
+    }
+
+    // largest |field| over the components of a compound measurement (CompareMeas*_PairFirst, dnatemplatestnmsrfuncs.hpp:1148-1810)
+    template <typename F>
+    double LargestOf(uint32_t first, F field) const
+    {
+        const dna_msr_t& m = msr_[first];
+        double v = 0.0;
+        switch (m.measType) {
+        case 'G': case 'X': case 'Y': {
+            size_t j = first;
+            const uint32_t count = std::max<uint32_t>(1u, m.vectorCount1);
+            for (uint32_t k = 0; k < count && j + 2 < msr_.size(); ++k) {
+                for (int q = 0; q < 3; ++q)
+                    v = std::max(v, std::fabs(field(msr_[j + q])));
+                j += 3 + 3 * (size_t)msr_[j].vectorCount2;
+            }
+            return v;
+        }
+        case 'D':
+            for (uint32_t d = 0; d < std::max<uint32_t>(1u, m.vectorCount1) && first + d < msr_.size(); ++d)
+                v = std::max(v, std::fabs(field(msr_[first + d])));
+            return v;
+        default:
+            return std::fabs(field(m));
+        }
+    }
+
+    void SortMeasurements(std::vector<uint32_t>& list) const
+    {
+        auto by_keys = [&](auto key) {
+            std::stable_sort(list.begin(), list.end(), [&](uint32_t a, uint32_t b) { return key(msr_[a]) < key(msr_[b]); });
+        };
+        auto by_largest = [&](auto field) {
+            std::vector<std::pair<double, uint32_t>> k;
+            for (uint32_t f : list)
+                k.emplace_back(LargestOf(f, field), f);
+            std::stable_sort(k.begin(), k.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+            for (size_t i = 0; i < k.size(); ++i)
+                list[i] = k[i].second;
+        };
+        switch (a_.sort_adj_msr) {
+        case 1:   // measurement type, first station, second station, value
+            by_keys([](const dna_msr_t& m) { return std::make_tuple(m.measType, m.station1, m.station2, m.term1); });
+            break;
+        case 2:   // "instrument station" sorts on the second station (SortMeasurementsbyToStn, PRN:1721)
+            by_keys([](const dna_msr_t& m) { return std::make_tuple(m.station2, m.measType, m.station1, m.term1); });
+            break;
+        case 3:   // "target station" sorts on the first station (SortMeasurementsbyFromStn, PRN:1724)
+            by_keys([](const dna_msr_t& m) { return std::make_tuple(m.station1, m.measType, m.station2, m.term1); });
+            break;
+        case 4: by_largest([](const dna_msr_t& m) { return m.term1; }); break;
+        case 5: by_largest([](const dna_msr_t& m) { return m.measCorr; }); break;
+        case 6: by_largest([](const dna_msr_t& m) { return m.measAdjPrec; }); break;
+        case 7: by_largest([](const dna_msr_t& m) { return m.NStat; }); break;
+        default: break;   // original (file) order
+        }
+    }
+
+    // StringFromTW (dnastrmanipfuncs.hpp:216-264): fixed notation when it fits the column, else scientific
+    static std::string StringFromTW(double t, int width, int precision)
+    {
+        char b[96];
+        snprintf(b, sizeof(b), "%.*f", precision, t);
+        if ((int)std::strlen(b) <= width) {
+            snprintf(b, sizeof(b), "%*.*f", width, precision, t);
+            return b;
+        }
+        const int need = t < 0.0 ? 6 : 5;
+        if (width < need)
+            return std::string((size_t)width, '#');
+        int prec1 = width - need;
+        if (prec1 > 0)
+            prec1--;
+        snprintf(b, sizeof(b), "%*.*e", width, std::min(precision, prec1), t);
+        return b;
+    }
+    static double removeNegativeZero(double t, int precision)
+    {
+        if (t < 0.0 || (t == 0.0 && std::signbit(t)))
+            return std::fabs(std::floor(t * std::pow(10.0, precision) + 0.5)) > 0.0 ? t : 0.0;
+        return t;
+    }
+    static std::string Fixed(double v, int width, int precision)
+    {
+        char b[96];
+        snprintf(b, sizeof(b), "%*.*f", width, precision, v);
+        return b;
+    }
+    // a number that may blow up in a questionable adjustment: column-safe notation then (PRN:2216-2223)
+    std::string Num(double v, int width, int precision, bool safe) const { return safe ? StringFromTW(v, width, precision) : Fixed(v, width, precision); }
+
+    // "ddd mm ss.ssss" / symbols / ddd.mmssssss / decimal degrees of an angular measurement (FormatAngularMeasurement PRN:2184-2260)
+    static std::string dms_fields(double rad, int sec_precision, char* sign, long long* d, long long* mi, long long* s_int, long long* s_frac)
+    {
+        const double deg = std::fabs(rad) * 180.0 / 3.14159265358979323846;
+        long long scale = 1;
+        for (int k = 0; k < sec_precision; ++k)
+            scale *= 10;
+        const long long units = std::llround(deg * 3600.0 * (double)scale);   // carries are exact in integer arithmetic
+        *d = units / (3600LL * scale);
+        const long long rem = units % (3600LL * scale);
+        *mi = rem / (60LL * scale);
+        const long long sec = rem % (60LL * scale);
+        *s_int = sec / scale;
+        *s_frac = sec % scale;
+        *sign = rad < 0 ? '-' : 0;
+        return std::string();
+    }
+    std::string AngleString(double rad, int sec_precision, int angular_type, int dms_format) const
+    {
+        char b[96];
+        if (angular_type == 1) {   // DDEG
+            snprintf(b, sizeof(b), "%.*f", 4 + sec_precision, rad * 180.0 / 3.14159265358979323846);
+            return b;
+        }
+        char sign;
+        long long d, mi, si, sf;
+        dms_fields(rad, sec_precision, &sign, &d, &mi, &si, &sf);
+        const std::string sg = sign ? "-" : "";
+        char frac[32] = "";
+        if (sec_precision > 0)
+            snprintf(frac, sizeof(frac), "%0*lld", sec_precision, sf);
+        switch (dms_format) {
+        case 1:   // ddd°mm'ss.sss" (Latin-1 symbols as the reference writes them)
+            snprintf(b, sizeof(b), "%s%lld\260%02lld\222%02lld%s%s\224", sg.c_str(), d, mi, si, sec_precision > 0 ? "." : "", frac);
+            break;
+        case 2:   // ddd.mmssssss
+            snprintf(b, sizeof(b), "%s%lld.%02lld%02lld%s", sg.c_str(), d, mi, si, frac);
+            break;
+        default:  // ddd mm ss.ssss
+            snprintf(b, sizeof(b), "%s%lld %02lld %02lld%s%s", sg.c_str(), d, mi, si, sec_precision > 0 ? "." : "", frac);
+        }
+        return b;
+    }
+
+    struct MsrRow {           // one printed row of the table, in the units of its frame
+        char type, cardinal;
+        bool angular, ignore;
+        const char *s1, *s2, *s3;
+        double measured, adjusted, corr, var, adj_prec, res_prec, nstat, tstat, pelzer, pre_adj_corr;
+        bool pre_adj_corr_linear;   // the H row of a geographic Y cluster prints its N value in metres
+        bool show_type;
+    };
+
+    void PrintMsrRow(std::ostream& os, const MsrRow& r, int mode /*0 adjusted, 1 computed / ignored*/) const
+    {
+        const double crit = stats_.critical_value;
+        const bool safe = std::fabs(r.nstat) > crit * 4.0;
+        const double SEC = 3.14159265358979323846 / 180.0 / 3600.0, DEG = 3.14159265358979323846 / 180.0;
+        const int pa = a_.precision_seconds_msr, pl = a_.precision_metres_msr;
+        char head[80];
+        snprintf(head, sizeof(head), "%-2s%-20s%-20s%-20s%-3s%-2c", r.show_type ? std::string(1, r.type).c_str() : "", r.s1, r.s2, r.s3,
+                 r.ignore ? "*" : " ", r.cardinal);
+        os << head;
+        if (r.angular) {
+            const double unit = a_.angular_type_msr == 1 ? DEG : SEC;
+            os << std::setw(19) << std::right << AngleString(r.measured, pa, a_.angular_type_msr, a_.dms_format_msr)
+               << std::setw(19) << std::right << AngleString(r.adjusted, pa, a_.angular_type_msr, a_.dms_format_msr)
+               << Num(removeNegativeZero(r.corr / unit, pa), 12, pa, safe) << Num(std::sqrt(r.var) / unit, 13, pa, safe);
+            if (mode == 0)
+                os << Num(std::sqrt(std::fabs(r.adj_prec)) / unit, 13, pa, safe) << Num(std::sqrt(r.res_prec) / unit, 13, pa, safe);
+        } else {
+            os << Fixed(r.measured, 19, pl) << Fixed(r.adjusted, 19, pl) << Num(removeNegativeZero(r.corr, pl), 12, pl, safe)
+               << Num(std::sqrt(r.var), 13, pl, safe);
+            if (mode == 0)
+                os << Num(std::sqrt(std::fabs(r.adj_prec)), 13, pl, safe) << Num(std::sqrt(r.res_prec), 13, pl, safe);
+        }
+        if (mode == 0) {
+            os << Num(removeNegativeZero(r.nstat, 2), 11, 2, safe);
+            if (a_.adj_msr_tstat)
+                os << Num(removeNegativeZero(r.tstat, 2), 11, 2, safe);
+            os << Fixed(r.pelzer, 12, 2);
+        }
+        // pre-adjustment correction (PrintMeasurementCorrection PRN:2435-2486): seconds for the angular types, else metres
+        if (std::strchr("ABDIJKPQVZ", r.type))
+            os << Fixed(removeNegativeZero(r.pre_adj_corr / SEC, pa), 14, pa);
+        else if (r.type == 'Y')
+            os << Fixed(r.pre_adj_corr_linear ? removeNegativeZero(r.pre_adj_corr, pl) : 0.0, 14, (r.angular || r.cardinal == 'h') ? pa : pl);
+        else
+            os << Fixed(removeNegativeZero(r.pre_adj_corr, pa), 14, pa);
+        if (mode == 0)
+            os << std::setw(12) << std::right << (std::fabs(r.nstat) > crit ? "*" : " ");
         os << "\n";
     }
 
-    void PrintMsrRow(std::ostream& os, char t, const char* s1, const char* s2, const char* s3, char comp, bool angular, double measured,
-                     double adjusted, double corr, double var, double adj_prec, double res_prec, double nstat, double pelzer,
-                     double pre_adj_corr, double crit) const
+    MsrRow ScalarRow(const dna_msr_t& m, char cardinal, double var) const
     {
-        const double SEC = 3.14159265358979323846 / 180.0 / 3600.0, unit = angular ? SEC : 1.0;
-        char meas[32], adjd[32], buf[512];
-        if (angular) {
-            snprintf(meas, sizeof(meas), "%s", dms_spaced(measured).c_str());
-            snprintf(adjd, sizeof(adjd), "%s", dms_spaced(adjusted).c_str());
-        } else {
-            snprintf(meas, sizeof(meas), "%.4f", measured);
-            snprintf(adjd, sizeof(adjd), "%.4f", adjusted);
+        MsrRow r{};
+        r.type = m.measType;
+        r.cardinal = cardinal;
+        r.angular = std::strchr("ABDKVZIJPQ", m.measType) != nullptr;
+        r.ignore = m.ignore != 0;
+        r.s1 = stn_[m.station1].stationName;
+        r.s2 = r.s3 = "";
+        r.measured = m.preAdjMeas;
+        r.adjusted = m.measAdj;
+        r.corr = m.measCorr;
+        r.var = var;
+        r.adj_prec = m.measAdjPrec;
+        r.res_prec = m.residualPrec;
+        r.nstat = m.NStat;
+        r.tstat = m.TStat;
+        r.pelzer = m.PelzerRel;
+        r.pre_adj_corr = m.preAdjCorr;
+        r.pre_adj_corr_linear = false;
+        r.show_type = true;
+        return r;
+    }
+
+    void PrintMsrTableHeader(std::ostream& os, const std::string& heading, int mode) const
+    {
+        os << "\n" << heading << "\n------------------------------------------\n\n";
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%-2s%-20s%-20s%-20s%-3s%-2s%19s%19s%12s%13s", "M", "Station 1", "Station 2", "Station 3", "*", "C", "Measured",
+                 mode == 0 ? "Adjusted" : "Computed", mode == 0 ? "Correction" : "Difference", "Meas. SD");
+        os << buf;
+        size_t width = 2 + 60 + 3 + 3 + 19 + 19 + 12 + 13;
+        if (mode == 0) {
+            os << std::setw(13) << std::right << "Adj. SD" << std::setw(13) << "Corr. SD" << std::setw(11) << "N-stat";
+            width += 13 + 13 + 11;
+            if (a_.adj_msr_tstat) {
+                os << std::setw(11) << "T-stat";
+                width += 11;
+            }
+            os << std::setw(12) << "Pelzer Rel";
+            width += 12;
         }
-        snprintf(buf, sizeof(buf), "%-2c%-20s%-20s%-20s%-3s%-2c%19s%19s%12.4f%13.4f%13.4f%13.4f%11.2f%12.2f%14.4f%7s", t, s1, s2, s3, "", comp, meas,
-                 adjd, corr / unit, std::sqrt(var) / unit, std::sqrt(std::fabs(adj_prec)) / unit, std::sqrt(res_prec) / unit, nstat, pelzer,
-                 pre_adj_corr / unit, std::fabs(nstat) > crit ? "*" : "");
-        os << buf << "\n";
+        os << std::setw(14) << std::right << "Pre Adj Corr";
+        width += 14;
+        if (mode == 0) {
+            os << std::setw(12) << "Outlier?";
+            width += 12;
+        }
+        os << "\n" << std::string(width, '-') << "\n";
+    }
+
+    void PrintAdjMeasurements(std::ostream& os, const std::vector<int32_t>* rec_block, int32_t block, const std::string& heading = "Adjusted Measurements") const
+    {
+        PrintMsrTableHeader(os, heading, 0);
+        std::vector<uint32_t> list = CollectMeasurements(rec_block, block, false);
+        SortMeasurements(list);
+        PrintMeasurementRecords(os, list, 0);
+        os << "\n";
+    }
+
+    // "Ignored Measurements (a-posteriori)" (PrintIgnoredAdjMeasurements PRN:1784-1923): measured, computed from the
+    // adjusted coordinates, difference, measurement SD and pre-adjustment correction of every ignored measurement
+    void PrintIgnoredAdjMeasurements(std::ostream& os)
+    {
+        check(gadj_update_ignored_measurements(ctx_));
+        PrintMsrTableHeader(os, "Ignored Measurements (a-posteriori)", 1);
+        PrintMeasurementRecords(os, CollectMeasurements(nullptr, -1, true), 1);
+        os << "\n\n";
+    }
+
+    void PrintMeasurementRecords(std::ostream& os, const std::vector<uint32_t>& list, int mode) const
+    {
+        for (uint32_t first : list) {
+            const dna_msr_t& m = msr_[first];
+            switch (m.measType) {
+            case 'G': case 'X': case 'Y':
+                PrintMeasurements_GXY(os, first, mode);
+                break;
+            case 'D':
+                PrintMeasurements_D(os, first, mode);
+                break;
+            default: {
+                MsrRow r = ScalarRow(m, ' ', m.term2);
+                if (m.measurementStations >= 2)
+                    r.s2 = stn_[m.station2].stationName;
+                if (m.measurementStations >= 3 && m.measType == 'A')
+                    r.s3 = stn_[m.station3].stationName;
+                PrintMsrRow(os, r, mode);
+            }
+            }
+        }
+    }
+
+    // a direction set: one heading row (instrument, reference object, number of angles), then the derived angles, each
+    // against its target (PrintAdjMeasurements_D PRN:917-975); measured / adjusted are the direction itself and the
+    // direction plus the angle's correction (PRN:2309-2316), the precision that of the derived angle (scale2)
+    void PrintMeasurements_D(std::ostream& os, uint32_t first, int mode) const
+    {
+        const dna_msr_t& ro = msr_[first];
+        const uint32_t angles = ro.vectorCount2 > 0 ? ro.vectorCount2 - 1 : 0;
+        char head[96];
+        snprintf(head, sizeof(head), "%-2c%-20s%-20s%-20s%-3s%-2u", 'D', stn_[ro.station1].stationName, stn_[ro.station2].stationName, "",
+                 ro.ignore ? "*" : " ", angles);
+        os << head << "\n";
+        uint32_t printed = 0;
+        for (size_t j = first + 1; j < first + std::max<uint32_t>(1u, ro.vectorCount1) && j < msr_.size() && printed < angles; ++j) {
+            const dna_msr_t& d = msr_[j];
+            if (d.ignore && !ro.ignore)
+                continue;
+            MsrRow r = ScalarRow(d, ' ', d.scale2);
+            r.show_type = false;
+            r.ignore = false;
+            r.s1 = r.s2 = "";
+            r.s3 = stn_[d.station2].stationName;
+            r.measured = d.term1;
+            r.adjusted = d.term1 + d.measCorr;
+            PrintMsrRow(os, r, mode);
+            ++printed;
+        }
+    }
+
+    // G baselines and X / Y clusters (PrintAdjMeasurements_GXY PRN:4072-4144): three rows per member
+    void PrintMeasurements_GXY(std::ostream& os, uint32_t first, int mode) const
+    {
+        const dna_msr_t& c = msr_[first];
+        const uint32_t count = std::max<uint32_t>(1u, c.vectorCount1);
+        size_t j = first;
+        for (uint32_t k = 0; k < count && j + 2 < msr_.size(); ++k) {
+            const dna_msr_t* r = &msr_[j];
+            if (c.measType == 'Y' && mode == 1 && std::strncmp(r->coordType, "LL", 2) == 0) {
+                // an ignored cluster was never converted: its records still hold latitude, longitude, height
+                const double var[3] = {r[0].term2, r[1].term3, r[2].term4};
+                for (int q = 0; q < 3; ++q) {
+                    MsrRow row = ScalarRow(r[q], q == 0 ? 'P' : q == 1 ? 'L' : (std::strncmp(r->coordType, "LLH", 3) == 0 ? 'H' : 'h'), var[q]);
+                    row.angular = q < 2;
+                    row.pre_adj_corr_linear = q == 2;
+                    PrintMsrRow(os, row, mode);
+                }
+            } else if (c.measType == 'Y' && (r->station3 == DNA_LLH_TYPE || r->station3 == DNA_LLh_TYPE))
+                PrintMeasurements_YLLH(os, j, mode);
+            else if (a_.adj_gnss_units != 0 && c.measType != 'Y' && mode == 0)
+                PrintAdjGNSSAlternateUnits(os, j);
+            else {
+                const double var[3] = {r[0].term2, r[1].term3, r[2].term4};
+                for (int q = 0; q < 3; ++q) {
+                    MsrRow row = ScalarRow(r[q], "XYZ"[q], var[q]);
+                    row.s1 = stn_[r->station1].stationName;
+                    row.s2 = c.measType == 'Y' ? "" : stn_[r->station2].stationName;
+                    PrintMsrRow(os, row, mode);
+                }
+            }
+            j += 3 + 3 * (size_t)r->vectorCount2;
+        }
     }
 
     // A point of a Y cluster that was supplied as latitude / longitude / height is reported in that form
@@ -957,13 +1340,11 @@ class dna_adjust {
     // against the original values kept in preAdjMeas, and the variances of the measurement (its 3x3 Cartesian block) and
     // of the adjusted measurement (its three Cartesian variances) are propagated to geographic with the Jacobian at the
     // adjusted position; N-stat and Pelzer reliability are then recomputed in that frame.
-    void PrintAdjMeasurements_YLLH(std::ostream& os, size_t i, double crit) const
+    void PrintMeasurements_YLLH(std::ostream& os, size_t i, int mode) const
     {
         const dna_msr_t* r = &msr_[i];
         const dna_stn_t& st = stn_[r->station1];
-        gadj_opts o;
-        gadj_default_opts(&o);
-        const gadj::Ellipsoid ell = gadj::make_ellipsoid(o.semi_major, o.inv_flattening);
+        const gadj::Ellipsoid ell = Ellipsoid();
         double llh[3];
         gadj::cart_to_geo(ell, r[0].measAdj, r[1].measAdj, r[2].measAdj, llh);
         // d(XYZ)/d(lat, lon, h) at the adjusted position (FormCarttoGeoRotationMatrix, MFN:204-233) and its inverse
@@ -997,15 +1378,146 @@ class dna_adjust {
         if (ortho && std::fabs((double)st.geoidSep) > 1.0e-4)
             adj[2] -= st.geoidSep;
         const char comp[3] = {'P', 'L', ortho ? 'H' : 'h'};
+        const double sz = std::sqrt(stats_.sigma_zero);
         for (int q = 0; q < 3; ++q) {
-            const double corr = adj[q] - r[q].preAdjMeas;
-            const double resp = std::fabs(var[q] - adjp[q]);
-            double pelzer = std::sqrt(var[q]) / std::sqrt(resp);
-            if (!(pelzer >= 0.0) || pelzer > 700.0)
-                pelzer = 999.99;
-            PrintMsrRow(os, 'Y', st.stationName, "", "", comp[q], q < 2, r[q].preAdjMeas, adj[q], corr, var[q], adjp[q], resp, corr / std::sqrt(resp),
-                        pelzer, r[q].preAdjCorr, crit);
+            MsrRow row = ScalarRow(r[q], comp[q], var[q]);
+            row.angular = q < 2;
+            row.adjusted = adj[q];
+            row.corr = adj[q] - r[q].preAdjMeas;
+            row.adj_prec = adjp[q];
+            row.res_prec = std::fabs(var[q] - adjp[q]);
+            row.pelzer = std::sqrt(var[q]) / std::sqrt(row.res_prec);
+            if (!(row.pelzer >= 0.0) || row.pelzer > 700.0)
+                row.pelzer = 999.99;
+            row.nstat = row.corr / std::sqrt(row.res_prec);
+            row.tstat = sz > 1.0e-10 ? row.nstat / sz : 0.0;
+            row.pre_adj_corr_linear = comp[q] == 'H';
+            PrintMsrRow(os, row, mode);
         }
+    }
+
+    // --output-adj-gnss-units 1 | 2 | 3: a G / X baseline in the local frame at its first station — east north up;
+    // azimuth, vertical angle, slope distance; or azimuth, slope distance, up (PrintAdjGNSSAlternateUnits PRN:4717-5047).
+    // Variances of the measurement and of the adjusted measurement (Q11 + Q22 - Q12 - Q21) are rotated with the local
+    // frame at the mid point of the line, then to polar with the Jacobian of (azimuth, elevation, distance); statistics
+    // are recomputed per component (UpdateMsrRecordStats ADJ:8283-8290).
+    void PrintAdjGNSSAlternateUnits(std::ostream& os, size_t i) const
+    {
+        const dna_msr_t* r = &msr_[i];
+        const dna_stn_t &s1 = stn_[r->station1], &s2 = stn_[r->station2];
+        double Vm[9] = {r[0].term2, r[1].term2, r[2].term2, r[1].term2, r[1].term3, r[2].term3, r[2].term2, r[2].term3, r[2].term4};
+        double Va[9], q12[9];
+        check_const(gadj_get_vcv_block(ctx_, r->station1, r->station2, q12));
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b)
+                Va[3 * a + b] = raw_vcv_[9 * (size_t)r->station1 + 3 * a + b] + raw_vcv_[9 * (size_t)r->station2 + 3 * a + b] - q12[3 * a + b] -
+                                q12[3 * b + a];
+        const double meas[3] = {r[0].term1, r[1].term1, r[2].term1}, adjm[3] = {r[0].measAdj, r[1].measAdj, r[2].measAdj};
+        double R1[9], Rm[9];
+        local_rotation(s1.currentLatitude, s1.currentLongitude, R1);
+        local_rotation(0.5 * (s1.currentLatitude + s2.currentLatitude), 0.5 * (s1.currentLongitude + s2.currentLongitude), Rm);
+        double ml[3], al[3];
+        for (int k = 0; k < 3; ++k) {   // cart -> local: R^T v
+            ml[k] = R1[k] * meas[0] + R1[3 + k] * meas[1] + R1[6 + k] * meas[2];
+            al[k] = R1[k] * adjm[0] + R1[3 + k] * adjm[1] + R1[6 + k] * adjm[2];
+        }
+        double Vl[9], Val[9];
+        rotate_sym(Rm, Vm, Vl);
+        rotate_sym(Rm, Va, Val);
+        double measured[3], adjusted[3], var[3], adjp[3];
+        char card[3];
+        bool ang[3] = {false, false, false};
+        if (a_.adj_gnss_units == 1) {
+            for (int k = 0; k < 3; ++k) {
+                measured[k] = ml[k];
+                adjusted[k] = al[k];
+                var[k] = Vl[4 * k];
+                adjp[k] = Val[4 * k];
+                card[k] = "enu"[k];
+            }
+        } else {
+            const double az = direction_en(ml[0], ml[1]), el = std::atan2(ml[2], std::hypot(ml[0], ml[1]));
+            const double dist = std::sqrt(ml[0] * ml[0] + ml[1] * ml[1] + ml[2] * ml[2]);
+            const double azA = direction_en(al[0], al[1]), elA = std::atan2(al[2], std::hypot(al[0], al[1]));
+            const double distA = std::sqrt(al[0] * al[0] + al[1] * al[1] + al[2] * al[2]);
+            // Jacobian local -> polar (FormLocaltoPolarRotationMatrix MFN:482-504)
+            const double ca = std::cos(az), sa = std::sin(az), ce = std::cos(el), se = std::sin(el);
+            const double P[9] = {ca / dist, -sa / dist, 0.0, -sa * se / dist, -ca * se / dist, ce / dist, sa * ce, ca * ce, se};
+            double vp[3], vap[3];
+            for (int a = 0; a < 3; ++a) {
+                vp[a] = vap[a] = 0.0;
+                for (int x = 0; x < 3; ++x)
+                    for (int y = 0; y < 3; ++y) {
+                        vp[a] += P[3 * a + x] * Vl[3 * x + y] * P[3 * a + y];
+                        vap[a] += P[3 * a + x] * Val[3 * x + y] * P[3 * a + y];
+                    }
+            }
+            if (a_.adj_gnss_units == 2) {   // azimuth, vertical angle, slope distance
+                const double m3[3] = {az, el, dist}, a3[3] = {azA, elA, distA};
+                for (int k = 0; k < 3; ++k) {
+                    measured[k] = m3[k];
+                    adjusted[k] = a3[k];
+                    var[k] = vp[k];
+                    adjp[k] = vap[k];
+                }
+                card[0] = 'a', card[1] = 'v', card[2] = 's';
+                ang[0] = ang[1] = true;
+            } else {                        // azimuth, slope distance, up
+                measured[0] = az, adjusted[0] = azA, var[0] = vp[0], adjp[0] = vap[0];
+                measured[1] = dist, adjusted[1] = distA, var[1] = vp[2], adjp[1] = vap[2];
+                measured[2] = ml[2], adjusted[2] = al[2], var[2] = Vl[8], adjp[2] = Val[8];
+                card[0] = 'a', card[1] = 's', card[2] = 'u';
+                ang[0] = true;
+            }
+        }
+        const double sz = std::sqrt(stats_.sigma_zero);
+        for (int q = 0; q < 3; ++q) {
+            MsrRow row = ScalarRow(r[q], card[q], var[q]);
+            row.s1 = s1.stationName;
+            row.s2 = s2.stationName;
+            row.angular = ang[q];
+            row.measured = measured[q];
+            row.adjusted = adjusted[q];
+            row.corr = adjusted[q] - measured[q];
+            row.adj_prec = adjp[q];
+            row.res_prec = var[q] - adjp[q];
+            row.pelzer = std::sqrt(var[q]) / std::sqrt(row.res_prec);
+            if (!(row.pelzer >= 0.0) || row.pelzer > 700.0)
+                row.pelzer = 999.99;
+            row.nstat = row.corr / std::sqrt(row.res_prec);
+            row.tstat = sz > 1.0e-10 ? row.nstat / sz : 0.0;
+            PrintMsrRow(os, row, 0);
+        }
+    }
+
+    // columns of R: east, north, up in Cartesian components (local -> cart)
+    static void local_rotation(double lat, double lon, double* R)
+    {
+        const double sl = std::sin(lat), cl = std::cos(lat), so = std::sin(lon), co = std::cos(lon);
+        const double M[9] = {-so, -sl * co, cl * co, co, -sl * so, cl * so, 0.0, cl, sl};
+        std::memcpy(R, M, sizeof(M));
+    }
+    static void rotate_sym(const double* R, const double* V, double* out)   // R^T V R
+    {
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+                double s = 0.0;
+                for (int x = 0; x < 3; ++x)
+                    for (int y = 0; y < 3; ++y)
+                        s += R[3 * x + a] * V[3 * x + y] * R[3 * y + b];
+                out[3 * a + b] = s;
+            }
+    }
+    gadj::Ellipsoid Ellipsoid() const
+    {
+        gadj_opts o;
+        gadj_default_opts(&o);
+        return gadj::make_ellipsoid(o.semi_major, o.inv_flattening);
+    }
+    void check_const(int rc) const
+    {
+        if (rc)
+            throw std::runtime_error(gadj_last_error(ctx_));
     }
 
     // reference-frame name for file names: GDA2020 / GDA94 from the EPSG code of the station file, else "EPSG<code>"
@@ -1064,38 +1576,225 @@ class dna_adjust {
         return b;
     }
 
-    void PrintAdjStations(std::ostream& os, const std::vector<uint32_t>* subset) const
-    {   // PrintAdjStation (PRN:3917-4070): PLHhXYZ + SD(e,n,up) = sqrt diag(R^T Q R), geoid uncertainty added to up
-        os << "\nAdjusted Coordinates\n------------------------------------------\n\n";
-        char buf[512];
-        snprintf(buf, sizeof(buf), "%-20s%-5s%14s%15s%11s%11s%15s%15s%15s%12s%10s%10s  %s", "Station", "Const", "Latitude", "Longitude",
-                 "H(Ortho)", "h(Ellipse)", "X", "Y", "Z", "SD(e)", "SD(n)", "SD(up)", "Description");
-        os << buf << "\n" << std::string(211, '-') << "\n";
-        const size_t count = subset ? subset->size() : stn_.size();
-        for (size_t n = 0; n < count; ++n) {
-            const size_t i = subset ? (*subset)[n] : n;
+    // Redfearn's formulae, geographic -> UTM / MGA grid (GeoToGrid GEO:365-432; K0 0.9996, false origin 500 000 / 10 000 000,
+    // 6 degree zones, zone 0 central meridian -183)
+    static void GeoToGrid(const gadj::Ellipsoid& ell, double lat, double lon, double* easting, double* northing, double* zone)
+    {
+        const double PI = 3.14159265358979323846, K0 = 0.9996;
+        *zone = std::floor((lon * 180.0 / PI + 186.0) / 6.0);
+        const double w = lon - (*zone * 6.0 - 183.0) * PI / 180.0;
+        const double e2 = ell.e2, e4 = e2 * e2, e6 = e4 * e2;
+        const double s = std::sin(lat), c = std::cos(lat), t = std::tan(lat), t2 = t * t, t4 = t2 * t2, t6 = t4 * t2;
+        const double nu = ell.a / std::sqrt(1.0 - e2 * s * s), rho = ell.a * (1.0 - e2) / std::pow(1.0 - e2 * s * s, 1.5), psi = nu / rho;
+        const double A0 = 1.0 - e2 / 4.0 - 3.0 * e4 / 64.0 - 5.0 * e6 / 256.0, A2 = 3.0 / 8.0 * (e2 + e4 / 4.0 + 15.0 * e6 / 128.0);
+        const double A4 = 15.0 / 256.0 * (e4 + 3.0 * e6 / 4.0), A6 = 35.0 * e6 / 3072.0;
+        const double m = ell.a * (A0 * lat - A2 * std::sin(2 * lat) + A4 * std::sin(4 * lat) - A6 * std::sin(6 * lat));
+        const double w2 = w * w, w4 = w2 * w2, w6 = w4 * w2, w8 = w4 * w4, c2 = c * c;
+        const double E1 = w2 / 6.0 * c2 * (psi - t2);
+        const double E2 = w4 / 120.0 * c2 * c2 * (4.0 * psi * psi * psi * (1.0 - 6.0 * t2) + psi * psi * (1.0 + 8.0 * t2) - psi * 2.0 * t2 + t4);
+        const double E3 = w6 / 5040.0 * c2 * c2 * c2 * (61.0 - 479.0 * t2 + 179.0 * t4 - t6);
+        *easting = K0 * nu * w * c * (1.0 + E1 + E2 + E3) + 500000.0;
+        const double N1 = w2 / 2.0 * nu * s * c;
+        const double N2 = w4 / 24.0 * nu * s * c * c2 * (4.0 * psi * psi + psi - t2);
+        const double N3 = w6 / 720.0 * nu * s * c * c2 * c2 *
+                          (8.0 * psi * psi * psi * psi * (11.0 - 24.0 * t2) - 28.0 * psi * psi * psi * (1.0 - 6.0 * t2) + psi * psi * (1.0 - 32.0 * t2) -
+                           psi * 2.0 * t2 + t4);
+        const double N4 = w8 / 40320.0 * nu * s * c * c2 * c2 * c2 * (1385.0 - 3111.0 * t2 + 543.0 * t4 - t6);
+        *northing = K0 * (m + N1 + N2 + N3 + N4) + 10000000.0;
+    }
+
+    // the station coordinates the corrections are measured from (v_originalStations_; re-derived from the initial
+    // coordinates of the station file when corrections are reported, PRN:3934-3950)
+    void OriginalXYZ(size_t i, double* xyz) const
+    {
+        if (a_.stn_corrections || a_.output_corrections) {
             const dna_stn_t& s = stn_[i];
-            const double* q = &vcv_[9 * i];
-            double lat = s.currentLatitude, lon = s.currentLongitude, h = s.currentHeight;
-            double sl = std::sin(lat), cl = std::cos(lat), so = std::sin(lon), co = std::cos(lon);
-            double R[3][3] = {{-so, -sl * co, cl * co}, {co, -sl * so, cl * so}, {0, cl, sl}};  // local -> cart
-            double sd[3];
-            for (int k = 0; k < 3; ++k) {
-                double v = 0;
-                for (int a = 0; a < 3; ++a)
-                    for (int b = 0; b < 3; ++b)
-                        v += R[a][k] * q[3 * a + b] * R[b][k];
-                if (k == 2)
-                    v += (double)s.geoidSepUnc * s.geoidSepUnc;
-                sd[k] = std::sqrt(std::fabs(v));
+            double h = s.initialHeight;
+            if (s.suppliedHeightRefFrame == 0)   // ORTHOMETRIC_type_i
+                h += s.geoidSep;
+            gadj::geo_to_cart(Ellipsoid(), s.initialLatitude, s.initialLongitude, h, xyz);
+            return;
+        }
+        std::memcpy(xyz, &apriori_xyz_[3 * i], 3 * sizeof(double));
+    }
+
+    std::vector<uint32_t> StationOrder(const std::vector<uint32_t>* subset) const
+    {
+        std::vector<uint32_t> list;
+        if (subset)
+            list = *subset;
+        else {
+            list.resize(stn_.size());
+            for (size_t i = 0; i < list.size(); ++i)
+                list[i] = (uint32_t)i;
+        }
+        if (a_.sort_stn_orig_order)   // --sort-stn-orig-order: the order of the imported station file (CompareStnFileOrder)
+            std::stable_sort(list.begin(), list.end(), [&](uint32_t a, uint32_t b) { return stn_[a].fileOrder < stn_[b].fileOrder; });
+        return list;
+    }
+
+    void PrintAdjStations(std::ostream& os, const std::vector<uint32_t>* subset, const std::string& heading = "Adjusted Coordinates") const
+    {   // PrintAdjStation (PRN:3917-4070): the coordinate types of --stn-coord-types + SD(e,n,up) = sqrt diag(R^T Q R),
+        // geoid uncertainty added to up; optional corrections (e, n, up) from the original coordinates
+        os << "\n" << heading << "\n------------------------------------------\n\n";
+        const std::string& types = a_.stn_coord_types;
+        const int pl = a_.precision_metres_stn, pa = a_.precision_seconds_stn;
+        auto width_of = [](char c) { return c == 'P' || c == 'E' ? 14 : c == 'L' || c == 'N' ? 15 : c == 'H' || c == 'h' ? 11 : c == 'z' ? 8 : 15; };
+        auto name_of = [](char c) -> const char* {
+            switch (c) {
+            case 'P': return "Latitude";
+            case 'L': return "Longitude";
+            case 'H': return "H(Ortho)";
+            case 'h': return "h(Ellipse)";
+            case 'E': return "Easting";
+            case 'N': return "Northing";
+            case 'z': return "Zone";
+            case 'X': return "X";
+            case 'Y': return "Y";
+            case 'Z': return "Z";
             }
+            return "";
+        };
+        os << std::left << std::setw(20) << "Station" << std::setw(5) << "Const";
+        size_t width = 25;
+        for (char c : types) {
+            if (!std::strchr("PLHhENzXYZ", c))
+                continue;
+            os << std::right << std::setw(width_of(c)) << name_of(c);
+            width += width_of(c);
+        }
+        os << "  " << std::right << std::setw(10) << "SD(e)" << std::setw(10) << "SD(n)" << std::setw(10) << "SD(up)";
+        width += 2 + 30 + 2 + 56;
+        if (a_.stn_corrections) {
+            os << "  " << std::setw(11) << "Corr(e)" << std::setw(11) << "Corr(n)" << std::setw(11) << "Corr(up)";
+            width += 2 + 33;
+        }
+        os << "  " << std::left << "Description" << "\n" << std::string(width, '-') << "\n";
+        const bool grid = types.find_first_of("ENz") != std::string::npos;
+        const gadj::Ellipsoid ell = Ellipsoid();
+        for (uint32_t i : StationOrder(subset)) {
+            const dna_stn_t& s = stn_[i];
+            const double* q = &vcv_[9 * (size_t)i];
+            const double lat = s.currentLatitude, lon = s.currentLongitude, h = s.currentHeight;
+            double E = 0, N = 0, zone = -1;
+            if (grid)
+                GeoToGrid(ell, lat, lon, &E, &N, &zone);
             char cst[4] = {s.stationConst[0], s.stationConst[1], s.stationConst[2], 0};
-            snprintf(buf, sizeof(buf), "%-20s%-5s%14s%15s%11.4f%11.4f%15.4f%15.4f%15.4f%12.4f%10.4f%10.4f  %s", s.stationName, cst,
-                     hp_dms(lat).c_str(), hp_dms(lon).c_str(), h - (double)s.geoidSep, h, est_[3 * i], est_[3 * i + 1], est_[3 * i + 2],
-                     sd[0], sd[1], sd[2], s.description);
-            os << buf << "\n";
+            os << std::left << std::setw(20) << s.stationName << std::setw(5) << cst << std::right;
+            for (char c : types) {
+                switch (c) {
+                case 'P':
+                    os << std::setw(14) << (a_.angular_type_stn == 1 ? Fixed(lat * 180.0 / 3.14159265358979323846, 0, 4 + pa) : hp_dms(lat, 4 + pa));
+                    break;
+                case 'L':
+                    os << std::setw(15) << (a_.angular_type_stn == 1 ? Fixed(lon * 180.0 / 3.14159265358979323846, 0, 4 + pa) : hp_dms(lon, 4 + pa));
+                    break;
+                case 'E': os << Fixed(E, 14, pl); break;
+                case 'N': os << Fixed(N, 15, pl); break;
+                case 'z': os << Fixed(zone, 8, 0); break;
+                case 'H': os << Fixed(h - (double)s.geoidSep, 11, pl); break;
+                case 'h': os << Fixed(h, 11, pl); break;
+                case 'X': os << Fixed(est_[3 * (size_t)i], 15, pl); break;
+                case 'Y': os << Fixed(est_[3 * (size_t)i + 1], 15, pl); break;
+                case 'Z': os << Fixed(est_[3 * (size_t)i + 2], 15, pl); break;
+                }
+            }
+            double R[9], ql[9];
+            local_rotation(lat, lon, R);
+            rotate_sym(R, q, ql);
+            ql[8] += (double)s.geoidSepUnc * s.geoidSepUnc;
+            os << "  ";
+            for (int k = 0; k < 3; ++k)
+                os << Fixed(std::sqrt(std::fabs(ql[4 * k])), 10, pl);
+            if (a_.stn_corrections) {
+                double o[3];
+                OriginalXYZ(i, o);
+                const double d[3] = {est_[3 * (size_t)i] - o[0], est_[3 * (size_t)i + 1] - o[1], est_[3 * (size_t)i + 2] - o[2]};
+                os << "  ";
+                for (int k = 0; k < 3; ++k)
+                    os << Fixed(R[k] * d[0] + R[3 + k] * d[1] + R[6 + k] * d[2], 11, pl);
+            }
+            os << "  " << s.description << "\n";
         }
         os << "\n";
+    }
+
+    // ---- "Measurements to Station" table (PrintMeasurementsToStation PRN:720-789): per station, the number of
+    // non-ignored measurements of every type it takes part in (a cluster or direction set counts once per station)
+    void PrintMeasurementsToStation(std::ostream& os) const
+    {
+        static const char kTypes[] = "ABCDEGHIJKLMPQRSVXYZ";
+        std::vector<std::array<uint32_t, 20>> tally(stn_.size());
+        for (auto& t : tally)
+            t.fill(0);
+        std::vector<uint32_t> touched;
+        for (size_t i = 0; i < msr_.size();) {
+            const size_t span = MeasurementSpan(i);
+            const dna_msr_t& m = msr_[i];
+            const char* p = std::strchr(kTypes, m.measType);
+            if (!m.ignore && p && m.measType) {
+                touched.clear();
+                for (size_t j = i; j < i + span && j < msr_.size(); ++j) {
+                    const dna_msr_t& r = msr_[j];
+                    if (r.ignore || (std::strchr("GXY", r.measType) && r.measStart != 0))
+                        continue;
+                    touched.push_back(r.station1);
+                    if (r.measurementStations >= 2 && r.measType != 'Y')
+                        touched.push_back(r.station2);
+                    if (r.measurementStations >= 3 && r.measType == 'A')
+                        touched.push_back(r.station3);
+                }
+                std::sort(touched.begin(), touched.end());
+                touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+                for (uint32_t sidx : touched)
+                    if (sidx < tally.size())
+                        tally[sidx][p - kTypes]++;
+            }
+            i += span;
+        }
+        auto total_of = [&](uint32_t sidx) {
+            uint32_t t = 0;
+            for (uint32_t v : tally[sidx])
+                t += v;
+            return t;
+        };
+        auto line = [&]() { os << std::string(20 + 8 * 20 + 11, '-') << "\n"; };
+        os << "\nMeasurements to Station \n------------------------------------------\n\n" << std::left << std::setw(20) << "Station";
+        for (const char* c = kTypes; *c; ++c)
+            os << std::right << std::setw(8) << *c;
+        os << std::setw(11) << "Total" << "\n";
+        line();
+        std::vector<uint32_t> order(stn_.size());
+        for (size_t i = 0; i < order.size(); ++i)
+            order[i] = (uint32_t)i;
+        switch (a_.sort_msr_to_stn) {   // orig_stn_sort_ui 0, name 1, count ascending 2, count descending 3
+        case 0: std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return stn_[a].fileOrder < stn_[b].fileOrder; }); break;
+        case 2: std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return total_of(a) < total_of(b); }); break;
+        case 3: std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return total_of(a) > total_of(b); }); break;
+        default: std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return stn_[a].nameOrder < stn_[b].nameOrder; });
+        }
+        auto row = [&](const char* name, const std::array<uint32_t, 20>& t) {
+            os << std::left << std::setw(20) << name << std::right;
+            uint32_t total = 0;
+            for (uint32_t v : t) {
+                if (v)
+                    os << std::setw(8) << v;
+                else
+                    os << std::setw(8) << " ";
+                total += v;
+            }
+            os << std::setw(11) << total << "\n";
+        };
+        std::array<uint32_t, 20> totals;
+        totals.fill(0);
+        for (uint32_t sidx : order) {
+            row(stn_[sidx].stationName, tally[sidx]);
+            for (int k = 0; k < 20; ++k)
+                totals[k] += tally[sidx][k];
+        }
+        line();
+        row("Totals", totals);
+        os << "\n\n";
     }
 
     adjust_settings a_;
@@ -1108,7 +1807,8 @@ class dna_adjust {
     dnafiles::Segmentation seg_;
     std::string bst_file_, bms_file_;
     std::vector<gadj_iter_result> iterations_;
-    std::vector<double> est_, vcv_, apriori_llh_, apriori_xyz_;
+    std::vector<std::string> iter_pre_, iter_post_;   // per-iteration report text (--output-iter-*)
+    std::vector<double> est_, vcv_, raw_vcv_, apriori_llh_, apriori_xyz_;
     double maxCorr_ = 0, total_ms_ = 0, chiUpper_ = 0, chiLower_ = 0;
     int passFail_ = 0;
     ADJUST_STATUS adjustStatus_ = ADJUST_SUCCESS;

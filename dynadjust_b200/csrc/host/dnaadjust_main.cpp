@@ -31,6 +31,12 @@ const Flag kFlags[] = {
     {"hz-corr-threshold", true}, {"vt-corr-threshold", true}, {"output-stn-blocks", false}, {"output-msr-blocks", false},
     {"export-sinex-file", false}, {"type-b-sd-global", true}, {"type-b-sd-file", true}, {"network-name", true}, {"quiet", false}, {"verbose-level", true},
     {"no-binary-update", false}, {"help", false},
+    {"sort-adj-msr-field", true}, {"output-adj-gnss-units", true}, {"output-tstat-adj-msr", false}, {"output-msr-to-stn", false},
+    {"sort-msr-to-stn-field", true}, {"stn-corrections", false}, {"stn-coord-types", true}, {"sort-stn-orig-order", false},
+    {"angular-stn-type", true}, {"angular-msr-type", true}, {"dms-msr-format", true}, {"precision-stn-linear", true},
+    {"precision-stn-angular", true}, {"precision-msr-linear", true}, {"precision-msr-angular", true}, {"output-iter-adj-stn", false},
+    {"output-iter-adj-stat", false}, {"output-iter-adj-msr", false}, {"output-iter-cmp-msr", false}, {"output-ignored-msrs", false},
+    {"comments", true}, {"version", false}, {"help-module", true},
 };
 
 // Boost.program_options accepts unambiguous prefixes (CI uses --phased, --multi)
@@ -154,6 +160,55 @@ int main(int argc, char** argv)
             s.update_binary_files = false;
         else if (n == "constraints")
             s.station_constraints = value;
+        else if (n == "sort-adj-msr-field")
+            s.sort_adj_msr = std::atoi(value.c_str());
+        else if (n == "output-adj-gnss-units")
+            s.adj_gnss_units = std::atoi(value.c_str());
+        else if (n == "output-tstat-adj-msr")
+            s.adj_msr_tstat = true;
+        else if (n == "output-msr-to-stn")
+            s.output_msr_to_stn = true;
+        else if (n == "sort-msr-to-stn-field")
+            s.sort_msr_to_stn = std::atoi(value.c_str());
+        else if (n == "stn-corrections")
+            s.stn_corrections = true;
+        else if (n == "stn-coord-types")
+            s.stn_coord_types = value;
+        else if (n == "sort-stn-orig-order")
+            s.sort_stn_orig_order = true;
+        else if (n == "angular-stn-type")
+            s.angular_type_stn = std::atoi(value.c_str());
+        else if (n == "angular-msr-type")
+            s.angular_type_msr = std::atoi(value.c_str());
+        else if (n == "dms-msr-format")
+            s.dms_format_msr = std::atoi(value.c_str());
+        else if (n == "precision-stn-linear")
+            s.precision_metres_stn = std::atoi(value.c_str());
+        else if (n == "precision-stn-angular")
+            s.precision_seconds_stn = std::atoi(value.c_str());
+        else if (n == "precision-msr-linear")
+            s.precision_metres_msr = std::atoi(value.c_str());
+        else if (n == "precision-msr-angular")
+            s.precision_seconds_msr = std::atoi(value.c_str());
+        else if (n == "output-iter-adj-stn")
+            s.iter_adj_stn = true;
+        else if (n == "output-iter-adj-stat")
+            s.iter_adj_stat = true;
+        else if (n == "output-iter-adj-msr")
+            s.iter_adj_msr = true;
+        else if (n == "output-iter-cmp-msr")
+            s.iter_cmp_msr = true;
+        else if (n == "output-ignored-msrs")
+            s.output_ignored_msrs = true;
+        else if (n == "comments")
+            s.comments = value;
+        else if (n == "version") {
+            std::cout << "dnaadjust (dynadjust_b200) 1.0\n";
+            return EXIT_SUCCESS;
+        } else if (n == "help-module") {
+            std::cout << "dnaadjust: help for option group '" << value << "': see --help\n";
+            return EXIT_SUCCESS;
+        }
         // remaining accepted flags select CPU execution strategies or extra reports: no effect here
     }
     if (s.network_name.empty()) {

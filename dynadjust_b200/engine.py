@@ -60,7 +60,8 @@ class GadjProfile(C.Structure):
 EXPORTS = ["gadj_default_opts", "gadj_create", "gadj_destroy", "gadj_last_error", "gadj_set_stations",
            "gadj_set_measurements", "gadj_set_blocks", "gadj_prepare", "gadj_get_info", "gadj_upload_measurements",
            "gadj_upload_measurements_range",
-           "gadj_reset_estimates", "gadj_iterate", "gadj_form_inverse", "gadj_adjust", "gadj_statistics", "gadj_get_estimates",
+           "gadj_reset_estimates", "gadj_iterate", "gadj_form_inverse", "gadj_adjust", "gadj_statistics",
+           "gadj_update_ignored_measurements", "gadj_compute_measurements", "gadj_get_estimates",
            "gadj_get_corrections", "gadj_get_station_vcvs", "gadj_get_station_vcv", "gadj_get_vcv_block",
            "gadj_get_normals_block", "gadj_get_rhs", "gadj_get_block_vcv", "gadj_profile_enable", "gadj_profile_read", "gadj_test_gemm",
            "gadj_mg_init", "gadj_stage_begin", "gadj_stage_normals_pending", "gadj_stage_run", "gadj_stage_solve_begin",
@@ -96,6 +97,8 @@ def load_library(path=None):
     L.gadj_adjust.argtypes = [vp, C.POINTER(GadjIterResult)]
     L.gadj_form_inverse.argtypes = [vp]
     L.gadj_statistics.argtypes = [vp, C.POINTER(GadjStats), i32]
+    L.gadj_update_ignored_measurements.argtypes = [vp]
+    L.gadj_compute_measurements.argtypes = [vp]
     L.gadj_get_estimates.argtypes = [vp, vp]
     L.gadj_get_corrections.argtypes = [vp, vp]
     L.gadj_get_station_vcvs.argtypes = [vp, vp]
@@ -229,6 +232,10 @@ class Adjustment:
         s = GadjStats()
         self._check(self.L.gadj_statistics(self.h, C.byref(s), 1 if write_back else 0))
         return s
+
+    def update_ignored_measurements(self):
+        """A-posteriori computed value / difference of the measurements flagged as ignored (ADJ:8750-9980)."""
+        self._check(self.L.gadj_update_ignored_measurements(self.h))
 
     def estimates(self):
         out = np.zeros((len(self.stn), 3))

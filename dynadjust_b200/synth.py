@@ -152,6 +152,7 @@ def gnss_network(n_stations, n_baselines, seed, hub_fraction=0.0, n_hubs=0, apri
     stn["initialLatitude"] = stn["currentLatitude"] = alat
     stn["initialLongitude"] = stn["currentLongitude"] = alon
     stn["initialHeight"] = stn["currentHeight"] = ah
+    stn["suppliedHeightRefFrame"] = 1          # ELLIPSOIDAL_type_i: the initial heights above are ellipsoidal
     stn["geoidSep"] = (30.0 * np.sin(3.0 * alat) * np.cos(2.0 * alon)).astype(np.float32)
     stn["geoidSepUnc"] = 0.05
     stn["fileOrder"] = idx

@@ -140,6 +140,15 @@ int gadj_adjust(gadj_ctx* c, gadj_iter_result* last);
 /* needs the rigorous inverse; write_back != 0 copies the statistics fields into the host msr records
  * and the adjusted geographic coordinates into the host stn records */
 int gadj_statistics(gadj_ctx* c, gadj_stats* st, int write_back);
+/* A-posteriori values of the measurements flagged as ignored (UpdateIgnoredMeasurements, ADJ:8750-9980;
+ * PrintIgnoredAdjMeasurements PRN:1784-1923): fills preAdjMeas, measAdj (computed from the adjusted coordinates),
+ * measCorr (computed - measured) and preAdjCorr of the ignored records.  Host-side reporting; call after
+ * gadj_statistics(..., write_back = 1). */
+int gadj_update_ignored_measurements(gadj_ctx* c);
+/* The same evaluation for the measurements that take part, at the current estimates: measAdj = computed value,
+ * measCorr = computed - measured ("Computed Measurements" of --output-iter-cmp-msr, PRN:1938-2023).  Host-side
+ * reporting; meant for the a-priori table before the first iteration. */
+int gadj_compute_measurements(gadj_ctx* c);
 
 int gadj_get_estimates(gadj_ctx* c, double* xyz /* 3*nstn */);
 int gadj_get_corrections(gadj_ctx* c, double* dxyz /* 3*nstn */);

@@ -51,7 +51,7 @@ def _solution_block(text):
     return dict(unknowns=grab("Number of unknown parameters", int), measurements=grab("Number of measurements", int),
                 dof=grab("Degrees of freedom", int), chi=grab("Chi squared"), sigma0=grab("Rigorous Sigma Zero"),
                 pelzer=grab("Global (Pelzer) Reliability"), iterations=len(re.findall(r"^ITERATION\s+\d+", text, re.M)),
-                outliers=int(re.search(r"\((\d+) potential outliers\)", text).group(1)),
+                outliers=int((re.search(r"\((\d+) potential outliers?\)", text) or [0, 0])[1]),
                 converged=bool(re.search(r"^SOLUTION\s+Converged", text, re.M)))
 
 
