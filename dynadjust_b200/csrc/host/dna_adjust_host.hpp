@@ -36,6 +36,8 @@ struct adjust_settings {            // the fields of project_settings.a / .g / .
     std::string network_name;
     std::string input_folder = ".", output_folder = ".";
     int adjust_mode = SimultaneousMode;
+    bool stage = false, multi_thread = false;    // --staged-adjustment / --multi-thread: phased; they name the outputs (WRAP:687-704)
+    std::string bst_file, bms_file, seg_file;    // --binary-stn-file / --binary-msr-file / --seg-file: override the network name
     double iteration_threshold = (double)0.0005f;   // float in the reference (dnaoptions.hpp:432)
     uint32_t max_iterations = 10;
     double free_std_dev = 10.0, fixed_std_dev = 1.0e-6, confidence_interval = 95.0;
@@ -45,8 +47,10 @@ struct adjust_settings {            // the fields of project_settings.a / .g / .
     bool output_msr_blocks = false;        // --output-msr-blocks: likewise the adjusted measurements
     bool output_pos_uncertainty = false;   // --output-pos-uncertainty: <net>.<mode>.apu
     bool output_corrections = false;       // --output-corrections-file: <net>.<mode>.cor
+    bool export_xml_stn = false, export_xml_msr = false, export_dna_stn = false, export_dna_msr = false;   // --export-xml-stn-file ... (WRAP:377-447)
     bool export_sinex = false;             // --export-sinex-file: <net>[-block<k>].<frame>.snx with the dense block variance matrix
     bool apu_vcv_enu = false;              // --output-apu-vcv-units ENU (default XYZ)
+    bool output_pu_covariances = false;    // --output-all-covariances: covariance blocks between the stations of a block in the .apu
     double hz_corr_threshold = 0.0, vt_corr_threshold = 0.0;   // dnaoptions.hpp:510
     bool update_binary_files = true;
     std::string type_b_global, type_b_file; // --type-b-sd-global "e,n,up" (metres, 1 sigma), --type-b-sd-file <file> (dnaoptions-interface.hpp)
@@ -81,8 +85,9 @@ class dna_adjust {
     {
         a_ = s;
         const std::string base = a_.input_folder + "/" + a_.network_name;
-        bst_file_ = base + ".bst";
-        bms_file_ = base + ".bms";
+        auto in_folder = [&](const std::string& f) { return f.find('/') == std::string::npos ? a_.input_folder + "/" + f : f; };
+        bst_file_ = a_.bst_file.empty() ? base + ".bst" : in_folder(a_.bst_file);
+        bms_file_ = a_.bms_file.empty() ? base + ".bms" : in_folder(a_.bms_file);
         dnafiles::load_binary(bst_file_, stn_, bst_meta_);
         dnafiles::load_binary(bms_file_, msr_, bms_meta_);
         ApplyConstraints();
@@ -94,10 +99,10 @@ class dna_adjust {
         o.max_iterations = a_.max_iterations;
         o.confidence_interval = a_.confidence_interval;
         o.scale_normals_to_unity = 1;   // internal equilibration is always safe; the flag is accepted for compatibility
-        if (a_.export_sinex && a_.adjust_mode == SimultaneousMode) {
-            // the SINEX file of a simultaneous adjustment carries the full variance matrix (PRN:2944-2946): one dense front
+        if ((a_.export_sinex || a_.export_xml_msr || a_.export_dna_msr || a_.output_pu_covariances) && a_.adjust_mode == SimultaneousMode) {
+            // the SINEX / Y cluster files of a simultaneous adjustment carry the full variance matrix (PRN:2944-2946, 3085-3087): one dense front
             if (stn_.size() > 12000)
-                SignalExceptionAdjustment("--export-sinex-file in simultaneous mode needs the full variance matrix of the network "
+                SignalExceptionAdjustment("--export-sinex-file / --export-*-msr-file / --output-all-covariances in simultaneous mode need the full variance matrix of the network "
                                           "(dense); segment the network (dnasegment) and run --phased-adjustment for per-block files");
             o.ordering = GADJ_ORDER_DENSE;
         }
@@ -106,7 +111,7 @@ class dna_adjust {
         check(gadj_set_stations(ctx_, stn_.data(), (uint32_t)stn_.size()));
         check(gadj_set_measurements(ctx_, msr_.data(), msr_.size()));
         if (a_.adjust_mode != SimultaneousMode) {
-            dnafiles::load_seg(base + ".seg", seg_);
+            dnafiles::load_seg(a_.seg_file.empty() ? base + ".seg" : in_folder(a_.seg_file), seg_);
             std::vector<uint32_t> off{0}, isl;
             for (auto& b : seg_.isl) {
                 isl.insert(isl.end(), b.begin(), b.end());
@@ -213,7 +218,7 @@ class dna_adjust {
     std::string ModeSuffix() const
     {   // output naming (WRAP:659-734)
         switch (a_.adjust_mode) {
-        case PhasedMode: return "phased";
+        case PhasedMode: return a_.stage ? "phased-stage" : (a_.multi_thread ? "phased-mt" : "phased");
         case Phased_Block_1Mode: return "phased-block1";
         default: return "simult";
         }
@@ -245,8 +250,198 @@ class dna_adjust {
             PrintPositionalUncertainty(stem + ".apu");
         if (a_.output_corrections)
             PrintNetworkStationCorrections(stem + ".cor");
+        if (a_.export_xml_stn)
+            PrintEstimatedStationCoordinatestoDNAXML(stem + ".adj.stn.xml", true, stem + ".adj");
+        if (a_.export_xml_msr)
+            PrintEstimatedStationCoordinatestoDNAXML_Y(stem + ".adj.msr.xml", true, stem + ".adj");
+        if (a_.export_dna_stn)
+            PrintEstimatedStationCoordinatestoDNAXML(stem + ".adj.stn", false, stem + ".adj");
+        if (a_.export_dna_msr)
+            PrintEstimatedStationCoordinatestoDNAXML_Y(stem + ".adj.msr", false, stem + ".adj");
         if (a_.export_sinex)
             PrintEstimatedStationCoordinatestoSNX();
+    }
+
+    // ---- DNA / DynaML exports of the adjusted stations (PrintEstimatedStationCoordinatestoDNAXML PRN:2775-2903;
+    // WriteDNAStn / WriteDynaMLStn dnastation.cpp:825-886): <adj file>.stn and <adj file>.stn.xml, stations in the order
+    // of the imported file, coordinates in the form they were supplied in (LLH / UTM: orthometric height)
+    static std::string today_ddmmyyyy()
+    {
+        std::time_t t = std::time(nullptr);
+        std::tm tmv;
+        localtime_r(&t, &tmv);
+        char b[32];
+        std::strftime(b, sizeof(b), "%d.%m.%Y", &tmv);
+        return b;
+    }
+    void dna_header(std::ostream& os, const char* type, size_t count) const
+    {   // dnastringfuncs.cpp:230-258
+        os << "!#=DNA 3.01 " << type << std::setw(14) << std::right << today_ddmmyyyy() << std::setw(14) << frame_name() << std::setw(14)
+           << bst_meta_.epoch << std::setw(10) << count << "\n"
+           << "* Created by:   dnaadjust (dynadjust_b200), B200 geodetic adjustment. \n* Version:      1.0. \n";
+    }
+    void dynaml_header(std::ostream& os, const char* type) const
+    {   // dnastringfuncs.cpp:173-190
+        os << "<?xml version=\"1.0\"?>\n<DnaXmlFormat type=\"" << type << "\" referenceframe=\"" << frame_name() << "\" epoch=\"" << bst_meta_.epoch
+           << "\" xmlns:xsi=\"http://www.w3.org/2001/XMLSchema-instance\" xsi:noNamespaceSchemaLocation=\"DynaML.xsd\">\n"
+           << "<!-- Created by:   dnaadjust (dynadjust_b200), B200 geodetic adjustment -->\n<!-- Version:      1.0 -->\n";
+    }
+    static std::string xml_escape(const char* s)
+    {
+        std::string o;
+        for (; *s; ++s)
+            o += *s == '&' ? "&amp;" : *s == '<' ? "&lt;" : *s == '>' ? "&gt;" : std::string(1, *s);
+        return o;
+    }
+
+    void PrintEstimatedStationCoordinatestoDNAXML(const std::string& file, bool dynaml, const std::string& adj_file) const
+    {
+        std::ofstream os(file);
+        const std::string source = "Source data:  Coordinates estimated from least squares adjustment.";
+        if (dynaml) {
+            dynaml_header(os, "Station File");
+            os << "<!-- File type:    Station file -->\n<!-- Project name: " << a_.network_name << " -->\n<!-- " << source << " -->\n<!-- Adj file:     "
+               << adj_file << " -->\n";
+        } else {
+            dna_header(os, "STN", stn_.size());
+            os << "* File type:    Station file\n* Project name: " << a_.network_name << "\n* " << source << "\n* Adj file:     " << adj_file << "\n";
+        }
+        std::vector<uint32_t> list;
+        if (a_.adjust_mode == Phased_Block_1Mode && !seg_.isl.empty()) {
+            list = seg_.isl[0];
+            if (!seg_.jsl.empty())
+                list.insert(list.end(), seg_.jsl[0].begin(), seg_.jsl[0].end());
+        } else {
+            list.resize(stn_.size());
+            for (size_t i = 0; i < list.size(); ++i)
+                list[i] = (uint32_t)i;
+        }
+        std::stable_sort(list.begin(), list.end(), [&](uint32_t a, uint32_t b) { return stn_[a].fileOrder < stn_[b].fileOrder; });
+        const gadj::Ellipsoid ell = Ellipsoid();
+        for (uint32_t i : list) {
+            const dna_stn_t& s = stn_[i];
+            const char* type = "LLH";
+            double c[3] = {s.currentLatitude, s.currentLongitude, s.currentHeight};
+            std::string zone;
+            int p12 = 4;
+            switch (s.suppliedStationType) {
+            case DNA_XYZ_TYPE:
+                type = "XYZ";
+                gadj::geo_to_cart(ell, s.currentLatitude, s.currentLongitude, s.currentHeight, c);
+                break;
+            case DNA_UTM_TYPE: {
+                type = "UTM";
+                double z;
+                GeoToGrid(ell, s.currentLatitude, s.currentLongitude, &c[0], &c[1], &z);
+                c[2] -= s.geoidSep;
+                zone = std::to_string((int)z);
+                break;
+            }
+            case DNA_LLh_TYPE:
+                type = "LLh";
+                [[fallthrough]];
+            default:   // LLH (and ENU, which the reference writes as LLH)
+                if (s.suppliedStationType != DNA_LLh_TYPE)
+                    c[2] -= s.geoidSep;
+                c[0] = std::atof(hp_dms(s.currentLatitude, 14).c_str());
+                c[1] = std::atof(hp_dms(s.currentLongitude, 14).c_str());
+                p12 = 10;
+            }
+            char cst[4] = {s.stationConst[0], s.stationConst[1], s.stationConst[2], 0};
+            if (dynaml) {
+                os << "  <DnaStation>\n    <Name>" << xml_escape(s.stationName) << "</Name>\n    <Constraints>" << cst << "</Constraints>\n    <Type>" << type
+                   << "</Type>\n    <StationCoord>\n      <Name>" << xml_escape(s.stationName) << "</Name>\n      <XAxis>" << Fixed(c[0], 0, p12)
+                   << "</XAxis>\n      <YAxis>" << Fixed(c[1], 0, p12) << "</YAxis>\n      <Height>" << Fixed(c[2], 0, 4) << "</Height>\n";
+                if (!zone.empty())
+                    os << "      <HemisphereZone>" << zone << "</HemisphereZone>\n";
+                os << "    </StationCoord>\n    <Description>" << xml_escape(s.description) << "</Description>\n  </DnaStation>\n";
+            } else {
+                os << std::left << std::setw(20) << s.stationName << std::setw(3) << cst << " " << std::setw(3) << type << std::right << Fixed(c[0], 20, p12)
+                   << Fixed(c[1], 20, p12) << Fixed(c[2], 20, 4) << std::setw(3) << (zone.empty() ? " " : zone) << " " << s.description << "\n";
+            }
+        }
+        if (dynaml)
+            os << "</DnaXmlFormat>\n";
+    }
+
+    // ---- DNA / DynaML exports of the estimates as GNSS point clusters (PrintEstimatedStationCoordinatestoDNAXML_Y
+    // PRN:3012-3164; CDnaGpsPoint::WriteDNAMsr / WriteDynaMLMsr dnagpspoint.cpp:232-366): one Y cluster per block — the
+    // Cartesian estimates of its stations with the block's full variance matrix — in <adj file>.msr / .msr.xml
+    void PrintEstimatedStationCoordinatestoDNAXML_Y(const std::string& file, bool dynaml, const std::string& adj_file)
+    {
+        std::ofstream os(file);
+        const uint32_t nblocks = (uint32_t)info_.nfronts;
+        std::ostringstream src;
+        src << "Source data:  Coordinates and uncertainties for " << stn_.size() << " unique stations in " << nblocks
+            << " blocks estimated from least squares adjustment.";
+        if (dynaml) {
+            dynaml_header(os, "Measurement File");
+            os << "<!-- File type:    Measurement file -->\n<!-- Project name: " << a_.network_name << " -->\n<!-- " << src.str()
+               << " -->\n<!-- Adj file:     " << adj_file << " -->\n";
+        } else {
+            dna_header(os, "MSR", nblocks);
+            os << "* File type:    Measurement file\n* Project name: " << a_.network_name << "\n* " << src.str() << "\n* Adj file:     " << adj_file << "\n";
+        }
+        const std::string frame = frame_name(), epoch = bst_meta_.epoch;
+        char num[64];
+        auto sci = [&](double v) {
+            snprintf(num, sizeof(num), dynaml ? "%.13e" : "%20.13e", v);
+            return std::string(num);
+        };
+        for (uint32_t b = 0; b < nblocks; ++b) {
+            if (a_.adjust_mode == Phased_Block_1Mode && b > 0)
+                break;
+            uint32_t n = 0;
+            check(gadj_get_block_vcv(ctx_, b, &n, nullptr, 0, nullptr));
+            std::vector<uint32_t> st(n);
+            const size_t dim = 3 * (size_t)n;
+            std::vector<double> q(dim * (dim + 1) / 2);
+            check(gadj_get_block_vcv(ctx_, b, &n, st.data(), n, q.data()));
+            auto at = [&](size_t i, size_t j) { return i >= j ? q[j * dim - j * (j - 1) / 2 + (i - j)] : q[i * dim - i * (i - 1) / 2 + (j - i)]; };
+            if (dynaml) {
+                os << "  <!--\n    - Estimated station coordinates and uncertainties";
+                if (nblocks > 1)
+                    os << " for block " << b + 1;
+                os << "\n    - Type (Y) GPS point cluster (set of " << n << " stations)\n  -->\n";
+                os << "  <DnaMeasurement>\n    <Type>Y</Type>\n    <Source></Source>\n    <Ignore/>\n    <ReferenceFrame>" << frame << "</ReferenceFrame>\n    <Epoch>" << epoch
+                   << "</Epoch>\n    <Vscale>1.000</Vscale>\n    <Pscale>1.000</Pscale>\n    <Lscale>1.000</Lscale>\n    <Hscale>1.000</Hscale>\n    <Coords>XYZ</Coords>\n"
+                   << "    <Total>" << n << "</Total>\n";
+            }
+            for (uint32_t k = 0; k < n; ++k) {
+                const double* x = &est_[3 * (size_t)st[k]];
+                const size_t r = 3 * (size_t)k;
+                if (dynaml) {
+                    os << "    <First>" << xml_escape(stn_[st[k]].stationName) << "</First>\n    <Clusterpoint>\n      <X>" << Fixed(x[0], 0, 4) << "</X>\n      <Y>"
+                       << Fixed(x[1], 0, 4) << "</Y>\n      <Z>" << Fixed(x[2], 0, 4) << "</Z>\n      <SigmaXX>" << sci(at(r, r)) << "</SigmaXX>\n      <SigmaXY>"
+                       << sci(at(r, r + 1)) << "</SigmaXY>\n      <SigmaXZ>" << sci(at(r, r + 2)) << "</SigmaXZ>\n      <SigmaYY>" << sci(at(r + 1, r + 1))
+                       << "</SigmaYY>\n      <SigmaYZ>" << sci(at(r + 1, r + 2)) << "</SigmaYZ>\n      <SigmaZZ>" << sci(at(r + 2, r + 2)) << "</SigmaZZ>\n";
+                    for (uint32_t j = k + 1; j < n; ++j) {
+                        os << "      <PointCovariance>\n";
+                        static const char* tag[9] = {"m11", "m12", "m13", "m21", "m22", "m23", "m31", "m32", "m33"};
+                        for (int a = 0; a < 3; ++a)
+                            for (int c = 0; c < 3; ++c)
+                                os << "        <" << tag[3 * a + c] << ">" << sci(at(r + a, 3 * (size_t)j + c)) << "</" << tag[3 * a + c] << ">\n";
+                        os << "      </PointCovariance>\n";
+                    }
+                    os << "    </Clusterpoint>\n";
+                    continue;
+                }
+                os << "Y " << std::left << std::setw(20) << stn_[st[k]].stationName;
+                if (k == 0)
+                    os << std::setw(20) << "XYZ" << std::setw(20) << n << std::right << Fixed(1.0, 10, 2) << Fixed(1.0, 10, 2) << Fixed(1.0, 10, 2)
+                       << Fixed(1.0, 10, 2) << std::setw(20) << frame << std::setw(20) << epoch;
+                os << "\n" << std::string(62, ' ') << Fixed(x[0], 20, 4) << sci(at(r, r)) << "\n"
+                   << std::string(62, ' ') << Fixed(x[1], 20, 4) << sci(at(r, r + 1)) << sci(at(r + 1, r + 1)) << "\n"
+                   << std::string(62, ' ') << Fixed(x[2], 20, 4) << sci(at(r, r + 2)) << sci(at(r + 1, r + 2)) << sci(at(r + 2, r + 2)) << "\n";
+                for (uint32_t j = k + 1; j < n; ++j)
+                    for (int a = 0; a < 3; ++a)
+                        os << std::string(82, ' ') << sci(at(r + a, 3 * (size_t)j)) << sci(at(r + a, 3 * (size_t)j + 1)) << sci(at(r + a, 3 * (size_t)j + 2)) << "\n";
+            }
+            if (dynaml)
+                os << "  </DnaMeasurement>\n";
+        }
+        if (dynaml)
+            os << "</DnaXmlFormat>\n";
     }
 
     // ---- .snx (PrintEstimatedStationCoordinatestoSNX PRN:2906-3010, DnaIoSnx::SerialiseSinex snx_file_writer.cpp) -----------
@@ -377,7 +572,7 @@ class dna_adjust {
     // Per station: horizontal / vertical positional uncertainty at 95 %, 1-sigma error ellipse, and the upper triangle
     // of its 3x3 variance block (XYZ or ENU).  Stations are listed as one block (the reference's layout for
     // simultaneous adjustments and for phased ones without --output-stn-blocks).
-    void PrintPositionalUncertainty(const std::string& file) const
+    void PrintPositionalUncertainty(const std::string& file)
     {
         std::ofstream os(file);
         PrintStationFileHeader(os, "POSITIONAL UNCERTAINTY", file);
@@ -387,7 +582,7 @@ class dna_adjust {
         var("Variances:", "68.3% (1 sigma)");
         var("Stations printed in blocks:", "No");
         var("Variance matrix units:", a_.apu_vcv_enu ? "ENU" : "XYZ");
-        var("Full covariance matrix:", "No");
+        var("Full covariance matrix:", a_.output_pu_covariances ? "Yes" : "No");
         if (!a_.type_b_global.empty())
             var("Type B uncertainties:", a_.type_b_global);
         if (!a_.type_b_file.empty())
@@ -395,7 +590,6 @@ class dna_adjust {
         os << std::string(80, '-') << "\n\n";
         os << "Positional uncertainty of adjusted station coordinates\n";
         os << "------------------------------------------------------\n\n";
-        char buf[512];
         const char* vn = a_.apu_vcv_enu ? "enu" : "XYZ";
         char v1[16], v2[16], v3[16];
         snprintf(v1, sizeof(v1), "Variance(%c)", vn[0]);
@@ -404,27 +598,85 @@ class dna_adjust {
             snprintf(v3, sizeof(v3), "Variance(up)");
         else
             snprintf(v3, sizeof(v3), "Variance(Z)");
-        snprintf(buf, sizeof(buf), "%-20s%2s%14s%15s%11s%11s%13s%13s%13s%19s%19s%19s", "Station", "", "Latitude", "Longitude", "Hz PosU",
+        char head[512];
+        snprintf(head, sizeof(head), "%-20s%2s%14s%15s%11s%11s%13s%13s%13s%19s%19s%19s", "Station", "", "Latitude", "Longitude", "Hz PosU",
                  "Vt PosU", "Semi-major", "Semi-minor", "Orientation", v1, v2, v3);
-        os << buf << "\n" << std::string(20 + 2 + 14 + 15 + 11 + 11 + 13 + 13 + 13 + 19 + 19 + 19, '-') << "\n";
-        const int pad = 20 + 2 + 14 + 15 + 11 + 11 + 13 + 13 + 13;
-        for (size_t i = 0; i < stn_.size(); ++i) {
-            const dna_stn_t& s = stn_[i];
-            const double* q = &vcv_[9 * i];
-            double ql[9];
-            to_local(q, s.currentLatitude, s.currentLongitude, ql);
-            double smaj, smin, az, hz, vt;
-            ErrorEllipseParameters(ql, smaj, smin, az);
-            PositionalUncertainty(smaj, smin, std::sqrt(std::fabs(ql[8])), hz, vt);
-            const double* v = a_.apu_vcv_enu ? ql : q;
-            snprintf(buf, sizeof(buf), "%-20s%2s%14.9f%15.9f%11.4f%11.4f%13.4f%13.4f%13.4f%19.9e%19.9e%19.9e", s.stationName, "",
-                     rad_to_dms(s.currentLatitude), rad_to_dms(s.currentLongitude), hz, vt, smaj, smin, rad_to_dms(az), v[0], v[1], v[2]);
-            os << buf << "\n";
-            snprintf(buf, sizeof(buf), "%*s%19.9e%19.9e", pad + 19, "", v[4], v[5]);
-            os << buf << "\n";
-            snprintf(buf, sizeof(buf), "%*s%19.9e", pad + 38, "", v[8]);
-            os << buf << "\n";
+        const std::string header = std::string(head) + "\n" + std::string(20 + 2 + 14 + 15 + 11 + 11 + 13 + 13 + 13 + 19 + 19 + 19, '-') + "\n";
+        if (!a_.output_pu_covariances) {
+            os << header;
+            for (uint32_t i : StationOrder(nullptr))
+                PrintPosUncertainty(os, i);
+            return;
         }
+        // --output-all-covariances (PrintPosUncertainty PRN:4438-4484): after each station, its 3x3 covariance blocks with the
+        // stations that follow it in the block, from the block's dense variance matrix; phased adjustments list block by block
+        const uint32_t nblocks = (uint32_t)info_.nfronts;
+        for (uint32_t b = 0; b < nblocks; ++b) {
+            if (a_.adjust_mode == Phased_Block_1Mode && b > 0)
+                break;
+            uint32_t n = 0;
+            check(gadj_get_block_vcv(ctx_, b, &n, nullptr, 0, nullptr));
+            std::vector<uint32_t> st(n);
+            const size_t dim = 3 * (size_t)n;
+            std::vector<double> q(dim * (dim + 1) / 2);
+            check(gadj_get_block_vcv(ctx_, b, &n, st.data(), n, q.data()));
+            auto at = [&](size_t i, size_t j) { return i >= j ? q[j * dim - j * (j - 1) / 2 + (i - j)] : q[i * dim - i * (i - 1) / 2 + (j - i)]; };
+            std::vector<uint32_t> order(n);   // positions in the block, in the order the stations are listed
+            for (uint32_t k = 0; k < n; ++k)
+                order[k] = k;
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+                return a_.sort_stn_orig_order ? stn_[st[x]].fileOrder < stn_[st[y]].fileOrder : st[x] < st[y];
+            });
+            if (a_.adjust_mode != SimultaneousMode)
+                os << "Block " << b + 1 << "\n";
+            os << header;
+            const int pad = 2 + 14 + 15 + 11 + 11 + 13 + 13 + 13;
+            char buf[256];
+            for (uint32_t k = 0; k < n; ++k) {
+                const uint32_t i = st[order[k]];
+                PrintPosUncertainty(os, i);
+                double R[9];
+                local_rotation(stn_[i].currentLatitude, stn_[i].currentLongitude, R);
+                for (uint32_t m = k + 1; m < n; ++m) {
+                    double c[9], cl[9];
+                    for (int x = 0; x < 3; ++x)
+                        for (int y = 0; y < 3; ++y)
+                            c[3 * x + y] = at(3 * (size_t)order[k] + x, 3 * (size_t)order[m] + y);
+                    const double* v = c;
+                    if (a_.apu_vcv_enu) {
+                        rotate_sym(R, c, cl);
+                        v = cl;
+                    }
+                    for (int x = 0; x < 3; ++x) {
+                        snprintf(buf, sizeof(buf), "%-20s%*s%19.9e%19.9e%19.9e", x == 0 ? stn_[st[order[m]]].stationName : "", pad, "", v[3 * x],
+                                 v[3 * x + 1], v[3 * x + 2]);
+                        os << buf << "\n";
+                    }
+                }
+            }
+            os << "\n";
+        }
+    }
+
+    void PrintPosUncertainty(std::ostream& os, size_t i) const
+    {
+        char buf[512];
+        const int pad = 20 + 2 + 14 + 15 + 11 + 11 + 13 + 13 + 13;
+        const dna_stn_t& s = stn_[i];
+        const double* q = &vcv_[9 * i];
+        double ql[9];
+        to_local(q, s.currentLatitude, s.currentLongitude, ql);
+        double smaj, smin, az, hz, vt;
+        ErrorEllipseParameters(ql, smaj, smin, az);
+        PositionalUncertainty(smaj, smin, std::sqrt(std::fabs(ql[8])), hz, vt);
+        const double* v = a_.apu_vcv_enu ? ql : q;
+        snprintf(buf, sizeof(buf), "%-20s%2s%14.9f%15.9f%11.4f%11.4f%13.4f%13.4f%13.4f%19.9e%19.9e%19.9e", s.stationName, "",
+                 rad_to_dms(s.currentLatitude), rad_to_dms(s.currentLongitude), hz, vt, smaj, smin, rad_to_dms(az), v[0], v[1], v[2]);
+        os << buf << "\n";
+        snprintf(buf, sizeof(buf), "%*s%19.9e%19.9e", pad + 19, "", v[4], v[5]);
+        os << buf << "\n";
+        snprintf(buf, sizeof(buf), "%*s%19.9e", pad + 38, "", v[8]);
+        os << buf << "\n";
     }
 
     // ---- .cor (PrintNetworkStationCorrections PRN:1349-1408, PrintCorStation PRN:4146-4230) -----------------------------

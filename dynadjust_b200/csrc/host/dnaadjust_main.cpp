@@ -4,7 +4,9 @@
 // (--multi-thread, --staged-adjustment, --create-stage-files, --purge-stage-files, --max-threads) are accepted and
 // ignored; unknown flags are a hard error, as in the reference (WRAP:1040-1046).
 #include <cstdlib>
+#include <cctype>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -37,6 +39,9 @@ const Flag kFlags[] = {
     {"precision-stn-angular", true}, {"precision-msr-linear", true}, {"precision-msr-angular", true}, {"output-iter-adj-stn", false},
     {"output-iter-adj-stat", false}, {"output-iter-adj-msr", false}, {"output-iter-cmp-msr", false}, {"output-ignored-msrs", false},
     {"comments", true}, {"version", false}, {"help-module", true},
+    {"project-file", true}, {"binary-stn-file", true}, {"binary-msr-file", true}, {"seg-file", true}, {"output-database-ids", false},
+    {"update-orig-stn-file", false}, {"inversion-method", true}, {"output-json", false},
+    {"export-xml-stn-file", false}, {"export-xml-msr-file", false}, {"export-dna-stn-file", false}, {"export-dna-msr-file", false},
 };
 
 // Boost.program_options accepts unambiguous prefixes (CI uses --phased, --multi)
@@ -61,6 +66,192 @@ const Flag* match(const std::string& key, std::string& err)
 
 }  // namespace
 
+// one option, by its full name (command line and project file share this)
+static int apply_option(adjust_settings& s, bool& quiet, const std::string& n, const std::string& value)
+{
+    if (n == "help") {
+        std::cout << "usage: dnaadjust <network> [--simultaneous-adjustment | --phased-adjustment] [--iteration-threshold x]\n"
+                     "       [--max-iterations n] [--free-stn-sd m] [--fixed-stn-sd m] [--conf-interval pct]\n"
+                     "       [--input-folder d] [--output-folder d] [--output-adj-msr] [--scale-normals-to-unity]\n";
+        return 1;
+    } else if (n == "phased-adjustment")
+        s.adjust_mode = s.adjust_mode == Phased_Block_1Mode ? Phased_Block_1Mode : PhasedMode;
+    else if (n == "multi-thread") {        // both imply a phased adjustment (WRAP:597-621); the execution strategy itself is the GPU's
+        s.adjust_mode = s.adjust_mode == Phased_Block_1Mode ? Phased_Block_1Mode : PhasedMode;
+        s.multi_thread = !s.stage;
+    } else if (n == "staged-adjustment") {
+        s.adjust_mode = s.adjust_mode == Phased_Block_1Mode ? Phased_Block_1Mode : PhasedMode;
+        s.stage = true;
+        s.multi_thread = false;
+    }
+    else if (n == "block1-phased")
+        s.adjust_mode = Phased_Block_1Mode;
+    else if (n == "simultaneous-adjustment")
+        s.adjust_mode = SimultaneousMode;
+    else if (n == "conf-interval")
+        s.confidence_interval = std::atof(value.c_str());
+    else if (n == "iteration-threshold")
+        s.iteration_threshold = (double)(float)std::atof(value.c_str());
+    else if (n == "max-iterations")
+        s.max_iterations = (uint32_t)std::atoi(value.c_str());
+    else if (n == "free-stn-sd")
+        s.free_std_dev = std::atof(value.c_str());
+    else if (n == "fixed-stn-sd")
+        s.fixed_std_dev = std::atof(value.c_str());
+    else if (n == "scale-normals-to-unity")
+        s.scale_normals_to_unity = true;
+    else if (n == "input-folder")
+        s.input_folder = value;
+    else if (n == "output-folder")
+        s.output_folder = value;
+    else if (n == "output-adj-msr")
+        s.output_adj_msr = true;
+    else if (n == "output-stn-blocks")
+        s.output_stn_blocks = true;
+    else if (n == "output-msr-blocks")
+        s.output_msr_blocks = true;
+    else if (n == "type-b-sd-global")
+        s.type_b_global = value;
+    else if (n == "type-b-sd-file")
+        s.type_b_file = value;
+    else if (n == "export-sinex-file")
+        s.export_sinex = true;
+    else if (n == "output-pos-uncertainty")
+        s.output_pos_uncertainty = true;
+    else if (n == "output-corrections-file")
+        s.output_corrections = true;
+    else if (n == "output-apu-vcv-units")
+        s.apu_vcv_enu = value == "ENU" || value == "enu" || value == "1";
+    else if (n == "hz-corr-threshold")
+        s.hz_corr_threshold = std::atof(value.c_str());
+    else if (n == "vt-corr-threshold")
+        s.vt_corr_threshold = std::atof(value.c_str());
+    else if (n == "output-all-covariances")
+        s.output_pu_covariances = true;
+    else if (n == "network-name")
+        s.network_name = value;
+    else if (n == "binary-stn-file")
+        s.bst_file = value;
+    else if (n == "binary-msr-file")
+        s.bms_file = value;
+    else if (n == "seg-file")
+        s.seg_file = value;
+    else if (n == "quiet")
+        quiet = true;
+    else if (n == "no-binary-update")
+        s.update_binary_files = false;
+    else if (n == "constraints")
+        s.station_constraints = value;
+    else if (n == "sort-adj-msr-field")
+        s.sort_adj_msr = std::atoi(value.c_str());
+    else if (n == "output-adj-gnss-units")
+        s.adj_gnss_units = std::atoi(value.c_str());
+    else if (n == "output-tstat-adj-msr")
+        s.adj_msr_tstat = true;
+    else if (n == "output-msr-to-stn")
+        s.output_msr_to_stn = true;
+    else if (n == "sort-msr-to-stn-field")
+        s.sort_msr_to_stn = std::atoi(value.c_str());
+    else if (n == "stn-corrections")
+        s.stn_corrections = true;
+    else if (n == "stn-coord-types")
+        s.stn_coord_types = value;
+    else if (n == "sort-stn-orig-order")
+        s.sort_stn_orig_order = true;
+    else if (n == "angular-stn-type")
+        s.angular_type_stn = std::atoi(value.c_str());
+    else if (n == "angular-msr-type")
+        s.angular_type_msr = std::atoi(value.c_str());
+    else if (n == "dms-msr-format")
+        s.dms_format_msr = std::atoi(value.c_str());
+    else if (n == "precision-stn-linear")
+        s.precision_metres_stn = std::atoi(value.c_str());
+    else if (n == "precision-stn-angular")
+        s.precision_seconds_stn = std::atoi(value.c_str());
+    else if (n == "precision-msr-linear")
+        s.precision_metres_msr = std::atoi(value.c_str());
+    else if (n == "precision-msr-angular")
+        s.precision_seconds_msr = std::atoi(value.c_str());
+    else if (n == "output-iter-adj-stn")
+        s.iter_adj_stn = true;
+    else if (n == "output-iter-adj-stat")
+        s.iter_adj_stat = true;
+    else if (n == "output-iter-adj-msr")
+        s.iter_adj_msr = true;
+    else if (n == "output-iter-cmp-msr")
+        s.iter_cmp_msr = true;
+    else if (n == "output-ignored-msrs")
+        s.output_ignored_msrs = true;
+    else if (n == "comments")
+        s.comments = value;
+    else if (n == "export-xml-stn-file")
+        s.export_xml_stn = true;
+    else if (n == "export-xml-msr-file")
+        s.export_xml_msr = true;
+    else if (n == "export-dna-stn-file")
+        s.export_dna_stn = true;
+    else if (n == "export-dna-msr-file")
+        s.export_dna_msr = true;
+    else if (n == "version") {
+        std::cout << "dnaadjust (dynadjust_b200) 1.0\n";
+        return 1;
+    } else if (n == "help-module") {
+        std::cout << "dnaadjust: help for option group '" << value << "': see --help\n";
+        return 1;
+    }
+    // remaining accepted flags select CPU execution strategies: no effect here
+    return 0;
+}
+
+// <net>.dnaproj (CDnaProjectFile::LoadProjectFile dnaprojectfile.cpp:127-310): "variable" in the first 35 columns, its value
+// after; sections #general, #adjust and #output hold what dnaadjust reads.  Switches are yes / no.
+static int load_project_file(const std::string& file, adjust_settings& s, bool& quiet)
+{
+    std::ifstream in(file);
+    if (!in) {
+        std::cerr << "\n- Error: project file " << file << " does not exist.\n\n";
+        return 2;
+    }
+    std::string line, section;
+    auto trim = [](std::string t) {
+        const size_t a = t.find_first_not_of(" \t\r"), b = t.find_last_not_of(" \t\r");
+        return a == std::string::npos ? std::string() : t.substr(a, b - a + 1);
+    };
+    while (std::getline(in, line)) {
+        if (line.size() <= 35 && line.find('#') == std::string::npos)
+            continue;
+        if (line[0] == '#') {
+            section = trim(line.substr(0, line.find(' ')));
+            continue;
+        }
+        if (line.find("----------") != std::string::npos || (section != "#general" && section != "#adjust" && section != "#output"))
+            continue;
+        std::string var = trim(line.substr(0, 35)), val = line.size() > 35 ? trim(line.substr(35)) : std::string();
+        if (val.empty())
+            continue;
+        if (var == "adjustment-mode") {
+            var = val;
+            val = "yes";
+        }
+        const Flag* f = nullptr;
+        for (const Flag& k : kFlags)
+            if (var == k.name)
+                f = &k;
+        if (!f || var == "help" || var == "version" || var == "help-module" || var == "project-file")
+            continue;   // settings of the other programs of the suite
+        if (!f->takes_value) {
+            std::string low = val;
+            for (char& ch : low)
+                ch = (char)std::tolower((unsigned char)ch);
+            if (low != "yes" && low != "1" && low != "true")
+                continue;
+        }
+        if (int rc = apply_option(s, quiet, f->name, val))
+            return rc;
+    }
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     adjust_settings s;
@@ -69,6 +260,24 @@ int main(int argc, char** argv)
     bool quiet = false;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
+        if (a.size() == 2 && a[0] == '-' && a[1] != '-') {   // short forms (WRAP:822-841 and the generic options)
+            const char* lng = nullptr;
+            switch (a[1]) {
+            case 'n': lng = "--network-name"; break;
+            case 'i': lng = "--input-folder"; break;
+            case 'o': lng = "--output-folder"; break;
+            case 'p': lng = "--project-file"; break;
+            case 's': lng = "--binary-stn-file"; break;
+            case 'm': lng = "--binary-msr-file"; break;
+            case 'h': lng = "--help"; break;
+            case 'v': lng = "--version"; break;
+            }
+            if (!lng) {
+                std::cerr << "- Error: unrecognised option '" << a << "'\n";
+                return EXIT_FAILURE;
+            }
+            a = lng;
+        }
         if (a.rfind("--", 0) != 0) {
             if (!s.network_name.empty()) {
                 std::cerr << "- Error: too many positional arguments ('" << a << "').\n";
@@ -97,119 +306,16 @@ int main(int argc, char** argv)
             }
             value = argv[++i];
         }
-        const std::string n = f->name;
-        if (n == "help") {
-            std::cout << "usage: dnaadjust <network> [--simultaneous-adjustment | --phased-adjustment] [--iteration-threshold x]\n"
-                         "       [--max-iterations n] [--free-stn-sd m] [--fixed-stn-sd m] [--conf-interval pct]\n"
-                         "       [--input-folder d] [--output-folder d] [--output-adj-msr] [--scale-normals-to-unity]\n";
-            return EXIT_SUCCESS;
-        } else if (n == "phased-adjustment" || n == "staged-adjustment" || n == "multi-thread")
-            s.adjust_mode = (n == "phased-adjustment") ? PhasedMode : s.adjust_mode;
-        else if (n == "block1-phased")
-            s.adjust_mode = Phased_Block_1Mode;
-        else if (n == "simultaneous-adjustment")
-            s.adjust_mode = SimultaneousMode;
-        else if (n == "conf-interval")
-            s.confidence_interval = std::atof(value.c_str());
-        else if (n == "iteration-threshold")
-            s.iteration_threshold = (double)(float)std::atof(value.c_str());
-        else if (n == "max-iterations")
-            s.max_iterations = (uint32_t)std::atoi(value.c_str());
-        else if (n == "free-stn-sd")
-            s.free_std_dev = std::atof(value.c_str());
-        else if (n == "fixed-stn-sd")
-            s.fixed_std_dev = std::atof(value.c_str());
-        else if (n == "scale-normals-to-unity")
-            s.scale_normals_to_unity = true;
-        else if (n == "input-folder")
-            s.input_folder = value;
-        else if (n == "output-folder")
-            s.output_folder = value;
-        else if (n == "output-adj-msr")
-            s.output_adj_msr = true;
-        else if (n == "output-stn-blocks")
-            s.output_stn_blocks = true;
-        else if (n == "output-msr-blocks")
-            s.output_msr_blocks = true;
-        else if (n == "type-b-sd-global")
-            s.type_b_global = value;
-        else if (n == "type-b-sd-file")
-            s.type_b_file = value;
-        else if (n == "export-sinex-file")
-            s.export_sinex = true;
-        else if (n == "output-pos-uncertainty")
-            s.output_pos_uncertainty = true;
-        else if (n == "output-corrections-file")
-            s.output_corrections = true;
-        else if (n == "output-apu-vcv-units")
-            s.apu_vcv_enu = value == "ENU" || value == "enu" || value == "1";
-        else if (n == "hz-corr-threshold")
-            s.hz_corr_threshold = std::atof(value.c_str());
-        else if (n == "vt-corr-threshold")
-            s.vt_corr_threshold = std::atof(value.c_str());
-        else if (n == "output-all-covariances") {
-            std::cerr << "- Error: --output-all-covariances needs the dense block variance matrix; this build keeps N^-1 on the "
-                         "sparsity pattern of the factor only (station blocks and measured pairs).\n";
-            return EXIT_FAILURE;
+        if (std::string(f->name) == "project-file") {
+            // "If specified, all other options are ignored" (WRAP:487-505)
+            s = adjust_settings();
+            s.command_line = std::string(argv[0]) + " -p " + value + " ";
+            if (int rc = load_project_file(value, s, quiet))
+                return rc == 1 ? EXIT_SUCCESS : EXIT_FAILURE;
+            break;
         }
-        else if (n == "network-name")
-            s.network_name = value;
-        else if (n == "quiet")
-            quiet = true;
-        else if (n == "no-binary-update")
-            s.update_binary_files = false;
-        else if (n == "constraints")
-            s.station_constraints = value;
-        else if (n == "sort-adj-msr-field")
-            s.sort_adj_msr = std::atoi(value.c_str());
-        else if (n == "output-adj-gnss-units")
-            s.adj_gnss_units = std::atoi(value.c_str());
-        else if (n == "output-tstat-adj-msr")
-            s.adj_msr_tstat = true;
-        else if (n == "output-msr-to-stn")
-            s.output_msr_to_stn = true;
-        else if (n == "sort-msr-to-stn-field")
-            s.sort_msr_to_stn = std::atoi(value.c_str());
-        else if (n == "stn-corrections")
-            s.stn_corrections = true;
-        else if (n == "stn-coord-types")
-            s.stn_coord_types = value;
-        else if (n == "sort-stn-orig-order")
-            s.sort_stn_orig_order = true;
-        else if (n == "angular-stn-type")
-            s.angular_type_stn = std::atoi(value.c_str());
-        else if (n == "angular-msr-type")
-            s.angular_type_msr = std::atoi(value.c_str());
-        else if (n == "dms-msr-format")
-            s.dms_format_msr = std::atoi(value.c_str());
-        else if (n == "precision-stn-linear")
-            s.precision_metres_stn = std::atoi(value.c_str());
-        else if (n == "precision-stn-angular")
-            s.precision_seconds_stn = std::atoi(value.c_str());
-        else if (n == "precision-msr-linear")
-            s.precision_metres_msr = std::atoi(value.c_str());
-        else if (n == "precision-msr-angular")
-            s.precision_seconds_msr = std::atoi(value.c_str());
-        else if (n == "output-iter-adj-stn")
-            s.iter_adj_stn = true;
-        else if (n == "output-iter-adj-stat")
-            s.iter_adj_stat = true;
-        else if (n == "output-iter-adj-msr")
-            s.iter_adj_msr = true;
-        else if (n == "output-iter-cmp-msr")
-            s.iter_cmp_msr = true;
-        else if (n == "output-ignored-msrs")
-            s.output_ignored_msrs = true;
-        else if (n == "comments")
-            s.comments = value;
-        else if (n == "version") {
-            std::cout << "dnaadjust (dynadjust_b200) 1.0\n";
-            return EXIT_SUCCESS;
-        } else if (n == "help-module") {
-            std::cout << "dnaadjust: help for option group '" << value << "': see --help\n";
-            return EXIT_SUCCESS;
-        }
-        // remaining accepted flags select CPU execution strategies or extra reports: no effect here
+        if (int rc = apply_option(s, quiet, f->name, value))
+            return rc == 1 ? EXIT_SUCCESS : EXIT_FAILURE;
     }
     if (s.network_name.empty()) {
         std::cerr << "- Error: no network name was given.\n";

@@ -200,8 +200,29 @@ def _apu_cor(exe, oracle, tmp_path):
     assert r.returncode == 0, r.stderr
     cor = open(os.path.join(tmp_path, "pu.simult.cor")).read()
     assert not [l for l in cor.split("Corrections to stations")[1].splitlines() if l[:1].isalnum() and not l.startswith("Station")]
-    r = _run(exe, tmp_path, "pu", "--output-all-covariances")
-    assert r.returncode == 1 and "dense block variance matrix" in r.stderr
+    # --output-all-covariances (PRN:4438-4484): after every station its covariance blocks with the stations that follow
+    r = _run(exe, tmp_path, "pu", "--output-pos-uncertainty", "--output-all-covariances", "--output-apu-vcv-units", "ENU", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    apu = open(os.path.join(tmp_path, "pu.simult.apu")).read()
+    assert re.search(r"Full covariance matrix:\s+Yes", apu)
+    body = apu.split("Positional uncertainty of adjusted station coordinates")[1].splitlines()
+    n, cur, seen = len(stn), -1, 0
+    names = [s.decode() for s in stn["stationName"]]
+    for k, l in enumerate(body):
+        f = l.split()
+        if len(f) == 11 and f[0] in names:                   # station row
+            cur = names.index(f[0])
+        elif len(f) == 4 and f[0] in names and cur >= 0:     # first row of a covariance block, then two more rows
+            j = names.index(f[0])
+            assert j > cur
+            C = np.array([[float(x) for x in f[1:4]], [float(x) for x in body[k + 1].split()], [float(x) for x in body[k + 2].split()]])
+            lat, lon = stn_o["currentLatitude"][cur], stn_o["currentLongitude"][cur]
+            sl, cl, so, co = np.sin(lat), np.cos(lat), np.sin(lon), np.cos(lon)
+            R = np.array([[-so, -sl * co, cl * co], [co, -sl * so, cl * so], [0, cl, sl]])
+            want = R.T @ V[3 * cur:3 * cur + 3, 3 * j:3 * j + 3] @ R
+            assert np.abs(C - want).max() <= 1e-8 * np.abs(V).max() + 1e-9 * np.abs(want).max()
+            seen += 1
+    assert seen == n * (n - 1) // 2
 
 
 def test_cli_constraints(cli_hostsim, oracle, tmp_path):

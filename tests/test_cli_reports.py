@@ -11,6 +11,7 @@ import pytest
 
 from dynadjust_b200 import dnafiles, synth
 from dynadjust_b200 import synth_terrestrial as st
+from tests import parity
 from tests.golden import dna_ascii
 from tests.test_cli import _run, _write_network, cli_gpu, cli_hostsim  # noqa: F401  (fixtures)
 
@@ -231,3 +232,120 @@ def test_cli_gnss_alternate_units(cli_hostsim, tmp_path):
         sd_az = float(fa[7]) * SEC * dist
         sd_en = [float(enu[b + q][67:].split()[3]) for q in range(2)]
         assert 0.5 * min(sd_en) < sd_az < 2.0 * max(sd_en)
+
+
+def _cluster_vcv_of(m):
+    """Full variance matrix of a Y cluster held in binary records (as the engine loads it)."""
+    first = [i for i in range(len(m)) if m["measStart"][i] == 0]
+    n = len(first)
+    V = np.zeros((3 * n, 3 * n))
+    for k, i in enumerate(first):
+        r = m[i:i + 3]
+        blk = np.array([[r["term2"][0], r["term2"][1], r["term2"][2]], [r["term2"][1], r["term3"][1], r["term3"][2]],
+                        [r["term2"][2], r["term3"][2], r["term4"][2]]])
+        V[3 * k:3 * k + 3, 3 * k:3 * k + 3] = blk
+        for q in range(int(r["vectorCount2"][0])):
+            cv = m[i + 3 + 3 * q:i + 6 + 3 * q]
+            B = np.stack([cv["term1"], cv["term2"], cv["term3"]], axis=1)
+            j = k + 1 + q
+            V[3 * k:3 * k + 3, 3 * j:3 * j + 3] = B
+            V[3 * j:3 * j + 3, 3 * k:3 * k + 3] = B.T
+    return [int(m["station1"][i]) for i in first], np.array([m["term1"][i:i + 3] for i in first]), V
+
+
+def _exports(exe, oracle, tmp_path):
+    """--export-dna-stn-file / --export-dna-msr-file / --export-xml-stn-file / --export-xml-msr-file (SURVEY 8f item 4;
+    PRN:2775-2903, 3012-3164): the adjusted stations in the form they were supplied in, and the estimates with their
+    full variance matrix as a GNSS point cluster per block.  The DNA files are read back with the DNA reader of the
+    golden fixtures; the DynaML files by tag."""
+    stn, msr, _, _ = synth.gnss_network(45, 130, 21)
+    stn["suppliedStationType"][::3] = 0            # XYZ
+    stn["suppliedStationType"][1::3] = 3           # UTM
+    stn["fileOrder"] = np.arange(len(stn))[::-1]   # exported in the order of the imported file
+    _write_network(tmp_path, "ex", stn, msr)
+    ref = oracle.adjust_simultaneous(stn.copy(), msr.copy(), want_vcv=True)
+    V, est = ref["vcv"], ref["est"].reshape(-1, 3)
+    names = [n.decode() for n in stn["stationName"]]
+    r = _run(exe, tmp_path, "ex", "--export-dna-stn-file", "--export-dna-msr", "--export-xml-stn-file", "--export-xml-msr-file", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    stem = os.path.join(tmp_path, "ex.simult.adj")
+    head = open(stem + ".stn").readline().split()
+    assert head[:3] == ["!#=DNA", "3.01", "STN"] and head[-1] == "45" and head[4] == "GDA2020"
+    back = dna_ascii.read_stations(stem + ".stn")
+    assert [n.decode() for n in back["stationName"]] == names[::-1]
+    xyz = synth.geo_to_cart(back["currentLatitude"], back["currentLongitude"], back["currentHeight"] +
+                            np.where(back["suppliedStationType"] == 0, 0.0, stn["geoidSep"][::-1]))   # LLH / UTM rows carry H
+    assert np.abs(xyz - est[::-1]).max() < 4e-4
+    assert sorted(set(l[24:27] for l in open(stem + ".stn") if l[0] not in "!*")) == ["LLH", "UTM", "XYZ"]
+    cl = dna_ascii.read_measurements(stem + ".msr", stn, reftran=False)
+    who, val, Q = _cluster_vcv_of(cl)
+    assert who == list(range(45)) and np.abs(val - est).max() < 1e-4
+    assert np.abs(Q - V).max() <= 2e-8 * np.abs(V).max()
+    x = open(stem + ".msr.xml").read()
+    assert x.count("<Clusterpoint>") == 45 and x.count("<PointCovariance>") == 45 * 44 // 2 and "<Total>45</Total>" in x
+    sxx = [float(v) for v in re.findall(r"<SigmaXX>(\S+)</SigmaXX>", x)]
+    assert np.abs(np.array(sxx) - np.diag(V)[0::3]).max() <= 2e-8 * np.abs(V).max()
+    m13 = [float(v) for v in re.findall(r"<m13>(\S+)</m13>", x)]
+    assert abs(m13[0] - V[0, 5]) <= 2e-8 * np.abs(V).max()
+    sx = open(stem + ".stn.xml").read()
+    assert sx.count("<DnaStation>") == 45 and sx.count("<HemisphereZone>") == 15 and sx.rstrip().endswith("</DnaXmlFormat>")
+    # phased: one cluster per block, inner and junction stations
+    isl = parity.chain_blocks(45, 15)
+    dnafiles.write_seg(os.path.join(tmp_path, "ex.seg"), isl, [[] for _ in isl], [[] for _ in isl])
+    r = _run(exe, tmp_path, "ex", "--phased", "--export-dna-msr-file", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    cl = dna_ascii.read_measurements(os.path.join(tmp_path, "ex.phased.adj.msr"), stn, reftran=False)
+    seen = set()
+    for cid in np.unique(cl["clusterID"]):
+        who, val, Q = _cluster_vcv_of(cl[cl["clusterID"] == cid])
+        idx = np.concatenate([[3 * s, 3 * s + 1, 3 * s + 2] for s in who])
+        assert np.abs(Q - V[np.ix_(idx, idx)]).max() <= 2e-8 * np.abs(V).max() and np.abs(val - est[who]).max() < 1e-4
+        seen.update(who)
+    assert seen == set(range(45)) and len(np.unique(cl["clusterID"])) == len(isl)
+
+
+def test_cli_exports_hostsim(cli_hostsim, oracle, tmp_path):
+    _exports(cli_hostsim, oracle, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_exports_gpu(cli_gpu, oracle, tmp_path):
+    _exports(cli_gpu, oracle, tmp_path)
+
+
+def test_cli_project_file_and_short_options(cli_hostsim, tmp_path):
+    """`dnaadjust -p <net>.dnaproj` (all other options ignored, WRAP:487-505; file syntax dnaprojectfile.cpp:127-310), the short
+    forms -n -i -o, file-name overrides, and the output names of the execution-strategy flags (WRAP:659-734)."""
+    stn, msr, _, _ = synth.gnss_network(40, 110, 8)
+    _write_network(tmp_path, "pj", stn, msr)
+    isl = parity.chain_blocks(40, 14)
+    dnafiles.write_seg(os.path.join(tmp_path, "pj.seg"), isl, [[] for _ in isl], [[] for _ in isl])
+    out = os.path.join(tmp_path, "out")
+    os.mkdir(out)
+    rec = lambda k, v: f"{k:<35}{v}\n"
+    with open(os.path.join(tmp_path, "pj.dnaproj"), "w") as f:
+        f.write("# DynAdjust project file\n\n#general" + " " * 40 + "\n" + "-" * 80 + "\n")
+        f.write(rec("network-name", "pj") + rec("input-folder", str(tmp_path)) + rec("output-folder", out) + rec("quiet", "yes"))
+        f.write("\n#import" + " " * 40 + "\n" + "-" * 80 + "\n" + rec("max-iterations", "1") + rec("reference-frame", "GDA2020"))
+        f.write("\n#adjust" + " " * 40 + "\n" + "-" * 80 + "\n")
+        f.write(rec("adjustment-mode", "phased-adjustment") + rec("multi-thread", "yes") + rec("staged-adjustment", "no") + rec("max-iterations", "7"))
+        f.write(rec("output-adj-msr", "yes") + rec("output-pos-uncertainty", "no") + rec("free-stn-sd", "5.0") + rec("stn-coord-types", "ENzPLh"))
+        f.write(rec("no-binary-update", "yes"))
+    r = subprocess.run([cli_hostsim, "--max-iterations", "1", "-p", os.path.join(tmp_path, "pj.dnaproj"), "--output-corrections-file"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout == "", r.stderr + r.stdout
+    assert sorted(os.listdir(out)) == ["pj.phased-mt.adj", "pj.phased-mt.xyz"]
+    text = open(os.path.join(out, "pj.phased-mt.adj")).read()
+    assert "Adjusted Measurements" in text and re.search(r"^SOLUTION\s+Converged", text, re.M)
+    head = _tables(text, "Adjusted Coordinates")[-1][0].split()
+    assert head[2:8] == ["Easting", "Northing", "Zone", "Latitude", "Longitude", "h(Ellipse)"]
+    r = subprocess.run([cli_hostsim, "-p", os.path.join(tmp_path, "missing.dnaproj")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "does not exist" in r.stderr
+    # short forms, file-name overrides, staged naming
+    os.rename(os.path.join(tmp_path, "pj.bst"), os.path.join(tmp_path, "stations.bin"))
+    r = subprocess.run([cli_hostsim, "-n", "pj", "-i", str(tmp_path), "-o", out, "--binary-stn-file", "stations.bin", "--staged", "--create-stage-files",
+                        "--no-binary-update"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert os.path.exists(os.path.join(out, "pj.phased-stage.adj"))
+    r = subprocess.run([cli_hostsim, "-x"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "unrecognised option" in r.stderr
