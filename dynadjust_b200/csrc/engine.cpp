@@ -1001,6 +1001,13 @@ int gadj_set_measurements(gadj_ctx* c, dna_msr_t* msr, uint64_t count)
     return 0;
 }
 
+int gadj_set_measurements_reduced(gadj_ctx* c, int reduced)
+{
+    c->reduced = reduced ? 1 : 0;
+    c->prepared = false;
+    return 0;
+}
+
 int gadj_set_blocks(gadj_ctx* c, uint32_t nblocks, const uint32_t* isl_off, const uint32_t* isl)
 {
     c->isl_off.clear();
@@ -2161,6 +2168,40 @@ int gadj_get_vcv_block(gadj_ctx* c, uint32_t si, uint32_t sj, double q[9])
     if (extract_vcv(c))
         return 1;
     return get_block(c, c->d_vcvd.p, c->d_vcvo.p, si, sj, q);
+}
+
+// bulk form of gadj_get_vcv_block: one device -> host copy of the stored variance blocks, then the pairs on the host
+int gadj_get_pair_vcvs(gadj_ctx* c, uint64_t npairs, const uint32_t* si, const uint32_t* sj, double* q)
+{
+    if (!c->prepared)
+        return c->fail("gadj_prepare has not been run");
+    if (extract_vcv(c))
+        return 1;
+    std::vector<double> diag(9 * (size_t)c->nstn), off(9 * (size_t)c->nedge);
+    dev::d2h(diag.data(), c->d_vcvd.p, diag.size() * sizeof(double));
+    if (!off.empty())
+        dev::d2h(off.data(), c->d_vcvo.p, off.size() * sizeof(double));
+    std::string e = dev::sync();
+    if (!e.empty())
+        return c->fail(e);
+    for (uint64_t p = 0; p < npairs; ++p) {
+        if (si[p] >= c->nstn || sj[p] >= c->nstn)
+            return c->fail("station index out of range");
+        const double* t;
+        bool tr = false;
+        if (si[p] == sj[p])
+            t = &diag[9 * (size_t)si[p]];
+        else {
+            uint64_t ei;
+            if (find_edge(c, si[p], sj[p], &ei, &tr))
+                return c->fail("no measurement joins the two stations: block is outside the stored pattern");
+            t = &off[9 * ei];
+        }
+        for (int r = 0; r < 3; ++r)
+            for (int k = 0; k < 3; ++k)
+                q[9 * p + r * 3 + k] = tr ? t[k * 3 + r] : t[r * 3 + k];
+    }
+    return 0;
 }
 
 int gadj_get_block_vcv(gadj_ctx* c, uint32_t block, uint32_t* nstations, uint32_t* stations, uint32_t cap, double* packed_lower)

@@ -38,6 +38,8 @@ struct adjust_settings {            // the fields of project_settings.a / .g / .
     int adjust_mode = SimultaneousMode;
     bool stage = false, multi_thread = false;    // --staged-adjustment / --multi-thread: phased; they name the outputs (WRAP:687-704)
     std::string bst_file, bms_file, seg_file;    // --binary-stn-file / --binary-msr-file / --seg-file: override the network name
+    std::string stage_path;                      // --stage-path: where <net>-rva.mtx / <net>-pam.mtx go (default: the output folder)
+    bool report_results = false;                 // --report-results: print the last adjustment again (WRAP:607-614)
     double iteration_threshold = (double)0.0005f;   // float in the reference (dnaoptions.hpp:432)
     uint32_t max_iterations = 10;
     double free_std_dev = 10.0, fixed_std_dev = 1.0e-6, confidence_interval = 95.0;
@@ -110,6 +112,7 @@ class dna_adjust {
             SignalExceptionAdjustment(gadj_last_error(nullptr));
         check(gadj_set_stations(ctx_, stn_.data(), (uint32_t)stn_.size()));
         check(gadj_set_measurements(ctx_, msr_.data(), msr_.size()));
+        check(gadj_set_measurements_reduced(ctx_, bms_meta_.reduced ? 1 : 0));   // isFirstTimeAdjustment_ (ADJ:296)
         if (a_.adjust_mode != SimultaneousMode) {
             dnafiles::load_seg(a_.seg_file.empty() ? base + ".seg" : in_folder(a_.seg_file), seg_);
             std::vector<uint32_t> off{0}, isl;
@@ -230,8 +233,19 @@ class dna_adjust {
         const std::string stem = a_.output_folder + "/" + a_.network_name + "." + ModeSuffix();
         std::ofstream adj(stem + ".adj");
         PrintOutputFileHeaderInfo(adj, "DYNADJUST ADJUSTMENT OUTPUT FILE", stem + ".adj");
-        adj << "\n+ Initialising adjustment\n+ Loading network files\n+ Allocating memory\n\n+ Preparing for adjustment...  done.\n";
-        adj << "+ Commencing " << (a_.adjust_mode == SimultaneousMode ? "simultaneous" : "phased") << " adjustment\n\n";
+        if (!a_.comments.empty())
+            adj << "\n" << std::left << std::setw(35) << "Comments:" << a_.comments << "\n";
+        if (report_mode_)
+            adj << "\n+ Loading network files\n+ Printing results of the last adjustment\n\n";
+        else {
+            adj << "\n+ Initialising adjustment\n+ Loading network files\n+ Allocating memory\n\n+ Preparing for adjustment...  done.\n";
+            adj << "+ Commencing " << (a_.adjust_mode == SimultaneousMode ? "simultaneous" : "phased") << " adjustment\n\n";
+        }
+        if (a_.adj_gnss_units != 0 && a_.output_adj_msr)
+            ComputeBaselinePrecisions();
+        if (report_mode_ && (a_.export_sinex || a_.export_xml_msr || a_.export_dna_msr || a_.output_pu_covariances))
+            SignalExceptionAdjustment("Report results: the block variance matrices (--export-sinex-file, --export-*-msr-file, --output-all-covariances) "
+                                      "are formed by an adjustment only; run the adjustment with these options.");
         for (size_t i = 0; i < iterations_.size(); ++i) {
             PrintIteration(adj, (uint32_t)i + 1, iterations_[i]);
             adj << iter_pre_[i] << iter_post_[i];
@@ -261,6 +275,140 @@ class dna_adjust {
         if (a_.export_sinex)
             PrintEstimatedStationCoordinatestoSNX();
     }
+
+    // ---- precision of the adjusted G / X baselines, full 3x3 (v_precAdjMsrsFull_; Precision_Adjusted_GNSS_bsl MFN:255-297):
+    // Q11 + Q22 - Q12 - Q21 from the station and pair blocks of the rigorous variances, fetched in one bulk call
+    void ComputeBaselinePrecisions()
+    {
+        if (!pam_rec_.empty() || !ctx_)
+            return;
+        std::vector<uint32_t> si, sj;
+        for (size_t i = 0; i < msr_.size();) {
+            const size_t span = MeasurementSpan(i);
+            const dna_msr_t& m = msr_[i];
+            if (!m.ignore && (m.measType == 'G' || m.measType == 'X'))
+                for (size_t j = i; j + 2 < i + span; j += 3 + 3 * (size_t)msr_[j].vectorCount2) {
+                    pam_rec_.push_back((uint32_t)j);
+                    si.push_back(msr_[j].station1);
+                    sj.push_back(msr_[j].station2);
+                }
+            i += span;
+        }
+        std::vector<double> q12(9 * si.size());
+        if (!si.empty())
+            check(gadj_get_pair_vcvs(ctx_, si.size(), si.data(), sj.data(), q12.data()));
+        pam_.resize(6 * si.size());
+        static const int ua[6] = {0, 0, 0, 1, 1, 2}, ub[6] = {0, 1, 2, 1, 2, 2};
+        for (size_t p = 0; p < si.size(); ++p)
+            for (int t = 0; t < 6; ++t) {
+                const int a = ua[t], b = ub[t];
+                pam_[6 * p + t] = raw_vcv_[9 * (size_t)si[p] + 3 * a + b] + raw_vcv_[9 * (size_t)sj[p] + 3 * a + b] - q12[9 * p + 3 * a + b] -
+                                  q12[9 * p + 3 * b + a];
+            }
+    }
+    void BaselinePrecision(size_t rec, double* Va) const
+    {
+        auto it = std::lower_bound(pam_rec_.begin(), pam_rec_.end(), (uint32_t)rec);
+        if (it == pam_rec_.end() || *it != rec)
+            throw std::runtime_error("the precision of an adjusted baseline is not available (re-run the adjustment)");
+        const double* v = &pam_[6 * (size_t)(it - pam_rec_.begin())];
+        const double M[9] = {v[0], v[1], v[2], v[1], v[3], v[4], v[2], v[4], v[5]};
+        std::memcpy(Va, M, sizeof(M));
+    }
+
+    // ---- <net>-rva.mtx / <net>-pam.mtx (SerialiseAdjustedVarianceMatrices ADJ:6770-6799): what --report-results needs to
+    // print the last adjustment again without solving — the solution summary and the 3x3 variance block of every station
+    // (rva), the precisions of the adjusted baselines (pam).  The reference keeps its dense per-block matrices in these
+    // files; they are private to dnaadjust, so the layout here is this program's own: an 8-byte tag, counts, raw doubles.
+    struct ReportHeader {
+        char tag[8];
+        uint64_t nstn, nmsr;
+        gadj_stats stats;
+        double chi_lower, chi_upper, max_corr, total_ms;
+        int32_t pass_fail, status, iterations, mode;
+    };
+    std::string StagePath(const char* what) const
+    {
+        return (a_.stage_path.empty() ? a_.output_folder : a_.stage_path) + "/" + a_.network_name + "-" + what + ".mtx";
+    }
+    void SerialiseAdjustedVarianceMatrices()
+    {
+        ComputeBaselinePrecisions();
+        ReportHeader h{};
+        std::memcpy(h.tag, "GADJRVA1", 8);
+        h.nstn = stn_.size();
+        h.nmsr = msr_.size();
+        h.stats = stats_;
+        h.chi_lower = chiLower_, h.chi_upper = chiUpper_, h.max_corr = maxCorr_, h.total_ms = total_ms_;
+        h.pass_fail = passFail_, h.status = (int32_t)adjustStatus_, h.iterations = (int32_t)iterations_.size(), h.mode = a_.adjust_mode;
+        std::ofstream rva(StagePath("rva"), std::ios::binary);
+        rva.write(reinterpret_cast<const char*>(&h), sizeof(h));
+        rva.write(reinterpret_cast<const char*>(raw_vcv_.data()), (std::streamsize)(raw_vcv_.size() * sizeof(double)));
+        std::memcpy(h.tag, "GADJPAM1", 8);
+        h.nstn = pam_rec_.size();
+        std::ofstream pam(StagePath("pam"), std::ios::binary);
+        pam.write(reinterpret_cast<const char*>(&h), sizeof(h));
+        pam.write(reinterpret_cast<const char*>(pam_rec_.data()), (std::streamsize)(pam_rec_.size() * sizeof(uint32_t)));
+        pam.write(reinterpret_cast<const char*>(pam_.data()), (std::streamsize)(pam_.size() * sizeof(double)));
+        if (!rva || !pam)
+            SignalExceptionAdjustment("SerialiseAdjustedVarianceMatrices(): could not write " + StagePath("rva") + " / " + StagePath("pam"));
+    }
+
+    // ---- --report-results (WRAP:607-614, 1382-1384; DeSerialiseAdjustedVarianceMatrices ADJ:6720-6767): the binary files of
+    // the last adjustment already hold the adjusted coordinates and the measurement statistics; with the two .mtx files
+    // every report is printed again.  No solve, no device.
+    void LoadLastAdjustment(const adjust_settings& s)
+    {
+        a_ = s;
+        report_mode_ = true;
+        const std::string base = a_.input_folder + "/" + a_.network_name;
+        auto in_folder = [&](const std::string& f) { return f.find('/') == std::string::npos ? a_.input_folder + "/" + f : f; };
+        bst_file_ = a_.bst_file.empty() ? base + ".bst" : in_folder(a_.bst_file);
+        bms_file_ = a_.bms_file.empty() ? base + ".bms" : in_folder(a_.bms_file);
+        dnafiles::load_binary(bst_file_, stn_, bst_meta_);
+        dnafiles::load_binary(bms_file_, msr_, bms_meta_);
+        if (a_.adjust_mode != SimultaneousMode)
+            dnafiles::load_seg(a_.seg_file.empty() ? base + ".seg" : in_folder(a_.seg_file), seg_);
+        ReportHeader h{};
+        std::ifstream rva(StagePath("rva"), std::ios::binary);
+        if (!rva || !rva.read(reinterpret_cast<char*>(&h), sizeof(h)) || std::memcmp(h.tag, "GADJRVA1", 8) != 0)
+            SignalExceptionAdjustment("Report results: " + StagePath("rva") + " was not found or is not a variance file of this program.\n"
+                                      "  Run an adjustment first.");
+        if (h.nstn != stn_.size() || h.nmsr != msr_.size())
+            SignalExceptionAdjustment("Report results: " + StagePath("rva") + " does not belong to the binary station and measurement files.");
+        raw_vcv_.resize(9 * stn_.size());
+        rva.read(reinterpret_cast<char*>(raw_vcv_.data()), (std::streamsize)(raw_vcv_.size() * sizeof(double)));
+        if (!rva)
+            SignalExceptionAdjustment("Report results: " + StagePath("rva") + " is truncated.");
+        stats_ = h.stats;
+        chiLower_ = h.chi_lower, chiUpper_ = h.chi_upper, maxCorr_ = h.max_corr, total_ms_ = h.total_ms;
+        passFail_ = h.pass_fail, adjustStatus_ = (ADJUST_STATUS)h.status, last_iterations_ = (uint32_t)h.iterations;
+        ReportHeader hp{};
+        std::ifstream pam(StagePath("pam"), std::ios::binary);
+        if (pam && pam.read(reinterpret_cast<char*>(&hp), sizeof(hp)) && std::memcmp(hp.tag, "GADJPAM1", 8) == 0 && hp.nmsr == msr_.size()) {
+            pam_rec_.resize(hp.nstn);
+            pam_.resize(6 * hp.nstn);
+            pam.read(reinterpret_cast<char*>(pam_rec_.data()), (std::streamsize)(pam_rec_.size() * sizeof(uint32_t)));
+            pam.read(reinterpret_cast<char*>(pam_.data()), (std::streamsize)(pam_.size() * sizeof(double)));
+            if (!pam)
+                pam_rec_.clear(), pam_.clear();
+        }
+        const gadj::Ellipsoid ell = Ellipsoid();
+        est_.resize(3 * stn_.size());
+        apriori_llh_.resize(3 * stn_.size());
+        for (size_t i = 0; i < stn_.size(); ++i) {
+            gadj::geo_to_cart(ell, stn_[i].currentLatitude, stn_[i].currentLongitude, stn_[i].currentHeight, &est_[3 * i]);
+            apriori_llh_[3 * i] = stn_[i].currentLatitude;
+            apriori_llh_[3 * i + 1] = stn_[i].currentLongitude;
+            apriori_llh_[3 * i + 2] = stn_[i].currentHeight;
+        }
+        apriori_xyz_ = est_;
+        vcv_ = raw_vcv_;
+        ApplyTypeBUncertainties();
+        info_.nstations = (uint32_t)stn_.size();
+        info_.nfronts = 0;
+    }
+    bool ReportMode() const { return report_mode_; }
 
     // ---- DNA / DynaML exports of the adjusted stations (PrintEstimatedStationCoordinatestoDNAXML PRN:2775-2903;
     // WriteDNAStn / WriteDynaMLStn dnastation.cpp:825-886): <adj file>.stn and <adj file>.stn.xml, stations in the order
@@ -713,7 +861,7 @@ class dna_adjust {
             double az = tiny ? 0.0 : direction_en(e, n);
             const double sd = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
             snprintf(buf, sizeof(buf), "%-20s%2s%19s%19s%19.4f%19.4f%11.4f%11.4f%11.4f", s.stationName, "",
-                     FormatDmsString(rad_to_dms(az)).c_str(), FormatDmsString(rad_to_dms(va)).c_str(), sd, hd, e, n, u);
+                     AngleString(az, 0, 0, 0).c_str(), AngleString(va, 0, 0, 0).c_str(), sd, hd, e, n, u);   // "ddd mm ss", carries exact
             os << buf << "\n";
         }
         os << "\n";
@@ -1150,7 +1298,8 @@ class dna_adjust {
         const std::string dash(80, '-');
         auto var = [&](const char* n) -> std::ostream& { return os << std::left << std::setw(35) << n; };
         os << "\n" << dash << "\n";
-        var("SOLUTION") << (adjustStatus_ == ADJUST_SUCCESS ? "Converged" : "Failed to converge after maximum iterations") << "\n";
+        var("SOLUTION") << (report_mode_ ? "Printing results of last adjustment only"
+                                         : (adjustStatus_ == ADJUST_SUCCESS ? "Converged" : "Failed to converge after maximum iterations")) << "\n";
         char buf[64];
         snprintf(buf, sizeof(buf), "00:00:%09.6f", total_ms_ / 1e3);
         var("Total time") << buf << "\n\n";
@@ -1495,7 +1644,8 @@ class dna_adjust {
     // adjusted coordinates, difference, measurement SD and pre-adjustment correction of every ignored measurement
     void PrintIgnoredAdjMeasurements(std::ostream& os)
     {
-        check(gadj_update_ignored_measurements(ctx_));
+        if (ctx_)   // report mode prints what the last adjustment left in the records
+            check(gadj_update_ignored_measurements(ctx_));
         PrintMsrTableHeader(os, "Ignored Measurements (a-posteriori)", 1);
         PrintMeasurementRecords(os, CollectMeasurements(nullptr, -1, true), 1);
         os << "\n\n";
@@ -1658,12 +1808,8 @@ class dna_adjust {
         const dna_msr_t* r = &msr_[i];
         const dna_stn_t &s1 = stn_[r->station1], &s2 = stn_[r->station2];
         double Vm[9] = {r[0].term2, r[1].term2, r[2].term2, r[1].term2, r[1].term3, r[2].term3, r[2].term2, r[2].term3, r[2].term4};
-        double Va[9], q12[9];
-        check_const(gadj_get_vcv_block(ctx_, r->station1, r->station2, q12));
-        for (int a = 0; a < 3; ++a)
-            for (int b = 0; b < 3; ++b)
-                Va[3 * a + b] = raw_vcv_[9 * (size_t)r->station1 + 3 * a + b] + raw_vcv_[9 * (size_t)r->station2 + 3 * a + b] - q12[3 * a + b] -
-                                q12[3 * b + a];
+        double Va[9];
+        BaselinePrecision(i, Va);
         const double meas[3] = {r[0].term1, r[1].term1, r[2].term1}, adjm[3] = {r[0].measAdj, r[1].measAdj, r[2].measAdj};
         double R1[9], Rm[9];
         local_rotation(s1.currentLatitude, s1.currentLongitude, R1);
@@ -1964,7 +2110,7 @@ class dna_adjust {
                 const double d[3] = {est_[3 * (size_t)i] - o[0], est_[3 * (size_t)i + 1] - o[1], est_[3 * (size_t)i + 2] - o[2]};
                 os << "  ";
                 for (int k = 0; k < 3; ++k)
-                    os << Fixed(R[k] * d[0] + R[3 + k] * d[1] + R[6 + k] * d[2], 11, pl);
+                    os << Fixed(removeNegativeZero(R[k] * d[0] + R[3 + k] * d[1] + R[6 + k] * d[2], pl), 11, pl);
             }
             os << "  " << s.description << "\n";
         }
@@ -2061,6 +2207,10 @@ class dna_adjust {
     std::vector<gadj_iter_result> iterations_;
     std::vector<std::string> iter_pre_, iter_post_;   // per-iteration report text (--output-iter-*)
     std::vector<double> est_, vcv_, raw_vcv_, apriori_llh_, apriori_xyz_;
+    std::vector<uint32_t> pam_rec_;     // first records of the G / X baselines, ascending
+    std::vector<double> pam_;           // 6 per baseline: upper triangle of the variance of the adjusted baseline
+    bool report_mode_ = false;
+    uint32_t last_iterations_ = 0;
     double maxCorr_ = 0, total_ms_ = 0, chiUpper_ = 0, chiLower_ = 0;
     int passFail_ = 0;
     ADJUST_STATUS adjustStatus_ = ADJUST_SUCCESS;

@@ -128,6 +128,10 @@ static int apply_option(adjust_settings& s, bool& quiet, const std::string& n, c
         s.vt_corr_threshold = std::atof(value.c_str());
     else if (n == "output-all-covariances")
         s.output_pu_covariances = true;
+    else if (n == "report-results")
+        s.report_results = true;
+    else if (n == "stage-path")
+        s.stage_path = value;
     else if (n == "network-name")
         s.network_name = value;
     else if (n == "binary-stn-file")
@@ -323,6 +327,13 @@ int main(int argc, char** argv)
     }
     try {
         dna_adjust adj;
+        if (s.report_results || s.max_iterations < 1) {   // WRAP:607-614
+            if (!quiet)
+                std::cout << "+ Report last adjustment results\n";
+            adj.LoadLastAdjustment(s);
+            adj.PrintAdjustedNetwork();
+            return EXIT_SUCCESS;
+        }
         if (!quiet)
             std::cout << "+ Preparing for adjustment... " << std::flush;
         adj.PrepareAdjustment(s);
@@ -331,6 +342,7 @@ int main(int argc, char** argv)
                       << " fronts)...\n";
         ADJUST_STATUS st = adj.AdjustNetwork();
         adj.GenerateStatistics();
+        adj.SerialiseAdjustedVarianceMatrices();   // <net>-rva.mtx / -pam.mtx for --report-results (WRAP:1397-1399)
         adj.PrintAdjustedNetwork();
         if (s.update_binary_files)
             adj.UpdateBinaryFiles();

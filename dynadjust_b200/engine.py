@@ -58,12 +58,12 @@ class GadjProfile(C.Structure):
 
 
 EXPORTS = ["gadj_default_opts", "gadj_create", "gadj_destroy", "gadj_last_error", "gadj_set_stations",
-           "gadj_set_measurements", "gadj_set_blocks", "gadj_prepare", "gadj_get_info", "gadj_upload_measurements",
+           "gadj_set_measurements", "gadj_set_measurements_reduced", "gadj_set_blocks", "gadj_prepare", "gadj_get_info", "gadj_upload_measurements",
            "gadj_upload_measurements_range",
            "gadj_reset_estimates", "gadj_iterate", "gadj_form_inverse", "gadj_adjust", "gadj_statistics",
            "gadj_update_ignored_measurements", "gadj_compute_measurements", "gadj_get_estimates",
            "gadj_get_corrections", "gadj_get_station_vcvs", "gadj_get_station_vcv", "gadj_get_vcv_block",
-           "gadj_get_normals_block", "gadj_get_rhs", "gadj_get_block_vcv", "gadj_profile_enable", "gadj_profile_read", "gadj_test_gemm",
+           "gadj_get_normals_block", "gadj_get_rhs", "gadj_get_block_vcv", "gadj_get_pair_vcvs", "gadj_profile_enable", "gadj_profile_read", "gadj_test_gemm",
            "gadj_mg_init", "gadj_stage_begin", "gadj_stage_normals_pending", "gadj_stage_run", "gadj_stage_solve_begin",
            "gadj_stage_solve_end", "gadj_stage_apply", "gadj_stage_end", "gadj_stage_mark_inverse", "gadj_sync", "gadj_mg_buffer",
            "gadj_mg_top_fronts", "gadj_mg_extract_vcv"]
@@ -87,6 +87,7 @@ def load_library(path=None):
     L.gadj_destroy.argtypes = [vp]
     L.gadj_set_stations.argtypes = [vp, vp, u32]
     L.gadj_set_measurements.argtypes = [vp, vp, u64]
+    L.gadj_set_measurements_reduced.argtypes = [vp, i32]
     L.gadj_set_blocks.argtypes = [vp, u32, vp, vp]
     L.gadj_prepare.argtypes = [vp]
     L.gadj_get_info.argtypes = [vp, C.POINTER(GadjInfo)]
@@ -105,6 +106,7 @@ def load_library(path=None):
     L.gadj_get_station_vcv.argtypes = [vp, u32, vp]
     L.gadj_get_vcv_block.argtypes = [vp, u32, u32, vp]
     L.gadj_get_block_vcv.argtypes = [vp, u32, vp, vp, u32, vp]
+    L.gadj_get_pair_vcvs.argtypes = [vp, C.c_uint64, vp, vp, vp]
     L.gadj_get_normals_block.argtypes = [vp, u32, u32, vp]
     L.gadj_get_rhs.argtypes = [vp, vp]
     L.gadj_profile_enable.argtypes = [vp, i32]
@@ -181,10 +183,12 @@ class Adjustment:
         self.stn = stn
         self._check(self.L.gadj_set_stations(self.h, self._p(stn), len(stn)))
 
-    def set_measurements(self, msr):
+    def set_measurements(self, msr, reduced=False):
+        """reduced: the records come from a measurement file an earlier adjustment has reduced (.bms metadata flag)."""
         assert msr.dtype == MSR_DTYPE and msr.flags.c_contiguous
         self.msr = msr
         self._check(self.L.gadj_set_measurements(self.h, self._p(msr), len(msr)))
+        self._check(self.L.gadj_set_measurements_reduced(self.h, 1 if reduced else 0))
 
     def set_blocks(self, inner_station_lists):
         """Chain segmentation as in a .seg file: one list of inner-station indices per block."""
@@ -255,6 +259,13 @@ class Adjustment:
     def vcv_block(self, si, sj):
         out = np.zeros((3, 3))
         self._check(self.L.gadj_get_vcv_block(self.h, si, sj, self._p(out)))
+        return out
+
+    def pair_vcvs(self, si, sj):
+        """Bulk vcv_block: (npairs, 3, 3) blocks of N^-1 at the station pairs (si[p], sj[p]) of the stored pattern."""
+        si, sj = np.ascontiguousarray(si, np.uint32), np.ascontiguousarray(sj, np.uint32)
+        out = np.zeros((len(si), 3, 3))
+        self._check(self.L.gadj_get_pair_vcvs(self.h, len(si), self._p(si), self._p(sj), self._p(out)))
         return out
 
     def normals_block(self, si, sj):

@@ -119,6 +119,11 @@ const char* gadj_last_error(const gadj_ctx* c);   /* c may be NULL: error of the
 /* borrowed: the arrays must outlive the context (or the next set_* call) */
 int gadj_set_stations(gadj_ctx* c, dna_stn_t* stn, uint32_t count);
 int gadj_set_measurements(gadj_ctx* c, dna_msr_t* msr, uint64_t count);
+/* Tell the library that the measurement file was reduced by an earlier adjustment (the `reduced` flag of the .bms
+ * metadata; isFirstTimeAdjustment_ ADJ:296, InitialiseMeasurement ADJ:3913-3935): measured values are restored from
+ * preAdjMeas before the reductions, and the one-off steps (variance scaling of GNSS measurements, conversion of
+ * latitude / longitude / height point clusters) are not repeated.  Call between gadj_set_measurements and gadj_prepare. */
+int gadj_set_measurements_reduced(gadj_ctx* c, int reduced);
 /* optional chain segmentation (.seg): block b's inner stations are isl[isl_off[b] .. isl_off[b+1]) */
 int gadj_set_blocks(gadj_ctx* c, uint32_t nblocks, const uint32_t* isl_off, const uint32_t* isl);
 
@@ -161,6 +166,10 @@ int gadj_get_vcv_block(gadj_ctx* c, uint32_t si, uint32_t sj, double q[9]);
  * read by the SINEX / covariance printers).  *nstations receives the station count n; when `stations` (capacity cap >= n)
  * and `packed_lower` (3n(3n+1)/2 doubles) are given they receive the station indices in matrix order and the matrix in
  * the reference's packed-lower column-major layout, idx(i,j) = j*3n - j(j-1)/2 + (i-j), i >= j (MATH:363-369). */
+/* Bulk form of gadj_get_vcv_block: q[9*p .. 9*p+8] = the 3x3 block of N^-1 at (si[p], sj[p]) for npairs station pairs of the
+ * stored pattern (si == sj: the station block), with one device -> host copy.  Used for the precisions of adjusted
+ * baselines in alternate units and the -pam.mtx file (v_precAdjMsrsFull_, ADJ:7784-8060, 6770-6799). */
+int gadj_get_pair_vcvs(gadj_ctx* c, uint64_t npairs, const uint32_t* si, const uint32_t* sj, double* q);
 int gadj_get_block_vcv(gadj_ctx* c, uint32_t block, uint32_t* nstations, uint32_t* stations, uint32_t cap, double* packed_lower);
 /* assembled normals (constraints included) of the last iterate call that built them, and its right-hand side */
 int gadj_get_normals_block(gadj_ctx* c, uint32_t si, uint32_t sj, double n[9]);

@@ -334,7 +334,7 @@ def test_cli_project_file_and_short_options(cli_hostsim, tmp_path):
     r = subprocess.run([cli_hostsim, "--max-iterations", "1", "-p", os.path.join(tmp_path, "pj.dnaproj"), "--output-corrections-file"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout == "", r.stderr + r.stdout
-    assert sorted(os.listdir(out)) == ["pj.phased-mt.adj", "pj.phased-mt.xyz"]
+    assert sorted(os.listdir(out)) == ["pj-pam.mtx", "pj-rva.mtx", "pj.phased-mt.adj", "pj.phased-mt.xyz"]
     text = open(os.path.join(out, "pj.phased-mt.adj")).read()
     assert "Adjusted Measurements" in text and re.search(r"^SOLUTION\s+Converged", text, re.M)
     head = _tables(text, "Adjusted Coordinates")[-1][0].split()
@@ -349,3 +349,68 @@ def test_cli_project_file_and_short_options(cli_hostsim, tmp_path):
     assert os.path.exists(os.path.join(out, "pj.phased-stage.adj"))
     r = subprocess.run([cli_hostsim, "-x"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "unrecognised option" in r.stderr
+
+
+def test_cli_report_results(cli_hostsim, tmp_path):
+    """--report-results (WRAP:607-614; SerialiseAdjustedVarianceMatrices ADJ:6770-6799): after an adjustment has updated the
+    binary files and written <net>-rva.mtx / <net>-pam.mtx, every report is printed again without solving — same numbers,
+    other layout options allowed."""
+    stn, msr, _, _ = st.terrestrial_network(50, 140, 61, scalars={"S": 20, "A": 8, "L": 8, "V": 6, "H": 4, "E": 3, "M": 3}, n_dir_sets=4, n_x=1, n_y=1,
+                                            v_scale=1.7)
+    g = np.where(msr["measType"] == b"G")[0]
+    msr["scale4"][g[:30]] = 2.5                    # variance scalars on some baselines: applied once, on the first run only
+    _write_network(tmp_path, "rr", stn, msr)
+    flags = ["--output-adj-msr", "--output-pos-uncertainty", "--output-corrections-file", "--output-tstat-adj-msr", "--stn-corrections"]
+    r = _run(cli_hostsim, tmp_path, "rr", *flags)
+    assert r.returncode == 0, r.stderr
+    first = {e: open(os.path.join(tmp_path, "rr.simult." + e)).read() for e in ("adj", "xyz", "apu", "cor")}
+    for e in first:
+        os.remove(os.path.join(tmp_path, "rr.simult." + e))
+    assert os.path.getsize(os.path.join(tmp_path, "rr-rva.mtx")) > 72 * 50 and os.path.exists(os.path.join(tmp_path, "rr-pam.mtx"))
+    r = _run(cli_hostsim, tmp_path, "rr", "--report-results", *flags)
+    assert r.returncode == 0 and "Report last adjustment results" in r.stdout, r.stderr
+    again = {e: open(os.path.join(tmp_path, "rr.simult." + e)).read() for e in ("adj", "xyz", "apu", "cor")}
+    assert "Printing results of last adjustment only" in again["adj"] and "ITERATION" not in again["adj"]
+    body = lambda t, h: [l for tab in _tables(t, h) for l in tab[1]]
+
+    def same(a, b, loose=False):   # the estimates come back through latitude / longitude / height: one unit of the last printed digit
+        assert len(a) == len(b)
+        for la, lb in zip(a, b):
+            fa, fb = la.split(), lb.split()
+            assert len(fa) == len(fb), (la, lb)
+            for x, y in zip(fa, fb):
+                if x != y:
+                    tol = 1.1 if "." not in x else (0.011 if len(x.split(".")[1]) == 2 else 1.1e-4)   # whole seconds of the .cor angles
+                    if loose:      # deflection corrections are re-evaluated at the adjusted coordinates
+                        tol *= 30
+                    assert abs(float(x) - float(y)) < tol, (la, lb)
+    assert body(again["adj"], "Adjusted Measurements") == body(first["adj"], "Adjusted Measurements")
+    same(body(again["adj"], "Adjusted Coordinates"), body(first["adj"], "Adjusted Coordinates"))
+    same(body(again["xyz"], "Adjusted Coordinates"), body(first["xyz"], "Adjusted Coordinates"))
+    pick = lambda t: t.split("----------\n\n", 1)[1] if "----------\n\n" in t else t
+    assert again["apu"].split("Positional uncertainty of adjusted")[1] == first["apu"].split("Positional uncertainty of adjusted")[1]
+    same(again["cor"].split("Corrections to stations")[1].splitlines()[4:], first["cor"].split("Corrections to stations")[1].splitlines()[4:])
+    for label in ("Chi squared", "Rigorous Sigma Zero", "Degrees of freedom", "Number of measurements"):
+        assert re.findall(r"^" + label + r".*$", again["adj"], re.M) == re.findall(r"^" + label + r".*$", first["adj"], re.M)
+    # a second adjustment starts from the files the first one updated (metadata `reduced`): measured values are restored
+    # from preAdjMeas, geoid / deflection reductions and variance scalars are not applied twice (ADJ:296, 3913-3935)
+    r = _run(cli_hostsim, tmp_path, "rr", *flags)
+    assert r.returncode == 0, r.stderr
+    second = open(os.path.join(tmp_path, "rr.simult.adj")).read()
+    sig = lambda t: float(re.findall(r"^Rigorous Sigma Zero\s+(\S+)", t, re.M)[-1])
+    assert abs(sig(second) - sig(first["adj"])) < 2e-3
+    same([l.replace("*", " ") for l in body(second, "Adjusted Measurements")], [l.replace("*", " ") for l in body(first["adj"], "Adjusted Measurements")],
+         loose=True)
+    # baselines in east / north / up need the full precision of the adjusted baselines: -pam.mtx
+    r = _run(cli_hostsim, tmp_path, "rr", "--output-adj-msr", "--output-adj-gnss-units", "1", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    enu = body(open(os.path.join(tmp_path, "rr.simult.adj")).read(), "Adjusted Measurements")
+    r = _run(cli_hostsim, tmp_path, "rr", "--max-iterations", "0", "--output-adj-msr", "--output-adj-gnss-units", "1")
+    assert r.returncode == 0, r.stderr
+    # (the run above started from the adjusted files: same solution to rounding)
+    same([l.replace("*", " ") for l in body(open(os.path.join(tmp_path, "rr.simult.adj")).read(), "Adjusted Measurements")],
+         [l.replace("*", " ") for l in enu])
+    # without the files: a clear error
+    os.remove(os.path.join(tmp_path, "rr-rva.mtx"))
+    r = _run(cli_hostsim, tmp_path, "rr", "--report-results")
+    assert r.returncode == 1 and "Run an adjustment first" in r.stderr
