@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 from dynadjust_b200 import dnafiles, synth
+from dynadjust_b200.records import MSR_DTYPE
 from dynadjust_b200 import synth_terrestrial as st
 from tests import parity
 from tests.golden import dna_ascii
@@ -414,3 +415,54 @@ def test_cli_report_results(cli_hostsim, tmp_path):
     os.remove(os.path.join(tmp_path, "rr-rva.mtx"))
     r = _run(cli_hostsim, tmp_path, "rr", "--report-results")
     assert r.returncode == 1 and "Run an adjustment first" in r.stderr
+
+
+def test_cli_output_json(cli_hostsim, tmp_path):
+    """--output-json (DynAdjustJsonPrinter dnaadjust_json_printer.cpp): one JSON object per line beside the
+    .adj / .xyz / .apu / .cor reports, the same numbers at full precision, keys as the reference names them."""
+    import json
+    stn, msr, _ = _network()
+    _write_network(tmp_path, "js", stn, msr)
+    r = _run(cli_hostsim, tmp_path, "js", "--output-adj-msr", "--output-json", "--output-pos-uncertainty", "--output-corrections-file",
+             "--output-tstat-adj-msr")
+    assert r.returncode == 0, r.stderr
+    load = lambda e: [json.loads(l) for l in open(os.path.join(tmp_path, "js.simult." + e + ".jsonl"))]
+    adj, xyz, apu, cor = load("adj"), load("xyz"), load("apu"), load("cor")
+    for recs, kind in ((adj, "adj"), (xyz, "xyz"), (apu, "apu"), (cor, "cor")):
+        h = recs[0]["DnaAdjustmentReport"]
+        assert h["report"] == kind and h["type"] == "Adjustment" and h["referenceframe"] == "GDA2020"
+    raw = open(os.path.join(tmp_path, "js.simult.adj.jsonl")).readline()
+    assert raw.index('"epoch"') < raw.index('"referenceframe"') < raw.index('"report"') < raw.index('"type"') and ", " not in raw   # sorted keys, compact
+    text = open(os.path.join(tmp_path, "js.simult.adj")).read()
+    stt = adj[1]["DnaStatistics"]
+    assert f'{stt["chisq"]:.2f}' == re.search(r"^Chi squared\s+(\S+)", text, re.M).group(1)
+    assert f'{stt["sigma_zero"]:.3f}' == re.search(r"^Rigorous Sigma Zero\s+(\S+)", text, re.M).group(1)
+    assert stt["dof"] == int(re.search(r"^Degrees of freedom\s+(\S+)", text, re.M).group(1)) and stt["chisq_test"] in ("passed", "warning", "failed")
+    back = dnafiles.read_binary(os.path.join(tmp_path, "js.bms"), MSR_DTYPE)
+    back = back[0] if isinstance(back, tuple) else back
+    ms = [r["DnaMeasurement"] for r in adj if "DnaMeasurement" in r]
+    used = back[back["ignore"] == 0]
+    names = [n.decode() for n in stn["stationName"]]
+    assert len(ms) == int(((used["measStart"] == 0) & np.isin(used["measType"], [b"G"])).sum()) + 4 + 6 + \
+        int(np.isin(used["measType"], [b"S", b"A", b"L", b"V", b"H", b"E", b"M", b"B", b"K", b"Z"]).sum())
+    s = next(m for m in ms if m["Type"] == "S")
+    rec = used[(used["measType"] == b"S") & (used["station1"] == names.index(s["First"])) & (used["station2"] == names.index(s["Second"]))][0]
+    assert s["Value"] == rec["term1"] and s["Adjusted"] == rec["measAdj"] and s["Correction"] == rec["measCorr"] and s["NStat"] == rec["NStat"]
+    assert abs(s["TStat"] - s["NStat"] / np.sqrt(stt["sigma_zero"])) < 1e-12 and s["StdDev"] == np.sqrt(rec["term2"])
+    d = next(m for m in ms if m["Type"] == "D")
+    assert d["Total"] == len(d["Directions"]) and all("Target" in e for e in d["Directions"]) and abs(d["Directions"][0]["StdDev"] - 1.0) < 1e-9
+    x = next(m for m in ms if m["Type"] == "X")
+    assert x["Total"] == len(x["GPSBaseline"]) == len(x["Adjusted"]) and "GPSCovariance" in x["GPSBaseline"][0] and set(x["Adjusted"][0]) == {"X", "Y", "Z"}
+    g = next(m for m in ms if m["Type"] == "G")
+    assert set(g["Adjusted"]) == {"X", "Y", "Z"} and g["Total"] == 1                   # a single baseline collapses to one triple
+    y = next(m for m in ms if m["Type"] == "Y")
+    assert y["Coords"] == "XYZ" and "Second" not in y and "PointCovariance" in y["Clusterpoint"][0]
+    sx = {r["DnaStation"]["Name"]: r["DnaStation"] for r in xyz[1:]}
+    rows = {l.split()[0]: l.split() for l in _tables(open(os.path.join(tmp_path, "js.simult.xyz")).read(), "Adjusted Coordinates")[-1][1]}
+    for name, f in rows.items():
+        a, u = sx[name]["Adjusted"], sx[name]["Uncertainty"]
+        assert np.abs(np.array([a["X"], a["Y"], a["Z"]]) - [float(v) for v in f[6:9]]).max() < 5.1e-5
+        assert np.abs(np.array([u["SE"], u["SN"], u["SU"]]) - [float(v) for v in f[9:12]]).max() < 5.1e-5
+        assert abs(a["Lat"] - float(f[2])) < 1e-9 and np.array(u["VarianceCart"]).shape == (3, 3)
+    assert [r["DnaStation"]["Name"] for r in apu[1:]] == names and "HzPosU" in apu[1]["DnaStation"]["Uncertainty"]
+    assert set(cor[1]["DnaStation"]["Corrections"]) == {"dE", "dN", "dUp"} and len(cor) == len(stn) + 1
