@@ -343,16 +343,26 @@ int main(int argc, char** argv)
             std::cout << "done.\n+ Adjusting network (" << adj.Info().nstations << " stations, " << adj.Info().nfronts
                       << " fronts)...\n";
         ADJUST_STATUS st = adj.AdjustNetwork();
+        if (st == ADJUST_MAX_ITERATIONS_EXCEEDED) {
+            // no statistics or tables for an adjustment that ran out of iterations: the iterations, the status and the
+            // stations that kept swinging (WRAP:1386-1390)
+            adj.PrintFailedAdjustment();
+            if (!quiet)
+                std::cout << "+ Solution failed to converge after " << adj.CurrentIteration() << " iteration(s).\n";
+            adj.PrintOscillationSummary(std::cout);
+            return EXIT_SUCCESS;
+        }
         adj.GenerateStatistics();
         adj.SerialiseAdjustedVarianceMatrices();   // <net>-rva.mtx / -pam.mtx for --report-results (WRAP:1397-1399)
         adj.PrintAdjustedNetwork();
         if (s.update_binary_files)
             adj.UpdateBinaryFiles();
         if (!quiet) {
-            std::cout << "+ Solution " << (st == ADJUST_SUCCESS ? "converged" : "failed to converge") << " after "
-                      << adj.CurrentIteration() << " iteration(s).\n";
+            std::cout << "+ Solution converged after " << adj.CurrentIteration() << " iteration(s).\n";
             std::cout << "+ Chi squared " << adj.GetChiSquared() << ", degrees of freedom " << adj.GetDegreesOfFreedom()
                       << ", rigorous sigma zero " << adj.GetSigmaZero() << "\n";
+            adj.PrintOscillationSummary(std::cout);
+            adj.PrintSuspectMeasurementSummary(std::cout);   // WRAP:1442-1443
         }
         return EXIT_SUCCESS;   // ADJUST_SUCCESS even when not converged: the status is reported in the text (WRAP:133-147)
     } catch (const std::exception& e) {

@@ -466,3 +466,31 @@ def test_cli_output_json(cli_hostsim, tmp_path):
         assert abs(a["Lat"] - float(f[2])) < 1e-9 and np.array(u["VarianceCart"]).shape == (3, 3)
     assert [r["DnaStation"]["Name"] for r in apu[1:]] == names and "HzPosU" in apu[1]["DnaStation"]["Uncertainty"]
     assert set(cor[1]["DnaStation"]["Corrections"]) == {"dE", "dN", "dUp"} and len(cor) == len(stn) + 1
+
+
+def test_cli_non_convergence_and_suspect_summary(cli_hostsim, tmp_path):
+    """An adjustment that runs out of iterations reports its iterations and "Failed to converge" only — no statistics, no
+    tables (WRAP:1386-1390) — and still exits 0; a converged one lists the measurements beyond the critical n-statistic on
+    the console (PrintSuspectMeasurementSummary ADJ:7652-7779)."""
+    stn, msr, _, _ = synth.gnss_network(40, 110, 3)
+    _write_network(tmp_path, "nc", stn, msr)
+    r = _run(cli_hostsim, tmp_path, "nc", "--max-iterations", "1", "--output-adj-msr")
+    assert r.returncode == 0 and "failed to converge after 1 iteration" in r.stdout, r.stderr
+    text = open(os.path.join(tmp_path, "nc.simult.adj")).read()
+    assert re.search(r"^SOLUTION\s+Failed to converge", text, re.M) and len(re.findall(r"^ITERATION", text, re.M)) == 1
+    assert "Adjusted Coordinates" not in text and "Chi squared" not in text and "Adjusted Measurements" not in text
+    assert not os.path.exists(os.path.join(tmp_path, "nc-rva.mtx"))
+    back = dnafiles.read_binary(os.path.join(tmp_path, "nc.bst"), stn.dtype)
+    back = back[0] if isinstance(back, tuple) else back
+    assert np.array_equal(back["currentLatitude"], stn["currentLatitude"])      # the binary files are left as they were
+    r = _run(cli_hostsim, tmp_path, "nc", "--output-adj-msr")
+    assert r.returncode == 0, r.stderr
+    text = open(os.path.join(tmp_path, "nc.simult.adj")).read()
+    outliers = int(re.search(r"\((\d+) potential outlier", text).group(1))
+    m = re.search(r"\+ Largest measurement N-statistics \((\d+) total, showing top (\d+)\):", r.stdout)
+    assert m and int(m.group(1)) == outliers and int(m.group(2)) == min(outliers, 20)
+    rows = re.findall(r"^  - G msr (\d+) cluster \d+ file-order \d+ (\S+) -> (\S+): N=(-?\d+\.\d+), corr=\S+, residual precision=\S+, Pelzer=\S+, exceeds critical$",
+                      r.stdout, re.M)
+    assert len(rows) == min(outliers, 20)
+    ns = [abs(float(x[3])) for x in rows]
+    assert ns == sorted(ns, reverse=True) and min(ns) > 1.95
