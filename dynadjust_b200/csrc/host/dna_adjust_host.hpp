@@ -73,6 +73,7 @@ struct adjust_settings {            // the fields of project_settings.a / .g / .
     int precision_seconds_stn = 5, precision_metres_stn = 4, precision_seconds_msr = 4, precision_metres_msr = 4;
     bool iter_adj_stn = false, iter_adj_stat = false, iter_adj_msr = false, iter_cmp_msr = false;   // --output-iter-*
     bool output_ignored_msrs = false;      // --output-ignored-msrs
+    bool database_ids = false;             // --output-database-ids: measurement / cluster ids of <net>.dbid beside every row
     std::string comments;                  // --comments
     std::string command_line;
 };
@@ -96,6 +97,8 @@ class dna_adjust {
         dnafiles::load_binary(bst_file_, stn_, bst_meta_);
         dnafiles::load_binary(bms_file_, msr_, bms_meta_);
         ApplyConstraints();
+        if (a_.database_ids)
+            LoadDatabaseId();
         gadj_opts o;
         gadj_default_opts(&o);
         o.fixed_std_dev = a_.fixed_std_dev;
@@ -376,6 +379,8 @@ class dna_adjust {
         dnafiles::load_binary(bms_file_, msr_, bms_meta_);
         if (a_.adjust_mode != SimultaneousMode)
             dnafiles::load_seg(a_.seg_file.empty() ? base + ".seg" : in_folder(a_.seg_file), seg_);
+        if (a_.database_ids)
+            LoadDatabaseId();
         ReportHeader h{};
         std::ifstream rva(StagePath("rva"), std::ios::binary);
         if (!rva || !rva.read(reinterpret_cast<char*>(&h), sizeof(h)) || std::memcmp(h.tag, "GADJRVA1", 8) != 0)
@@ -1489,13 +1494,32 @@ class dna_adjust {
         std::unordered_map<std::string, uint32_t> by_name;
         for (size_t i = 0; i < stn_.size(); ++i)
             by_name.emplace(stn_[i].stationName, (uint32_t)i);
+        // discontinuity sites (AddDiscontinuitySites LDR:314-359): when dnaimport renamed stations of a discontinuity file
+        // (stationName differs from stationNameOrig), a constraint given for the original name also goes to its renamed
+        // sites, and a name that no longer exists is passed over instead of being an error (LDR:246-249)
+        bool discontinuities = false;
+        for (const dna_stn_t& st : stn_)
+            if (st.stationNameOrig[0] && std::strncmp(st.stationName, st.stationNameOrig, sizeof(st.stationName)) != 0)
+                discontinuities = true;
+        if (discontinuities) {
+            const size_t given = tok.size();
+            for (size_t k = 0; k + 1 < given; k += 2)
+                for (const dna_stn_t& st : stn_)
+                    if (tok[k] == st.stationNameOrig && tok[k] != st.stationName) {
+                        tok.push_back(st.stationName);
+                        tok.push_back(tok[k + 1]);
+                    }
+        }
         for (size_t k = 0; k + 1 < tok.size(); k += 2) {
             std::string c = tok[k + 1];
             for (char& ch : c)
                 ch = (char)std::toupper((unsigned char)ch);
             auto it = by_name.find(tok[k]);
-            if (it == by_name.end())
+            if (it == by_name.end()) {
+                if (discontinuities)
+                    continue;
                 SignalExceptionAdjustment("The supplied constraint station '" + tok[k] + "' is not in the stations map");
+            }
             if (c.size() != 3 || c.find_first_not_of("CF") != std::string::npos)   // CDnaStation::IsValidConstraint
                 SignalExceptionAdjustment("Invalid station constraint: '" + tok[k + 1] + "'");
             snprintf(stn_[it->second].stationConst, sizeof(stn_[it->second].stationConst), "%s", c.c_str());
@@ -2043,6 +2067,7 @@ class dna_adjust {
         double measured, adjusted, corr, var, adj_prec, res_prec, nstat, tstat, pelzer, pre_adj_corr;
         bool pre_adj_corr_linear;   // the H row of a geographic Y cluster prints its N value in metres
         bool show_type;
+        int64_t rec;                // binary record the row belongs to (database ids)
     };
 
     void PrintMsrRow(std::ostream& os, const MsrRow& r, int mode /*0 adjusted, 1 computed / ignored*/) const
@@ -2083,7 +2108,54 @@ class dna_adjust {
             os << Fixed(removeNegativeZero(r.pre_adj_corr, pa), 14, pa);
         if (mode == 0)
             os << std::setw(12) << std::right << (std::fabs(r.nstat) > crit ? "*" : " ");
+        if (a_.database_ids && r.rec >= 0)
+            PrintMeasurementDatabaseID(os, (size_t)r.rec);
         os << "\n";
+    }
+
+    // measurement id, and for D G X Y the cluster id, of a record (PrintMeasurementDatabaseID PRN:239-263)
+    void PrintMeasurementDatabaseID(std::ostream& os, size_t rec) const
+    {
+        if (rec >= dbid_.size())
+            return;
+        const DbId& d = dbid_[rec];
+        if (d.msr_set)
+            os << std::setw(10) << std::right << d.msr_id;
+        else
+            os << std::setw(10) << " ";
+        if (std::strchr("DGXY", msr_[rec].measType)) {
+            if (d.cls_set)
+                os << std::setw(10) << std::right << d.cluster_id;
+            else
+                os << std::setw(10) << " ";
+        }
+    }
+    // <net>.dbid of dnaimport (LoadDatabaseId ADJ:2211-2276): u32 count, then per binary measurement record u32 measurement
+    // id, u32 cluster id, u16 / u16 "is set" flags
+    struct DbId {
+        uint32_t msr_id, cluster_id;
+        bool msr_set, cls_set;
+    };
+    void LoadDatabaseId()
+    {
+        const std::string file = a_.output_folder + "/" + a_.network_name + ".dbid";
+        std::ifstream in(file, std::ios::binary);
+        uint32_t count = 0;
+        if (!in || !in.read(reinterpret_cast<char*>(&count), sizeof(count)))
+            SignalExceptionAdjustment("LoadDatabaseId(): could not open " + file + " (written by dnaimport; needed for --output-database-ids)");
+        dbid_.resize(count);
+        for (uint32_t r = 0; r < count; ++r) {
+            uint16_t a = 0, b = 0;
+            in.read(reinterpret_cast<char*>(&dbid_[r].msr_id), 4);
+            in.read(reinterpret_cast<char*>(&dbid_[r].cluster_id), 4);
+            in.read(reinterpret_cast<char*>(&a), 2);
+            in.read(reinterpret_cast<char*>(&b), 2);
+            dbid_[r].msr_set = a != 0;
+            dbid_[r].cls_set = b != 0;
+        }
+        if (!in)
+            SignalExceptionAdjustment("LoadDatabaseId(): " + file + " is truncated");
+        a_.output_msr_blocks = false;   // ids go with one contiguous list in the original order (ADJ:2222-2226)
     }
 
     MsrRow ScalarRow(const dna_msr_t& m, char cardinal, double var) const
@@ -2107,6 +2179,7 @@ class dna_adjust {
         r.pre_adj_corr = m.preAdjCorr;
         r.pre_adj_corr_linear = false;
         r.show_type = true;
+        r.rec = (&m >= msr_.data() && &m < msr_.data() + msr_.size()) ? (int64_t)(&m - msr_.data()) : -1;
         return r;
     }
 
@@ -2133,6 +2206,10 @@ class dna_adjust {
         if (mode == 0) {
             os << std::setw(12) << "Outlier?";
             width += 12;
+        }
+        if (a_.database_ids) {
+            os << std::setw(10) << "Meas. ID" << std::setw(10) << "Clust. ID";
+            width += 20;
         }
         os << "\n" << std::string(width, '-') << "\n";
     }
@@ -2190,7 +2267,12 @@ class dna_adjust {
         char head[96];
         snprintf(head, sizeof(head), "%-2c%-20s%-20s%-20s%-3s%-2u", 'D', stn_[ro.station1].stationName, stn_[ro.station2].stationName, "",
                  ro.ignore ? "*" : " ", angles);
-        os << head << "\n";
+        os << head;
+        if (a_.database_ids) {
+            os << std::string(19 + 19 + 12 + 13 + (mode == 0 ? 13 + 13 + 11 + (a_.adj_msr_tstat ? 11 : 0) + 12 : 0) + 14 + (mode == 0 ? 12 : 0), ' ');
+            PrintMeasurementDatabaseID(os, first);
+        }
+        os << "\n";
         uint32_t printed = 0;
         for (size_t j = first + 1; j < first + std::max<uint32_t>(1u, ro.vectorCount1) && j < msr_.size() && printed < angles; ++j) {
             const dna_msr_t& d = msr_[j];
@@ -2711,6 +2793,7 @@ class dna_adjust {
     dnafiles::Segmentation seg_;
     std::string bst_file_, bms_file_;
     std::vector<gadj_iter_result> iterations_;
+    std::vector<DbId> dbid_;
     std::vector<double> corrPrev_;
     std::vector<uint32_t> stnOscCount_;
     std::map<uint32_t, OscillationRecord> oscHistory_;

@@ -188,6 +188,8 @@ static int apply_option(adjust_settings& s, bool& quiet, const std::string& n, c
         s.output_ignored_msrs = true;
     else if (n == "comments")
         s.comments = value;
+    else if (n == "output-database-ids")
+        s.database_ids = true;
     else if (n == "output-json")
         s.output_json = true;
     else if (n == "export-xml-stn-file")

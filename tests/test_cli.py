@@ -244,6 +244,18 @@ def test_cli_constraints(cli_hostsim, oracle, tmp_path):
     assert r.returncode == 1 and "is not in the stations map" in r.stderr
     r = _run(cli_hostsim, tmp_path, "cn", "--constraints", f"{n1},CXC")
     assert r.returncode == 1 and "Invalid station constraint" in r.stderr
+    # discontinuity sites (LDR:314-359): dnaimport renamed two stations of a discontinuity file; a constraint given for the
+    # original name reaches the renamed sites, and the original name itself (no longer a station) is passed over
+    stn_d = stn.copy()
+    stn_d["stationNameOrig"][20] = stn_d["stationNameOrig"][21] = b"SITE"
+    stn_d["stationName"][20], stn_d["stationName"][21] = b"SITE_20100101", b"SITE_20150101"
+    _write_network(tmp_path, "cd", stn_d, msr)
+    r = _run(cli_hostsim, tmp_path, "cd", "--constraints", f"SITE,CCF,{n1},CCC", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    stn_c = stn_d.copy()
+    stn_c["stationConst"][[20, 21]] = b"CCF"
+    stn_c["stationConst"][7] = b"CCC"
+    _check_outputs(oracle, tmp_path, "cd", "simult", stn_c, msr, False)
 
 
 def test_cli_block_outputs(cli_hostsim, oracle, tmp_path):

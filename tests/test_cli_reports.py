@@ -494,3 +494,42 @@ def test_cli_non_convergence_and_suspect_summary(cli_hostsim, tmp_path):
     assert len(rows) == min(outliers, 20)
     ns = [abs(float(x[3])) for x in rows]
     assert ns == sorted(ns, reverse=True) and min(ns) > 1.95
+
+
+def test_cli_database_ids(cli_hostsim, tmp_path):
+    """--output-database-ids (LoadDatabaseId ADJ:2211-2276, PrintMeasurementDatabaseID PRN:239-263): the measurement id of
+    <net>.dbid beside every row, the cluster id as well for D G X Y; one list in file order whatever --output-msr-blocks says."""
+    stn, msr, _ = _network()
+    _write_network(tmp_path, "db", stn, msr)
+    n = len(msr)
+    ids = np.zeros(n, dtype=[("m", "<u4"), ("c", "<u4"), ("ms", "<u2"), ("cs", "<u2")])
+    ids["m"], ids["c"], ids["ms"], ids["cs"] = 100000 + np.arange(n), 5000 + msr["clusterID"], 1, 1
+    with open(os.path.join(tmp_path, "db.dbid"), "wb") as f:
+        f.write(np.uint32(n).tobytes() + ids.tobytes())
+    r = _run(cli_hostsim, tmp_path, "db", "--output-adj-msr", "--output-database-ids", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    head, body = _tables(open(os.path.join(tmp_path, "db.simult.adj")).read(), "Adjusted Measurements")[-1]
+    assert head.split()[-4:] == ["Meas.", "ID", "Clust.", "ID"]
+    used = np.where((msr["ignore"] == 0) & (msr["measStart"] <= 2))[0]
+    k = 0
+    for l in body:
+        f = l.split()
+        if l[0] == "D" and len(f) == 6:                      # heading row: D inst RO count, ids of the set's first record
+            rec = used[k]
+            assert msr["measType"][rec] == b"D" and int(f[-2]) == 100000 + rec and int(f[-1]) == 5000 + msr["clusterID"][rec]
+            k += 1
+            continue
+        rec = used[k]
+        while msr["measType"][rec] == b"D" and msr["vectorCount1"][rec] > 0:
+            k += 1
+            rec = used[k]
+        t = chr(msr["measType"][rec][0])
+        if t in "DGXY":
+            assert int(f[-2]) == 100000 + rec and int(f[-1]) == 5000 + msr["clusterID"][rec], (l, rec)
+        else:
+            assert int(f[-1]) == 100000 + rec and not f[-2].isdigit() or f[-2] == "*", (l, rec)
+        k += 1
+    assert k == len(used)
+    os.remove(os.path.join(tmp_path, "db.dbid"))
+    r = _run(cli_hostsim, tmp_path, "db", "--output-adj-msr", "--output-database-ids", "--no-binary-update")
+    assert r.returncode == 1 and "dbid" in r.stderr
