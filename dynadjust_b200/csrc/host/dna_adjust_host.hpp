@@ -241,8 +241,6 @@ class dna_adjust {
         const std::string stem = a_.output_folder + "/" + a_.network_name + "." + ModeSuffix();
         std::ofstream adj(stem + ".adj");
         PrintOutputFileHeaderInfo(adj, "DYNADJUST ADJUSTMENT OUTPUT FILE", stem + ".adj");
-        if (!a_.comments.empty())
-            adj << "\n" << std::left << std::setw(35) << "Comments:" << a_.comments << "\n";
         if (report_mode_)
             adj << "\n+ Loading network files\n+ Printing results of the last adjustment\n\n";
         else {
@@ -1769,12 +1767,13 @@ class dna_adjust {
         os << "\n";
         var("Stations file:", bst_file_);
         var("Measurements file:", bms_file_);
-        var("Reference frame:", std::string("EPSG ") + bst_meta_.epsgCode);
+        var("Reference frame:", frame_name());
         var("Epoch:", bst_meta_.epoch);
+        var("Geoid model:", "");
+        if (a_.adjust_mode != SimultaneousMode)
+            var("Segmentation file:", a_.seg_file.empty() ? a_.input_folder + "/" + a_.network_name + ".seg" : a_.seg_file);
         std::ostringstream t;
         t << a_.fixed_std_dev;
-        if (!a_.station_constraints.empty())
-            var("Station constraints:", a_.station_constraints);   // PRN:3490
         var("Constrained Station S.D. (m):", t.str());
         t.str("");
         t << a_.free_std_dev;
@@ -1787,8 +1786,39 @@ class dna_adjust {
         t << std::fixed << std::setprecision(1) << a_.confidence_interval << "%";
         var("Test confidence interval:", t.str());
         var("Uncertainties SD(e,n,up):", "68.3% (1 sigma)");
-        var("Station coordinate types:", "PLHhXYZ");
-        var("Stations printed in blocks:", "No");
+        if (!a_.station_constraints.empty())
+            var("Station constraints:", a_.station_constraints);   // PRN:3490
+        var("Station coordinate types:", a_.stn_coord_types);
+        var("Stations printed in blocks:", a_.adjust_mode != SimultaneousMode && a_.output_stn_blocks ? "Yes" : "No");
+        if (a_.stn_corrections)
+            var("Station coordinate corrections:", "Yes");
+        if (!a_.type_b_global.empty())
+            var("Type B uncertainties:", a_.type_b_global);
+        if (!a_.type_b_file.empty())
+            var("Type B uncertainty file:", a_.type_b_file);
+        // user comments, wrapped at word breaks to the value column ("\n" in the text starts a new line) (PRN:3540-3592)
+        if (!a_.comments.empty()) {
+            std::string text = a_.comments, label = "Comments: ";
+            for (size_t p2; (p2 = text.find("\\n")) != std::string::npos;)
+                text.replace(p2, 2, "\n");
+            std::istringstream lines(text);
+            for (std::string ln; std::getline(lines, ln);) {
+                while (!ln.empty() && ln[0] == ' ')
+                    ln.erase(0, 1);
+                while (ln.size() > 45) {
+                    size_t cut = ln.rfind(' ', 45);
+                    if (cut == std::string::npos || cut == 0)
+                        cut = 45;
+                    var(label.c_str(), ln.substr(0, cut));
+                    label = " ";
+                    ln.erase(0, cut);
+                    while (!ln.empty() && ln[0] == ' ')
+                        ln.erase(0, 1);
+                }
+                var(label.c_str(), ln);
+                label = " ";
+            }
+        }
         t.str("");
         t << info_.nfronts << " fronts on " << info_.nlevels << " levels (supernodal Cholesky on B200)";
         var("Elimination tree:", t.str());
