@@ -58,6 +58,7 @@ struct adjust_settings {            // the fields of project_settings.a / .g / .
     bool output_pu_covariances = false;    // --output-all-covariances: covariance blocks between the stations of a block in the .apu
     double hz_corr_threshold = 0.0, vt_corr_threshold = 0.0;   // dnaoptions.hpp:510
     bool update_binary_files = true;
+    bool update_project_file = true;       // <net>.dnaproj is rewritten with the settings of the run (WRAP:1456-1466)
     std::string type_b_global, type_b_file; // --type-b-sd-global "e,n,up" (metres, 1 sigma), --type-b-sd-file <file> (dnaoptions-interface.hpp)
     std::string station_constraints;       // --constraints "STN1,CCC,STN2,FFC" (dnaoptions.hpp:481)
     // report layout (output_settings, dnaoptions.hpp:496-516)

@@ -7,7 +7,9 @@
 #include <cctype>
 #include <cstring>
 #include <fstream>
+#include <iomanip>
 #include <iostream>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -143,7 +145,7 @@ static int apply_option(adjust_settings& s, bool& quiet, const std::string& n, c
     else if (n == "quiet")
         quiet = true;
     else if (n == "no-binary-update")
-        s.update_binary_files = false;
+        s.update_binary_files = s.update_project_file = false;
     else if (n == "constraints")
         s.station_constraints = value;
     else if (n == "sort-adj-msr-field")
@@ -260,6 +262,130 @@ static int load_project_file(const std::string& file, adjust_settings& s, bool& 
     return 0;
 }
 
+// After an adjustment the project file carries the settings it ran with (CDnaProjectFile::UpdateSettingsAdjust /
+// UpdateSettingsOutput / PrintProjectFile, dnaprojectfile.cpp:1703-2027; WRAP:1456-1466): the #adjust and #output sections
+// are rewritten, the sections of the other programs of the suite are kept as they are.
+static void update_project_file(const adjust_settings& s)
+{
+    const std::string file = s.output_folder + "/" + s.network_name + ".dnaproj";
+    std::vector<std::pair<std::string, std::string>> sections;   // name, text (header line included)
+    std::string preamble;
+    {
+        std::ifstream in(file);
+        std::string line;
+        while (in && std::getline(in, line)) {
+            if (line.size() > 1 && line[0] == '#' && line[1] != ' ')
+                sections.emplace_back(line.substr(0, line.find(' ')), std::string());
+            if (sections.empty())
+                preamble += line + "\n";
+            else
+                sections.back().second += line + "\n";
+        }
+    }
+    std::ostringstream adj, out;
+    const std::string dash(80, '-');
+    auto rec = [](std::ostream& os, const std::string& k, const std::string& v) { os << std::left << std::setw(35) << k << std::setw(45) << v << "\n"; };
+    auto yn = [](bool b) { return std::string(b ? "yes" : "no"); };
+    auto num = [](double v, int prec, bool sci = false) {
+        std::ostringstream t;
+        t << (sci ? std::scientific : std::fixed) << std::setprecision(prec) << v;
+        return t.str();
+    };
+    auto plain = [](double v) {
+        std::ostringstream t;
+        t << v;
+        return t.str();
+    };
+    rec(adj, "#adjust (35)", "VALUE");
+    adj << dash << "\n";
+    rec(adj, "seg-file", s.seg_file.empty() && s.adjust_mode != SimultaneousMode ? s.network_name + ".seg" : s.seg_file);
+    rec(adj, "comments", s.comments);
+    rec(adj, "adjustment-mode", s.adjust_mode == PhasedMode ? "phased-adjustment" : (s.adjust_mode == Phased_Block_1Mode ? "block1-phased" : "simultaneous-adjustment"));
+    rec(adj, "multi-thread", yn(s.multi_thread));
+    rec(adj, "staged-adjustment", yn(s.stage));
+    rec(adj, "conf-interval", plain(s.confidence_interval));
+    rec(adj, "iteration-threshold", plain((float)s.iteration_threshold));
+    rec(adj, "max-iterations", std::to_string(s.max_iterations));
+    rec(adj, "constraints", s.station_constraints);
+    rec(adj, "free-stn-sd", num(s.free_std_dev, 3));
+    rec(adj, "fixed-stn-sd", num(s.fixed_std_dev, 4, true));
+    rec(adj, "scale-normals-to-unity", yn(s.scale_normals_to_unity));
+    rec(adj, "create-stage-files", "no");
+    rec(adj, "purge-stage-files", "no");
+    rec(adj, "type-b-sd-global", s.type_b_global);
+    rec(adj, "type-b-sd-file", s.type_b_file);
+    adj << "\n";
+    rec(out, "#output (35)", "VALUE");
+    out << dash << "\n";
+    rec(out, "output-msr-to-stn", yn(s.output_msr_to_stn));
+    rec(out, "sort-msr-to-stn-field", std::to_string(s.sort_msr_to_stn));
+    rec(out, "output-iter-adj-stn", yn(s.iter_adj_stn));
+    rec(out, "output-iter-adj-stat", yn(s.iter_adj_stat));
+    rec(out, "output-iter-adj-msr", yn(s.iter_adj_msr));
+    rec(out, "output-iter-cmp-msr", yn(s.iter_cmp_msr));
+    rec(out, "output-adj-msr", yn(s.output_adj_msr));
+    rec(out, "output-adj-gnss-units", std::to_string(s.adj_gnss_units));
+    rec(out, "output-tstat-adj-msr", yn(s.adj_msr_tstat));
+    rec(out, "sort-adj-msr-field", std::to_string(s.sort_adj_msr));
+    rec(out, "output-database-ids", yn(s.database_ids));
+    rec(out, "output-msr-blocks", yn(s.output_msr_blocks));
+    rec(out, "sort-stn-orig-order", yn(s.sort_stn_orig_order));
+    rec(out, "stn-coord-types", s.stn_coord_types);
+    rec(out, "angular-stn-type", std::to_string(s.angular_type_stn));
+    rec(out, "stn-corrections", yn(s.stn_corrections));
+    rec(out, "precision-stn-linear", std::to_string(s.precision_metres_stn));
+    rec(out, "precision-stn-angular", std::to_string(s.precision_seconds_stn));
+    rec(out, "precision-msr-linear", std::to_string(s.precision_metres_msr));
+    rec(out, "precision-msr-angular", std::to_string(s.precision_seconds_msr));
+    rec(out, "angular-msr-type", std::to_string(s.angular_type_msr));
+    rec(out, "dms-msr-format", std::to_string(s.dms_format_msr));
+    rec(out, "output-pos-uncertainty", yn(s.output_pos_uncertainty));
+    rec(out, "output-all-covariances", yn(s.output_pu_covariances));
+    rec(out, "output-apu-vcv-units", s.apu_vcv_enu ? "1" : "0");
+    rec(out, "output-corrections-file", yn(s.output_corrections));
+    rec(out, "hz-corr-threshold", num(s.hz_corr_threshold, 3));
+    rec(out, "vt-corr-threshold", num(s.vt_corr_threshold, 3));
+    rec(out, "export-xml-stn-file", yn(s.export_xml_stn));
+    rec(out, "export-dna-stn-file", yn(s.export_dna_stn));
+    rec(out, "export-sinex-file", yn(s.export_sinex));
+    out << "\n";
+    if (sections.empty()) {
+        std::ostringstream g;
+        preamble = "# " + s.network_name + " project file. Created by dnaadjust (dynadjust_b200).\n\n\n";
+        rec(g, "#general (35)", "VALUE");
+        g << dash << "\n";
+        rec(g, "network-name", s.network_name);
+        rec(g, "input-folder", s.input_folder);
+        rec(g, "output-folder", s.output_folder);
+        rec(g, "verbose-level", "0");
+        rec(g, "quiet", "no");
+        rec(g, "project-file", file);
+        g << "\n";
+        sections.emplace_back("#general", g.str());
+    }
+    bool has_adj = false, has_out = false;
+    for (auto& sec : sections) {
+        if (sec.first == "#adjust")
+            sec.second = adj.str(), has_adj = true;
+        if (sec.first == "#output")
+            sec.second = out.str(), has_out = true;
+    }
+    auto before_plot = [&](const std::string& name, const std::string& text) {
+        auto it = sections.begin();
+        while (it != sections.end() && it->first != "#plot" && it->first != "#display" && !(name == "#adjust" && it->first == "#output"))
+            ++it;
+        sections.insert(it, {name, text});
+    };
+    if (!has_adj)
+        before_plot("#adjust", adj.str());
+    if (!has_out)
+        before_plot("#output", out.str());
+    std::ofstream os(file);
+    os << preamble;
+    for (const auto& sec : sections)
+        os << sec.second;
+}
+
 int main(int argc, char** argv)
 {
     adjust_settings s;
@@ -365,7 +491,10 @@ int main(int argc, char** argv)
                       << ", rigorous sigma zero " << adj.GetSigmaZero() << "\n";
             adj.PrintOscillationSummary(std::cout);
             adj.PrintSuspectMeasurementSummary(std::cout);   // WRAP:1442-1443
+            std::cout << "\n+ Open " << s.network_name << "." << adj.ModeSuffix() << ".adj to view the adjustment details.\n\n";
         }
+        if (s.update_project_file)
+            update_project_file(s);
         return EXIT_SUCCESS;   // ADJUST_SUCCESS even when not converged: the status is reported in the text (WRAP:133-147)
     } catch (const std::exception& e) {
         std::cerr << "\n- Error: " << e.what() << "\n";

@@ -533,3 +533,34 @@ def test_cli_database_ids(cli_hostsim, tmp_path):
     os.remove(os.path.join(tmp_path, "db.dbid"))
     r = _run(cli_hostsim, tmp_path, "db", "--output-adj-msr", "--output-database-ids", "--no-binary-update")
     assert r.returncode == 1 and "dbid" in r.stderr
+
+
+def test_cli_writes_project_file(cli_hostsim, tmp_path):
+    """After an adjustment <net>.dnaproj holds the settings of the run (dnaprojectfile.cpp:1703-2027; WRAP:1456-1466): the
+    #adjust / #output sections are rewritten, sections of the other programs are kept, and `-p` on it repeats the run."""
+    stn, msr, _, _ = synth.gnss_network(40, 110, 19)
+    _write_network(tmp_path, "pw", stn, msr)
+    proj = os.path.join(tmp_path, "pw.dnaproj")
+    with open(proj, "w") as f:
+        f.write("# pw project file. Created by dnaimport.\n\n\n" + f"{'#general (35)':<35}VALUE\n" + "-" * 80 + "\n" + f"{'network-name':<35}pw\n" +
+                f"{'input-folder':<35}{tmp_path}\n" + f"{'output-folder':<35}{tmp_path}\n\n" + f"{'#import (35)':<35}VALUE\n" + "-" * 80 + "\n" +
+                f"{'reference-frame':<35}GDA2020\n" + f"{'stn-msr-file':<35}pw.stn\n\n" + f"{'#plot (35)':<35}VALUE\n" + "-" * 80 + "\n\n")
+    r = _run(cli_hostsim, tmp_path, "pw", "--output-adj-msr", "--sort-adj-msr-field", "7", "--free-stn-sd", "4", "--stn-coord-types", "ENzh",
+             "--output-tstat-adj-msr", "--max-iterations", "12")
+    assert r.returncode == 0 and "+ Open pw.simult.adj to view the adjustment details." in r.stdout, r.stderr
+    text = open(proj).read()
+    secs = re.findall(r"^(#\w+) \(35\)", text, re.M)
+    assert secs == ["#general", "#import", "#adjust", "#output", "#plot"] and "stn-msr-file                       pw.stn" in text
+    val = lambda k: re.search(r"^" + re.escape(k) + r"\s+(\S+)", text, re.M).group(1)
+    assert val("adjustment-mode") == "simultaneous-adjustment" and val("max-iterations") == "12" and val("free-stn-sd") == "4.000"
+    assert val("fixed-stn-sd") == "1.0000e-06" and val("output-adj-msr") == "yes" and val("sort-adj-msr-field") == "7" and val("stn-coord-types") == "ENzh"
+    assert val("output-tstat-adj-msr") == "yes" and val("output-pos-uncertainty") == "no"
+    first = open(os.path.join(tmp_path, "pw.simult.adj")).read()
+    stn2, msr2, _, _ = synth.gnss_network(40, 110, 19)           # fresh binaries: -p repeats the same adjustment
+    _write_network(tmp_path, "pw", stn2, msr2)
+    r = subprocess.run([cli_hostsim, "-p", proj], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    again = open(os.path.join(tmp_path, "pw.simult.adj")).read()
+    tab = lambda t, h: _tables(t, h)[-1]
+    assert tab(again, "Adjusted Measurements") == tab(first, "Adjusted Measurements") and tab(again, "Adjusted Coordinates") == tab(first, "Adjusted Coordinates")
+    assert re.findall(r"^(#\w+) \(35\)", open(proj).read(), re.M) == secs
