@@ -12,7 +12,7 @@
         var("PU confidence interval:", "95.0%");
         var("Error ellipse axes:", "68.3% (1 sigma)");
         var("Variances:", "68.3% (1 sigma)");
-        var("Stations printed in blocks:", "No");
+        var("Stations printed in blocks:", a_.adjust_mode != SimultaneousMode && a_.output_pu_covariances ? "Yes" : "No");
         var("Variance matrix units:", a_.apu_vcv_enu ? "ENU" : "XYZ");
         var("Full covariance matrix:", a_.output_pu_covariances ? "Yes" : "No");
         if (!a_.type_b_global.empty())
