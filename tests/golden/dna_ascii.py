@@ -19,7 +19,8 @@ from dynadjust_b200.records import GRS80_A, GRS80_INVF, LLH_TYPE, UTM_TYPE, XYZ_
 ITRF2008_TO_GDA2020 = (13.790, 4.550, 15.220, 2.5500, 0.2808, 0.2677, -0.4638,
                        1.420, 1.340, 0.900, 0.1090, 1.5461, 1.1820, 1.1551)
 ITRF2014_TO_GDA2020 = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.50379, 1.18346, 1.20716)   # :1593-1614
-PARAMETERS = {"ITRF2008": ITRF2008_TO_GDA2020, "ITRF2014": ITRF2014_TO_GDA2020}
+GDA94_TO_GDA2020 = (61.55, -10.87, -40.19, -9.994, -39.4924, -32.7221, -32.8979, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)            # :2465-2481
+PARAMETERS = {"ITRF2008": ITRF2008_TO_GDA2020, "ITRF2014": ITRF2014_TO_GDA2020, "GDA94": GDA94_TO_GDA2020}
 CUMULATIVE_DAYS = ((0, 31, 59, 90, 120, 151, 181, 212, 243, 273, 304, 334), (0, 31, 60, 91, 121, 152, 182, 213, 244, 274, 305, 335))
 
 
@@ -105,6 +106,20 @@ def apply_geoid(stn, path, convert_heights=True):
         stn["verticalDef"][i] = np.radians(float(f[3]) / 3600.0)
         if convert_heights:
             stn["currentHeight"][i] = stn["initialHeight"][i] + float(stn["geoidSep"][i])
+
+
+def reftran_stations(stn, frame, epoch="01.01.2020"):
+    """dnareftran on the station file: every station from `frame` to GDA2020.  Run before the geoid step, as in the
+    reference's urban_mt pipeline (CMakeLists.txt:1078-1079): horizontal position through the 7-parameter transformation."""
+    for i in range(len(stn)):
+        x = synth.geo_to_cart(stn["initialLatitude"][i:i + 1], stn["initialLongitude"][i:i + 1], stn["initialHeight"][i:i + 1])[0]
+        lat, lon, h = synth.cart_to_geo(helmert_to_gda2020(x, frame, epoch)[None, :])
+        stn["initialLatitude"][i] = stn["currentLatitude"][i] = lat[0]
+        stn["initialLongitude"][i] = stn["currentLongitude"][i] = lon[0]
+        if stn["suppliedStationType"][i] == XYZ_TYPE:
+            stn["initialHeight"][i] = stn["currentHeight"][i] = h[0]
+        # else: an orthometric height does not depend on the reference frame and stays as supplied (the expected run keeps
+        # the height-constrained station 1042 at its H)
 
 
 def read_stations(path):
@@ -213,7 +228,7 @@ def read_measurements(path, stn, reftran=True):
             frame, epoch = l[102:122].strip(), l[122:142].strip()
             ctype = l[22:42].strip() if kind == "Y" else "XYZ"
             if kind == "Y":
-                assert ctype in ("XYZ", "LLH", "LLh") and (not reftran or frame in ("GDA2020", "GDA94")), "point cluster form not handled"
+                assert ctype in ("XYZ", "LLH", "LLh"), "point cluster form not handled"
             total = sum(3 + 3 * (count - 1 - k) for k in range(count))
             m = new_msr(total)
             m["measType"], m["coordType"], m["clusterID"], m["ignore"] = kind.encode(), ctype.encode(), cluster, ignore
@@ -229,6 +244,12 @@ def read_measurements(path, stn, reftran=True):
                 d = np.array([x[0] for x in vals])
                 if ctype != "XYZ":
                     d[0], d[1] = dms_to_rad(d[0]), dms_to_rad(d[1])     # latitude and longitude arrive as ddd.mmssss
+                    if reftran and kind == "Y" and frame.upper() != "GDA2020":    # the point itself goes to the new frame
+                        x = synth.geo_to_cart(d[0:1], d[1:2], d[2:3])[0]
+                        la, lo, hh = synth.cart_to_geo(helmert_to_gda2020(x, frame, epoch)[None, :])
+                        d = np.array([la[0], lo[0], hh[0]])
+                elif reftran and kind == "Y" and frame.upper() != "GDA2020":
+                    d = helmert_to_gda2020(d, frame, epoch)
                 if kind == "X":
                     r["station2"] = index[L[i][22:42].strip()]
                     if reftran and frame.upper() != "GDA2020":

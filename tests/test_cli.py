@@ -396,6 +396,58 @@ def test_cli_reproduces_reference_expected_urban_adj_gpu(cli_gpu, tmp_path):
     _golden_urban_text(cli_gpu, tmp_path)
 
 
+def _golden_urban_mt_text(exe, tmp_path):
+    """The reference's CI chain on urban_mt, with its own two command lines (CMakeLists.txt:1081, 1083): the first adjustment
+    with the full set of report options updates the binary files, the second `dnaadjust urban_mt --output-adj-msr --multi`
+    starts from them; its .adj is compared with sampleData/urban_mt.phased-mt.adj.expected (tests/golden/urban_mt_sample.npz:
+    data moved GDA94 -> GDA2020 by the reference-frame step, 1182 rows incl. the point cluster in P / L / H form)."""
+    from tests.golden.make_urban_sample import parse_expected
+    z = np.load(os.path.join(ROOT, "tests", "golden", "urban_mt_sample.npz"))
+    stn, msr = np.ascontiguousarray(z["stn"].astype(STN_DTYPE)), np.ascontiguousarray(z["msr"].astype(MSR_DTYPE))
+    _write_network(tmp_path, "urban_mt", stn, msr)
+    isl = parity.chain_blocks(len(stn), 60)
+    dnafiles.write_seg(os.path.join(tmp_path, "urban_mt.seg"), isl, [[] for _ in isl], [[] for _ in isl])
+    first = ("--output-adj-msr --multi --free-stn-sd 4.0 --fixed-stn-sd 0.000001 --max-iterations 20 --output-tstat-adj-msr --sort-adj-msr-field 2 "
+             "--sort-stn-orig-order --stn-coord-types PLHhENz --angular-stn-type 1 --angular-msr-type 1 --precision-stn-linear 3 --precision-msr-linear 3 "
+             "--precision-stn-angular 4 --precision-msr-angular 4 --output-pos-uncertainty --output-all-covariances --output-corrections-file").split()
+    r = _run(exe, tmp_path, "urban_mt", *first)
+    assert r.returncode == 0, r.stderr
+    for e in ("adj", "xyz", "apu", "cor"):
+        assert os.path.getsize(os.path.join(tmp_path, "urban_mt.phased-mt." + e)) > 1000
+    r = _run(exe, tmp_path, "urban_mt", "--output-adj-msr", "--multi")
+    assert r.returncode == 0, r.stderr
+    text = open(os.path.join(tmp_path, "urban_mt.phased-mt.adj")).read()
+    assert len(re.findall(r"^ITERATION", text, re.M)) == 1          # already at the solution, as in the expected file
+    sol, keys, rows, stn_names, stn_rows = parse_expected(os.path.join(tmp_path, "urban_mt.phased-mt.adj"))
+    want = dict(zip(z["solution_keys"].tolist(), z["solution"].tolist()))
+    assert all(sol[k] == want[k] for k in ("unknowns", "measurements", "dof", "outliers"))
+    assert abs(sol["chi_squared"] - want["chi_squared"]) < 1.0 and abs(sol["sigma_zero"] - want["sigma_zero"]) < 0.0011
+    assert keys == z["msr_keys"].tolist() and len(keys) == 1182
+    sec = np.radians(1.0 / 3600.0)
+    for key, got, w in zip(keys, rows, z["msr_rows"]):
+        t, comp = key[0], key.split()[-1]
+        ang = t in "ABKVZ" or (t == "Y" and comp in "PL")
+        unit = sec if ang else 1.0
+        assert abs(got[0] - w[0]) / unit < 1.1e-4, key                                   # the measurement as the file gave it
+        assert np.abs(got[3:6] - w[3:6]).max() < (2.6e-4 if ang else 1.1e-4), (key, got, w)
+        tol = (0.6 if t in "VZ" else 0.05) if ang else 8e-4
+        assert abs(got[1] - w[1]) / unit < tol and abs(got[2] - w[2]) < tol, (key, got, w)
+        assert abs(got[6] - w[6]) < 0.08 and abs(got[7] - w[7]) < 0.011, (key, got, w)
+        assert abs(got[8] - w[8]) < (0.05 if ang else 1.1e-3), (key, got, w)
+    stn_rows = stn_rows[[stn_names.index(n) for n in z["stn_names"].tolist()]]
+    assert np.abs(stn_rows[:, [0, 1]] - z["stn_rows"][:, [0, 1]]).max() < 2e-9 and np.abs(stn_rows[:, 3:7] - z["stn_rows"][:, 3:7]).max() < 7e-4
+    assert np.abs(stn_rows[:, 7:10] - z["stn_rows"][:, 7:10]).max() < 1.1e-4
+
+
+def test_cli_reference_ci_chain_urban_mt_hostsim(cli_hostsim, tmp_path):
+    _golden_urban_mt_text(cli_hostsim, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_reference_ci_chain_urban_mt_gpu(cli_gpu, tmp_path):
+    _golden_urban_mt_text(cli_gpu, tmp_path)
+
+
 def _read_snx(path):
     text = open(path).read()
     assert text.startswith("%=SNX 2.00 DNA") and text.rstrip().endswith("%ENDSNX")

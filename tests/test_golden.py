@@ -186,3 +186,47 @@ def test_engine_host_logic_reproduces_reference_urban_output(oracle, hostsim_pat
 def test_cuda_path_reproduces_reference_urban_output(oracle, gpu_lib, urban):
     # trigonometric rows: CUDA's and glibc's libm differ in the last ulp (see tests/test_gpu_parity.py)
     _engine_urban(urban, oracle, gpu_lib, 1e-7, leaf_stations=12)
+
+
+# ---- the reference's urban_mt chain: data moved GDA94 -> GDA2020, adjusted, then adjusted again from the updated files ----
+@pytest.fixture(scope="module")
+def urban_mt():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "urban_mt_sample.npz"))
+    return dict(stn=np.ascontiguousarray(z["stn"].astype(STN_DTYPE)), msr=np.ascontiguousarray(z["msr"].astype(MSR_DTYPE)),
+                sol=dict(zip(z["solution_keys"].tolist(), z["solution"].tolist())), msr_keys=z["msr_keys"].tolist(),
+                msr_rows=z["msr_rows"], stn_names=z["stn_names"].tolist(), stn_rows=z["stn_rows"])
+
+
+def _engine_urban_mt(g, lib):
+    """tests/golden/urban_mt_sample.npz (made by make_urban_mt_sample.py): sampleData/urban_mt.phased-mt.adj.expected is the
+    output of the SECOND dnaadjust of the reference's CI chain (CMakeLists.txt:1081-1083) — the first runs with
+    --free-stn-sd 4.0 --fixed-stn-sd 0.000001 --max-iterations 20 and updates the binary files, the second starts from them
+    with the defaults.  Reproducing it needs the re-adjustment semantics of reduced files: measured values restored from
+    preAdjMeas, reductions and scalars not applied twice, the converted point cluster left as it is."""
+    stn, msr = g["stn"].copy(), g["msr"].copy()
+    first = engine.Adjustment(stn, msr, lib_path=lib, leaf_stations=12, free_std_dev=4.0, fixed_std_dev=1.0e-6, max_iterations=20)
+    first.prepare()
+    first.adjust()
+    first.statistics(write_back=True)          # adjusted coordinates and statistics into the records, as UpdateBinaryFiles leaves them
+    first.close()
+    second = engine.Adjustment(lib_path=lib, leaf_stations=12)
+    second.set_stations(stn)
+    second.set_measurements(msr, reduced=True)
+    second.prepare()
+    last = second.adjust()
+    st = second.statistics(write_back=True)
+    assert last.iteration == 1                 # the expected file shows one iteration with corrections of 1e-8 m
+    q = second.station_vcvs().reshape(-1, 3, 3)
+    _check_urban(g, stn, msr, second.estimates().reshape(-1, 3), lambda i: q[i],
+                 dict(unknowns=st.unknown_params, measurements=st.measurement_params, dof=st.dof, chi_squared=st.chi_squared,
+                      sigma_zero=st.sigma_zero, pelzer=st.global_pelzer, outliers=st.outliers))
+    second.close()
+
+
+def test_engine_host_logic_reproduces_reference_readjusted_urban_output(hostsim_path, urban_mt):
+    _engine_urban_mt(urban_mt, hostsim_path)
+
+
+@pytest.mark.gpu
+def test_cuda_path_reproduces_reference_readjusted_urban_output(gpu_lib, urban_mt):
+    _engine_urban_mt(urban_mt, gpu_lib)
