@@ -144,7 +144,7 @@
             adj << iter_pre_[i] << iter_post_[i];
         }
         const std::string dash(80, '-');
-        adj << "\n" << dash << "\n" << std::left << std::setw(35) << "SOLUTION" << "Failed to converge\n";
+        adj << "\n" << dash << "\n" << std::left << std::setw(35) << "SOLUTION" << (adjustStatus_ == ADJUST_CANCELLED ? "Adjustment cancelled" : "Failed to converge") << "\n";
         char buf[64];
         snprintf(buf, sizeof(buf), "00:00:%09.6f", total_ms_ / 1e3);
         adj << std::left << std::setw(35) << "Total time" << buf << "\n\n";

@@ -17,6 +17,7 @@
 #include <stdexcept>
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <charconv>
 #include <map>
 #include <tuple>
@@ -32,7 +33,7 @@
 namespace dynadjust_b200 {
 
 enum ADJUST_MODE { SimultaneousMode = 0, PhasedMode = 1, Phased_Block_1Mode = 2 };
-enum ADJUST_STATUS { ADJUST_SUCCESS = 0, ADJUST_MAX_ITERATIONS_EXCEEDED = 2, ADJUST_EXCEPTION_RAISED = 4 };
+enum ADJUST_STATUS { ADJUST_SUCCESS = 0, ADJUST_MAX_ITERATIONS_EXCEEDED = 2, ADJUST_EXCEPTION_RAISED = 4, ADJUST_CANCELLED = 5 };
 
 struct adjust_settings {            // the fields of project_settings.a / .g / .o the solve path reads
     std::string network_name;
@@ -173,6 +174,10 @@ class dna_adjust {
             iter_post_.push_back(std::string());
             if (std::fabs(r.max_corr) <= a_.iteration_threshold)
                 break;
+            if (cancel_ && cancel_->load()) {   // SIGINT: CancelAdjustment(), polled once per iteration (WRAP:67-71, ADJ:2432)
+                adjustStatus_ = ADJUST_CANCELLED;
+                break;
+            }
             if (iter_reports && i + 1 < a_.max_iterations) {
                 // --output-iter-adj-stat / -msr / -stn: statistics, adjusted measurements and stations of an iteration that
                 // is followed by another (ADJ:2483-2502); needs the rigorous variances of this iteration
@@ -187,7 +192,7 @@ class dna_adjust {
                 iter_post_.back() = post.str();
             }
         }
-        if (iterations_.size() == a_.max_iterations && std::fabs(maxCorr_) > a_.iteration_threshold)
+        if (adjustStatus_ != ADJUST_CANCELLED && iterations_.size() == a_.max_iterations && std::fabs(maxCorr_) > a_.iteration_threshold)
             adjustStatus_ = ADJUST_MAX_ITERATIONS_EXCEEDED;   // ADJ:2523-2525
         if (adjustStatus_ == ADJUST_SUCCESS)
             check(gadj_form_inverse(ctx_));                    // rigorous variances (v_rigorousVariances_)
@@ -213,6 +218,8 @@ class dna_adjust {
                     m.TStat = std::fabs(sz) < 1.0e-10 ? 0.0 : m.NStat / sz;
         }
     }
+
+    void SetCancelFlag(const std::atomic<bool>* flag) { cancel_ = flag; }
 
     // getters (ADJH:336-354)
     double GetChiSquared() const { return stats_.chi_squared; }
@@ -823,6 +830,7 @@ class dna_adjust {
     dnafiles::Segmentation seg_;
     std::string bst_file_, bms_file_;
     std::vector<gadj_iter_result> iterations_;
+    const std::atomic<bool>* cancel_ = nullptr;
     std::vector<DbId> dbid_;
     std::vector<double> corrPrev_;
     std::vector<uint32_t> stnOscCount_;

@@ -4,7 +4,9 @@
 // (--multi-thread, --staged-adjustment, --create-stage-files, --purge-stage-files, --max-threads) are accepted and
 // ignored; unknown flags are a hard error, as in the reference (WRAP:1040-1046).
 #include <cstdlib>
+#include <atomic>
 #include <cctype>
+#include <csignal>
 #include <cstring>
 #include <fstream>
 #include <iomanip>
@@ -67,6 +69,9 @@ const Flag* match(const std::string& key, std::string& err)
 }
 
 }  // namespace
+
+static std::atomic<bool> g_cancel{false};
+extern "C" void sigint_handler(int) { g_cancel.store(true); }
 
 // one option, by its full name (command line and project file share this)
 static int apply_option(adjust_settings& s, bool& quiet, const std::string& n, const std::string& value)
@@ -464,13 +469,20 @@ int main(int argc, char** argv)
             adj.PrintAdjustedNetwork();
             return EXIT_SUCCESS;
         }
+        std::signal(SIGINT, sigint_handler);   // graceful cancellation between iterations (WRAP:67-71, 1362)
+        adj.SetCancelFlag(&g_cancel);
         if (!quiet)
             std::cout << "+ Preparing for adjustment... " << std::flush;
         adj.PrepareAdjustment(s);
         if (!quiet)
             std::cout << "done.\n+ Adjusting network (" << adj.Info().nstations << " stations, " << adj.Info().nfronts
-                      << " fronts)...\n";
+                      << " fronts)..." << std::endl;
         ADJUST_STATUS st = adj.AdjustNetwork();
+        if (st == ADJUST_CANCELLED) {
+            adj.PrintFailedAdjustment();
+            std::cout << "\n- Adjustment cancelled by the user after " << adj.CurrentIteration() << " iteration(s).\n";
+            return EXIT_SUCCESS;
+        }
         if (st == ADJUST_MAX_ITERATIONS_EXCEEDED) {
             // no statistics or tables for an adjustment that ran out of iterations: the iterations, the status and the
             // stations that kept swinging (WRAP:1386-1390)

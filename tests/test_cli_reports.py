@@ -564,3 +564,23 @@ def test_cli_writes_project_file(cli_hostsim, tmp_path):
     tab = lambda t, h: _tables(t, h)[-1]
     assert tab(again, "Adjusted Measurements") == tab(first, "Adjusted Measurements") and tab(again, "Adjusted Coordinates") == tab(first, "Adjusted Coordinates")
     assert re.findall(r"^(#\w+) \(35\)", open(proj).read(), re.M) == secs
+
+
+def test_cli_sigint_cancels_between_iterations(cli_hostsim, tmp_path):
+    """SIGINT asks for a graceful stop (WRAP:67-71; CancelAdjustment polled once per iteration, ADJ:2432): the iteration in
+    flight finishes, the .adj records the iterations done and the status, the binary files stay untouched, exit code 0."""
+    import signal
+    stn, msr, _, _ = synth.gnss_network(1500, 4500, 41)
+    _write_network(tmp_path, "sg", stn, msr)
+    p = subprocess.Popen([cli_hostsim, "sg", "--input-folder", str(tmp_path), "--output-folder", str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                         text=True)
+    line = p.stdout.readline()                    # "+ Preparing for adjustment... " is flushed once the handler is installed
+    while "Adjusting network" not in line and line:
+        line = p.stdout.readline()
+    p.send_signal(signal.SIGINT)                  # the first of the two iterations this network needs is under way
+    out, err = p.communicate(timeout=600)
+    assert p.returncode == 0, err
+    assert "Adjustment cancelled by the user after 1 iteration" in out
+    text = open(os.path.join(tmp_path, "sg.simult.adj")).read()
+    assert re.search(r"^SOLUTION\s+Adjustment cancelled", text, re.M) and len(re.findall(r"^ITERATION", text, re.M)) == 1
+    assert not os.path.exists(os.path.join(tmp_path, "sg-rva.mtx"))
