@@ -570,7 +570,7 @@ def test_cli_sigint_cancels_between_iterations(cli_hostsim, tmp_path):
     """SIGINT asks for a graceful stop (WRAP:67-71; CancelAdjustment polled once per iteration, ADJ:2432): the iteration in
     flight finishes, the .adj records the iterations done and the status, the binary files stay untouched, exit code 0."""
     import signal
-    stn, msr, _, _ = synth.gnss_network(1500, 4500, 41)
+    stn, msr, _, _ = synth.gnss_network(4000, 12000, 41)      # an iteration on the CPU stand-in takes about a second
     _write_network(tmp_path, "sg", stn, msr)
     p = subprocess.Popen([cli_hostsim, "sg", "--input-folder", str(tmp_path), "--output-folder", str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                          text=True)
