@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <ctime>
+#include <filesystem>
 #include <fstream>
 #include <iomanip>
 #include <sstream>
@@ -122,6 +123,24 @@ class dna_adjust {
         check(gadj_set_measurements(ctx_, msr_.data(), msr_.size()));
         check(gadj_set_measurements_reduced(ctx_, bms_meta_.reduced ? 1 : 0));   // isFirstTimeAdjustment_ (ADJ:296)
         if (a_.adjust_mode != SimultaneousMode) {
+            if (a_.seg_file.empty()) {
+                // a default .seg file older than station / measurement files that dnaimport wrote since describes another
+                // network (WRAP:1239-1265); files updated by an adjustment keep their segmentation
+                namespace fs = std::filesystem;
+                auto imported = [](const dnafiles::BinaryMeta& m) {
+                    std::string by(m.modifiedBy, strnlen(m.modifiedBy, sizeof(m.modifiedBy)));
+                    for (char& ch : by)
+                        ch = (char)std::tolower((unsigned char)ch);
+                    return by == "import" || by == "dnaimport" || by == "dnainterop.dll" || by == "libdnaimport.so";
+                };
+                std::error_code ec1, ec2, ec3;
+                const auto t_seg = fs::last_write_time(base + ".seg", ec1), t_bst = fs::last_write_time(bst_file_, ec2),
+                           t_bms = fs::last_write_time(bms_file_, ec3);
+                if (!ec1 && !ec2 && !ec3 && ((imported(bst_meta_) && t_seg < t_bst) || (imported(bms_meta_) && t_seg < t_bms)))
+                    SignalExceptionAdjustment("The raw stations and measurements have been imported after\n  the segmentation file was created.\n"
+                                              "  Run 'segment " + a_.network_name + " [options]' to re-create the segmentation file, or re-run\n"
+                                              "  adjust using the --seg-file option if the file " + a_.network_name + ".seg must\n  be used.");
+            }
             dnafiles::load_seg(a_.seg_file.empty() ? base + ".seg" : in_folder(a_.seg_file), seg_);
             std::vector<uint32_t> off{0}, isl;
             for (auto& b : seg_.isl) {

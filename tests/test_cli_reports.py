@@ -584,3 +584,21 @@ def test_cli_sigint_cancels_between_iterations(cli_hostsim, tmp_path):
     text = open(os.path.join(tmp_path, "sg.simult.adj")).read()
     assert re.search(r"^SOLUTION\s+Adjustment cancelled", text, re.M) and len(re.findall(r"^ITERATION", text, re.M)) == 1
     assert not os.path.exists(os.path.join(tmp_path, "sg-rva.mtx"))
+
+
+def test_cli_stale_segmentation_file(cli_hostsim, tmp_path):
+    """A default .seg older than station / measurement files that dnaimport has written since is refused (WRAP:1239-1265);
+    naming it with --seg-file, or files last written by an adjustment, are fine."""
+    import time
+    stn, msr, _, _ = synth.gnss_network(40, 110, 23)
+    isl = parity.chain_blocks(40, 14)
+    dnafiles.write_seg(os.path.join(tmp_path, "sf.seg"), isl, [[] for _ in isl], [[] for _ in isl])
+    past = time.time() - 3600
+    os.utime(os.path.join(tmp_path, "sf.seg"), (past, past))
+    _write_network(tmp_path, "sf", stn, msr)                      # "imported" after the segmentation
+    r = _run(cli_hostsim, tmp_path, "sf", "--phased")
+    assert r.returncode == 1 and "imported after" in r.stderr and "--seg-file" in r.stderr
+    r = _run(cli_hostsim, tmp_path, "sf", "--phased", "--seg-file", "sf.seg")
+    assert r.returncode == 0, r.stderr                             # this run updates the binaries: modified by "adjust"
+    r = _run(cli_hostsim, tmp_path, "sf", "--phased")
+    assert r.returncode == 0, r.stderr
