@@ -725,7 +725,7 @@ int scan_measurements(gadj_ctx* c)
     c->nbsl = c->first.size();
     c->nrows = c->rows.size();
     if (c->nbsl + c->nrows == 0)
-        return c->fail("no measurements to adjust");
+        return c->fail("No valid measurements to process. All measurements may be ignored.");   // LoadNetworkFiles (ADJ:10176)
     c->contiguous = true;
     for (uint64_t b = 0; b < c->nbsl; ++b)
         if (c->first[b] != c->first[0] + 3 * b) {
