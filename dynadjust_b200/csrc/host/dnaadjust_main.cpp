@@ -76,10 +76,20 @@ extern "C" void sigint_handler(int) { g_cancel.store(true); }
 // one option, by its full name (command line and project file share this)
 static int apply_option(adjust_settings& s, bool& quiet, const std::string& n, const std::string& value)
 {
-    if (n == "help") {
-        std::cout << "usage: dnaadjust <network> [--simultaneous-adjustment | --phased-adjustment] [--iteration-threshold x]\n"
-                     "       [--max-iterations n] [--free-stn-sd m] [--fixed-stn-sd m] [--conf-interval pct]\n"
-                     "       [--input-folder d] [--output-folder d] [--output-adj-msr] [--scale-normals-to-unity]\n";
+    if (n == "help" || n == "help-module") {
+        std::cout << "usage: dnaadjust <network> [options]      (options may be shortened to an unambiguous prefix)\n\n"
+                     "  -n network-name  -i input-folder  -o output-folder  -p project-file  -s binary-stn-file  -m binary-msr-file\n\n";
+        int col = 0;
+        for (const Flag& f : kFlags) {
+            std::string item = std::string("--") + f.name + (f.takes_value ? " arg" : "");
+            if (col + (int)item.size() + 2 > 100) {
+                std::cout << "\n";
+                col = 0;
+            }
+            std::cout << "  " << item;
+            col += (int)item.size() + 2;
+        }
+        std::cout << "\n\nThe option groups and their meaning are those of DynAdjust's dnaadjust (see INTEGRATION.md).\n";
         return 1;
     } else if (n == "phased-adjustment")
         s.adjust_mode = s.adjust_mode == Phased_Block_1Mode ? Phased_Block_1Mode : PhasedMode;
@@ -209,9 +219,6 @@ static int apply_option(adjust_settings& s, bool& quiet, const std::string& n, c
         s.export_dna_msr = true;
     else if (n == "version") {
         std::cout << "dnaadjust (dynadjust_b200) 1.0\n";
-        return 1;
-    } else if (n == "help-module") {
-        std::cout << "dnaadjust: help for option group '" << value << "': see --help\n";
         return 1;
     }
     // remaining accepted flags select CPU execution strategies: no effect here
