@@ -116,7 +116,34 @@
         case 4: by_largest([](const dna_msr_t& m) { return m.term1; }); break;
         case 5: by_largest([](const dna_msr_t& m) { return m.measCorr; }); break;
         case 6: by_largest([](const dna_msr_t& m) { return m.measAdjPrec; }); break;
-        case 7: by_largest([](const dna_msr_t& m) { return m.NStat; }); break;
+        case 7:
+            if (a_.adj_gnss_units != 0 && !pam_rec_.empty()) {
+                // baselines are listed by the n-statistics of the frame they are printed in (UpdateGNSSNstatsForAlternateUnits PRN:4526-4715)
+                std::vector<std::pair<double, uint32_t>> k;
+                for (uint32_t f : list) {
+                    const dna_msr_t& m = msr_[f];
+                    double v = 0.0;
+                    if (m.measType == 'G' || m.measType == 'X') {
+                        size_t j = f;
+                        for (uint32_t b = 0; b < std::max<uint32_t>(1u, m.vectorCount1) && j + 2 < msr_.size(); ++b) {
+                            MsrRow rows[3];
+                            AlternateUnitRows(j, rows);
+                            for (int q = 0; q < 3; ++q)
+                                if (std::isfinite(rows[q].nstat))
+                                    v = std::max(v, std::fabs(rows[q].nstat));
+                            j += 3 + 3 * (size_t)msr_[j].vectorCount2;
+                        }
+                    } else
+                        v = LargestOf(f, [](const dna_msr_t& x) { return x.NStat; });
+                    k.emplace_back(v, f);
+                }
+                std::stable_sort(k.begin(), k.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+                for (size_t i = 0; i < k.size(); ++i)
+                    list[i] = k[i].second;
+                break;
+            }
+            by_largest([](const dna_msr_t& m) { return m.NStat; });
+            break;
         default: break;   // original (file) order
         }
     }
@@ -531,6 +558,13 @@
     // are recomputed per component (UpdateMsrRecordStats ADJ:8283-8290).
     void PrintAdjGNSSAlternateUnits(std::ostream& os, size_t i) const
     {
+        MsrRow rows[3];
+        AlternateUnitRows(i, rows);
+        for (int q = 0; q < 3; ++q)
+            PrintMsrRow(os, rows[q], 0);
+    }
+    void AlternateUnitRows(size_t i, MsrRow* rows) const
+    {
         const dna_msr_t* r = &msr_[i];
         const dna_stn_t &s1 = stn_[r->station1], &s2 = stn_[r->station2];
         double Vm[9] = {r[0].term2, r[1].term2, r[2].term2, r[1].term2, r[1].term3, r[2].term3, r[2].term2, r[2].term3, r[2].term4};
@@ -610,7 +644,7 @@
                 row.pelzer = 999.99;
             row.nstat = row.corr / std::sqrt(row.res_prec);
             row.tstat = sz > 1.0e-10 ? row.nstat / sz : 0.0;
-            PrintMsrRow(os, row, 0);
+            rows[q] = row;
         }
     }
 

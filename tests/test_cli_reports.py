@@ -602,3 +602,24 @@ def test_cli_stale_segmentation_file(cli_hostsim, tmp_path):
     assert r.returncode == 0, r.stderr                             # this run updates the binaries: modified by "adjust"
     r = _run(cli_hostsim, tmp_path, "sf", "--phased")
     assert r.returncode == 0, r.stderr
+
+
+def test_cli_nstat_sort_in_alternate_units(cli_hostsim, tmp_path):
+    """--sort-adj-msr-field 7 with --output-adj-gnss-units 1/2/3 (the reference's CI runs these, CMakeLists.txt:1046-1060):
+    baselines are ordered by the n-statistics of the frame they are printed in (PRN:1708-1712, 4526-4715)."""
+    stn, msr, _, _ = synth.gnss_network(40, 110, 6)
+    _write_network(tmp_path, "ns", stn, msr)
+    for units in ("1", "2", "3"):
+        r = _run(cli_hostsim, tmp_path, "ns", "--output-adj-msr", "--sort-adj-msr-field", "7", "--output-adj-gnss-units", units, "--scale-normals-to-unity",
+                 "--no-binary-update")
+        assert r.returncode == 0, r.stderr
+        body = _tables(open(os.path.join(tmp_path, "ns.simult.adj")).read(), "Adjusted Measurements")[-1][1]
+        assert len(body) == 330
+        big = []
+        for b in range(0, 330, 3):
+            ns = []
+            for l in body[b:b + 3]:
+                f = l[67:].split()
+                ns.append(abs(float(f[10] if not re.fullmatch(r"-?\d+\.\d+", f[0]) else f[6])))
+            big.append(max(ns))
+        assert all(a >= b - 0.0051 for a, b in zip(big, big[1:])), units
