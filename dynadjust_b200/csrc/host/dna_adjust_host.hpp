@@ -204,8 +204,11 @@ class dna_adjust {
                 GenerateStatistics();
                 if (a_.iter_adj_stat)
                     PrintStatisticsSummary(post, false);
-                if (a_.iter_adj_msr)
+                if (a_.iter_adj_msr) {
+                    if (a_.adj_gnss_units != 0)
+                        ComputeBaselinePrecisions();
                     PrintAdjMeasurements(post, nullptr, -1);
+                }
                 if (a_.iter_adj_stn)
                     PrintAdjStations(post, nullptr);
                 iter_post_.back() = post.str();
@@ -228,6 +231,8 @@ class dna_adjust {
         check(gadj_get_estimates(ctx_, est_.data()));
         check(gadj_get_station_vcvs(ctx_, vcv_.data()));
         raw_vcv_ = vcv_;                              // before type B uncertainties: adjusted-measurement precisions use these
+        pam_rec_.clear();                             // precisions of adjusted baselines belong to the variances just fetched
+        pam_.clear();
         ApplyTypeBUncertainties();
         ComputeTestStat();
         if (a_.adj_msr_tstat) {                       // Student's t = n-stat / sqrt(sigma zero) (UpdateMsrTstatistic ADJ:6914-7092)

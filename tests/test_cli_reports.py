@@ -623,3 +623,64 @@ def test_cli_nstat_sort_in_alternate_units(cli_hostsim, tmp_path):
                 ns.append(abs(float(f[10] if not re.fullmatch(r"-?\d+\.\d+", f[0]) else f[6])))
             big.append(max(ns))
         assert all(a >= b - 0.0051 for a, b in zip(big, big[1:])), units
+
+
+def test_cli_accepts_the_reference_ci_command_lines(cli_hostsim, tmp_path):
+    """Every option set the reference's CI drives dnaadjust with (CMakeLists.txt:1046-1963) runs to completion here on a
+    mixed network; the ones its CI expects to fail, fail."""
+    import shlex
+    stn, msr, _ = _network()
+    name = stn["stationName"][5].decode()
+    isl = parity.chain_blocks(len(stn), 20)
+    n = len(msr)
+    ids = np.zeros(n, dtype=[("m", "<u4"), ("c", "<u4"), ("ms", "<u2"), ("cs", "<u2")])
+    ids["m"], ids["c"], ids["ms"], ids["cs"] = np.arange(n), msr["clusterID"], 1, 1
+    with open(os.path.join(tmp_path, "dsg.typeb"), "w") as f:
+        f.write("!#=DNA 1.00 TBU\n" + f"{name:<20}0.010 0.010 0.030\n")
+
+    def fresh():
+        _write_network(tmp_path, "ci", stn.copy(), msr.copy())
+        dnafiles.write_seg(os.path.join(tmp_path, "ci.seg"), isl, [[] for _ in isl], [[] for _ in isl])
+        with open(os.path.join(tmp_path, "ci.dbid"), "wb") as f:
+            f.write(np.uint32(n).tobytes() + ids.tobytes())
+    ok = [
+        "--output-adj-msr --scale-normals-to-unity",
+        *[f"--output-adj-msr --sort-adj-msr-field 7 --output-adj-gnss-units {u} --scale-normals-to-unity" for u in range(4)],
+        "--output-msr-to-stn", *[f"--output-msr-to-stn --sort-msr-to-stn-field {k}" for k in range(4)],
+        "--block1-phased --output-adj-msr --output-adj-gnss-units 1",
+        "--phased --output-adj-msr --output-adj-gnss-units 2 --output-iter-adj-msr",
+        "--phased --output-adj-msr --sort-adj-msr-field 7 --output-adj-gnss-units 1",
+        "--staged-adjustment --create-stage-files --output-adj-msr --output-adj-gnss-units 2 --sort-adj-msr-field 4",
+        "--staged-adjustment --create-stage-files --output-adj-msr --sort-adj-msr-field 7 --output-adj-gnss-units 2",
+        "--staged-adjustment --purge-stage-files --output-adj-msr --output-adj-gnss-units 3 --output-stn-blocks --output-msr-blocks --sort-adj-msr-field 5",
+        "--verbose 5", "--staged --create --purge", "--staged", "--multi --output-adj-msr",
+        "--output-adj-msr --phased --stn-corrections --export-sinex-file --export-xml-stn-file --export-dna-stn-file --output-pos-uncertainty "
+        "--export-dna-msr --export-xml-msr",
+        "--phased --staged-adjustment --create-stage-files --output-adj-msr --export-sinex-file --output-pos-uncertainty --export-xml-stn-file "
+        "--export-xml-msr-file --export-dna-stn-file --export-dna-msr --output-iter-adj-stn --output-iter-adj-stat --output-iter-adj-msr "
+        "--output-iter-cmp-msr --stn-corrections --output-corrections-file",
+        "--output-adj-msr --free-stn-sd 5.0 --fixed-stn-sd 0.000005 --max-iterations 15 --output-tstat-adj-msr --sort-adj-msr-field 7 --sort-stn-orig-order "
+        "--stn-coord-types XYZPLHhENz --angular-stn-type 1 --angular-msr-type 1 --precision-stn-linear 3 --precision-msr-linear 3 --precision-stn-angular 4 "
+        "--precision-msr-angular 4 --output-pos-uncertainty --output-all-covariances --output-corrections-file",
+        f'--type-b-sd-glob "0.01,0.01,0.035" --type-b-sd-file {os.path.join(tmp_path, "dsg.typeb")} --output-pos',
+        '--comments "This is a comment that is quite lengthy in content and is relatively meaningless.  Feel free to delete this comment."',
+        "--output-adj-msr --output-database-ids --output-ignored-msrs --sort-adj-msr-field 6 --output-msr-to-stn --sort-msr-to-stn-field 1 "
+        "--output-iter-adj-stn --output-iter-adj-stat --output-iter-adj-msr --output-iter-cmp-msr",
+        f'--constraint "{name},CCC"',
+    ]
+    for cmd in ok:
+        fresh()
+        r = _run(cli_hostsim, tmp_path, "ci", *shlex.split(cmd))
+        assert r.returncode == 0, (cmd, r.stderr)
+    # the last run left updated binaries and the .mtx files: report mode on them (adjust-dbid-04 of the reference)
+    r = _run(cli_hostsim, tmp_path, "ci", *shlex.split(f'--report-results --output-adj-msr --output-pos-uncertainty --output-apu-vcv-units 1 --constraints "{name},CCC"'))
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([cli_hostsim, "-p", os.path.join(tmp_path, "ci.dnaproj")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    for cmd in ('ci --constraints "no-name,CCC"', f'ci --constraints "{name},AAA"', "-x", "-p ./nofile.dnaproj", "--phased", "missing"):
+        r = subprocess.run([cli_hostsim, *shlex.split(cmd), "--input-folder", str(tmp_path), "--output-folder", str(tmp_path)], capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 1 and "Error" in r.stderr, cmd
+    for cmd in ("-h", "--version", "--help-module output"):
+        r = subprocess.run([cli_hostsim, *shlex.split(cmd)], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0 and r.stdout, cmd
