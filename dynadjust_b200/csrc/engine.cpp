@@ -190,7 +190,7 @@ struct gadj_ctx {
     std::vector<uint32_t> edge_hi, edge_lo;
     bool contiguous = false;
     uint64_t nbsl = 0, nedge = 0;
-    uint32_t constrained_components = 0;
+    uint32_t constrained_components = 0, unused_stations = 0;
     // structure
     Symbolic sym;
     Plan plan;
@@ -1091,10 +1091,24 @@ int gadj_prepare(gadj_ctx* c)
         edges[e] = {(uint32_t)(uniq[e] >> 32), (uint32_t)(uniq[e] & 0xFFFFFFFFu)};
 
     std::vector<double> lat(c->nstn), lon(c->nstn);
+    // stations no measurement that takes part touches are not parameters of the adjustment: the reference leaves them out
+    // of its station lists (RemoveInvalidStations LDR:286-300, unknownParams_ ADJ:632-693); here they stay in the system,
+    // held by their a-priori weight alone, but do not count as unknowns
+    std::vector<uint8_t> used(c->nstn, 0);
+    for (uint32_t f : c->first)
+        used[c->msr[f].station1] = used[c->msr[f].station2] = 1;
+    for (const RowDesc& r : c->rows)
+        for (int k = 0; k < r.nst; ++k)
+            used[r.st[k]] = 1;
     c->constrained_components = 0;
+    c->unused_stations = 0;
     for (uint32_t s = 0; s < c->nstn; ++s) {
         lat[s] = c->stn[s].currentLatitude;
         lon[s] = c->stn[s].currentLongitude;
+        if (!used[s]) {
+            c->unused_stations++;
+            continue;
+        }
         for (int k = 0; k < 3; ++k)
             c->constrained_components += c->stn[s].stationConst[k] == 'C';
     }
@@ -1893,7 +1907,7 @@ int gadj_statistics(gadj_ctx* c, gadj_stats* stt, int write_back)
     std::memset(stt, 0, sizeof(*stt));
     stt->chi_squared = sums[0];
     stt->measurement_params = (uint32_t)(3 * c->nbsl + c->nrows);
-    stt->unknown_params = 3 * c->nstn - c->constrained_components;
+    stt->unknown_params = 3 * (c->nstn - c->unused_stations) - c->constrained_components;
     stt->dof = (int64_t)stt->measurement_params - (int64_t)stt->unknown_params;   // ADJ:6856
     stt->sigma_zero = stt->dof != 0 ? stt->chi_squared / (double)stt->dof : 0.0;
     stt->outliers = (uint32_t)sums[3];

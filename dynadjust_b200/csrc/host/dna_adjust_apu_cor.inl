@@ -124,11 +124,11 @@
         snprintf(buf, sizeof(buf), "%-20s%2s%19s%19s%19s%19s%11s%11s%11s", "Station", "", "Azimuth", "V. Angle", "S. Distance", "H. Distance",
                  "east", "north", "up");
         os << buf << "\n" << std::string(20 + 2 + 4 * 19 + 3 * 11, '-') << "\n";
-        for (size_t i = 0; i < stn_.size(); ++i) {
+        for (uint32_t i : StationOrder(nullptr)) {
             const dna_stn_t& s = stn_[i];
             double o[3];
             OriginalXYZ(i, o);
-            const double d[3] = {est_[3 * i] - o[0], est_[3 * i + 1] - o[1], est_[3 * i + 2] - o[2]};
+            const double d[3] = {est_[3 * (size_t)i] - o[0], est_[3 * (size_t)i + 1] - o[1], est_[3 * (size_t)i + 2] - o[2]};
             const double lat = s.currentLatitude, lon = s.currentLongitude;   // the adjusted position, as in the reference
             const double e = -std::sin(lon) * d[0] + std::cos(lon) * d[1];
             const double n = -std::sin(lat) * std::cos(lon) * d[0] - std::sin(lat) * std::sin(lon) * d[1] + std::cos(lat) * d[2];

@@ -100,6 +100,7 @@ class dna_adjust {
         dnafiles::load_binary(bst_file_, stn_, bst_meta_);
         dnafiles::load_binary(bms_file_, msr_, bms_meta_);
         ApplyConstraints();
+        ComputeStationValidity();
         if (a_.database_ids)
             LoadDatabaseId();
         gadj_opts o;
@@ -855,6 +856,7 @@ class dna_adjust {
     std::string bst_file_, bms_file_;
     std::vector<gadj_iter_result> iterations_;
     const std::atomic<bool>* cancel_ = nullptr;
+    std::vector<uint8_t> valid_;        // station takes part in the adjustment (a measurement that is not ignored touches it)
     std::vector<DbId> dbid_;
     std::vector<double> corrPrev_;
     std::vector<uint32_t> stnOscCount_;

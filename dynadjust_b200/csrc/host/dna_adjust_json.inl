@@ -330,12 +330,12 @@
         if (a_.output_corrections) {
             std::ofstream os(stem + ".cor.jsonl");
             JsonHeader(os, "cor");
-            for (size_t i = 0; i < stn_.size(); ++i) {
+            for (uint32_t i : StationOrder(nullptr)) {
                 const dna_stn_t& s = stn_[i];
                 double o[3], R[9];
                 OriginalXYZ(i, o);
                 local_rotation(s.currentLatitude, s.currentLongitude, R);
-                const double d[3] = {est_[3 * i] - o[0], est_[3 * i + 1] - o[1], est_[3 * i + 2] - o[2]};
+                const double d[3] = {est_[3 * (size_t)i] - o[0], est_[3 * (size_t)i + 1] - o[1], est_[3 * (size_t)i + 2] - o[2]};
                 Json j = JsonStationIdentity(s), c;
                 j["Initial"] = JsonInitial(s);
                 c["dE"] = R[0] * d[0] + R[3] * d[1] + R[6] * d[2];

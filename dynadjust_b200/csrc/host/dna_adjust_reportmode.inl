@@ -93,6 +93,7 @@
         dnafiles::load_binary(bms_file_, msr_, bms_meta_);
         if (a_.adjust_mode != SimultaneousMode)
             dnafiles::load_seg(a_.seg_file.empty() ? base + ".seg" : in_folder(a_.seg_file), seg_);
+        ComputeStationValidity();
         if (a_.database_ids)
             LoadDatabaseId();
         ReportHeader h{};

@@ -52,6 +52,30 @@
         }
     }
 
+    void ComputeStationValidity()
+    {
+        valid_.assign(stn_.size(), 0);
+        for (size_t i = 0; i < msr_.size();) {
+            const size_t span = MeasurementSpan(i);
+            if (!msr_[i].ignore)
+                for (size_t j = i; j < i + span && j < msr_.size(); ++j) {
+                    const dna_msr_t& r = msr_[j];
+                    if (r.ignore || (std::strchr("GXY", r.measType) && r.measStart != 0))
+                        continue;
+                    auto mark = [&](uint32_t sidx) {
+                        if (sidx < valid_.size())
+                            valid_[sidx] = 1;
+                    };
+                    mark(r.station1);
+                    if (r.measType != 'Y' && !std::strchr("HRIJPQ", r.measType))
+                        mark(r.station2);
+                    if (r.measType == 'A')
+                        mark(r.station3);
+                }
+            i += span;
+        }
+    }
+
     std::vector<uint32_t> CollectMeasurements(const std::vector<int32_t>* rec_block, int32_t block, bool ignored) const
     {
         std::vector<uint32_t> list;
@@ -782,9 +806,11 @@
         if (subset)
             list = *subset;
         else {
-            list.resize(stn_.size());
-            for (size_t i = 0; i < list.size(); ++i)
-                list[i] = (uint32_t)i;
+            // every station a measurement that takes part touches; the others were not adjusted and are not reported
+            // (the reference's station lists hold valid stations only, LDR:286-300)
+            for (size_t i = 0; i < stn_.size(); ++i)
+                if (valid_.empty() || valid_[i])
+                    list.push_back((uint32_t)i);
         }
         if (a_.sort_stn_orig_order)   // --sort-stn-orig-order: the order of the imported station file (CompareStnFileOrder)
             std::stable_sort(list.begin(), list.end(), [&](uint32_t a, uint32_t b) { return stn_[a].fileOrder < stn_[b].fileOrder; });

@@ -1298,10 +1298,30 @@ int oracle_adjust_simultaneous(const oracle_opts* opts, dna_stn_t* stn, uint32_t
 
     // PopulateEstimatedStationMatrix (ADJ:632-693)
     c.est.resize(c.n);
-    uint32_t unknownParams = c.n;
+    // stations without a measurement that takes part are not in the reference's station lists (RemoveInvalidStations,
+    // network_data_loader.cpp:286-300), so they are not unknowns (ADJ:632-693 runs over the lists)
+    std::vector<uint8_t> used(nstn, 0);
+    auto touch = [&](const dna_msr_t& r, char type) {
+        used[r.station1] = 1;
+        if (type != 'Y' && !std::strchr("HRIJPQ", type))
+            used[r.station2] = 1;
+        if (type == 'A')
+            used[r.station3] = 1;
+    };
+    for (const Meas& me : c.meas) {
+        touch(msr[me.first], me.type);
+        for (uint64_t r : me.rec)
+            touch(msr[r], me.type);
+        for (uint64_t r : me.base)
+            touch(msr[r], me.type);
+    }
+    uint32_t unknownParams = 0;
     for (uint32_t s = 0; s < nstn; ++s) {
         geo_to_cart(c.ell, stn[s].currentLatitude, stn[s].currentLongitude, stn[s].currentHeight, &c.est[3 * s],
                     &c.est[3 * s + 1], &c.est[3 * s + 2]);
+        if (!used[s])
+            continue;
+        unknownParams += 3;
         for (int k = 0; k < 3; ++k)
             if (stn[s].stationConst[k] == 'C')
                 unknownParams--;

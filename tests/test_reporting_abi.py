@@ -7,6 +7,7 @@ import pytest
 from dynadjust_b200 import engine, synth
 from dynadjust_b200 import synth_terrestrial as st
 from tests import parity
+from tests.test_cli import cli_hostsim  # noqa: F401  (fixture)
 
 SEC = np.radians(1 / 3600.0)
 
@@ -172,3 +173,30 @@ def test_readjustment_of_reduced_records(hostsim_path):
 @pytest.mark.gpu
 def test_readjustment_of_reduced_records_gpu(gpu_lib):
     _readjust(gpu_lib, 1e-5)
+
+
+def test_station_without_measurements_is_not_an_unknown(hostsim_path, oracle, cli_hostsim, tmp_path):
+    """A station no measurement (that takes part) touches is not in the reference's station lists (network_data_loader.cpp:
+    286-300): it does not count as three unknowns, and the reports leave it out."""
+    import os
+    import re
+    from dynadjust_b200 import dnafiles
+    from tests.test_cli import _run, _write_network
+    stn, msr, _, _ = synth.gnss_network(30, 85, 13)
+    lone = 17
+    touching = np.isin(msr["station1"], [lone]) | np.isin(msr["station2"], [lone])
+    for i in np.where(touching & (msr["measStart"] == 0))[0]:
+        msr["ignore"][i:i + 3] = 1                       # every baseline at that station is flagged as ignored
+    ref = oracle.adjust_simultaneous(stn.copy(), msr.copy(), want_vcv=False)
+    adj, _, _, st = parity.run_engine(hostsim_path, stn.copy(), msr.copy(), leaf_stations=8)
+    assert st.unknown_params == ref["res"].unknown_params == 3 * 29 - 9 and st.dof == ref["res"].dof
+    assert abs(st.sigma_zero - ref["res"].sigma_zero) < 1e-10
+    adj.close()
+    _write_network(tmp_path, "un", stn, msr)
+    r = _run(cli_hostsim, tmp_path, "un", "--output-pos-uncertainty", "--output-corrections-file", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    name = stn["stationName"][lone].decode()
+    for ext in ("adj", "xyz", "apu", "cor"):
+        text = open(os.path.join(tmp_path, "un.simult." + ext)).read()
+        assert not re.search(r"^" + name + r"\s", text, re.M), ext
+        assert re.search(r"^" + stn["stationName"][3].decode() + r"\s", text, re.M), ext
