@@ -12,7 +12,7 @@
         var("PU confidence interval:", "95.0%");
         var("Error ellipse axes:", "68.3% (1 sigma)");
         var("Variances:", "68.3% (1 sigma)");
-        var("Stations printed in blocks:", a_.adjust_mode != SimultaneousMode && a_.output_pu_covariances ? "Yes" : "No");
+        var("Stations printed in blocks:", a_.adjust_mode != SimultaneousMode && (a_.output_pu_covariances || a_.output_stn_blocks) ? "Yes" : "No");
         var("Variance matrix units:", a_.apu_vcv_enu ? "ENU" : "XYZ");
         var("Full covariance matrix:", a_.output_pu_covariances ? "Yes" : "No");
         if (!a_.type_b_global.empty())
@@ -35,9 +35,15 @@
                  "Vt PosU", "Semi-major", "Semi-minor", "Orientation", v1, v2, v3);
         const std::string header = std::string(head) + "\n" + std::string(20 + 2 + 14 + 15 + 11 + 11 + 13 + 13 + 13 + 19 + 19 + 19, '-') + "\n";
         if (!a_.output_pu_covariances) {
-            os << header;
-            for (uint32_t i : StationOrder(nullptr))
-                PrintPosUncertainty(os, i);
+            for (const auto& blk : BlockStationLists()) {
+                if (blk.first >= 0)
+                    os << "Block " << blk.first + 1 << "\n";
+                os << header;
+                for (uint32_t i : StationOrder(blk.first != -1 ? &blk.second : nullptr))
+                    PrintPosUncertainty(os, i);
+                if (blk.first >= 0)
+                    os << "\n";
+            }
             return;
         }
         // --output-all-covariances (PrintPosUncertainty PRN:4438-4484): after each station, its 3x3 covariance blocks with the
@@ -114,17 +120,45 @@
     // ---- .cor (PrintNetworkStationCorrections PRN:1349-1408, PrintCorStation PRN:4146-4230) -----------------------------
     // Per station: azimuth, vertical angle, slope and horizontal distance of the shift a-priori -> adjusted position and
     // its local e / n / up components; stations inside both thresholds are left out.
+    // the station lists of a report: one list of every station, or — phased modes with --output-stn-blocks — one per .seg
+    // block (inner and junction stations); block-1 mode stops after the first (PRN:535-595, 1349-1408, 2665-2770)
+    std::vector<std::pair<int, std::vector<uint32_t>>> BlockStationLists() const
+    {
+        std::vector<std::pair<int, std::vector<uint32_t>>> lists;
+        const bool phased = a_.adjust_mode != SimultaneousMode && !seg_.isl.empty();
+        if (!phased || (!a_.output_stn_blocks && a_.adjust_mode != Phased_Block_1Mode)) {
+            lists.emplace_back(-1, std::vector<uint32_t>());
+            return lists;
+        }
+        for (size_t b = 0; b < seg_.isl.size(); ++b) {
+            std::vector<uint32_t> list(seg_.isl[b]);
+            if (b < seg_.jsl.size())
+                list.insert(list.end(), seg_.jsl[b].begin(), seg_.jsl[b].end());
+            std::sort(list.begin(), list.end());
+            list.erase(std::unique(list.begin(), list.end()), list.end());
+            lists.emplace_back(a_.output_stn_blocks ? (int)b : -2, list);
+            if (a_.adjust_mode == Phased_Block_1Mode)
+                break;
+        }
+        return lists;
+    }
+
     void PrintNetworkStationCorrections(const std::string& file) const
     {
         std::ofstream os(file);
         PrintStationFileHeader(os, "CORRECTIONS", file);
-        os << std::left << std::setw(35) << "Stations printed in blocks:" << "No\n" << std::string(80, '-') << "\n\n";
+        os << std::left << std::setw(35) << "Stations printed in blocks:" << (a_.adjust_mode != SimultaneousMode && a_.output_stn_blocks ? "Yes" : "No")
+           << "\n" << std::string(80, '-') << "\n\n";
         os << "Corrections to stations\n------------------------------------------\n\n";
         char buf[512];
         snprintf(buf, sizeof(buf), "%-20s%2s%19s%19s%19s%19s%11s%11s%11s", "Station", "", "Azimuth", "V. Angle", "S. Distance", "H. Distance",
                  "east", "north", "up");
-        os << buf << "\n" << std::string(20 + 2 + 4 * 19 + 3 * 11, '-') << "\n";
-        for (uint32_t i : StationOrder(nullptr)) {
+        const std::string header = std::string(buf) + "\n" + std::string(20 + 2 + 4 * 19 + 3 * 11, '-') + "\n";
+        for (const auto& blk : BlockStationLists()) {
+        if (blk.first >= 0)
+            os << "Block " << blk.first + 1 << "\n";
+        os << header;
+        for (uint32_t i : StationOrder(blk.first != -1 ? &blk.second : nullptr)) {
             const dna_stn_t& s = stn_[i];
             double o[3];
             OriginalXYZ(i, o);
@@ -149,4 +183,5 @@
             os << buf << "\n";
         }
         os << "\n";
+        }
     }

@@ -132,6 +132,12 @@
         apriori_xyz_ = est_;
         vcv_ = raw_vcv_;
         ApplyTypeBUncertainties();
+        if (a_.adj_msr_tstat) {   // the last run may not have asked for them: t = n-stat / sqrt(sigma zero)
+            const double sz = std::sqrt(stats_.sigma_zero);
+            for (dna_msr_t& m : msr_)
+                if (!m.ignore && m.measStart <= 2)
+                    m.TStat = std::fabs(sz) < 1.0e-10 ? 0.0 : m.NStat / sz;
+        }
         info_.nstations = (uint32_t)stn_.size();
         info_.nfronts = 0;
     }
