@@ -10,6 +10,12 @@
 // (MATH:363-369) and inverted by the reference's own compiled matrix_2d when
 // oracle/_ref/libref_matrix.so is loaded; otherwise by the plain Cholesky
 // below ("port" mode).
+//
+// Pinned by the reference's own end-to-end expected outputs (tests/test_golden.py):
+// sampleData/gnss.simult.adj.expected (every printed digit) and
+// sampleData/urban.phased.adj.expected (every terrestrial type; to the accuracy
+// of the exported geoid values), through tests/golden/*.npz; the reference's
+// matrix_2d, compiled in place, inverts the normals.
 #include "oracle.h"
 
 #include <dlfcn.h>
