@@ -27,6 +27,10 @@
  *   v_rigorousVariances_ (pattern blocks)    ADJ:7784-8060      gadj_get_vcv_block
  *   v_rigorousVariances_.at(block) (dense)   ADJ:3805, PRN:2942   gadj_get_block_vcv
  *   v_normals_ / At V^-1 l (before Solve)    ADJ:893-896        gadj_get_normals_block / gadj_get_rhs
+ *   bms_meta_.reduced / InitialiseMeasurement ADJ:296, 3913-3935 gadj_set_measurements_reduced
+ *   v_precAdjMsrsFull_ (bulk pattern blocks) ADJ:7784-8060, 6770 gadj_get_pair_vcvs
+ *   UpdateIgnoredMeasurements                ADJ:8750-9980      gadj_update_ignored_measurements
+ *   PrintCompMeasurements ("a-priori")       PRN:1938-2023      gadj_compute_measurements
  */
 #ifndef GADJ_H_
 #define GADJ_H_
