@@ -59,6 +59,22 @@ def main():
     msr = dna_ascii.read_measurements(os.path.join(SAMPLE, "gnss-network.msr"), stn)
     sol, msr_keys, msr_rows, stn_names, stn_rows = parse_expected(os.path.join(SAMPLE, "gnss.simult.adj.expected"))
     assert len(msr_rows) == 417 and len(stn_rows) == 43
+    # dnaimport writes the binary station file sorted by name (fileOrder keeps the order of the input file): same here,
+    # with the station indices of the measurement records following
+    names = [n.decode() for n in stn["stationName"]]
+    order = sorted(range(len(stn)), key=lambda i: names[i])
+    new_index = np.empty(len(stn), np.uint32)
+    new_index[order] = np.arange(len(stn), dtype=np.uint32)
+    stn = stn[order].copy()
+    msr["station1"] = new_index[msr["station1"]]
+    two = msr["measType"] != b"Y"
+    msr["station2"][two] = new_index[msr["station2"][two]]
+    # dnageoid stores the geoid separation of every station; the grid file is not reproduced here, but the expected table
+    # prints both heights, so N = h(Ellipse) - H(Ortho) is recovered from it (an input of the run, not a result: the
+    # adjustment of this GNSS-only network does not use it)
+    where = {n.decode(): i for i, n in enumerate(stn["stationName"])}
+    for n, row in zip(stn_names, stn_rows):
+        stn["geoidSep"][where[n]] = row[3] - row[2]
     out = os.path.join(ROOT, "tests", "golden", "gnss_sample.npz")
     np.savez_compressed(out, stn=stn, msr=msr, solution_keys=np.array(sorted(sol)), solution=np.array([sol[k] for k in sorted(sol)]),
                         msr_keys=np.array(msr_keys), msr_columns=np.array(["measured", "adjusted", "correction", "meas_sd", "adj_sd",

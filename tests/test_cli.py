@@ -351,6 +351,35 @@ def test_cli_reproduces_reference_expected_adj_gpu(cli_gpu, tmp_path):
     _golden_gnss_text(cli_gpu, tmp_path)
 
 
+REFERENCE_EXPECTED = "/root/reference/sampleData/gnss.simult.adj.expected"
+
+
+@pytest.mark.skipif(not os.path.exists(REFERENCE_EXPECTED), reason="needs the reference checkout (its expected file is not copied into this repo)")
+def test_cli_passes_the_reference_ci_check_on_the_gnss_network(cli_hostsim, tmp_path):
+    """The reference's own CI test `test-gnss-network` (CMakeLists.txt:1033-1034): `dnadiff gnss.simult.adj
+    gnss.simult.adj.expected --skip-headers 52 -t 0.001` — with the comparison rule of dnadiff restated in tools/dnadiff.py
+    (dnadiff.cpp:40-268: line by line, token by token, numbers within the tolerance, text exactly).  Our file has the same
+    line layout as the reference's, so everything after the first 52 lines is compared: the solution block, all 417
+    adjusted-measurement rows and the 43 adjusted-station rows."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("dnadiff", os.path.join(ROOT, "tools", "dnadiff.py"))
+    dnadiff = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(dnadiff)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "gnss_sample.npz"))
+    stn, msr = np.ascontiguousarray(z["stn"].astype(STN_DTYPE)), np.ascontiguousarray(z["msr"].astype(MSR_DTYPE))
+    _write_network(tmp_path, "gnss", stn, msr)
+    r = _run(cli_hostsim, tmp_path, "gnss", "--output-adj-msr", "--scale-normals-to-unity")     # the CI's adjust-gnss-network command line
+    assert r.returncode == 0, r.stderr
+    import io
+    log = io.StringIO()
+    differences = dnadiff.compare(os.path.join(tmp_path, "gnss.simult.adj"), REFERENCE_EXPECTED, tolerance=0.001, skip_headers=52, verbose=True, out=log)
+    assert differences == 0, log.getvalue()[:4000]
+    # the rule does bite: a changed digit is a difference
+    text = open(os.path.join(tmp_path, "gnss.simult.adj")).read().replace("336.64", "336.74", 1)
+    open(os.path.join(tmp_path, "tampered.adj"), "w").write(text)
+    assert dnadiff.compare(os.path.join(tmp_path, "tampered.adj"), REFERENCE_EXPECTED, tolerance=0.001, skip_headers=52) == 1
+
+
 def _golden_urban_text(exe, tmp_path):
     """`dnaadjust urban --output-adj-msr` on the reference's urban sample (tests/golden/urban_sample.npz: types
     A B G H K L M S V Y Z, the Y cluster given as latitude / longitude / orthometric height) against the rows of
