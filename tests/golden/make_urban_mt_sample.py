@@ -30,6 +30,13 @@ def main():
     msr = dna_ascii.read_measurements(os.path.join(SAMPLE, "urban-network.msr"), stn, reftran=True)
     sol, keys, rows, stn_names, stn_rows = parse_expected(os.path.join(SAMPLE, "urban_mt.phased-mt.adj.expected"))
     assert len(rows) == 1182 and len(stn_rows) == 149, (len(rows), len(stn_rows))
+    # the exported geoid file carries N to a millimetre; the expected table prints both heights of every station to a tenth
+    # of that, so the separation the run used is recovered as h(Ellipse) - H(Ortho) (an input of the run: the geoid model)
+    where = {n.decode(): i for i, n in enumerate(stn["stationName"])}
+    for n, row in zip(stn_names, stn_rows):
+        i = where[n]
+        stn["geoidSep"][i] = row[3] - row[2]
+        stn["currentHeight"][i] = stn["initialHeight"][i] + float(stn["geoidSep"][i])
     out = os.path.join(ROOT, "tests", "golden", "urban_mt_sample.npz")
     np.savez_compressed(out, stn=stn, msr=msr, solution_keys=np.array(sorted(sol)), solution=np.array([sol[k] for k in sorted(sol)]),
                         msr_keys=np.array(keys), msr_rows=rows, stn_names=np.array(stn_names), stn_rows=stn_rows)

@@ -395,7 +395,7 @@ def _golden_urban_text(exe, tmp_path):
     sol, keys, rows, stn_names, stn_rows = parse_expected(os.path.join(tmp_path, "urban.simult.adj"))
     want = dict(zip(z["solution_keys"].tolist(), z["solution"].tolist()))
     assert all(sol[k] == want[k] for k in ("unknowns", "measurements", "dof", "outliers"))
-    assert abs(sol["chi_squared"] - want["chi_squared"]) < 1.0 and abs(sol["sigma_zero"] - want["sigma_zero"]) < 0.0011
+    assert abs(sol["chi_squared"] - want["chi_squared"]) < 0.2 and abs(sol["sigma_zero"] - want["sigma_zero"]) < 0.0011
     assert keys == z["msr_keys"].tolist() and len(keys) == 1182
     sec = np.radians(1.0 / 3600.0)
     for key, got, w in zip(keys, rows, z["msr_rows"]):
@@ -404,15 +404,15 @@ def _golden_urban_text(exe, tmp_path):
         unit = sec if ang else 1.0
         assert abs(got[0] - w[0]) / unit < 1.1e-4, key                                   # the measurement as given
         assert np.abs(got[3:6] - w[3:6]).max() < (2.6e-4 if ang else 1.1e-4), (key, got, w)     # the three SD columns
-        tol = (0.6 if t in "VZ" else 0.05) if ang else 8e-4
+        tol = (0.07 if t in "VZ" else 0.01) if ang else 3e-4
         assert abs(got[1] - w[1]) / unit < tol and abs(got[2] - w[2]) < tol, (key, got, w)
-        assert abs(got[6] - w[6]) < 0.08 and abs(got[7] - w[7]) < 0.011, (key, got, w)
-        assert abs(got[8] - w[8]) < (0.05 if ang else 1.1e-3), (key, got, w)
+        assert abs(got[6] - w[6]) < 0.021 and abs(got[7] - w[7]) < 0.011, (key, got, w)
+        assert abs(got[8] - w[8]) < (0.05 if ang else 3e-4), (key, got, w)
     # dnaimport sorts the station file by name; the fixture keeps the order of the ASCII file — pair the rows by name
     assert sorted(stn_names) == sorted(z["stn_names"].tolist())
     stn_rows = stn_rows[[stn_names.index(n) for n in z["stn_names"].tolist()]]
     assert np.abs(stn_rows[:, [0, 1]] - z["stn_rows"][:, [0, 1]]).max() < 2e-9          # latitude, longitude as ddd.mmsssssss
-    assert np.abs(stn_rows[:, 3:7] - z["stn_rows"][:, 3:7]).max() < 7e-4                # h, X Y Z
+    assert np.abs(stn_rows[:, 3:7] - z["stn_rows"][:, 3:7]).max() < 2.1e-4                # h, X Y Z
     assert np.abs(stn_rows[:, 7:10] - z["stn_rows"][:, 7:10]).max() < 1.1e-4            # SD e n up
 
 
@@ -450,7 +450,7 @@ def _golden_urban_mt_text(exe, tmp_path):
     sol, keys, rows, stn_names, stn_rows = parse_expected(os.path.join(tmp_path, "urban_mt.phased-mt.adj"))
     want = dict(zip(z["solution_keys"].tolist(), z["solution"].tolist()))
     assert all(sol[k] == want[k] for k in ("unknowns", "measurements", "dof", "outliers"))
-    assert abs(sol["chi_squared"] - want["chi_squared"]) < 1.0 and abs(sol["sigma_zero"] - want["sigma_zero"]) < 0.0011
+    assert abs(sol["chi_squared"] - want["chi_squared"]) < 0.2 and abs(sol["sigma_zero"] - want["sigma_zero"]) < 0.0011
     assert keys == z["msr_keys"].tolist() and len(keys) == 1182
     sec = np.radians(1.0 / 3600.0)
     for key, got, w in zip(keys, rows, z["msr_rows"]):
@@ -459,12 +459,12 @@ def _golden_urban_mt_text(exe, tmp_path):
         unit = sec if ang else 1.0
         assert abs(got[0] - w[0]) / unit < 1.1e-4, key                                   # the measurement as the file gave it
         assert np.abs(got[3:6] - w[3:6]).max() < (2.6e-4 if ang else 1.1e-4), (key, got, w)
-        tol = (0.6 if t in "VZ" else 0.05) if ang else 8e-4
+        tol = (0.07 if t in "VZ" else 0.01) if ang else 3e-4
         assert abs(got[1] - w[1]) / unit < tol and abs(got[2] - w[2]) < tol, (key, got, w)
-        assert abs(got[6] - w[6]) < 0.08 and abs(got[7] - w[7]) < 0.011, (key, got, w)
-        assert abs(got[8] - w[8]) < (0.05 if ang else 1.1e-3), (key, got, w)
+        assert abs(got[6] - w[6]) < 0.021 and abs(got[7] - w[7]) < 0.011, (key, got, w)
+        assert abs(got[8] - w[8]) < (0.05 if ang else 3e-4), (key, got, w)
     stn_rows = stn_rows[[stn_names.index(n) for n in z["stn_names"].tolist()]]
-    assert np.abs(stn_rows[:, [0, 1]] - z["stn_rows"][:, [0, 1]]).max() < 2e-9 and np.abs(stn_rows[:, 3:7] - z["stn_rows"][:, 3:7]).max() < 7e-4
+    assert np.abs(stn_rows[:, [0, 1]] - z["stn_rows"][:, [0, 1]]).max() < 2e-9 and np.abs(stn_rows[:, 3:7] - z["stn_rows"][:, 3:7]).max() < 2.1e-4
     assert np.abs(stn_rows[:, 7:10] - z["stn_rows"][:, 7:10]).max() < 1.1e-4
 
 

@@ -117,17 +117,19 @@ def _check_urban(g, stn, msr, est, vcv_of, stats):
     """tests/golden/urban_sample.npz: 149 stations (UTM, mixed constraints CCC / CCF / CFF / FFC), 1182 rows of types
     A B G H K L M S V Y Z, the Y cluster in latitude / longitude / orthometric height.  Every standard deviation the
     reference prints (measurement, adjusted measurement, correction; SD e/n/up of the stations) is reproduced at print
-    resolution; values that depend on station heights carry the 0.5 mm rounding of the exported geoid file the fixture
-    is built from (heights to 0.5 mm, zenith angles over 10-100 m lines to 0.5", levelled differences to 1 mm)."""
+    resolution; stations and linear measurements agree to 0.1-0.2 mm (the geoid separations of the fixture are good to
+    0.05 mm), horizontal angles to 0.005"; zenith angles over 10-100 m lines to 0.05": their deflection corrections are
+    taken at the coordinates of the moment a block is first adjusted, which in the expected *phased* run are not the
+    a-priori ones for every block."""
     sol = g["sol"]
     assert stats["unknowns"] == sol["unknowns"] and stats["measurements"] == sol["measurements"] and stats["dof"] == sol["dof"]
     assert stats["outliers"] == sol["outliers"]
-    assert abs(stats["chi_squared"] - sol["chi_squared"]) < 1.0            # 0.15 %
+    assert abs(stats["chi_squared"] - sol["chi_squared"]) < 0.2            # 0.03 %
     assert abs(stats["sigma_zero"] - sol["sigma_zero"]) < 0.0011 and abs(stats["pelzer"] - sol["pelzer"]) < 0.0011
     names = [n.decode() for n in stn["stationName"]]
     for name, row in zip(g["stn_names"], g["stn_rows"]):
         i = names.index(name)
-        assert np.abs(est[i] - row[4:7]).max() < 5e-4 and abs(stn["currentHeight"][i] - row[3]) < 6e-4, name
+        assert np.abs(est[i] - row[4:7]).max() < 1.5e-4 and abs(stn["currentHeight"][i] - row[3]) < 1.5e-4, name
         lat, lon = stn["currentLatitude"][i], stn["currentLongitude"][i]
         sl, cl, so, co = np.sin(lat), np.cos(lat), np.sin(lon), np.cos(lon)
         R = np.array([[-so, -sl * co, cl * co], [co, -sl * so, cl * so], [0, cl, sl]])
@@ -147,10 +149,10 @@ def _check_urban(g, stn, msr, est, vcv_of, stats):
         var = (m["term2"], m["term3"], m["term4"])[m["measStart"]] if t == "G" else m["term2"]
         sds = np.array([np.sqrt(var), np.sqrt(abs(m["measAdjPrec"])), np.sqrt(m["residualPrec"])]) / unit
         assert np.abs(sds - w[3:6]).max() < 0.51e-4 + (1.5e-4 if ang else 0.0), (key, sds, w[3:6])
-        tol_adj = (0.6 if t in "VZ" else 0.05) if ang else 7e-4
+        tol_adj = (0.07 if t in "VZ" else 0.01) if ang else 2e-4
         assert abs(m["measAdj"] - w[1]) / unit < tol_adj and abs(m["measCorr"] / unit - w[2]) < tol_adj, key
-        assert abs(m["NStat"] - w[6]) < 0.07 and abs(m["PelzerRel"] - w[7]) < 0.011, key
-        assert abs(m["preAdjCorr"] / unit - w[8]) < (0.05 if ang else 1e-3), key
+        assert abs(m["NStat"] - w[6]) < 0.015 and abs(m["PelzerRel"] - w[7]) < 0.011, key
+        assert abs(m["preAdjCorr"] / unit - w[8]) < (0.05 if ang else 2e-4), key
     assert seen == set("ABGHKLMSVYZ")
 
 
