@@ -76,4 +76,7 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    try:
+        sys.exit(main())
+    except BrokenPipeError:      # output cut short by the reader (| head)
+        sys.exit(1)
