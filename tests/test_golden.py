@@ -118,9 +118,9 @@ def _check_urban(g, stn, msr, est, vcv_of, stats):
     A B G H K L M S V Y Z, the Y cluster in latitude / longitude / orthometric height.  Every standard deviation the
     reference prints (measurement, adjusted measurement, correction; SD e/n/up of the stations) is reproduced at print
     resolution; stations and linear measurements agree to 0.1-0.2 mm (the geoid separations of the fixture are good to
-    0.05 mm), horizontal angles to 0.005"; zenith angles over 10-100 m lines to 0.05": their deflection corrections are
-    taken at the coordinates of the moment a block is first adjusted, which in the expected *phased* run are not the
-    a-priori ones for every block."""
+    0.05 mm), horizontal angles to 0.005"; zenith angles over 10-100 m lines to 0.05" (their deflection corrections
+    differ on a few lines — probably the phased expected run reducing a block at the coordinates carried in from earlier
+    blocks; in the re-adjusted urban_mt run the same column agrees to 0.001")."""
     sol = g["sol"]
     assert stats["unknowns"] == sol["unknowns"] and stats["measurements"] == sol["measurements"] and stats["dof"] == sol["dof"]
     assert stats["outliers"] == sol["outliers"]
