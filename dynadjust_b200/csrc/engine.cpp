@@ -6,6 +6,7 @@
 // mirroring dna_adjust::PrepareAdjustment / AdjustSimultaneous / Solve /
 // GenerateStatistics (ADJ:258, ADJ:2413-2511, ADJ:6586-6667, ADJ:6802-6841).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -458,8 +459,12 @@ int convert_llh_point_clusters(gadj_ctx* c)
         }
         i = std::max<uint64_t>(j, i + 1);
         const bool LLH = std::strncmp(m->coordType, "LLH", 3) == 0, LLh = std::strncmp(m->coordType, "LLh", 3) == 0;
-        if ((!LLH && !LLh) || m->ignore || rec.size() != count || j > c->nmsr)
+        if ((!LLH && !LLh) || m->ignore)
             continue;
+        if (rec.size() != count || j > c->nmsr)
+            return c->fail("truncated GNSS point cluster 'Y' (record " + std::to_string(rec.empty() ? j : rec[0]) + "): " +
+                           std::to_string(count) + " points announced, the measurement list ends after " +
+                           std::to_string(rec.size()));
         const uint32_t n = 3 * count;
         std::vector<double> V((size_t)n * n, 0.0), J((size_t)n * 3, 0.0);   // J: one 3x3 block per member
         auto sym = [&](uint32_t r, uint32_t col, double v) { V[(size_t)r * n + col] = V[(size_t)col * n + r] = v; };
@@ -658,7 +663,12 @@ int scan_measurements(gadj_ctx* c)
                 c->row_base.push_back((uint32_t)i);
                 c->non_gps = true;   // v_msrTally_.ContainsNonGPS() (ADJ:2457)
             } else if (m.measType == 'D') {
-                // derived angles between consecutive non-ignored directions (ADJ:5088-5129)
+                // derived angles between consecutive non-ignored directions (ADJ:5088-5129).  vectorCount2 = the number of
+                // directions that take part (dnaimport sets it, the RO included): a set that is not ignored needs two
+                if (m.vectorCount2 < 2 || m.vectorCount2 > m.vectorCount1)
+                    return c->fail("direction set (record " + std::to_string(i) + ") takes part in the adjustment with " +
+                                   std::to_string(m.vectorCount2) + " of " + std::to_string(m.vectorCount1) +
+                                   " directions: at least two non-ignored directions are needed (ignore the set otherwise)");
                 const uint32_t row0 = (uint32_t)c->rows.size();
                 uint64_t prev = i;
                 for (uint64_t j = i + 1; j < i + step && c->rows.size() - row0 + 1 < m.vectorCount2; ++j) {
@@ -1137,7 +1147,7 @@ int gadj_prepare(gadj_ctx* c)
     c->edge_lo.resize(c->nedge);
     std::vector<uint64_t> off_dest(c->nedge), diag_dest(c->nstn);
     std::vector<uint32_t> off_ld(c->nedge), diag_ld(c->nstn);
-    bool bad = false;
+    std::atomic<bool> bad{false};
     parallel_for(c->nedge, [&](uint64_t e0, uint64_t e1) {
         for (uint64_t ei = e0; ei < e1; ++ei) {
             uint32_t a = edges[ei].first, b2 = edges[ei].second;
@@ -1147,7 +1157,7 @@ int gadj_prepare(gadj_ctx* c)
             c->edge_lo[ei] = lo;
             uint64_t slot = find_slot(S, std::max(pa, pb), std::min(pa, pb));
             if (slot == UINT64_MAX) {
-                bad = true;
+                bad.store(true, std::memory_order_relaxed);
                 continue;
             }
             off_dest[ei] = S.ndest[slot];

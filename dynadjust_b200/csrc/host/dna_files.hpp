@@ -178,10 +178,20 @@ void load_binary(const std::string& path, std::vector<Rec>& recs, BinaryMeta& me
     if (!version_at_least(meta.version, 1, 2))
         throw std::runtime_error("LoadFile(): " + path + " predates observation_epoch support (v1.2); please re-run dnaimport.");
     read_metadata(f, meta);
+    const std::string read_error = "LoadFile(): An error was encountered when reading from " + path + ".";
+    if (!f)
+        throw std::runtime_error(read_error);
+    // the record count comes from the file: bound it by what the file can hold before allocating
+    const std::streamoff here = f.tellg();
+    f.seekg(0, std::ios::end);
+    const std::streamoff end = f.tellg();
+    f.seekg(here, std::ios::beg);
+    if (here < 0 || end < here || meta.binCount > (uint64_t)(end - here) / sizeof(Rec))
+        throw std::runtime_error(read_error);
     recs.resize(meta.binCount);
     f.read(reinterpret_cast<char*>(recs.data()), (std::streamsize)(sizeof(Rec) * meta.binCount));
     if (!f)
-        throw std::runtime_error("LoadFile(): An error was encountered when reading from " + path + ".");
+        throw std::runtime_error(read_error);
 }
 
 template <class Rec>
@@ -209,51 +219,78 @@ inline void load_seg(const std::string& path, Segmentation& seg)
     std::ifstream f(path);
     if (!f)
         throw std::runtime_error("LoadSegFile(): An error was encountered when opening " + path + ".");
+    const std::string bad = "LoadSegFile(): " + path + " is not a valid segmentation file: ";
+    // one unsigned field of a fixed-width row; blank or non-numeric fields are format errors, not exceptions from stoul
+    auto field = [&](const std::string& ln, size_t pos, size_t width, const char* what) -> uint32_t {
+        const std::string t = pos < ln.size() ? trim(ln.substr(pos, width)) : std::string();
+        if (t.empty() || t.size() > 9 || t.find_first_not_of("0123456789") != std::string::npos)
+            throw std::runtime_error(bad + what);
+        return (uint32_t)std::stoul(t);
+    };
+    auto next = [&](std::string& ln, const char* what) {
+        if (!std::getline(f, ln))
+            throw std::runtime_error(bad + "file ends before " + what);
+    };
     std::string line;
     uint32_t nblocks = 0;
     while (std::getline(f, line))
         if (line.find("No. blocks produced") != std::string::npos) {
-            nblocks = (uint32_t)std::stoul(trim(line.substr(35)));
+            nblocks = field(line, 35, std::string::npos, "block count");
             break;
         }
     if (!nblocks)
         throw std::runtime_error("LoadSegFile(): no blocks in " + path);
-    std::getline(f, line);  // dashes
-    std::getline(f, line);  // column header
+    next(line, "the block summary");  // dashes
+    next(line, "the block summary");  // column header
     std::vector<uint32_t> nj(nblocks), ni(nblocks), nm(nblocks);
     seg.net_id.assign(nblocks, 0);
     for (uint32_t b = 0; b < nblocks; ++b) {
-        std::getline(f, line);
-        line.resize(std::max<size_t>(line.size(), 92), ' ');
-        seg.net_id[b] = (uint32_t)std::stoul(trim(line.substr(14, 14)));
-        nj[b] = (uint32_t)std::stoul(trim(line.substr(28, 16)));
-        ni[b] = (uint32_t)std::stoul(trim(line.substr(44, 16)));
-        nm[b] = (uint32_t)std::stoul(trim(line.substr(60, 16)));
+        next(line, "the end of the block summary");
+        if (field(line, 0, 14, "block number in the summary") != b + 1)
+            throw std::runtime_error(bad + "summary rows are not numbered consecutively");
+        seg.net_id[b] = field(line, 14, 14, "network id");
+        nj[b] = field(line, 28, 16, "junction station count");
+        ni[b] = field(line, 44, 16, "inner station count");
+        nm[b] = field(line, 60, 16, "measurement count");
+        // total must equal inner + junction (seg_file.cpp:277)
+        if (field(line, 76, 16, "total station count") != ni[b] + nj[b])
+            throw std::runtime_error(bad + "total stations of block " + std::to_string(b + 1) + " is not inner + junction");
     }
     seg.isl.assign(nblocks, {});
     seg.jsl.assign(nblocks, {});
     seg.cml.assign(nblocks, {});
     for (uint32_t b = 0; b < nblocks; ++b) {
+        bool found = false;
         while (std::getline(f, line))
-            if (line.compare(0, 5, "Block") == 0)
+            if (line.compare(0, 5, "Block") == 0) {
+                found = true;
                 break;
-        std::getline(f, line);  // dashes
+            }
+        if (!found || field(line, 5, std::string::npos, "block header") != b + 1)
+            throw std::runtime_error(bad + "data of block " + std::to_string(b + 1) + " not found");
+        next(line, "block data");  // dashes
         for (int k = 0; k < 4; ++k)
-            std::getline(f, line);  // four count lines
-        std::getline(f, line);      // blank
-        std::getline(f, line);      // column header
-        std::getline(f, line);      // dashes
+            next(line, "block data");  // four count lines
+        next(line, "block data");      // blank
+        next(line, "block data");      // column header
+        next(line, "block data");      // dashes
         uint32_t rows = std::max(std::max(ni[b], nj[b]), nm[b]);
         for (uint32_t r = 0; r < rows; ++r) {
-            std::getline(f, line);
-            line.resize(std::max<size_t>(line.size(), 48), ' ');
-            std::string a = trim(line.substr(0, 16)), c = trim(line.substr(16, 16)), d = trim(line.substr(32, 16));
-            if (r < ni[b] && !a.empty())
-                seg.isl[b].push_back((uint32_t)std::stoul(a));
-            if (r < nj[b] && !c.empty())
-                seg.jsl[b].push_back((uint32_t)std::stoul(c));
-            if (r < nm[b] && !d.empty())
+            next(line, "the end of a block's station lists");
+            if (r < ni[b])
+                seg.isl[b].push_back(field(line, 0, 16, "inner station index"));
+            if (r < nj[b])
+                seg.jsl[b].push_back(field(line, 16, 16, "junction station index"));
+            if (r < nm[b]) {
+                // measurement index, optionally followed by its type letter
+                std::string d = 32 < line.size() ? trim(line.substr(32, 16)) : std::string();
+                size_t e = d.find_first_not_of("0123456789");
+                if (e != std::string::npos)
+                    d.resize(e);
+                if (d.empty() || d.size() > 9)
+                    throw std::runtime_error(bad + "measurement index");
                 seg.cml[b].push_back((uint32_t)std::stoul(d));
+            }
         }
     }
 }

@@ -23,7 +23,9 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -1187,6 +1189,340 @@ double norm_quantile(double p)
     return x;
 }
 
+// ComputeStatistics (ADJ:7116-7148) over one block / the whole network: c.N holds the rigorous variances (the inverse),
+// c.ell_rows the measured - computed values at the final estimates.  Adds to chi / outliers, writes the records.
+int compute_statistics(Ctx& c, double critical, double& chi, uint32_t& outliers)
+{
+    dna_msr_t* msr = c.msr;
+    dna_stn_t* stn = c.stn;
+    int rc = 0;
+        auto Q = [&](uint32_t i, uint32_t j) { return i >= j ? c.N[pidx(c.n, i, j)] : c.N[pidx(c.n, j, i)]; };
+        // ComputePrecisionAdjMsrs_A / _BCEKLMSVZ / _HIJPQR (ADJ:7880-8003): a Q a^T over the row's stations
+        auto row_precision = [&](const Row& rw) {
+            double prec = 0.;
+            for (int bs = 0; bs < rw.nst; ++bs)
+                for (int i = 0; i < 3; ++i) {
+                    double part = 0.;
+                    for (int bj = 0; bj < rw.nst; ++bj)
+                        for (int k = 0; k < 3; ++k)
+                            part += rw.a[3 * bj + k] * Q(3 * rw.st[bj] + k, 3 * rw.st[bs] + i);
+                    prec += part * rw.a[3 * bs + i];
+                }
+            return prec;
+        };
+        for (Meas& me : c.meas) {
+            dna_msr_t* m = &msr[me.first];
+            const uint32_t row = me.row0;
+            switch (me.type) {
+            case 'G':
+            case 'X':
+            case 'Y': {
+                const size_t members = me.type == 'G' ? 1 : me.rec.size();
+                for (size_t k = 0; k < members; ++k) {
+                    dna_msr_t* r = me.type == 'G' ? m : &msr[me.rec[k]];
+                    uint32_t s1 = r->station1 * 3, s2 = r->station2 * 3;
+                    double p6[6];
+                    if (me.type == 'Y') {
+                        // ComputePrecisionAdjMsrs_Y (ADJ:8035-8060)
+                        int q = 0;
+                        for (int i = 0; i < 3; ++i)
+                            for (int j = i; j < 3; ++j)
+                                p6[q++] = Q(s1 + i, s1 + j);
+                    } else
+                        precision_adjusted_gnss_bsl(c, s1, s2, p6);   // ComputePrecisionAdjMsrs_GX (ADJ:8006-8032)
+                    // UpdateMsrRecords_GXY (ADJ:8152-8184): XX row+0, YY row+3, ZZ row+5
+                    const uint32_t rr = row + 3 * (uint32_t)k;
+                    update_msr_record(r[0], c.ell_rows[rr + 0], p6[0], r[0].term2, critical, outliers);
+                    update_msr_record(r[1], c.ell_rows[rr + 1], p6[3], r[1].term3, critical, outliers);
+                    update_msr_record(r[2], c.ell_rows[rr + 2], p6[5], r[2].term4, critical, outliers);
+                }
+                if (me.type == 'G') {
+                    // ComputeChiSquare_G (ADJ:8530-8549)
+                    M3 Vinv;
+                    rc = inverse_gps_variance_G(c, m, Vinv);
+                    if (rc)
+                        return rc;
+                    double cs = 0.;
+                    for (int r = 0; r < 3; ++r)
+                        for (int col = 0; col < 3; ++col)
+                            cs += Vinv(r, col) * c.ell_rows[row + r] * c.ell_rows[row + col];
+                    chi += cs;
+                } else {
+                    // ComputeChiSquare_XY (ADJ:8552-8577): r^T V^-1 r with V^-1 from the records as they stand
+                    rc = load_variance_matrix_XY(c, me, false);
+                    if (rc)
+                        return rc;
+                    const uint32_t n = me.nrows;
+                    double cs = 0.;
+                    for (uint32_t j = 0; j < n; ++j) {
+                        double t = 0.;
+                        for (uint32_t i = 0; i < n; ++i)
+                            t += c.ell_rows[row + i] * me.vinv[(size_t)j * n + i];
+                        cs += t * c.ell_rows[row + j];
+                    }
+                    chi += cs;
+                }
+                break;
+            }
+            case 'D': {
+                // ComputePrecisionAdjMsrs_D (ADJ:7912-7946), UpdateMsrRecords_D (ADJ:8120-8149), ComputeChiSquare_D (ADJ:8440-8469)
+                for (uint32_t a = 0; a < me.nrows; ++a) {
+                    dna_msr_t& d = msr[me.rec[a]];
+                    const double prec = row_precision(c.row[row + a]);
+                    update_msr_record(d, c.ell_rows[row + a], prec, d.scale2, critical, outliers);
+                    d.measAdj = d.scale1 + d.measCorr;   // ADJ:8194-8199
+                    if (d.measAdj > TWO_PI)
+                        d.measAdj -= TWO_PI;
+                    d.measAdj += d.preAdjCorr;           // ADJ:8259-8268
+                    chi += c.ell_rows[row + a] * c.ell_rows[row + a] / d.scale2;
+                }
+                break;
+            }
+            default: {
+                const Row& rw = c.row[row];
+                const double prec = row_precision(rw);
+                update_msr_record(*m, c.ell_rows[row], prec, m->term2, critical, outliers);
+                const double* p1 = &c.est[3 * (size_t)m->station1];
+                const double* p2 = &c.est[3 * (size_t)m->station2];
+                const dna_stn_t& st1 = stn[m->station1];
+                switch (m->measType) {   // ADJ:8205-8271
+                case 'E':
+                    m->measAdj = ell_chord_to_arc(c.ell, m->measAdj, p1, p2, st1.currentLatitude, st1.currentLongitude,
+                                                  stn[m->station2].currentLatitude);
+                    break;
+                case 'M':
+                    m->measAdj = ell_chord_to_msl_arc(c.ell, m->measAdj, st1.currentLatitude, stn[m->station2].currentLatitude,
+                                                      st1.geoidSep, stn[m->station2].geoidSep);
+                    break;
+                case 'H':
+                case 'L':
+                    m->measAdj -= m->preAdjCorr;
+                    break;
+                case 'A':
+                case 'I':
+                case 'J':
+                case 'K':
+                case 'Z':
+                    m->measAdj += m->preAdjCorr;
+                    break;
+                case 'V':
+                    m->measAdj -= m->preAdjCorr;
+                    break;
+                }
+                chi += c.ell_rows[row] * c.ell_rows[row] / m->term2;   // ADJ:8430-8437
+            }
+            }
+        }
+    return rc;
+}
+
+// ComputeGlobalPelzer (ADJ:8302-8427): tally over one block
+void pelzer_tally(Ctx& c, double& sum, uint32_t& num)
+{
+    dna_msr_t* msr = c.msr;
+    auto tally = [&](dna_msr_t& r, double limit) {
+        if (r.PelzerRel > 0. && r.PelzerRel < limit) {
+            sum += (r.PelzerRel * r.PelzerRel - 1.);
+            num++;
+        } else
+            r.PelzerRel = UNRELIABLE;
+    };
+    for (Meas& me : c.meas) {
+        dna_msr_t* m = &msr[me.first];
+        switch (me.type) {
+        case 'G':
+            for (int k = 0; k < 3; ++k)
+                tally(m[k], UNRELIABLE);
+            break;
+        case 'X':
+        case 'Y':
+            for (uint64_t r0 : me.rec)
+                for (int k = 0; k < 3; ++k)
+                    tally(msr[r0 + k], UNRELIABLE);
+            break;
+        case 'D':
+            for (uint64_t r0 : me.rec)
+                tally(msr[r0], UNRELIABLE);   // ComputeGlobalPelzer_D (ADJ:8362-8393)
+            break;
+        default:
+            tally(*m, STABLE_LIMIT);          // ADJ:8339-8345
+        }
+    }
+}
+
+// ---- phased adjustment (AdjustPhased, ADJ:2579-2670) --------------------------------------------------------------
+// A network segmented into a chain of blocks (dnasegment's .seg): block b holds its inner stations ISL(b) and its
+// junction stations JSL(b), the stations that appear again in block b+1 (seg_file.cpp:432-486).  Every block is a small
+// dense network of its own here: copies of its station and measurement records with block-local station numbers, so that
+// the simultaneous-mode restatements above (design rows, normals, statistics) serve unchanged per block.
+uint64_t record_span(const dna_msr_t* msr, uint64_t nmsr, uint64_t i)
+{
+    const dna_msr_t& m = msr[i];
+    switch (m.measType) {
+    case 'G':
+        return 3;
+    case 'X':
+    case 'Y': {
+        uint64_t j = i;
+        for (uint32_t k = 0; k < m.vectorCount1 && j < nmsr; ++k)
+            j += 3 + 3ull * msr[j].vectorCount2;
+        return j - i;
+    }
+    case 'D':
+        return m.vectorCount1 ? m.vectorCount1 : 1;
+    default:
+        return 1;
+    }
+}
+
+// stations a measurement's rows refer to (the station lists dnasegment builds the blocks from)
+void stations_of(const dna_msr_t* msr, const Meas& me, std::vector<uint32_t>& out)
+{
+    out.clear();
+    auto touch = [&](const dna_msr_t& r) {
+        out.push_back(r.station1);
+        if (me.type != 'Y' && !std::strchr("HRIJPQ", me.type))
+            out.push_back(r.station2);
+        if (me.type == 'A')
+            out.push_back(r.station3);
+    };
+    touch(msr[me.first]);
+    for (uint64_t r : me.rec)
+        touch(msr[r]);
+    for (uint64_t r : me.base)
+        touch(msr[r]);
+}
+
+struct Block {
+    std::vector<uint32_t> stations;           // v_parameterStationList_: inner stations, then junction stations (global indices)
+    uint32_t n_inner = 0;
+    std::vector<uint32_t> jprev;              // local index in this block of every station of JSL(b-1), in JSL(b-1) order
+    std::vector<uint8_t> first_fwd;           // per local station: first appearance in a forward pass (seg_file.cpp:432-486)
+    std::vector<dna_stn_t> stn;               // block-local copies
+    std::vector<dna_msr_t> msr;
+    std::vector<uint64_t> src;                // source index of every copied record
+    Ctx c;
+    uint32_t n = 0;
+    std::vector<double> orig;                 // v_originalStations_
+    std::vector<double> corr_final;           // corrections of the rigorous solution of this iteration
+    std::vector<double> jvar_fwd, jest_fwd;   // v_junctionVariancesFwd_ (inverted, full column-major), v_junctionEstimatesFwd_ over JSL(b)
+    std::vector<double> Q;                    // v_rigorousVariances_ (packed)
+    explicit Block(const oracle_opts* o) : c(o) {}
+    uint32_t njunction() const { return (uint32_t)stations.size() - n_inner; }
+};
+
+// measurement part of the normals and of At V^-1 l at the block's current estimates (RebuildNormals ADJ:2721-2753 without
+// the parameter-station step; v_normalsR_ "contributions from all apriori measurement variances")
+void block_measurement_system(Block& B)
+{
+    std::fill(B.c.N.begin(), B.c.N.end(), 0.0);
+    update_normals(B.c);
+    weighted_rhs(B.c);
+}
+
+// AddConstraintStationstoNormalsForward / Reverse / Combine (ADJ:1884-2002): sign +1 adds, -1 removes
+int block_constraints(Block& B, int mode /*0 forward, 1 reverse, 2 combine*/)
+{
+    for (uint32_t s = 0; s < B.stations.size(); ++s) {
+        const bool first_rev = s < B.n_inner;   // last block the station appears in = the block it is inner to
+        double sign = 1.0;
+        if (mode == 0 && !B.first_fwd[s])
+            continue;
+        if (mode == 1 && !first_rev)
+            continue;
+        if (mode == 2) {
+            if (B.first_fwd[s])
+                continue;
+            sign = -1.0;                         // carried in from the forward pass already: applied twice otherwise
+        }
+        M3 V;
+        int rc = constraint_block(B.c, B.stn[s], V);
+        if (rc)
+            return rc;
+        for (int col = 0; col < 3; ++col)
+            for (int r = col; r < 3; ++r)
+                B.c.N[pidx(B.n, s * 3 + r, s * 3 + col)] += sign * V(r, col);
+    }
+    return 0;
+}
+
+// Junction stations as pseudo measurements (CarryStnEstimatesandVariances{Forward,Reverse,Combine}, ADJ:998-1281,
+// 3196-3333): the inverted junction variance matrix J (full, 3j x 3j, over `idx`) is added to the normals and
+// J (carried estimates - current estimates) to At V^-1 l  (the reference grows AtVinv / measMinusComp by the pseudo rows
+// and multiplies; the product is this sum).
+void add_junction_pseudo_measurements(Block& B, const std::vector<uint32_t>& idx, const std::vector<double>& J,
+                                      const std::vector<double>& jest)
+{
+    const uint32_t nj = 3 * (uint32_t)idx.size();
+    std::vector<double> d(nj);
+    for (uint32_t a = 0; a < idx.size(); ++a)
+        for (int k = 0; k < 3; ++k)
+            d[3 * a + k] = jest[3 * a + k] - B.c.est[3 * idx[a] + k];
+    for (uint32_t a = 0; a < nj; ++a) {
+        const uint32_t ra = 3 * idx[a / 3] + a % 3;
+        double t = 0.;
+        for (uint32_t b = 0; b < nj; ++b) {
+            const uint32_t rb = 3 * idx[b / 3] + b % 3;
+            const double v = J[(size_t)b * nj + a];
+            if (ra >= rb)
+                B.c.N[pidx(B.n, ra, rb)] += v;
+            t += v * d[b];
+        }
+        B.c.w[ra] += t;
+    }
+}
+
+// Solve (ADJ:6586-6667) on a block whose normals and At V^-1 l are complete; estimates += corrections
+int block_solve(Block& B, double* t_inv)
+{
+    Ctx& c = B.c;
+    std::vector<double> sdiag;
+    if (c.o->scale_normals_to_unity) {
+        sdiag.resize(c.n);
+        for (uint32_t i = 0; i < c.n; ++i)
+            sdiag[i] = 1.0 / std::sqrt(c.N[pidx(c.n, i, i)]);
+        for (uint32_t j = 0; j < c.n; ++j)
+            for (uint32_t i = j; i < c.n; ++i)
+                c.N[pidx(c.n, i, j)] *= sdiag[i] * sdiag[j];
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = inverse_packed(c.N, c.n, c.use_ref);
+    *t_inv += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (rc) {
+        g_err = "Matrix inversion failed, the matrix is singular.";
+        return rc;
+    }
+    if (c.o->scale_normals_to_unity)
+        for (uint32_t j = 0; j < c.n; ++j)
+            for (uint32_t i = j; i < c.n; ++i)
+                c.N[pidx(c.n, i, j)] *= sdiag[i] * sdiag[j];
+    sym_packed_mv(c.N, c.n, c.w.data(), c.corr.data(), c.use_ref);
+    for (uint32_t k = 0; k < c.n; ++k)
+        c.est[k] += c.corr[k];
+    return 0;
+}
+
+// variances and estimates of the stations `idx` of an adjusted block -> inverted junction variance matrix + estimates
+int junction_carry(const Block& B, const std::vector<uint32_t>& idx, bool use_ref, std::vector<double>& J, std::vector<double>& jest)
+{
+    const uint32_t nj = 3 * (uint32_t)idx.size();
+    J.assign((size_t)nj * nj, 0.0);
+    jest.resize(nj);
+    auto Q = [&](uint32_t i, uint32_t j) { return i >= j ? B.c.N[pidx(B.n, i, j)] : B.c.N[pidx(B.n, j, i)]; };
+    for (uint32_t a = 0; a < nj; ++a) {
+        const uint32_t ra = 3 * idx[a / 3] + a % 3;
+        jest[a] = B.c.est[ra];
+        for (uint32_t b = 0; b < nj; ++b)
+            J[(size_t)b * nj + a] = Q(ra, 3 * idx[b / 3] + b % 3);
+    }
+    if (nj == 0)
+        return 0;
+    int rc = inverse_variance(J.data(), nj, false, use_ref);   // FormInverseVarianceMatrix (ADJ:1053, 1201)
+    if (rc)
+        g_err = "Matrix inversion failed, the junction station variance matrix is singular.";
+    return rc;
+}
+
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 }  // namespace
@@ -1415,163 +1751,19 @@ int oracle_adjust_simultaneous(const oracle_opts* opts, dna_stn_t* stn, uint32_t
     // ComputeStatistics (ADJ:7116-7148)
     uint32_t outliers = 0;
     double chi = 0.;
-    {
-        auto Q = [&](uint32_t i, uint32_t j) { return i >= j ? c.N[pidx(c.n, i, j)] : c.N[pidx(c.n, j, i)]; };
-        // ComputePrecisionAdjMsrs_A / _BCEKLMSVZ / _HIJPQR (ADJ:7880-8003): a Q a^T over the row's stations
-        auto row_precision = [&](const Row& rw) {
-            double prec = 0.;
-            for (int bs = 0; bs < rw.nst; ++bs)
-                for (int i = 0; i < 3; ++i) {
-                    double part = 0.;
-                    for (int bj = 0; bj < rw.nst; ++bj)
-                        for (int k = 0; k < 3; ++k)
-                            part += rw.a[3 * bj + k] * Q(3 * rw.st[bj] + k, 3 * rw.st[bs] + i);
-                    prec += part * rw.a[3 * bs + i];
-                }
-            return prec;
-        };
-        for (Meas& me : c.meas) {
-            dna_msr_t* m = &msr[me.first];
-            const uint32_t row = me.row0;
-            switch (me.type) {
-            case 'G':
-            case 'X':
-            case 'Y': {
-                const size_t members = me.type == 'G' ? 1 : me.rec.size();
-                for (size_t k = 0; k < members; ++k) {
-                    dna_msr_t* r = me.type == 'G' ? m : &msr[me.rec[k]];
-                    uint32_t s1 = r->station1 * 3, s2 = r->station2 * 3;
-                    double p6[6];
-                    if (me.type == 'Y') {
-                        // ComputePrecisionAdjMsrs_Y (ADJ:8035-8060)
-                        int q = 0;
-                        for (int i = 0; i < 3; ++i)
-                            for (int j = i; j < 3; ++j)
-                                p6[q++] = Q(s1 + i, s1 + j);
-                    } else
-                        precision_adjusted_gnss_bsl(c, s1, s2, p6);   // ComputePrecisionAdjMsrs_GX (ADJ:8006-8032)
-                    // UpdateMsrRecords_GXY (ADJ:8152-8184): XX row+0, YY row+3, ZZ row+5
-                    const uint32_t rr = row + 3 * (uint32_t)k;
-                    update_msr_record(r[0], c.ell_rows[rr + 0], p6[0], r[0].term2, critical, outliers);
-                    update_msr_record(r[1], c.ell_rows[rr + 1], p6[3], r[1].term3, critical, outliers);
-                    update_msr_record(r[2], c.ell_rows[rr + 2], p6[5], r[2].term4, critical, outliers);
-                }
-                if (me.type == 'G') {
-                    // ComputeChiSquare_G (ADJ:8530-8549)
-                    M3 Vinv;
-                    rc = inverse_gps_variance_G(c, m, Vinv);
-                    if (rc)
-                        return rc;
-                    double cs = 0.;
-                    for (int r = 0; r < 3; ++r)
-                        for (int col = 0; col < 3; ++col)
-                            cs += Vinv(r, col) * c.ell_rows[row + r] * c.ell_rows[row + col];
-                    chi += cs;
-                } else {
-                    // ComputeChiSquare_XY (ADJ:8552-8577): r^T V^-1 r with V^-1 from the records as they stand
-                    rc = load_variance_matrix_XY(c, me, false);
-                    if (rc)
-                        return rc;
-                    const uint32_t n = me.nrows;
-                    double cs = 0.;
-                    for (uint32_t j = 0; j < n; ++j) {
-                        double t = 0.;
-                        for (uint32_t i = 0; i < n; ++i)
-                            t += c.ell_rows[row + i] * me.vinv[(size_t)j * n + i];
-                        cs += t * c.ell_rows[row + j];
-                    }
-                    chi += cs;
-                }
-                break;
-            }
-            case 'D': {
-                // ComputePrecisionAdjMsrs_D (ADJ:7912-7946), UpdateMsrRecords_D (ADJ:8120-8149), ComputeChiSquare_D (ADJ:8440-8469)
-                for (uint32_t a = 0; a < me.nrows; ++a) {
-                    dna_msr_t& d = msr[me.rec[a]];
-                    const double prec = row_precision(c.row[row + a]);
-                    update_msr_record(d, c.ell_rows[row + a], prec, d.scale2, critical, outliers);
-                    d.measAdj = d.scale1 + d.measCorr;   // ADJ:8194-8199
-                    if (d.measAdj > TWO_PI)
-                        d.measAdj -= TWO_PI;
-                    d.measAdj += d.preAdjCorr;           // ADJ:8259-8268
-                    chi += c.ell_rows[row + a] * c.ell_rows[row + a] / d.scale2;
-                }
-                break;
-            }
-            default: {
-                const Row& rw = c.row[row];
-                const double prec = row_precision(rw);
-                update_msr_record(*m, c.ell_rows[row], prec, m->term2, critical, outliers);
-                const double* p1 = &c.est[3 * (size_t)m->station1];
-                const double* p2 = &c.est[3 * (size_t)m->station2];
-                const dna_stn_t& st1 = stn[m->station1];
-                switch (m->measType) {   // ADJ:8205-8271
-                case 'E':
-                    m->measAdj = ell_chord_to_arc(c.ell, m->measAdj, p1, p2, st1.currentLatitude, st1.currentLongitude,
-                                                  stn[m->station2].currentLatitude);
-                    break;
-                case 'M':
-                    m->measAdj = ell_chord_to_msl_arc(c.ell, m->measAdj, st1.currentLatitude, stn[m->station2].currentLatitude,
-                                                      st1.geoidSep, stn[m->station2].geoidSep);
-                    break;
-                case 'H':
-                case 'L':
-                    m->measAdj -= m->preAdjCorr;
-                    break;
-                case 'A':
-                case 'I':
-                case 'J':
-                case 'K':
-                case 'Z':
-                    m->measAdj += m->preAdjCorr;
-                    break;
-                case 'V':
-                    m->measAdj -= m->preAdjCorr;
-                    break;
-                }
-                chi += c.ell_rows[row] * c.ell_rows[row] / m->term2;   // ADJ:8430-8437
-            }
-            }
-        }
-    }
+    rc = compute_statistics(c, critical, chi, outliers);
+    if (rc)
+        return rc;
     res->chi_squared = chi;
     res->measurement_params = c.rows;
     res->unknown_params = unknownParams;
     res->dof = (int64_t)c.rows - (int64_t)unknownParams;  // ADJ:6856
     res->sigma_zero = res->dof != 0 ? chi / (double)res->dof : 0.;
     res->outliers = outliers;
-    // ComputeGlobalPelzer (ADJ:8302-8427)
     {
         double sum = 0.;
         uint32_t num = 0;
-        auto tally = [&](dna_msr_t& r, double limit) {
-            if (r.PelzerRel > 0. && r.PelzerRel < limit) {
-                sum += (r.PelzerRel * r.PelzerRel - 1.);
-                num++;
-            } else
-                r.PelzerRel = UNRELIABLE;
-        };
-        for (Meas& me : c.meas) {
-            dna_msr_t* m = &msr[me.first];
-            switch (me.type) {
-            case 'G':
-                for (int k = 0; k < 3; ++k)
-                    tally(m[k], UNRELIABLE);
-                break;
-            case 'X':
-            case 'Y':
-                for (uint64_t r0 : me.rec)
-                    for (int k = 0; k < 3; ++k)
-                        tally(msr[r0 + k], UNRELIABLE);
-                break;
-            case 'D':
-                for (uint64_t r0 : me.rec)
-                    tally(msr[r0], UNRELIABLE);   // ComputeGlobalPelzer_D (ADJ:8362-8393)
-                break;
-            default:
-                tally(*m, STABLE_LIMIT);          // ADJ:8339-8345
-            }
-        }
+        pelzer_tally(c, sum, num);
         res->global_pelzer = num > 0 ? std::sqrt(sum / num) : UNRELIABLE;
     }
 
@@ -1581,6 +1773,374 @@ int oracle_adjust_simultaneous(const oracle_opts* opts, dna_stn_t* stn, uint32_t
         for (uint32_t j = 0; j < c.n; ++j)
             for (uint32_t i = j; i < c.n; ++i)
                 vcv_full[(size_t)j * c.n + i] = vcv_full[(size_t)i * c.n + j] = c.N[pidx(c.n, i, j)];
+    return 0;
+}
+
+/* AdjustPhased (ADJ:2579-2670): forward pass (ADJ:2756-2852), reverse + combination pass (ADJ:3461-3590) per iteration. */
+int oracle_adjust_phased(const oracle_opts* opts, dna_stn_t* stn, uint32_t nstn, dna_msr_t* msr, uint64_t nmsr, uint32_t nblocks,
+                         const uint32_t* isl_off, const uint32_t* isl, double* est_xyz, double* stn_vcv, int32_t want_block,
+                         uint32_t* block_nstn, uint32_t* block_stations, double* block_vcv, oracle_result* res)
+{
+    g_err.clear();
+    std::memset(res, 0, sizeof(*res));
+    const bool use_ref = opts->use_ref && g_ref.h;
+    if (use_ref && g_ref.set_threads && opts->threads > 0)
+        g_ref.set_threads(opts->threads);
+    res->used_ref = use_ref ? 1 : 0;
+    double t0 = now_s();
+    double conf = opts->confidence_interval * 0.01;
+    conf += (1.0 - conf) / 2.0;
+    const double critical = norm_quantile(conf);
+    res->critical_value = critical;
+    if (nblocks == 0) {
+        g_err = "oracle: no blocks";
+        return 2;
+    }
+
+    // ---- block lists: ISL given; CML(b) = the measurements whose first-eliminated station is inner to b;
+    //      JSL(b) = (stations of CML(b) + JSL(b-1)) - ISL(b)   (what dnasegment writes to the .seg file)
+    std::vector<int32_t> block_of(nstn, -1);
+    for (uint32_t b = 0; b < nblocks; ++b)
+        for (uint32_t k = isl_off[b]; k < isl_off[b + 1]; ++k) {
+            if (isl[k] >= nstn || block_of[isl[k]] >= 0) {
+                g_err = "oracle: bad inner station list";
+                return 2;
+            }
+            block_of[isl[k]] = (int32_t)b;
+        }
+    Ctx g(opts);   // the whole list, only to split it into measurements
+    g.stn = stn;
+    g.nstn = nstn;
+    g.msr = msr;
+    g.nmsr = nmsr;
+    int rc = build_cml(g);
+    if (rc)
+        return rc;
+    std::vector<std::vector<size_t>> cml(nblocks);
+    std::vector<uint8_t> used(nstn, 0);
+    std::vector<uint32_t> touched;
+    uint32_t total_rows = 0;
+    for (size_t k = 0; k < g.meas.size(); ++k) {
+        stations_of(msr, g.meas[k], touched);
+        int32_t b = (int32_t)nblocks;
+        for (uint32_t s : touched) {
+            if (s >= nstn || block_of[s] < 0) {
+                g_err = "oracle: measurement refers to a station outside every block";
+                return 2;
+            }
+            used[s] = 1;
+            b = std::min(b, block_of[s]);
+        }
+        cml[b].push_back(k);
+        total_rows += g.meas[k].nrows;
+    }
+    uint32_t unknownParams = 0;
+    for (uint32_t s = 0; s < nstn; ++s) {
+        if (!used[s])
+            continue;
+        unknownParams += 3;
+        for (int k = 0; k < 3; ++k)
+            if (stn[s].stationConst[k] == 'C')
+                unknownParams--;
+    }
+
+    std::vector<std::unique_ptr<Block>> blocks;
+    std::vector<int32_t> local(nstn, -1);
+    std::vector<uint32_t> jprev_global;   // JSL(b-1), global indices
+    for (uint32_t b = 0; b < nblocks; ++b) {
+        blocks.emplace_back(new Block(opts));
+        Block& B = *blocks.back();
+        B.stations.assign(isl + isl_off[b], isl + isl_off[b + 1]);
+        B.n_inner = (uint32_t)B.stations.size();
+        std::vector<uint32_t> junction;
+        for (size_t k : cml[b]) {
+            stations_of(msr, g.meas[k], touched);
+            for (uint32_t s : touched)
+                if (block_of[s] != (int32_t)b)
+                    junction.push_back(s);
+        }
+        for (uint32_t s : jprev_global)
+            if (block_of[s] != (int32_t)b)
+                junction.push_back(s);
+        std::sort(junction.begin(), junction.end());
+        junction.erase(std::unique(junction.begin(), junction.end()), junction.end());
+        for (uint32_t s : junction)
+            if (block_of[s] < (int32_t)b) {
+                g_err = "oracle: the blocks do not form a chain (a junction station belongs to an earlier block)";
+                return 2;
+            }
+        if (b + 1 == nblocks && !junction.empty()) {
+            g_err = "oracle: the last block has junction stations";
+            return 2;
+        }
+        B.stations.insert(B.stations.end(), junction.begin(), junction.end());
+        for (uint32_t i = 0; i < B.stations.size(); ++i)
+            local[B.stations[i]] = (int32_t)i;
+        B.first_fwd.assign(B.stations.size(), 1);
+        for (uint32_t s : jprev_global) {
+            B.jprev.push_back((uint32_t)local[s]);
+            B.first_fwd[local[s]] = 0;
+        }
+        // block-local copies of the records
+        B.stn.resize(B.stations.size());
+        for (uint32_t i = 0; i < B.stations.size(); ++i)
+            B.stn[i] = stn[B.stations[i]];
+        for (size_t k : cml[b]) {
+            const Meas& me = g.meas[k];
+            const uint64_t span = record_span(msr, nmsr, me.first);
+            for (uint64_t r = me.first; r < me.first + span && r < nmsr; ++r) {
+                dna_msr_t rec = msr[r];
+                auto renumber = [&](uint32_t& st) {
+                    if (st < nstn && local[st] >= 0)
+                        st = (uint32_t)local[st];
+                };
+                renumber(rec.station1);
+                if (me.type != 'Y' && !std::strchr("HRIJPQ", me.type))
+                    renumber(rec.station2);
+                if (me.type == 'A')
+                    renumber(rec.station3);
+                B.msr.push_back(rec);
+                B.src.push_back(r);
+            }
+        }
+        for (uint32_t s : B.stations)
+            local[s] = -1;
+        jprev_global = junction;
+
+        // PrepareAdjustmentBlock (ADJ:2873-3003): design rows, variance matrices, first-run reductions
+        Ctx& c = B.c;
+        c.stn = B.stn.data();
+        c.nstn = (uint32_t)B.stn.size();
+        c.msr = B.msr.data();
+        c.nmsr = B.msr.size();
+        c.n = B.n = 3 * c.nstn;
+        c.use_ref = use_ref;
+        rc = build_cml(c);
+        if (rc)
+            return rc;
+        size_t gi = 0;
+        for (Meas& me : c.meas) {
+            me.row0 = c.rows;
+            c.rows += me.nrows;
+            if (me.type == 'G')
+                me.g = gi++;
+        }
+        c.est.resize(c.n);
+        for (uint32_t i = 0; i < c.nstn; ++i)
+            geo_to_cart(c.ell, B.stn[i].currentLatitude, B.stn[i].currentLongitude, B.stn[i].currentHeight, &c.est[3 * i],
+                        &c.est[3 * i + 1], &c.est[3 * i + 2]);
+        B.orig = c.est;
+        c.N.assign(psize(c.n), 0.0);
+        c.ell_rows.assign(c.rows, 0.0);
+        c.vinv.assign(c.cml.size() * 9, 0.0);
+        c.row.assign(c.rows, Row());
+        c.corr.assign(c.n, 0.0);
+        c.w.assign(c.n, 0.0);
+        rc = fill_design_normals(c, true);
+        if (rc)
+            return rc;
+    }
+    res->seconds_prepare = now_s() - t0;
+
+    const uint32_t NB = nblocks;
+    // UpdateAdjustment (ADJ:473-627): geographic coordinates of the station records from the blocks' estimates, in block
+    // order (UpdateGeographicCoordsPhased, ADJ:8711-8731: a junction station ends up with the values of the last block
+    // that holds it), for the blocks with local-frame measurements, the last block, or every block once the iteration
+    // has stopped; then the measured - computed values at the new estimates
+    auto update_adjustment = [&](bool iterate) -> int {
+        for (uint32_t b = 0; b < NB; ++b) {
+            Block& B = *blocks[b];
+            Ctx& c = B.c;
+            if (c.non_gps || b + 1 == NB || !iterate)
+                for (uint32_t i = 0; i < c.nstn; ++i) {
+                    dna_stn_t& st = stn[B.stations[i]];
+                    cart_to_geo(c.ell, c.est[3 * i], c.est[3 * i + 1], c.est[3 * i + 2], &st.currentLatitude,
+                                &st.currentLongitude, &st.currentHeight);
+                }
+        }
+        for (uint32_t b = 0; b < NB; ++b) {
+            Block& B = *blocks[b];
+            for (uint32_t i = 0; i < B.c.nstn; ++i) {
+                const dna_stn_t& st = stn[B.stations[i]];
+                B.stn[i].currentLatitude = st.currentLatitude;
+                B.stn[i].currentLongitude = st.currentLongitude;
+                B.stn[i].currentHeight = st.currentHeight;
+            }
+            int r2 = fill_design_normals(B.c, false);
+            if (r2)
+                return r2;
+        }
+        return 0;
+    };
+    double maxCorr = 0.;
+    uint32_t iter = 0;
+    std::vector<double> jvar_rev, jest_rev, NR, wR, est_fwd_last;
+    for (uint32_t it = 0; it < opts->max_iterations; ++it) {
+        ++iter;
+        maxCorr = 0.;
+        auto track = [&](const std::vector<double>& corr) {   // compute_maximum_value (MATC:1532-1555)
+            size_t mr = 0;
+            for (size_t k = 0; k < corr.size(); ++k)
+                if (std::fabs(corr[k]) > std::fabs(corr[mr]))
+                    mr = k;
+            if (!corr.empty() && std::fabs(corr[mr]) > std::fabs(maxCorr))
+                maxCorr = corr[mr];
+        };
+        double ts = now_s();
+        // ---- AdjustPhasedForward (ADJ:2756-2852)
+        for (uint32_t b = 0; b < NB; ++b) {
+            Block& B = *blocks[b];
+            B.c.est = B.orig;
+            block_measurement_system(B);
+            rc = block_constraints(B, 0);
+            if (rc)
+                return rc;
+            if (b > 0)   // CarryStnEstimatesandVariancesForward (ADJ:998-1128) left these with the previous block
+                add_junction_pseudo_measurements(B, B.jprev, blocks[b - 1]->jvar_fwd, blocks[b - 1]->jest_fwd);
+            rc = block_solve(B, &res->seconds_inverse);   // SolveTry + UpdateEstimatesForward (ADJ:3022-3060)
+            if (rc)
+                return rc;
+            if (b + 1 == NB) {
+                // the last block is rigorous after the forward pass
+                B.Q = B.c.N;
+                B.corr_final = B.c.corr;
+                est_fwd_last = B.c.est;
+                track(B.c.corr);
+            } else {
+                std::vector<uint32_t> jidx(B.njunction());
+                for (uint32_t i = 0; i < jidx.size(); ++i)
+                    jidx[i] = B.n_inner + i;
+                rc = junction_carry(B, jidx, use_ref, B.jvar_fwd, B.jest_fwd);
+                if (rc)
+                    return rc;
+            }
+        }
+        // ---- AdjustPhasedReverseCombine (ADJ:3461-3590); a single block is rigorous already
+        for (uint32_t bb = 0; NB > 1 && bb < NB; ++bb) {
+            const uint32_t b = NB - 1 - bb;
+            Block& B = *blocks[b];
+            // PrepareAdjustmentReverse (ADJ:3112-3167) / CarryReverseJunctions (ADJ:3833-3883): original coordinates,
+            // the measurement normals, junction stations of the block adjusted before, parameter stations (reverse)
+            B.c.est = B.orig;
+            block_measurement_system(B);
+            if (b + 1 < NB) {
+                std::vector<uint32_t> jidx(B.njunction());
+                for (uint32_t i = 0; i < jidx.size(); ++i)
+                    jidx[i] = B.n_inner + i;
+                add_junction_pseudo_measurements(B, jidx, jvar_rev, jest_rev);
+            }
+            rc = block_constraints(B, 1);
+            if (rc)
+                return rc;
+            const bool combine = b > 0 && b + 1 < NB;   // CombineRequired
+            if (combine) {   // BackupNormals (ADJ:3170-3192)
+                NR = B.c.N;
+                wR = B.c.w;
+            }
+            rc = block_solve(B, &res->seconds_inverse);   // reverse, in isolation (rigorous for the first block)
+            if (rc)
+                return rc;
+            if (b > 0) {
+                // CarryStnEstimatesandVariancesReverse (ADJ:1133-1281): the junction stations shared with block b-1
+                rc = junction_carry(B, B.jprev, use_ref, jvar_rev, jest_rev);
+                if (rc)
+                    return rc;
+            }
+            if (combine) {
+                // PrepareAdjustmentCombine (ADJ:3336-3396), CarryStnEstimatesandVariancesCombine (ADJ:3196-3333)
+                B.c.est = B.orig;
+                B.c.N = NR;
+                B.c.w = wR;
+                add_junction_pseudo_measurements(B, B.jprev, blocks[b - 1]->jvar_fwd, blocks[b - 1]->jest_fwd);
+                rc = block_constraints(B, 2);
+                if (rc)
+                    return rc;
+                rc = block_solve(B, &res->seconds_inverse);
+                if (rc)
+                    return rc;
+            }
+            // UpdateEstimatesFinal (ADJ:3744-3830)
+            if (b + 1 == NB) {
+                B.c.est = est_fwd_last;   // the rigorous forward solution of the last block stands
+                continue;
+            }
+            B.Q = B.c.N;
+            B.corr_final = B.c.corr;
+            track(B.c.corr);
+        }
+        res->seconds_solve += now_s() - ts;
+        // rigorous estimates become the original ones of the next iteration (ADJ:3815, 521-523)
+        for (auto& pb : blocks)
+            pb->orig = pb->c.est;
+        const bool iterate = std::fabs(maxCorr) > opts->iteration_threshold;
+        if (!iterate)
+            break;
+        // UpdateAdjustment(true) (ADJ:473-627): geographic coordinates where local-frame measurements need them, new
+        // measured - computed; the normals are rebuilt at the start of the next pass
+        rc = update_adjustment(true);
+        if (rc)
+            return rc;
+    }
+    res->iterations = iter;
+    res->max_corr = maxCorr;
+    res->converged = std::fabs(maxCorr) <= opts->iteration_threshold;
+
+    // ---- GenerateStatistics (ADJ:6802-6841): UpdateAdjustment(false), then per block with its rigorous variances
+    uint32_t outliers = 0;
+    double chi = 0., psum = 0.;
+    uint32_t pnum = 0;
+    rc = update_adjustment(false);
+    if (rc)
+        return rc;
+    for (uint32_t b = 0; b < NB; ++b) {
+        Block& B = *blocks[b];
+        Ctx& c = B.c;
+        c.N = B.Q;
+        rc = compute_statistics(c, critical, chi, outliers);
+        if (rc)
+            return rc;
+        pelzer_tally(c, psum, pnum);
+        // results back into the caller's records (station numbers restored)
+        for (size_t r = 0; r < B.msr.size(); ++r) {
+            dna_msr_t out = B.msr[r];
+            const dna_msr_t& in = msr[B.src[r]];
+            out.station1 = in.station1;
+            out.station2 = in.station2;
+            if (c.msr[r].measType == 'A')
+                out.station3 = in.station3;
+            msr[B.src[r]] = out;
+        }
+        auto Q = [&](uint32_t i, uint32_t j) { return i >= j ? B.Q[pidx(B.n, i, j)] : B.Q[pidx(B.n, j, i)]; };
+        for (uint32_t i = 0; i < B.n_inner; ++i) {
+            const uint32_t s = B.stations[i];
+            if (est_xyz)
+                for (int k = 0; k < 3; ++k)
+                    est_xyz[3 * (size_t)s + k] = c.est[3 * i + k];
+            if (stn_vcv)
+                for (int r = 0; r < 3; ++r)
+                    for (int k = 0; k < 3; ++k)
+                        stn_vcv[9 * (size_t)s + 3 * r + k] = Q(3 * i + r, 3 * i + k);
+        }
+        if ((int32_t)b == want_block) {
+            if (block_nstn)
+                *block_nstn = c.nstn;
+            if (block_stations)
+                std::memcpy(block_stations, B.stations.data(), c.nstn * sizeof(uint32_t));
+            if (block_vcv)
+                for (uint32_t j = 0; j < B.n; ++j)
+                    for (uint32_t i = 0; i < B.n; ++i)
+                        block_vcv[(size_t)j * B.n + i] = Q(i, j);
+        }
+        std::vector<double>().swap(B.Q);
+        std::vector<double>().swap(c.N);
+    }
+    res->chi_squared = chi;
+    res->measurement_params = total_rows;
+    res->unknown_params = unknownParams;
+    res->dof = (int64_t)total_rows - (int64_t)unknownParams;
+    res->sigma_zero = res->dof != 0 ? chi / (double)res->dof : 0.;
+    res->outliers = outliers;
+    res->global_pelzer = pnum > 0 ? std::sqrt(psum / pnum) : UNRELIABLE;
     return 0;
 }
 

@@ -83,6 +83,25 @@ int oracle_adjust_simultaneous(const oracle_opts* opts,
                                double* first_corr, double* vcv_full,
                                oracle_result* res);
 
+/*
+ * Phased adjustment (AdjustPhased, ADJ:2579-2670) of a network segmented into a chain of blocks: per iteration a
+ * forward pass (ADJ:2756-2852) that carries the junction stations' estimates and inverted variances into the next
+ * block as pseudo measurements (CarryStnEstimatesandVariancesForward, ADJ:998-1128), then a reverse pass with the
+ * combination adjustment of every intermediate block (ADJ:3461-3590, 1133-1281, 3196-3333); parameter-station
+ * constraints enter once per pass through the first-appearance rule (ADJ:1884-2002, seg_file.cpp:432-486).
+ * Every block is solved dense with the reference's explicit inverse, like oracle_adjust_simultaneous does the network.
+ *
+ * Blocks: the inner stations of block b are isl[isl_off[b] .. isl_off[b+1]); measurements belong to the block that
+ * holds their first-eliminated station, junction lists follow (the .seg chain rule: JSL(b) is part of block b+1).
+ * Outputs (may be NULL): est_xyz 3*nstn; stn_vcv 9*nstn (each station's rigorous 3x3 block from the block it is
+ * inner to); for block `want_block` (>= 0): its station count, station list (inner then junction) and dense
+ * column-major variance matrix (capacity (3 n)^2, n <= nstn).
+ */
+int oracle_adjust_phased(const oracle_opts* opts, dna_stn_t* stn, uint32_t nstn, dna_msr_t* msr, uint64_t nmsr,
+                         uint32_t nblocks, const uint32_t* isl_off, const uint32_t* isl, double* est_xyz, double* stn_vcv,
+                         int32_t want_block, uint32_t* block_nstn, uint32_t* block_stations, double* block_vcv,
+                         oracle_result* res);
+
 /* geodesy restatements exposed for unit tests */
 void oracle_geo_to_cart(double lat, double lon, double h, double a, double invf, double* xyz);
 void oracle_cart_to_geo(double x, double y, double z, double a, double invf, double* llh);

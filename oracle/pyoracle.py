@@ -49,6 +49,9 @@ def lib():
         L.oracle_adjust_simultaneous.argtypes = [C.POINTER(OracleOpts), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                  C.POINTER(OracleResult)]
+        L.oracle_adjust_phased.argtypes = [C.POINTER(OracleOpts), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_uint32),
+                                           C.c_void_p, C.c_void_p, C.POINTER(OracleResult)]
         L.oracle_spd_inverse.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
         L.oracle_geo_to_cart.argtypes = [C.c_double] * 5 + [C.c_void_p]
         L.oracle_cart_to_geo.argtypes = [C.c_double] * 5 + [C.c_void_p]
@@ -90,6 +93,41 @@ def adjust_simultaneous(stn, msr, opts=None, want_normals=False, want_vcv=False)
     if rc != 0:
         raise RuntimeError(f"oracle failed ({rc}): {L.oracle_last_error().decode()}")
     return dict(est=est.reshape(-1, 3), rhs=rhs, first_corr=corr, normals=normals, vcv=vcv, res=res)
+
+
+def adjust_phased(stn, msr, inner_station_lists, opts=None, want_block=-1):
+    """The reference's phased adjustment (forward pass, reverse pass, combination) over a chain of blocks given by
+    their inner-station lists.  Returns estimates, every station's rigorous 3x3 variance block and, for block
+    ``want_block``, its station list (inner then junction) and dense variance matrix."""
+    L = lib()
+    o = opts or default_opts()
+    off = np.zeros(len(inner_station_lists) + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(b) for b in inner_station_lists])
+    isl = np.concatenate([np.asarray(b, dtype=np.uint32) for b in inner_station_lists])
+    est = np.zeros((len(stn), 3))
+    vcv = np.zeros((len(stn), 3, 3))
+    res = OracleResult()
+    bn = C.c_uint32(0)
+    bst = bv = None
+    if want_block >= 0:
+        # capacity: a block never holds more stations than the network
+        cap = len(stn)
+        bst = np.zeros(cap, np.uint32)
+        # size the dense matrix from the block's own station count: run is cheap to bound by inner + all later stations
+        nmax = min(cap, len(inner_station_lists[want_block]) + cap)
+        bv = np.zeros((3 * nmax) * (3 * nmax)) if nmax <= 4000 else None
+        if bv is None:
+            raise ValueError("block too large for the dense block-variance output")
+    rc = L.oracle_adjust_phased(C.byref(o), _ptr(stn), len(stn), _ptr(msr), len(msr), len(inner_station_lists), _ptr(off),
+                                _ptr(isl), _ptr(est), _ptr(vcv), want_block, C.byref(bn), _ptr(bst), _ptr(bv), C.byref(res))
+    if rc != 0:
+        raise RuntimeError(f"phased oracle failed ({rc}): {L.oracle_last_error().decode()}")
+    out = dict(est=est, vcv=vcv, res=res)
+    if want_block >= 0:
+        n = bn.value
+        out["block_stations"] = bst[:n].copy()
+        out["block_vcv"] = bv[:(3 * n) * (3 * n)].reshape(3 * n, 3 * n).copy()
+    return out
 
 
 def spd_inverse(a, use_ref=True):

@@ -94,3 +94,45 @@ def test_variance_scaling_write_back(oracle):
     # scaling every VCV by 4 divides chi^2 by 4 and leaves the estimates unchanged (to solver accuracy)
     assert abs(out["res"].chi_squared * 4.0 - out2["res"].chi_squared) / out2["res"].chi_squared < 1e-6
     assert np.abs(out["est"] - out2["est"]).max() < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["gnss", "mixed", "terrestrial"])
+def test_phased_oracle_matches_simultaneous(oracle, kind):
+    """The reference's phased mode restated (forward pass with the junction-station carry ADJ:998-1128, reverse pass
+    ADJ:1133-1281, combination ADJ:3196-3333, first-appearance constraints ADJ:1884-2002) against its simultaneous mode
+    on the same network: one block is the same arithmetic bit for bit; chains of 3 and 5 blocks agree to the rounding of
+    the explicit junction-variance inversions.  This is the reference-side statement of "phased == simultaneous" that
+    the engine's supernodal elimination relies on."""
+    from dynadjust_b200 import synth_terrestrial
+    from tests import parity
+    if kind == "gnss":
+        stn, msr, _, _ = synth.gnss_network(300, 900, 5)
+    elif kind == "mixed":
+        stn, msr, _, _ = synth.mixed_network(300, 900, 6, n_distances=200, n_levels=150)
+    else:
+        stn, msr, _, _ = synth_terrestrial.terrestrial_network(300, 700, 7, scalars={"S": 150, "L": 100}, n_dir_sets=40)
+    s1, m1 = stn.copy(), msr.copy()
+    ref = oracle.adjust_simultaneous(s1, m1, want_vcv=True)
+    V = ref["vcv"]
+    qd = np.stack([V[3 * s:3 * s + 3, 3 * s:3 * s + 3] for s in range(len(stn))])
+    for width, exact in ((300, True), (100, False), (64, False)):
+        s2, m2 = stn.copy(), msr.copy()
+        blocks = parity.chain_blocks(len(stn), width)
+        ph = oracle.adjust_phased(s2, m2, blocks, want_block=min(1, len(blocks) - 1))
+        r1, r2 = ref["res"], ph["res"]
+        assert r2.iterations == r1.iterations and r2.converged
+        assert (r2.dof, r2.measurement_params, r2.unknown_params, r2.outliers) == \
+            (r1.dof, r1.measurement_params, r1.unknown_params, r1.outliers)
+        tol = 0.0 if exact else 1.0
+        assert np.abs(ph["est"] - ref["est"]).max() <= tol * 2e-9
+        assert abs(r2.sigma_zero - r1.sigma_zero) <= tol * 5e-9
+        assert np.abs(ph["vcv"] - qd).max() <= tol * 1e-12 * np.abs(qd).max()
+        assert abs(r2.global_pelzer - r1.global_pelzer) <= tol * 1e-12
+        for f, t in (("measCorr", 5e-9), ("measAdj", 5e-9), ("measAdjPrec", 1e-15), ("NStat", 1e-5), ("term2", 0.0)):
+            assert np.abs(m1[f] - m2[f]).max() <= (tol * t if t else 0.0), f
+        assert np.abs(s1["currentLatitude"] - s2["currentLatitude"]).max() <= tol * 1e-15
+        # the dense rigorous variance matrix the reference keeps per block (v_rigorousVariances_, ADJ:3805)
+        bs = ph["block_stations"]
+        idx = (3 * bs[:, None] + np.arange(3)[None, :]).ravel()
+        assert np.abs(ph["block_vcv"] - V[np.ix_(idx, idx)]).max() <= tol * 1e-12 * np.abs(V).max()
+
