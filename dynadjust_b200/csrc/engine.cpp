@@ -135,20 +135,26 @@ template <class T>
 struct DevArray {
     T* p = nullptr;
     size_t n = 0;
+    bool shared = false;     // peer-visible allocation (multi-GPU exchange buffers)
     ~DevArray() { release(); }
     void release()
     {
-        if (p)
-            dev::free_(p);
+        if (p) {
+            if (shared)
+                dev::free_shared(p);
+            else
+                dev::free_(p);
+        }
         p = nullptr;
         n = 0;
     }
-    bool resize(size_t count)
+    bool resize(size_t count, bool peer_visible = false)
     {
         release();
+        shared = peer_visible;
         if (count == 0)
             return true;
-        p = (T*)dev::alloc(count * sizeof(T));
+        p = (T*)(shared ? dev::alloc_shared(count * sizeof(T)) : dev::alloc(count * sizeof(T)));
         n = p ? count : 0;
         return p != nullptr;
     }
@@ -168,6 +174,7 @@ struct DevArray {
 struct gadj_ctx {
     gadj_opts o{};
     std::string err;
+    dev::Device* device = nullptr;   // this context's device state (ordinal, stream); made current by every entry point
     Ellipsoid ell{};
     // borrowed host data
     dna_stn_t* stn = nullptr;
@@ -198,6 +205,15 @@ struct gadj_ctx {
     bool prepared = false, factor_valid = false, inverse_valid = false, normals_valid = false;
     bool stage_normals = false, vcv_extracted = false;
     int32_t mg_rank = 0, mg_world = 1;
+    // multi-GPU: peer table (byte offsets to the other ranks' replicas, their barrier counters), filled by gadj_mg_connect
+    bool connected = false;
+    PeerTable peers{};
+    DevArray<PeerTable> d_peers;
+    DevArray<unsigned long long> d_counter;
+    uint64_t barrier_round = 0;
+    std::vector<std::pair<void*, int64_t>> peer_maps;   // mapped peer buffers (pointer, owning process) to unmap on destroy
+    DevArray<ReduceOp> d_reduce, d_reduce_misc;
+    DevArray<double> d_apply;
     DevArray<uint8_t> d_pos_owned;
     uint32_t iteration = 0;
     double critical = 0;
@@ -222,6 +238,7 @@ struct gadj_ctx {
     DevArray<GemvOp> d_gemv;
     DevArray<TransposeOp> d_tr;
     DevArray<GatherOp> d_gather;
+    const PeerTable* pt() const { return d_peers.p; }
     std::vector<double> h_corr;
     void* ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint64_t device_bytes = 0;
@@ -265,21 +282,32 @@ struct gadj_ctx {
 
 namespace {
 
+// all ranks meet on the device (no host synchronisation): see launch_barrier
+void mg_barrier(gadj_ctx* c)
+{
+    if (c->mg_world <= 1)
+        return;
+    c->barrier_round++;
+    launch_barrier(c->pt(), c->barrier_round * (uint64_t)c->mg_world, c->d_info.p, dev::stream());
+}
+
 void run_one(gadj_ctx* c, const Launch& L)
 {
     void* st = dev::stream();
     {
-        if (L.kind == L_SYNC)
+        if (L.kind == L_BARRIER) {
+            mg_barrier(c);
             return;
+        }
         c->prof_begin(L.kind, L.flops, L.total_tiles, L.tag, L.level);
         if (L.kind == L_ZERO)
             c->launch_count--;  // a memset, not one of our kernels
         switch (L.kind) {
         case L_GEMM:
-            launch_gemm(c->d_gemm.p + L.op_begin, L.op_count, c->d_tiles.p + L.tile_begin, L.total_tiles, st);
+            launch_gemm(c->d_gemm.p + L.op_begin, L.op_count, c->d_tiles.p + L.tile_begin, L.total_tiles, c->pt(), L.mcast != 0, st);
             break;
         case L_DIAG:
-            launch_diag(c->d_diag.p + L.op_begin, L.op_count, c->d_info.p, st);
+            launch_diag(c->d_diag.p + L.op_begin, L.op_count, c->d_info.p, c->pt(), st);
             break;
         case L_TRI_FWD:
         case L_TRI_BWD:
@@ -297,11 +325,21 @@ void run_one(gadj_ctx* c, const Launch& L)
         case L_GATHER:
             launch_gather(c->d_gather.p + L.op_begin, L.op_count, L.total_tiles, st);
             break;
+        case L_ALLREDUCE: {
+            double* base = L.buf == MC_PANELS ? c->d_panels.p : L.buf == MC_X ? c->d_x.p : nullptr;
+            if (base)
+                launch_allreduce(c->d_reduce.p + L.op_begin, L.op_count, c->pt(), base, L.buf, st);
+            break;
+        }
         case L_ZERO:
             dev::zero(L.zero_ptr, L.zero_bytes);
             break;
         }
         c->prof_end();
+        // debugging aid (GADJ_SYNC_EVERY_LAUNCH=1): wait for every launch, so that no two kernels ever overlap
+        static const bool sync_every = getenv("GADJ_SYNC_EVERY_LAUNCH") != nullptr;
+        if (sync_every)
+            dev::sync();
     }
 }
 
@@ -959,12 +997,14 @@ int gadj_create(const gadj_opts* o, gadj_ctx** out)
     gadj_default_opts(&d);
     if (o)
         d = *o;
-    std::string e = dev::init(d.device);
-    if (!e.empty()) {
+    std::string e;
+    dev::Device* device = dev::open(d.device, e);
+    if (!device) {
         g_create_error = e;
         return 1;
     }
     gadj_ctx* c = new gadj_ctx();
+    c->device = device;
     c->o = d;
     if (c->o.leaf_stations == 0)
         c->o.leaf_stations = 96;
@@ -982,17 +1022,23 @@ void gadj_destroy(gadj_ctx* c)
 {
     if (!c)
         return;
+    dev::use(c->device);
     dev::sync();
     for (auto& e : c->ev)
         if (e)
             dev::event_destroy(e);
     for (auto& e : c->prof_ev)
         dev::event_destroy(e);
-    delete c;
+    for (auto& m : c->peer_maps)
+        dev::peer_unmap(m.first, m.second);
+    dev::Device* device = c->device;
+    delete c;          // frees the device arrays while the device is still current
+    dev::close(device);
 }
 
 int gadj_set_stations(gadj_ctx* c, dna_stn_t* stn, uint32_t count)
 {
+    dev::use(c->device);
     if (!stn || count == 0)
         return c->fail("empty station list");
     c->stn = stn;
@@ -1003,6 +1049,7 @@ int gadj_set_stations(gadj_ctx* c, dna_stn_t* stn, uint32_t count)
 
 int gadj_set_measurements(gadj_ctx* c, dna_msr_t* msr, uint64_t count)
 {
+    dev::use(c->device);
     if (!msr || count == 0)
         return c->fail("empty measurement list");
     c->msr = msr;
@@ -1013,6 +1060,7 @@ int gadj_set_measurements(gadj_ctx* c, dna_msr_t* msr, uint64_t count)
 
 int gadj_set_measurements_reduced(gadj_ctx* c, int reduced)
 {
+    dev::use(c->device);
     c->reduced = reduced ? 1 : 0;
     c->prepared = false;
     return 0;
@@ -1020,6 +1068,7 @@ int gadj_set_measurements_reduced(gadj_ctx* c, int reduced)
 
 int gadj_set_blocks(gadj_ctx* c, uint32_t nblocks, const uint32_t* isl_off, const uint32_t* isl)
 {
+    dev::use(c->device);
     c->isl_off.clear();
     c->isl.clear();
     if (nblocks > 1) {
@@ -1034,6 +1083,7 @@ int gadj_set_blocks(gadj_ctx* c, uint32_t nblocks, const uint32_t* isl_off, cons
 
 int gadj_prepare(gadj_ctx* c)
 {
+    dev::use(c->device);
     c->prepared = false;
     c->factor_valid = c->inverse_valid = c->normals_valid = false;
     c->iteration = 0;
@@ -1137,7 +1187,8 @@ int gadj_prepare(gadj_ctx* c)
     if (const char* fp = getenv("GADJ_DUMP_FRONTS")) {   // ordering studies: level, own unknowns, boundary unknowns, flops
         if (FILE* f = fopen(fp, "w")) {
             for (const Front& fr : S.fronts)
-                fprintf(f, "%d,%u,%u,%.6e\n", fr.level, fr.k, fr.r, fr.work);
+                fprintf(f, "%d,%u,%u,%.6e,%llu,%u,%u\n", fr.level, fr.k, fr.r, fr.work, (unsigned long long)fr.panel_off, fr.ldk,
+                        fr.own_begin);
             fclose(f);
         }
     }
@@ -1240,7 +1291,9 @@ int gadj_prepare(gadj_ctx* c)
     build_rowidx(S, c->plan);
     std::vector<double> z;
     bool ok = true;
-    ok &= c->d_msr.resize(c->nmsr + 64);   // slack: sharded uploads gather equal chunks of ceil(nmsr / ranks) records
+    const bool mg = c->mg_world > 1;   // buffers the other ranks read / write over NVLink are allocated peer-visible
+    c->connected = false;
+    ok &= c->d_msr.resize(c->nmsr + 64, mg);
     ok &= c->d_first.upload(c->first);
     ok &= c->d_edge.upload(c->edge_word);
     ok &= c->d_binc_ptr.upload(c->binc_ptr);
@@ -1275,19 +1328,21 @@ int gadj_prepare(gadj_ctx* c)
     ok &= c->d_noff.resize(9 * (size_t)c->nedge);
     ok &= c->d_w.resize(3 * (size_t)c->nstn);
     ok &= c->d_dscale.resize(3 * (size_t)c->nstn);
-    ok &= c->d_x.resize(3 * (size_t)c->nstn);
+    ok &= c->d_x.resize(3 * (size_t)c->nstn, mg);
     ok &= c->d_y.resize(3 * (size_t)c->nstn);
-    ok &= c->d_wbuf.resize(wbuf_doubles(S));
+    ok &= c->d_wbuf.resize(wbuf_doubles(S), mg);
     ok &= c->d_corr.resize(3 * (size_t)c->nstn + 8);
-    ok &= c->d_vcvd.resize(9 * (size_t)c->nstn);
-    ok &= c->d_vcvo.resize(9 * (size_t)c->nedge);
+    ok &= c->d_vcvd.resize(9 * (size_t)c->nstn, mg);
+    ok &= c->d_vcvo.resize(9 * (size_t)c->nedge, mg);
     ok &= c->d_sums.resize(8);
-    ok &= c->d_info.resize(4);
+    ok &= c->d_info.resize(4, mg);
+    ok &= c->d_counter.resize(2, mg);
+    ok &= c->d_apply.resize(APPLY_SCRATCH_DOUBLES);
     ok &= c->d_rowmap.upload(S.rowmap);
     ok &= c->d_tgt.resize(S.targets.size());
     ok &= c->d_coltgt.resize(S.bnd.size());
     ok &= c->d_rowidx.upload(c->plan.rowidx);
-    ok &= c->d_panels.resize(S.panel_doubles);
+    ok &= c->d_panels.resize(S.panel_doubles, mg);
     if (!ok)
         return c->fail("out of device memory while allocating the adjustment state");
     dev::h2d(c->d_msr.p, c->msr, c->nmsr * sizeof(dna_msr_t));
@@ -1319,7 +1374,7 @@ int gadj_prepare(gadj_ctx* c)
     else
         budget = (size_t)(0.6 * (double)dev::mem_free() / 8);
     size_t pool = std::max(least, std::min(want, budget));
-    if (!c->d_pool.resize(pool))
+    if (!c->d_pool.resize(pool, mg))
         return c->fail("out of device memory while allocating the inverse workspace");
 
     PlanBuffers pb;
@@ -1349,6 +1404,18 @@ int gadj_prepare(gadj_ctx* c)
     ok &= c->d_gemv.upload(c->plan.gemv);
     ok &= c->d_tr.upload(c->plan.transpose);
     ok &= c->d_gather.upload(c->plan.gather);
+    ok &= c->d_reduce.upload(c->plan.reduce);
+    {
+        // whole-vector reductions of a multi-GPU run: the solution vector, the station / pair variance blocks
+        std::vector<ReduceOp> misc = {ReduceOp{0, 3 * (uint64_t)c->nstn}, ReduceOp{0, 9 * (uint64_t)c->nstn},
+                                      ReduceOp{0, 9 * (uint64_t)c->nedge}};
+        ok &= c->d_reduce_misc.upload(misc);
+    }
+    dev::zero(c->d_info.p, c->d_info.bytes());
+    // the barrier counter starts at zero before any peer can see it (the handles are exchanged after gadj_prepare)
+    if (c->d_counter.p)
+        dev::zero(c->d_counter.p, c->d_counter.bytes());
+    c->barrier_round = 0;
     if (!ok)
         return c->fail("out of device memory while uploading the launch plan");
     e = dev::sync();
@@ -1363,6 +1430,7 @@ int gadj_prepare(gadj_ctx* c)
 
 int gadj_get_info(const gadj_ctx* c, gadj_info* info)
 {
+    dev::use(c->device);
     std::memset(info, 0, sizeof(*info));
     if (!c->prepared)
         return 1;
@@ -1394,14 +1462,40 @@ int gadj_get_info(const gadj_ctx* c, gadj_info* info)
 
 int gadj_upload_measurements(gadj_ctx* c)
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
-    dev::h2d(c->d_msr.p, c->msr, c->nmsr * sizeof(dna_msr_t));
+    if (c->mg_world <= 1 || !c->connected) {
+        dev::h2d(c->d_msr.p, c->msr, c->nmsr * sizeof(dna_msr_t));
+        return 0;
+    }
+    // multi-GPU: every rank sends 1/world of the list over its own PCIe link; the other shares are pulled from the peers'
+    // device copies over NVLink (every rank assembles from the whole list)
+    const uint64_t chunk = (c->nmsr + c->mg_world - 1) / c->mg_world;
+    auto range = [&](int q, uint64_t& first, uint64_t& count) {
+        first = std::min<uint64_t>(c->nmsr, (uint64_t)q * chunk);
+        count = std::min<uint64_t>(chunk, c->nmsr - first);
+    };
+    uint64_t first, count;
+    range(c->mg_rank, first, count);
+    mg_barrier(c);   // nobody still assembles from the previous copy
+    if (count)
+        dev::h2d(c->d_msr.p + first, c->msr + first, count * sizeof(dna_msr_t));
+    mg_barrier(c);
+    for (int q = 0; q < c->mg_world; ++q) {
+        if (q == c->mg_rank)
+            continue;
+        range(q, first, count);
+        if (count)
+            dev::d2d(c->d_msr.p + first, (const char*)(c->d_msr.p + first) + c->peers.delta[MC_MSR][q], count * sizeof(dna_msr_t));
+    }
+    mg_barrier(c);
     return 0;
 }
 
 int gadj_upload_measurements_range(gadj_ctx* c, uint64_t first, uint64_t count)
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     if (first > c->nmsr || count > c->nmsr - first)
@@ -1413,6 +1507,7 @@ int gadj_upload_measurements_range(gadj_ctx* c, uint64_t first, uint64_t count)
 
 int gadj_reset_estimates(gadj_ctx* c)
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     dev::d2d(c->d_est.p, c->d_est0.p, c->d_est.bytes());
@@ -1503,11 +1598,11 @@ static void fill_scatter(gadj_ctx* c, ScatterParams& sp)
 
 static int extract_vcv(gadj_ctx* c);
 
-// ---- staged execution -------------------------------------------------------------------------
-// gadj_iterate runs the stages back to back; a multi-GPU driver (dynadjust_b200/multigpu.py) calls them one by
-// one and exchanges the top fronts between stages where gadj_stage_run stops at a sync marker.
+// ---- the stages of one iteration --------------------------------------------------------------------
+// gadj_iterate runs them back to back.  In a multi-GPU run every rank executes the same sequence on its own
+// stream; the launch lists carry the device-side barriers and all-reduces that join the ranks (plan.cpp).
 
-int gadj_stage_begin(gadj_ctx* c, int flags)
+static int stage_begin(gadj_ctx* c, int flags)
 {
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
@@ -1570,45 +1665,7 @@ int gadj_stage_begin(gadj_ctx* c, int flags)
     return 0;
 }
 
-int gadj_stage_run(gadj_ctx* c, int phase, int64_t* cursor, int32_t* sync_level)
-{
-    if (!c->prepared)
-        return c->fail("gadj_prepare has not been run");
-    const std::vector<Launch>* list = nullptr;
-    switch (phase) {
-    case GADJ_PHASE_FACTOR:
-        list = &c->plan.factor;
-        break;
-    case GADJ_PHASE_FORWARD:
-        list = &c->plan.fwd;
-        break;
-    case GADJ_PHASE_BACKWARD:
-        list = &c->plan.bwd;
-        break;
-    case GADJ_PHASE_INVERSE:
-        list = &c->plan.selinv;
-        break;
-    default:
-        return c->fail("unknown phase");
-    }
-    int64_t i = cursor ? *cursor : 0;
-    int32_t lvl = -1;
-    for (; i < (int64_t)list->size(); ++i) {
-        if ((*list)[i].kind == L_SYNC) {
-            lvl = (*list)[i].level;
-            ++i;
-            break;
-        }
-        run_one(c, (*list)[i]);
-    }
-    if (cursor)
-        *cursor = i;
-    if (sync_level)
-        *sync_level = lvl;
-    return 0;
-}
-
-int gadj_stage_solve_begin(gadj_ctx* c)
+static int stage_solve_begin(gadj_ctx* c)
 {
     dev::event_record(c->ev[2]);
     c->prof_begin(PK_OTHER);
@@ -1618,24 +1675,35 @@ int gadj_stage_solve_begin(gadj_ctx* c)
     return 0;
 }
 
-int gadj_stage_solve_end(gadj_ctx* c)
+// multi-GPU: every rank holds the solution of the replicated top fronts and of its own subtrees; the entries of the other
+// ranks' subtrees are zeroed and the vector summed over the ranks (every rank updates all estimates: the next assembly
+// is replicated)
+static int stage_solve_end(gadj_ctx* c)
 {
-    if (c->mg_world > 1)
-        launch_mask_positions(c->d_x.p, c->d_pos_owned.p, c->nstn, dev::stream());
+    if (c->mg_world <= 1)
+        return 0;
+    void* st = dev::stream();
+    launch_mask_positions(c->d_x.p, c->d_pos_owned.p, c->nstn, st);
+    mg_barrier(c);
+    launch_allreduce(c->d_reduce_misc.p + 0, 1, c->pt(), c->d_x.p, MC_X, st);
+    mg_barrier(c);
+    // a non-positive pivot met by any rank (the owner of the pivot tile) is everybody's
+    launch_share_info(c->pt(), c->d_info.p, st);
+    mg_barrier(c);
     return 0;
 }
 
-int gadj_stage_apply(gadj_ctx* c)
+static int stage_apply(gadj_ctx* c)
 {
     c->prof_begin(PK_OTHER);
     c->launch_count++;  // two kernels: update + max reduction
-    launch_apply_corrections(c->d_x.p, c->d_dscale.p, c->d_pos.p, c->d_corr.p, c->d_est.p, c->nstn, dev::stream());
+    launch_apply_corrections(c->d_x.p, c->d_dscale.p, c->d_pos.p, c->d_corr.p, c->d_est.p, c->nstn, c->d_apply.p, dev::stream());
     c->prof_end();
     dev::event_record(c->ev[3]);
     return 0;
 }
 
-int gadj_stage_end(gadj_ctx* c, int flags, int32_t global_info, gadj_iter_result* res)
+static int stage_end(gadj_ctx* c, int flags, gadj_iter_result* res)
 {
     dev::event_record(c->ev[4]);
     int32_t info[4] = {0, 0, 0, 0};
@@ -1645,8 +1713,8 @@ int gadj_stage_end(gadj_ctx* c, int flags, int32_t global_info, gadj_iter_result
     std::string e = dev::sync();
     if (!e.empty())
         return c->fail(e);
-    if (global_info > info[0])
-        info[0] = global_info;   // another rank met a non-positive pivot
+    if (info[1] != 0)
+        return c->fail("multi-GPU barrier timed out: another rank has stopped");
     if (c->stage_normals) {
         if (info[0] != 0) {
             c->factor_valid = false;
@@ -1688,44 +1756,35 @@ int gadj_stage_end(gadj_ctx* c, int flags, int32_t global_info, gadj_iter_result
 
 int gadj_iterate(gadj_ctx* c, int flags, gadj_iter_result* res)
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
-    if (c->mg_world > 1)
-        return c->fail("this context is one shard of a multi-GPU adjustment: drive it through the staged calls");
-    if (gadj_stage_begin(c, flags))
+    if (c->mg_world > 1 && !c->connected)
+        return c->fail("this context is one rank of a multi-GPU adjustment: exchange the peer handles first (gadj_mg_connect)");
+    if (stage_begin(c, flags))
         return 1;
     if (c->stage_normals)
         run_launches(c, c->plan.factor);
-    gadj_stage_solve_begin(c);
+    stage_solve_begin(c);
     run_launches(c, c->plan.fwd);
     run_launches(c, c->plan.bwd);
-    gadj_stage_apply(c);
+    stage_solve_end(c);
+    stage_apply(c);
     if (flags & GADJ_ITER_INVERSE)
         run_launches(c, c->plan.selinv);
-    return gadj_stage_end(c, flags, 0, res);
-}
-
-int gadj_stage_normals_pending(gadj_ctx* c) { return c->stage_normals ? 1 : 0; }
-
-int gadj_stage_mark_inverse(gadj_ctx* c)
-{
-    std::string e = dev::sync();
-    if (!e.empty())
-        return c->fail(e);
-    c->inverse_valid = true;
-    c->vcv_extracted = false;
-    c->factor_valid = false;
-    return 0;
+    return stage_end(c, flags, res);
 }
 
 int gadj_sync(gadj_ctx* c)
 {
+    dev::use(c->device);
     std::string e = dev::sync();
     return e.empty() ? 0 : c->fail(e);
 }
 
 int gadj_mg_init(gadj_ctx* c, int32_t rank, int32_t world)
 {
+    dev::use(c->device);
     if (world < 1 || rank < 0 || rank >= world)
         return c->fail("bad rank / world size");
     c->mg_rank = rank;
@@ -1736,6 +1795,7 @@ int gadj_mg_init(gadj_ctx* c, int32_t rank, int32_t world)
 
 int gadj_mg_buffer(gadj_ctx* c, int which, void** ptr, uint64_t* count)
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     switch (which) {
@@ -1763,54 +1823,132 @@ int gadj_mg_buffer(gadj_ctx* c, int which, void** ptr, uint64_t* count)
         *ptr = c->d_msr.p;
         *count = c->d_msr.n * sizeof(dna_msr_t);
         break;
+    case 6:   // W = L11^-1 and its transpose of every owned front (diagnostics)
+        *ptr = c->d_wbuf.p;
+        *count = c->d_wbuf.n;
+        break;
+    case 7:   // selected-inverse workspace pool (diagnostics)
+        *ptr = c->d_pool.p;
+        *count = c->d_pool.n;
+        break;
     default:
         return c->fail("unknown buffer");
     }
     return 0;
 }
 
-int gadj_mg_top_fronts(gadj_ctx* c, int32_t level, uint32_t cap, uint32_t* n, uint64_t* panel_off, uint64_t* panel_len,
-                       uint64_t* x_off, uint64_t* x_len, int32_t* owner)
+// ---- multi-GPU: one rank per GPU, peers' buffers mapped over NVLink --------------------------------------------
+namespace {
+struct ExportedBuffer {
+    int which;
+    void* p;
+    size_t bytes;
+};
+// the peer-visible buffers of a prepared context, in gadj_peer_info order (index = McBuf, 0 = the barrier counter)
+void exported_buffers(gadj_ctx* c, ExportedBuffer out[GADJ_PEER_BUFFERS])
 {
+    for (int i = 0; i < GADJ_PEER_BUFFERS; ++i)
+        out[i] = ExportedBuffer{i, nullptr, 0};
+    out[0] = {0, c->d_counter.p, c->d_counter.bytes()};
+    out[MC_PANELS] = {MC_PANELS, c->d_panels.p, c->d_panels.bytes()};
+    out[MC_WBUF] = {MC_WBUF, c->d_wbuf.p, c->d_wbuf.bytes()};
+    out[MC_POOL] = {MC_POOL, c->d_pool.p, c->d_pool.bytes()};
+    out[MC_X] = {MC_X, c->d_x.p, c->d_x.bytes()};
+    out[MC_VCVD] = {MC_VCVD, c->d_vcvd.p, c->d_vcvd.bytes()};
+    out[MC_VCVO] = {MC_VCVO, c->d_vcvo.p, c->d_vcvo.bytes()};
+    out[MC_MSR] = {MC_MSR, c->d_msr.p, c->d_msr.bytes()};
+    out[MC_BUFS] = {MC_BUFS, c->d_info.p, c->d_info.bytes()};
+}
+}  // namespace
+
+int gadj_mg_export(gadj_ctx* c, gadj_peer_info* out)
+{
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
-    uint32_t k = 0;
-    if (level >= 0 && level < (int32_t)c->sym.levels.size())
-        for (uint32_t fi : c->sym.levels[level]) {
-            const Front& f = c->sym.fronts[fi];
-            if (!f.top)
-                continue;
-            if (k < cap) {
-                panel_off[k] = f.panel_off;
-                panel_len[k] = (uint64_t)f.m * f.ldk;
-                x_off[k] = 3ull * f.own_begin;
-                x_len[k] = f.k;
-                owner[k] = f.owner;
-            }
-            ++k;
-        }
-    *n = k;
+    if (c->mg_world <= 1)
+        return c->fail("not a multi-GPU context (gadj_mg_init)");
+    static_assert(GADJ_PEER_BUFFERS == MC_BUFS + 1, "peer buffer table");
+    static_assert(GADJ_IPC_HANDLE_BYTES == dev::IPC_HANDLE_BYTES, "IPC handle size");
+    std::memset(out, 0, sizeof(*out));
+    out->rank = c->mg_rank;
+    out->device = dev::ordinal();
+    out->pid = dev::process_id();
+    ExportedBuffer eb[GADJ_PEER_BUFFERS];
+    exported_buffers(c, eb);
+    for (int i = 0; i < GADJ_PEER_BUFFERS; ++i) {
+        out->ptr[i] = (uint64_t)(uintptr_t)eb[i].p;
+        out->bytes[i] = eb[i].bytes;
+        if (eb[i].p && !dev::ipc_export(eb[i].p, eb[i].bytes, out->handle[i]))
+            return c->fail("cannot export a device buffer to the other ranks (IPC handle)");
+    }
+    // the replicated part of the layout must be the same on every rank
+    out->top_panel_doubles = c->sym.top_panel_doubles;
+    out->nstations = c->nstn;
     return 0;
 }
 
-int gadj_mg_extract_vcv(gadj_ctx* c)
+int gadj_mg_connect(gadj_ctx* c, const gadj_peer_info* all)
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
-    c->vcv_extracted = false;
-    return extract_vcv(c);
+    if (c->mg_world <= 1)
+        return c->fail("not a multi-GPU context (gadj_mg_init)");
+    if (c->mg_world > MAX_RANKS)
+        return c->fail("at most " + std::to_string(MAX_RANKS) + " ranks (the GPUs of one NVLink node)");
+    ExportedBuffer mine[GADJ_PEER_BUFFERS];
+    exported_buffers(c, mine);
+    PeerTable& t = c->peers;
+    std::memset(&t, 0, sizeof(t));
+    t.nranks = c->mg_world;
+    t.rank = c->mg_rank;
+    for (int q = 0; q < c->mg_world; ++q) {
+        const gadj_peer_info& pi = all[q];
+        if (pi.rank != q)
+            return c->fail("peer table out of order");
+        if (pi.top_panel_doubles != c->sym.top_panel_doubles || pi.nstations != c->nstn)
+            return c->fail("the ranks prepared different networks / orderings");
+        for (int i = 0; i < GADJ_PEER_BUFFERS; ++i) {
+            void* mapped = nullptr;
+            if (q == c->mg_rank)
+                mapped = mine[i].p;
+            else if (pi.ptr[i]) {
+                std::string e;
+                mapped = dev::peer_map(pi.device, pi.pid, (void*)(uintptr_t)pi.ptr[i], pi.handle[i], pi.bytes[i], e);
+                if (!mapped)
+                    return c->fail("cannot map a buffer of rank " + std::to_string(q) + ": " + e);
+                c->peer_maps.push_back({mapped, pi.pid});
+            }
+            if (i == 0)
+                t.counter[q] = (unsigned long long*)mapped;
+            else if (i == MC_BUFS)
+                t.info[q] = (int32_t*)mapped;
+            else
+                t.delta[i][q] = mapped && mine[i].p ? (int64_t)((char*)mapped - (char*)mine[i].p) : 0;
+        }
+    }
+    if (!c->d_peers.resize(1))
+        return c->fail("out of device memory");
+    dev::h2d(c->d_peers.p, &t, sizeof(t));
+    std::string e = dev::sync();
+    if (!e.empty())
+        return c->fail(e);
+    c->connected = true;
+    return 0;
 }
 
 int gadj_form_inverse(gadj_ctx* c)
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     if (c->inverse_valid)
         return 0;
     if (!c->factor_valid)
         return c->fail("no valid factorisation to invert (run gadj_iterate first)");
-    if (c->mg_world > 1)
-        return c->fail("this context is one shard of a multi-GPU adjustment: drive it through the staged calls");
+    if (c->mg_world > 1 && !c->connected)
+        return c->fail("this context is one rank of a multi-GPU adjustment: exchange the peer handles first (gadj_mg_connect)");
     dev::event_record(c->ev[3]);
     run_launches(c, c->plan.selinv);
     dev::event_record(c->ev[4]);
@@ -1825,6 +1963,7 @@ int gadj_form_inverse(gadj_ctx* c)
 
 int gadj_adjust(gadj_ctx* c, gadj_iter_result* last)
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     gadj_iter_result r{};
@@ -1855,17 +1994,26 @@ static int extract_vcv(gadj_ctx* c)
     if (!c->inverse_valid)
         return c->fail("the rigorous inverse has not been formed (run gadj_adjust or iterate with GADJ_ITER_INVERSE)");
     if (c->vcv_extracted)
-        return 0;   // (a multi-GPU driver has already summed the per-rank pieces in place)
+        return 0;
     c->vcv_extracted = true;
     void* st = dev::stream();
     launch_extract_station_vcv(c->d_panels.p, c->d_diag_dest.p, c->d_diag_ld.p, c->d_dscale.p, c->d_vcvd.p, c->nstn, st);
     launch_extract_edge_vcv(c->d_panels.p, c->d_off_dest.p, c->d_off_ld.p, c->d_edge_hi.p, c->d_edge_lo.p, c->d_dscale.p,
                             c->d_vcvo.p, c->nedge, st);
+    if (c->mg_world > 1) {
+        // every rank extracted the blocks of the fronts it assembles (zeros elsewhere): the sum over the ranks is the whole
+        mg_barrier(c);
+        launch_allreduce(c->d_reduce_misc.p + 1, 1, c->pt(), c->d_vcvd.p, MC_VCVD, st);
+        if (c->nedge)
+            launch_allreduce(c->d_reduce_misc.p + 2, 1, c->pt(), c->d_vcvo.p, MC_VCVO, st);
+        mg_barrier(c);
+    }
     return 0;
 }
 
 int gadj_statistics(gadj_ctx* c, gadj_stats* stt, int write_back)
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     if (extract_vcv(c))
@@ -1934,6 +2082,7 @@ int gadj_statistics(gadj_ctx* c, gadj_stats* stt, int write_back)
 // with write_back (the stations' geographic coordinates are then the adjusted ones).
 static int compute_measurements_host(gadj_ctx* c, bool want_ignored)
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     const uint32_t ns = c->nstn;
@@ -2099,6 +2248,7 @@ int gadj_compute_measurements(gadj_ctx* c) { return compute_measurements_host(c,
 
 int gadj_get_estimates(gadj_ctx* c, double* xyz)
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     dev::d2h(xyz, c->d_est.p, c->d_est.bytes());
@@ -2108,6 +2258,7 @@ int gadj_get_estimates(gadj_ctx* c, double* xyz)
 
 int gadj_get_corrections(gadj_ctx* c, double* dxyz)
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     dev::d2h(dxyz, c->d_corr.p, 3 * (size_t)c->nstn * sizeof(double));
@@ -2117,6 +2268,7 @@ int gadj_get_corrections(gadj_ctx* c, double* dxyz)
 
 int gadj_get_station_vcvs(gadj_ctx* c, double* q)
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     if (extract_vcv(c))
@@ -2128,6 +2280,7 @@ int gadj_get_station_vcvs(gadj_ctx* c, double* q)
 
 int gadj_get_station_vcv(gadj_ctx* c, uint32_t stn, double q[9])
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     if (stn >= c->nstn)
@@ -2187,6 +2340,7 @@ static int get_block(gadj_ctx* c, const double* diag, const double* off, uint32_
 
 int gadj_get_vcv_block(gadj_ctx* c, uint32_t si, uint32_t sj, double q[9])
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     if (extract_vcv(c))
@@ -2197,6 +2351,7 @@ int gadj_get_vcv_block(gadj_ctx* c, uint32_t si, uint32_t sj, double q[9])
 // bulk form of gadj_get_vcv_block: one device -> host copy of the stored variance blocks, then the pairs on the host
 int gadj_get_pair_vcvs(gadj_ctx* c, uint64_t npairs, const uint32_t* si, const uint32_t* sj, double* q)
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     if (extract_vcv(c))
@@ -2230,6 +2385,7 @@ int gadj_get_pair_vcvs(gadj_ctx* c, uint64_t npairs, const uint32_t* si, const u
 
 int gadj_get_block_vcv(gadj_ctx* c, uint32_t block, uint32_t* nstations, uint32_t* stations, uint32_t cap, double* packed_lower)
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     if (!c->inverse_valid)
@@ -2238,7 +2394,7 @@ int gadj_get_block_vcv(gadj_ctx* c, uint32_t block, uint32_t* nstations, uint32_
     if (block >= S.fronts.size())
         return c->fail("block index out of range");
     const Front& f = S.fronts[block];
-    if (f.owner != S.rank)
+    if (f.owner != S.rank && !f.top)
         return c->fail("the block is held by another rank");
     const uint32_t nst = f.own_count + f.bnd_count;
     *nstations = nst;
@@ -2303,6 +2459,7 @@ int gadj_get_block_vcv(gadj_ctx* c, uint32_t block, uint32_t* nstations, uint32_
 
 int gadj_get_normals_block(gadj_ctx* c, uint32_t si, uint32_t sj, double n[9])
 {
+    dev::use(c->device);
     if (!c->prepared || !c->normals_valid)
         return c->fail("normals have not been assembled");
     if (si != sj && si < c->nstn && sj < c->nstn) {
@@ -2325,6 +2482,7 @@ int gadj_get_normals_block(gadj_ctx* c, uint32_t si, uint32_t sj, double n[9])
 
 int gadj_get_rhs(gadj_ctx* c, double* w)
 {
+    dev::use(c->device);
     if (!c->prepared)
         return c->fail("gadj_prepare has not been run");
     dev::d2h(w, c->d_w.p, c->d_w.bytes());
@@ -2334,12 +2492,14 @@ int gadj_get_rhs(gadj_ctx* c, double* w)
 
 int gadj_profile_enable(gadj_ctx* c, int on)
 {
+    dev::use(c->device);
     c->profiling = on != 0;
     return 0;
 }
 
 int gadj_profile_read(gadj_ctx* c, gadj_profile* out, int reset)
 {
+    dev::use(c->device);
     std::string e = dev::sync();
     if (!e.empty())
         return c->fail(e);
@@ -2404,6 +2564,7 @@ int gadj_profile_read(gadj_ctx* c, gadj_profile* out, int reset)
 
 int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int M, int N, int K, int reps, float* ms)
 {
+    dev::use(c->device);
     if (M <= 0 || N <= 0 || K <= 0 || (K & 1))
         return c->fail("gadj_test_gemm: M, N, K must be positive and K even");
     DevArray<double> dA, dB, dC;
@@ -2437,7 +2598,7 @@ int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int
     if (!dev::encode_tma_2d(&op.tmA, op.A, M, K, K, TILE_M) || !dev::encode_tma_2d(&op.tmB, op.B, N, K, K, TILE_N))
         return c->fail("tensor-map encoding failed");
     dev::h2d(dop.p, &op, sizeof(op));
-    launch_gemm(dop.p, 1, dtl.p, (int)tl.size(), dev::stream());
+    launch_gemm(dop.p, 1, dtl.p, (int)tl.size(), nullptr, false, dev::stream());
     std::string e = dev::sync();
     if (!e.empty())
         return c->fail(e);
@@ -2445,7 +2606,7 @@ int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int
         reps = 1;
     dev::event_record(c->ev[0]);
     for (int i = 0; i < reps; ++i)
-        launch_gemm(dop.p, 1, dtl.p, (int)tl.size(), dev::stream());
+        launch_gemm(dop.p, 1, dtl.p, (int)tl.size(), nullptr, false, dev::stream());
     dev::event_record(c->ev[1]);
     std::vector<double> hc((size_t)M * ldc);
     dev::d2h(hc.data(), dC.p, dC.bytes());

@@ -53,11 +53,11 @@
             if (a_.adjust_mode == Phased_Block_1Mode && b > 0)
                 break;
             uint32_t n = 0;
-            check(gadj_get_block_vcv(ctx_, b, &n, nullptr, 0, nullptr));
+            block_vcv(b, &n, nullptr, 0, nullptr);
             std::vector<uint32_t> st(n);
             const size_t dim = 3 * (size_t)n;
             std::vector<double> q(dim * (dim + 1) / 2);
-            check(gadj_get_block_vcv(ctx_, b, &n, st.data(), n, q.data()));
+            block_vcv(b, &n, st.data(), n, q.data());
             auto at = [&](size_t i, size_t j) { return i >= j ? q[j * dim - j * (j - 1) / 2 + (i - j)] : q[i * dim - i * (i - 1) / 2 + (j - i)]; };
             std::vector<uint32_t> order(n);   // positions in the block, in the order the stations are listed
             for (uint32_t k = 0; k < n; ++k)

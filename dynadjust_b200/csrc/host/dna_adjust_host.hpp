@@ -13,6 +13,7 @@
 #include <ctime>
 #include <filesystem>
 #include <fstream>
+#include <functional>
 #include <iomanip>
 #include <sstream>
 #include <stdexcept>
@@ -30,6 +31,7 @@
 #include "../../../include/gadj.h"
 #include "../geodesy.h"
 #include "dna_files.hpp"
+#include "gpu_group.hpp"
 
 namespace dynadjust_b200 {
 
@@ -40,6 +42,7 @@ struct adjust_settings {            // the fields of project_settings.a / .g / .
     std::string network_name;
     std::string input_folder = ".", output_folder = ".";
     int adjust_mode = SimultaneousMode;
+    int gpus = 1, first_device = 0;              // --gpus N: the adjustment sharded over N GPUs (one host thread per GPU)
     bool stage = false, multi_thread = false;    // --staged-adjustment / --multi-thread: phased; they name the outputs (WRAP:687-704)
     std::string bst_file, bms_file, seg_file;    // --binary-stn-file / --binary-msr-file / --seg-file: override the network name
     std::string stage_path;                      // --stage-path: where <net>-rva.mtx / <net>-pam.mtx go (default: the output folder)
@@ -85,6 +88,7 @@ class dna_adjust {
   public:
     ~dna_adjust()
     {
+        group_.stop();
         if (ctx_)
             gadj_destroy(ctx_);
     }
@@ -118,11 +122,21 @@ class dna_adjust {
                                           "(dense); segment the network (dnasegment) and run --phased-adjustment for per-block files");
             o.ordering = GADJ_ORDER_DENSE;
         }
+        o.device = a_.first_device;
+        if (a_.gpus > 1 && o.ordering == GADJ_ORDER_DENSE)
+            SignalExceptionAdjustment("--gpus: a single dense front cannot be sharded; drop the full-matrix exports or run on one GPU");
         if (gadj_create(&o, &ctx_))
             SignalExceptionAdjustment(gadj_last_error(nullptr));
-        check(gadj_set_stations(ctx_, stn_.data(), (uint32_t)stn_.size()));
-        check(gadj_set_measurements(ctx_, msr_.data(), msr_.size()));
-        check(gadj_set_measurements_reduced(ctx_, bms_meta_.reduced ? 1 : 0));   // isFirstTimeAdjustment_ (ADJ:296)
+        if (a_.gpus > 1)
+            group_.start(a_.gpus, a_.first_device, o, stn_, msr_);   // worker ranks: own contexts, own copies of the records
+        const int reduced = bms_meta_.reduced ? 1 : 0;
+        all_ranks([&](gadj_ctx* c, int rank) -> int {
+            if (a_.gpus > 1 && gadj_mg_init(c, rank, a_.gpus))
+                return 1;
+            return gadj_set_stations(c, rank ? group_.stn(rank) : stn_.data(), (uint32_t)stn_.size()) ||
+                   gadj_set_measurements(c, rank ? group_.msr(rank) : msr_.data(), msr_.size()) ||
+                   gadj_set_measurements_reduced(c, reduced);   // isFirstTimeAdjustment_ (ADJ:296)
+        });
         if (a_.adjust_mode != SimultaneousMode) {
             if (a_.seg_file.empty()) {
                 // a default .seg file older than station / measurement files that dnaimport wrote since describes another
@@ -148,9 +162,15 @@ class dna_adjust {
                 isl.insert(isl.end(), b.begin(), b.end());
                 off.push_back((uint32_t)isl.size());
             }
-            check(gadj_set_blocks(ctx_, (uint32_t)seg_.isl.size(), off.data(), isl.data()));
+            all_ranks([&](gadj_ctx* c, int) { return gadj_set_blocks(c, (uint32_t)seg_.isl.size(), off.data(), isl.data()); });
         }
-        check(gadj_prepare(ctx_));
+        all_ranks([&](gadj_ctx* c, int) { return gadj_prepare(c); });
+        if (a_.gpus > 1) {
+            // the ranks' buffer handles, once: from here on the GPUs talk to each other over NVLink
+            std::vector<gadj_peer_info> peers(a_.gpus);
+            all_ranks([&](gadj_ctx* c, int rank) { return gadj_mg_export(c, &peers[rank]); });
+            all_ranks([&](gadj_ctx* c, int) { return gadj_mg_connect(c, peers.data()); });
+        }
         gadj_get_info(ctx_, &info_);
         apriori_llh_.resize(3 * stn_.size());
         apriori_xyz_.resize(3 * stn_.size());   // v_originalStations_ (ADJ:632-693)
@@ -185,7 +205,10 @@ class dna_adjust {
             }
             auto ti = std::chrono::steady_clock::now();
             gadj_iter_result r;
-            check(gadj_iterate(ctx_, i == 0 ? GADJ_ITER_NORMALS : 0, &r));
+            all_ranks([&](gadj_ctx* c, int rank) {
+                gadj_iter_result rr;
+                return gadj_iterate(c, i == 0 ? GADJ_ITER_NORMALS : 0, rank ? &rr : &r);
+            });
             r.ms_inverse = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - ti).count();  // wall
             iterations_.push_back(r);
             maxCorr_ = r.max_corr;
@@ -201,7 +224,7 @@ class dna_adjust {
             if (iter_reports && i + 1 < a_.max_iterations) {
                 // --output-iter-adj-stat / -msr / -stn: statistics, adjusted measurements and stations of an iteration that
                 // is followed by another (ADJ:2483-2502); needs the rigorous variances of this iteration
-                check(gadj_form_inverse(ctx_));
+                all_ranks([&](gadj_ctx* c, int) { return gadj_form_inverse(c); });
                 GenerateStatistics();
                 if (a_.iter_adj_stat)
                     PrintStatisticsSummary(post, false);
@@ -218,7 +241,7 @@ class dna_adjust {
         if (adjustStatus_ != ADJUST_CANCELLED && iterations_.size() == a_.max_iterations && std::fabs(maxCorr_) > a_.iteration_threshold)
             adjustStatus_ = ADJUST_MAX_ITERATIONS_EXCEEDED;   // ADJ:2523-2525
         if (adjustStatus_ == ADJUST_SUCCESS)
-            check(gadj_form_inverse(ctx_));                    // rigorous variances (v_rigorousVariances_)
+            all_ranks([&](gadj_ctx* c, int) { return gadj_form_inverse(c); });   // rigorous variances (v_rigorousVariances_)
         total_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         return adjustStatus_;
     }
@@ -226,7 +249,11 @@ class dna_adjust {
     // ---- GenerateStatistics (ADJ:6802) ------------------------------------------------------------------------
     void GenerateStatistics()
     {
-        check(gadj_statistics(ctx_, &stats_, 1));   // also refreshes the records: adjusted lat/lon/h and measurement statistics
+        // also refreshes the records: adjusted lat/lon/h and measurement statistics
+        all_ranks([&](gadj_ctx* c, int rank) {
+            gadj_stats st;
+            return gadj_statistics(c, rank ? &st : &stats_, 1);
+        });
         est_.resize(3 * stn_.size());
         vcv_.resize(9 * stn_.size());
         check(gadj_get_estimates(ctx_, est_.data()));
@@ -479,6 +506,28 @@ class dna_adjust {
     {
         if (rc)
             SignalExceptionAdjustment(gadj_last_error(ctx_));
+    }
+    // a call every rank of a multi-GPU run makes together (it contains device-side barriers); one GPU: just the call
+    void all_ranks(const std::function<int(gadj_ctx*, int)>& fn)
+    {
+        if (group_.size() <= 1) {
+            check(fn(ctx_, 0));
+            return;
+        }
+        const std::string e = group_.all(fn, ctx_);
+        if (!e.empty())
+            SignalExceptionAdjustment(e);
+    }
+    // dense variance matrix of a block, from the rank that holds it (rank 0 holds its own subtrees and the shared top fronts)
+    void block_vcv(uint32_t b, uint32_t* n, uint32_t* stations, uint32_t cap, double* packed)
+    {
+        if (gadj_get_block_vcv(ctx_, b, n, stations, cap, packed) == 0)
+            return;
+        const std::string first = gadj_last_error(ctx_);
+        for (int r = 1; r < group_.size(); ++r)
+            if (group_.one(r, [&](gadj_ctx* c, int) { return gadj_get_block_vcv(c, b, n, stations, cap, packed); }).empty())
+                return;
+        SignalExceptionAdjustment(first);
     }
     [[noreturn]] void SignalExceptionAdjustment(const std::string& msg)
     {   // ADJ:10049-10069
@@ -847,6 +896,7 @@ class dna_adjust {
 
     adjust_settings a_;
     gadj_ctx* ctx_ = nullptr;
+    GpuGroup group_;             // ranks 1..N-1 of a --gpus N run
     gadj_info info_{};
     gadj_stats stats_{};
     std::vector<dna_stn_t> stn_;

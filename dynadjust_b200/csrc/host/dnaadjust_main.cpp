@@ -46,6 +46,7 @@ const Flag kFlags[] = {
     {"project-file", true}, {"binary-stn-file", true}, {"binary-msr-file", true}, {"seg-file", true}, {"output-database-ids", false},
     {"update-orig-stn-file", false}, {"inversion-method", true}, {"output-json", false},
     {"export-xml-stn-file", false}, {"export-xml-msr-file", false}, {"export-dna-stn-file", false}, {"export-dna-msr-file", false},
+    {"gpus", true}, {"first-gpu", true},   // this program's own: shard the adjustment over N GPUs of the node
 };
 
 // Boost.program_options accepts unambiguous prefixes (CI uses --phased, --multi)
@@ -101,6 +102,14 @@ static int apply_option(adjust_settings& s, bool& quiet, const std::string& n, c
         s.stage = true;
         s.multi_thread = false;
     }
+    else if (n == "gpus") {
+        s.gpus = std::atoi(value.c_str());
+        if (s.gpus < 1 || s.gpus > 8) {
+            std::cerr << "--gpus takes 1 to 8 (the GPUs of one NVLink node)\n";
+            return 2;
+        }
+    } else if (n == "first-gpu")
+        s.first_device = std::atoi(value.c_str());
     else if (n == "block1-phased")
         s.adjust_mode = Phased_Block_1Mode;
     else if (n == "simultaneous-adjustment")

@@ -25,6 +25,25 @@ struct alignas(64) TmaDesc {
     uint64_t opaque[16];     // CUtensorMap (128 bytes)
 };
 
+// ---- multi-GPU: replicated buffers and the peer table ---------------------------------------------------------
+// The fronts above the subtree cut ("top" fronts) are stored by every rank at identical offsets of its panel,
+// pivot-inverse and workspace buffers.  A rank that finishes a tile of such a front stores it into every replica
+// through NVLink peer mappings (GEMM_MCAST / DiagOp::mc): byte address in rank p's copy = local address + delta[buf][p].
+constexpr int MAX_RANKS = 8;
+enum McBuf : int32_t { MC_NONE = 0, MC_PANELS = 1, MC_WBUF = 2, MC_POOL = 3, MC_X = 4, MC_VCVD = 5, MC_VCVO = 6, MC_MSR = 7, MC_BUFS = 8 };
+struct PeerTable {
+    int32_t nranks, rank;
+    int64_t delta[MC_BUFS][MAX_RANKS];             // delta[b][rank] == 0
+    unsigned long long* counter[MAX_RANKS];        // every rank's barrier counter, as mapped into this rank
+    int32_t* info[MAX_RANKS];                      // every rank's info words: [0] first front with a non-positive pivot + 1, [1] barrier time-out
+};
+
+// sum of `count` doubles at offset `off` of a replicated buffer over all ranks, result stored into every replica
+// (each rank reduces its 1/nranks slice; fixed rank order, so every replica ends up with the same bits)
+struct ReduceOp {
+    uint64_t off, count;
+};
+
 enum GemmFlags : int32_t {
     GEMM_ACCUM = 1,     // C += alpha*A*B^T   (else C = alpha*A*B^T)
     GEMM_NEG = 2,       // alpha = -1         (else +1)
@@ -33,6 +52,7 @@ enum GemmFlags : int32_t {
     GEMM_KLO_MAX = 32,  // A and B upper triangular: start the K loop at max(first row, first column) of the tile
     GEMM_KHI_ROW = 64,  // A is lower triangular (zero for k > row): end the K loop after the tile's last row
     GEMM_DUAL = 128,    // also store the transpose: Ct[j][i] = C[i][j] (row-major, pitch ldct); not with ACCUM / LOWER / SCATTER
+    GEMM_MCAST = 256,   // the result (and its DUAL transpose) is stored into every rank's replica (GemmOp::mc names the buffers)
     GEMM_SCATTER = 8,   // Schur update of a front, scattered into its ancestors' panels: column j belongs to boundary
                         // station j/3, whose owning ancestor is target t = coltgt[j/3]; element (i, j) is added
                         // atomically to tgt[t].C at row 3*tgt[t].rowmap[i/3 - tgt[t].jb] + i%3 and column
@@ -62,7 +82,7 @@ struct alignas(64) GemmOp {
     int32_t M, N, K;
     int32_t flags;
     int32_t tri_off;
-    int32_t pad0;
+    int32_t mc;              // GEMM_MCAST: McBuf of C in bits 0..7, McBuf of Ct in bits 8..15
     int32_t tiles_m, tiles_n;
 };
 
@@ -85,7 +105,7 @@ struct DiagOp {
     int32_t w;
     int32_t factor;
     int32_t front;           // for error reporting
-    int32_t pad;
+    int32_t mc;              // 1: D (panels), W and Wt (pivot-inverse buffer) are stored into every rank's replica
 };
 
 // y[row0 + i] = sum_c A[i][c] * x[c]  for one chunk of rows of a k x k triangular matrix (W = L11^-1 in the forward
@@ -133,10 +153,20 @@ struct GatherOp {
     int32_t col0;
 };
 
+// keys of dev::first_use: per-device one-time kernel attribute set-up
+enum FirstUseKey : int { KEY_GEMM = 1, KEY_DIAG = 2, KEY_ASSEMBLE = 3 };
+
 // ---- launches -----------------------------------------------------------------
 // All pointers are device pointers; `stream` is the backend's stream handle.
-void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, void* stream);
-void launch_diag(const DiagOp* ops, int nops, int* info, void* stream);
+// pt: the rank's peer table (device copy); only read by launches whose ops carry GEMM_MCAST / DiagOp::mc
+void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, const PeerTable* pt, bool mcast, void* stream);
+void launch_diag(const DiagOp* ops, int nops, int* info, const PeerTable* pt, void* stream);
+// all ranks meet: every store issued before the barrier by any rank is visible to every rank after it.  `target` =
+// (number of barriers so far on this context) * nranks.  A rank that waits longer than ~20 s sets info[1] and gives up.
+void launch_barrier(const PeerTable* pt, unsigned long long target, int* info, void* stream);
+void launch_allreduce(const ReduceOp* ops, int nops, const PeerTable* pt, double* base, int buf, void* stream);
+// info[0] <- max over ranks (non-positive pivot met by any rank); between two barriers
+void launch_share_info(const PeerTable* pt, int* info, void* stream);
 void launch_trimv(const TrimvOp* ops, int nops, void* stream);
 void launch_gemv(const GemvOp* ops, int nops, const double* x_ro, double* x, int backward, void* stream);
 // grid_x: CTAs per op (each op loops over its tiles); the planner passes min(cap, largest tile count)
@@ -213,8 +243,11 @@ void launch_permute_rhs(const double* w, const double* dscale, const uint32_t* p
 // x[3p+c] = 0 for positions this rank does not own (before the cross-rank sum of the solution vector)
 void launch_mask_positions(double* x, const uint8_t* pos_owned, uint32_t nstn, void* stream);
 // corr[3s+c] = dscale * x[3*pos[s]+c]; est += corr; tracks the largest |corr| (first in station order on ties)
+// scratch: APPLY_SCRATCH_DOUBLES doubles of the context (per-CTA partial maxima)
+constexpr int APPLY_MAX_PARTS = 148 * 8;
+constexpr int APPLY_SCRATCH_DOUBLES = 2 * APPLY_MAX_PARTS;
 void launch_apply_corrections(const double* x, const double* dscale, const uint32_t* pos_of_stn, double* corr,
-                              double* est, uint32_t nstn, void* stream);
+                              double* est, uint32_t nstn, double* scratch, void* stream);
 // vcv[s] (9 doubles, row-major) = dscale_i * Z_ss * dscale_j read from the panels (lower triangle mirrored)
 void launch_extract_station_vcv(const double* panels, const uint64_t* diag_dest, const uint32_t* diag_ld,
                                 const double* dscale, double* vcv, uint32_t nstn, void* stream);

@@ -20,6 +20,7 @@
 #include <cstdlib>
 
 #include "geodesy.h"
+#include "dev.h"
 #include "kernels.h"
 
 namespace gadj {
@@ -149,8 +150,11 @@ __global__ void __launch_bounds__(ASM_TILE) assemble_g_kernel(const AssemblePara
         }
         if (active)
             baseline_contribution(m, p, b, ew);
-        if (STAGED)
-            __syncthreads();  // everyone is done with the stage before the next copy overwrites it
+        if (STAGED) {
+            // everyone is done with the stage before the next bulk copy (async proxy) overwrites it
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+        }
     }
 }
 
@@ -479,20 +483,18 @@ inline int grid_for(uint64_t n, int block, int max_blocks = 148 * 16)
     return (int)(g > (uint64_t)max_blocks ? max_blocks : g);
 }
 
-double* g_part_val = nullptr;
-unsigned long long* g_part_idx = nullptr;
-constexpr int MAX_PARTS = 148 * 8;
+constexpr int MAX_PARTS = APPLY_MAX_PARTS;
 
 }  // namespace
 
 void launch_assemble_g(const AssembleParams& p, void* stream)
 {
-    static int mode = -1;  // 0 staged (bulk async copies), 1 direct loads (debug aid: GADJ_ASSEMBLE_DIRECT=1)
-    if (mode < 0) {
+    static const int mode = [] {   // 0 staged (bulk async copies), 1 direct loads (debug aid: GADJ_ASSEMBLE_DIRECT=1)
         const char* e = getenv("GADJ_ASSEMBLE_DIRECT");
-        mode = (e && e[0] == '1') ? 1 : 0;
+        return (e && e[0] == '1') ? 1 : 0;
+    }();
+    if (dev::first_use(KEY_ASSEMBLE))
         cudaFuncSetAttribute(assemble_g_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ASM_SMEM);
-    }
     if (p.nbaselines == 0)
         return;
     const uint64_t ntiles = (p.nbaselines + ASM_TILE - 1) / ASM_TILE;
@@ -541,12 +543,10 @@ void launch_mask_positions(double* x, const uint8_t* pos_owned, uint32_t nstn, v
 }
 
 void launch_apply_corrections(const double* x, const double* dscale, const uint32_t* pos_of_stn, double* corr, double* est,
-                              uint32_t nstn, void* stream)
+                              uint32_t nstn, double* scratch, void* stream)
 {
-    if (!g_part_val) {
-        cudaMalloc(&g_part_val, MAX_PARTS * sizeof(double));
-        cudaMalloc(&g_part_idx, MAX_PARTS * sizeof(unsigned long long));
-    }
+    double* g_part_val = scratch;
+    unsigned long long* g_part_idx = reinterpret_cast<unsigned long long*>(scratch + MAX_PARTS);
     const int grid = grid_for(3ull * nstn, 256, MAX_PARTS);
     apply_corrections_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, dscale, pos_of_stn, corr, est, nstn, g_part_val,
                                                                      g_part_idx);

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdlib>
 
+#include "dev.h"
 #include "kernels.h"
 
 namespace gadj {
@@ -56,7 +57,8 @@ __device__ __forceinline__ void tile_mm(const double* __restrict__ S, int prow, 
 }
 
 template <int CTAS_PER_SM>
-__global__ void __launch_bounds__(DIAG_THREADS, CTAS_PER_SM) diag_kernel(const DiagOp* __restrict__ ops, int* __restrict__ info)
+__global__ void __launch_bounds__(DIAG_THREADS, CTAS_PER_SM)
+    diag_kernel(const DiagOp* __restrict__ ops, int* __restrict__ info, const PeerTable* __restrict__ pt)
 {
     extern __shared__ double S[];
     __shared__ double colbuf[PBW];
@@ -151,10 +153,17 @@ __global__ void __launch_bounds__(DIAG_THREADS, CTAS_PER_SM) diag_kernel(const D
             }
             __syncthreads();
         }
+        // multi-GPU: the pivot tile of a replicated (top) front is factorised by one rank and stored into every replica
+        const int peers = op.mc ? pt->nranks : 0;
         for (int idx = tid; idx < w * w; idx += DIAG_THREADS) {
             const int i = idx / w, j = idx - i * w;
-            if (j <= i)
-                op.D[i * ld + j] = S[tri(i, j)];
+            if (j <= i) {
+                const double v = S[tri(i, j)];
+                op.D[i * ld + j] = v;
+                for (int q = 0; q < peers; ++q)
+                    if (q != pt->rank)
+                        *reinterpret_cast<double*>(reinterpret_cast<char*>(op.D + i * ld + j) + pt->delta[MC_PANELS][q]) = v;
+            }
         }
     }
     if (op.W == nullptr && op.Wt == nullptr)
@@ -218,12 +227,104 @@ __global__ void __launch_bounds__(DIAG_THREADS, CTAS_PER_SM) diag_kernel(const D
         }
         __syncthreads();
     }
+    const int peers = op.mc ? pt->nranks : 0;
     for (int idx = tid; idx < w * w; idx += DIAG_THREADS) {
         const int i = idx / w, j = idx - i * w;
+        const double vw = (j <= i) ? S[tri(i, j)] : 0.0;     // W[i][j] (row-major, lower)
+        const double vt = (j >= i) ? S[tri(j, i)] : 0.0;     // Wt[i][j] = W[j][i] (upper)
         if (op.W)
-            op.W[i * op.ldw + j] = (j <= i) ? S[tri(i, j)] : 0.0;     // W[i][j] (row-major, lower)
+            op.W[i * op.ldw + j] = vw;
         if (op.Wt)
-            op.Wt[i * op.ldwt + j] = (j >= i) ? S[tri(j, i)] : 0.0;   // Wt[i][j] = W[j][i] (upper)
+            op.Wt[i * op.ldwt + j] = vt;
+        for (int q = 0; q < peers; ++q)
+            if (q != pt->rank) {
+                if (op.W)
+                    *reinterpret_cast<double*>(reinterpret_cast<char*>(op.W + i * op.ldw + j) + pt->delta[MC_WBUF][q]) = vw;
+                if (op.Wt)
+                    *reinterpret_cast<double*>(reinterpret_cast<char*>(op.Wt + i * op.ldwt + j) + pt->delta[MC_WBUF][q]) = vt;
+            }
+    }
+}
+
+// ---- multi-GPU: barrier, all-reduce, shared status -------------------------------------------------
+// Every rank adds one to every rank's counter (its own included) and waits until its own counter has seen all the ranks
+// of this round: counter == rounds * nranks.  The launches before the barrier on every rank — stores into peers'
+// replicas included — have completed when the stream reaches this kernel; the system-scope fences order them against
+// the counter updates and the reads that follow.  A rank that waits for more than ~20 s (a peer has failed) flags
+// info[1] and leaves; the host reports it.
+__global__ void barrier_kernel(const PeerTable* __restrict__ pt, unsigned long long target, int* __restrict__ info)
+{
+    const int p = threadIdx.x;
+    __threadfence_system();
+    if (p < pt->nranks)
+        atomicAdd_system(pt->counter[p], 1ull);
+    if (p == 0) {
+        volatile unsigned long long* c = pt->counter[pt->rank];
+        const long long t0 = clock64();
+        while (*c < target) {
+            __nanosleep(64);
+            if (clock64() - t0 > 40000000000ll) {
+                atomicExch(info + 1, 1);
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+}
+
+// Sum over the ranks' replicas of the ranges in `ops` (doubles at base + off), the result stored into every replica.
+// Rank r reduces the r-th slice of every range, reading the other replicas over NVLink and adding them in rank order,
+// so all replicas receive identical bits (and the same bits run after run).
+__global__ void __launch_bounds__(256) allreduce_kernel(const ReduceOp* __restrict__ ops, const PeerTable* __restrict__ pt,
+                                                       double* __restrict__ base, int buf)
+{
+    const ReduceOp op = ops[blockIdx.y];
+    const int n = pt->nranks, me = pt->rank;
+    const int64_t* d = pt->delta[buf];
+    // slices in units of two doubles when the range starts on a 16-byte boundary (vector accesses), else single doubles
+    double* p0 = base + op.off;
+    const bool vec = ((reinterpret_cast<uintptr_t>(p0) & 15) == 0);
+    if (vec) {
+        const uint64_t pairs = op.count / 2;
+        const uint64_t lo = pairs * me / n, hi = pairs * (me + 1) / n;
+        for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (uint64_t)gridDim.x * blockDim.x) {
+            double2 s = make_double2(0.0, 0.0);
+            for (int q = 0; q < n; ++q) {
+                const double2 v = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(p0 + 2 * i) + d[q]);
+                s.x += v.x;
+                s.y += v.y;
+            }
+            for (int q = 0; q < n; ++q)
+                *reinterpret_cast<double2*>(reinterpret_cast<char*>(p0 + 2 * i) + d[q]) = s;
+        }
+        if ((op.count & 1) && me == n - 1 && blockIdx.x == 0 && threadIdx.x == 0) {
+            const uint64_t i = op.count - 1;
+            double s = 0.0;
+            for (int q = 0; q < n; ++q)
+                s += *reinterpret_cast<const double*>(reinterpret_cast<const char*>(p0 + i) + d[q]);
+            for (int q = 0; q < n; ++q)
+                *reinterpret_cast<double*>(reinterpret_cast<char*>(p0 + i) + d[q]) = s;
+        }
+    } else {
+        const uint64_t lo = op.count * me / n, hi = op.count * (me + 1) / n;
+        for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (uint64_t)gridDim.x * blockDim.x) {
+            double s = 0.0;
+            for (int q = 0; q < n; ++q)
+                s += *reinterpret_cast<const double*>(reinterpret_cast<const char*>(p0 + i) + d[q]);
+            for (int q = 0; q < n; ++q)
+                *reinterpret_cast<double*>(reinterpret_cast<char*>(p0 + i) + d[q]) = s;
+        }
+    }
+}
+
+__global__ void share_info_kernel(const PeerTable* __restrict__ pt, int* __restrict__ info)
+{
+    const int p = threadIdx.x;
+    if (p < pt->nranks && p != pt->rank) {
+        if (info[0] != 0)
+            atomicMax_system(pt->info[p], info[0]);
+        if (info[1] != 0)
+            atomicMax_system(pt->info[p] + 1, info[1]);
     }
 }
 
@@ -391,21 +492,39 @@ constexpr int TILE_SMEM = TRI_DOUBLES * 8;
 
 }  // namespace
 
-void launch_diag(const DiagOp* ops, int nops, int* info, void* stream)
+void launch_diag(const DiagOp* ops, int nops, int* info, const PeerTable* pt, void* stream)
 {
     if (nops <= 0)
         return;
-    static int ctas = 0;
-    if (!ctas) {
+    static const int ctas = [] {
+        const char* e = getenv("GADJ_DIAG_CTAS");   // register budget: 2 CTAs/SM without spills, 3 with a few spilled values
+        return (e && e[0] == '3') ? 3 : 2;
+    }();
+    if (dev::first_use(KEY_DIAG)) {
         cudaFuncSetAttribute(diag_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM);
         cudaFuncSetAttribute(diag_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM);
-        const char* e = getenv("GADJ_DIAG_CTAS");   // register budget: 2 CTAs/SM without spills, 3 with a few spilled values
-        ctas = (e && e[0] == '3') ? 3 : 2;
     }
     if (ctas == 3)
-        diag_kernel<3><<<nops, DIAG_THREADS, TILE_SMEM, (cudaStream_t)stream>>>(ops, info);
+        diag_kernel<3><<<nops, DIAG_THREADS, TILE_SMEM, (cudaStream_t)stream>>>(ops, info, pt);
     else
-        diag_kernel<2><<<nops, DIAG_THREADS, TILE_SMEM, (cudaStream_t)stream>>>(ops, info);
+        diag_kernel<2><<<nops, DIAG_THREADS, TILE_SMEM, (cudaStream_t)stream>>>(ops, info, pt);
+}
+
+void launch_barrier(const PeerTable* pt, unsigned long long target, int* info, void* stream)
+{
+    barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pt, target, info);
+}
+
+void launch_allreduce(const ReduceOp* ops, int nops, const PeerTable* pt, double* base, int buf, void* stream)
+{
+    if (nops <= 0)
+        return;
+    allreduce_kernel<<<dim3(148 * 2, nops), 256, 0, (cudaStream_t)stream>>>(ops, pt, base, buf);
+}
+
+void launch_share_info(const PeerTable* pt, int* info, void* stream)
+{
+    share_info_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pt, info);
 }
 
 void launch_trimv(const TrimvOp* ops, int nops, void* stream)

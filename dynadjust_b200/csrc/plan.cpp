@@ -59,14 +59,29 @@ struct Builder {
 
     std::vector<size_t> woff;   // per front: offset of its W block in b.wbuf (Wt follows at + wblock)
 
+    // per op of a batch: how its tiles are shared out among the ranks (multi-GPU, replicated top fronts)
+    enum Dist { D_ALL = 0, D_ROW = 1, D_SUM = 2 };
+    struct Share {
+        int dist;   // D_ALL: this rank runs every tile; D_ROW: the tiles of panel row tile T go to rank T % world;
+                    // D_SUM: tile (tm, tn) goes to rank (tm + tn) % world
+        int rt0;    // D_ROW: row tile (of the front's panel) the op's first row sits in
+    };
+    std::vector<Share> share;   // parallel to the pending GEMM batch
+
     Builder(const Symbolic& S, const PlanBuffers& B, Plan& P) : s(S), b(B), p(P)
     {
+        // top fronts first: the same offsets on every rank (see finalize_layout)
         woff.assign(s.fronts.size(), 0);
         size_t o = 0;
-        for (size_t f = 0; f < s.fronts.size(); ++f)
-            if (s.fronts[f].owner == s.rank) {
-                woff[f] = o;
-                o += 2 * wblock(s.fronts[f]);
+        for (int pass = 0; pass < 2; ++pass)
+            for (size_t f = 0; f < s.fronts.size(); ++f) {
+                const Front& fr = s.fronts[f];
+                if ((pass == 0) != (fr.top != 0))
+                    continue;
+                if (fr.top || fr.owner == s.rank) {
+                    woff[f] = o;
+                    o += 2 * wblock(fr);
+                }
             }
     }
 
@@ -74,30 +89,59 @@ struct Builder {
     double* Wof(uint32_t fi) const { return b.wbuf + woff[fi]; }
     double* Wtof(uint32_t fi) const { return b.wbuf + woff[fi] + wblock(s.fronts[fi]); }
 
-    // fronts of a level that this rank factorises
-    std::vector<uint32_t> owned(size_t lv) const
+    // fronts of a level inside this rank's subtrees / the replicated top fronts of a level (every rank works on those)
+    std::vector<uint32_t> local_fronts(size_t lv) const
     {
         std::vector<uint32_t> v;
         for (uint32_t f : s.levels[lv])
-            if (s.fronts[f].owner == s.rank)
+            if (s.fronts[f].owner == s.rank && !s.fronts[f].top)
                 v.push_back(f);
         return v;
     }
-    void add_sync(std::vector<Launch>& out, size_t lv)
+    std::vector<uint32_t> top_fronts(size_t lv) const
     {
-        if (s.world <= 1 || (int)lv < s.cut_level)
+        std::vector<uint32_t> v;
+        for (uint32_t f : s.levels[lv])
+            if (s.fronts[f].top)
+                v.push_back(f);
+        return v;
+    }
+    bool multi() const { return s.world > 1; }
+    void add_barrier(std::vector<Launch>& out, int level)
+    {
+        if (!multi())
             return;
         Launch L{};
-        L.kind = L_SYNC;
-        L.level = (int32_t)lv;
+        L.kind = L_BARRIER;
+        L.level = level;
         out.push_back(L);
+    }
+    // barrier; sum over the ranks of the given ranges of a replicated buffer; barrier
+    void add_allreduce(std::vector<Launch>& out, int level, int buf, const std::vector<ReduceOp>& ranges)
+    {
+        if (!multi() || ranges.empty())
+            return;
+        add_barrier(out, level);
+        Launch L{};
+        L.kind = L_ALLREDUCE;
+        L.level = level;
+        L.buf = buf;
+        L.op_begin = (int64_t)p.reduce.size();
+        L.op_count = (int32_t)ranges.size();
+        p.reduce.insert(p.reduce.end(), ranges.begin(), ranges.end());
+        out.push_back(L);
+        add_barrier(out, level);
     }
 
     void add_gemm(std::vector<GemmOp>& batch, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
-                  int64_t ldc, int M, int N, int K, int flags, int tri_off = 0, const int32_t* coltgt = nullptr)
+                  int64_t ldc, int M, int N, int K, int flags, int tri_off = 0, const int32_t* coltgt = nullptr,
+                  Share sh = Share{D_ALL, 0}, int mc = 0)
     {
         if (M <= 0 || N <= 0 || K <= 0)
             return;
+        if (share.size() != batch.size())
+            share.resize(batch.size(), Share{D_ALL, 0});
+        share.push_back(sh);
         GemmOp op{};
         op.A = A;
         op.B = B;
@@ -112,6 +156,7 @@ struct Builder {
         op.K = K;
         op.flags = flags;
         op.tri_off = tri_off;
+        op.mc = mc;
         op.tiles_m = cdiv(M, TILE_M);
         op.tiles_n = cdiv(N, TILE_N);
         batch.push_back(op);
@@ -129,14 +174,25 @@ struct Builder {
         L.op_count = (int32_t)batch.size();
         L.level = level;
         L.tile_begin = (int64_t)p.tiles.size();
+        share.resize(batch.size(), Share{D_ALL, 0});
         int32_t opi = 0;
         for (GemmOp& op : batch) {
+            const Share sh = share[opi];
+            size_t all_tiles = 0, my_tiles = 0;
             for (int tm = 0; tm < op.tiles_m; ++tm)
                 for (int tn = 0; tn < op.tiles_n; ++tn) {
                     if ((op.flags & GEMM_LOWER) && tm * TILE_M + (TILE_M - 1) + op.tri_off < tn * TILE_N)
                         continue;   // wholly above the diagonal
+                    ++all_tiles;
+                    if (sh.dist == D_ROW && (sh.rt0 + tm) % s.world != s.rank)
+                        continue;   // another rank's row of tiles
+                    if (sh.dist == D_SUM && (tm + tn) % s.world != s.rank)
+                        continue;
+                    ++my_tiles;
                     p.tiles.push_back(GemmTile{opi, (uint16_t)tm, (uint16_t)tn});
                 }
+            if (op.flags & GEMM_MCAST)
+                L.mcast = 1;
             ++opi;
             // useful flops: lower-only outputs drop the strict upper triangle of the leading square;
             // triangular operands halve the K range over that square
@@ -150,6 +206,8 @@ struct Builder {
                 fl *= 0.5;
             if (op.flags & GEMM_KLO_MAX)
                 fl = 2.0 * M * M * M / 6.0 * (op.flags & GEMM_LOWER ? 1.0 : 2.0);
+            if (all_tiles)
+                fl *= (double)my_tiles / (double)all_tiles;   // this rank's share of a distributed op
             L.flops += fl;
             if (!dev::encode_tma_2d(&op.tmA, op.A, (uint64_t)op.M, (uint64_t)op.K, (uint64_t)op.lda, TILE_M) ||
                 !dev::encode_tma_2d(&op.tmB, op.B, (uint64_t)op.N, (uint64_t)op.K, (uint64_t)op.ldb, TILE_N))
@@ -159,6 +217,7 @@ struct Builder {
         L.total_tiles = (int32_t)(p.tiles.size() - (size_t)L.tile_begin);
         out.push_back(L);
         batch.clear();
+        share.clear();
     }
 
     void flush_diag(std::vector<DiagOp>& batch, std::vector<Launch>& out, int level)
@@ -220,14 +279,19 @@ struct Builder {
     // W21 = -W22 (L21 W11),  as  Tt = Wt11 L21^T  (parked in the unused upper part of W),  W21 = -W22 Tt^T,
     // Wt12 = W21^T.  Every pair of every front of the level is in the same three launches: 3 log2(k / 128)
     // launches per level.
-    void build_trtri(const std::vector<uint32_t>& fl, std::vector<Launch>& out, int level)
+    // dist (replicated top fronts of a multi-GPU run): the tiles of the two products are shared out among the ranks and
+    // stored into every replica, with a barrier after each; the transposes are cheap and every rank does its own.
+    void build_trtri(const std::vector<uint32_t>& fl, std::vector<Launch>& out, int level, bool dist)
     {
         std::vector<TransposeOp> trb;
         int maxk = 0;
         for (uint32_t fi : fl)
             maxk = std::max<int>(maxk, (int)s.fronts[fi].k);
+        const Share sh{dist ? D_SUM : D_ALL, 0};
+        const int mcf = dist ? GEMM_MCAST : 0;
         for (int bw = NB; bw < maxk; bw <<= 1) {
             std::vector<GemmOp> ga, gbb;
+            std::vector<Share> sa, sb;
             for (uint32_t fi : fl) {
                 const Front& f = s.fronts[fi];
                 const uint32_t ldw = ldw_of(f);
@@ -238,9 +302,14 @@ struct Builder {
                     const int rows2 = std::min<int>(bw, (int)f.k - r1);
                     double* Tt = W + (size_t)r0 * ldw + r1;                    // bw x rows2
                     double* W21 = W + (size_t)r1 * ldw + r0;                   // rows2 x bw
+                    share.swap(sa);
                     add_gemm(ga, Wt + (size_t)r0 * ldw + r0, ldw, panel(f) + (size_t)r1 * f.ldk + r0, f.ldk, Tt, ldw, bw, rows2,
-                             bw, GEMM_KLO_ROW);
-                    add_gemm(gbb, W + (size_t)r1 * ldw + r1, ldw, Tt, ldw, W21, ldw, rows2, bw, rows2, GEMM_NEG | GEMM_KHI_ROW);
+                             bw, GEMM_KLO_ROW | mcf, 0, nullptr, sh, MC_WBUF);
+                    share.swap(sa);
+                    share.swap(sb);
+                    add_gemm(gbb, W + (size_t)r1 * ldw + r1, ldw, Tt, ldw, W21, ldw, rows2, bw, rows2,
+                             GEMM_NEG | GEMM_KHI_ROW | mcf, 0, nullptr, sh, MC_WBUF);
+                    share.swap(sb);
                     TransposeOp t{};
                     t.src = W21;
                     t.dst = Wt + (size_t)r0 * ldw + r1;
@@ -251,101 +320,146 @@ struct Builder {
                     trb.push_back(t);
                 }
             }
+            const bool any = !ga.empty();
+            share.swap(sa);
             flush_gemm(ga, out, level, T_TRTRI_A);
+            if (dist && any)
+                add_barrier(out, level);
+            share.swap(sb);
             flush_gemm(gbb, out, level, T_TRTRI_B);
+            if (dist && any)
+                add_barrier(out, level);
             flush_simple(trb, p.transpose, L_TRANSPOSE, out, level);
         }
     }
 
     // ---- numeric factorisation ------------------------------------------------
-    void build_factor()
+    // One tree level of fronts.  dist: the replicated top fronts of a multi-GPU run — right-looking; panel row tile T of a
+    // front belongs to rank T % world, which applies the pivot inverse to its tiles of the current block column and
+    // stores them into every replica, and keeps its tiles of the trailing matrix up to date locally; the pivot tile is
+    // factorised by the owner of its row and stored into every replica.
+    void factor_level(const std::vector<uint32_t>& fl, int lv, bool dist)
     {
         std::vector<GemmOp> gb;
         std::vector<DiagOp> db;
-        for (size_t lv = 0; lv < s.levels.size(); ++lv) {
-            const std::vector<uint32_t> fl = owned(lv);
-            add_sync(p.factor, lv);   // contributions to this level's top fronts are reduced to their owners first
-            int nsteps = 0;
-            for (uint32_t f : fl)
-                nsteps = std::max(nsteps, cdiv((int)s.fronts[f].k, NB));
-            // Levels with enough fronts to fill the GPU from one block column per front run left-looking
-            // (each block column is updated once, from all columns to its left, K = jb: half the panel traffic
-            // and long K loops); sparse top levels run right-looking (2-D tile parallelism inside few big fronts).
-            size_t row_tiles = 0;
-            for (uint32_t f : fl)
-                row_tiles += (size_t)cdiv((int)s.fronts[f].m, TILE_M);
-            const bool left = row_tiles >= 2 * 148;
-            for (int j = 0; j < nsteps; ++j) {
-                const int jb = j * NB;
-                if (left && jb > 0) {
-                    for (size_t i = 0; i < fl.size(); ++i) {
-                        const Front& f = s.fronts[fl[i]];
-                        if (jb >= (int)f.k)
-                            continue;
-                        int w = std::min<int>(NB, (int)f.k - jb);
-                        double* A = panel(f) + (size_t)jb * f.ldk;
-                        add_gemm(gb, A, f.ldk, A, f.ldk, A + jb, f.ldk, (int)f.m - jb, w, jb,
-                                 GEMM_ACCUM | GEMM_NEG | GEMM_LOWER);
-                    }
-                    flush_gemm(gb, p.factor, (int)lv, T_LEFT_UPDATE);
-                }
-                // pivot tiles
-                for (size_t i = 0; i < fl.size(); ++i) {
-                    const Front& f = s.fronts[fl[i]];
-                    if (jb >= (int)f.k)
-                        continue;
-                    DiagOp d{};
-                    d.D = panel(f) + (size_t)jb * f.ldk + jb;
-                    d.ldd = f.ldk;
-                    d.w = std::min<int>(NB, (int)f.k - jb);
-                    d.factor = 1;
-                    d.ldw = d.ldwt = ldw_of(f);
-                    d.W = Wof(fl[i]) + (size_t)jb * d.ldw + jb;
-                    d.Wt = Wtof(fl[i]) + (size_t)jb * d.ldw + jb;
-                    d.front = (int32_t)fl[i];
-                    db.push_back(d);
-                }
-                flush_diag(db, p.factor, (int)lv);
-                // rows below the pivot tile: P <- P * W^T
+        int nsteps = 0;
+        for (uint32_t f : fl)
+            nsteps = std::max(nsteps, cdiv((int)s.fronts[f].k, NB));
+        // Levels with enough fronts to fill the GPU from one block column per front run left-looking
+        // (each block column is updated once, from all columns to its left, K = jb: half the panel traffic
+        // and long K loops); sparse top levels run right-looking (2-D tile parallelism inside few big fronts).
+        size_t row_tiles = 0;
+        for (uint32_t f : fl)
+            row_tiles += (size_t)cdiv((int)s.fronts[f].m, TILE_M);
+        const bool left = !dist && row_tiles >= 2 * 148;
+        const int mcf = dist ? GEMM_MCAST : 0;
+        for (int j = 0; j < nsteps; ++j) {
+            const int jb = j * NB;
+            if (left && jb > 0) {
                 for (size_t i = 0; i < fl.size(); ++i) {
                     const Front& f = s.fronts[fl[i]];
                     if (jb >= (int)f.k)
                         continue;
                     int w = std::min<int>(NB, (int)f.k - jb);
-                    double* A = panel(f) + (size_t)(jb + w) * f.ldk + jb;
-                    add_gemm(gb, A, f.ldk, Wof(fl[i]) + (size_t)jb * ldw_of(f) + jb, ldw_of(f), A, f.ldk, (int)f.m - (jb + w), w, w,
-                             0);
+                    double* A = panel(f) + (size_t)jb * f.ldk;
+                    add_gemm(gb, A, f.ldk, A, f.ldk, A + jb, f.ldk, (int)f.m - jb, w, jb, GEMM_ACCUM | GEMM_NEG | GEMM_LOWER);
                 }
-                flush_gemm(gb, p.factor, (int)lv, T_PANEL);
-                if (left)
+                flush_gemm(gb, p.factor, lv, T_LEFT_UPDATE);
+            }
+            // pivot tiles
+            bool any = false;
+            for (size_t i = 0; i < fl.size(); ++i) {
+                const Front& f = s.fronts[fl[i]];
+                if (jb >= (int)f.k)
                     continue;
-                // trailing update inside the panel (columns still to be factorised)
-                for (size_t i = 0; i < fl.size(); ++i) {
-                    const Front& f = s.fronts[fl[i]];
-                    if (jb >= (int)f.k)
-                        continue;
-                    int w = std::min<int>(NB, (int)f.k - jb);
-                    int nc = (int)f.k - (jb + w);
-                    double* A = panel(f) + (size_t)(jb + w) * f.ldk + jb;
-                    double* C = panel(f) + (size_t)(jb + w) * f.ldk + (jb + w);
-                    add_gemm(gb, A, f.ldk, A, f.ldk, C, f.ldk, (int)f.m - (jb + w), nc, w,
-                             GEMM_ACCUM | GEMM_NEG | GEMM_LOWER);
+                any = true;
+                if (dist && j % s.world != s.rank)
+                    continue;   // the rank that owns panel row tile j factorises the pivot tile for everybody
+                DiagOp d{};
+                d.D = panel(f) + (size_t)jb * f.ldk + jb;
+                d.ldd = f.ldk;
+                d.w = std::min<int>(NB, (int)f.k - jb);
+                d.factor = 1;
+                d.ldw = d.ldwt = ldw_of(f);
+                d.W = Wof(fl[i]) + (size_t)jb * d.ldw + jb;
+                d.Wt = Wtof(fl[i]) + (size_t)jb * d.ldw + jb;
+                d.front = (int32_t)fl[i];
+                d.mc = dist ? 1 : 0;
+                db.push_back(d);
+            }
+            flush_diag(db, p.factor, lv);
+            if (dist && any)
+                add_barrier(p.factor, lv);
+            // rows below the pivot tile: P <- P * W^T
+            for (size_t i = 0; i < fl.size(); ++i) {
+                const Front& f = s.fronts[fl[i]];
+                if (jb >= (int)f.k)
+                    continue;
+                int w = std::min<int>(NB, (int)f.k - jb);
+                int r0 = jb + w;
+                const double* Wj = Wof(fl[i]) + (size_t)jb * ldw_of(f) + jb;
+                if (dist && w < NB) {
+                    // ragged last pivot tile: the rows up to the next 128-row boundary sit in the pivot's own row tile
+                    const int head = std::min<int>((int)f.m, jb + NB) - r0;
+                    double* A0 = panel(f) + (size_t)r0 * f.ldk + jb;
+                    add_gemm(gb, A0, f.ldk, Wj, ldw_of(f), A0, f.ldk, head, w, w, mcf, 0, nullptr, Share{D_ROW, j}, MC_PANELS);
+                    r0 += head;
                 }
-                flush_gemm(gb, p.factor, (int)lv, T_RIGHT_UPDATE);
+                double* A = panel(f) + (size_t)r0 * f.ldk + jb;
+                add_gemm(gb, A, f.ldk, Wj, ldw_of(f), A, f.ldk, (int)f.m - r0, w, w, mcf, 0, nullptr,
+                         Share{dist ? D_ROW : D_ALL, j + 1}, MC_PANELS);
             }
-            build_trtri(fl, p.factor, (int)lv);
-            // Schur update -L21 L21^T of every front, one lower-triangular r x r product per front, scattered into the
-            // ancestors' panels through the per-column target table
-            for (uint32_t fi : fl) {
-                const Front& f = s.fronts[fi];
-                if (!f.r)
+            flush_gemm(gb, p.factor, lv, T_PANEL);
+            if (dist && any)
+                add_barrier(p.factor, lv);
+            if (left)
+                continue;
+            // trailing update inside the panel (columns still to be factorised)
+            for (size_t i = 0; i < fl.size(); ++i) {
+                const Front& f = s.fronts[fl[i]];
+                if (jb >= (int)f.k)
                     continue;
-                double* A = panel(f) + (size_t)f.k * f.ldk;
-                add_gemm(gb, A, f.ldk, A, f.ldk, nullptr, 0, (int)f.r, (int)f.r, (int)f.k, GEMM_SCATTER | GEMM_NEG | GEMM_LOWER, 0,
-                         b.coltgt + f.bnd_begin);
+                int w = std::min<int>(NB, (int)f.k - jb);
+                int nc = (int)f.k - (jb + w);
+                double* A = panel(f) + (size_t)(jb + w) * f.ldk + jb;
+                double* C = panel(f) + (size_t)(jb + w) * f.ldk + (jb + w);
+                add_gemm(gb, A, f.ldk, A, f.ldk, C, f.ldk, (int)f.m - (jb + w), nc, w, GEMM_ACCUM | GEMM_NEG | GEMM_LOWER, 0,
+                         nullptr, Share{dist ? D_ROW : D_ALL, j + 1});
             }
-            flush_gemm(gb, p.factor, (int)lv, T_SCHUR);
+            flush_gemm(gb, p.factor, lv, T_RIGHT_UPDATE);
         }
+        build_trtri(fl, p.factor, lv, dist);
+        // Schur update -L21 L21^T of every front, one lower-triangular r x r product per front, scattered into the
+        // ancestors' panels through the per-column target table (dist: each rank scatters its share of the tiles into
+        // its own replicas of the ancestors; the partial sums meet in the all-reduce before the ancestors' level)
+        for (uint32_t fi : fl) {
+            const Front& f = s.fronts[fi];
+            if (!f.r)
+                continue;
+            double* A = panel(f) + (size_t)f.k * f.ldk;
+            add_gemm(gb, A, f.ldk, A, f.ldk, nullptr, 0, (int)f.r, (int)f.r, (int)f.k, GEMM_SCATTER | GEMM_NEG | GEMM_LOWER, 0,
+                     b.coltgt + f.bnd_begin, Share{dist ? D_SUM : D_ALL, 0});
+        }
+        flush_gemm(gb, p.factor, lv, T_SCHUR);
+    }
+
+    void build_factor()
+    {
+        for (size_t lv = 0; lv < s.levels.size(); ++lv)
+            factor_level(local_fronts(lv), (int)lv, false);
+        if (multi())
+            for (size_t lv = 0; lv < s.levels.size(); ++lv) {
+                const std::vector<uint32_t> tl = top_fronts(lv);
+                if (tl.empty())
+                    continue;
+                // the ranks' partial sums of these fronts (their subtrees' and the lower top fronts' Schur updates, the
+                // assembled blocks on one rank) become the assembled fronts on every rank
+                std::vector<ReduceOp> ranges;
+                for (uint32_t fi : tl)
+                    ranges.push_back(ReduceOp{s.fronts[fi].panel_off, (uint64_t)s.fronts[fi].m * s.fronts[fi].ldk});
+                add_allreduce(p.factor, (int)lv, MC_PANELS, ranges);
+                factor_level(tl, (int)lv, true);
+            }
         for (auto& L : p.factor)
             p.factor_flops += L.flops;
     }
@@ -393,34 +507,52 @@ struct Builder {
     {
         std::vector<TrimvOp> tb;
         std::vector<GemvOp> vb;
-        for (size_t lv = 0; lv < s.levels.size(); ++lv) {
-            add_sync(p.fwd, lv);      // right-hand-side contributions to this level's top fronts are summed first
-            for (uint32_t fi : owned(lv)) {
+        auto forward = [&](const std::vector<uint32_t>& fl, int lv) {
+            for (uint32_t fi : fl) {
                 add_trimv(tb, fi, false);
                 add_gemv(vb, fi);
             }
-            flush_simple(tb, p.tri, L_TRI_FWD, p.fwd, (int)lv);
-            flush_simple(vb, p.gemv, L_GEMV_FWD, p.fwd, (int)lv);
-        }
-        for (size_t lvi = s.levels.size(); lvi-- > 0;) {
-            for (uint32_t fi : owned(lvi)) {
+            flush_simple(tb, p.tri, L_TRI_FWD, p.fwd, lv);
+            flush_simple(vb, p.gemv, L_GEMV_FWD, p.fwd, lv);
+        };
+        auto backward = [&](const std::vector<uint32_t>& fl, int lv) {
+            for (uint32_t fi : fl) {
                 add_gemv(vb, fi);
                 add_trimv(tb, fi, true);
             }
-            flush_simple(vb, p.gemv, L_GEMV_BWD, p.bwd, (int)lvi);
-            flush_simple(tb, p.tri, L_TRI_BWD, p.bwd, (int)lvi);
-            add_sync(p.bwd, lvi);     // the solved top fronts of this level are broadcast to every rank
+            flush_simple(vb, p.gemv, L_GEMV_BWD, p.bwd, lv);
+            flush_simple(tb, p.tri, L_TRI_BWD, p.bwd, lv);
+        };
+        for (size_t lv = 0; lv < s.levels.size(); ++lv)
+            forward(local_fronts(lv), (int)lv);
+        if (multi()) {
+            // the subtrees' contributions to the top fronts' right-hand sides are summed over the ranks; from there on every
+            // rank carries the (cheap) substitutions of the replicated top fronts itself and needs no further exchange
+            std::vector<ReduceOp> ranges;
+            for (const Front& f : s.fronts)
+                if (f.top)
+                    ranges.push_back(ReduceOp{3ull * f.own_begin, f.k});
+            add_allreduce(p.fwd, s.cut_level, MC_X, ranges);
+            for (size_t lv = 0; lv < s.levels.size(); ++lv)
+                forward(top_fronts(lv), (int)lv);
+            for (size_t lvi = s.levels.size(); lvi-- > 0;)
+                backward(top_fronts(lvi), (int)lvi);
         }
+        for (size_t lvi = s.levels.size(); lvi-- > 0;)
+            backward(local_fronts(lvi), (int)lvi);
     }
 
     // ---- selected inverse -------------------------------------------------------
-    void build_selinv_chunk(const std::vector<uint32_t>& chunk, const std::vector<size_t>& base, size_t used, int level)
+    // dist: one replicated top front at a time, its workspace at the start of the pool on every rank; the tiles of the
+    // four products are shared out among the ranks and every finished tile is stored into all replicas.
+    void build_selinv_chunk(const std::vector<uint32_t>& chunk, const std::vector<size_t>& base, int level, bool dist)
     {
         std::vector<GemmOp> gb;
         std::vector<GatherOp> gab;
+        const Share sh{dist ? D_SUM : D_ALL, 0};
+        const int mcf = dist ? GEMM_MCAST : 0;
         // no clearing of the workspace: every tile that is read has been written before (the K-range
         // flags keep the triangular products inside the written tiles)
-        (void)used;
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];
             SelinvWs w = ws_layout(f);
@@ -443,16 +575,20 @@ struct Builder {
         }
         flush_simple(gab, p.gather, L_GATHER, p.selinv, level);
         // Yt = Wt * L21^T
+        bool any_r = false;
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];
             if (!f.r)
                 continue;
+            any_r = true;
             SelinvWs w = ws_layout(f);
             double* ws = b.pool + base[i];
             add_gemm(gb, Wtof(chunk[i]), ldw_of(f), panel(f) + (size_t)f.k * f.ldk, f.ldk, ws + w.Yt, w.ldr, (int)f.k, (int)f.r,
-                     (int)f.k, GEMM_KLO_ROW);
+                     (int)f.k, GEMM_KLO_ROW | mcf, 0, nullptr, sh, MC_POOL);
         }
         flush_gemm(gb, p.selinv, level, T_YT);
+        if (dist && any_r)
+            add_barrier(p.selinv, level);
         // Z21 = -G * Y   (overwrites L21), with its transpose Z21t stored by the same epilogue
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];
@@ -461,16 +597,21 @@ struct Builder {
             SelinvWs w = ws_layout(f);
             double* ws = b.pool + base[i];
             add_gemm(gb, ws + w.G, w.ldg, ws + w.Yt, w.ldr, panel(f) + (size_t)f.k * f.ldk, f.ldk, (int)f.r, (int)f.k,
-                     (int)f.r, GEMM_NEG | GEMM_DUAL);
+                     (int)f.r, GEMM_NEG | GEMM_DUAL | mcf, 0, nullptr, sh, MC_PANELS | (MC_POOL << 8));
             gb.back().Ct = ws + w.Z21t;
             gb.back().ldct = w.ldr;
         }
         flush_gemm(gb, p.selinv, level, T_Z21);
-        // Z11 = Wt Wt^T   (overwrites L11, lower triangle)
+        if (dist && any_r)
+            add_barrier(p.selinv, level);
+        // Z11 = Wt Wt^T   (overwrites L11, lower triangle); fronts without a boundary are finished by this product
+        bool any_root = false;
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];
+            const bool last = f.r == 0;
+            any_root = any_root || last;
             add_gemm(gb, Wtof(chunk[i]), ldw_of(f), Wtof(chunk[i]), ldw_of(f), panel(f), f.ldk, (int)f.k, (int)f.k, (int)f.k,
-                     GEMM_LOWER | GEMM_KLO_MAX);
+                     GEMM_LOWER | GEMM_KLO_MAX | (last ? mcf : 0), 0, nullptr, sh, MC_PANELS);
         }
         flush_gemm(gb, p.selinv, level, T_Z11_WW);
         // Z11 -= Yt * Z21t^T
@@ -481,15 +622,26 @@ struct Builder {
             SelinvWs w = ws_layout(f);
             double* ws = b.pool + base[i];
             add_gemm(gb, ws + w.Yt, w.ldr, ws + w.Z21t, w.ldr, panel(f), f.ldk, (int)f.k, (int)f.k, (int)f.r,
-                     GEMM_ACCUM | GEMM_NEG | GEMM_LOWER);
+                     GEMM_ACCUM | GEMM_NEG | GEMM_LOWER | mcf, 0, nullptr, sh, MC_PANELS);
         }
         flush_gemm(gb, p.selinv, level, T_Z11_YZ);
+        if (dist && (any_r || any_root))
+            add_barrier(p.selinv, level);
     }
 
     void build_selinv()
     {
+        if (multi())
+            for (size_t lvi = s.levels.size(); lvi-- > 0;)
+                for (uint32_t fi : top_fronts(lvi)) {
+                    if (ws_layout(s.fronts[fi]).total > b.pool_doubles) {
+                        err = "workspace pool smaller than the largest front";
+                        return;
+                    }
+                    build_selinv_chunk({fi}, {0}, (int)lvi, true);
+                }
         for (size_t lvi = s.levels.size(); lvi-- > 0;) {
-            const std::vector<uint32_t> fl = owned(lvi);
+            const std::vector<uint32_t> fl = local_fronts(lvi);
             std::vector<uint32_t> chunk;
             std::vector<size_t> base;
             size_t used = 0;
@@ -500,7 +652,7 @@ struct Builder {
                     return;
                 }
                 if (used + need > b.pool_doubles) {
-                    build_selinv_chunk(chunk, base, used, (int)lvi);
+                    build_selinv_chunk(chunk, base, (int)lvi, false);
                     chunk.clear();
                     base.clear();
                     used = 0;
@@ -510,8 +662,7 @@ struct Builder {
                 used += need;
             }
             if (!chunk.empty())
-                build_selinv_chunk(chunk, base, used, (int)lvi);
-            add_sync(p.selinv, lvi);  // the inverse panels of this level's top fronts are broadcast to every rank
+                build_selinv_chunk(chunk, base, (int)lvi, false);
         }
         for (auto& L : p.selinv)
             p.selinv_flops += L.flops;
@@ -526,7 +677,7 @@ size_t min_pool_doubles(const Symbolic& s)
 {
     size_t need = 0;
     for (const Front& f : s.fronts)
-        if (f.owner == s.rank)
+        if (f.owner == s.rank || f.top)
             need = std::max(need, ws_layout(f).total);
     return std::max<size_t>(16, need);
 }
@@ -535,7 +686,7 @@ size_t wbuf_doubles(const Symbolic& s)
 {
     size_t o = 0;
     for (const Front& f : s.fronts)
-        if (f.owner == s.rank)
+        if (f.owner == s.rank || f.top)
             o += 2 * wblock(f);
     return std::max<size_t>(16, o);
 }
@@ -546,7 +697,7 @@ size_t ideal_pool_doubles(const Symbolic& s)
     for (auto& lv : s.levels) {
         size_t t = 0;
         for (uint32_t f : lv)
-            if (s.fronts[f].owner == s.rank)
+            if (s.fronts[f].owner == s.rank && !s.fronts[f].top)
                 t += ws_layout(s.fronts[f]).total;
         best = std::max(best, t);
     }
@@ -582,6 +733,7 @@ std::string build_plan(const Symbolic& s, const PlanBuffers& b, Plan& p)
     p.gemv.clear();
     p.transpose.clear();
     p.gather.clear();
+    p.reduce.clear();
     p.factor.clear();
     p.fwd.clear();
     p.bwd.clear();
@@ -593,7 +745,7 @@ std::string build_plan(const Symbolic& s, const PlanBuffers& b, Plan& p)
     p.tgt.assign(s.targets.size(), ScatterTarget{});
     p.coltgt.assign(s.bnd.size(), -1);
     for (const Front& f : s.fronts) {
-        if (f.owner != s.rank)
+        if (f.owner != s.rank && !f.top)
             continue;
         for (uint32_t t = 0; t < f.tgt_count; ++t) {
             const Target& tg = s.targets[f.tgt_begin + t];

@@ -18,7 +18,8 @@ enum LaunchKind : int32_t {
     L_TRANSPOSE,
     L_GATHER,
     L_ZERO,
-    L_SYNC,      // multi-GPU stage boundary: the host exchanges the top fronts of `level` before going on
+    L_BARRIER,   // multi-GPU: all ranks meet (device-side barrier over NVLink); stores into peers' replicas are visible after it
+    L_ALLREDUCE, // multi-GPU: sum of the ranks' replicas of some ranges of a buffer, written back to every replica
 };
 
 struct Launch {
@@ -32,6 +33,8 @@ struct Launch {
     size_t zero_bytes;
     double flops;         // algorithmic flops of this launch (GEMM: 2MNK, halved for LOWER)
     int32_t tag;          // which step of the algorithm (profiling label)
+    int32_t mcast;        // L_GEMM: some op of the launch stores into the peers' replicas (GEMM_MCAST)
+    int32_t buf;          // L_ALLREDUCE: McBuf of the buffer the ranges live in
 };
 
 enum LaunchTag : int32_t {
@@ -61,6 +64,7 @@ struct Plan {
     std::vector<GemvOp> gemv;
     std::vector<TransposeOp> transpose;
     std::vector<GatherOp> gather;
+    std::vector<ReduceOp> reduce;
     std::vector<Launch> factor, fwd, bwd, selinv;
     std::vector<int32_t> rowidx;            // host copy (uploaded by the caller before build_plan's pointers are used)
     std::vector<uint64_t> rowidx_off;       // per front

@@ -430,22 +430,34 @@ void finalize_layout(Symbolic& s, int world, int rank)
             s.cut_level = std::min(s.cut_level, f.level);
         }
     }
-    // storage: owned fronts + all top fronts
+    // storage: every top front first, in front order — the same offsets on every rank, so that a tile finished by one rank
+    // can be stored into all replicas at (peer base + local offset) — then the fronts of this rank's subtrees
     uint64_t off = 0;
     s.my_factor_flops = s.my_inverse_flops = 0;
-    for (uint32_t fi = 0; fi < F; ++fi) {
-        Front& f = s.fronts[fi];
-        if (f.owner == rank || f.top) {
-            f.panel_off = off;
-            uint64_t sz = (uint64_t)f.m * f.ldk;
-            off += (sz + 15) & ~(uint64_t)15;
-        } else
-            f.panel_off = NO_DEST;
-        if (f.owner == rank) {
+    for (int pass = 0; pass < 2; ++pass) {
+        for (uint32_t fi = 0; fi < F; ++fi) {
+            Front& f = s.fronts[fi];
+            if ((pass == 0) != (f.top != 0))
+                continue;
+            if (f.top || f.owner == rank) {
+                f.panel_off = off;
+                uint64_t sz = (uint64_t)f.m * f.ldk;
+                off += (sz + 15) & ~(uint64_t)15;
+            } else
+                f.panel_off = NO_DEST;
             double k = f.k, r = f.r;
-            s.my_factor_flops += k * k * k / 3.0 + k * k * r + k * r * r;
-            s.my_inverse_flops += 2.0 * k * k * k / 3.0 + 2.0 * k * k * r + 2.0 * k * r * r + 2.0 * k * k * r;
+            const double ff = k * k * k / 3.0 + k * k * r + k * r * r;
+            const double fi2 = 2.0 * k * k * k / 3.0 + 2.0 * k * k * r + 2.0 * k * r * r + 2.0 * k * k * r;
+            if (f.top) {   // the tiles of a top front are shared out among the ranks
+                s.my_factor_flops += ff / world;
+                s.my_inverse_flops += fi2 / world;
+            } else if (f.owner == rank) {
+                s.my_factor_flops += ff;
+                s.my_inverse_flops += fi2;
+            }
         }
+        if (pass == 0)
+            s.top_panel_doubles = off;
     }
     s.panel_doubles = off;
     s.pos_owned.assign(s.nstn, 0);

@@ -24,8 +24,8 @@ struct Front {
     uint32_t ldk = 0;         // panel row pitch (doubles), even
     uint64_t panel_off = 0;   // offset (doubles) of the m x ldk row-major panel
     uint32_t tgt_begin = 0, tgt_count = 0;  // range into Symbolic::targets
-    int32_t owner = 0;        // rank that factorises this front (multi-GPU sharding by subtree)
-    uint8_t top = 0;          // 1: above the subtree cut — storage replicated on every rank, contributions reduced
+    int32_t owner = 0;        // rank that holds this front (multi-GPU sharding by subtree); top fronts: the rank that assembles N into it
+    uint8_t top = 0;          // 1: above the subtree cut — replicated on every rank, its tiles shared out among the ranks
     double work = 0;          // factor + inverse flops of this front
 };
 
@@ -50,6 +50,7 @@ struct Symbolic {
     std::vector<int32_t> rowmap;        // concatenated station-level row maps
     std::vector<std::vector<uint32_t>> levels;  // fronts by level
     uint64_t panel_doubles = 0;
+    uint64_t top_panel_doubles = 0;     // leading part of the panel storage: the replicated top fronts (same layout on every rank)
     // block-CSR pattern of N in elimination order: column block p holds the diagonal slot
     // followed by its later neighbours q > p (ascending)
     std::vector<uint64_t> ncol_ptr;     // size nstn+1, slot offsets

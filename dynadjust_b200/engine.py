@@ -57,6 +57,12 @@ class GadjProfile(C.Structure):
                 ("launches", C.c_uint64), ("gemm_launches", C.c_uint64), ("gemm_tiles", C.c_uint64)]
 
 
+class GadjPeerInfo(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("device", C.c_int32), ("pid", C.c_int64), ("ptr", C.c_uint64 * 9),
+                ("bytes", C.c_uint64 * 9), ("handle", (C.c_uint8 * 64) * 9), ("top_panel_doubles", C.c_uint64),
+                ("nstations", C.c_uint64)]
+
+
 EXPORTS = ["gadj_default_opts", "gadj_create", "gadj_destroy", "gadj_last_error", "gadj_set_stations",
            "gadj_set_measurements", "gadj_set_measurements_reduced", "gadj_set_blocks", "gadj_prepare", "gadj_get_info", "gadj_upload_measurements",
            "gadj_upload_measurements_range",
@@ -64,9 +70,7 @@ EXPORTS = ["gadj_default_opts", "gadj_create", "gadj_destroy", "gadj_last_error"
            "gadj_update_ignored_measurements", "gadj_compute_measurements", "gadj_get_estimates",
            "gadj_get_corrections", "gadj_get_station_vcvs", "gadj_get_station_vcv", "gadj_get_vcv_block",
            "gadj_get_normals_block", "gadj_get_rhs", "gadj_get_block_vcv", "gadj_get_pair_vcvs", "gadj_profile_enable", "gadj_profile_read", "gadj_test_gemm",
-           "gadj_mg_init", "gadj_stage_begin", "gadj_stage_normals_pending", "gadj_stage_run", "gadj_stage_solve_begin",
-           "gadj_stage_solve_end", "gadj_stage_apply", "gadj_stage_end", "gadj_stage_mark_inverse", "gadj_sync", "gadj_mg_buffer",
-           "gadj_mg_top_fronts", "gadj_mg_extract_vcv"]
+           "gadj_mg_init", "gadj_mg_export", "gadj_mg_connect", "gadj_sync", "gadj_mg_buffer"]
 
 _libs = {}
 
@@ -112,18 +116,10 @@ def load_library(path=None):
     L.gadj_profile_enable.argtypes = [vp, i32]
     L.gadj_profile_read.argtypes = [vp, C.POINTER(GadjProfile), i32]
     L.gadj_mg_init.argtypes = [vp, C.c_int32, C.c_int32]
-    L.gadj_stage_begin.argtypes = [vp, i32]
-    L.gadj_stage_normals_pending.argtypes = [vp]
-    L.gadj_stage_run.argtypes = [vp, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
-    L.gadj_stage_solve_begin.argtypes = [vp]
-    L.gadj_stage_solve_end.argtypes = [vp]
-    L.gadj_stage_apply.argtypes = [vp]
-    L.gadj_stage_end.argtypes = [vp, i32, C.c_int32, C.POINTER(GadjIterResult)]
-    L.gadj_stage_mark_inverse.argtypes = [vp]
+    L.gadj_mg_export.argtypes = [vp, C.POINTER(GadjPeerInfo)]
+    L.gadj_mg_connect.argtypes = [vp, C.POINTER(GadjPeerInfo)]
     L.gadj_sync.argtypes = [vp]
     L.gadj_mg_buffer.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]
-    L.gadj_mg_top_fronts.argtypes = [vp, C.c_int32, u32, C.POINTER(u32), vp, vp, vp, vp, vp]
-    L.gadj_mg_extract_vcv.argtypes = [vp]
     L.gadj_test_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, C.POINTER(C.c_float)]
     _libs[path] = L
     return L

@@ -135,9 +135,10 @@ int gadj_set_blocks(gadj_ctx* c, uint32_t nblocks, const uint32_t* isl_off, cons
 int gadj_prepare(gadj_ctx* c);
 int gadj_get_info(const gadj_ctx* c, gadj_info* info);
 
-/* re-send the host measurement records / a-priori station coordinates to the device */
+/* re-send the host measurement records to the device (multi-GPU: every rank sends its 1/world share over its own PCIe
+ * link and pulls the rest from the peers' device copies over NVLink) */
 int gadj_upload_measurements(gadj_ctx* c);
-/* same for records [first, first + count): one rank's share of a sharded upload (the ranks then all-gather the device copies) */
+/* records [first, first + count) only */
 int gadj_upload_measurements_range(gadj_ctx* c, uint64_t first, uint64_t count);
 int gadj_reset_estimates(gadj_ctx* c);
 
@@ -180,32 +181,41 @@ int gadj_get_normals_block(gadj_ctx* c, uint32_t si, uint32_t sj, double n[9]);
 int gadj_get_rhs(gadj_ctx* c, double* w /* 3*nstn */);
 
 /*
- * Staged execution and multi-GPU sharding.  The dissection tree is cut into subtrees, one set per rank
- * (one process per GPU); fronts above the cut ("top" fronts) have storage on every rank, are factorised by one
- * owner, and are the only data exchanged: before an owner factorises a top front the ranks' partial Schur sums
- * of its panel are reduced to it; before/after its triangular solves its slice of the solution vector is
- * summed / broadcast; after its inverse panel is formed it is broadcast.  gadj_stage_run executes one phase's
- * launches from *cursor up to the next exchange point and reports the tree level whose top fronts
- * (gadj_mg_top_fronts) must be exchanged there (-1: phase finished).  The host driver does the collectives
- * (torch.distributed / NCCL in dynadjust_b200/multigpu.py) on the buffers returned by gadj_mg_buffer.
- * This is the sum form of the reference's junction-station carry between blocks (ADJ:998-1281, 3196-3333).
+ * Multi-GPU: one rank per GPU (threads of one process or one process per GPU), the dissection tree cut into subtrees,
+ * one set per rank.  The fronts above the cut ("top" fronts = the separators shared by several ranks' subtrees, the
+ * junction stations of the reference's phased mode) are stored by every rank at the same offsets; their work is shared
+ * out tile by tile, and the exchange happens inside the kernels over NVLink peer mappings:
+ *   - the ranks' partial Schur sums of a top front meet in an all-reduce kernel (each rank reduces a slice, reading the
+ *     peers' replicas, and stores the sum into every replica);
+ *   - a rank that finishes a tile of a top front (panel, pivot-tile inverse, inverse panel) stores it into every
+ *     replica from the GEMM epilogue;
+ *   - the ranks meet at device-side barriers (counters in peer memory), never on the host.
+ * This is the sum form of the reference's junction-station carry between blocks (ADJ:998-1281, 3196-3333) and of
+ * its thread pool over blocks (dnaadjust-multi.cpp:92-310).  Call sequence per rank:
+ *   gadj_create, gadj_mg_init(rank, world), gadj_set_*, gadj_prepare, gadj_mg_export  -> exchange the gadj_peer_info
+ *   records of all ranks (any host transport: shared memory between threads, a torch.distributed all_gather, a pipe) ->
+ *   gadj_mg_connect(all)  ->  gadj_iterate / gadj_adjust / gadj_statistics / getters as on one GPU.  Every rank must make
+ *   the same calls in the same order (each one contains the same barriers).
  */
-enum { GADJ_PHASE_FACTOR = 0, GADJ_PHASE_FORWARD = 1, GADJ_PHASE_BACKWARD = 2, GADJ_PHASE_INVERSE = 3 };
-enum { GADJ_BUF_X = 0, GADJ_BUF_PANELS = 1, GADJ_BUF_STATION_VCV = 2, GADJ_BUF_EDGE_VCV = 3, GADJ_BUF_INFO = 4 };
+enum { GADJ_IPC_HANDLE_BYTES = 64, GADJ_PEER_BUFFERS = 9 };
+typedef struct gadj_peer_info {
+    int32_t rank, device;
+    int64_t pid;                                        /* ranks of one process use the raw pointers (peer access enabled) */
+    uint64_t ptr[GADJ_PEER_BUFFERS];                    /* device address in the exporting process */
+    uint64_t bytes[GADJ_PEER_BUFFERS];
+    uint8_t handle[GADJ_PEER_BUFFERS][GADJ_IPC_HANDLE_BYTES];   /* cudaIpcMemHandle of each buffer (other processes) */
+    uint64_t top_panel_doubles;                         /* consistency check: the replicated layout */
+    uint64_t nstations;
+} gadj_peer_info;
 int gadj_mg_init(gadj_ctx* c, int32_t rank, int32_t world);          /* before gadj_prepare */
-int gadj_stage_begin(gadj_ctx* c, int flags);                         /* assembly, equilibration, scatter */
-int gadj_stage_normals_pending(gadj_ctx* c);                          /* 1 when this iteration refactorises */
-int gadj_stage_run(gadj_ctx* c, int phase, int64_t* cursor, int32_t* sync_level);
-int gadj_stage_solve_begin(gadj_ctx* c);                              /* right-hand side into the solution vector */
-int gadj_stage_solve_end(gadj_ctx* c);                                /* zero the entries other ranks own (then sum across ranks) */
-int gadj_stage_apply(gadj_ctx* c);                                    /* corrections, estimates, largest correction */
-int gadj_stage_end(gadj_ctx* c, int flags, int32_t global_info, gadj_iter_result* res);
-int gadj_stage_mark_inverse(gadj_ctx* c);                             /* after a stand-alone GADJ_PHASE_INVERSE run */
+int gadj_mg_export(gadj_ctx* c, gadj_peer_info* out);                /* after gadj_prepare */
+int gadj_mg_connect(gadj_ctx* c, const gadj_peer_info* all /* world entries, in rank order */);
 int gadj_sync(gadj_ctx* c);                                           /* wait for the context's stream */
+/* raw device buffers (diagnostics and tests): x, panels, station / pair variance blocks, info words, records,
+ * pivot-block inverses, inverse workspace */
+enum { GADJ_BUF_X = 0, GADJ_BUF_PANELS = 1, GADJ_BUF_STATION_VCV = 2, GADJ_BUF_EDGE_VCV = 3, GADJ_BUF_INFO = 4, GADJ_BUF_MSR = 5,
+       GADJ_BUF_WBUF = 6, GADJ_BUF_POOL = 7 };
 int gadj_mg_buffer(gadj_ctx* c, int which, void** ptr, uint64_t* count);
-int gadj_mg_top_fronts(gadj_ctx* c, int32_t level, uint32_t cap, uint32_t* n, uint64_t* panel_off, uint64_t* panel_len,
-                       uint64_t* x_off, uint64_t* x_len, int32_t* owner);
-int gadj_mg_extract_vcv(gadj_ctx* c);                                 /* per-rank VCV pieces (zeros elsewhere), then sum across ranks */
 
 /* optional per-launch timing; small overhead (two event records per launch) */
 int gadj_profile_enable(gadj_ctx* c, int on);

@@ -2,8 +2,10 @@
 // Plain-loop stand-ins for every launch in csrc/kernels.h: an executable statement of what
 // each CUDA kernel must compute, used to validate the planner / index maps / control flow on
 // CPU.  Never linked into the product library.
+#include <chrono>
 #include <cmath>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../dynadjust_b200/csrc/geodesy.h"
@@ -12,7 +14,17 @@
 
 namespace gadj {
 
-void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, void*)
+// store into this rank's buffer and, for multicast ops, into every other rank's replica
+static inline void mc_store(double* p, double v, const PeerTable* pt, int buf)
+{
+    *p = v;
+    if (pt && buf != MC_NONE)
+        for (int q = 0; q < pt->nranks; ++q)
+            if (q != pt->rank)
+                *reinterpret_cast<double*>(reinterpret_cast<char*>(p) + pt->delta[buf][q]) = v;
+}
+
+void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, const PeerTable* pt, bool mcast, void*)
 {
     // tile by tile, exactly the work list the persistent CTAs stride through: a tile missing from the planner's
     // list, or listed twice, changes the results
@@ -52,18 +64,18 @@ void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles,
                     int64_t r = 3ll * tg.rowmap[i / 3 - tg.jb] + i % 3;
                     int64_t c = 3ll * tg.rowmap[j / 3 - tg.jb] + j % 3;
                     tg.C[r * tg.ldc + c] += v;
-                } else if (op.flags & GEMM_ACCUM)
-                    op.C[(int64_t)i * op.ldc + j] += v;
-                else {
-                    op.C[(int64_t)i * op.ldc + j] = v;
+                } else {
+                    const bool mc = mcast && (op.flags & GEMM_MCAST);
+                    double* c = op.C + (int64_t)i * op.ldc + j;
+                    mc_store(c, (op.flags & GEMM_ACCUM) ? *c + v : v, mc ? pt : nullptr, op.mc & 0xff);
                     if (op.flags & GEMM_DUAL)
-                        op.Ct[(int64_t)j * op.ldct + i] = v;
+                        mc_store(op.Ct + (int64_t)j * op.ldct + i, v, mc ? pt : nullptr, (op.mc >> 8) & 0xff);
                 }
             }
     }
 }
 
-void launch_diag(const DiagOp* ops, int nops, int* info, void*)
+void launch_diag(const DiagOp* ops, int nops, int* info, const PeerTable* pt, void*)
 {
     for (int o = 0; o < nops; ++o) {
         const DiagOp& op = ops[o];
@@ -104,12 +116,60 @@ void launch_diag(const DiagOp* ops, int nops, int* info, void*)
             for (int i = 0; i < w; ++i)
                 for (int j = 0; j < w; ++j) {
                     if (op.W)
-                        op.W[i * op.ldw + j] = W[(size_t)i * w + j];
+                        mc_store(op.W + i * op.ldw + j, W[(size_t)i * w + j], op.mc ? pt : nullptr, MC_WBUF);
                     if (op.Wt)
-                        op.Wt[j * op.ldwt + i] = W[(size_t)i * w + j];
+                        mc_store(op.Wt + j * op.ldwt + i, W[(size_t)i * w + j], op.mc ? pt : nullptr, MC_WBUF);
                 }
         }
+        if (op.factor && op.mc && pt)
+            for (int i = 0; i < w; ++i)
+                for (int j = 0; j <= i; ++j)
+                    mc_store(D + i * ld + j, D[i * ld + j], pt, MC_PANELS);
     }
+}
+
+// ---- multi-rank stand-ins: the ranks are threads of one process or separate processes sharing memory ----
+void launch_barrier(const PeerTable* pt, unsigned long long target, int* info, void*)
+{
+    for (int q = 0; q < pt->nranks; ++q)
+        __atomic_fetch_add(pt->counter[q], 1ull, __ATOMIC_SEQ_CST);
+    const auto t0 = std::chrono::steady_clock::now();
+    while (__atomic_load_n(pt->counter[pt->rank], __ATOMIC_SEQ_CST) < target) {
+        std::this_thread::yield();
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60)) {
+            info[1] = 1;
+            break;
+        }
+    }
+}
+
+void launch_allreduce(const ReduceOp* ops, int nops, const PeerTable* pt, double* base, int buf, void*)
+{
+    const int n = pt->nranks, me = pt->rank;
+    for (int o = 0; o < nops; ++o) {
+        const uint64_t lo = ops[o].count * me / n, hi = ops[o].count * (me + 1) / n;
+        for (uint64_t i = lo; i < hi; ++i) {
+            double* p = base + ops[o].off + i;
+            double s = 0.0;
+            for (int q = 0; q < n; ++q)
+                s += *reinterpret_cast<const double*>(reinterpret_cast<const char*>(p) + pt->delta[buf][q]);
+            for (int q = 0; q < n; ++q)
+                *reinterpret_cast<double*>(reinterpret_cast<char*>(p) + pt->delta[buf][q]) = s;
+        }
+    }
+}
+
+void launch_share_info(const PeerTable* pt, int* info, void*)
+{
+    for (int q = 0; q < pt->nranks; ++q)
+        if (q != pt->rank)
+            for (int k = 0; k < 2; ++k)
+                if (info[k] != 0) {
+                    int cur = __atomic_load_n(pt->info[q] + k, __ATOMIC_SEQ_CST);
+                    while (cur < info[k] && !__atomic_compare_exchange_n(pt->info[q] + k, &cur, info[k], false, __ATOMIC_SEQ_CST,
+                                                                         __ATOMIC_SEQ_CST)) {
+                    }
+                }
 }
 
 void launch_trimv(const TrimvOp* ops, int nops, void*)
@@ -382,7 +442,7 @@ void launch_mask_positions(double* x, const uint8_t* pos_owned, uint32_t nstn, v
 }
 
 void launch_apply_corrections(const double* x, const double* dscale, const uint32_t* pos, double* corr, double* est,
-                              uint32_t nstn, void*)
+                              uint32_t nstn, double*, void*)
 {
     size_t best = 0;
     for (uint32_t s = 0; s < nstn; ++s)

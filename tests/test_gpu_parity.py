@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 16), (128, 128, 128), (1, 1, 2), (3, 5, 4), (64, 64, 64), (129, 127, 18),
-                                   (200, 72, 50), (300, 260, 130), (512, 384, 1000), (1000, 1000, 6)])
+                                   (200, 72, 50), (300, 260, 130), (512, 384, 1000), (1000, 1000, 6),
+                                   (129, 127, 141), (64, 200, 33), (300, 260, 177), (257, 131, 3)])
 def test_gemm_tile_kernel(gpu_lib, M, N, K):
     """TMA-fed DMMA tile kernel: C = A B^T, ragged edges zero-filled by the tensor maps.  FP64: 1e-13 relative."""
     rng = np.random.default_rng(M * 1000003 + N * 1009 + K)
