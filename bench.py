@@ -218,7 +218,8 @@ def run_engine(args):
 
     if world > 1:
         from dynadjust_b200 import multigpu
-        runner = multigpu.ShardedAdjustment(stn, msr_p, rank, world, device=local_rank, **eng_opts)
+        runner = multigpu.ShardedAdjustment(stn, msr_p, rank, world, multigpu.TorchExchange(torch.device("cuda", local_rank)),
+                                            device=local_rank, **eng_opts)
     else:
         runner = engine.Adjustment(stn, msr_p, device=local_rank, **eng_opts)
     t = time.time()
@@ -241,8 +242,6 @@ def run_engine(args):
         step()
     runner.profile_enable(True)
     runner.profile_read(reset=True)
-    if getattr(runner, "_trace", None) is not None:
-        runner._trace.clear()
     phase = dict(assemble=0.0, factor=0.0, solve=0.0, inverse=0.0)
     with ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank) as clk:
         barrier()
@@ -257,9 +256,6 @@ def run_engine(args):
         t1 = time.perf_counter()
     prof = runner.profile_read(reset=True)
     runner.profile_enable(False)
-    if getattr(runner, "_trace", None) is not None:     # GADJ_MG_TRACE=<path prefix>: per-rank stage / exchange wall times
-        with open(f"{os.environ['GADJ_MG_TRACE']}.rank{rank}.json", "w") as f:
-            json.dump(dict(steps=args.steps, records=runner._trace), f)
     clocks = clk.summary()
     ms_step = (t1 - t0) * 1e3 / args.steps
     if world > 1:
@@ -320,7 +316,8 @@ def run_engine(args):
                             ordering=f"nested dissection, leaf {eng_opts.get('leaf_stations')} stations",
                             fronts=int(info.nfronts), levels=int(info.nlevels), l2_note="inputs larger than L2",
                             sharding=(f"{world} ranks, subtrees of the dissection tree; {info.top_fronts} shared top fronts "
-                                      f"exchanged by NCCL reduce/broadcast (cut at level {info.cut_level})") if world > 1 else "none",
+                                      f"replicated, their tiles shared out among the ranks; all-reduce / multicast stores / barriers in "
+                                      f"our kernels over NVLink peer mappings (cut at level {info.cut_level})") if world > 1 else "none",
                             panel_gb=info.panel_bytes / 1e9, prepare_s=prepare_s),
                 e2e=dict(value=e2e_ms, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
                 gpu_launches=int(prof.launches), clocks=clocks, roofline=roofline, roofline_assembly=roofline_asm,

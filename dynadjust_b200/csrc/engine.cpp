@@ -2565,23 +2565,36 @@ int gadj_profile_read(gadj_ctx* c, gadj_profile* out, int reset)
 int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int M, int N, int K, int reps, float* ms)
 {
     dev::use(c->device);
-    if (M <= 0 || N <= 0 || K <= 0 || (K & 1))
-        return c->fail("gadj_test_gemm: M, N, K must be positive and K even");
+    if (M <= 0 || N <= 0 || K <= 0)
+        return c->fail("gadj_test_gemm: M, N, K must be positive");
     DevArray<double> dA, dB, dC;
     DevArray<GemmOp> dop;
     DevArray<GemmTile> dtl;
-    const int ldc = N + (N & 1);
-    if (!dA.resize((size_t)M * K) || !dB.resize((size_t)N * K) || !dC.resize((size_t)M * ldc) || !dop.resize(1))
+    // rows padded to an even pitch like every panel of the engine (odd K = 3 x an odd station count is the common case);
+    // the padding holds NaNs: it lies beyond the tensor map's extent and must never reach the product
+    const int ldc = N + (N & 1), ldk = K + (K & 1);
+    if (!dA.resize((size_t)M * ldk) || !dB.resize((size_t)N * ldk) || !dC.resize((size_t)M * ldc) || !dop.resize(1))
         return c->fail("out of device memory");
-    dev::h2d(dA.p, A, dA.bytes());
-    dev::h2d(dB.p, B, dB.bytes());
+    {
+        const double nan = std::nan("");
+        std::vector<double> pa((size_t)M * ldk, nan), pb((size_t)N * ldk, nan);
+        for (int i = 0; i < M; ++i)
+            std::memcpy(pa.data() + (size_t)i * ldk, A + (size_t)i * K, (size_t)K * sizeof(double));
+        for (int i = 0; i < N; ++i)
+            std::memcpy(pb.data() + (size_t)i * ldk, B + (size_t)i * K, (size_t)K * sizeof(double));
+        dev::h2d(dA.p, pa.data(), dA.bytes());
+        dev::h2d(dB.p, pb.data(), dB.bytes());
+        std::string e0 = dev::sync();
+        if (!e0.empty())
+            return c->fail(e0);
+    }
     dev::zero(dC.p, dC.bytes());
     GemmOp op{};
     op.A = dA.p;
     op.B = dB.p;
     op.C = dC.p;
-    op.lda = K;
-    op.ldb = K;
+    op.lda = ldk;
+    op.ldb = ldk;
     op.ldc = ldc;
     op.M = M;
     op.N = N;
@@ -2595,7 +2608,7 @@ int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int
             tl.push_back(GemmTile{0, (uint16_t)tm, (uint16_t)tn});
     if (!dtl.upload(tl))
         return c->fail("out of device memory");
-    if (!dev::encode_tma_2d(&op.tmA, op.A, M, K, K, TILE_M) || !dev::encode_tma_2d(&op.tmB, op.B, N, K, K, TILE_N))
+    if (!dev::encode_tma_2d(&op.tmA, op.A, M, K, ldk, TILE_M) || !dev::encode_tma_2d(&op.tmB, op.B, N, K, ldk, TILE_N))
         return c->fail("tensor-map encoding failed");
     dev::h2d(dop.p, &op, sizeof(op));
     launch_gemm(dop.p, 1, dtl.p, (int)tl.size(), nullptr, false, dev::stream());
