@@ -12,6 +12,11 @@ K steps through the C-ABI with the measurement records in pinned host memory (H2
 and the adjusted coordinates + every station's 3x3 VCV read back (D2H inside the timed region).
 Inputs (6.2 GB of records, ~30 GB of front panels) are far larger than the 126 MB L2, so no explicit flush
 is needed between iterations.
+
+--workload selects the other BASELINE.json configurations (records of those runs are kept under profiles/):
+  C2  10k stations, dense normals (one 30 000 x 30 000 front: Solve ADJ:6586 on dense normals)
+  C3  100k stations, GNSS + direction sets + distances + levelling, phased: a chain of 1000-station blocks
+  C5  100k stations, rigorous full inverse: every block's dense variance matrix and every pattern block read back
 """
 import argparse
 import json
@@ -31,28 +36,34 @@ UNIT = "ms"
 BYTES_PER_BASELINE = 944   # 3*208 records + 8 plan words + 48 station XYZ + 27*8 block updates + 48 rhs
 
 WORKLOADS = {
-    # name: (synth config, engine options)
-    "C4": ("C4", dict(leaf_stations=64)),      # leaf sweep on the current kernels: profiles/r1_leaf_sweep_c4.json
-    "C3g": ("C3g", dict(leaf_stations=96)),
-    "C2": ("C2", dict(leaf_stations=96)),
-    "C1": ("C1", dict(leaf_stations=16)),
+    # name: synth config, engine options, chain block width (phased), extras
+    "C4": dict(cfg="C4", opts=dict(leaf_stations=64)),      # leaf sweep: profiles/r1_leaf_sweep_c4.json
+    "C2": dict(cfg="C2", opts=dict(ordering=1), dense=True),
+    "C3": dict(cfg="C3", opts=dict(), chain=1000),
+    "C5": dict(cfg="C5", opts=dict(leaf_stations=96), full_vcv=True),
+    "C3g": dict(cfg="C3g", opts=dict(leaf_stations=96)),
+    "C1": dict(cfg="C1", opts=dict(leaf_stations=16)),
 }
 
 
 def workload_name(key, cfg):
-    return (f"{key}: {cfg['n_stations']} stations / {cfg['n_baselines']} GNSS baselines, "
+    extra = {"C2": ", dense normals (one front)", "C3": " + direction sets, distances, levelling; phased over a chain of 1000-station blocks",
+             "C5": ", rigorous full inverse: every block's dense variance matrix and every pattern block read back"}.get(key, "")
+    return (f"{key}: {cfg['n_stations']} stations / {cfg['n_baselines']} GNSS baselines{extra}, "
             "one Gauss-Newton iteration = assemble + factorise + solve + rigorous (selected) inverse")
 
 
 def ncu_traffic(*kernels):
     """DRAM bytes per launch of the named kernel(s), summed, from the committed ncu capture of this workload
-    (profiles/r1_ncu_dram_traffic_c4.json: dram__bytes_read.sum + dram__bytes_write.sum, C4 on one GPU)."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_dram_traffic_c4.json")
-    try:
-        k = json.load(open(p))["kernels"]
-        return float(sum(k[name]["dram_bytes_per_launch"] for name in kernels))
-    except (OSError, KeyError, ValueError):
-        return None
+    (dram__bytes_read.sum + dram__bytes_write.sum, C4 on one GPU)."""
+    for name in ("r2_ncu_dram_traffic_c4.json", "r1_ncu_dram_traffic_c4.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        try:
+            k = json.load(open(p))["kernels"]
+            return float(sum(k[kn]["dram_bytes_per_launch"] for kn in kernels)), name
+        except (OSError, KeyError, ValueError):
+            continue
+    return None, None
 
 
 def measured_peaks():
@@ -114,7 +125,9 @@ class ClockSampler:
 
 
 def fp64_peak_tflops():
-    """cuBLAS DGEMM 8192^3, best of 5 — MEASURED_PEAKS.json carries no FP64 figure."""
+    """cuBLAS DGEMM 8192^3: best of 5 (burst) and back to back for ~2 s (sustained) — MEASURED_PEAKS.json carries no FP64
+    figure.  The GEMM kernel is timed inside a step that runs for seconds, so the roofline uses the
+    sustained rate."""
     import torch
     n = 8192
     a = torch.randn(n, n, dtype=torch.float64, device="cuda")
@@ -129,43 +142,128 @@ def fp64_peak_tflops():
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
+    reps = max(8, int(2000.0 / best))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    sustained = e0.elapsed_time(e1) / reps
     del a, b
     torch.cuda.empty_cache()
-    return 2.0 * n ** 3 / best / 1e9
+    return 2.0 * n ** 3 / best / 1e9, 2.0 * n ** 3 / sustained / 1e9
 
 
-def cpu_sample(total_stations, baselines_per_station, blocks=1000, block_stations=150, threads=None):
-    """The reference's CPU path on a bounded sample of the workload.
+def cached_cpu_run(key):
+    """The full CPU run of this configuration made once with tools/cpu_baselines.py (C2, C3), if its record is committed."""
+    p = os.path.join(ROOT, "profiles", f"r2_cpu_baseline_{key.lower()}.json")
+    try:
+        return json.load(open(p))
+    except (OSError, ValueError):
+        return None
 
-    The reference adjusts a network of this size block by block (phased mode) on blocks produced by dnasegment,
-    whose default block size is 150 stations (min_inner_stations = max_total_stations = 150,
-    include/config/dnaoptions.hpp:382).  The sample is `blocks` such blocks of the same synthetic recipe, each run
-    through the oracle's dense per-block path (assembly, dpotrf+dpotri inverse through the compiled reference
-    matrix_2d when oracle/_ref is present, solve); the figure is extrapolated to total_stations/150 blocks,
-    forward pass only — the reference's reverse and combine passes (two more dense inversions per block,
-    ADJ:3512, ADJ:3556) and the junction-station carry are NOT counted, so this is a lower bound on its time."""
+
+def first_stations_subnetwork(stn, msr, nkeep):
+    """The measurements among the first `nkeep` stations (whole measurements only: baselines, clusters and direction sets
+    are kept or dropped as a unit) — a slice of the network with the full network's width, for bounded CPU samples."""
+    keep = np.zeros(len(msr), dtype=bool)
+    i, n = 0, len(msr)
+    mt, st1, st2, st3 = msr["measType"], msr["station1"], msr["station2"], msr["station3"]
+    vc1, vc2 = msr["vectorCount1"], msr["vectorCount2"]
+    while i < n:
+        t = mt[i]
+        if t == b"G":
+            span = 3
+            ok = st1[i] < nkeep and st2[i] < nkeep
+        elif t in (b"X", b"Y"):
+            j = i
+            ok = True
+            for _ in range(int(vc1[i])):
+                ok = ok and st1[j] < nkeep and (t == b"Y" or st2[j] < nkeep)
+                j += 3 + 3 * int(vc2[j])
+            span = j - i
+        elif t == b"D":
+            span = max(1, int(vc1[i]))
+            ok = st1[i] < nkeep and bool((st2[i:i + span] < nkeep).all())
+        else:
+            span = 1
+            ok = st1[i] < nkeep and (t in (b"H", b"R", b"I", b"J", b"P", b"Q") or st2[i] < nkeep) and (t != b"A" or st3[i] < nkeep)
+        if ok:
+            keep[i:i + span] = True
+        i += span
+    sub = msr[keep].copy()
+    return stn[:nkeep].copy(), sub
+
+
+def cpu_sample(key, args, threads=None):
+    """The reference's CPU path on a bounded sample of the workload (about 10-30 s of CPU work), scaled to the workload.
+
+    C4 / C5 / C3g: the reference adjusts a network of this size block by block (phased mode) on blocks produced by
+      dnasegment, whose default block size is 150 stations (dnaoptions.hpp:382).  The sample is a number of such blocks of
+      the same synthetic recipe, each run through the oracle's dense per-block path (assembly, packed Cholesky inverse
+      through the compiled reference matrix_2d when oracle/_ref is present, solve), extrapolated to stations/150 blocks,
+      forward pass only — reverse / combination passes and the junction carry are NOT counted: a lower bound.
+    C2: the dense simultaneous path on a 2 500-station network of the same recipe (n = 7 500), its inverse + solve time
+      scaled by (30 000 / 7 500)^3, its assembly by the measurement count.
+    C3: the phased path (forward, reverse and combination passes) on the first blocks of the C3 network itself
+      (same width, same junction sizes), time per block x 100 blocks.
+    The full runs of C2 and C3 made once with tools/cpu_baselines.py are quoted beside the sample (`full_run`)."""
     from dynadjust_b200 import synth
     from oracle import pyoracle
     threads = threads or os.cpu_count() or 1
-    o = pyoracle.default_opts(threads=threads, max_iterations=1)
-    nets = [synth.gnss_network(block_stations, int(block_stations * baselines_per_station), 4242 + (s % 16))[:2]
-            for s in range(min(blocks, 16))]
-    pyoracle.adjust_simultaneous(nets[0][0].copy(), nets[0][1].copy(), opts=o)   # library / BLAS thread start-up
-    t_total = 0.0
-    for s in range(blocks):
-        stn, msr = nets[s % len(nets)]
-        stn, msr = stn.copy(), msr.copy()
-        t = time.perf_counter()
-        pyoracle.adjust_simultaneous(stn, msr, opts=o)
-        t_total += time.perf_counter() - t
-    total_blocks = total_stations / block_stations
     kind = "reference" if pyoracle.ref_loaded() else "port"
-    per_block = t_total / blocks
-    return dict(value=per_block * 1e3 * total_blocks, unit=UNIT, cores=threads if kind == "reference" else 1, kind=kind,
-                sample=(f"{blocks} blocks of {block_stations} stations ({3 * block_stations} unknowns, dnasegment's default block "
-                        f"size, same synthetic recipe) through the per-block dense path: {t_total:.1f} s of CPU work, "
-                        f"{per_block * 1e3:.2f} ms/block; extrapolated to {total_blocks:.0f} blocks, forward pass only "
-                        "(reverse/combine passes and junction carry not counted: lower bound)")), t_total
+    cores = threads if kind == "reference" else 1
+    cfg = synth.CONFIGS[WORKLOADS[key]["cfg"]]
+    full = cached_cpu_run(key)
+    if key == "C2":
+        n_s = 2500
+        stn, msr, _, _ = synth.gnss_network(n_s, 3 * n_s, 4242)
+        o = pyoracle.default_opts(threads=threads, max_iterations=1)
+        t = time.perf_counter()
+        r = pyoracle.adjust_simultaneous(stn, msr, opts=o)["res"]
+        wall = time.perf_counter() - t
+        scale3 = (cfg["n_stations"] / n_s) ** 3
+        value = 1e3 * (r.seconds_solve * scale3 + r.seconds_prepare * cfg["n_baselines"] / (3 * n_s))
+        sample = (f"dense simultaneous path on {n_s} stations (n = {3 * n_s}): {wall:.1f} s of CPU work, inverse + solve "
+                  f"{r.seconds_solve:.2f} s scaled by (30000/{3 * n_s})^3")
+    elif key == "C3":
+        nblocks = args.sample_blocks_c3
+        stn, msr, _, _ = synth.config_network("C3")
+        sub_stn, sub_msr = first_stations_subnetwork(stn, msr, 1000 * nblocks)
+        from tests import parity
+        o = pyoracle.default_opts(threads=threads, max_iterations=1)
+        t = time.perf_counter()
+        r = pyoracle.adjust_phased(sub_stn, sub_msr, parity.chain_blocks(len(sub_stn), 1000), opts=o)["res"]
+        wall = time.perf_counter() - t
+        value = 1e3 * r.seconds_solve / nblocks * (cfg["n_stations"] / 1000)
+        sample = (f"phased path (forward + reverse + combination, one iteration) on the first {nblocks} blocks of the C3 network: "
+                  f"{wall:.1f} s of CPU work, {r.seconds_solve / nblocks:.2f} s per block x {cfg['n_stations'] // 1000} blocks")
+    else:
+        blocks, block_stations = args.sample_blocks, 150
+        bps = cfg["n_baselines"] / cfg["n_stations"]
+        o = pyoracle.default_opts(threads=threads, max_iterations=1)
+        nets = [synth.gnss_network(block_stations, int(block_stations * bps), 4242 + (s % 16))[:2] for s in range(min(blocks, 16))]
+        pyoracle.adjust_simultaneous(nets[0][0].copy(), nets[0][1].copy(), opts=o)   # library / BLAS thread start-up
+        t_total = 0.0
+        for s in range(blocks):
+            stn, msr = nets[s % len(nets)]
+            stn, msr = stn.copy(), msr.copy()
+            t = time.perf_counter()
+            pyoracle.adjust_simultaneous(stn, msr, opts=o)
+            t_total += time.perf_counter() - t
+        total_blocks = cfg["n_stations"] / block_stations
+        value = t_total / blocks * 1e3 * total_blocks
+        sample = (f"{blocks} blocks of {block_stations} stations ({3 * block_stations} unknowns, dnasegment's default block size, same "
+                  f"synthetic recipe) through the per-block dense path: {t_total:.1f} s of CPU work, {t_total / blocks * 1e3:.2f} ms/block; "
+                  f"extrapolated to {total_blocks:.0f} blocks, forward pass only (reverse / combination passes and junction carry not "
+                  "counted: lower bound)")
+    base = dict(value=value, unit=UNIT, cores=cores, kind=kind, sample=sample)
+    if full:
+        base["full_run"] = dict(ms_per_iteration=full.get("ms_per_iteration"), cores=full.get("cores"), mode=full.get("mode"),
+                                iterations=full.get("iterations"), wall_s=full.get("wall_s"), host_cpu=full.get("cpu"),
+                                record=f"profiles/r2_cpu_baseline_{key.lower()}.json (tools/cpu_baselines.py, run once)")
+    return base
 
 
 def run_reference(args):
@@ -173,20 +271,20 @@ def run_reference(args):
     if rank != 0:
         return
     from dynadjust_b200 import synth
-    cfg = synth.CONFIGS[WORKLOADS[args.workload][0]]
-    for _ in range(min(args.warmup, 1)):
-        cpu_sample(cfg["n_stations"], cfg["n_baselines"] / cfg["n_stations"], blocks=20)
+    cfg = synth.CONFIGS[WORKLOADS[args.workload]["cfg"]]
     vals = []
-    for _ in range(args.steps):
-        base, _ = cpu_sample(cfg["n_stations"], cfg["n_baselines"] / cfg["n_stations"], blocks=args.sample_blocks)
-        vals.append(base["value"])
+    base = None
+    for i in range(min(args.warmup, 1) + args.steps):
+        base = cpu_sample(args.workload, args)
+        if i >= min(args.warmup, 1):
+            vals.append(base["value"])
     base["value"] = float(np.mean(vals))
     line = dict(metric=METRIC, value=base["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=base["value"], higher_is_better=False, scaling="strong", vs_baseline=None, dtype="f64",
                 data="synthetic", impl="reference",
                 config=dict(workload=workload_name(args.workload, cfg),
-                            note="the reference's per-block dense CPU path (oracle + compiled reference matrix_2d) on a bounded sample "
-                                 "of dnasegment-size blocks, extrapolated to the network; forward pass only"),
+                            note="the reference's CPU path (oracle + compiled reference matrix_2d) on a bounded sample of the workload, "
+                                 "scaled to it (see cpu_baseline.sample)"),
                 cpu_baseline=base,
                 e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
@@ -195,7 +293,7 @@ def run_reference(args):
 def run_engine(args):
     import torch
     import torch.distributed as dist
-    from dynadjust_b200 import engine, synth
+    from dynadjust_b200 import checks, engine, synth
     from dynadjust_b200.records import MSR_DTYPE
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,25 +305,39 @@ def run_engine(args):
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
 
-    cfg_name, eng_opts = WORKLOADS[args.workload]
-    cfg = synth.CONFIGS[cfg_name]
-    stn, msr, truth, _ = synth.config_network(cfg_name)
+    wl = WORKLOADS[args.workload]
+    eng_opts = dict(wl["opts"])
+    cfg = synth.CONFIGS[wl["cfg"]]
+    stn, msr, truth, _ = synth.config_network(wl["cfg"])
+    gnss_only = bool((msr["measType"] == b"G").all())
+    blocks = None
+    if wl.get("chain"):
+        from tests import parity
+        blocks = parity.chain_blocks(len(stn), wl["chain"])
+    if wl.get("dense") and world > 1:
+        raise SystemExit("C2 (one dense front) does not shard: run it on one GPU")
     # measurement records in pinned host memory (the e2e leg copies them H2D every step)
     pinned = torch.empty(msr.nbytes, dtype=torch.uint8, pin_memory=True)
     msr_p = pinned.numpy().view(MSR_DTYPE)
     msr_p[:] = msr
     del msr
 
-    if world > 1:
-        from dynadjust_b200 import multigpu
-        runner = multigpu.ShardedAdjustment(stn, msr_p, rank, world, multigpu.TorchExchange(torch.device("cuda", local_rank)),
-                                            device=local_rank, **eng_opts)
-    else:
-        runner = engine.Adjustment(stn, msr_p, device=local_rank, **eng_opts)
+    def make_runner(sharded):
+        if sharded:
+            from dynadjust_b200 import multigpu
+            r = multigpu.ShardedAdjustment(stn, msr_p, rank, world, multigpu.TorchExchange(torch.device("cuda", local_rank)),
+                                           device=local_rank, **eng_opts)
+        else:
+            r = engine.Adjustment(stn, msr_p, device=local_rank, **eng_opts)
+        if blocks is not None:
+            r.set_blocks(blocks)
+        return r
+
+    runner = make_runner(world > 1)
     t = time.time()
     info = runner.prepare()
     prepare_s = time.time() - t
-    peak_tf = fp64_peak_tflops()
+    peak_burst, peak_sustained = fp64_peak_tflops()
     peaks, peaks_kind = measured_peaks()
 
     def barrier():
@@ -238,7 +350,19 @@ def run_engine(args):
         runner.reset_estimates()
         return runner.iterate(normals=True, inverse=True)
 
-    for _ in range(args.warmup):
+    def reduce_max(x):
+        if world > 1:
+            tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        return x
+
+    t = time.perf_counter()
+    barrier()
+    step()
+    barrier()
+    first_iteration_ms = (time.perf_counter() - t) * 1e3     # cold: module load, first touch of every buffer
+    for _ in range(max(0, args.warmup - 1)):
         step()
     runner.profile_enable(True)
     runner.profile_read(reset=True)
@@ -257,81 +381,119 @@ def run_engine(args):
     prof = runner.profile_read(reset=True)
     runner.profile_enable(False)
     clocks = clk.summary()
-    ms_step = (t1 - t0) * 1e3 / args.steps
-    if world > 1:
-        tt = torch.tensor([ms_step], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_step = float(tt.item())
+    ms_step = reduce_max((t1 - t0) * 1e3 / args.steps)
+    device_ms = reduce_max(sum(phase.values()) / args.steps)       # CUDA events around the four phases, max over ranks
 
     # ---- end to end through the C-ABI with host buffers ------------------------------
     nstn = len(stn)
-    h2d = msr_p.nbytes
+    h2d = msr_p.nbytes // world if world > 1 else msr_p.nbytes      # every rank sends its share over its own PCIe link
     d2h = nstn * 24 + nstn * 72
+    rec = msr_p.reshape(-1, 3) if gnss_only else None
+    full_vcv = bool(wl.get("full_vcv")) and world == 1
+    if full_vcv:
+        d2h += len(rec) * 72
     barrier()
     t0 = time.perf_counter()
+    block_bytes = 0
     for _ in range(args.steps):
         runner.upload_measurements()
         step()
         est = runner.estimates()
         vcv = runner.station_vcvs()
+        if full_vcv:
+            # C5: every pattern block (one per baseline) and every block's dense variance matrix (v_rigorousVariances_, ADJ:3805)
+            pv = runner.pair_vcvs(rec["station1"][:, 0], rec["station2"][:, 0])
+            block_bytes = 0
+            for b in range(int(info.nfronts)):
+                bs, bv = runner.block_vcv(b)
+                block_bytes += bv.shape[0] * (bv.shape[0] + 1) // 2 * 8
     barrier()
     t1 = time.perf_counter()
-    e2e_ms = (t1 - t0) * 1e3 / args.steps
-    if world > 1:
-        tt = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item())
+    e2e_ms = reduce_max((t1 - t0) * 1e3 / args.steps)
+    d2h += block_bytes
 
     # sanity of what was timed: the step really solved the network
     rms = float(np.sqrt(((est - truth) ** 2).mean()))
     if not (rms < 0.05 and np.isfinite(vcv).all()):
         raise SystemExit(f"bench: adjusted coordinates are off (rms vs truth {rms})")
+    parity_rec = dict(rms_vs_truth_m=rms)
+    if gnss_only and rank == 0 and not args.no_checks:
+        # oracle-free identity on every station: sum_j N[s,j] Z[j,s] = I from the records and the returned variance blocks
+        res, worst = checks.normal_identity_residual(runner, stn, msr_p)
+        parity_rec.update(normal_identity_max=res, normal_identity_worst_station=worst,
+                          normal_identity_note="max over all stations of |sum_j N_sj Z_js - I| (dynadjust_b200/checks.py)")
+    if world > 1 and not args.no_checks:
+        # the same step on one GPU (rank 0's), compared with what the sharded run returned
+        barrier()
+        if rank == 0:
+            one = make_runner(False)
+            one.prepare()
+            one.reset_estimates()
+            one.iterate(normals=True, inverse=True)
+            e1, q1 = one.estimates(), one.station_vcvs()
+            one.close()
+            parity_rec["parity_vs_1gpu"] = dict(max_dx_m=float(np.abs(est - e1).max()),
+                                                max_rel_dvcv=float(np.abs(vcv - q1).max() / np.abs(q1).max()))
+        barrier()
 
-    if rank != 0:
-        return
-    alg_flops = info.factor_flops + info.inverse_flops            # whole network
-    rank_flops = info.rank_factor_flops + info.rank_inverse_flops   # this rank's fronts (== alg_flops on one GPU)
-    gemm_ms = prof.ms_gemm / args.steps
-    roofline = dict(bound="tensor", kernel="gemm_tile_kernel (TMA-fed DMMA, all panel/Schur/inverse products)",
-                    achieved=rank_flops / gemm_ms / 1e9 if gemm_ms > 0 else None, peak=peak_tf, unit="TFLOP/s",
-                    frac=(rank_flops / gemm_ms / 1e9 / peak_tf) if gemm_ms > 0 else None,
-                    traffic=ncu_traffic("gemm_tile_kernel") if (world == 1 and args.workload == "C4") else None,
-                    traffic_note="DRAM bytes per launch (avg over the iteration's launches) from profiles/r1_ncu_dram_traffic_c4.json",
-                    algorithmic_flops_per_launch=(rank_flops / (prof.gemm_launches / args.steps)) if prof.gemm_launches else None,
-                    peak_source="cuBLAS DGEMM 8192^3 best-of-5 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                    algorithmic_flops_per_step=alg_flops, rank0_algorithmic_flops_per_step=rank_flops,
-                    executed_gemm_flops_per_step=prof.flops_gemm / args.steps,
-                    kernel_ms_per_step=gemm_ms, kernel_share_of_step=gemm_ms / ms_step,
-                    launches_per_step=prof.gemm_launches / args.steps)
-    asm_ms = prof.ms_assemble / args.steps
-    roofline_asm = dict(bound="hbm", kernel="init_normals_kernel + assemble_g_kernel + station_sum_kernel (the assembly pass)", achieved=info.nbaselines * BYTES_PER_BASELINE / asm_ms / 1e6,
-                        peak=peaks["hbm_gbs"], unit="GB/s", peak_source=peaks_kind,
-                        frac=info.nbaselines * BYTES_PER_BASELINE / asm_ms / 1e6 / peaks["hbm_gbs"],
-                        bytes_per_baseline=BYTES_PER_BASELINE, kernel_ms_per_step=asm_ms,
-                        traffic=ncu_traffic("init_normals_kernel", "assemble_g_kernel", "station_sum_kernel") if args.workload == "C4" else None)
-    line = dict(metric=METRIC, value=ms_step, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms_step, higher_is_better=False, scaling="strong", vs_baseline=None, dtype="f64",
-                data="synthetic",
-                config=dict(workload=workload_name(args.workload, cfg),
-                            ordering=f"nested dissection, leaf {eng_opts.get('leaf_stations')} stations",
-                            fronts=int(info.nfronts), levels=int(info.nlevels), l2_note="inputs larger than L2",
-                            sharding=(f"{world} ranks, subtrees of the dissection tree; {info.top_fronts} shared top fronts "
-                                      f"replicated, their tiles shared out among the ranks; all-reduce / multicast stores / barriers in "
-                                      f"our kernels over NVLink peer mappings (cut at level {info.cut_level})") if world > 1 else "none",
-                            panel_gb=info.panel_bytes / 1e9, prepare_s=prepare_s),
-                e2e=dict(value=e2e_ms, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
-                gpu_launches=int(prof.launches), clocks=clocks, roofline=roofline, roofline_assembly=roofline_asm,
-                phase_ms_per_step={k: v / args.steps for k, v in phase.items()},
-                kernel_ms_per_step=dict(gemm=prof.ms_gemm / args.steps, diag=prof.ms_diag / args.steps,
-                                        tri=prof.ms_tri / args.steps, gemv=prof.ms_gemv / args.steps,
-                                        transpose=prof.ms_transpose / args.steps, gather=prof.ms_gather / args.steps,
-                                        memset=prof.ms_zero / args.steps, assemble=prof.ms_assemble / args.steps,
-                                        other=prof.ms_other / args.steps),
-                gflops=alg_flops / ms_step / 1e6, rms_vs_truth_m=rms)
-    if world == 1 and not args.no_cpu_baseline:
-        base, _ = cpu_sample(cfg["n_stations"], cfg["n_baselines"] / cfg["n_stations"], blocks=args.sample_blocks)
-        line["cpu_baseline"] = base
-    print(json.dumps(line))
+    if rank == 0:
+        alg_flops = info.factor_flops + info.inverse_flops            # whole network (SURVEY 8d count, from the symbolic factorisation)
+        rank_flops = info.rank_factor_flops + info.rank_inverse_flops   # this rank's share (== alg_flops on one GPU)
+        gemm_ms = prof.ms_gemm / args.steps
+        executed = prof.flops_gemm / args.steps                        # useful flops of the GEMM launches actually run (planner's count)
+        tr, tr_file = ncu_traffic("gemm_tile_kernel") if (world == 1 and args.workload == "C4") else (None, None)
+        roofline = dict(bound="tensor", kernel="gemm_tile_kernel (TMA-fed DMMA, all panel/Schur/inverse products)",
+                        achieved=executed / gemm_ms / 1e9 if gemm_ms > 0 else None, peak=peak_sustained, unit="TFLOP/s",
+                        frac=(executed / gemm_ms / 1e9 / peak_sustained) if gemm_ms > 0 else None,
+                        traffic=tr, traffic_note=f"DRAM bytes per launch (avg over the iteration's launches) from profiles/{tr_file}" if tr_file else None,
+                        flops_note="achieved = executed useful GEMM flops of this rank (the planner's per-launch count: 2MNK, halved for "
+                                   "triangular outputs / operands) / summed GEMM-kernel time (CUDA events around every launch)",
+                        peak_source="cuBLAS DGEMM 8192^3 sustained (back to back ~2 s) measured in this run; MEASURED_PEAKS.json has no FP64 entry",
+                        peak_burst=peak_burst, executed_gemm_flops_per_step=executed,
+                        algorithmic_flops_per_step=alg_flops, rank0_algorithmic_flops_per_step=rank_flops,
+                        whole_step_frac=alg_flops / world / (ms_step * 1e9) / peak_sustained,
+                        kernel_ms_per_step=gemm_ms, kernel_share_of_step=gemm_ms / ms_step,
+                        launches_per_step=prof.gemm_launches / args.steps)
+        if wl.get("dense"):
+            n3 = float(3 * nstn) ** 3
+            roofline.update(dense_n3_flops=n3, dense_n3_tflops=n3 / (ms_step * 1e9), dense_n3_frac=n3 / (ms_step * 1e9) / peak_sustained)
+        asm_ms = prof.ms_assemble / args.steps
+        ta, _ = ncu_traffic("init_normals_kernel", "assemble_g_kernel", "station_sum_kernel") if args.workload == "C4" else (None, None)
+        roofline_asm = dict(bound="hbm", kernel="init_normals_kernel + assemble_g_kernel + station_sum_kernel (the assembly pass)",
+                            achieved=info.nbaselines * BYTES_PER_BASELINE / asm_ms / 1e6, peak=peaks["hbm_gbs"], unit="GB/s",
+                            peak_source=peaks_kind, frac=info.nbaselines * BYTES_PER_BASELINE / asm_ms / 1e6 / peaks["hbm_gbs"],
+                            bytes_per_baseline=BYTES_PER_BASELINE, kernel_ms_per_step=asm_ms, traffic=ta)
+        ordering = ("one dense front" if wl.get("dense") else f"chain of {wl['chain']}-station blocks (phased)" if wl.get("chain")
+                    else f"nested dissection, leaf {eng_opts.get('leaf_stations')} stations")
+        line = dict(metric=METRIC, value=ms_step, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_step, higher_is_better=False, scaling="strong", vs_baseline=None, dtype="f64",
+                    data="synthetic",
+                    config=dict(workload=workload_name(args.workload, cfg), ordering=ordering,
+                                fronts=int(info.nfronts), levels=int(info.nlevels), l2_note="inputs larger than L2",
+                                sharding=(f"{world} ranks, subtrees of the dissection tree; {info.top_fronts} top fronts replicated, their "
+                                          f"tiles shared out among the ranks; all-reduce, stores into the peers' replicas and barriers in our "
+                                          f"own kernels over NVLink peer mappings (cut at level {info.cut_level})") if world > 1 else "none",
+                                panel_gb=info.panel_bytes / 1e9, prepare_s=prepare_s),
+                    e2e=dict(value=e2e_ms, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
+                    e2e_first_iteration_ms=prepare_s * 1e3 + first_iteration_ms,
+                    device_ms_per_step=device_ms,
+                    gpu_launches=int(prof.launches), clocks=clocks, roofline=roofline, roofline_assembly=roofline_asm,
+                    phase_ms_per_step={k: v / args.steps for k, v in phase.items()},
+                    kernel_ms_per_step=dict(gemm=prof.ms_gemm / args.steps, diag=prof.ms_diag / args.steps,
+                                            tri=prof.ms_tri / args.steps, gemv=prof.ms_gemv / args.steps,
+                                            transpose=prof.ms_transpose / args.steps, gather=prof.ms_gather / args.steps,
+                                            memset=prof.ms_zero / args.steps, assemble=prof.ms_assemble / args.steps,
+                                            other=prof.ms_other / args.steps),
+                    gflops=alg_flops / ms_step / 1e6, parity=parity_rec, rms_vs_truth_m=rms)
+        if world > 1:
+            line["nvlink"] = dict(bytes_read_per_step=info.nvlink_read_bytes, bytes_written_per_step=info.nvlink_write_bytes,
+                                  barriers_per_step=int(info.barriers_per_step),
+                                  note="rank 0: all-reduce slices read from / written to the peers' replicas + finished tiles stored into the "
+                                       "peers' replicas, per iteration (factor + solve + inverse), from the launch plan")
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_sample(args.workload, args)
+        print(json.dumps(line))
+    barrier()
     runner.close()
     if world > 1:
         dist.destroy_process_group()
@@ -345,8 +507,10 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
     ap.add_argument("--sample-blocks", type=int, default=2000,
-                    help="150-station blocks per reference step (bounded CPU sample)")
+                    help="150-station blocks per reference step (bounded CPU sample, C4 / C5)")
+    ap.add_argument("--sample-blocks-c3", type=int, default=3, help="blocks of the C3 chain in the bounded phased CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-checks", action="store_true", help="skip the identity / one-GPU parity checks after the timed region")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -1448,6 +1448,9 @@ int gadj_get_info(const gadj_ctx* c, gadj_info* info)
     info->rank_inverse_flops = c->sym.world > 1 ? c->sym.my_inverse_flops : c->sym.inverse_flops;
     info->cut_level = c->sym.world > 1 ? c->sym.cut_level : -1;
     info->top_fronts = 0;
+    info->nvlink_read_bytes = c->plan.nvlink_read_bytes;
+    info->nvlink_write_bytes = c->plan.nvlink_write_bytes;
+    info->barriers_per_step = c->plan.barriers;
     for (const Front& f : c->sym.fronts)
         info->top_fronts += f.top;
     info->launches_factor = c->plan.factor.size();

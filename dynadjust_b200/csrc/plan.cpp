@@ -115,6 +115,7 @@ struct Builder {
         L.kind = L_BARRIER;
         L.level = level;
         out.push_back(L);
+        p.barriers++;
     }
     // barrier; sum over the ranks of the given ranges of a replicated buffer; barrier
     void add_allreduce(std::vector<Launch>& out, int level, int buf, const std::vector<ReduceOp>& ranges)
@@ -129,6 +130,10 @@ struct Builder {
         L.op_begin = (int64_t)p.reduce.size();
         L.op_count = (int32_t)ranges.size();
         p.reduce.insert(p.reduce.end(), ranges.begin(), ranges.end());
+        for (const ReduceOp& r : ranges) {   // this rank's slice: read from and stored into world - 1 peers
+            p.nvlink_read_bytes += 8.0 * (double)r.count * (s.world - 1) / s.world;
+            p.nvlink_write_bytes += 8.0 * (double)r.count * (s.world - 1) / s.world;
+        }
         out.push_back(L);
         add_barrier(out, level);
     }
@@ -191,8 +196,13 @@ struct Builder {
                     ++my_tiles;
                     p.tiles.push_back(GemmTile{opi, (uint16_t)tm, (uint16_t)tn});
                 }
-            if (op.flags & GEMM_MCAST)
+            if (op.flags & GEMM_MCAST) {
                 L.mcast = 1;
+                if (all_tiles) {
+                    double bytes = 8.0 * (double)op.M * op.N * ((op.flags & GEMM_LOWER) ? 0.5 : 1.0) * ((op.flags & GEMM_DUAL) ? 2.0 : 1.0);
+                    p.nvlink_write_bytes += bytes * (double)my_tiles / (double)all_tiles * (s.world - 1);
+                }
+            }
             ++opi;
             // useful flops: lower-only outputs drop the strict upper triangle of the leading square;
             // triangular operands halve the K range over that square
@@ -231,6 +241,8 @@ struct Builder {
         L.level = level;
         for (auto& op : batch) {
             L.flops += (double)op.w * op.w * op.w * (op.factor ? 2.0 / 3.0 : 1.0 / 3.0);
+            if (op.mc)
+                p.nvlink_write_bytes += 8.0 * 2.5 * (double)op.w * op.w * (s.world - 1);
             p.diag.push_back(op);
         }
         out.push_back(L);
@@ -739,6 +751,8 @@ std::string build_plan(const Symbolic& s, const PlanBuffers& b, Plan& p)
     p.bwd.clear();
     p.selinv.clear();
     p.factor_flops = p.selinv_flops = 0;
+    p.nvlink_read_bytes = p.nvlink_write_bytes = 0;
+    p.barriers = 0;
     if (b.pool_doubles < min_pool_doubles(s))
         return "workspace pool smaller than the largest front";
     // scatter tables of the Schur updates

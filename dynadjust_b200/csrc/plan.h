@@ -69,6 +69,9 @@ struct Plan {
     std::vector<int32_t> rowidx;            // host copy (uploaded by the caller before build_plan's pointers are used)
     std::vector<uint64_t> rowidx_off;       // per front
     double factor_flops = 0, selinv_flops = 0;
+    // multi-GPU, per iteration of this rank: bytes read from / stored into the peers' replicas, barriers
+    double nvlink_read_bytes = 0, nvlink_write_bytes = 0;
+    uint64_t barriers = 0;
     // device copies of the op arrays (owned by the context)
     GemmOp* d_gemm = nullptr;
     DiagOp* d_diag = nullptr;

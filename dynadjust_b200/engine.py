@@ -47,7 +47,8 @@ class GadjInfo(C.Structure):
                 ("inverse_flops", C.c_double), ("launches_factor", C.c_uint64), ("launches_solve", C.c_uint64),
                 ("launches_inverse", C.c_uint64), ("max_front_rows", C.c_uint32), ("max_front_cols", C.c_uint32),
                 ("rank_factor_flops", C.c_double), ("rank_inverse_flops", C.c_double), ("cut_level", C.c_int32),
-                ("top_fronts", C.c_uint32)]
+                ("top_fronts", C.c_uint32), ("nvlink_read_bytes", C.c_double), ("nvlink_write_bytes", C.c_double),
+                ("barriers_per_step", C.c_uint64)]
 
 
 class GadjProfile(C.Structure):

@@ -103,6 +103,10 @@ typedef struct gadj_info {
     double rank_factor_flops, rank_inverse_flops;   /* the share of this rank (multi-GPU sharding) */
     int32_t cut_level;                               /* first tree level holding a shared ("top") front; -1 single GPU */
     uint32_t top_fronts;
+    /* multi-GPU, per full iteration (factor + solve + inverse) of this rank, from the launch plan: bytes read from and
+     * stored into the other ranks' replicas over NVLink, and the device-side barriers */
+    double nvlink_read_bytes, nvlink_write_bytes;
+    uint64_t barriers_per_step;
 } gadj_info;
 
 /* per-kernel-family device time (CUDA events around every launch) accumulated since the last reset */
