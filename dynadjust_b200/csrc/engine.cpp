@@ -7,6 +7,7 @@
 // GenerateStatistics (ADJ:258, ADJ:2413-2511, ADJ:6586-6667, ADJ:6802-6841).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -213,6 +214,8 @@ struct gadj_ctx {
     uint64_t barrier_round = 0;
     std::vector<std::pair<void*, int64_t>> peer_maps;   // mapped peer buffers (pointer, owning process) to unmap on destroy
     DevArray<ReduceOp> d_reduce, d_reduce_misc;
+    DevArray<PushOp> d_push;
+    DevArray<double*> d_bases;          // this rank's replicated buffers by McBuf index
     DevArray<double> d_apply;
     DevArray<uint8_t> d_pos_owned;
     uint32_t iteration = 0;
@@ -304,10 +307,10 @@ void run_one(gadj_ctx* c, const Launch& L)
             c->launch_count--;  // a memset, not one of our kernels
         switch (L.kind) {
         case L_GEMM:
-            launch_gemm(c->d_gemm.p + L.op_begin, L.op_count, c->d_tiles.p + L.tile_begin, L.total_tiles, c->pt(), L.mcast != 0, st);
+            launch_gemm(c->d_gemm.p + L.op_begin, L.op_count, c->d_tiles.p + L.tile_begin, L.total_tiles, st);
             break;
         case L_DIAG:
-            launch_diag(c->d_diag.p + L.op_begin, L.op_count, c->d_info.p, c->pt(), st);
+            launch_diag(c->d_diag.p + L.op_begin, L.op_count, c->d_info.p, st);
             break;
         case L_TRI_FWD:
         case L_TRI_BWD:
@@ -331,6 +334,9 @@ void run_one(gadj_ctx* c, const Launch& L)
                 launch_allreduce(c->d_reduce.p + L.op_begin, L.op_count, c->pt(), base, L.buf, st);
             break;
         }
+        case L_PUSH:
+            launch_push(c->d_push.p + L.op_begin, L.op_count, L.total_tiles, c->pt(), c->d_bases.p, st);
+            break;
         case L_ZERO:
             dev::zero(L.zero_ptr, L.zero_bytes);
             break;
@@ -1084,6 +1090,16 @@ int gadj_set_blocks(gadj_ctx* c, uint32_t nblocks, const uint32_t* isl_off, cons
 int gadj_prepare(gadj_ctx* c)
 {
     dev::use(c->device);
+    // GADJ_DEBUG: wall time of the host phases
+    const bool timing = getenv("GADJ_DEBUG") != nullptr;
+    auto tick = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing)
+            return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "gadj_prepare[%d]: %-28s %8.1f ms\n", c->mg_rank, what, std::chrono::duration<double, std::milli>(now - tick).count());
+        tick = now;
+    };
     c->prepared = false;
     c->factor_valid = c->inverse_valid = c->normals_valid = false;
     c->iteration = 0;
@@ -1104,9 +1120,11 @@ int gadj_prepare(gadj_ctx* c)
     std::vector<double> est(3 * (size_t)c->nstn);
     for (uint32_t s = 0; s < c->nstn; ++s)
         geo_to_cart(c->ell, c->stn[s].currentLatitude, c->stn[s].currentLongitude, c->stn[s].currentHeight, &est[3 * s]);
+    lap("scan + a-priori coordinates");
     first_run_reduction(c);
     if (first_run_reduction_rows(c, est.data()))
         return 1;
+    lap("first-run reductions");
 
     // unique station pairs -> edge slots: baselines, the station pairs of every independent row, every pair of a cluster
     const uint64_t nb = c->nbsl;
@@ -1172,6 +1190,7 @@ int gadj_prepare(gadj_ctx* c)
         for (int k = 0; k < 3; ++k)
             c->constrained_components += c->stn[s].stationConst[k] == 'C';
     }
+    lap("station pairs");
     OrderingOptions oo;
     oo.leaf_stations = c->o.leaf_stations;
     oo.dense = c->o.ordering == GADJ_ORDER_DENSE;
@@ -1183,6 +1202,7 @@ int gadj_prepare(gadj_ctx* c)
         return c->fail(e);
     if (c->mg_world > 1)
         finalize_layout(c->sym, c->mg_world, c->mg_rank);
+    lap("ordering + symbolic");
     const Symbolic& S = c->sym;
     if (const char* fp = getenv("GADJ_DUMP_FRONTS")) {   // ordering studies: level, own unknowns, boundary unknowns, flops
         if (FILE* f = fopen(fp, "w")) {
@@ -1287,6 +1307,7 @@ int gadj_prepare(gadj_ctx* c)
             return c->fail("station constraint variance matrix is not positive definite");
     }
 
+    lap("edge words, incidence lists");
     // ---- device memory ---------------------------------------------------------
     build_rowidx(S, c->plan);
     std::vector<double> z;
@@ -1367,6 +1388,7 @@ int gadj_prepare(gadj_ctx* c)
         c->cvmat.shrink_to_fit();
     }
 
+    lap("device arrays + upload");
     size_t want = ideal_pool_doubles(S), least = min_pool_doubles(S);
     size_t budget;
     if (c->o.workspace_gb > 0)
@@ -1391,6 +1413,7 @@ int gadj_prepare(gadj_ctx* c)
     e = build_plan(S, pb, c->plan);
     if (!e.empty())
         return c->fail(e);
+    lap("launch plan");
     ok = true;
     ok &= c->d_gemm.upload(c->plan.gemm);
     ok &= c->d_tiles.upload(c->plan.tiles);
@@ -1405,6 +1428,17 @@ int gadj_prepare(gadj_ctx* c)
     ok &= c->d_tr.upload(c->plan.transpose);
     ok &= c->d_gather.upload(c->plan.gather);
     ok &= c->d_reduce.upload(c->plan.reduce);
+    ok &= c->d_push.upload(c->plan.push);
+    {
+        std::vector<double*> bases(MC_BUFS, nullptr);
+        bases[MC_PANELS] = c->d_panels.p;
+        bases[MC_WBUF] = c->d_wbuf.p;
+        bases[MC_POOL] = c->d_pool.p;
+        bases[MC_X] = c->d_x.p;
+        bases[MC_VCVD] = c->d_vcvd.p;
+        bases[MC_VCVO] = c->d_vcvo.p;
+        ok &= c->d_bases.upload(bases);
+    }
     {
         // whole-vector reductions of a multi-GPU run: the solution vector, the station / pair variance blocks
         std::vector<ReduceOp> misc = {ReduceOp{0, 3 * (uint64_t)c->nstn}, ReduceOp{0, 9 * (uint64_t)c->nstn},
@@ -1424,6 +1458,7 @@ int gadj_prepare(gadj_ctx* c)
     c->device_bytes = c->d_msr.bytes() + c->d_panels.bytes() + c->d_pool.bytes() + c->d_wbuf.bytes() + c->d_noff.bytes() + c->d_ndiag.bytes() +
                       c->d_gemm.bytes() + c->d_gemv.bytes() + c->d_vcvo.bytes() + c->d_vcvd.bytes();
     c->h_corr.assign(3 * (size_t)c->nstn, 0.0);
+    lap("plan upload");
     c->prepared = true;
     return 0;
 }
@@ -2614,7 +2649,7 @@ int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int
     if (!dev::encode_tma_2d(&op.tmA, op.A, M, K, ldk, TILE_M) || !dev::encode_tma_2d(&op.tmB, op.B, N, K, ldk, TILE_N))
         return c->fail("tensor-map encoding failed");
     dev::h2d(dop.p, &op, sizeof(op));
-    launch_gemm(dop.p, 1, dtl.p, (int)tl.size(), nullptr, false, dev::stream());
+    launch_gemm(dop.p, 1, dtl.p, (int)tl.size(), dev::stream());
     std::string e = dev::sync();
     if (!e.empty())
         return c->fail(e);
@@ -2622,7 +2657,7 @@ int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int
         reps = 1;
     dev::event_record(c->ev[0]);
     for (int i = 0; i < reps; ++i)
-        launch_gemm(dop.p, 1, dtl.p, (int)tl.size(), nullptr, false, dev::stream());
+        launch_gemm(dop.p, 1, dtl.p, (int)tl.size(), dev::stream());
     dev::event_record(c->ev[1]);
     std::vector<double> hc((size_t)M * ldc);
     dev::d2h(hc.data(), dC.p, dC.bytes());

@@ -27,8 +27,9 @@ struct alignas(64) TmaDesc {
 
 // ---- multi-GPU: replicated buffers and the peer table ---------------------------------------------------------
 // The fronts above the subtree cut ("top" fronts) are stored by every rank at identical offsets of its panel,
-// pivot-inverse and workspace buffers.  A rank that finishes a tile of such a front stores it into every replica
-// through NVLink peer mappings (GEMM_MCAST / DiagOp::mc): byte address in rank p's copy = local address + delta[buf][p].
+// pivot-inverse and workspace buffers.  A rank that finishes a piece of such a front (a factorised panel, tiles of the
+// inverse) pushes it into every replica through NVLink peer mappings (launch_push): byte address in rank p's copy =
+// local address + delta[buf][p].
 constexpr int MAX_RANKS = 8;
 enum McBuf : int32_t { MC_NONE = 0, MC_PANELS = 1, MC_WBUF = 2, MC_POOL = 3, MC_X = 4, MC_VCVD = 5, MC_VCVO = 6, MC_MSR = 7, MC_BUFS = 8 };
 struct PeerTable {
@@ -36,6 +37,15 @@ struct PeerTable {
     int64_t delta[MC_BUFS][MAX_RANKS];             // delta[b][rank] == 0
     unsigned long long* counter[MAX_RANKS];        // every rank's barrier counter, as mapped into this rank
     int32_t* info[MAX_RANKS];                      // every rank's info words: [0] first front with a non-positive pivot + 1, [1] barrier time-out
+};
+
+// a rows x cols block (row pitch ld, doubles) at offset `off` of replicated buffer `buf`, copied into every peer's replica
+struct PushOp {
+    uint64_t off;
+    int64_t ld;
+    int32_t rows, cols;
+    int32_t buf;
+    int32_t pad;
 };
 
 // sum of `count` doubles at offset `off` of a replicated buffer over all ranks, result stored into every replica
@@ -52,7 +62,6 @@ enum GemmFlags : int32_t {
     GEMM_KLO_MAX = 32,  // A and B upper triangular: start the K loop at max(first row, first column) of the tile
     GEMM_KHI_ROW = 64,  // A is lower triangular (zero for k > row): end the K loop after the tile's last row
     GEMM_DUAL = 128,    // also store the transpose: Ct[j][i] = C[i][j] (row-major, pitch ldct); not with ACCUM / LOWER / SCATTER
-    GEMM_MCAST = 256,   // the result (and its DUAL transpose) is stored into every rank's replica (GemmOp::mc names the buffers)
     GEMM_SCATTER = 8,   // Schur update of a front, scattered into its ancestors' panels: column j belongs to boundary
                         // station j/3, whose owning ancestor is target t = coltgt[j/3]; element (i, j) is added
                         // atomically to tgt[t].C at row 3*tgt[t].rowmap[i/3 - tgt[t].jb] + i%3 and column
@@ -82,7 +91,7 @@ struct alignas(64) GemmOp {
     int32_t M, N, K;
     int32_t flags;
     int32_t tri_off;
-    int32_t mc;              // GEMM_MCAST: McBuf of C in bits 0..7, McBuf of Ct in bits 8..15
+    int32_t pad0;
     int32_t tiles_m, tiles_n;
 };
 
@@ -105,7 +114,7 @@ struct DiagOp {
     int32_t w;
     int32_t factor;
     int32_t front;           // for error reporting
-    int32_t mc;              // 1: D (panels), W and Wt (pivot-inverse buffer) are stored into every rank's replica
+    int32_t pad;
 };
 
 // y[row0 + i] = sum_c A[i][c] * x[c]  for one chunk of rows of a k x k triangular matrix (W = L11^-1 in the forward
@@ -158,9 +167,11 @@ enum FirstUseKey : int { KEY_GEMM = 1, KEY_DIAG = 2, KEY_ASSEMBLE = 3 };
 
 // ---- launches -----------------------------------------------------------------
 // All pointers are device pointers; `stream` is the backend's stream handle.
-// pt: the rank's peer table (device copy); only read by launches whose ops carry GEMM_MCAST / DiagOp::mc
-void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, const PeerTable* pt, bool mcast, void* stream);
-void launch_diag(const DiagOp* ops, int nops, int* info, const PeerTable* pt, void* stream);
+void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, void* stream);
+void launch_diag(const DiagOp* ops, int nops, int* info, void* stream);
+// multi-GPU: blocks of the replicated buffers copied into every peer's replica (bases[buf] = this rank's buffer);
+// grid_x CTAs per op
+void launch_push(const PushOp* ops, int nops, int grid_x, const PeerTable* pt, double* const* bases, void* stream);
 // all ranks meet: every store issued before the barrier by any rank is visible to every rank after it.  `target` =
 // (number of barriers so far on this context) * nranks.  A rank that waits longer than ~20 s sets info[1] and gives up.
 void launch_barrier(const PeerTable* pt, unsigned long long target, int* info, void* stream);

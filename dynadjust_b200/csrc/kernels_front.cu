@@ -57,8 +57,7 @@ __device__ __forceinline__ void tile_mm(const double* __restrict__ S, int prow, 
 }
 
 template <int CTAS_PER_SM>
-__global__ void __launch_bounds__(DIAG_THREADS, CTAS_PER_SM)
-    diag_kernel(const DiagOp* __restrict__ ops, int* __restrict__ info, const PeerTable* __restrict__ pt)
+__global__ void __launch_bounds__(DIAG_THREADS, CTAS_PER_SM) diag_kernel(const DiagOp* __restrict__ ops, int* __restrict__ info)
 {
     extern __shared__ double S[];
     __shared__ double colbuf[PBW];
@@ -153,17 +152,10 @@ __global__ void __launch_bounds__(DIAG_THREADS, CTAS_PER_SM)
             }
             __syncthreads();
         }
-        // multi-GPU: the pivot tile of a replicated (top) front is factorised by one rank and stored into every replica
-        const int peers = op.mc ? pt->nranks : 0;
         for (int idx = tid; idx < w * w; idx += DIAG_THREADS) {
             const int i = idx / w, j = idx - i * w;
-            if (j <= i) {
-                const double v = S[tri(i, j)];
-                op.D[i * ld + j] = v;
-                for (int q = 0; q < peers; ++q)
-                    if (q != pt->rank)
-                        *reinterpret_cast<double*>(reinterpret_cast<char*>(op.D + i * ld + j) + pt->delta[MC_PANELS][q]) = v;
-            }
+            if (j <= i)
+                op.D[i * ld + j] = S[tri(i, j)];
         }
     }
     if (op.W == nullptr && op.Wt == nullptr)
@@ -227,22 +219,53 @@ __global__ void __launch_bounds__(DIAG_THREADS, CTAS_PER_SM)
         }
         __syncthreads();
     }
-    const int peers = op.mc ? pt->nranks : 0;
     for (int idx = tid; idx < w * w; idx += DIAG_THREADS) {
         const int i = idx / w, j = idx - i * w;
-        const double vw = (j <= i) ? S[tri(i, j)] : 0.0;     // W[i][j] (row-major, lower)
-        const double vt = (j >= i) ? S[tri(j, i)] : 0.0;     // Wt[i][j] = W[j][i] (upper)
         if (op.W)
-            op.W[i * op.ldw + j] = vw;
+            op.W[i * op.ldw + j] = (j <= i) ? S[tri(i, j)] : 0.0;     // W[i][j] (row-major, lower)
         if (op.Wt)
-            op.Wt[i * op.ldwt + j] = vt;
-        for (int q = 0; q < peers; ++q)
-            if (q != pt->rank) {
-                if (op.W)
-                    *reinterpret_cast<double*>(reinterpret_cast<char*>(op.W + i * op.ldw + j) + pt->delta[MC_WBUF][q]) = vw;
-                if (op.Wt)
-                    *reinterpret_cast<double*>(reinterpret_cast<char*>(op.Wt + i * op.ldwt + j) + pt->delta[MC_WBUF][q]) = vt;
+            op.Wt[i * op.ldwt + j] = (j >= i) ? S[tri(j, i)] : 0.0;   // Wt[i][j] = W[j][i] (upper)
+    }
+}
+
+// ---- multi-GPU: finished regions of a replicated front pushed into every peer's replica ----------------------
+// One op = a rows x cols block of a replicated buffer (a tile a rank has just computed, or a whole panel its owner has
+// just factorised); a warp moves one row at a time with 16-byte accesses, so the NVLink traffic is whole lines.
+// (Storing the tiles into the peers straight from the GEMM epilogue was tried first: the scattered 16-byte remote stores
+// of 288 threads stalled the tensor pipe — 237 ms per C4 iteration on 8 GPUs against 204 ms for the host-driven NCCL
+// exchange of round 1, profiles/r2_bench_8gpu_c4_first.json.)
+__global__ void __launch_bounds__(256) push_kernel(const PushOp* __restrict__ ops, const PeerTable* __restrict__ pt, double* const* __restrict__ bases)
+{
+    const PushOp op = ops[blockIdx.y];
+    const int n = pt->nranks, me = pt->rank;
+    const int64_t* d = pt->delta[op.buf];
+    double* base = bases[op.buf] + op.off;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool vec = ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((op.ld & 1) == 0);
+    for (int r = blockIdx.x * 8 + warp; r < op.rows; r += gridDim.x * 8) {
+        double* row = base + (int64_t)r * op.ld;
+        if (vec) {
+            const int pairs = op.cols >> 1;
+            for (int i = lane; i < pairs; i += 32) {
+                const double2 v = reinterpret_cast<const double2*>(row)[i];
+                for (int q = 0; q < n; ++q)
+                    if (q != me)
+                        reinterpret_cast<double2*>(reinterpret_cast<char*>(row) + d[q])[i] = v;
             }
+            if ((op.cols & 1) && lane == 0) {
+                const double v = row[op.cols - 1];
+                for (int q = 0; q < n; ++q)
+                    if (q != me)
+                        *reinterpret_cast<double*>(reinterpret_cast<char*>(row + op.cols - 1) + d[q]) = v;
+            }
+        } else {
+            for (int i = lane; i < op.cols; i += 32) {
+                const double v = row[i];
+                for (int q = 0; q < n; ++q)
+                    if (q != me)
+                        *reinterpret_cast<double*>(reinterpret_cast<char*>(row + i) + d[q]) = v;
+            }
+        }
     }
 }
 
@@ -492,7 +515,7 @@ constexpr int TILE_SMEM = TRI_DOUBLES * 8;
 
 }  // namespace
 
-void launch_diag(const DiagOp* ops, int nops, int* info, const PeerTable* pt, void* stream)
+void launch_diag(const DiagOp* ops, int nops, int* info, void* stream)
 {
     if (nops <= 0)
         return;
@@ -505,9 +528,9 @@ void launch_diag(const DiagOp* ops, int nops, int* info, const PeerTable* pt, vo
         cudaFuncSetAttribute(diag_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM);
     }
     if (ctas == 3)
-        diag_kernel<3><<<nops, DIAG_THREADS, TILE_SMEM, (cudaStream_t)stream>>>(ops, info, pt);
+        diag_kernel<3><<<nops, DIAG_THREADS, TILE_SMEM, (cudaStream_t)stream>>>(ops, info);
     else
-        diag_kernel<2><<<nops, DIAG_THREADS, TILE_SMEM, (cudaStream_t)stream>>>(ops, info, pt);
+        diag_kernel<2><<<nops, DIAG_THREADS, TILE_SMEM, (cudaStream_t)stream>>>(ops, info);
 }
 
 void launch_barrier(const PeerTable* pt, unsigned long long target, int* info, void* stream)
@@ -520,6 +543,14 @@ void launch_allreduce(const ReduceOp* ops, int nops, const PeerTable* pt, double
     if (nops <= 0)
         return;
     allreduce_kernel<<<dim3(148 * 2, nops), 256, 0, (cudaStream_t)stream>>>(ops, pt, base, buf);
+}
+
+void launch_push(const PushOp* ops, int nops, int grid_x, const PeerTable* pt, double* const* bases, void* stream)
+{
+    for (int o = 0; o < nops; o += 65535) {
+        const int n = nops - o < 65535 ? nops - o : 65535;
+        push_kernel<<<dim3(grid_x < 1 ? 1 : (grid_x > 64 ? 64 : grid_x), n), 256, 0, (cudaStream_t)stream>>>(ops + o, pt, bases);
+    }
 }
 
 void launch_share_info(const PeerTable* pt, int* info, void* stream)

@@ -104,12 +104,9 @@ __device__ __forceinline__ void tile_k_range(int flags, int row0, int col0, int 
 // LOADER 0: TMA producer warp + mbarrier ring (the product path).
 // LOADER 1: debug aid (GADJ_GEMM_LOADER=ldg) — the consumers fill one stage themselves with plain loads
 //           into the same swizzled layout; isolates tensor-map problems from fragment-layout problems.
-// MC 1: launches of the replicated top fronts of a multi-GPU run — ops flagged GEMM_MCAST store their result tiles into
-//       every rank's replica through the peer table (plain stores over NVLink; a barrier launch follows).
-template <int LOADER, int MC>
+template <int LOADER>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-    gemm_tile_kernel(const GemmOp* __restrict__ ops, const GemmTile* __restrict__ tiles, int ntiles,
-                     const PeerTable* __restrict__ pt)
+    gemm_tile_kernel(const GemmOp* __restrict__ ops, const GemmTile* __restrict__ tiles, int ntiles)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -318,16 +315,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
     } else {
         const bool accum = (flags & GEMM_ACCUM) != 0;
-        // multicast (MC): byte offsets from this rank's buffers to every replica; peers == 0 for ordinary ops
-        int peers = 0, me = 0;
-        const int64_t* dC = nullptr;
-        const int64_t* dT = nullptr;
-        if (MC && (flags & GEMM_MCAST)) {
-            peers = pt->nranks;
-            me = pt->rank;
-            dC = pt->delta[op->mc & 0xff];
-            dT = pt->delta[(op->mc >> 8) & 0xff];
-        }
         // fragments j = 2p and 2p+1 interleave: together a thread owns 4 consecutive columns
         // c0 .. c0+3 = {acc[i][2p][0], acc[i][2p+1][0], acc[i][2p][1], acc[i][2p+1][1]} -> two 16-byte accesses
 #pragma unroll
@@ -347,13 +334,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     double* __restrict__ ct = op->Ct + (int64_t)c0 * op->ldct + r;
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
-                        if (c0 + e < N) {
+                        if (c0 + e < N)
                             ct[(int64_t)e * op->ldct] = v[e];
-                            if (MC)
-                                for (int q = 0; q < peers; ++q)
-                                    if (q != me)
-                                        *reinterpret_cast<double*>(reinterpret_cast<char*>(ct + (int64_t)e * op->ldct) + dT[q]) = v[e];
-                        }
                 }
                 if (c0 + 3 < N && (!lower || r + tri_off >= c0 + 3)) {
                     double2* q = reinterpret_cast<double2*>(crow + c0);
@@ -366,25 +348,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     }
                     q[0] = make_double2(v[0], v[1]);
                     q[1] = make_double2(v[2], v[3]);
-                    if (MC)
-                        for (int z = 0; z < peers; ++z)
-                            if (z != me) {
-                                double2* qq = reinterpret_cast<double2*>(reinterpret_cast<char*>(q) + dC[z]);
-                                qq[0] = make_double2(v[0], v[1]);
-                                qq[1] = make_double2(v[2], v[3]);
-                            }
                 } else {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int c = c0 + e;
                         if (c >= N || (lower && r + tri_off < c))
                             continue;
-                        const double val = accum ? crow[c] + v[e] : v[e];
-                        crow[c] = val;
-                        if (MC)
-                            for (int z = 0; z < peers; ++z)
-                                if (z != me)
-                                    *reinterpret_cast<double*>(reinterpret_cast<char*>(crow + c) + dC[z]) = val;
+                        crow[c] = accum ? crow[c] + v[e] : v[e];
                     }
                 }
             }
@@ -397,7 +367,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
 }  // namespace
 
-void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, const PeerTable* pt, bool mcast, void* stream)
+void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, void* stream)
 {
     if (nops <= 0 || ntiles <= 0)
         return;
@@ -406,25 +376,16 @@ void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles,
         return (e && e[0] == 'l') ? 1 : 0;
     }();
     if (dev::first_use(KEY_GEMM)) {   // kernel attributes are per device
-        cudaFuncSetAttribute(gemm_tile_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-        cudaFuncSetAttribute(gemm_tile_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-        cudaFuncSetAttribute(gemm_tile_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-        cudaFuncSetAttribute(gemm_tile_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        cudaFuncSetAttribute(gemm_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        cudaFuncSetAttribute(gemm_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     }
     const int sms = dev::sm_count();
     const int grid = ntiles < sms ? ntiles : sms;   // one persistent CTA per SM (the 132 KB ring allows no more)
     cudaStream_t st = (cudaStream_t)stream;
-    if (loader == 0) {
-        if (mcast)
-            gemm_tile_kernel<0, 1><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ops, tiles, ntiles, pt);
-        else
-            gemm_tile_kernel<0, 0><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ops, tiles, ntiles, pt);
-    } else {
-        if (mcast)
-            gemm_tile_kernel<1, 1><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ops, tiles, ntiles, pt);
-        else
-            gemm_tile_kernel<1, 0><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ops, tiles, ntiles, pt);
-    }
+    if (loader == 0)
+        gemm_tile_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ops, tiles, ntiles);
+    else
+        gemm_tile_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ops, tiles, ntiles);
 }
 
 }  // namespace gadj

@@ -60,13 +60,13 @@ struct Builder {
     std::vector<size_t> woff;   // per front: offset of its W block in b.wbuf (Wt follows at + wblock)
 
     // per op of a batch: how its tiles are shared out among the ranks (multi-GPU, replicated top fronts)
-    enum Dist { D_ALL = 0, D_ROW = 1, D_SUM = 2 };
+    enum Dist { D_ALL = 0, D_SUM = 1 };
     struct Share {
-        int dist;   // D_ALL: this rank runs every tile; D_ROW: the tiles of panel row tile T go to rank T % world;
-                    // D_SUM: tile (tm, tn) goes to rank (tm + tn) % world
-        int rt0;    // D_ROW: row tile (of the front's panel) the op's first row sits in
+        int dist;   // D_ALL: this rank runs every tile; D_SUM: tile (tm, tn) goes to rank (tm + tn) % world
+        int push;   // the finished tiles are pushed into every peer's replica: McBuf of C in bits 0..7, of Ct in bits 8..15
     };
     std::vector<Share> share;   // parallel to the pending GEMM batch
+    std::vector<PushOp> pushes; // pending pushes (the tiles of the launches since the last flush_push)
 
     Builder(const Symbolic& S, const PlanBuffers& B, Plan& P) : s(S), b(B), p(P)
     {
@@ -138,9 +138,46 @@ struct Builder {
         add_barrier(out, level);
     }
 
+    double* buffer_base(int buf) const { return buf == MC_PANELS ? b.panels : buf == MC_WBUF ? b.wbuf : buf == MC_POOL ? b.pool : nullptr; }
+    void add_push(int buf, const double* ptr, int64_t ld, int rows, int cols)
+    {
+        if (!multi() || rows <= 0 || cols <= 0)
+            return;
+        PushOp o{};
+        o.off = (uint64_t)(ptr - buffer_base(buf));
+        o.ld = ld;
+        o.rows = rows;
+        o.cols = cols;
+        o.buf = buf;
+        pushes.push_back(o);
+        p.nvlink_write_bytes += 8.0 * rows * cols * (s.world - 1);
+    }
+    // the pending pushes as one launch, then a barrier: afterwards every replica holds what the ranks have just finished.
+    // Every rank calls this at the same points of the plan (a rank with nothing to push still meets the others).
+    void flush_push(std::vector<Launch>& out, int level)
+    {
+        if (!multi())
+            return;
+        if (!pushes.empty()) {
+            Launch L{};
+            L.kind = L_PUSH;
+            L.level = level;
+            L.op_begin = (int64_t)p.push.size();
+            L.op_count = (int32_t)pushes.size();
+            int maxrows = 0;
+            for (const PushOp& o : pushes)
+                maxrows = std::max(maxrows, o.rows);
+            L.total_tiles = std::max(1, std::min(64, maxrows / 16));   // CTAs per op
+            p.push.insert(p.push.end(), pushes.begin(), pushes.end());
+            pushes.clear();
+            out.push_back(L);
+        }
+        add_barrier(out, level);
+    }
+
     void add_gemm(std::vector<GemmOp>& batch, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                   int64_t ldc, int M, int N, int K, int flags, int tri_off = 0, const int32_t* coltgt = nullptr,
-                  Share sh = Share{D_ALL, 0}, int mc = 0)
+                  Share sh = Share{D_ALL, 0})
     {
         if (M <= 0 || N <= 0 || K <= 0)
             return;
@@ -161,7 +198,6 @@ struct Builder {
         op.K = K;
         op.flags = flags;
         op.tri_off = tri_off;
-        op.mc = mc;
         op.tiles_m = cdiv(M, TILE_M);
         op.tiles_n = cdiv(N, TILE_N);
         batch.push_back(op);
@@ -189,20 +225,18 @@ struct Builder {
                     if ((op.flags & GEMM_LOWER) && tm * TILE_M + (TILE_M - 1) + op.tri_off < tn * TILE_N)
                         continue;   // wholly above the diagonal
                     ++all_tiles;
-                    if (sh.dist == D_ROW && (sh.rt0 + tm) % s.world != s.rank)
-                        continue;   // another rank's row of tiles
                     if (sh.dist == D_SUM && (tm + tn) % s.world != s.rank)
-                        continue;
+                        continue;   // another rank's tile
                     ++my_tiles;
                     p.tiles.push_back(GemmTile{opi, (uint16_t)tm, (uint16_t)tn});
+                    if (sh.push) {
+                        const int rows = std::min(TILE_M, op.M - tm * TILE_M), cols = std::min(TILE_N, op.N - tn * TILE_N);
+                        const int bc = sh.push & 0xff, bt = (sh.push >> 8) & 0xff;
+                        add_push(bc, op.C + (int64_t)tm * TILE_M * op.ldc + (int64_t)tn * TILE_N, op.ldc, rows, cols);
+                        if (bt)
+                            add_push(bt, op.Ct + (int64_t)tn * TILE_N * op.ldct + (int64_t)tm * TILE_M, op.ldct, cols, rows);
+                    }
                 }
-            if (op.flags & GEMM_MCAST) {
-                L.mcast = 1;
-                if (all_tiles) {
-                    double bytes = 8.0 * (double)op.M * op.N * ((op.flags & GEMM_LOWER) ? 0.5 : 1.0) * ((op.flags & GEMM_DUAL) ? 2.0 : 1.0);
-                    p.nvlink_write_bytes += bytes * (double)my_tiles / (double)all_tiles * (s.world - 1);
-                }
-            }
             ++opi;
             // useful flops: lower-only outputs drop the strict upper triangle of the leading square;
             // triangular operands halve the K range over that square
@@ -241,8 +275,6 @@ struct Builder {
         L.level = level;
         for (auto& op : batch) {
             L.flops += (double)op.w * op.w * op.w * (op.factor ? 2.0 / 3.0 : 1.0 / 3.0);
-            if (op.mc)
-                p.nvlink_write_bytes += 8.0 * 2.5 * (double)op.w * op.w * (s.world - 1);
             p.diag.push_back(op);
         }
         out.push_back(L);
@@ -291,19 +323,14 @@ struct Builder {
     // W21 = -W22 (L21 W11),  as  Tt = Wt11 L21^T  (parked in the unused upper part of W),  W21 = -W22 Tt^T,
     // Wt12 = W21^T.  Every pair of every front of the level is in the same three launches: 3 log2(k / 128)
     // launches per level.
-    // dist (replicated top fronts of a multi-GPU run): the tiles of the two products are shared out among the ranks and
-    // stored into every replica, with a barrier after each; the transposes are cheap and every rank does its own.
-    void build_trtri(const std::vector<uint32_t>& fl, std::vector<Launch>& out, int level, bool dist)
+    void build_trtri(const std::vector<uint32_t>& fl, std::vector<Launch>& out, int level)
     {
         std::vector<TransposeOp> trb;
         int maxk = 0;
         for (uint32_t fi : fl)
             maxk = std::max<int>(maxk, (int)s.fronts[fi].k);
-        const Share sh{dist ? D_SUM : D_ALL, 0};
-        const int mcf = dist ? GEMM_MCAST : 0;
         for (int bw = NB; bw < maxk; bw <<= 1) {
             std::vector<GemmOp> ga, gbb;
-            std::vector<Share> sa, sb;
             for (uint32_t fi : fl) {
                 const Front& f = s.fronts[fi];
                 const uint32_t ldw = ldw_of(f);
@@ -314,14 +341,12 @@ struct Builder {
                     const int rows2 = std::min<int>(bw, (int)f.k - r1);
                     double* Tt = W + (size_t)r0 * ldw + r1;                    // bw x rows2
                     double* W21 = W + (size_t)r1 * ldw + r0;                   // rows2 x bw
-                    share.swap(sa);
+                    share.clear();
                     add_gemm(ga, Wt + (size_t)r0 * ldw + r0, ldw, panel(f) + (size_t)r1 * f.ldk + r0, f.ldk, Tt, ldw, bw, rows2,
-                             bw, GEMM_KLO_ROW | mcf, 0, nullptr, sh, MC_WBUF);
-                    share.swap(sa);
-                    share.swap(sb);
-                    add_gemm(gbb, W + (size_t)r1 * ldw + r1, ldw, Tt, ldw, W21, ldw, rows2, bw, rows2,
-                             GEMM_NEG | GEMM_KHI_ROW | mcf, 0, nullptr, sh, MC_WBUF);
-                    share.swap(sb);
+                             bw, GEMM_KLO_ROW);
+                    share.clear();
+                    add_gemm(gbb, W + (size_t)r1 * ldw + r1, ldw, Tt, ldw, W21, ldw, rows2, bw, rows2, GEMM_NEG | GEMM_KHI_ROW);
+                    share.clear();
                     TransposeOp t{};
                     t.src = W21;
                     t.dst = Wt + (size_t)r0 * ldw + r1;
@@ -332,25 +357,14 @@ struct Builder {
                     trb.push_back(t);
                 }
             }
-            const bool any = !ga.empty();
-            share.swap(sa);
             flush_gemm(ga, out, level, T_TRTRI_A);
-            if (dist && any)
-                add_barrier(out, level);
-            share.swap(sb);
             flush_gemm(gbb, out, level, T_TRTRI_B);
-            if (dist && any)
-                add_barrier(out, level);
             flush_simple(trb, p.transpose, L_TRANSPOSE, out, level);
         }
     }
 
     // ---- numeric factorisation ------------------------------------------------
-    // One tree level of fronts.  dist: the replicated top fronts of a multi-GPU run — right-looking; panel row tile T of a
-    // front belongs to rank T % world, which applies the pivot inverse to its tiles of the current block column and
-    // stores them into every replica, and keeps its tiles of the trailing matrix up to date locally; the pivot tile is
-    // factorised by the owner of its row and stored into every replica.
-    void factor_level(const std::vector<uint32_t>& fl, int lv, bool dist)
+    void factor_level(const std::vector<uint32_t>& fl, int lv)
     {
         std::vector<GemmOp> gb;
         std::vector<DiagOp> db;
@@ -363,8 +377,7 @@ struct Builder {
         size_t row_tiles = 0;
         for (uint32_t f : fl)
             row_tiles += (size_t)cdiv((int)s.fronts[f].m, TILE_M);
-        const bool left = !dist && row_tiles >= 2 * 148;
-        const int mcf = dist ? GEMM_MCAST : 0;
+        const bool left = row_tiles >= 2 * 148;
         for (int j = 0; j < nsteps; ++j) {
             const int jb = j * NB;
             if (left && jb > 0) {
@@ -379,14 +392,10 @@ struct Builder {
                 flush_gemm(gb, p.factor, lv, T_LEFT_UPDATE);
             }
             // pivot tiles
-            bool any = false;
             for (size_t i = 0; i < fl.size(); ++i) {
                 const Front& f = s.fronts[fl[i]];
                 if (jb >= (int)f.k)
                     continue;
-                any = true;
-                if (dist && j % s.world != s.rank)
-                    continue;   // the rank that owns panel row tile j factorises the pivot tile for everybody
                 DiagOp d{};
                 d.D = panel(f) + (size_t)jb * f.ldk + jb;
                 d.ldd = f.ldk;
@@ -396,34 +405,20 @@ struct Builder {
                 d.W = Wof(fl[i]) + (size_t)jb * d.ldw + jb;
                 d.Wt = Wtof(fl[i]) + (size_t)jb * d.ldw + jb;
                 d.front = (int32_t)fl[i];
-                d.mc = dist ? 1 : 0;
                 db.push_back(d);
             }
             flush_diag(db, p.factor, lv);
-            if (dist && any)
-                add_barrier(p.factor, lv);
             // rows below the pivot tile: P <- P * W^T
             for (size_t i = 0; i < fl.size(); ++i) {
                 const Front& f = s.fronts[fl[i]];
                 if (jb >= (int)f.k)
                     continue;
                 int w = std::min<int>(NB, (int)f.k - jb);
-                int r0 = jb + w;
-                const double* Wj = Wof(fl[i]) + (size_t)jb * ldw_of(f) + jb;
-                if (dist && w < NB) {
-                    // ragged last pivot tile: the rows up to the next 128-row boundary sit in the pivot's own row tile
-                    const int head = std::min<int>((int)f.m, jb + NB) - r0;
-                    double* A0 = panel(f) + (size_t)r0 * f.ldk + jb;
-                    add_gemm(gb, A0, f.ldk, Wj, ldw_of(f), A0, f.ldk, head, w, w, mcf, 0, nullptr, Share{D_ROW, j}, MC_PANELS);
-                    r0 += head;
-                }
-                double* A = panel(f) + (size_t)r0 * f.ldk + jb;
-                add_gemm(gb, A, f.ldk, Wj, ldw_of(f), A, f.ldk, (int)f.m - r0, w, w, mcf, 0, nullptr,
-                         Share{dist ? D_ROW : D_ALL, j + 1}, MC_PANELS);
+                double* A = panel(f) + (size_t)(jb + w) * f.ldk + jb;
+                add_gemm(gb, A, f.ldk, Wof(fl[i]) + (size_t)jb * ldw_of(f) + jb, ldw_of(f), A, f.ldk, (int)f.m - (jb + w), w, w,
+                         0);
             }
             flush_gemm(gb, p.factor, lv, T_PANEL);
-            if (dist && any)
-                add_barrier(p.factor, lv);
             if (left)
                 continue;
             // trailing update inside the panel (columns still to be factorised)
@@ -435,22 +430,21 @@ struct Builder {
                 int nc = (int)f.k - (jb + w);
                 double* A = panel(f) + (size_t)(jb + w) * f.ldk + jb;
                 double* C = panel(f) + (size_t)(jb + w) * f.ldk + (jb + w);
-                add_gemm(gb, A, f.ldk, A, f.ldk, C, f.ldk, (int)f.m - (jb + w), nc, w, GEMM_ACCUM | GEMM_NEG | GEMM_LOWER, 0,
-                         nullptr, Share{dist ? D_ROW : D_ALL, j + 1});
+                add_gemm(gb, A, f.ldk, A, f.ldk, C, f.ldk, (int)f.m - (jb + w), nc, w, GEMM_ACCUM | GEMM_NEG | GEMM_LOWER);
             }
             flush_gemm(gb, p.factor, lv, T_RIGHT_UPDATE);
         }
-        build_trtri(fl, p.factor, lv, dist);
+        build_trtri(fl, p.factor, lv);
         // Schur update -L21 L21^T of every front, one lower-triangular r x r product per front, scattered into the
-        // ancestors' panels through the per-column target table (dist: each rank scatters its share of the tiles into
-        // its own replicas of the ancestors; the partial sums meet in the all-reduce before the ancestors' level)
+        // ancestors' panels through the per-column target table (multi-GPU: into this rank's replicas of the top fronts —
+        // the ranks' partial sums meet in the all-reduce before the ancestors' level)
         for (uint32_t fi : fl) {
             const Front& f = s.fronts[fi];
             if (!f.r)
                 continue;
             double* A = panel(f) + (size_t)f.k * f.ldk;
             add_gemm(gb, A, f.ldk, A, f.ldk, nullptr, 0, (int)f.r, (int)f.r, (int)f.k, GEMM_SCATTER | GEMM_NEG | GEMM_LOWER, 0,
-                     b.coltgt + f.bnd_begin, Share{dist ? D_SUM : D_ALL, 0});
+                     b.coltgt + f.bnd_begin);
         }
         flush_gemm(gb, p.factor, lv, T_SCHUR);
     }
@@ -458,7 +452,7 @@ struct Builder {
     void build_factor()
     {
         for (size_t lv = 0; lv < s.levels.size(); ++lv)
-            factor_level(local_fronts(lv), (int)lv, false);
+            factor_level(local_fronts(lv), (int)lv);
         if (multi())
             for (size_t lv = 0; lv < s.levels.size(); ++lv) {
                 const std::vector<uint32_t> tl = top_fronts(lv);
@@ -470,7 +464,23 @@ struct Builder {
                 for (uint32_t fi : tl)
                     ranges.push_back(ReduceOp{s.fronts[fi].panel_off, (uint64_t)s.fronts[fi].m * s.fronts[fi].ldk});
                 add_allreduce(p.factor, (int)lv, MC_PANELS, ranges);
-                factor_level(tl, (int)lv, true);
+                // Each top front is factorised by one rank (the fronts of a level by different ranks, side by side) with the
+                // one-GPU launch lists, and the factor — panel, W, Wt — pushed into every replica: every rank needs it for the
+                // substitutions and for its share of the selected inverse.  (Sharing the factorisation itself out tile by
+                // tile was measured first: ~100 dependent pivot steps of two barriers each cost more than they saved,
+                // profiles/r2_bench_8gpu_c4_first.json.)
+                std::vector<uint32_t> mine;
+                for (uint32_t fi : tl)
+                    if (s.fronts[fi].owner == s.rank)
+                        mine.push_back(fi);
+                factor_level(mine, (int)lv);
+                for (uint32_t fi : mine) {
+                    const Front& f = s.fronts[fi];
+                    add_push(MC_PANELS, panel(f), f.ldk, (int)f.m, (int)f.k);
+                    add_push(MC_WBUF, Wof(fi), ldw_of(f), (int)f.k, (int)f.k);
+                    add_push(MC_WBUF, Wtof(fi), ldw_of(f), (int)f.k, (int)f.k);
+                }
+                flush_push(p.factor, (int)lv);
             }
         for (auto& L : p.factor)
             p.factor_flops += L.flops;
@@ -555,14 +565,14 @@ struct Builder {
     }
 
     // ---- selected inverse -------------------------------------------------------
-    // dist: one replicated top front at a time, its workspace at the start of the pool on every rank; the tiles of the
-    // four products are shared out among the ranks and every finished tile is stored into all replicas.
+    // dist (multi-GPU): the replicated top fronts of one level, their workspaces at the same pool offsets on every rank;
+    // the tiles of the four products are shared out among the ranks, every rank pushes the tiles it has finished into
+    // all replicas and the ranks meet before the next product reads them.
     void build_selinv_chunk(const std::vector<uint32_t>& chunk, const std::vector<size_t>& base, int level, bool dist)
     {
         std::vector<GemmOp> gb;
         std::vector<GatherOp> gab;
-        const Share sh{dist ? D_SUM : D_ALL, 0};
-        const int mcf = dist ? GEMM_MCAST : 0;
+        const int D = dist ? D_SUM : D_ALL;
         // no clearing of the workspace: every tile that is read has been written before (the K-range
         // flags keep the triangular products inside the written tiles)
         for (size_t i = 0; i < chunk.size(); ++i) {
@@ -587,20 +597,18 @@ struct Builder {
         }
         flush_simple(gab, p.gather, L_GATHER, p.selinv, level);
         // Yt = Wt * L21^T
-        bool any_r = false;
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];
             if (!f.r)
                 continue;
-            any_r = true;
             SelinvWs w = ws_layout(f);
             double* ws = b.pool + base[i];
             add_gemm(gb, Wtof(chunk[i]), ldw_of(f), panel(f) + (size_t)f.k * f.ldk, f.ldk, ws + w.Yt, w.ldr, (int)f.k, (int)f.r,
-                     (int)f.k, GEMM_KLO_ROW | mcf, 0, nullptr, sh, MC_POOL);
+                     (int)f.k, GEMM_KLO_ROW, 0, nullptr, Share{D, dist ? MC_POOL : 0});
         }
         flush_gemm(gb, p.selinv, level, T_YT);
-        if (dist && any_r)
-            add_barrier(p.selinv, level);
+        if (dist)
+            flush_push(p.selinv, level);
         // Z21 = -G * Y   (overwrites L21), with its transpose Z21t stored by the same epilogue
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];
@@ -609,21 +617,18 @@ struct Builder {
             SelinvWs w = ws_layout(f);
             double* ws = b.pool + base[i];
             add_gemm(gb, ws + w.G, w.ldg, ws + w.Yt, w.ldr, panel(f) + (size_t)f.k * f.ldk, f.ldk, (int)f.r, (int)f.k,
-                     (int)f.r, GEMM_NEG | GEMM_DUAL | mcf, 0, nullptr, sh, MC_PANELS | (MC_POOL << 8));
+                     (int)f.r, GEMM_NEG | GEMM_DUAL, 0, nullptr, Share{D, dist ? (MC_PANELS | (MC_POOL << 8)) : 0});
             gb.back().Ct = ws + w.Z21t;
             gb.back().ldct = w.ldr;
         }
         flush_gemm(gb, p.selinv, level, T_Z21);
-        if (dist && any_r)
-            add_barrier(p.selinv, level);
-        // Z11 = Wt Wt^T   (overwrites L11, lower triangle); fronts without a boundary are finished by this product
-        bool any_root = false;
+        if (dist)
+            flush_push(p.selinv, level);
+        // Z11 = Wt Wt^T   (overwrites L11, lower triangle); a front without a boundary is finished by this product
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];
-            const bool last = f.r == 0;
-            any_root = any_root || last;
             add_gemm(gb, Wtof(chunk[i]), ldw_of(f), Wtof(chunk[i]), ldw_of(f), panel(f), f.ldk, (int)f.k, (int)f.k, (int)f.k,
-                     GEMM_LOWER | GEMM_KLO_MAX | (last ? mcf : 0), 0, nullptr, sh, MC_PANELS);
+                     GEMM_LOWER | GEMM_KLO_MAX, 0, nullptr, Share{D, (dist && f.r == 0) ? MC_PANELS : 0});
         }
         flush_gemm(gb, p.selinv, level, T_Z11_WW);
         // Z11 -= Yt * Z21t^T
@@ -634,24 +639,33 @@ struct Builder {
             SelinvWs w = ws_layout(f);
             double* ws = b.pool + base[i];
             add_gemm(gb, ws + w.Yt, w.ldr, ws + w.Z21t, w.ldr, panel(f), f.ldk, (int)f.k, (int)f.k, (int)f.r,
-                     GEMM_ACCUM | GEMM_NEG | GEMM_LOWER | mcf, 0, nullptr, sh, MC_PANELS);
+                     GEMM_ACCUM | GEMM_NEG | GEMM_LOWER, 0, nullptr, Share{D, dist ? MC_PANELS : 0});
         }
         flush_gemm(gb, p.selinv, level, T_Z11_YZ);
-        if (dist && (any_r || any_root))
-            add_barrier(p.selinv, level);
+        if (dist)
+            flush_push(p.selinv, level);
     }
 
     void build_selinv()
     {
         if (multi())
-            for (size_t lvi = s.levels.size(); lvi-- > 0;)
-                for (uint32_t fi : top_fronts(lvi)) {
-                    if (ws_layout(s.fronts[fi]).total > b.pool_doubles) {
-                        err = "workspace pool smaller than the largest front";
-                        return;
-                    }
-                    build_selinv_chunk({fi}, {0}, (int)lvi, true);
+            for (size_t lvi = s.levels.size(); lvi-- > 0;) {
+                // all top fronts of the level together (min_pool_doubles has made room for them on every rank)
+                const std::vector<uint32_t> tl = top_fronts(lvi);
+                if (tl.empty())
+                    continue;
+                std::vector<size_t> base;
+                size_t used = 0;
+                for (uint32_t fi : tl) {
+                    base.push_back(used);
+                    used += ws_layout(s.fronts[fi]).total;
                 }
+                if (used > b.pool_doubles) {
+                    err = "workspace pool smaller than the top fronts of a level";
+                    return;
+                }
+                build_selinv_chunk(tl, base, (int)lvi, true);
+            }
         for (size_t lvi = s.levels.size(); lvi-- > 0;) {
             const std::vector<uint32_t> fl = local_fronts(lvi);
             std::vector<uint32_t> chunk;
@@ -689,8 +703,16 @@ size_t min_pool_doubles(const Symbolic& s)
 {
     size_t need = 0;
     for (const Front& f : s.fronts)
-        if (f.owner == s.rank || f.top)
+        if (f.owner == s.rank && !f.top)
             need = std::max(need, ws_layout(f).total);
+    // the replicated top fronts of a level are inverted together, their workspaces side by side
+    for (auto& lv : s.levels) {
+        size_t t = 0;
+        for (uint32_t f : lv)
+            if (s.fronts[f].top)
+                t += ws_layout(s.fronts[f]).total;
+        need = std::max(need, t);
+    }
     return std::max<size_t>(16, need);
 }
 
@@ -746,6 +768,7 @@ std::string build_plan(const Symbolic& s, const PlanBuffers& b, Plan& p)
     p.transpose.clear();
     p.gather.clear();
     p.reduce.clear();
+    p.push.clear();
     p.factor.clear();
     p.fwd.clear();
     p.bwd.clear();

@@ -20,6 +20,7 @@ enum LaunchKind : int32_t {
     L_ZERO,
     L_BARRIER,   // multi-GPU: all ranks meet (device-side barrier over NVLink); stores into peers' replicas are visible after it
     L_ALLREDUCE, // multi-GPU: sum of the ranks' replicas of some ranges of a buffer, written back to every replica
+    L_PUSH,      // multi-GPU: blocks this rank has finished, copied into every peer's replica
 };
 
 struct Launch {
@@ -33,7 +34,6 @@ struct Launch {
     size_t zero_bytes;
     double flops;         // algorithmic flops of this launch (GEMM: 2MNK, halved for LOWER)
     int32_t tag;          // which step of the algorithm (profiling label)
-    int32_t mcast;        // L_GEMM: some op of the launch stores into the peers' replicas (GEMM_MCAST)
     int32_t buf;          // L_ALLREDUCE: McBuf of the buffer the ranges live in
 };
 
@@ -65,6 +65,7 @@ struct Plan {
     std::vector<TransposeOp> transpose;
     std::vector<GatherOp> gather;
     std::vector<ReduceOp> reduce;
+    std::vector<PushOp> push;
     std::vector<Launch> factor, fwd, bwd, selinv;
     std::vector<int32_t> rowidx;            // host copy (uploaded by the caller before build_plan's pointers are used)
     std::vector<uint64_t> rowidx_off;       // per front

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 
 namespace gadj {
@@ -378,6 +379,10 @@ void finalize_layout(Symbolic& s, int world, int rank)
                 total += sub[f];
             }
         // split the heaviest subtree while there are too few, or it alone exceeds a fair share
+        // (GADJ_MG_SUBTREES=n: at least n subtrees — a deeper cut than the rank count needs, for experiments)
+        size_t min_subtrees = (size_t)world;
+        if (const char* e = getenv("GADJ_MG_SUBTREES"))
+            min_subtrees = std::max<size_t>(min_subtrees, (size_t)atoi(e));
         for (;;) {
             size_t best = cand.size();
             for (size_t i = 0; i < cand.size(); ++i)
@@ -389,7 +394,7 @@ void finalize_layout(Symbolic& s, int world, int rank)
             for (uint32_t c : cand)
                 if (sub[c] > sub[cand[best]])
                     heaviest_is_best = false;
-            if (cand.size() >= (size_t)world && !(heaviest_is_best && sub[cand[best]] > total / world))
+            if (cand.size() >= min_subtrees && !(heaviest_is_best && sub[cand[best]] > total / (double)min_subtrees))
                 break;
             uint32_t f = cand[best];
             s.fronts[f].top = 1;

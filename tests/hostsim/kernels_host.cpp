@@ -14,17 +14,7 @@
 
 namespace gadj {
 
-// store into this rank's buffer and, for multicast ops, into every other rank's replica
-static inline void mc_store(double* p, double v, const PeerTable* pt, int buf)
-{
-    *p = v;
-    if (pt && buf != MC_NONE)
-        for (int q = 0; q < pt->nranks; ++q)
-            if (q != pt->rank)
-                *reinterpret_cast<double*>(reinterpret_cast<char*>(p) + pt->delta[buf][q]) = v;
-}
-
-void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, const PeerTable* pt, bool mcast, void*)
+void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, void*)
 {
     // tile by tile, exactly the work list the persistent CTAs stride through: a tile missing from the planner's
     // list, or listed twice, changes the results
@@ -64,18 +54,18 @@ void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles,
                     int64_t r = 3ll * tg.rowmap[i / 3 - tg.jb] + i % 3;
                     int64_t c = 3ll * tg.rowmap[j / 3 - tg.jb] + j % 3;
                     tg.C[r * tg.ldc + c] += v;
-                } else {
-                    const bool mc = mcast && (op.flags & GEMM_MCAST);
-                    double* c = op.C + (int64_t)i * op.ldc + j;
-                    mc_store(c, (op.flags & GEMM_ACCUM) ? *c + v : v, mc ? pt : nullptr, op.mc & 0xff);
+                } else if (op.flags & GEMM_ACCUM)
+                    op.C[(int64_t)i * op.ldc + j] += v;
+                else {
+                    op.C[(int64_t)i * op.ldc + j] = v;
                     if (op.flags & GEMM_DUAL)
-                        mc_store(op.Ct + (int64_t)j * op.ldct + i, v, mc ? pt : nullptr, (op.mc >> 8) & 0xff);
+                        op.Ct[(int64_t)j * op.ldct + i] = v;
                 }
             }
     }
 }
 
-void launch_diag(const DiagOp* ops, int nops, int* info, const PeerTable* pt, void*)
+void launch_diag(const DiagOp* ops, int nops, int* info, void*)
 {
     for (int o = 0; o < nops; ++o) {
         const DiagOp& op = ops[o];
@@ -116,15 +106,26 @@ void launch_diag(const DiagOp* ops, int nops, int* info, const PeerTable* pt, vo
             for (int i = 0; i < w; ++i)
                 for (int j = 0; j < w; ++j) {
                     if (op.W)
-                        mc_store(op.W + i * op.ldw + j, W[(size_t)i * w + j], op.mc ? pt : nullptr, MC_WBUF);
+                        op.W[i * op.ldw + j] = W[(size_t)i * w + j];
                     if (op.Wt)
-                        mc_store(op.Wt + j * op.ldwt + i, W[(size_t)i * w + j], op.mc ? pt : nullptr, MC_WBUF);
+                        op.Wt[j * op.ldwt + i] = W[(size_t)i * w + j];
                 }
         }
-        if (op.factor && op.mc && pt)
-            for (int i = 0; i < w; ++i)
-                for (int j = 0; j <= i; ++j)
-                    mc_store(D + i * ld + j, D[i * ld + j], pt, MC_PANELS);
+    }
+}
+
+void launch_push(const PushOp* ops, int nops, int, const PeerTable* pt, double* const* bases, void*)
+{
+    for (int o = 0; o < nops; ++o) {
+        const PushOp& op = ops[o];
+        double* base = bases[op.buf] + op.off;
+        for (int r = 0; r < op.rows; ++r)
+            for (int c = 0; c < op.cols; ++c) {
+                double* p = base + (int64_t)r * op.ld + c;
+                for (int q = 0; q < pt->nranks; ++q)
+                    if (q != pt->rank)
+                        *reinterpret_cast<double*>(reinterpret_cast<char*>(p) + pt->delta[op.buf][q]) = *p;
+            }
     }
 }
 

@@ -244,3 +244,82 @@ def test_scale_properties_config_c3(gpu_lib):
                              f"{np.abs(q0).max():.3e}; {len(bad)} stations off, first {bad[:20].tolist()}, last {bad[-5:].tolist()}")
     # the per-record statistics written back by the two runs agree as well
     assert np.abs(m1["measCorr"] - m0["measCorr"]).max() < 1e-7
+
+
+def test_rigorous_inverse_config_c5(gpu_lib):
+    """BASELINE config C5 (100k stations, rigorous full inverse), no dense oracle at this size: the normal-equation identity
+    sum_j N[s,j] Z[j,s] = I on EVERY station, built from the records and the returned variance blocks in extended
+    precision (dynadjust_b200/checks.py), under both elimination orders; the dense per-block variance matrices
+    (v_rigorousVariances_, ADJ:3805) agree with the station and pair blocks; the two orders agree with each other."""
+    from dynadjust_b200 import checks
+    stn, msr, truth, _ = synth.config_network("C5")
+    rec = msr.reshape(-1, 3)
+    results = []
+    for kw, blocks in ((dict(leaf_stations=96), None), (dict(), parity.chain_blocks(len(stn), 1000))):
+        s, m = stn.copy(), msr.copy()
+        adj, info, last, stats = parity.run_engine(gpu_lib, s, m, blocks=blocks, **kw)
+        assert last.converged
+        res, worst = checks.normal_identity_residual(adj, s, m)
+        assert res < 1e-10, (res, worst)
+        q = adj.station_vcvs()
+        # dense block matrices of a few blocks against the blocks stored along the measured pairs
+        for b in (0, int(info.nfronts) // 2, int(info.nfronts) - 1):
+            bs, V = adj.block_vcv(b)
+            pos = {int(st): i for i, st in enumerate(bs)}
+            for i, st in enumerate(bs[:40]):
+                assert np.abs(V[3 * i:3 * i + 3, 3 * i:3 * i + 3] - q[st]).max() <= 1e-12 * np.abs(q[st]).max()
+            sel = [k for k in range(0, len(rec), 997) if int(rec["station1"][k, 0]) in pos and int(rec["station2"][k, 0]) in pos][:20]
+            for k in sel:
+                s1, s2 = int(rec["station1"][k, 0]), int(rec["station2"][k, 0])
+                blk = adj.vcv_block(s1, s2)
+                i, j = pos[s1], pos[s2]
+                assert np.abs(V[3 * i:3 * i + 3, 3 * j:3 * j + 3] - blk).max() <= 1e-12 * np.abs(q[s1]).max()
+        results.append((adj.estimates(), q, stats))
+        adj.close()
+    (e0, q0, s0), (e1, q1, s1) = results
+    assert np.abs(e1 - e0).max() < 2e-9
+    assert abs(s1.sigma_zero - s0.sigma_zero) < 1e-11
+    assert np.abs(q1 - q0).max() < 1e-10 * np.abs(q0).max()
+
+
+def test_dense_normals_config_c2(gpu_lib):
+    """BASELINE config C2 as named: 10k stations on ONE dense front (n = 30 000; the reference's Solve on dense normals,
+    ADJ:6586) — identity on every station, and agreement with the nested-dissection run of the same network."""
+    from dynadjust_b200 import checks
+    stn, msr, truth, _ = synth.config_network("C2")
+    out = []
+    for kw in (dict(ordering=engine.ORDER_DENSE), dict(leaf_stations=96)):
+        s, m = stn.copy(), msr.copy()
+        adj, info, last, stats = parity.run_engine(gpu_lib, s, m, **kw)
+        if "ordering" in kw:
+            assert info.nfronts == 1 and info.max_front_cols == 3 * len(stn)
+        res, worst = checks.normal_identity_residual(adj, s, m)
+        assert res < 1e-10, (res, worst)
+        out.append((adj.estimates(), adj.station_vcvs(), stats))
+        adj.close()
+    assert np.abs(out[0][0] - out[1][0]).max() < 2e-9
+    assert abs(out[0][2].sigma_zero - out[1][2].sigma_zero) < 1e-12
+    assert np.abs(out[0][1] - out[1][1]).max() < 1e-10 * np.abs(out[1][1]).max()
+    assert np.sqrt(((out[0][0] - truth) ** 2).mean()) < 0.05
+
+
+def test_phased_reference_arithmetic_config_c3(gpu_lib):
+    """BASELINE config C3 (100k stations; GNSS + direction sets + distances + levelling) against the reference's PHASED
+    arithmetic at full size: tests/golden/c3_phased_oracle_sample.npz holds every 20th station of the oracle's phased run
+    (forward / reverse / combination over the same 100 blocks, tools/cpu_baselines.py C3, ~half an hour of CPU)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c3_phased_oracle_sample.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden sample of the phased oracle at C3 size not generated")
+    g = np.load(path)
+    stn, msr, truth, _ = synth.config_network("C3")
+    idx = g["stations"]
+    for kw, blocks in ((dict(), parity.chain_blocks(len(stn), int(g["block_width"]))), (dict(leaf_stations=96), None)):
+        s, m = stn.copy(), msr.copy()
+        adj, info, last, stats = parity.run_engine(gpu_lib, s, m, blocks=blocks, **kw)
+        assert last.iteration == int(g["iterations"])
+        assert stats.dof == int(g["dof"])
+        e, q = adj.estimates(), adj.station_vcvs()
+        assert np.abs(e[idx] - g["est"]).max() < 2e-9                      # 1e-9 m + one ulp of a 6.4e6 m coordinate
+        assert abs(stats.sigma_zero - float(g["sigma_zero"])) < 1e-8      # the reference's own two modes differ by ~1e-9 here
+        assert np.abs(q[idx] - g["vcv"]).max() < 2e-8 * np.abs(g["vcv"]).max()
+        adj.close()

@@ -136,3 +136,22 @@ def test_phased_oracle_matches_simultaneous(oracle, kind):
         idx = (3 * bs[:, None] + np.arange(3)[None, :]).ravel()
         assert np.abs(ph["block_vcv"] - V[np.ix_(idx, idx)]).max() <= tol * 1e-12 * np.abs(V).max()
 
+
+
+def test_reference_matrix_unit_tests_pass_on_ref_build(oracle):
+    """The reference's own tests/test_matrix.cpp (72 cases: constructors, packed / full Cholesky inverse known answers,
+    failure modes, scaling, mmap-backed storage) compiled in place against the same matrix_2d sources and BLAS that
+    oracle/_ref/libref_matrix.so is built from (oracle/Makefile): the build the oracle inverts with is the build the
+    reference's tests accept."""
+    import os
+    import subprocess
+    import sysconfig
+    exe = os.path.join(os.path.dirname(oracle.LIB_PATH), "_ref", "test_matrix")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/test_matrix not built (needs /root/reference)")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(sysconfig.get_paths()["purelib"], "opencv_python_headless.libs") + ":" + env.get("LD_LIBRARY_PATH", "")
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=env)
+    assert res.returncode == 0, res.stdout[-2000:]
+    tail = res.stdout.strip().splitlines()[-1]
+    assert tail.startswith("Total tests: 72") and tail.endswith("Failures: 0"), tail

@@ -39,5 +39,10 @@ else:
                sigma_zero=r.sigma_zero, rms_vs_truth=float(np.sqrt(((res["est"] - truth) ** 2).mean())),
                ms_per_iteration=1e3 * r.seconds_solve / max(1, r.iterations))
     np.savez_compressed(f"/tmp/phased_{which}.npz", est=res["est"], vcv=res["vcv"])
+    # golden fixture for the GPU parity test at this size: every 20th station's adjusted coordinates and rigorous 3x3 block
+    idx = np.arange(0, len(stn), 20)
+    np.savez_compressed(os.path.join("tests", "golden", f"{which.lower()}_phased_oracle_sample.npz"), stations=idx,
+                        est=res["est"][idx], vcv=res["vcv"][idx], sigma_zero=r.sigma_zero, chi_squared=r.chi_squared, dof=r.dof,
+                        iterations=r.iterations, outliers=r.outliers, block_width=1000)
 print(json.dumps(out), flush=True)
 json.dump(out, open(f"profiles/r2_cpu_baseline_{which.lower()}.json", "w"), indent=1)
