@@ -20,6 +20,7 @@
 #include "dev.h"
 #include "geodesy.h"
 #include "kernels.h"
+#include "par.h"
 #include "plan.h"
 #include "rows.h"
 #include "symbolic.h"
@@ -29,26 +30,6 @@ using namespace gadj;
 namespace {
 
 std::string g_create_error;
-
-template <class F>
-void parallel_for(uint64_t n, F&& fn)
-{
-    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    if (n < 65536 || nt == 1) {
-        fn(0, n);
-        return;
-    }
-    std::vector<std::thread> th;
-    uint64_t chunk = (n + nt - 1) / nt;
-    for (unsigned t = 0; t < nt; ++t) {
-        uint64_t b = t * chunk, e = std::min(n, b + chunk);
-        if (b >= e)
-            break;
-        th.emplace_back([=, &fn] { fn(b, e); });
-    }
-    for (auto& t : th)
-        t.join();
-}
 
 // acklam + one Halley step; stands in for boost::math::quantile(normal) (ADJ:203-206)
 double norm_quantile(double p)
@@ -627,6 +608,48 @@ int scan_measurements(gadj_ctx* c)
     c->inc_ptr.assign(1, 0u);
     c->inc.clear();
     c->non_gps = false;
+    // a list of nothing but GNSS baselines (three records each) — the national-scale case — is scanned by all host threads
+    if (c->nmsr % 3 == 0 && c->nmsr >= 3 * 65536) {
+        const uint64_t nb = c->nmsr / 3;
+        std::atomic<bool> pure{true};
+        const unsigned nt = host_threads();
+        std::vector<uint64_t> cnt(nt + 1, 0);
+        const uint64_t chunk = (nb + nt - 1) / nt;
+        parallel_for(nt, [&](uint64_t t0, uint64_t t1) {
+            for (uint64_t t = t0; t < t1; ++t) {
+                uint64_t n = 0;
+                for (uint64_t b = t * chunk; b < std::min(nb, (t + 1) * chunk); ++b) {
+                    const dna_msr_t* m = c->msr + 3 * b;
+                    if (m[0].measType != 'G' || m[1].measType != 'G' || m[2].measType != 'G' || m[0].measStart != 0) {
+                        pure.store(false, std::memory_order_relaxed);
+                        return;
+                    }
+                    n += !m[0].ignore;
+                }
+                cnt[t + 1] = n;
+            }
+        }, 0);
+        if (pure.load() && 3 * nb <= 0xFFFFFFF0ull) {
+            for (unsigned t = 0; t < nt; ++t)
+                cnt[t + 1] += cnt[t];
+            c->first.resize(cnt[nt]);
+            parallel_for(nt, [&](uint64_t t0, uint64_t t1) {
+                for (uint64_t t = t0; t < t1; ++t) {
+                    uint64_t o = cnt[t];
+                    for (uint64_t b = t * chunk; b < std::min(nb, (t + 1) * chunk); ++b)
+                        if (!c->msr[3 * b].ignore)
+                            c->first[o++] = (uint32_t)(3 * b);
+                }
+            }, 0);
+            c->nbsl = c->first.size();
+            c->nrows = 0;
+            if (c->nbsl == 0)
+                return c->fail("No valid measurements to process. All measurements may be ignored.");   // LoadNetworkFiles (ADJ:10176)
+            // first[] rises in steps of at least three records: no gaps exactly when the last one is where a gapless list ends
+            c->contiguous = c->first[c->nbsl - 1] == c->first[0] + 3 * (c->nbsl - 1);
+            return 0;
+        }
+    }
     uint64_t i = 0;
     auto bad_station = [&](uint32_t s) { return s >= c->nstn; };
     // close a cluster: local stations + incidence lists from rows [row0, rows.size())
@@ -1109,17 +1132,28 @@ int gadj_prepare(gadj_ctx* c)
         return 1;
     if (scan_measurements(c))
         return 1;
-    for (uint64_t b = 0; b < c->nbsl; ++b) {
-        const dna_msr_t& m = c->msr[c->first[b]];
-        if (m.station1 >= c->nstn || m.station2 >= c->nstn)
+    {
+        std::atomic<int> bad_bsl{0};
+        parallel_for(c->nbsl, [&](uint64_t b0, uint64_t b1) {
+            for (uint64_t b = b0; b < b1; ++b) {
+                const dna_msr_t& m = c->msr[c->first[b]];
+                if (m.station1 >= c->nstn || m.station2 >= c->nstn)
+                    bad_bsl.store(1, std::memory_order_relaxed);
+                else if (m.station1 == m.station2)
+                    bad_bsl.fetch_or(2, std::memory_order_relaxed);
+            }
+        });
+        if (bad_bsl.load() & 1)
             return c->fail("measurement refers to a station index beyond the station list");
-        if (m.station1 == m.station2)
+        if (bad_bsl.load() & 2)
             return c->fail("GNSS baseline with identical end stations");
     }
     // a-priori Cartesian coordinates (PopulateEstimatedStationMatrix, ADJ:632-693): the first-run reductions need them
     std::vector<double> est(3 * (size_t)c->nstn);
-    for (uint32_t s = 0; s < c->nstn; ++s)
-        geo_to_cart(c->ell, c->stn[s].currentLatitude, c->stn[s].currentLongitude, c->stn[s].currentHeight, &est[3 * s]);
+    parallel_for(c->nstn, [&](uint64_t s0, uint64_t s1) {
+        for (uint64_t s = s0; s < s1; ++s)
+            geo_to_cart(c->ell, c->stn[s].currentLatitude, c->stn[s].currentLongitude, c->stn[s].currentHeight, &est[3 * s]);
+    });
     lap("scan + a-priori coordinates");
     first_run_reduction(c);
     if (first_run_reduction_rows(c, est.data()))
@@ -1130,10 +1164,15 @@ int gadj_prepare(gadj_ctx* c)
     const uint64_t nb = c->nbsl;
     auto pair_key = [](uint32_t a, uint32_t b2) { return ((uint64_t)std::min(a, b2) << 32) | std::max(a, b2); };
     std::vector<uint64_t> keys(nb);
-    for (uint64_t b = 0; b < nb; ++b) {
-        const dna_msr_t& m = c->msr[c->first[b]];
-        keys[b] = pair_key(m.station1, m.station2);
-    }
+    std::vector<uint32_t> end1(nb), end2(nb);   // the baselines' end stations, once: the 208-byte records are not walked again
+    parallel_for(nb, [&](uint64_t b0, uint64_t b1) {
+        for (uint64_t b = b0; b < b1; ++b) {
+            const dna_msr_t& m = c->msr[c->first[b]];
+            end1[b] = m.station1;
+            end2[b] = m.station2;
+            keys[b] = pair_key(m.station1, m.station2);
+        }
+    });
     for (const RowDesc& d : c->rows) {
         if (d.clustered)
             continue;
@@ -1147,7 +1186,7 @@ int gadj_prepare(gadj_ctx* c)
                 keys.push_back(pair_key(c->cstn[cd.st0 + x], c->cstn[cd.st0 + y]));
     // distinct pairs, and how many measurements contribute to each: a pair fed by a single GNSS baseline is stored, not added
     std::vector<uint64_t> uniq(keys);
-    std::sort(uniq.begin(), uniq.end());
+    parallel_sort(uniq);
     std::vector<uint32_t> pair_count;
     {
         size_t o = 0;
@@ -1173,8 +1212,8 @@ int gadj_prepare(gadj_ctx* c)
     // of its station lists (RemoveInvalidStations LDR:286-300, unknownParams_ ADJ:632-693); here they stay in the system,
     // held by their a-priori weight alone, but do not count as unknowns
     std::vector<uint8_t> used(c->nstn, 0);
-    for (uint32_t f : c->first)
-        used[c->msr[f].station1] = used[c->msr[f].station2] = 1;
+    for (uint64_t b = 0; b < nb; ++b)
+        used[end1[b]] = used[end2[b]] = 1;
     for (const RowDesc& r : c->rows)
         for (int k = 0; k < r.nst; ++k)
             used[r.st[k]] = 1;
@@ -1250,8 +1289,7 @@ int gadj_prepare(gadj_ctx* c)
     c->edge_word.resize(nb);
     parallel_for(nb, [&](uint64_t b0, uint64_t b1) {
         for (uint64_t b = b0; b < b1; ++b) {
-            const dna_msr_t& m = c->msr[c->first[b]];
-            uint32_t w = edge_word_of(m.station1, m.station2);
+            uint32_t w = edge_word_of(end1[b], end2[b]);
             if (pair_count[w & EDGE_SLOT_MASK] == 1)
                 w |= EDGE_EXCLUSIVE;
             c->edge_word[b] = w;
@@ -1264,9 +1302,8 @@ int gadj_prepare(gadj_ctx* c)
     // incidence lists of the stations over the GNSS baselines, ascending baseline index (fixed summation order)
     c->binc_ptr.assign((size_t)c->nstn + 1, 0);
     for (uint64_t b = 0; b < nb; ++b) {
-        const dna_msr_t& m = c->msr[c->first[b]];
-        ++c->binc_ptr[m.station1 + 1];
-        ++c->binc_ptr[m.station2 + 1];
+        ++c->binc_ptr[end1[b] + 1];
+        ++c->binc_ptr[end2[b] + 1];
     }
     for (uint32_t s2 = 0; s2 < c->nstn; ++s2)
         c->binc_ptr[s2 + 1] += c->binc_ptr[s2];
@@ -1274,9 +1311,8 @@ int gadj_prepare(gadj_ctx* c)
     {
         std::vector<uint32_t> cur(c->binc_ptr.begin(), c->binc_ptr.end() - 1);
         for (uint64_t b = 0; b < nb; ++b) {
-            const dna_msr_t& m = c->msr[c->first[b]];
-            c->binc[cur[m.station1]++] = (uint32_t)b;
-            c->binc[cur[m.station2]++] = (uint32_t)b | 0x80000000u;
+            c->binc[cur[end1[b]]++] = (uint32_t)b;
+            c->binc[cur[end2[b]]++] = (uint32_t)b | 0x80000000u;
         }
     }
     for (RowDesc& d : c->rows) {
