@@ -45,7 +45,8 @@ struct PushOp {
     int64_t ld;
     int32_t rows, cols;
     int32_t buf;
-    int32_t pad;
+    int16_t target;          // >= 0: to that rank only; -1: to every peer
+    int16_t skip;            // >= 0: not to that rank (it holds the block already); -1: nobody skipped
 };
 
 // sum of `count` doubles at offset `off` of a replicated buffer over all ranks, result stored into every replica

@@ -239,6 +239,11 @@ __global__ void __launch_bounds__(256) push_kernel(const PushOp* __restrict__ op
     const PushOp op = ops[blockIdx.y];
     const int n = pt->nranks, me = pt->rank;
     const int64_t* d = pt->delta[op.buf];
+    // destinations of this block: every peer, or one rank only, possibly leaving out a rank that has the block already
+    unsigned dst = 0;
+    for (int q = 0; q < n; ++q)
+        if (q != me && q != op.skip && (op.target < 0 || q == op.target))
+            dst |= 1u << q;
     double* base = bases[op.buf] + op.off;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool vec = ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((op.ld & 1) == 0);
@@ -249,20 +254,20 @@ __global__ void __launch_bounds__(256) push_kernel(const PushOp* __restrict__ op
             for (int i = lane; i < pairs; i += 32) {
                 const double2 v = reinterpret_cast<const double2*>(row)[i];
                 for (int q = 0; q < n; ++q)
-                    if (q != me)
+                    if (dst >> q & 1)
                         reinterpret_cast<double2*>(reinterpret_cast<char*>(row) + d[q])[i] = v;
             }
             if ((op.cols & 1) && lane == 0) {
                 const double v = row[op.cols - 1];
                 for (int q = 0; q < n; ++q)
-                    if (q != me)
+                    if (dst >> q & 1)
                         *reinterpret_cast<double*>(reinterpret_cast<char*>(row + op.cols - 1) + d[q]) = v;
             }
         } else {
             for (int i = lane; i < op.cols; i += 32) {
                 const double v = row[i];
                 for (int q = 0; q < n; ++q)
-                    if (q != me)
+                    if (dst >> q & 1)
                         *reinterpret_cast<double*>(reinterpret_cast<char*>(row + i) + d[q]) = v;
             }
         }

@@ -139,7 +139,7 @@ struct Builder {
     }
 
     double* buffer_base(int buf) const { return buf == MC_PANELS ? b.panels : buf == MC_WBUF ? b.wbuf : buf == MC_POOL ? b.pool : nullptr; }
-    void add_push(int buf, const double* ptr, int64_t ld, int rows, int cols)
+    void add_push(int buf, const double* ptr, int64_t ld, int rows, int cols, int target = -1, int skip = -1)
     {
         if (!multi() || rows <= 0 || cols <= 0)
             return;
@@ -149,8 +149,35 @@ struct Builder {
         o.rows = rows;
         o.cols = cols;
         o.buf = buf;
+        o.target = (int16_t)target;
+        o.skip = (int16_t)skip;
         pushes.push_back(o);
-        p.nvlink_write_bytes += 8.0 * rows * cols * (s.world - 1);
+        const int ndst = target >= 0 ? 1 : s.world - 1 - (skip >= 0 ? 1 : 0);
+        p.nvlink_write_bytes += 8.0 * rows * cols * ndst;
+    }
+    // Broadcast of a block its owner has finished, in two launches: the owner sends each of the other ranks one slice of
+    // the rows (its NVLink egress carries the block once), then every rank forwards the slice it received to the others.
+    // stage 0 is planned by the owner, stage 1 by everybody else; a barrier (flush_push) follows each stage.
+    void add_broadcast(int stage, int owner, int buf, const double* ptr, int64_t ld, int rows, int cols)
+    {
+        const int P = s.world;
+        auto slice = [&](int q, int& r0, int& r1) {
+            const int idx = q < owner ? q : q - 1;   // the ranks other than the owner, in order
+            r0 = (int)((int64_t)rows * idx / (P - 1));
+            r1 = (int)((int64_t)rows * (idx + 1) / (P - 1));
+        };
+        int r0, r1;
+        if (stage == 0 && s.rank == owner) {
+            for (int q = 0; q < P; ++q) {
+                if (q == owner)
+                    continue;
+                slice(q, r0, r1);
+                add_push(buf, ptr + (int64_t)r0 * ld, ld, r1 - r0, cols, q);
+            }
+        } else if (stage == 1 && s.rank != owner && P > 2) {
+            slice(s.rank, r0, r1);
+            add_push(buf, ptr + (int64_t)r0 * ld, ld, r1 - r0, cols, -1, owner);
+        }
     }
     // the pending pushes as one launch, then a barrier: afterwards every replica holds what the ranks have just finished.
     // Every rank calls this at the same points of the plan (a rank with nothing to push still meets the others).
@@ -474,13 +501,15 @@ struct Builder {
                     if (s.fronts[fi].owner == s.rank)
                         mine.push_back(fi);
                 factor_level(mine, (int)lv);
-                for (uint32_t fi : mine) {
-                    const Front& f = s.fronts[fi];
-                    add_push(MC_PANELS, panel(f), f.ldk, (int)f.m, (int)f.k);
-                    add_push(MC_WBUF, Wof(fi), ldw_of(f), (int)f.k, (int)f.k);
-                    add_push(MC_WBUF, Wtof(fi), ldw_of(f), (int)f.k, (int)f.k);
+                for (int stage = 0; stage < 2; ++stage) {
+                    for (uint32_t fi : tl) {
+                        const Front& f = s.fronts[fi];
+                        add_broadcast(stage, f.owner, MC_PANELS, panel(f), f.ldk, (int)f.m, (int)f.k);
+                        add_broadcast(stage, f.owner, MC_WBUF, Wof(fi), ldw_of(f), (int)f.k, (int)f.k);
+                        add_broadcast(stage, f.owner, MC_WBUF, Wtof(fi), ldw_of(f), (int)f.k, (int)f.k);
+                    }
+                    flush_push(p.factor, (int)lv);
                 }
-                flush_push(p.factor, (int)lv);
             }
         for (auto& L : p.factor)
             p.factor_flops += L.flops;

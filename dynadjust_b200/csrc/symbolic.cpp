@@ -1,10 +1,14 @@
 // symbolic.cpp — ordering, supernode tree, front layout and scatter maps (host).
 #include "symbolic.h"
 
+#include "par.h"
+
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <numeric>
+#include <thread>
 
 namespace gadj {
 namespace {
@@ -34,16 +38,22 @@ Graph build_graph(uint32_t n, const std::vector<std::pair<uint32_t, uint32_t>>& 
         tmp[fill[e.first]++] = e.second;
         tmp[fill[e.second]++] = e.first;
     }
-    // sort + unique per vertex, then compact
+    // sort + unique per vertex (all host threads), then compact
     std::vector<uint64_t> nptr((size_t)n + 1, 0);
-    g.adj.reserve(tmp.size());
-    for (uint32_t i = 0; i < n; ++i) {
-        auto b = tmp.begin() + g.ptr[i], e = tmp.begin() + g.ptr[i + 1];
-        std::sort(b, e);
-        e = std::unique(b, e);
-        g.adj.insert(g.adj.end(), b, e);
-        nptr[i + 1] = g.adj.size();
-    }
+    parallel_for(n, [&](uint64_t v0, uint64_t v1) {
+        for (uint64_t i = v0; i < v1; ++i) {
+            auto b = tmp.begin() + g.ptr[i], e = tmp.begin() + g.ptr[i + 1];
+            std::sort(b, e);
+            nptr[i + 1] = (uint64_t)(std::unique(b, e) - b);
+        }
+    });
+    for (uint32_t i = 0; i < n; ++i)
+        nptr[i + 1] += nptr[i];
+    g.adj.resize(nptr[n]);
+    parallel_for(n, [&](uint64_t v0, uint64_t v1) {
+        for (uint64_t i = v0; i < v1; ++i)
+            std::copy(tmp.begin() + g.ptr[i], tmp.begin() + g.ptr[i] + (nptr[i + 1] - nptr[i]), g.adj.begin() + nptr[i]);
+    });
     g.ptr.swap(nptr);
     return g;
 }
@@ -55,27 +65,30 @@ struct Dissector {
     const double* lon;
     const OrderingOptions& opt;
     std::vector<uint32_t> label;
-    uint32_t next_tag = 1;
-    std::vector<std::vector<uint32_t>> supernodes;  // in elimination order
+    std::atomic<uint32_t> next_tag{1};
+    typedef std::vector<std::vector<uint32_t>> Nodes;   // supernodes in elimination order
 
     Dissector(const Graph& G, const double* la, const double* lo, const OrderingOptions& o)
         : g(G), lat(la), lon(lo), opt(o), label(G.ptr.size() - 1, 0)
     {
     }
 
-    void emit(std::vector<uint32_t>& v)
+    static void emit(Nodes& out, std::vector<uint32_t>& v)
     {
         if (v.empty())
             return;
         std::sort(v.begin(), v.end());
-        supernodes.emplace_back(std::move(v));
+        out.emplace_back(std::move(v));
     }
 
-    void run(std::vector<uint32_t>& verts)
+    // the two halves of a split are independent: the first levels of the recursion run them on separate threads
+    // (labels are written per vertex, tags come from an atomic counter)
+    Nodes run(std::vector<uint32_t>& verts, int depth = 0)
     {
+        Nodes out;
         if (verts.size() <= opt.leaf_stations) {
-            emit(verts);
-            return;
+            emit(out, verts);
+            return out;
         }
         // pick the wider axis (metres, roughly): x = lon * cos(mean lat), y = lat
         double la0 = 1e300, la1 = -1e300, lo0 = 1e300, lo1 = -1e300, lam = 0;
@@ -93,7 +106,7 @@ struct Dissector {
         std::nth_element(verts.begin(), verts.begin() + half, verts.end(), [&](uint32_t a, uint32_t b) {
             return key[a] < key[b] || (key[a] == key[b] && a < b);
         });
-        uint32_t tagL = next_tag++, tagR = next_tag++, tagS = next_tag++;
+        const uint32_t tagL = next_tag.fetch_add(3), tagR = tagL + 1, tagS = tagL + 2;
         for (size_t i = 0; i < verts.size(); ++i)
             label[verts[i]] = i < half ? tagL : tagR;
         // vertices with many cut edges (hubs) go straight into the separator
@@ -136,13 +149,23 @@ struct Dissector {
         }
         if (L.empty() || R.empty() || S.size() * 2 > verts.size()) {
             // degenerate split (clique-like subgraph): keep it as one dense front
-            emit(verts);
-            return;
+            emit(out, verts);
+            return out;
         }
         std::vector<uint32_t>().swap(verts);
-        run(L);
-        run(R);
-        emit(S);
+        Nodes right;
+        if (depth < 4 && L.size() + R.size() > 20000) {
+            std::thread other([&] { right = run(R, depth + 1); });
+            out = run(L, depth + 1);
+            other.join();
+        } else {
+            out = run(L, depth + 1);
+            right = run(R, depth + 1);
+        }
+        for (auto& v : right)
+            out.emplace_back(std::move(v));
+        emit(out, S);
+        return out;
     }
 };
 
@@ -198,8 +221,7 @@ std::string analyse(uint32_t nstn, const std::vector<std::pair<uint32_t, uint32_
         Dissector d(g, lat, lon, opt);
         std::vector<uint32_t> all(nstn);
         std::iota(all.begin(), all.end(), 0u);
-        d.run(all);
-        sn.swap(d.supernodes);
+        sn = d.run(all);
     }
 
     const uint32_t F = (uint32_t)sn.size();
@@ -330,25 +352,31 @@ std::string analyse(uint32_t nstn, const std::vector<std::pair<uint32_t, uint32_
 
     // ---- 5. block pattern of N in elimination order + panel destinations -----
     out.ncol_ptr.assign((size_t)nstn + 1, 0);
-    for (uint32_t p = 0; p < nstn; ++p) {
-        uint32_t v = out.stn_of_pos[p];
-        uint64_t later = 0;
-        for (uint64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e)
-            later += out.pos_of_stn[g.adj[e]] > p;
-        out.ncol_ptr[p + 1] = out.ncol_ptr[p] + 1 + later;
-    }
-    out.nrow.resize(out.ncol_ptr[nstn]);
-    for (uint32_t p = 0; p < nstn; ++p) {
-        uint32_t v = out.stn_of_pos[p];
-        uint64_t s = out.ncol_ptr[p];
-        out.nrow[s++] = p;
-        for (uint64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e) {
-            uint32_t q = out.pos_of_stn[g.adj[e]];
-            if (q > p)
-                out.nrow[s++] = q;
+    parallel_for(nstn, [&](uint64_t p0, uint64_t p1) {
+        for (uint64_t p = p0; p < p1; ++p) {
+            uint32_t v = out.stn_of_pos[p];
+            uint64_t later = 0;
+            for (uint64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e)
+                later += out.pos_of_stn[g.adj[e]] > p;
+            out.ncol_ptr[p + 1] = 1 + later;
         }
-        std::sort(out.nrow.begin() + out.ncol_ptr[p] + 1, out.nrow.begin() + out.ncol_ptr[p + 1]);
-    }
+    });
+    for (uint32_t p = 0; p < nstn; ++p)
+        out.ncol_ptr[p + 1] += out.ncol_ptr[p];
+    out.nrow.resize(out.ncol_ptr[nstn]);
+    parallel_for(nstn, [&](uint64_t p0, uint64_t p1) {
+        for (uint64_t p = p0; p < p1; ++p) {
+            uint32_t v = out.stn_of_pos[p];
+            uint64_t s = out.ncol_ptr[p];
+            out.nrow[s++] = (uint32_t)p;
+            for (uint64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e) {
+                uint32_t q = out.pos_of_stn[g.adj[e]];
+                if (q > p)
+                    out.nrow[s++] = q;
+            }
+            std::sort(out.nrow.begin() + out.ncol_ptr[p] + 1, out.nrow.begin() + out.ncol_ptr[p + 1]);
+        }
+    });
     finalize_layout(out, 1, 0);
     return std::string();
 }
@@ -470,27 +498,29 @@ void finalize_layout(Symbolic& s, int world, int rank)
     const uint64_t nslots = s.ncol_ptr[s.nstn];
     s.ndest.assign(nslots, NO_DEST);
     s.ndest_ld.assign(nslots, 0);
-    for (uint32_t p = 0; p < s.nstn; ++p) {
-        const Front& fr = s.fronts[s.front_of_pos[p]];
-        if (fr.owner != rank)
-            continue;
-        s.pos_owned[p] = 1;
-        const uint32_t own_end = fr.own_begin + fr.own_count;
-        const uint32_t* b = s.bnd.data() + fr.bnd_begin;
-        const uint64_t col = 3ull * (p - fr.own_begin);
-        for (uint64_t t = s.ncol_ptr[p]; t < s.ncol_ptr[p + 1]; ++t) {
-            uint32_t q = s.nrow[t];
-            uint64_t row;
-            if (q < own_end)
-                row = 3ull * (q - fr.own_begin);
-            else {
-                const uint32_t* it = std::lower_bound(b, b + fr.bnd_count, q);
-                row = 3ull * (fr.own_count + (uint32_t)(it - b));
+    parallel_for(s.nstn, [&](uint64_t p0, uint64_t p1) {
+        for (uint64_t p = p0; p < p1; ++p) {
+            const Front& fr = s.fronts[s.front_of_pos[p]];
+            if (fr.owner != rank)
+                continue;
+            s.pos_owned[p] = 1;
+            const uint32_t own_end = fr.own_begin + fr.own_count;
+            const uint32_t* b = s.bnd.data() + fr.bnd_begin;
+            const uint64_t col = 3ull * (p - fr.own_begin);
+            for (uint64_t t = s.ncol_ptr[p]; t < s.ncol_ptr[p + 1]; ++t) {
+                uint32_t q = s.nrow[t];
+                uint64_t row;
+                if (q < own_end)
+                    row = 3ull * (q - fr.own_begin);
+                else {
+                    const uint32_t* it = std::lower_bound(b, b + fr.bnd_count, q);
+                    row = 3ull * (fr.own_count + (uint32_t)(it - b));
+                }
+                s.ndest[t] = fr.panel_off + row * fr.ldk + col;
+                s.ndest_ld[t] = fr.ldk;
             }
-            s.ndest[t] = fr.panel_off + row * fr.ldk + col;
-            s.ndest_ld[t] = fr.ldk;
         }
-    }
+    });
 }
 
 }  // namespace gadj

@@ -123,7 +123,7 @@ void launch_push(const PushOp* ops, int nops, int, const PeerTable* pt, double* 
             for (int c = 0; c < op.cols; ++c) {
                 double* p = base + (int64_t)r * op.ld + c;
                 for (int q = 0; q < pt->nranks; ++q)
-                    if (q != pt->rank)
+                    if (q != pt->rank && q != op.skip && (op.target < 0 || q == op.target))
                         *reinterpret_cast<double*>(reinterpret_cast<char*>(p) + pt->delta[op.buf][q]) = *p;
             }
     }
