@@ -105,6 +105,7 @@ class dna_adjust {
         dnafiles::load_binary(bms_file_, msr_, bms_meta_);
         ApplyConstraints();
         ComputeStationValidity();
+        LoadAssociatedStationList(base + ".asl");
         if (a_.database_ids)
             LoadDatabaseId();
         gadj_opts o;
@@ -467,9 +468,25 @@ class dna_adjust {
             size_t b = t.find_first_not_of(" \t"), e = t.find_last_not_of(" \t");
             tok.push_back(b == std::string::npos ? std::string() : t.substr(b, e - b + 1));
         }
+        // station name -> .bst index: the station map <net>.map that dnaimport wrote (map_file.cpp:44-98, looked up by the
+        // reference at LDR:243-244) when it is there and covers the station file, else the names in the .bst records
         std::unordered_map<std::string, uint32_t> by_name;
-        for (size_t i = 0; i < stn_.size(); ++i)
-            by_name.emplace(stn_[i].stationName, (uint32_t)i);
+        {
+            const std::string map_path = a_.input_folder + "/" + a_.network_name + ".map";
+            std::vector<std::pair<std::string, uint32_t>> smap;
+            if (std::filesystem::exists(map_path)) {
+                dnafiles::load_map(map_path, smap);
+                bool usable = smap.size() == stn_.size();
+                for (const auto& e : smap)
+                    usable = usable && e.second < stn_.size();
+                if (usable)
+                    for (const auto& e : smap)
+                        by_name.emplace(e.first, e.second);
+            }
+            if (by_name.empty())
+                for (size_t i = 0; i < stn_.size(); ++i)
+                    by_name.emplace(stn_[i].stationName, (uint32_t)i);
+        }
         // discontinuity sites (AddDiscontinuitySites LDR:314-359): when dnaimport renamed stations of a discontinuity file
         // (stationName differs from stationNameOrig), a constraint given for the original name also goes to its renamed
         // sites, and a name that no longer exists is passed over instead of being an error (LDR:246-249)
@@ -907,6 +924,7 @@ class dna_adjust {
     std::vector<gadj_iter_result> iterations_;
     const std::atomic<bool>* cancel_ = nullptr;
     std::vector<uint8_t> valid_;        // station takes part in the adjustment (a measurement that is not ignored touches it)
+    size_t asl_differs_ = 0;            // stations whose <net>.asl validity disagrees with the measurement list
     std::vector<DbId> dbid_;
     std::vector<double> corrPrev_;
     std::vector<uint32_t> stnOscCount_;

@@ -76,6 +76,26 @@
         }
     }
 
+    // <net>.asl (asl_file.cpp:80-93): the station validity flags dnaimport derived (LDR:146-160 builds the parameter list
+    // from them).  When the file is there and covers the station file its flags are used for the reports; a station it
+    // calls valid that no measurement taking part touches stays out (the engine holds it by its a-priori weight only).
+    void LoadAssociatedStationList(const std::string& path)
+    {
+        if (!std::filesystem::exists(path))
+            return;
+        std::vector<dnafiles::AslEntry> asl;
+        dnafiles::load_asl(path, asl);
+        if (asl.size() != stn_.size())
+            return;   // written for another station file
+        size_t differ = 0;
+        for (size_t i = 0; i < asl.size(); ++i) {
+            const uint8_t v = asl[i].validity != 0;
+            differ += v != valid_[i];
+            valid_[i] = v && valid_[i];
+        }
+        asl_differs_ = differ;
+    }
+
     std::vector<uint32_t> CollectMeasurements(const std::vector<int32_t>* rec_block, int32_t block, bool ignored) const
     {
         std::vector<uint32_t> list;

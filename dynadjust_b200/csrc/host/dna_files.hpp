@@ -206,6 +206,103 @@ void write_binary(const std::string& path, const std::vector<Rec>& recs, BinaryM
     f.write(reinterpret_cast<const char*>(recs.data()), (std::streamsize)(sizeof(Rec) * recs.size()));
 }
 
+// ---- .asl / .map -----------------------------------------------------------------------------------
+// <net>.asl (asl_file.cpp:80-93, dnatemplatestnmsrfuncs.hpp:894-899): header, u64 count, then per station
+// { u32 assocMsrCount; u32 amlStnIndex; u16 validity } with no padding.  validity != 0 = the station takes part
+// (the reference's parameter list is the stations with validity set, network_data_loader.cpp:146-160).
+struct AslEntry {
+    uint32_t assoc_msr_count;
+    uint32_t aml_index;
+    uint16_t validity;
+};
+inline void load_asl(const std::string& path, std::vector<AslEntry>& asl)
+{
+    std::ifstream f(path, std::ios::in | std::ios::binary);
+    if (!f)
+        throw std::runtime_error("LoadFile(): An error was encountered when opening " + path + ".");
+    BinaryMeta meta;
+    read_header(f, meta);
+    uint64_t n = 0;
+    f.read(reinterpret_cast<char*>(&n), sizeof(n));
+    const std::string read_error = "LoadFile(): An error was encountered when reading from " + path + ".";
+    const std::streamoff here = f.tellg();
+    f.seekg(0, std::ios::end);
+    const std::streamoff end = f.tellg();
+    f.seekg(here, std::ios::beg);
+    if (!f || here < 0 || n > (uint64_t)(end - here) / 10)
+        throw std::runtime_error(read_error);
+    asl.resize(n);
+    for (AslEntry& e : asl) {
+        f.read(reinterpret_cast<char*>(&e.assoc_msr_count), 4);
+        f.read(reinterpret_cast<char*>(&e.aml_index), 4);
+        f.read(reinterpret_cast<char*>(&e.validity), 2);
+    }
+    if (!f)
+        throw std::runtime_error(read_error);
+}
+
+// <net>.map (map_file.cpp:44-98): header, u32 count, then { char name[31]; u32 bstIndex } sorted by name
+// (looked up by binary search for --constraints, network_data_loader.cpp:243-244)
+inline void load_map(const std::string& path, std::vector<std::pair<std::string, uint32_t>>& map)
+{
+    std::ifstream f(path, std::ios::in | std::ios::binary);
+    if (!f)
+        throw std::runtime_error("LoadFile(): An error was encountered when opening " + path + ".");
+    BinaryMeta meta;
+    read_header(f, meta);
+    uint32_t n = 0;
+    f.read(reinterpret_cast<char*>(&n), sizeof(n));
+    const std::string read_error = "LoadFile(): An error was encountered when reading from " + path + ".";
+    const std::streamoff here = f.tellg();
+    f.seekg(0, std::ios::end);
+    const std::streamoff end = f.tellg();
+    f.seekg(here, std::ios::beg);
+    if (!f || here < 0 || n > (uint64_t)(end - here) / 35)
+        throw std::runtime_error(read_error);
+    map.clear();
+    map.reserve(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        char name[32] = {0};
+        uint32_t idx = 0;
+        f.read(name, 31);
+        f.read(reinterpret_cast<char*>(&idx), 4);
+        map.emplace_back(std::string(name, strnlen(name, 31)), idx);
+    }
+    if (!f)
+        throw std::runtime_error(read_error);
+}
+
+inline void write_asl(const std::string& path, const std::vector<AslEntry>& asl, BinaryMeta meta)
+{
+    std::ofstream f(path, std::ios::out | std::ios::binary | std::ios::trunc);
+    if (!f)
+        throw std::runtime_error("WriteFile(): An error was encountered when opening " + path + ".");
+    write_header(f, meta);
+    const uint64_t n = asl.size();
+    f.write(reinterpret_cast<const char*>(&n), sizeof(n));
+    for (const AslEntry& e : asl) {
+        f.write(reinterpret_cast<const char*>(&e.assoc_msr_count), 4);
+        f.write(reinterpret_cast<const char*>(&e.aml_index), 4);
+        f.write(reinterpret_cast<const char*>(&e.validity), 2);
+    }
+}
+
+inline void write_map(const std::string& path, const std::vector<std::pair<std::string, uint32_t>>& map, BinaryMeta meta)
+{
+    std::ofstream f(path, std::ios::out | std::ios::binary | std::ios::trunc);
+    if (!f)
+        throw std::runtime_error("WriteFile(): An error was encountered when opening " + path + ".");
+    write_header(f, meta);
+    const uint32_t n = (uint32_t)map.size();
+    f.write(reinterpret_cast<const char*>(&n), sizeof(n));
+    for (const auto& e : map) {
+        char name[31] = {0};
+        std::memcpy(name, e.first.c_str(), std::min<size_t>(30, e.first.size()));
+        f.write(name, 31);
+        f.write(reinterpret_cast<const char*>(&e.second), 4);
+    }
+}
+
 // ---- .seg ------------------------------------------------------------------------------------------
 struct Segmentation {
     std::vector<std::vector<uint32_t>> isl, jsl, cml;   // per block: inner stations, junction stations, measurement firsts

@@ -391,7 +391,8 @@ struct Builder {
     }
 
     // ---- numeric factorisation ------------------------------------------------
-    void factor_level(const std::vector<uint32_t>& fl, int lv)
+    // schur: also the Schur updates of the fronts (a multi-GPU run does those of the top fronts apart, shared out)
+    void factor_level(const std::vector<uint32_t>& fl, int lv, bool schur = true)
     {
         std::vector<GemmOp> gb;
         std::vector<DiagOp> db;
@@ -462,16 +463,24 @@ struct Builder {
             flush_gemm(gb, p.factor, lv, T_RIGHT_UPDATE);
         }
         build_trtri(fl, p.factor, lv);
-        // Schur update -L21 L21^T of every front, one lower-triangular r x r product per front, scattered into the
-        // ancestors' panels through the per-column target table (multi-GPU: into this rank's replicas of the top fronts —
-        // the ranks' partial sums meet in the all-reduce before the ancestors' level)
+        if (schur)
+            schur_level(fl, lv, false);
+    }
+
+    // Schur update -L21 L21^T of every front, one lower-triangular r x r product per front, scattered into the
+    // ancestors' panels through the per-column target table (multi-GPU: into this rank's replicas of the top fronts —
+    // the ranks' partial sums meet in the all-reduce before the ancestors' level).  dist: the tiles of the products are
+    // shared out among the ranks (top fronts, whose factor every rank holds by then).
+    void schur_level(const std::vector<uint32_t>& fl, int lv, bool dist)
+    {
+        std::vector<GemmOp> gb;
         for (uint32_t fi : fl) {
             const Front& f = s.fronts[fi];
             if (!f.r)
                 continue;
             double* A = panel(f) + (size_t)f.k * f.ldk;
             add_gemm(gb, A, f.ldk, A, f.ldk, nullptr, 0, (int)f.r, (int)f.r, (int)f.k, GEMM_SCATTER | GEMM_NEG | GEMM_LOWER, 0,
-                     b.coltgt + f.bnd_begin);
+                     b.coltgt + f.bnd_begin, Share{dist ? D_SUM : D_ALL, 0});
         }
         flush_gemm(gb, p.factor, lv, T_SCHUR);
     }
@@ -500,7 +509,7 @@ struct Builder {
                 for (uint32_t fi : tl)
                     if (s.fronts[fi].owner == s.rank)
                         mine.push_back(fi);
-                factor_level(mine, (int)lv);
+                factor_level(mine, (int)lv, false);
                 for (int stage = 0; stage < 2; ++stage) {
                     for (uint32_t fi : tl) {
                         const Front& f = s.fronts[fi];
@@ -510,6 +519,9 @@ struct Builder {
                     }
                     flush_push(p.factor, (int)lv);
                 }
+                // the Schur updates of these fronts (the larger part of their factorisation flops) by all ranks together, each
+                // scattering its tiles into its own replicas of the fronts above: partial sums again, joined before their level
+                schur_level(tl, (int)lv, true);
             }
         for (auto& L : p.factor)
             p.factor_flops += L.flops;

@@ -84,3 +84,24 @@ def write_seg(path, isl, jsl, cml, bst="", bms=""):
         L.append(dash)
     with open(path, "w") as f:
         f.write("\n".join(L) + "\n")
+
+
+def write_asl(path, assoc_msr_count, aml_index, validity):
+    """<net>.asl (include/io/asl_file.cpp:80-93): header, u64 count, then {u32 assocMsrCount; u32 amlStnIndex; u16 validity}."""
+    with open(path, "wb") as f:
+        f.write(_header())
+        f.write(struct.pack("<Q", len(validity)))
+        for a, i, v in zip(assoc_msr_count, aml_index, validity):
+            f.write(struct.pack("<IIH", int(a), int(i), int(v)))
+
+
+def write_map(path, names):
+    """<net>.map (include/io/map_file.cpp:44-98): header, u32 count, then {char name[31]; u32 bstIndex} sorted by name."""
+    order = sorted(range(len(names)), key=lambda i: names[i])
+    with open(path, "wb") as f:
+        f.write(_header())
+        f.write(struct.pack("<I", len(names)))
+        for i in order:
+            nm = names[i] if isinstance(names[i], bytes) else names[i].encode()
+            f.write(nm[:30].ljust(31, b"\0"))
+            f.write(struct.pack("<I", i))

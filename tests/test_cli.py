@@ -609,3 +609,62 @@ def test_cli_phased_seg_gpu(cli_gpu, oracle, tmp_path):
 @pytest.mark.gpu
 def test_cli_apu_cor_gpu(cli_gpu, oracle, tmp_path):
     _apu_cor(cli_gpu, oracle, tmp_path)
+
+
+def test_cli_station_map_and_associated_station_list(cli_hostsim, oracle, tmp_path):
+    """<net>.map and <net>.asl as dnaimport writes them (map_file.cpp:44-98, asl_file.cpp:80-93) are read when present:
+    --constraints resolves names through the station map (LDR:243-244), and the validity flags of the .asl — one station
+    here is in the station file without any measurement — decide with the measurement list which stations are reported."""
+    stn, msr, _, _ = synth.gnss_network(60, 170, 35)
+    # a 61st station nobody measures: in the files, not in the adjustment
+    stn2 = np.zeros(61, dtype=STN_DTYPE)
+    stn2[:60] = stn
+    stn2[60] = stn[5]
+    stn2["stationName"][60] = stn2["stationNameOrig"][60] = b"LONELY"
+    _write_network(tmp_path, "am", stn2, msr)
+    names = [s.decode() for s in stn2["stationName"]]
+    dnafiles.write_map(os.path.join(tmp_path, "am.map"), names)
+    validity = np.ones(61, dtype=np.uint16)
+    validity[60] = 0
+    dnafiles.write_asl(os.path.join(tmp_path, "am.asl"), np.ones(61), np.arange(61), validity)
+    n1 = names[7]
+    r = _run(cli_hostsim, tmp_path, "am", "--constraints", f"{n1},CCC", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    stn_c = stn.copy()
+    stn_c["stationConst"][7] = b"CCC"
+    _check_outputs(oracle, tmp_path, "am", "simult", stn_c, msr, False)
+    adj = open(os.path.join(tmp_path, "am.simult.adj")).read()
+    assert "LONELY" not in adj.split("Adjusted Coordinates")[1]
+    # a station map that does not cover the station file is not used (the names in the .bst records are)
+    dnafiles.write_map(os.path.join(tmp_path, "am.map"), names[:10])
+    r = _run(cli_hostsim, tmp_path, "am", "--constraints", f"{names[40]},CCC", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    # truncated files fail loudly with the reference's wording
+    with open(os.path.join(tmp_path, "am.asl"), "r+b") as f:
+        f.truncate(100)
+    r = _run(cli_hostsim, tmp_path, "am")
+    assert r.returncode == 1 and "An error was encountered when reading from" in r.stderr
+
+
+def test_cli_gpus_option_threads(cli_hostsim, oracle, tmp_path):
+    """dnaadjust --gpus N: the ranks as threads of the command line (csrc/host/gpu_group.hpp), every collective call made by
+    all of them; outputs as from one device — simultaneous and phased, with the per-block SINEX files whose dense block matrices come
+    from the rank holding the block."""
+    stn, msr, _, _ = synth.gnss_network(900, 2700, 41)
+    _write_network(tmp_path, "mg", stn, msr)
+    r = _run(cli_hostsim, tmp_path, "mg", "--gpus", "3", "--output-adj-msr", "--output-pos-uncertainty", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    _check_outputs(oracle, tmp_path, "mg", "simult", stn, msr, True)
+    one = _run(cli_hostsim, tmp_path, "mg", "--output-adj-msr", "--output-pos-uncertainty", "--no-binary-update", "--output-folder",
+               str(tmp_path / "one"))
+    # phased over a chain of blocks, block-wise station output and per-block SINEX (dense block matrices from their holders)
+    blocks = parity.chain_blocks(len(stn), 150)
+    isl = [list(b) for b in blocks]
+    jsl, cml = [[] for _ in isl], [[] for _ in isl]
+    dnafiles.write_seg(os.path.join(tmp_path, "mg.seg"), isl, jsl, cml)
+    r = _run(cli_hostsim, tmp_path, "mg", "--phased", "--gpus", "2", "--export-sinex-file", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    _check_outputs(oracle, tmp_path, "mg", "phased", stn, msr, False)
+    assert len([f for f in os.listdir(tmp_path) if f.endswith(".snx")]) == len(blocks)
+    r = _run(cli_hostsim, tmp_path, "mg", "--gpus", "9")
+    assert r.returncode != 0 and "--gpus takes 1 to 8" in r.stderr
