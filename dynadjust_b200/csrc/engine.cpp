@@ -223,7 +223,8 @@ struct gadj_ctx {
     DevArray<TransposeOp> d_tr;
     DevArray<GatherOp> d_gather;
     const PeerTable* pt() const { return d_peers.p; }
-    std::vector<double> h_corr;
+    std::vector<double> h_corr, h_dscale;
+    uint32_t h_dscale_iteration = ~0u;
     void* ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint64_t device_bytes = 0;
     // profiling
@@ -1721,6 +1722,7 @@ static int stage_begin(gadj_ctx* c, int flags)
         c->inverse_valid = false;
         c->factor_valid = false;
         c->vcv_extracted = false;
+        c->h_dscale_iteration = ~0u;   // new equilibration factors: the host copy is stale
         ScatterParams sp;
         fill_scatter(c, sp);
         c->prof_begin(PK_OTHER);
@@ -2482,9 +2484,15 @@ int gadj_get_block_vcv(gadj_ctx* c, uint32_t block, uint32_t* nstations, uint32_
         stations[f.own_count + i] = S.stn_of_pos[S.bnd[f.bnd_begin + i]];
     const size_t k = f.k, r = f.r, m = f.m, n = m;
     // the front's panel [Z11; Z21] and the junction block Z22, gathered from the ancestors' panels like the selected inverse does
-    std::vector<double> P(m * (size_t)f.ldk), G, d(3 * (size_t)c->nstn);
+    std::vector<double> P(m * (size_t)f.ldk), G;
     dev::d2h(P.data(), c->d_panels.p + f.panel_off, P.size() * sizeof(double));
-    dev::d2h(d.data(), c->d_dscale.p, d.size() * sizeof(double));
+    // the equilibration factors of the inverse in the panels: fetched once per inverse, not once per block
+    if (c->h_dscale_iteration != c->iteration + 1 || c->h_dscale.size() != 3 * (size_t)c->nstn) {
+        c->h_dscale.resize(3 * (size_t)c->nstn);
+        dev::d2h(c->h_dscale.data(), c->d_dscale.p, c->h_dscale.size() * sizeof(double));
+        c->h_dscale_iteration = c->iteration + 1;
+    }
+    const std::vector<double>& d = c->h_dscale;
     const size_t ldg = r + (r & 1);
     DevArray<double> dG;
     DevArray<GatherOp> dops;

@@ -291,12 +291,12 @@ class Adjustment:
         dim = 3 * n.value
         packed = np.zeros(dim * (dim + 1) // 2)
         self._check(self.L.gadj_get_block_vcv(self.h, block, C.byref(n), self._p(stations), n.value, self._p(packed)))
+        # packed lower, column-major = the upper triangle walked row by row with the roles of row and column swapped
+        cols, rows = np.triu_indices(dim)
         V = np.zeros((dim, dim))
-        o = 0
-        for j in range(dim):          # packed lower, column-major
-            V[j:, j] = packed[o:o + dim - j]
-            o += dim - j
-        return stations, V + np.tril(V, -1).T
+        V[rows, cols] = packed
+        V[cols, rows] = packed
+        return stations, V
 
     def test_gemm(self, A, B, reps=1):
         A = np.ascontiguousarray(A, dtype=np.float64)

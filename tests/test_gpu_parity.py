@@ -232,18 +232,20 @@ def test_scale_properties_config_c3(gpu_lib):
     e1, q1, s1, m1 = results[1]
     assert 0.97 < s0.sigma_zero < 1.03
     assert np.sqrt(((e0 - truth) ** 2).mean()) < 0.05
-    assert np.abs(e1 - e0).max() < 1e-8
-    assert abs(s1.sigma_zero - s0.sigma_zero) < 1e-9
+    # measured agreement of the two orders on this network (tools/diag_c3.py): coordinates one ulp of 6.4e6 m (9.3e-10),
+    # sigma-zero 1e-11, station variances 6e-13 of the largest — the bars leave a factor of a few, not orders of magnitude
+    assert np.abs(e1 - e0).max() < 2e-9
+    assert abs(s1.sigma_zero - s0.sigma_zero) < 1e-10
     assert s1.dof == s0.dof and s1.measurement_params == s0.measurement_params
     dq = np.abs(q1 - q0).reshape(len(stn), -1).max(axis=1)
-    if not dq.max() < 1e-8 * np.abs(q0).max():
-        bad = np.nonzero(dq > 1e-10 * np.abs(q0).max())[0]
+    if not dq.max() < 1e-10 * np.abs(q0).max():
+        bad = np.nonzero(dq > 1e-11 * np.abs(q0).max())[0]
         np.savez(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "c3_vcv_mismatch.npz"),
                  q0=q0, q1=q1, e0=e0, e1=e1)
         raise AssertionError(f"station variances differ between the two orderings: max {dq.max():.3e} vs scale "
                              f"{np.abs(q0).max():.3e}; {len(bad)} stations off, first {bad[:20].tolist()}, last {bad[-5:].tolist()}")
     # the per-record statistics written back by the two runs agree as well
-    assert np.abs(m1["measCorr"] - m0["measCorr"]).max() < 1e-7
+    assert np.abs(m1["measCorr"] - m0["measCorr"]).max() < 1e-8
 
 
 def test_rigorous_inverse_config_c5(gpu_lib):
