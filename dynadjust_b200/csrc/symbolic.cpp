@@ -449,18 +449,43 @@ void finalize_layout(Symbolic& s, int world, int rank)
             else
                 f.owner = s.fronts[f.parent].owner;
         }
-        // a top front is factorised by the owner of its heaviest child
-        for (uint32_t fi = 0; fi < F; ++fi) {
-            Front& f = s.fronts[fi];
-            if (!f.top)
-                continue;
-            double bw = -1;
-            for (uint32_t c : children[fi])
-                if (sub[c] > bw) {
-                    bw = sub[c];
-                    f.owner = s.fronts[c].owner;
+        // A top front is assembled and its pivot panel factorised by one rank.  Level by level (the fronts of a level are
+        // factorised side by side): the heaviest front goes to the rank with the least work so far, no rank takes two
+        // fronts of a level while another has none.
+        s.rank_load.assign(world, 0.0);
+        for (uint32_t fi = 0; fi < F; ++fi)
+            if (!s.fronts[fi].top)
+                s.rank_load[s.fronts[fi].owner] += s.fronts[fi].work;
+        {
+            std::vector<double> load = s.rank_load;
+            int32_t maxlv = 0;
+            for (uint32_t fi = 0; fi < F; ++fi)
+                if (s.fronts[fi].top) {
+                    s.cut_level = std::min(s.cut_level, s.fronts[fi].level);
+                    maxlv = std::max(maxlv, s.fronts[fi].level);
                 }
-            s.cut_level = std::min(s.cut_level, f.level);
+            for (int32_t lv = s.cut_level; lv <= maxlv; ++lv) {
+                std::vector<uint32_t> fl;
+                for (uint32_t fi = 0; fi < F; ++fi)
+                    if (s.fronts[fi].top && s.fronts[fi].level == lv)
+                        fl.push_back(fi);
+                std::sort(fl.begin(), fl.end(), [&](uint32_t a, uint32_t b) {
+                    return s.fronts[a].work > s.fronts[b].work || (s.fronts[a].work == s.fronts[b].work && a < b);
+                });
+                std::vector<int> taken(world, 0);
+                for (uint32_t fi : fl) {
+                    int best = -1;
+                    const int round = *std::min_element(taken.begin(), taken.end());
+                    for (int r = 0; r < world; ++r)
+                        if (taken[r] == round && (best < 0 || load[r] < load[best]))
+                            best = r;
+                    Front& f = s.fronts[fi];
+                    f.owner = best;
+                    taken[best]++;
+                    const double k = f.k, r = f.r;
+                    load[best] += k * k * k / 3.0 + k * k * r;   // pivot panel + W; the Schur update and the inverse are shared out
+                }
+            }
         }
     }
     // storage: every top front first, in front order — the same offsets on every rank, so that a tile finished by one rank

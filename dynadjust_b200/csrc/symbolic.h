@@ -64,6 +64,7 @@ struct Symbolic {
     int32_t cut_level = 1 << 30;               // first level that holds a top front
     std::vector<uint8_t> pos_owned;             // per elimination position: its front is owned by this rank
     double my_factor_flops = 0, my_inverse_flops = 0;
+    std::vector<double> rank_load;              // per rank: work (flops) of the fronts in its subtrees
 };
 
 struct OrderingOptions {
