@@ -381,6 +381,15 @@ def run_engine(args):
     prof = runner.profile_read(reset=True)
     runner.profile_enable(False)
     clocks = clk.summary()
+    per_rank = None
+    if world > 1:
+        # every rank's device time per phase and in its GEMM / exchange kernels: where the ranks wait for each other
+        mine = torch.tensor([phase["assemble"], phase["factor"], phase["solve"], phase["inverse"], prof.ms_gemm, prof.ms_other, prof.ms_diag],
+                            dtype=torch.float64, device="cuda") / args.steps
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        per_rank = [dict(zip(("assemble", "factor", "solve", "inverse", "gemm_kernels", "exchange_and_other_kernels", "diag_kernels"),
+                             [round(float(v), 3) for v in p.cpu()])) for p in parts]
     ms_step = reduce_max((t1 - t0) * 1e3 / args.steps)
     device_ms = reduce_max(sum(phase.values()) / args.steps)       # CUDA events around the four phases, max over ranks
 
@@ -486,6 +495,7 @@ def run_engine(args):
                                             other=prof.ms_other / args.steps),
                     gflops=alg_flops / ms_step / 1e6, parity=parity_rec, rms_vs_truth_m=rms)
         if world > 1:
+            line["per_rank_ms"] = per_rank
             line["nvlink"] = dict(bytes_read_per_step=info.nvlink_read_bytes, bytes_written_per_step=info.nvlink_write_bytes,
                                   barriers_per_step=int(info.barriers_per_step),
                                   note="rank 0: all-reduce slices read from / written to the peers' replicas + finished tiles stored into the "

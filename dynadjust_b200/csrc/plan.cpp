@@ -62,10 +62,9 @@ struct Builder {
     std::vector<size_t> woff;   // per front: offset of its W block in b.wbuf (Wt follows at + wblock)
 
     // per op of a batch: how its tiles are shared out among the ranks (multi-GPU, replicated top fronts)
-    enum Dist { D_ALL = 0, D_SUM = 1, D_LOAD = 2 };
+    enum Dist { D_ALL = 0, D_SUM = 1 };
     struct Share {
-        int dist;   // D_ALL: this rank runs every tile; D_SUM: tile (tm, tn) goes to rank (tm + tn) % world;
-                    // D_LOAD: tile (tm, tn) goes to the rank picked by tile_rank(): ranks whose subtrees hold less work take more
+        int dist;   // D_ALL: this rank runs every tile; D_SUM: tile (tm, tn) goes to rank (tm + tn) % world
         int push;   // the finished tiles are pushed into every peer's replica: McBuf of C in bits 0..7, of Ct in bits 8..15
     };
     std::vector<Share> share;   // parallel to the pending GEMM batch
@@ -111,54 +110,6 @@ struct Builder {
     }
     bool multi() const { return s.world > 1; }
 
-    // Shares of the top fronts' selected-inverse tiles.  The inverse runs the top fronts first and the subtrees after,
-    // so a rank whose subtrees hold less work can take more of the shared tiles and everybody finishes together:
-    // share_q = (mean subtree work + W_top / world - subtree work of q) / W_top, clipped at zero.  cum[] are the
-    // cumulative shares; a tile picks its rank through a low-discrepancy sequence over its coordinates, so that every
-    // rank computes the same map and the shares are met within a few tiles.
-    std::vector<double> cum;
-    void build_shares()
-    {
-        cum.assign(s.world, 1.0);
-        if (!multi())
-            return;
-        double wtop = 0, mean = 0;
-        for (const Front& f : s.fronts)
-            if (f.top) {
-                const double k = f.k, r = f.r;
-                wtop += 2.0 * k * k * k / 3.0 + 2.0 * k * k * r + 2.0 * k * r * r + 2.0 * k * k * r;
-            }
-        std::vector<double> load(s.world, 0.0);
-        if ((int)s.rank_load.size() == s.world)
-            for (int q = 0; q < s.world; ++q)
-                load[q] = s.rank_load[q] * (2.0 / 3.0);   // the inverse is about two thirds of a front's work
-        for (double l : load)
-            mean += l / s.world;
-        std::vector<double> share(s.world, 1.0 / s.world);
-        if (wtop > 0 && !getenv("GADJ_MG_EQUAL_SHARES")) {
-            double tot = 0;
-            for (int q = 0; q < s.world; ++q) {
-                share[q] = std::max(0.0, (mean + wtop / s.world - load[q]) / wtop);
-                tot += share[q];
-            }
-            for (double& x : share)
-                x = tot > 0 ? x / tot : 1.0 / s.world;
-        }
-        double c = 0;
-        for (int q = 0; q < s.world; ++q) {
-            c += share[q];
-            cum[q] = c;
-        }
-        cum[s.world - 1] = 2.0;
-    }
-    int tile_rank(int tm, int tn, int tiles_n) const
-    {
-        const double u = std::fmod(0.6180339887498949 * (double)((int64_t)tm * tiles_n + tn), 1.0);   // golden-ratio sequence over the tiles
-        int q = 0;
-        while (q + 1 < s.world && u >= cum[q])
-            ++q;
-        return q;
-    }
     void add_barrier(std::vector<Launch>& out, int level)
     {
         if (!multi())
@@ -306,8 +257,6 @@ struct Builder {
                     ++all_tiles;
                     if (sh.dist == D_SUM && (tm + tn) % s.world != s.rank)
                         continue;   // another rank's tile
-                    if (sh.dist == D_LOAD && tile_rank(tm, tn, op.tiles_n) != s.rank)
-                        continue;
                     ++my_tiles;
                     p.tiles.push_back(GemmTile{opi, (uint16_t)tm, (uint16_t)tn});
                     if (sh.push) {
@@ -667,7 +616,7 @@ struct Builder {
     {
         std::vector<GemmOp> gb;
         std::vector<GatherOp> gab;
-        const int D = dist ? D_LOAD : D_ALL;
+        const int D = dist ? D_SUM : D_ALL;
         // no clearing of the workspace: every tile that is read has been written before (the K-range
         // flags keep the triangular products inside the written tiles)
         for (size_t i = 0; i < chunk.size(); ++i) {
@@ -892,7 +841,6 @@ std::string build_plan(const Symbolic& s, const PlanBuffers& b, Plan& p)
         }
     }
     Builder B(s, b, p);
-    B.build_shares();
     B.build_factor();
     B.build_solves();
     B.build_selinv();
