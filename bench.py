@@ -238,7 +238,9 @@ def cpu_sample(key, args, threads=None):
         wall = time.perf_counter() - t
         value = 1e3 * r.seconds_solve / nblocks * (cfg["n_stations"] / 1000)
         sample = (f"phased path (forward + reverse + combination, one iteration) on the first {nblocks} blocks of the C3 network: "
-                  f"{wall:.1f} s of CPU work, {r.seconds_solve / nblocks:.2f} s per block x {cfg['n_stations'] // 1000} blocks")
+                  f"{wall:.1f} s of CPU work, {r.seconds_solve / nblocks:.2f} s per block x {cfg['n_stations'] // 1000} blocks "
+                  "(a lower bound: the last block of the sample carries no junction stations and the two end blocks need no "
+                  "combination pass; the full run is quoted beside it)")
     else:
         blocks, block_stations = args.sample_blocks, 150
         bps = cfg["n_baselines"] / cfg["n_stations"]

@@ -1,9 +1,9 @@
 """Multi-GPU host side: one rank per GPU, the dissection tree sharded by subtree.
 
 All of the exchange between the ranks happens on the devices (csrc/plan.cpp, kernels_gemm.cu, kernels_front.cu): the
-fronts above the subtree cut are replicated, their tiles shared out among the ranks, finished tiles stored into every
-replica over NVLink peer mappings from the GEMM epilogue, partial Schur sums joined by an all-reduce kernel, and the
-ranks meet at device-side barriers.  The host only has to pass the ranks' buffer handles around once after
+fronts above the subtree cut are replicated; each is factorised by an owner rank, its Schur update and inverse tiles
+shared out among the ranks, finished blocks copied into every replica over NVLink peer mappings by a push kernel,
+partial Schur sums joined by an all-reduce kernel, and the ranks meet at device-side barriers.  The host only has to pass the ranks' buffer handles around once after
 ``prepare`` — that is all this module does, with two transports:
 
 * ``TorchExchange``: one process per GPU under torchrun (``torch.distributed`` all-gather of the handle records;

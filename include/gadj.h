@@ -191,8 +191,9 @@ int gadj_get_rhs(gadj_ctx* c, double* w /* 3*nstn */);
  * out tile by tile, and the exchange happens inside the kernels over NVLink peer mappings:
  *   - the ranks' partial Schur sums of a top front meet in an all-reduce kernel (each rank reduces a slice, reading the
  *     peers' replicas, and stores the sum into every replica);
- *   - a rank that finishes a tile of a top front (panel, pivot-tile inverse, inverse panel) stores it into every
- *     replica from the GEMM epilogue;
+ *   - each top front is factorised by one owner rank (owners spread by load, level by level) and its finished panel
+ *     and pivot-tile inverses are copied into every replica by a push kernel (scatter to the peers, then forward);
+ *     its Schur update and its inverse panels are computed tile-share by tile-share and pushed the same way;
  *   - the ranks meet at device-side barriers (counters in peer memory), never on the host.
  * This is the sum form of the reference's junction-station carry between blocks (ADJ:998-1281, 3196-3333) and of
  * its thread pool over blocks (dnaadjust-multi.cpp:92-310).  Call sequence per rank:
