@@ -500,7 +500,7 @@ def run_engine(args):
             line["per_rank_ms"] = per_rank
             line["nvlink"] = dict(bytes_read_per_step=info.nvlink_read_bytes, bytes_written_per_step=info.nvlink_write_bytes,
                                   barriers_per_step=int(info.barriers_per_step),
-                                  note="rank 0: all-reduce slices read from / written to the peers' replicas + finished tiles stored into the "
+                                  note="rank 0: all-reduce slices read from / written to the peers' replicas + finished blocks pushed into the "
                                        "peers' replicas, per iteration (factor + solve + inverse), from the launch plan")
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_sample(args.workload, args)
