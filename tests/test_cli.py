@@ -225,13 +225,13 @@ def _apu_cor(exe, oracle, tmp_path):
     assert seen == n * (n - 1) // 2
 
 
-def test_cli_constraints(cli_hostsim, oracle, tmp_path):
+def _constraints(exe, oracle, tmp_path):
     """--constraints "name,CCC,..." (network_data_loader.cpp:211-263): the override reaches the solve; bad names and
     bad codes are errors with the reference's wording."""
     stn, msr, _, _ = synth.gnss_network(60, 170, 35)
     _write_network(tmp_path, "cn", stn, msr)
     n1, n2 = stn["stationName"][7].decode(), stn["stationName"][11].decode()
-    r = _run(cli_hostsim, tmp_path, "cn", "--constraints", f"{n1},ccc,{n2},FFC", "--no-binary-update")
+    r = _run(exe, tmp_path, "cn", "--constraints", f"{n1},ccc,{n2},FFC", "--no-binary-update")
     assert r.returncode == 0, r.stderr
     stn_c = stn.copy()
     stn_c["stationConst"][7] = b"CCC"
@@ -240,9 +240,9 @@ def test_cli_constraints(cli_hostsim, oracle, tmp_path):
     adj = open(os.path.join(tmp_path, "cn.simult.adj")).read()
     assert "Station constraints:" in adj
     rows = _station_table(adj)
-    r = _run(cli_hostsim, tmp_path, "cn", "--constraints", "NOSUCH,CCC")
+    r = _run(exe, tmp_path, "cn", "--constraints", "NOSUCH,CCC")
     assert r.returncode == 1 and "is not in the stations map" in r.stderr
-    r = _run(cli_hostsim, tmp_path, "cn", "--constraints", f"{n1},CXC")
+    r = _run(exe, tmp_path, "cn", "--constraints", f"{n1},CXC")
     assert r.returncode == 1 and "Invalid station constraint" in r.stderr
     # discontinuity sites (LDR:314-359): dnaimport renamed two stations of a discontinuity file; a constraint given for the
     # original name reaches the renamed sites, and the original name itself (no longer a station) is passed over
@@ -250,7 +250,7 @@ def test_cli_constraints(cli_hostsim, oracle, tmp_path):
     stn_d["stationNameOrig"][20] = stn_d["stationNameOrig"][21] = b"SITE"
     stn_d["stationName"][20], stn_d["stationName"][21] = b"SITE_20100101", b"SITE_20150101"
     _write_network(tmp_path, "cd", stn_d, msr)
-    r = _run(cli_hostsim, tmp_path, "cd", "--constraints", f"SITE,CCF,{n1},CCC", "--no-binary-update")
+    r = _run(exe, tmp_path, "cd", "--constraints", f"SITE,CCF,{n1},CCC", "--no-binary-update")
     assert r.returncode == 0, r.stderr
     stn_c = stn_d.copy()
     stn_c["stationConst"][[20, 21]] = b"CCF"
@@ -258,7 +258,16 @@ def test_cli_constraints(cli_hostsim, oracle, tmp_path):
     _check_outputs(oracle, tmp_path, "cd", "simult", stn_c, msr, False)
 
 
-def test_cli_block_outputs(cli_hostsim, oracle, tmp_path):
+def test_cli_constraints_hostsim(cli_hostsim, oracle, tmp_path):
+    _constraints(cli_hostsim, oracle, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_constraints_gpu(cli_gpu, oracle, tmp_path):
+    _constraints(cli_gpu, oracle, tmp_path)
+
+
+def _block_outputs(exe, oracle, tmp_path):
     """--output-stn-blocks (one station table per .seg block) and --block1-phased (only block 1 is reported, no global
     test; PRN:535-595, ADJ:7140-7147).  Every block is rigorous here, so the printed values are the simultaneous ones."""
     stn, msr, _, _ = synth.gnss_network(120, 360, 12)
@@ -268,7 +277,7 @@ def test_cli_block_outputs(cli_hostsim, oracle, tmp_path):
     dnafiles.write_seg(os.path.join(tmp_path, "blk.seg"), isl, jsl, [[] for _ in isl])
     ref = oracle.adjust_simultaneous(stn.copy(), msr.copy(), want_vcv=True)
     est = ref["est"].reshape(-1, 3)
-    r = _run(cli_hostsim, tmp_path, "blk", "--phased", "--output-stn-blocks", "--no-binary-update")
+    r = _run(exe, tmp_path, "blk", "--phased", "--output-stn-blocks", "--no-binary-update")
     assert r.returncode == 0, r.stderr
     adj = open(os.path.join(tmp_path, "blk.phased.adj")).read()
     parts = re.split(r"^Block (\d+)$", adj.split("SOLUTION")[1], flags=re.M)
@@ -291,22 +300,31 @@ def test_cli_block_outputs(cli_hostsim, oracle, tmp_path):
     for b_ in range(len(rec)):
         cml[max(blk_of(int(rec["station1"][b_, 0])), blk_of(int(rec["station2"][b_, 0])))].append(3 * b_)
     dnafiles.write_seg(os.path.join(tmp_path, "blk.seg"), isl, jsl, cml)
-    r = _run(cli_hostsim, tmp_path, "blk", "--phased", "--output-adj-msr", "--output-msr-blocks", "--no-binary-update")
+    r = _run(exe, tmp_path, "blk", "--phased", "--output-adj-msr", "--output-msr-blocks", "--no-binary-update")
     assert r.returncode == 0, r.stderr
     adj = open(os.path.join(tmp_path, "blk.phased.adj")).read()
     parts = re.split(r"^Block (\d+)$", adj.split("SOLUTION")[1].split("Adjusted Coordinates")[0], flags=re.M)
     counts = [len([l for l in parts[2 * b_ + 2].splitlines() if l.startswith("G ")]) for b_ in range(len(isl))]
     assert counts == [3 * len(c) for c in cml] and sum(counts) == len(msr)
-    r = _run(cli_hostsim, tmp_path, "blk", "--block1-phased", "--output-adj-msr", "--no-binary-update")
+    r = _run(exe, tmp_path, "blk", "--block1-phased", "--output-adj-msr", "--no-binary-update")
     assert r.returncode == 0, r.stderr
     adj = open(os.path.join(tmp_path, "blk.phased-block1.adj")).read()
     assert len([l for l in adj.splitlines() if l.startswith("G ")]) == 3 * len(cml[0])
-    r = _run(cli_hostsim, tmp_path, "blk", "--block1-phased", "--no-binary-update")
+    r = _run(exe, tmp_path, "blk", "--block1-phased", "--no-binary-update")
     assert r.returncode == 0, r.stderr
     adj = open(os.path.join(tmp_path, "blk.phased-block1.adj")).read()
     assert "Chi-Square test" not in adj and "Rigorous Sigma Zero" in adj
     rows = _station_table(adj)
     assert sorted(rows) == sorted(stn["stationName"][i].decode() for i in set(isl[0]) | set(jsl[0]))
+
+
+def test_cli_block_outputs_hostsim(cli_hostsim, oracle, tmp_path):
+    _block_outputs(cli_hostsim, oracle, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_block_outputs_gpu(cli_gpu, oracle, tmp_path):
+    _block_outputs(cli_gpu, oracle, tmp_path)
 
 
 def _golden_gnss_text(exe, tmp_path):
@@ -539,7 +557,7 @@ def test_cli_sinex_gpu(cli_gpu, oracle, tmp_path):
     _sinex(cli_gpu, oracle, tmp_path)
 
 
-def test_cli_type_b_uncertainties(cli_hostsim, oracle, tmp_path):
+def _type_b_uncertainties(exe, oracle, tmp_path):
     """--type-b-sd-global / --type-b-sd-file (ADJ:10231-10323, PRN:4000-4029): type B variances (e, n, up) added to the
     printed station uncertainties; site-specific values from the file override the global ones."""
     stn, msr, _, _ = synth.gnss_network(40, 110, 52)
@@ -548,7 +566,7 @@ def test_cli_type_b_uncertainties(cli_hostsim, oracle, tmp_path):
     s7 = stn["stationName"][7].decode()
     with open(tbu, "w") as f:
         f.write("!#=DNA 1.00 TBU\n* site-specific type B uncertainties\n%-20s%-13s%-13s%-13s\nNOTINNET            1.0 1.0 1.0\n" % (s7, "0.030", "0.040", "0.050"))
-    r = _run(cli_hostsim, tmp_path, "tb", "--type-b-sd-global", "0.010,0.010,0.020", "--type-b-sd-file", tbu, "--output-pos-uncertainty",
+    r = _run(exe, tmp_path, "tb", "--type-b-sd-global", "0.010,0.010,0.020", "--type-b-sd-file", tbu, "--output-pos-uncertainty",
              "--no-binary-update")
     assert r.returncode == 0, r.stderr
     stn_o = stn.copy()
@@ -564,8 +582,17 @@ def test_cli_type_b_uncertainties(cli_hostsim, oracle, tmp_path):
         sd = np.sqrt(np.diag(q) + tb ** 2 + np.array([0, 0, float(stn["geoidSepUnc"][i]) ** 2]))
         assert np.abs(np.array(rows[stn["stationName"][i].decode()][7:10]) - sd).max() < 1e-4
     assert "Type B uncertainties:" in open(os.path.join(tmp_path, "tb.simult.apu")).read()
-    r = _run(cli_hostsim, tmp_path, "tb", "--type-b-sd-global", "0.01,abc")
+    r = _run(exe, tmp_path, "tb", "--type-b-sd-global", "0.01,abc")
     assert r.returncode == 1 and "is not a number" in r.stderr
+
+
+def test_cli_type_b_uncertainties_hostsim(cli_hostsim, oracle, tmp_path):
+    _type_b_uncertainties(cli_hostsim, oracle, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_type_b_uncertainties_gpu(cli_gpu, oracle, tmp_path):
+    _type_b_uncertainties(cli_gpu, oracle, tmp_path)
 
 
 def test_cli_apu_cor_hostsim(cli_hostsim, oracle, tmp_path):
@@ -611,7 +638,7 @@ def test_cli_apu_cor_gpu(cli_gpu, oracle, tmp_path):
     _apu_cor(cli_gpu, oracle, tmp_path)
 
 
-def test_cli_station_map_and_associated_station_list(cli_hostsim, oracle, tmp_path):
+def _station_map_and_asl(exe, oracle, tmp_path):
     """<net>.map and <net>.asl as dnaimport writes them (map_file.cpp:44-98, asl_file.cpp:80-93) are read when present:
     --constraints resolves names through the station map (LDR:243-244), and the validity flags of the .asl — one station
     here is in the station file without any measurement — decide with the measurement list which stations are reported."""
@@ -628,7 +655,7 @@ def test_cli_station_map_and_associated_station_list(cli_hostsim, oracle, tmp_pa
     validity[60] = 0
     dnafiles.write_asl(os.path.join(tmp_path, "am.asl"), np.ones(61), np.arange(61), validity)
     n1 = names[7]
-    r = _run(cli_hostsim, tmp_path, "am", "--constraints", f"{n1},CCC", "--no-binary-update")
+    r = _run(exe, tmp_path, "am", "--constraints", f"{n1},CCC", "--no-binary-update")
     assert r.returncode == 0, r.stderr
     stn_c = stn.copy()
     stn_c["stationConst"][7] = b"CCC"
@@ -637,13 +664,22 @@ def test_cli_station_map_and_associated_station_list(cli_hostsim, oracle, tmp_pa
     assert "LONELY" not in adj.split("Adjusted Coordinates")[1]
     # a station map that does not cover the station file is not used (the names in the .bst records are)
     dnafiles.write_map(os.path.join(tmp_path, "am.map"), names[:10])
-    r = _run(cli_hostsim, tmp_path, "am", "--constraints", f"{names[40]},CCC", "--no-binary-update")
+    r = _run(exe, tmp_path, "am", "--constraints", f"{names[40]},CCC", "--no-binary-update")
     assert r.returncode == 0, r.stderr
     # truncated files fail loudly with the reference's wording
     with open(os.path.join(tmp_path, "am.asl"), "r+b") as f:
         f.truncate(100)
-    r = _run(cli_hostsim, tmp_path, "am")
+    r = _run(exe, tmp_path, "am")
     assert r.returncode == 1 and "An error was encountered when reading from" in r.stderr
+
+
+def test_cli_station_map_and_associated_station_list_hostsim(cli_hostsim, oracle, tmp_path):
+    _station_map_and_asl(cli_hostsim, oracle, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_station_map_and_associated_station_list_gpu(cli_gpu, oracle, tmp_path):
+    _station_map_and_asl(cli_gpu, oracle, tmp_path)
 
 
 def test_cli_gpus_option_threads(cli_hostsim, oracle, tmp_path):

@@ -352,7 +352,7 @@ def test_cli_project_file_and_short_options(cli_hostsim, tmp_path):
     assert r.returncode == 1 and "unrecognised option" in r.stderr
 
 
-def test_cli_report_results(cli_hostsim, tmp_path):
+def _report_results(exe, tmp_path):
     """--report-results (WRAP:607-614; SerialiseAdjustedVarianceMatrices ADJ:6770-6799): after an adjustment has updated the
     binary files and written <net>-rva.mtx / <net>-pam.mtx, every report is printed again without solving — same numbers,
     other layout options allowed."""
@@ -362,13 +362,13 @@ def test_cli_report_results(cli_hostsim, tmp_path):
     msr["scale4"][g[:30]] = 2.5                    # variance scalars on some baselines: applied once, on the first run only
     _write_network(tmp_path, "rr", stn, msr)
     flags = ["--output-adj-msr", "--output-pos-uncertainty", "--output-corrections-file", "--output-tstat-adj-msr", "--stn-corrections"]
-    r = _run(cli_hostsim, tmp_path, "rr", *flags)
+    r = _run(exe, tmp_path, "rr", *flags)
     assert r.returncode == 0, r.stderr
     first = {e: open(os.path.join(tmp_path, "rr.simult." + e)).read() for e in ("adj", "xyz", "apu", "cor")}
     for e in first:
         os.remove(os.path.join(tmp_path, "rr.simult." + e))
     assert os.path.getsize(os.path.join(tmp_path, "rr-rva.mtx")) > 72 * 50 and os.path.exists(os.path.join(tmp_path, "rr-pam.mtx"))
-    r = _run(cli_hostsim, tmp_path, "rr", "--report-results", *flags)
+    r = _run(exe, tmp_path, "rr", "--report-results", *flags)
     assert r.returncode == 0 and "Report last adjustment results" in r.stdout, r.stderr
     again = {e: open(os.path.join(tmp_path, "rr.simult." + e)).read() for e in ("adj", "xyz", "apu", "cor")}
     assert "Printing results of last adjustment only" in again["adj"] and "ITERATION" not in again["adj"]
@@ -395,7 +395,7 @@ def test_cli_report_results(cli_hostsim, tmp_path):
         assert re.findall(r"^" + label + r".*$", again["adj"], re.M) == re.findall(r"^" + label + r".*$", first["adj"], re.M)
     # a second adjustment starts from the files the first one updated (metadata `reduced`): measured values are restored
     # from preAdjMeas, geoid / deflection reductions and variance scalars are not applied twice (ADJ:296, 3913-3935)
-    r = _run(cli_hostsim, tmp_path, "rr", *flags)
+    r = _run(exe, tmp_path, "rr", *flags)
     assert r.returncode == 0, r.stderr
     second = open(os.path.join(tmp_path, "rr.simult.adj")).read()
     sig = lambda t: float(re.findall(r"^Rigorous Sigma Zero\s+(\S+)", t, re.M)[-1])
@@ -403,18 +403,27 @@ def test_cli_report_results(cli_hostsim, tmp_path):
     same([l.replace("*", " ") for l in body(second, "Adjusted Measurements")], [l.replace("*", " ") for l in body(first["adj"], "Adjusted Measurements")],
          loose=True)
     # baselines in east / north / up need the full precision of the adjusted baselines: -pam.mtx
-    r = _run(cli_hostsim, tmp_path, "rr", "--output-adj-msr", "--output-adj-gnss-units", "1", "--no-binary-update")
+    r = _run(exe, tmp_path, "rr", "--output-adj-msr", "--output-adj-gnss-units", "1", "--no-binary-update")
     assert r.returncode == 0, r.stderr
     enu = body(open(os.path.join(tmp_path, "rr.simult.adj")).read(), "Adjusted Measurements")
-    r = _run(cli_hostsim, tmp_path, "rr", "--max-iterations", "0", "--output-adj-msr", "--output-adj-gnss-units", "1")
+    r = _run(exe, tmp_path, "rr", "--max-iterations", "0", "--output-adj-msr", "--output-adj-gnss-units", "1")
     assert r.returncode == 0, r.stderr
     # (the run above started from the adjusted files: same solution to rounding)
     same([l.replace("*", " ") for l in body(open(os.path.join(tmp_path, "rr.simult.adj")).read(), "Adjusted Measurements")],
          [l.replace("*", " ") for l in enu])
     # without the files: a clear error
     os.remove(os.path.join(tmp_path, "rr-rva.mtx"))
-    r = _run(cli_hostsim, tmp_path, "rr", "--report-results")
+    r = _run(exe, tmp_path, "rr", "--report-results")
     assert r.returncode == 1 and "Run an adjustment first" in r.stderr
+
+
+def test_cli_report_results_hostsim(cli_hostsim, tmp_path):
+    _report_results(cli_hostsim, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_report_results_gpu(cli_gpu, tmp_path):
+    _report_results(cli_gpu, tmp_path)
 
 
 def test_cli_output_json(cli_hostsim, tmp_path):
@@ -468,13 +477,13 @@ def test_cli_output_json(cli_hostsim, tmp_path):
     assert set(cor[1]["DnaStation"]["Corrections"]) == {"dE", "dN", "dUp"} and len(cor) == len(stn) + 1
 
 
-def test_cli_non_convergence_and_suspect_summary(cli_hostsim, tmp_path):
+def _non_convergence(exe, tmp_path):
     """An adjustment that runs out of iterations reports its iterations and "Failed to converge" only — no statistics, no
     tables (WRAP:1386-1390) — and still exits 0; a converged one lists the measurements beyond the critical n-statistic on
     the console (PrintSuspectMeasurementSummary ADJ:7652-7779)."""
     stn, msr, _, _ = synth.gnss_network(40, 110, 3)
     _write_network(tmp_path, "nc", stn, msr)
-    r = _run(cli_hostsim, tmp_path, "nc", "--max-iterations", "1", "--output-adj-msr")
+    r = _run(exe, tmp_path, "nc", "--max-iterations", "1", "--output-adj-msr")
     assert r.returncode == 0 and "failed to converge after 1 iteration" in r.stdout, r.stderr
     text = open(os.path.join(tmp_path, "nc.simult.adj")).read()
     assert re.search(r"^SOLUTION\s+Failed to converge", text, re.M) and len(re.findall(r"^ITERATION", text, re.M)) == 1
@@ -483,7 +492,7 @@ def test_cli_non_convergence_and_suspect_summary(cli_hostsim, tmp_path):
     back = dnafiles.read_binary(os.path.join(tmp_path, "nc.bst"), stn.dtype)
     back = back[0] if isinstance(back, tuple) else back
     assert np.array_equal(back["currentLatitude"], stn["currentLatitude"])      # the binary files are left as they were
-    r = _run(cli_hostsim, tmp_path, "nc", "--output-adj-msr")
+    r = _run(exe, tmp_path, "nc", "--output-adj-msr")
     assert r.returncode == 0, r.stderr
     text = open(os.path.join(tmp_path, "nc.simult.adj")).read()
     outliers = int(re.search(r"\((\d+) potential outlier", text).group(1))
@@ -496,7 +505,16 @@ def test_cli_non_convergence_and_suspect_summary(cli_hostsim, tmp_path):
     assert ns == sorted(ns, reverse=True) and min(ns) > 1.95
 
 
-def test_cli_database_ids(cli_hostsim, tmp_path):
+def test_cli_non_convergence_and_suspect_summary_hostsim(cli_hostsim, tmp_path):
+    _non_convergence(cli_hostsim, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_non_convergence_and_suspect_summary_gpu(cli_gpu, tmp_path):
+    _non_convergence(cli_gpu, tmp_path)
+
+
+def _database_ids(exe, tmp_path):
     """--output-database-ids (LoadDatabaseId ADJ:2211-2276, PrintMeasurementDatabaseID PRN:239-263): the measurement id of
     <net>.dbid beside every row, the cluster id as well for D G X Y; one list in file order whatever --output-msr-blocks says."""
     stn, msr, _ = _network()
@@ -506,7 +524,7 @@ def test_cli_database_ids(cli_hostsim, tmp_path):
     ids["m"], ids["c"], ids["ms"], ids["cs"] = 100000 + np.arange(n), 5000 + msr["clusterID"], 1, 1
     with open(os.path.join(tmp_path, "db.dbid"), "wb") as f:
         f.write(np.uint32(n).tobytes() + ids.tobytes())
-    r = _run(cli_hostsim, tmp_path, "db", "--output-adj-msr", "--output-database-ids", "--no-binary-update")
+    r = _run(exe, tmp_path, "db", "--output-adj-msr", "--output-database-ids", "--no-binary-update")
     assert r.returncode == 0, r.stderr
     head, body = _tables(open(os.path.join(tmp_path, "db.simult.adj")).read(), "Adjusted Measurements")[-1]
     assert head.split()[-4:] == ["Meas.", "ID", "Clust.", "ID"]
@@ -531,8 +549,17 @@ def test_cli_database_ids(cli_hostsim, tmp_path):
         k += 1
     assert k == len(used)
     os.remove(os.path.join(tmp_path, "db.dbid"))
-    r = _run(cli_hostsim, tmp_path, "db", "--output-adj-msr", "--output-database-ids", "--no-binary-update")
+    r = _run(exe, tmp_path, "db", "--output-adj-msr", "--output-database-ids", "--no-binary-update")
     assert r.returncode == 1 and "dbid" in r.stderr
+
+
+def test_cli_database_ids_hostsim(cli_hostsim, tmp_path):
+    _database_ids(cli_hostsim, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_database_ids_gpu(cli_gpu, tmp_path):
+    _database_ids(cli_gpu, tmp_path)
 
 
 def test_cli_writes_project_file(cli_hostsim, tmp_path):
@@ -625,7 +652,7 @@ def test_cli_nstat_sort_in_alternate_units(cli_hostsim, tmp_path):
         assert all(a >= b - 0.0051 for a, b in zip(big, big[1:])), units
 
 
-def test_cli_accepts_the_reference_ci_command_lines(cli_hostsim, tmp_path):
+def _reference_ci_command_lines(exe, tmp_path):
     """Every option set the reference's CI drives dnaadjust with (CMakeLists.txt:1046-1963) runs to completion here on a
     mixed network; the ones its CI expects to fail, fail."""
     import shlex
@@ -670,17 +697,28 @@ def test_cli_accepts_the_reference_ci_command_lines(cli_hostsim, tmp_path):
     ]
     for cmd in ok:
         fresh()
-        r = _run(cli_hostsim, tmp_path, "ci", *shlex.split(cmd))
+        r = _run(exe, tmp_path, "ci", *shlex.split(cmd))
         assert r.returncode == 0, (cmd, r.stderr)
     # the last run left updated binaries and the .mtx files: report mode on them (adjust-dbid-04 of the reference)
-    r = _run(cli_hostsim, tmp_path, "ci", *shlex.split(f'--report-results --output-adj-msr --output-pos-uncertainty --output-apu-vcv-units 1 --constraints "{name},CCC"'))
+    r = _run(exe, tmp_path, "ci", *shlex.split(f'--report-results --output-adj-msr --output-pos-uncertainty --output-apu-vcv-units 1 --constraints "{name},CCC"'))
     assert r.returncode == 0, r.stderr
-    r = subprocess.run([cli_hostsim, "-p", os.path.join(tmp_path, "ci.dnaproj")], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe, "-p", os.path.join(tmp_path, "ci.dnaproj")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     for cmd in ('ci --constraints "no-name,CCC"', f'ci --constraints "{name},AAA"', "-x", "-p ./nofile.dnaproj", "--phased", "missing"):
-        r = subprocess.run([cli_hostsim, *shlex.split(cmd), "--input-folder", str(tmp_path), "--output-folder", str(tmp_path)], capture_output=True, text=True,
+        r = subprocess.run([exe, *shlex.split(cmd), "--input-folder", str(tmp_path), "--output-folder", str(tmp_path)], capture_output=True, text=True,
                            timeout=600)
         assert r.returncode == 1 and "Error" in r.stderr, cmd
     for cmd in ("-h", "--version", "--help-module output"):
-        r = subprocess.run([cli_hostsim, *shlex.split(cmd)], capture_output=True, text=True, timeout=60)
+        r = subprocess.run([exe, *shlex.split(cmd)], capture_output=True, text=True, timeout=60)
         assert r.returncode == 0 and r.stdout, cmd
+
+
+def test_cli_accepts_the_reference_ci_command_lines_hostsim(cli_hostsim, tmp_path):
+    _reference_ci_command_lines(cli_hostsim, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cli_accepts_the_reference_ci_command_lines_gpu(cli_gpu, tmp_path):
+    _reference_ci_command_lines(cli_gpu, tmp_path)
+
+

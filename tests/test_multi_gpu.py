@@ -127,3 +127,27 @@ def test_processes_match_one_gpu(gpu_lib, tmp_path):
         assert np.abs(g["est"] - e1).max() < 2e-9
         assert abs(float(g["sigma0"]) - st1.sigma_zero) < 1e-11
         assert np.abs(g["q"] - q1).max() < 1e-10 * np.abs(q1).max()
+
+
+def test_command_line_gpus_option(oracle, gpu_lib, tmp_path):
+    """`dnaadjust <net> --gpus 2` (the product binary; ranks as threads with peer access, csrc/host/gpu_group.hpp): the reports
+    equal the oracle's at print resolution, simultaneous and phased, per-block SINEX from the ranks holding the blocks."""
+    from dynadjust_b200 import dnafiles
+    from tests import parity
+    from tests.test_cli import _check_outputs, _run, _write_network
+    if gpu_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    exe = os.path.join(ROOT, "dynadjust_b200", "bin", "dnaadjust")
+    assert os.path.exists(exe), "dynadjust_b200/bin/dnaadjust is missing on a GPU box: run __graft_entry__.build()"
+    stn, msr, _, _ = synth.gnss_network(900, 2700, 41)
+    _write_network(tmp_path, "mg", stn, msr)
+    r = _run(exe, tmp_path, "mg", "--gpus", "2", "--output-adj-msr", "--output-pos-uncertainty", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    _check_outputs(oracle, tmp_path, "mg", "simult", stn, msr, True)
+    blocks = parity.chain_blocks(len(stn), 150)
+    isl = [list(b) for b in blocks]
+    dnafiles.write_seg(os.path.join(tmp_path, "mg.seg"), isl, [[] for _ in isl], [[] for _ in isl])
+    r = _run(exe, tmp_path, "mg", "--phased", "--gpus", "2", "--export-sinex-file", "--no-binary-update")
+    assert r.returncode == 0, r.stderr
+    _check_outputs(oracle, tmp_path, "mg", "phased", stn, msr, False)
+    assert len([f for f in os.listdir(tmp_path) if f.endswith(".snx")]) == len(blocks)
