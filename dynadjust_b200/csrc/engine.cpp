@@ -289,7 +289,7 @@ void run_one(gadj_ctx* c, const Launch& L)
             c->launch_count--;  // a memset, not one of our kernels
         switch (L.kind) {
         case L_GEMM:
-            launch_gemm(c->d_gemm.p + L.op_begin, L.op_count, c->d_tiles.p + L.tile_begin, L.total_tiles, st);
+            launch_gemm(c->d_gemm.p + L.op_begin, L.op_count, c->d_tiles.p + L.tile_begin, L.total_tiles, L.shape, st);
             break;
         case L_DIAG:
             launch_diag(c->d_diag.p + L.op_begin, L.op_count, c->d_info.p, st);
@@ -1447,6 +1447,11 @@ int gadj_prepare(gadj_ctx* c)
     pb.rowidx = c->d_rowidx.p;
     pb.tgt = c->d_tgt.p;
     pb.coltgt = c->d_coltgt.p;
+    pb.gemm_tile = c->o.gemm_tile;
+    if (const char* gt = getenv("GADJ_GEMM_TILE"))   // tuning aid: overrides the option
+        pb.gemm_tile = atoi(gt);
+    if (pb.gemm_tile != 0 && pb.gemm_tile != 64 && pb.gemm_tile != 128)
+        return c->fail("gemm_tile must be 0 (automatic), 64 or 128");
     e = build_plan(S, pb, c->plan);
     if (!e.empty())
         return c->fail(e);
@@ -2644,19 +2649,28 @@ int gadj_profile_read(gadj_ctx* c, gadj_profile* out, int reset)
     return 0;
 }
 
-int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int M, int N, int K, int reps, float* ms)
+int gadj_test_gemm_ex(gadj_ctx* c, const double* A, const double* B, double* C, double* Ct, int M, int N, int K, int flags,
+                      int tile, int reps, float* ms)
 {
     dev::use(c->device);
     if (M <= 0 || N <= 0 || K <= 0)
         return c->fail("gadj_test_gemm: M, N, K must be positive");
-    DevArray<double> dA, dB, dC;
+    if (tile != 64 && tile != 128)
+        return c->fail("gadj_test_gemm: tile must be 64 or 128");
+    const int allowed = GEMM_ACCUM | GEMM_NEG | GEMM_LOWER | GEMM_KLO_ROW | GEMM_KLO_MAX | GEMM_KHI_ROW | GEMM_DUAL;
+    if ((flags & ~allowed) || ((flags & GEMM_DUAL) && (!Ct || (flags & (GEMM_ACCUM | GEMM_LOWER)))))
+        return c->fail("gadj_test_gemm: unsupported flags");
+    const int shape = tile == 64 ? TILE_SHAPE_64 : TILE_SHAPE_128;
+    DevArray<double> dA, dB, dC, dCt;
     DevArray<GemmOp> dop;
     DevArray<GemmTile> dtl;
     // rows padded to an even pitch like every panel of the engine (odd K = 3 x an odd station count is the common case);
     // the padding holds NaNs: it lies beyond the tensor map's extent and must never reach the product
-    const int ldc = N + (N & 1), ldk = K + (K & 1);
-    if (!dA.resize((size_t)M * ldk) || !dB.resize((size_t)N * ldk) || !dC.resize((size_t)M * ldc) || !dop.resize(1))
+    const int ldc = N + (N & 1), ldk = K + (K & 1), ldct = M + (M & 1);
+    if (!dA.resize((size_t)M * ldk) || !dB.resize((size_t)N * ldk) || !dC.resize((size_t)M * ldc) || !dop.resize(1) ||
+        !dCt.resize((size_t)N * ldct))
         return c->fail("out of device memory");
+    std::vector<double> hc((size_t)M * ldc, 0.0);
     {
         const double nan = std::nan("");
         std::vector<double> pa((size_t)M * ldk, nan), pb((size_t)N * ldk, nan);
@@ -2664,55 +2678,76 @@ int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int
             std::memcpy(pa.data() + (size_t)i * ldk, A + (size_t)i * K, (size_t)K * sizeof(double));
         for (int i = 0; i < N; ++i)
             std::memcpy(pb.data() + (size_t)i * ldk, B + (size_t)i * K, (size_t)K * sizeof(double));
+        for (int i = 0; i < M; ++i)   // C on entry: what GEMM_ACCUM adds to and what GEMM_LOWER leaves alone above the diagonal
+            std::memcpy(hc.data() + (size_t)i * ldc, C + (size_t)i * N, (size_t)N * sizeof(double));
         dev::h2d(dA.p, pa.data(), dA.bytes());
         dev::h2d(dB.p, pb.data(), dB.bytes());
+        dev::h2d(dC.p, hc.data(), dC.bytes());
         std::string e0 = dev::sync();
         if (!e0.empty())
             return c->fail(e0);
     }
-    dev::zero(dC.p, dC.bytes());
+    dev::zero(dCt.p, dCt.bytes());
     GemmOp op{};
     op.A = dA.p;
     op.B = dB.p;
     op.C = dC.p;
+    op.Ct = dCt.p;
+    op.ldct = ldct;
     op.lda = ldk;
     op.ldb = ldk;
     op.ldc = ldc;
     op.M = M;
     op.N = N;
     op.K = K;
-    op.flags = 0;
-    op.tiles_m = (M + TILE_M - 1) / TILE_M;
-    op.tiles_n = (N + TILE_N - 1) / TILE_N;
+    op.flags = flags;
+    const int T = tile_dim(shape);
+    op.tiles_m = (M + T - 1) / T;
+    op.tiles_n = (N + T - 1) / T;
     std::vector<GemmTile> tl;
     for (int tm = 0; tm < op.tiles_m; ++tm)
         for (int tn = 0; tn < op.tiles_n; ++tn)
-            tl.push_back(GemmTile{0, (uint16_t)tm, (uint16_t)tn});
+            if (!((flags & GEMM_LOWER) && tm * T + (T - 1) < tn * T))
+                tl.push_back(GemmTile{0, (uint16_t)tm, (uint16_t)tn});
     if (!dtl.upload(tl))
         return c->fail("out of device memory");
-    if (!dev::encode_tma_2d(&op.tmA, op.A, M, K, ldk, TILE_M) || !dev::encode_tma_2d(&op.tmB, op.B, N, K, ldk, TILE_N))
+    if (!dev::encode_tma_2d(&op.tmA, op.A, M, K, ldk, T) || !dev::encode_tma_2d(&op.tmB, op.B, N, K, ldk, T))
         return c->fail("tensor-map encoding failed");
     dev::h2d(dop.p, &op, sizeof(op));
-    launch_gemm(dop.p, 1, dtl.p, (int)tl.size(), dev::stream());
+    launch_gemm(dop.p, 1, dtl.p, (int)tl.size(), shape, dev::stream());
+    dev::d2h(hc.data(), dC.p, dC.bytes());
+    std::vector<double> hct;
+    if (flags & GEMM_DUAL) {
+        hct.resize((size_t)N * ldct);
+        dev::d2h(hct.data(), dCt.p, dCt.bytes());
+    }
     std::string e = dev::sync();
     if (!e.empty())
         return c->fail(e);
-    if (reps < 1)
-        reps = 1;
-    dev::event_record(c->ev[0]);
-    for (int i = 0; i < reps; ++i)
-        launch_gemm(dop.p, 1, dtl.p, (int)tl.size(), dev::stream());
-    dev::event_record(c->ev[1]);
-    std::vector<double> hc((size_t)M * ldc);
-    dev::d2h(hc.data(), dC.p, dC.bytes());
-    e = dev::sync();
-    if (!e.empty())
-        return c->fail(e);
+    if (reps > 0) {   // timing (the accumulating form keeps adding into the device copy: the results above are from call 1)
+        dev::event_record(c->ev[0]);
+        for (int i = 0; i < reps; ++i)
+            launch_gemm(dop.p, 1, dtl.p, (int)tl.size(), shape, dev::stream());
+        dev::event_record(c->ev[1]);
+        e = dev::sync();
+        if (!e.empty())
+            return c->fail(e);
+        if (ms)
+            *ms = dev::event_elapsed_ms(c->ev[0], c->ev[1]) / (float)reps;
+    }
     for (int i = 0; i < M; ++i)
         std::memcpy(C + (size_t)i * N, hc.data() + (size_t)i * ldc, (size_t)N * sizeof(double));
-    if (ms)
-        *ms = dev::event_elapsed_ms(c->ev[0], c->ev[1]) / (float)reps;
+    if (flags & GEMM_DUAL)
+        for (int j = 0; j < N; ++j)
+            std::memcpy(Ct + (size_t)j * M, hct.data() + (size_t)j * ldct, (size_t)M * sizeof(double));
     return 0;
+}
+
+int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int M, int N, int K, int reps, float* ms)
+{
+    if (M > 0 && N > 0)
+        std::memset(C, 0, (size_t)M * N * sizeof(double));
+    return gadj_test_gemm_ex(c, A, B, C, nullptr, M, N, K, 0, 128, reps < 1 ? 1 : reps, ms);
 }
 
 }  // extern "C"

@@ -19,6 +19,10 @@ namespace gadj {
 constexpr int TILE_M = 128;
 constexpr int TILE_N = 128;
 constexpr int TILE_K = 16;   // doubles per TMA box row (= 128 bytes, SWIZZLE_128B)
+// Tile shape of a GEMM launch (all tiles of a launch have the same shape; GemmTile::tm / tn and the ops' tensor-map
+// boxes are in its units): 128 x 128 for the large fronts, 64 x 64 for launches made of small fronts (plan.cpp picks).
+enum TileShape : int32_t { TILE_SHAPE_128 = 0, TILE_SHAPE_64 = 1 };
+constexpr int tile_dim(int shape) { return shape == TILE_SHAPE_64 ? 64 : TILE_M; }
 constexpr int NB = 128;      // pivot block width of the blocked factorisation
 
 struct alignas(64) TmaDesc {
@@ -96,9 +100,9 @@ struct alignas(64) GemmOp {
     int32_t tiles_m, tiles_n;
 };
 
-// One 128 x 128 output tile of one op.  The planner lists only the tiles that hold work (tiles wholly above the
-// diagonal of a lower-only output are left out); a launch is a contiguous run of this list and the persistent
-// GEMM CTAs stride through it.
+// One output tile (128 x 128 or 64 x 64: the launch's TileShape) of one op.  The planner lists only the tiles that
+// hold work (tiles wholly above the diagonal of a lower-only output are left out); a launch is a contiguous run of
+// this list and the persistent GEMM CTAs stride through it.
 struct GemmTile {
     int32_t op;              // index into the launch's op array
     uint16_t tm, tn;         // tile row / column inside the op
@@ -164,11 +168,11 @@ struct GatherOp {
 };
 
 // keys of dev::first_use: per-device one-time kernel attribute set-up
-enum FirstUseKey : int { KEY_GEMM = 1, KEY_DIAG = 2, KEY_ASSEMBLE = 3 };
+enum FirstUseKey : int { KEY_GEMM = 1, KEY_DIAG = 2, KEY_ASSEMBLE = 3, KEY_GEMM64 = 4, KEY_GEMM_LDG = 5, KEY_GEMM64_LDG = 6 };
 
 // ---- launches -----------------------------------------------------------------
 // All pointers are device pointers; `stream` is the backend's stream handle.
-void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, void* stream);
+void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, int shape /* TileShape */, void* stream);
 void launch_diag(const DiagOp* ops, int nops, int* info, void* stream);
 // multi-GPU: blocks of the replicated buffers copied into every peer's replica (bases[buf] = this rank's buffer);
 // grid_x CTAs per op

@@ -2,13 +2,18 @@
 //
 //   C[M x N] (+)= alpha * A[M x K] * B[N x K]^T        (all row-major, K contiguous)
 //
-// The unit of work is one 128 x 128 output tile of one op; a launch covers the tiles of many ops (all the
+// The unit of work is one output tile of one op; a launch covers the tiles of many ops (all the
 // panel updates / Schur complements / inverse products of one tree level), listed by the planner (only tiles
-// that hold work), and one persistent CTA per SM strides through the list.
+// that hold work), and persistent CTAs stride through the list.  Two tile shapes, chosen per launch by the planner:
+//   128 x 128 — 8 consumer warps (2 x 4, 64 x 32 each), a 132 KB ring, one CTA per SM: the large fronts;
+//    64 x 64  — 4 consumer warps (2 x 2, 32 x 32 each), a 66 KB ring, three CTAs per SM: the small fronts of the low
+//               tree levels, whose 128-wide tiles are mostly padding and whose short K loops leave the epilogue
+//               (stores, RED.ADD scatter) exposed — with three resident CTAs one tile's epilogue runs under the
+//               others' products.
 //
-// Data path: a producer warp issues cp.async.bulk.tensor (TMA) loads of 128 x 16 FP64
+// Data path: a producer warp issues cp.async.bulk.tensor (TMA) loads of TM x 16 / TN x 16 FP64
 // boxes of A and B into a 4-stage shared-memory ring (SWIZZLE_128B, mbarrier full/empty
-// pairs); 8 consumer warps (2 along M x 4 along N, 64 x 32 each) read fragments with
+// pairs); the consumer warps (2 along M, 4 or 2 along N) read fragments with
 // bank-conflict-free LDS.64 and issue mma.sync.m8n8k4.f64 (DMMA).  The swizzle makes a
 // fragment's 8 rows conflict-free only when they are 2 apart, so fragment i of a warp
 // covers rows {16*(i/2) + 2g + (i&1)}: the same map is applied to A rows, B rows (= C
@@ -30,12 +35,19 @@ namespace gadj {
 namespace {
 
 constexpr int STAGES = 4;
-constexpr int A_TILE_BYTES = TILE_M * TILE_K * 8;   // 16 KB
-constexpr int B_TILE_BYTES = TILE_N * TILE_K * 8;   // 16 KB
-constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int CONSUMER_WARPS = 8;
-constexpr int GEMM_THREADS = (CONSUMER_WARPS + 1) * 32;
+// geometry of one tile shape: TM x TN output tile, CW consumer warps as 2 (along M) x CW/2 (along N)
+template <int TM, int TN, int CW>
+struct TileCfg {
+    static constexpr int A_TILE_BYTES = TM * TILE_K * 8;
+    static constexpr int B_TILE_BYTES = TN * TILE_K * 8;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int THREADS = (CW + 1) * 32;
+    static constexpr int WTM = TM / 2, WTN = TN / (CW / 2);   // warp tile
+    static constexpr int FI = WTM / 8, FJ = WTN / 8;          // 8-row fragments of A / B per warp
+    static_assert(TM % 32 == 0 && TN % 32 == 0 && FI % 2 == 0 && FJ % 2 == 0, "fragment pairs");
+    static_assert(TM * TN * 8 <= STAGES * STAGE_BYTES, "the scatter epilogue parks the tile in the ring");
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -85,7 +97,7 @@ __device__ __forceinline__ double lds_f64(uint32_t addr)
 }
 
 // K range (in 16-deep steps) of the tile at (row0, col0): triangular operands carry explicit zeros outside it
-__device__ __forceinline__ void tile_k_range(int flags, int row0, int col0, int K, int& kc0, int& nk)
+__device__ __forceinline__ void tile_k_range(int flags, int row0, int col0, int K, int tm_rows, int& kc0, int& nk)
 {
     int k_lo = 0, k_hi = K;
     if (flags & GEMM_KLO_ROW)
@@ -93,21 +105,25 @@ __device__ __forceinline__ void tile_k_range(int flags, int row0, int col0, int 
     if (flags & GEMM_KLO_MAX)
         k_lo = row0 > col0 ? row0 : col0;
     if (flags & GEMM_KHI_ROW)
-        k_hi = (row0 + TILE_M < K) ? row0 + TILE_M : K;
+        k_hi = (row0 + tm_rows < K) ? row0 + tm_rows : K;
     kc0 = k_lo / TILE_K;
     nk = k_hi > k_lo ? (k_hi + TILE_K - 1) / TILE_K - kc0 : 0;
 }
 
-// Persistent CTAs: the grid is one CTA per SM (or fewer), each CTA strides through the launch's tile list.  The
+// Persistent CTAs: the grid is MINB CTAs per SM (or fewer), each CTA strides through the launch's tile list.  The
 // mbarrier ring runs on across tiles, so while the consumer warps store one tile the producer warp is already
 // fetching the first stages of the next one; the per-tile cost is the epilogue, not a CTA launch + pipeline fill.
 // LOADER 0: TMA producer warp + mbarrier ring (the product path).
 // LOADER 1: debug aid (GADJ_GEMM_LOADER=ldg) — the consumers fill one stage themselves with plain loads
 //           into the same swizzled layout; isolates tensor-map problems from fragment-layout problems.
-template <int LOADER>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int LOADER, int TM, int TN, int CW, int MINB>
+__global__ void __launch_bounds__((CW + 1) * 32, MINB)
     gemm_tile_kernel(const GemmOp* __restrict__ ops, const GemmTile* __restrict__ tiles, int ntiles)
 {
+    using Cfg = TileCfg<TM, TN, CW>;
+    constexpr int A_TILE_BYTES = Cfg::A_TILE_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
+    constexpr int FI = Cfg::FI, FJ = Cfg::FJ;
+    constexpr int CTHREADS = CW * 32;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_full = base + STAGES * STAGE_BYTES;
@@ -118,24 +134,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (LOADER == 0 && threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, CONSUMER_WARPS);
+            mbar_init(bar_empty + 8 * s, CW);
         }
-        mbar_init(bar_tile, CONSUMER_WARPS);
+        mbar_init(bar_tile, CW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == CONSUMER_WARPS) {
+    if (warp == CW) {
         // ---- TMA producer -------------------------------------------------------
         if (LOADER == 0 && lane == 0) {
             uint32_t gk = 0, nscatter = 0;
             for (int it = blockIdx.x; it < ntiles; it += gridDim.x) {
                 const GemmTile tl = tiles[it];
                 const GemmOp* op = ops + tl.op;
-                const int row0 = tl.tm * TILE_M, col0 = tl.tn * TILE_N;
+                const int row0 = tl.tm * TM, col0 = tl.tn * TN;
                 const int flags = op->flags;
                 int kc0, nk;
-                tile_k_range(flags, row0, col0, op->K, kc0, nk);
+                tile_k_range(flags, row0, col0, op->K, TM, kc0, nk);
                 const void* tmA = &op->tmA;
                 const void* tmB = &op->tmB;
                 asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmA) : "memory");
@@ -161,9 +177,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
     // ---- DMMA consumers ----------------------------------------------------------
     const int g = lane >> 2, t = lane & 3;
-    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+    const int wm = (warp & 1) * Cfg::WTM, wn = (warp >> 1) * Cfg::WTN;
     // per-thread constant parts of the swizzled fragment addresses
-    // element (r, k) of a 128 x 16 tile: r*128 + (((k>>1) ^ (r&7)) << 4) + ((k&1) << 3)
+    // element (r, k) of a rows x 16 tile: r*128 + (((k>>1) ^ (r&7)) << 4) + ((k&1) << 3)
     // fragment i of A sits at row wm + 16*(i>>1) + 2g + (i&1): a per-thread base plus a compile-time offset; the
     // swizzle term depends on (row & 7) = (2g + (i&1)) & 7 only.  Likewise B.
     const uint32_t a_base = (uint32_t)(wm + 2 * g) * 128u, b_base = (uint32_t)(wn + 2 * g) * 128u;
@@ -178,17 +194,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     if (it + (int)gridDim.x < ntiles)
         next = tiles[it + gridDim.x];   // in flight during this tile
     const GemmOp* op = ops + tl.op;
-    const int row0 = tl.tm * TILE_M, col0 = tl.tn * TILE_N;
+    const int row0 = tl.tm * TM, col0 = tl.tn * TN;
     const int M = op->M, N = op->N, K = op->K;
     const int flags = op->flags, tri_off = op->tri_off;
     int kc0, nk;
-    tile_k_range(flags, row0, col0, K, kc0, nk);
+    tile_k_range(flags, row0, col0, K, TM, kc0, nk);
 
-    double acc[8][4][2];
+    double acc[FI][FJ][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < FI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < FJ; ++j)
             acc[i][j][0] = acc[i][j][1] = 0.0;
 
     for (int kc = 0; kc < nk; ++kc, ++gk) {
@@ -198,19 +214,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (LOADER == 0) {
             mbar_wait(bar_full + 8 * s, (gk / STAGES) & 1);
         } else {
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(CTHREADS) : "memory");
             const double* __restrict__ gA = op->A;
             const double* __restrict__ gB = op->B;
-            for (int idx = threadIdx.x; idx < TILE_M * TILE_K; idx += CONSUMER_WARPS * 32) {
-                const int r = idx / TILE_K, k = idx - r * TILE_K;
+            for (int idx = threadIdx.x; idx < (TM + TN) * TILE_K; idx += CTHREADS) {
+                const bool isb = idx >= TM * TILE_K;
+                const int id = isb ? idx - TM * TILE_K : idx;
+                const int r = id / TILE_K, k = id - r * TILE_K;
                 const int gkk = (kc0 + kc) * TILE_K + k;
                 const uint32_t off = (uint32_t)r * 128u + ((uint32_t)((k >> 1) ^ (r & 7)) << 4) + ((uint32_t)(k & 1) << 3);
-                const double va = (row0 + r < M && gkk < K) ? gA[(int64_t)(row0 + r) * op->lda + gkk] : 0.0;
-                const double vb = (col0 + r < N && gkk < K) ? gB[(int64_t)(col0 + r) * op->ldb + gkk] : 0.0;
-                asm volatile("st.shared.f64 [%0], %1;" ::"r"(sa + off), "d"(va) : "memory");
-                asm volatile("st.shared.f64 [%0], %1;" ::"r"(sb + off), "d"(vb) : "memory");
+                double v;
+                if (!isb)
+                    v = (row0 + r < M && gkk < K) ? gA[(int64_t)(row0 + r) * op->lda + gkk] : 0.0;
+                else
+                    v = (col0 + r < N && gkk < K) ? gB[(int64_t)(col0 + r) * op->ldb + gkk] : 0.0;
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"((isb ? sb : sa) + off), "d"(v) : "memory");
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(CTHREADS) : "memory");
         }
 #pragma unroll
         for (int k4 = 0; k4 < TILE_K / 4; ++k4) {
@@ -219,17 +239,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const uint32_t o1 = ((uint32_t)(chunk ^ x1) << 4) + khalf + 128u;
             const uint32_t pa0 = sa + a_base + o0, pa1 = sa + a_base + o1;
             const uint32_t pb0 = sb + b_base + o0, pb1 = sb + b_base + o1;
-            double a[8], b[4];
+            double a[FI], b[FJ];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < FI; ++i)
                 a[i] = lds_f64(((i & 1) ? pa1 : pa0) + (uint32_t)(i >> 1) * 2048u);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < FJ; ++j)
                 b[j] = lds_f64(((j & 1) ? pb1 : pb0) + (uint32_t)(j >> 1) * 2048u);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < FI; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < FJ; ++j)
                     dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
         if (LOADER == 0) {
@@ -252,19 +272,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     const bool lower = (flags & GEMM_LOWER) != 0;
     if (flags & GEMM_SCATTER) {
         // Scatter through the station-level row map with FP64 RED.ADD.  The accumulators are first parked in the
-        // (now idle) pipeline stages as a 128 x 128 row-major tile, XOR-swizzled in groups of four columns so that
+        // (now idle) pipeline stages as a TM x TN row-major tile, XOR-swizzled in groups of four columns so that
         // the row-order loads are bank-conflict free; the atomics are then issued row by row with the 32 lanes on
         // 32 consecutive source columns (consecutive boundary stations are mostly consecutive in the ancestor, so
         // a warp instruction touches far fewer 32-byte sectors than in fragment order) and the column part of
         // the map is looked up once per lane instead of once per element.
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // every consumer has finished reading the last stages
+        constexpr int CC = TN / 32;
+        asm volatile("bar.sync 1, %0;" ::"n"(CTHREADS) : "memory");   // every consumer has finished reading the last stages
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < FI; ++i) {
             const int rr = wm + 16 * (i >> 1) + 2 * g + (i & 1);
-            const uint32_t rbase = base + (uint32_t)rr * (TILE_N * 8);
+            const uint32_t rbase = base + (uint32_t)rr * (TN * 8);
             const int sw = (rr >> 1) & 7;
 #pragma unroll
-            for (int p = 0; p < 2; ++p) {
+            for (int p = 0; p < FJ / 2; ++p) {
                 const int cg = ((wn + 16 * p) >> 2) + t;            // group of four columns owned by this thread
                 const uint32_t addr = rbase + (uint32_t)((cg ^ sw) << 5);
                 asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(acc[i][2 * p][0]), "d"(acc[i][2 * p + 1][0])
@@ -274,13 +295,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                              : "memory");
             }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        // per lane: its four columns' targets (ancestor panel, pitch, station row map) and column positions
-        double* cbase[4];
-        const int32_t* rmap[4];
-        int64_t cld[4];
+        asm volatile("bar.sync 1, %0;" ::"n"(CTHREADS) : "memory");
+        // per lane: its columns' targets (ancestor panel, pitch, station row map) and column positions
+        double* cbase[CC];
+        const int32_t* rmap[CC];
+        int64_t cld[CC];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < CC; ++cc) {
             const int c = col0 + 32 * cc + lane;
             cbase[cc] = nullptr;
             if (c < N) {
@@ -290,15 +311,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 cbase[cc] = tg.C + 3ll * rmap[cc][c / 3] + c % 3;
             }
         }
-        for (int rr = warp; rr < TILE_M; rr += CONSUMER_WARPS) {
+        for (int rr = warp; rr < TM; rr += CW) {
             const int r = row0 + rr;
             if (r >= M)
                 break;
             const int si = r / 3, rc = r - 3 * si;
-            const uint32_t rbase = base + (uint32_t)rr * (TILE_N * 8);
+            const uint32_t rbase = base + (uint32_t)rr * (TN * 8);
             const int sw = (rr >> 1) & 7;
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < CC; ++cc) {
                 const int cl = 32 * cc + lane;
                 if (cbase[cc] == nullptr || (lower && r + tri_off < col0 + cl))
                     continue;
@@ -318,13 +339,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         // fragments j = 2p and 2p+1 interleave: together a thread owns 4 consecutive columns
         // c0 .. c0+3 = {acc[i][2p][0], acc[i][2p+1][0], acc[i][2p][1], acc[i][2p+1][1]} -> two 16-byte accesses
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < FI; ++i) {
             const int r = row0 + wm + 16 * (i >> 1) + 2 * g + (i & 1);
             if (r >= M)
                 continue;
             double* __restrict__ crow = C + (int64_t)r * ldc;
 #pragma unroll
-            for (int p = 0; p < 2; ++p) {
+            for (int p = 0; p < FJ / 2; ++p) {
                 const int c0 = col0 + wn + 16 * p + 4 * t;
                 double v[4] = {alpha * acc[i][2 * p][0], alpha * acc[i][2 * p + 1][0], alpha * acc[i][2 * p][1],
                                alpha * acc[i][2 * p + 1][1]};
@@ -361,13 +382,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
     }
     if (LOADER != 0)
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // debug loader: the next tile's self-loads reuse stage 0
+        asm volatile("bar.sync 1, %0;" ::"n"(CTHREADS) : "memory");   // debug loader: the next tile's self-loads reuse stage 0
     }   // tile loop
+}
+
+template <int LOADER, int TM, int TN, int CW, int MINB>
+void launch_shape(const GemmOp* ops, const GemmTile* tiles, int ntiles, int first_use_key, cudaStream_t st)
+{
+    using Cfg = TileCfg<TM, TN, CW>;
+    auto* k = gemm_tile_kernel<LOADER, TM, TN, CW, MINB>;
+    if (dev::first_use(first_use_key))   // kernel attributes are per device
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    const int cap = dev::sm_count() * MINB;   // persistent CTAs: as many as are resident at once
+    const int grid = ntiles < cap ? ntiles : cap;
+    k<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(ops, tiles, ntiles);
 }
 
 }  // namespace
 
-void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, void* stream)
+void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, int shape, void* stream)
 {
     if (nops <= 0 || ntiles <= 0)
         return;
@@ -375,17 +408,18 @@ void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles,
         const char* e = getenv("GADJ_GEMM_LOADER");
         return (e && e[0] == 'l') ? 1 : 0;
     }();
-    if (dev::first_use(KEY_GEMM)) {   // kernel attributes are per device
-        cudaFuncSetAttribute(gemm_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-        cudaFuncSetAttribute(gemm_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-    }
-    const int sms = dev::sm_count();
-    const int grid = ntiles < sms ? ntiles : sms;   // one persistent CTA per SM (the 132 KB ring allows no more)
     cudaStream_t st = (cudaStream_t)stream;
-    if (loader == 0)
-        gemm_tile_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ops, tiles, ntiles);
-    else
-        gemm_tile_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ops, tiles, ntiles);
+    if (shape == TILE_SHAPE_64) {
+        if (loader == 0)
+            launch_shape<0, 64, 64, 4, 3>(ops, tiles, ntiles, KEY_GEMM64, st);
+        else
+            launch_shape<1, 64, 64, 4, 3>(ops, tiles, ntiles, KEY_GEMM64_LDG, st);
+    } else {
+        if (loader == 0)
+            launch_shape<0, TILE_M, TILE_N, 8, 1>(ops, tiles, ntiles, KEY_GEMM, st);
+        else
+            launch_shape<1, TILE_M, TILE_N, 8, 1>(ops, tiles, ntiles, KEY_GEMM_LDG, st);
+    }
 }
 
 }  // namespace gadj

@@ -72,6 +72,8 @@ struct Builder {
 
     Builder(const Symbolic& S, const PlanBuffers& B, Plan& P) : s(S), b(B), p(P)
     {
+        if (const char* e = getenv("GADJ_TILE64_MARGIN"))   // tuning aid
+            tile64_margin = atof(e);
         // top fronts first: the same offsets on every rank (see finalize_layout)
         woff.assign(s.fronts.size(), 0);
         size_t o = 0;
@@ -228,12 +230,64 @@ struct Builder {
         op.K = K;
         op.flags = flags;
         op.tri_off = tri_off;
-        op.tiles_m = cdiv(M, TILE_M);
-        op.tiles_n = cdiv(N, TILE_N);
-        batch.push_back(op);
+        batch.push_back(op);   // tiles_m / tiles_n: flush_gemm, once the launch's tile shape is known
     }
 
-    // appends a batch as one launch; assigns tile ranges and encodes the tensor maps
+    // K steps (16 deep) of the tile at (row0, col0) — the kernel's tile_k_range
+    static int tile_ksteps(const GemmOp& op, int row0, int col0, int T)
+    {
+        int k_lo = 0, k_hi = op.K;
+        if (op.flags & GEMM_KLO_ROW)
+            k_lo = row0;
+        if (op.flags & GEMM_KLO_MAX)
+            k_lo = std::max(row0, col0);
+        if (op.flags & GEMM_KHI_ROW)
+            k_hi = std::min(row0 + T, op.K);
+        return k_hi > k_lo ? cdiv(k_hi, TILE_K) - k_lo / TILE_K : 0;
+    }
+    static bool tile_has_work(const GemmOp& op, int tm, int tn, int T)
+    {
+        return !((op.flags & GEMM_LOWER) && tm * T + (T - 1) + op.tri_off < tn * T);   // else wholly above the diagonal
+    }
+    // Tile shape of a launch.  The tensor pipe spends the same time on a padded element as on a useful one, so the cost
+    // of a launch is its tiles' area x (K steps + the epilogue's equivalent in K steps: a plain store ~2, the RED.ADD
+    // scatter ~12); 64 x 64 tiles are taken when they shrink that by more than `margin` — the small fronts of the low
+    // tree levels (k ~ 40-190, r ~ 200-600), where 128-wide tiles are half padding.  Ops whose tiles are shared out
+    // among the ranks or pushed to the peers (top fronts: large) and in-place products wider than 64 stay on 128 x 128.
+    int choose_shape(const std::vector<GemmOp>& batch) const
+    {
+        for (size_t i = 0; i < batch.size(); ++i) {
+            if (share[i].dist != D_ALL || share[i].push)
+                return TILE_SHAPE_128;
+            // in-place products (the pivot panel P <- P W^T: C is A) need every row block in ONE tile — a second column
+            // tile would read rows the first one has already overwritten
+            if ((batch[i].C == batch[i].A || batch[i].C == batch[i].B) && batch[i].N > tile_dim(TILE_SHAPE_64))
+                return TILE_SHAPE_128;
+        }
+        if (b.gemm_tile == 128)
+            return TILE_SHAPE_128;
+        if (b.gemm_tile == 64)
+            return TILE_SHAPE_64;
+        double cost[2] = {0, 0};
+        const size_t stride = std::max<size_t>(1, batch.size() / 512);   // a sample of the ops is enough
+        for (size_t i = 0; i < batch.size(); i += stride) {
+            const GemmOp& op = batch[i];
+            const double epi = (op.flags & GEMM_SCATTER) ? 12.0 : (op.flags & GEMM_DUAL) ? 4.0 : 2.0;
+            for (int sh = 0; sh < 2; ++sh) {
+                const int T = tile_dim(sh);
+                double c = 0;
+                for (int tm = 0; tm < cdiv(op.M, T); ++tm)
+                    for (int tn = 0; tn < cdiv(op.N, T); ++tn)
+                        if (tile_has_work(op, tm, tn, T))
+                            c += tile_ksteps(op, tm * T, tn * T, T) + epi;
+                cost[sh] += c * T * T;
+            }
+        }
+        return cost[TILE_SHAPE_64] * tile64_margin < cost[TILE_SHAPE_128] ? TILE_SHAPE_64 : TILE_SHAPE_128;
+    }
+    double tile64_margin = 1.10;
+
+    // appends a batch as one launch; picks the tile shape, assigns tile ranges and encodes the tensor maps
     void flush_gemm(std::vector<GemmOp>& batch, std::vector<Launch>& out, int level, int tag = T_NONE)
     {
         if (batch.empty())
@@ -246,25 +300,31 @@ struct Builder {
         L.level = level;
         L.tile_begin = (int64_t)p.tiles.size();
         share.resize(batch.size(), Share{D_ALL, 0});
+        L.shape = choose_shape(batch);
+        if (L.shape == TILE_SHAPE_64)
+            p.launches_tile64++;
+        const int T = tile_dim(L.shape);
         int32_t opi = 0;
         for (GemmOp& op : batch) {
             const Share sh = share[opi];
             size_t all_tiles = 0, my_tiles = 0;
+            op.tiles_m = cdiv(op.M, T);
+            op.tiles_n = cdiv(op.N, T);
             for (int tm = 0; tm < op.tiles_m; ++tm)
                 for (int tn = 0; tn < op.tiles_n; ++tn) {
-                    if ((op.flags & GEMM_LOWER) && tm * TILE_M + (TILE_M - 1) + op.tri_off < tn * TILE_N)
-                        continue;   // wholly above the diagonal
+                    if (!tile_has_work(op, tm, tn, T))
+                        continue;
                     ++all_tiles;
                     if (sh.dist == D_SUM && (tm + tn) % s.world != s.rank)
                         continue;   // another rank's tile
                     ++my_tiles;
                     p.tiles.push_back(GemmTile{opi, (uint16_t)tm, (uint16_t)tn});
                     if (sh.push) {
-                        const int rows = std::min(TILE_M, op.M - tm * TILE_M), cols = std::min(TILE_N, op.N - tn * TILE_N);
+                        const int rows = std::min(T, op.M - tm * T), cols = std::min(T, op.N - tn * T);
                         const int bc = sh.push & 0xff, bt = (sh.push >> 8) & 0xff;
-                        add_push(bc, op.C + (int64_t)tm * TILE_M * op.ldc + (int64_t)tn * TILE_N, op.ldc, rows, cols);
+                        add_push(bc, op.C + (int64_t)tm * T * op.ldc + (int64_t)tn * T, op.ldc, rows, cols);
                         if (bt)
-                            add_push(bt, op.Ct + (int64_t)tn * TILE_N * op.ldct + (int64_t)tm * TILE_M, op.ldct, cols, rows);
+                            add_push(bt, op.Ct + (int64_t)tn * T * op.ldct + (int64_t)tm * T, op.ldct, cols, rows);
                     }
                 }
             ++opi;
@@ -283,8 +343,8 @@ struct Builder {
             if (all_tiles)
                 fl *= (double)my_tiles / (double)all_tiles;   // this rank's share of a distributed op
             L.flops += fl;
-            if (!dev::encode_tma_2d(&op.tmA, op.A, (uint64_t)op.M, (uint64_t)op.K, (uint64_t)op.lda, TILE_M) ||
-                !dev::encode_tma_2d(&op.tmB, op.B, (uint64_t)op.N, (uint64_t)op.K, (uint64_t)op.ldb, TILE_N))
+            if (!dev::encode_tma_2d(&op.tmA, op.A, (uint64_t)op.M, (uint64_t)op.K, (uint64_t)op.lda, (uint32_t)T) ||
+                !dev::encode_tma_2d(&op.tmB, op.B, (uint64_t)op.N, (uint64_t)op.K, (uint64_t)op.ldb, (uint32_t)T))
                 err = "tensor-map encoding failed";
             p.gemm.push_back(op);
         }
@@ -820,6 +880,7 @@ std::string build_plan(const Symbolic& s, const PlanBuffers& b, Plan& p)
     p.factor_flops = p.selinv_flops = 0;
     p.nvlink_read_bytes = p.nvlink_write_bytes = 0;
     p.barriers = 0;
+    p.launches_tile64 = 0;
     if (b.pool_doubles < min_pool_doubles(s))
         return "workspace pool smaller than the largest front";
     // scatter tables of the Schur updates

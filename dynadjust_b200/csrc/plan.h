@@ -35,6 +35,7 @@ struct Launch {
     double flops;         // algorithmic flops of this launch (GEMM: 2MNK, halved for LOWER)
     int32_t tag;          // which step of the algorithm (profiling label)
     int32_t buf;          // L_ALLREDUCE: McBuf of the buffer the ranges live in
+    int32_t shape;        // L_GEMM: TileShape of the launch's tiles
 };
 
 enum LaunchTag : int32_t {
@@ -52,6 +53,8 @@ struct PlanBuffers {
     const int32_t* rowidx = nullptr;  // device: global unknown index per front row (concatenated, Plan::rowidx_off)
     const ScatterTarget* tgt = nullptr;   // device, Symbolic::targets.size() entries (filled from Plan::tgt)
     const int32_t* coltgt = nullptr;      // device, Symbolic::bnd.size() entries (filled from Plan::coltgt)
+    // GEMM tile shape: 0 = per launch by the padded-work model (below), 64 / 128 = that shape wherever it is allowed
+    int32_t gemm_tile = 0;
 };
 
 struct Plan {
@@ -73,6 +76,7 @@ struct Plan {
     // multi-GPU, per iteration of this rank: bytes read from / stored into the peers' replicas, barriers
     double nvlink_read_bytes = 0, nvlink_write_bytes = 0;
     uint64_t barriers = 0;
+    uint64_t launches_tile64 = 0;   // GEMM launches planned with 64 x 64 tiles
     // device copies of the op arrays (owned by the context)
     GemmOp* d_gemm = nullptr;
     DiagOp* d_diag = nullptr;

@@ -24,7 +24,7 @@ class GadjOpts(C.Structure):
     _fields_ = [("fixed_std_dev", C.c_double), ("free_std_dev", C.c_double), ("iteration_threshold", C.c_double),
                 ("semi_major", C.c_double), ("inv_flattening", C.c_double), ("confidence_interval", C.c_double),
                 ("workspace_gb", C.c_double), ("max_iterations", C.c_uint32), ("scale_normals_to_unity", C.c_int32),
-                ("ordering", C.c_int32), ("leaf_stations", C.c_uint32), ("device", C.c_int32), ("reserved", C.c_int32)]
+                ("ordering", C.c_int32), ("leaf_stations", C.c_uint32), ("device", C.c_int32), ("gemm_tile", C.c_int32)]
 
 
 class GadjIterResult(C.Structure):
@@ -70,7 +70,7 @@ EXPORTS = ["gadj_default_opts", "gadj_create", "gadj_destroy", "gadj_last_error"
            "gadj_reset_estimates", "gadj_iterate", "gadj_form_inverse", "gadj_adjust", "gadj_statistics",
            "gadj_update_ignored_measurements", "gadj_compute_measurements", "gadj_get_estimates",
            "gadj_get_corrections", "gadj_get_station_vcvs", "gadj_get_station_vcv", "gadj_get_vcv_block",
-           "gadj_get_normals_block", "gadj_get_rhs", "gadj_get_block_vcv", "gadj_get_pair_vcvs", "gadj_profile_enable", "gadj_profile_read", "gadj_test_gemm",
+           "gadj_get_normals_block", "gadj_get_rhs", "gadj_get_block_vcv", "gadj_get_pair_vcvs", "gadj_profile_enable", "gadj_profile_read", "gadj_test_gemm", "gadj_test_gemm_ex",
            "gadj_mg_init", "gadj_mg_export", "gadj_mg_connect", "gadj_sync", "gadj_mg_buffer"]
 
 _libs = {}
@@ -122,6 +122,7 @@ def load_library(path=None):
     L.gadj_sync.argtypes = [vp]
     L.gadj_mg_buffer.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]
     L.gadj_test_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, C.POINTER(C.c_float)]
+    L.gadj_test_gemm_ex.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_float)]
     _libs[path] = L
     return L
 
@@ -307,3 +308,16 @@ class Adjustment:
         ms = C.c_float()
         self._check(self.L.gadj_test_gemm(self.h, self._p(A), self._p(B), self._p(Cm), M, N, K, reps, C.byref(ms)))
         return Cm, ms.value
+
+    def test_gemm_ex(self, A, B, C0=None, flags=0, tile=128, reps=0):
+        """The tile kernel with its epilogue / K-range flags and either tile shape: returns (C, Ct or None, ms)."""
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        B = np.ascontiguousarray(B, dtype=np.float64)
+        M, K = A.shape
+        N = B.shape[0]
+        Cm = np.zeros((M, N)) if C0 is None else np.array(C0, dtype=np.float64, order="C")
+        Ct = np.zeros((N, M)) if flags & 128 else None
+        ms = C.c_float()
+        self._check(self.L.gadj_test_gemm_ex(self.h, self._p(A), self._p(B), self._p(Cm), self._p(Ct) if Ct is not None else None,
+                                             M, N, K, flags, tile, reps, C.byref(ms)))
+        return Cm, Ct, ms.value

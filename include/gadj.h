@@ -68,7 +68,8 @@ typedef struct gadj_opts {
     int32_t ordering;              /* GADJ_ORDER_* */
     uint32_t leaf_stations;        /* nested-dissection leaf size, default 96 */
     int32_t device;                /* CUDA device ordinal */
-    int32_t reserved;
+    int32_t gemm_tile;             /* tile shape of the FP64 tensor GEMM launches: 0 = chosen per launch from the fronts'
+                                      sizes (default), 64 or 128 = that shape wherever it is allowed (tuning / tests) */
 } gadj_opts;
 
 typedef struct gadj_iter_result {
@@ -229,6 +230,11 @@ int gadj_profile_read(gadj_ctx* c, gadj_profile* out, int reset);
 /* FP64 GEMM self-test / micro-benchmark of the tensor-core tile kernel: C = A * B^T (row-major host arrays).
  * returns device milliseconds per call in *ms (averaged over reps) */
 int gadj_test_gemm(gadj_ctx* c, const double* A, const double* B, double* C, int M, int N, int K, int reps, float* ms);
+/* The same with the kernel's epilogue / K-range flags (GemmFlags of csrc/kernels.h: 1 accumulate into C, 2 negate, 4 lower
+ * triangle only, 16 / 32 / 64 triangular operands, 128 also store the transpose into Ct [N x M]) and the tile shape
+ * (64 or 128).  C holds the initial values on entry.  reps = 0: no timing. */
+int gadj_test_gemm_ex(gadj_ctx* c, const double* A, const double* B, double* C, double* Ct, int M, int N, int K, int flags,
+                      int tile, int reps, float* ms);
 
 #ifdef __cplusplus
 }

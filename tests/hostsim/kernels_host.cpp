@@ -14,8 +14,9 @@
 
 namespace gadj {
 
-void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, void*)
+void launch_gemm(const GemmOp* ops, int nops, const GemmTile* tiles, int ntiles, int shape, void*)
 {
+    const int TILE_M = tile_dim(shape), TILE_N = tile_dim(shape);   // the launch's tile shape (shadows the 128 defaults)
     // tile by tile, exactly the work list the persistent CTAs stride through: a tile missing from the planner's
     // list, or listed twice, changes the results
     std::vector<double> out((size_t)TILE_M * TILE_N);

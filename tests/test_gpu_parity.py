@@ -25,6 +25,55 @@ def test_gemm_tile_kernel(gpu_lib, M, N, K):
     adj.close()
 
 
+# GemmFlags of csrc/kernels.h
+ACCUM, NEG, LOWER, KLO_ROW, KLO_MAX, KHI_ROW, DUAL = 1, 2, 4, 16, 32, 64, 128
+
+
+@pytest.mark.parametrize("tile", [64, 128])
+@pytest.mark.parametrize("M,N,K,flags", [
+    (200, 72, 50, 0), (129, 127, 141, NEG), (300, 260, 177, ACCUM | NEG), (257, 257, 100, LOWER),
+    (330, 330, 75, ACCUM | NEG | LOWER), (190, 410, 190, KLO_ROW), (259, 200, 259, NEG | KHI_ROW),
+    (301, 301, 301, LOWER | KLO_MAX), (410, 190, 410, NEG | DUAL), (65, 63, 17, DUAL), (1, 1, 2, 0), (64, 64, 64, 0),
+    (700, 130, 40, 0), (640, 640, 16, LOWER)])
+def test_gemm_tile_kernel_flags_and_shapes(gpu_lib, tile, M, N, K, flags):
+    """Both tile shapes of the tile kernel (128 x 128: 8 consumer warps, one CTA per SM; 64 x 64: 4 consumer warps,
+    three CTAs per SM) with every epilogue (store, accumulate, negate, lower triangle only, transposed copy) and every
+    K-range rule for triangular operands, on ragged sizes.  FP64: 1e-13 relative."""
+    rng = np.random.default_rng(M * 1000003 + N * 1009 + K + flags)
+    A = rng.standard_normal((M, K))
+    B = rng.standard_normal((N, K))
+    if flags & KLO_ROW:      # A upper triangular: zero for k < row
+        A = np.triu(A)
+    if flags & KHI_ROW:      # A lower triangular: zero for k > row
+        A = np.tril(A)
+    if flags & KLO_MAX:      # A and B upper triangular
+        A, B = np.triu(A), np.triu(B)
+    C0 = rng.standard_normal((M, N))
+    adj = engine.Adjustment(lib_path=gpu_lib)
+    C, Ct, _ = adj.test_gemm_ex(A, B, C0, flags=flags, tile=tile)
+    prod = (-1.0 if flags & NEG else 1.0) * (A @ B.T)
+    ref = C0 + prod if flags & ACCUM else prod.copy()
+    if flags & LOWER:        # strictly upper part: untouched
+        iu = np.triu_indices(M, 1, N)
+        ref[iu] = C0[iu]
+    tol = 1e-13 * K * max(1.0, np.abs(prod).max())
+    assert np.abs(C - ref).max() <= tol
+    if flags & DUAL:
+        assert np.abs(Ct - ref.T).max() <= tol
+    adj.close()
+
+
+@pytest.mark.parametrize("tile", [64, 128])
+def test_tile_shapes_match_oracle(oracle, gpu_lib, tile):
+    """The whole path with one tile shape forced wherever the planner allows it (by default it picks per launch):
+    nested dissection, a chain of blocks, one dense front, mixed measurement types."""
+    parity.check_against_oracle(oracle, gpu_lib, 1000, 3000, 7, leaf_stations=24, gemm_tile=tile)
+    parity.check_against_oracle(oracle, gpu_lib, 300, 900, 9, blocks=lambda n: parity.chain_blocks(n, 40), gemm_tile=tile)
+    parity.check_against_oracle(oracle, gpu_lib, 500, 1500, 22, ordering=engine.ORDER_DENSE, gemm_tile=tile)
+    parity.check_against_oracle(oracle, gpu_lib, 300, 500, 23, n_distances=400, n_levels=300, leaf_stations=24,
+                                gemm_tile=tile, tol_sigma0=1e-7)
+
+
 def test_mixed_terrestrial_rows(oracle, gpu_lib):
     """GNSS baselines + slope distances 'S' + levelled height differences 'L' (geoid-reduced on the first run):
     the partials move with the estimates, so the normals are rebuilt and refactorised on every iteration."""
