@@ -222,6 +222,7 @@ struct gadj_ctx {
     DevArray<GemvOp> d_gemv;
     DevArray<TransposeOp> d_tr;
     DevArray<GatherOp> d_gather;
+    DevArray<GatherTile> d_gather_tiles;
     const PeerTable* pt() const { return d_peers.p; }
     std::vector<double> h_corr, h_dscale;
     uint32_t h_dscale_iteration = ~0u;
@@ -308,7 +309,7 @@ void run_one(gadj_ctx* c, const Launch& L)
             launch_transpose(c->d_tr.p + L.op_begin, L.op_count, L.total_tiles, st);
             break;
         case L_GATHER:
-            launch_gather(c->d_gather.p + L.op_begin, L.op_count, L.total_tiles, st);
+            launch_gather(c->d_gather.p + L.op_begin, L.op_count, c->d_gather_tiles.p + L.tile_begin, L.total_tiles, st);
             break;
         case L_ALLREDUCE: {
             double* base = L.buf == MC_PANELS ? c->d_panels.p : L.buf == MC_X ? c->d_x.p : nullptr;
@@ -1469,6 +1470,7 @@ int gadj_prepare(gadj_ctx* c)
     ok &= c->d_gemv.upload(c->plan.gemv);
     ok &= c->d_tr.upload(c->plan.transpose);
     ok &= c->d_gather.upload(c->plan.gather);
+    ok &= c->d_gather_tiles.upload(c->plan.gather_tiles);
     ok &= c->d_reduce.upload(c->plan.reduce);
     ok &= c->d_push.upload(c->plan.push);
     {
@@ -2501,9 +2503,9 @@ int gadj_get_block_vcv(gadj_ctx* c, uint32_t block, uint32_t* nstations, uint32_
     const size_t ldg = r + (r & 1);
     DevArray<double> dG;
     DevArray<GatherOp> dops;
+    DevArray<GatherTile> dtiles;
     if (r) {
         std::vector<GatherOp> ops;
-        int grid = 1;
         if (!dG.resize(r * ldg))
             return c->fail("out of device memory");
         for (uint32_t t = 0; t < f.tgt_count; ++t) {
@@ -2520,11 +2522,12 @@ int gadj_get_block_vcv(gadj_ctx* c, uint32_t block, uint32_t* nstations, uint32_
             g.nb = (int32_t)f.bnd_count;
             g.col0 = (int32_t)tg.col0;
             ops.push_back(g);
-            grid = std::max<int>(grid, (int)(((g.nb - g.jb + 15) / 16) * ((g.je - g.jb + 15) / 16)));
         }
-        if (!dops.upload(ops))
+        std::vector<GatherTile> tiles;
+        append_gather_tiles(ops, tiles);
+        if (!dops.upload(ops) || !dtiles.upload(tiles))
             return c->fail("out of device memory");
-        launch_gather(dops.p, (int)ops.size(), grid, dev::stream());
+        launch_gather(dops.p, (int)ops.size(), dtiles.p, (int)tiles.size(), dev::stream());
         G.resize(r * ldg);
         dev::d2h(G.data(), dG.p, G.size() * sizeof(double));
     }

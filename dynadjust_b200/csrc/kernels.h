@@ -167,6 +167,14 @@ struct GatherOp {
     int32_t col0;
 };
 
+// One 16 x 16-station tile of one gather op, on or below the op's diagonal (the planner lists only those; the kernel
+// mirrors them into the upper part of G).
+constexpr int GATHER_TILE_STATIONS = 16;
+struct GatherTile {
+    int32_t op;              // index into the launch's op array
+    uint16_t ti, tj;         // tile row / column, in units of 16 stations relative to the op's jb
+};
+
 // keys of dev::first_use: per-device one-time kernel attribute set-up
 enum FirstUseKey : int { KEY_GEMM = 1, KEY_DIAG = 2, KEY_ASSEMBLE = 3, KEY_GEMM64 = 4, KEY_GEMM_LDG = 5, KEY_GEMM64_LDG = 6 };
 
@@ -187,7 +195,7 @@ void launch_trimv(const TrimvOp* ops, int nops, void* stream);
 void launch_gemv(const GemvOp* ops, int nops, const double* x_ro, double* x, int backward, void* stream);
 // grid_x: CTAs per op (each op loops over its tiles); the planner passes min(cap, largest tile count)
 void launch_transpose(const TransposeOp* ops, int nops, int grid_x, void* stream);
-void launch_gather(const GatherOp* ops, int nops, int grid_x, void* stream);
+void launch_gather(const GatherOp* ops, int nops, const GatherTile* tiles, int ntiles, void* stream);
 
 // ---- assembly -----------------------------------------------------------------
 // Edge word of a GNSS baseline: bits 0..29 edge slot, bit 31 = station1 is eliminated after station2, bit 30 = this

@@ -471,17 +471,15 @@ __global__ void __launch_bounds__(256) transpose_kernel(const TransposeOp* __res
 // and its mirror image are written with coalesced rows.
 constexpr int GT = 16;            // stations per tile edge
 constexpr int GE = 3 * GT;        // doubles per tile edge
-__global__ void __launch_bounds__(256) gather_kernel(const GatherOp* __restrict__ ops)
+__global__ void __launch_bounds__(256) gather_kernel(const GatherOp* __restrict__ ops, const GatherTile* __restrict__ tiles, int ntiles)
 {
     __shared__ double T[GE][GE + 1];
-    const GatherOp op = ops[blockIdx.y];
-    const int ni = op.nb - op.jb, nj = op.je - op.jb;
-    const int ti_n = (ni + GT - 1) / GT, tj_n = (nj + GT - 1) / GT;
-    for (int tl = blockIdx.x; tl < ti_n * tj_n; tl += gridDim.x) {
-        const int ti = tl / tj_n, tj = tl - ti * tj_n;
-        const int i0 = ti * GT, j0 = tj * GT;            // station offsets relative to jb
-        if (i0 + GT - 1 < j0)
-            continue;                                    // tile wholly above the diagonal (uniform per block)
+    // the planner lists exactly the tiles on or below the diagonal of every op; the CTAs stride through the list
+    for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+        const GatherTile gt = tiles[tl];
+        const GatherOp op = ops[gt.op];
+        const int ni = op.nb - op.jb, nj = op.je - op.jb;
+        const int i0 = gt.ti * GT, j0 = gt.tj * GT;      // station offsets relative to jb
         for (int e = threadIdx.x; e < GE * GE; e += 256) {
             const int ar = e / GE, bc = e - ar * GE;
             const int ii = i0 + ar / 3, jj = j0 + bc / 3;
@@ -590,14 +588,13 @@ void launch_transpose(const TransposeOp* ops, int nops, int grid_x, void* stream
     }
 }
 
-void launch_gather(const GatherOp* ops, int nops, int grid_x, void* stream)
+void launch_gather(const GatherOp* ops, int nops, const GatherTile* tiles, int ntiles, void* stream)
 {
-    if (nops <= 0)
+    if (nops <= 0 || ntiles <= 0)
         return;
-    for (int o = 0; o < nops; o += 65535) {
-        int n = nops - o < 65535 ? nops - o : 65535;
-        gather_kernel<<<dim3(grid_x < 1 ? 1 : (grid_x > 592 ? 592 : grid_x), n), 256, 0, (cudaStream_t)stream>>>(ops + o);
-    }
+    static_assert(GATHER_TILE_STATIONS == GT, "the planner's tile edge");
+    const int cap = dev::sm_count() * 8;   // 8 resident CTAs per SM (19 KB of shared memory each) keep enough loads in flight
+    gather_kernel<<<ntiles < cap ? ntiles : cap, 256, 0, (cudaStream_t)stream>>>(ops, tiles, ntiles);
 }
 
 }  // namespace gadj

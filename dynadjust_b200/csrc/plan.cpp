@@ -72,8 +72,8 @@ struct Builder {
 
     Builder(const Symbolic& S, const PlanBuffers& B, Plan& P) : s(S), b(B), p(P)
     {
-        if (const char* e = getenv("GADJ_TILE64_MARGIN"))   // tuning aid
-            tile64_margin = atof(e);
+        if (const char* e = getenv("GADJ_TILE_LONG_K"))   // tuning aid: K (in 16-deep steps) from which 128 x 128 tiles are kept
+            tile_long_ksteps = atof(e);
         // top fronts first: the same offsets on every rank (see finalize_layout)
         woff.assign(s.fronts.size(), 0);
         size_t o = 0;
@@ -250,10 +250,14 @@ struct Builder {
         return !((op.flags & GEMM_LOWER) && tm * T + (T - 1) + op.tri_off < tn * T);   // else wholly above the diagonal
     }
     // Tile shape of a launch.  The tensor pipe spends the same time on a padded element as on a useful one, so the cost
-    // of a launch is its tiles' area x (K steps + the epilogue's equivalent in K steps: a plain store ~2, the RED.ADD
-    // scatter ~12); 64 x 64 tiles are taken when they shrink that by more than `margin` — the small fronts of the low
-    // tree levels (k ~ 40-190, r ~ 200-600), where 128-wide tiles are half padding.  Ops whose tiles are shared out
-    // among the ranks or pushed to the peers (top fronts: large) and in-place products wider than 64 stay on 128 x 128.
+    // of a launch is its tiles' area x (K steps + the epilogue's equivalent in K steps: a plain store ~2, the transposed
+    // second copy ~4, the RED.ADD scatter ~12).  Measured on C4 launch by launch (profiles/r2_tile_shapes_c4.txt): the
+    // 64 x 64 shape — three CTAs per SM, so one tile's epilogue runs under the others' products — wins or ties wherever
+    // it does not cost more padded work, by 2x on the small fronts of the low tree levels (k ~ 40-190, r ~ 200-600, where
+    // 128-wide tiles are half padding) and still by 2-15 % in the middle of the tree; only launches of long products
+    // (K >= ~2000: the Z21 / Schur products of the top fronts) run 1.5-3.5 % faster on 128 x 128 tiles, whose operands
+    // are read half as often.  Ops whose tiles are shared out among the ranks or pushed to the peers (top fronts) and
+    // in-place products wider than 64 stay on 128 x 128.
     int choose_shape(const std::vector<GemmOp>& batch) const
     {
         for (size_t i = 0; i < batch.size(); ++i) {
@@ -268,7 +272,7 @@ struct Builder {
             return TILE_SHAPE_128;
         if (b.gemm_tile == 64)
             return TILE_SHAPE_64;
-        double cost[2] = {0, 0};
+        double cost[2] = {0, 0}, ksteps128 = 0, tiles128 = 0;
         const size_t stride = std::max<size_t>(1, batch.size() / 512);   // a sample of the ops is enough
         for (size_t i = 0; i < batch.size(); i += stride) {
             const GemmOp& op = batch[i];
@@ -278,14 +282,21 @@ struct Builder {
                 double c = 0;
                 for (int tm = 0; tm < cdiv(op.M, T); ++tm)
                     for (int tn = 0; tn < cdiv(op.N, T); ++tn)
-                        if (tile_has_work(op, tm, tn, T))
-                            c += tile_ksteps(op, tm * T, tn * T, T) + epi;
+                        if (tile_has_work(op, tm, tn, T)) {
+                            const int nk = tile_ksteps(op, tm * T, tn * T, T);
+                            c += nk + epi;
+                            if (sh == TILE_SHAPE_128) {
+                                ksteps128 += nk;
+                                tiles128 += 1;
+                            }
+                        }
                 cost[sh] += c * T * T;
             }
         }
-        return cost[TILE_SHAPE_64] * tile64_margin < cost[TILE_SHAPE_128] ? TILE_SHAPE_64 : TILE_SHAPE_128;
+        const bool long_k = tiles128 > 0 && ksteps128 / tiles128 >= tile_long_ksteps;
+        return cost[TILE_SHAPE_64] <= cost[TILE_SHAPE_128] * (long_k ? 0.97 : 1.02) ? TILE_SHAPE_64 : TILE_SHAPE_128;
     }
-    double tile64_margin = 1.10;
+    double tile_long_ksteps = 128.0;   // K >= 2048
 
     // appends a batch as one launch; picks the tile shape, assigns tile ranges and encodes the tensor maps
     void flush_gemm(std::vector<GemmOp>& batch, std::vector<Launch>& out, int level, int tag = T_NONE)
@@ -393,13 +404,6 @@ struct Builder {
         int t = 1;
         for (auto& o : b)
             t = std::max(t, cdiv(o.rows, 32) * cdiv(o.cols, 32));
-        return t;
-    }
-    static int tiles_hint(const std::vector<GatherOp>& b)
-    {
-        int t = 1;
-        for (auto& o : b)
-            t = std::max(t, cdiv(o.nb - o.jb, 16) * cdiv(o.je - o.jb, 16));
         return t;
     }
     template <class Op>
@@ -699,7 +703,20 @@ struct Builder {
                 gab.push_back(g);
             }
         }
-        flush_simple(gab, p.gather, L_GATHER, p.selinv, level);
+        if (!gab.empty()) {
+            // the tiles (16 x 16 stations) on or below the diagonal of every op, as one work list for the launch
+            Launch L{};
+            L.kind = L_GATHER;
+            L.level = level;
+            L.op_begin = (int64_t)p.gather.size();
+            L.op_count = (int32_t)gab.size();
+            L.tile_begin = (int64_t)p.gather_tiles.size();
+            append_gather_tiles(gab, p.gather_tiles);
+            L.total_tiles = (int32_t)(p.gather_tiles.size() - (size_t)L.tile_begin);
+            p.gather.insert(p.gather.end(), gab.begin(), gab.end());
+            p.selinv.push_back(L);
+            gab.clear();
+        }
         // Yt = Wt * L21^T
         for (size_t i = 0; i < chunk.size(); ++i) {
             const Front& f = s.fronts[chunk[i]];
@@ -871,6 +888,7 @@ std::string build_plan(const Symbolic& s, const PlanBuffers& b, Plan& p)
     p.gemv.clear();
     p.transpose.clear();
     p.gather.clear();
+    p.gather_tiles.clear();
     p.reduce.clear();
     p.push.clear();
     p.factor.clear();

@@ -27,8 +27,8 @@ struct Launch {
     int32_t kind;
     int32_t op_count;
     int64_t op_begin;     // index into the per-kind op array
-    int32_t total_tiles;  // L_GEMM: tiles with work (entries of Plan::tiles from tile_begin); transpose / gather: CTAs per op
-    int64_t tile_begin;   // L_GEMM
+    int32_t total_tiles;  // L_GEMM / L_GATHER: tiles with work (entries of Plan::tiles / gather_tiles from tile_begin); transpose: CTAs per op
+    int64_t tile_begin;   // L_GEMM, L_GATHER
     int32_t level;
     double* zero_ptr;     // L_ZERO
     size_t zero_bytes;
@@ -67,6 +67,7 @@ struct Plan {
     std::vector<GemvOp> gemv;
     std::vector<TransposeOp> transpose;
     std::vector<GatherOp> gather;
+    std::vector<GatherTile> gather_tiles;   // work lists of the gather launches (Launch::tile_begin / total_tiles)
     std::vector<ReduceOp> reduce;
     std::vector<PushOp> push;
     std::vector<Launch> factor, fwd, bwd, selinv;
@@ -94,6 +95,18 @@ size_t selinv_workspace(const Front& f);
 size_t min_pool_doubles(const Symbolic& s);
 // pool size that lets every level run as a single chunk
 size_t ideal_pool_doubles(const Symbolic& s);
+
+// the gather work list of a batch of ops: the 16 x 16-station tiles on or below each op's diagonal, appended to `out`
+inline void append_gather_tiles(const std::vector<GatherOp>& ops, std::vector<GatherTile>& out)
+{
+    const int GT = GATHER_TILE_STATIONS;
+    for (size_t o = 0; o < ops.size(); ++o) {
+        const int ni = ops[o].nb - ops[o].jb, nj = ops[o].je - ops[o].jb;
+        for (int ti = 0; ti < (ni + GT - 1) / GT; ++ti)
+            for (int tj = 0; tj < (nj + GT - 1) / GT && tj * GT <= ti * GT + GT - 1; ++tj)
+                out.push_back(GatherTile{(int32_t)o, (uint16_t)ti, (uint16_t)tj});
+    }
+}
 
 void build_rowidx(const Symbolic& s, Plan& p);
 // builds all four launch lists; encodes TMA descriptors through dev::encode_tma_2d

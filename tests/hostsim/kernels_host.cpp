@@ -221,13 +221,18 @@ void launch_transpose(const TransposeOp* ops, int nops, int, void*)
     }
 }
 
-void launch_gather(const GatherOp* ops, int nops, int, void*)
+void launch_gather(const GatherOp* ops, int nops, const GatherTile* tiles, int ntiles, void*)
 {
-    for (int o = 0; o < nops; ++o) {
-        const GatherOp& op = ops[o];
-        for (int i = op.jb; i < op.nb; ++i) {
+    // tile by tile, exactly the planner's list (a missing tile leaves part of G unwritten and shows in the results)
+    const int GT = GATHER_TILE_STATIONS;
+    for (int t = 0; t < ntiles; ++t) {
+        if (tiles[t].op < 0 || tiles[t].op >= nops)
+            continue;
+        const GatherOp& op = ops[tiles[t].op];
+        const int i_lo = op.jb + tiles[t].ti * GT, j_lo = op.jb + tiles[t].tj * GT;
+        for (int i = i_lo; i < i_lo + GT && i < op.nb; ++i) {
             const int64_t zr = 3ll * op.rowmap[i - op.jb];
-            for (int j = op.jb; j < op.je && j <= i; ++j) {
+            for (int j = j_lo; j < j_lo + GT && j < op.je && j <= i; ++j) {
                 const int64_t zc = 3ll * op.rowmap[j - op.jb];
                 for (int a = 0; a < 3; ++a)
                     for (int b = 0; b < 3; ++b) {

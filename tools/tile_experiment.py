@@ -5,7 +5,7 @@ timed iterations, and the results against the 128 x 128 run (largest coordinate 
 difference of the station variance blocks) plus the normal-equation identity on every station.
 
     python tools/tile_experiment.py [C4] [leaf] [modes, e.g. 128,64,0,0:1.3]   -> gpurun_out/tile_<mode>.csv, tile_experiment.json
-A mode "0:<margin>" runs the planner's choice with GADJ_TILE64_MARGIN=<margin>.
+A mode "0:<steps>" runs the planner's choice with GADJ_TILE_LONG_K=<steps> (16-deep K steps from which 128-wide tiles are kept).
 """
 import json
 import os
@@ -30,9 +30,9 @@ results = {}
 ref = None
 for mode in modes:
     tile, _, margin = mode.partition(":")
-    os.environ.pop("GADJ_TILE64_MARGIN", None)
+    os.environ.pop("GADJ_TILE_LONG_K", None)
     if margin:
-        os.environ["GADJ_TILE64_MARGIN"] = margin
+        os.environ["GADJ_TILE_LONG_K"] = margin
     stn, msr = stn0.copy(), msr0.copy()
     adj = engine.Adjustment(stn, msr, leaf_stations=leaf, gemm_tile=int(tile))
     t = time.time()
