@@ -133,7 +133,10 @@ struct TrimvOp {
     int32_t row0, nrows;     // rows [row0, row0 + nrows) of the front
     int32_t k;
     int32_t upper;           // 0: lower triangular, 1: upper triangular
+    int32_t wide;            // 1: nrows <= TRIMV_WIDE_ROWS and the whole CTA strides across the columns (wide fronts)
 };
+constexpr int TRIMV_WIDE_ROWS = 8;     // rows per CTA of a wide front
+constexpr int TRIMV_WIDE_K = 1024;     // fronts at least this wide take the wide form
 
 // forward : x[rowidx[i]] -= sum_c P[i][c] * xj[c]         for i in [0, nrows)
 // backward: xj[c]        -= sum_i P[i][c] * x[rowidx[i]]

@@ -18,8 +18,10 @@ namespace {
 // by barrier and shared-memory latency, not by arithmetic, so co-resident tiles are what fills the SM.  The tile is
 // padded to 128 x 128 with an identity so that every step runs on full blocks.
 //   factor : blocked right-looking Cholesky, panel width 16.  Panel: one thread per row keeps its 16 panel
-//            entries in registers (two barriers per column); trailing update: 4 x 4 register tiles over all
-//            256 threads, rank-16 per step.
+//            entries in registers; the 16 x 16 diagonal block is factorised inside one warp with shuffles, the rows
+//            below it by substitution against the finished block (three CTA barriers per panel instead of two per
+//            column: the kernel is latency-bound — one tile per launch at the top of the tree); trailing update:
+//            4 x 4 register tiles over all 256 threads, rank-16 per step.
 //   inverse: in place in the lower triangle (L has been stored to global memory by then): 16 x 16 diagonal
 //            blocks by forward substitution in registers, then block doubling 16 -> 32 -> 64 -> 128 with
 //            W21 = -W22 (L21 W11) as two register-tiled products per level.
@@ -60,22 +62,41 @@ template <int CTAS_PER_SM>
 __global__ void __launch_bounds__(DIAG_THREADS, CTAS_PER_SM) diag_kernel(const DiagOp* __restrict__ ops, int* __restrict__ info)
 {
     extern __shared__ double S[];
-    __shared__ double colbuf[PBW];
-    __shared__ double piv;
+    __shared__ double Lb[PBW][PBW + 1];   // the finished 16 x 16 diagonal block of the current panel
+    __shared__ double pinv[PBW];          // reciprocals of its diagonal
     const DiagOp op = ops[blockIdx.x];
     const int w = op.w, tid = threadIdx.x;
     const int64_t ld = op.ldd;
     const int wpad = (w + PBW - 1) & ~(PBW - 1);
-    // coalesced load of the lower triangle (row-major source); identity padding
-    for (int idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
-        const int i = idx >> 7, j = idx & (NB - 1);
-        if (j <= i)
-            S[tri(i, j)] = i < w ? op.D[i * ld + j] : (i == j ? 1.0 : 0.0);
+    // coalesced load of the lower triangle (row-major source), identity padding; a warp takes rows warp + 8 t and issues
+    // the loads of four rows together (one tile per launch at the top of the tree: latency is all that counts here)
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i0 = warp; i0 < NB; i0 += 32) {
+        double v[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 8 * u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = lane + 32 * q;
+                v[u][q] = (j <= i && i < w) ? op.D[i * ld + j] : (i == j ? 1.0 : 0.0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 8 * u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = lane + 32 * q;
+                if (j <= i)
+                    S[tri(i, j)] = v[u][q];
+            }
+        }
     }
     __syncthreads();
     if (op.factor) {
         for (int p0 = 0; p0 < wpad; p0 += PBW) {
-            // ---- panel: rows p0 .. wpad-1, columns p0 .. p0+15
+            // ---- panel: rows p0 .. wpad-1, columns p0 .. p0+15; one thread per row keeps its 16 entries in registers
             const int i = tid;
             const bool act = tid < wpad && i >= p0;
             double r[PBW];
@@ -84,31 +105,54 @@ __global__ void __launch_bounds__(DIAG_THREADS, CTAS_PER_SM) diag_kernel(const D
                 for (int kk = 0; kk < PBW; ++kk)
                     r[kk] = tri_ld(S, i, p0 + kk);
             }
+            // (a) the 16 x 16 diagonal block, by the warp that holds its rows (16 consecutive lanes), through shuffles:
+            //     no CTA barrier inside the 16 column steps
+            if ((tid >> 5) == (p0 >> 5)) {
+                const int lane = tid & 31, l0 = p0 & 31;
+                const bool inblk = lane >= l0 && lane < l0 + PBW;
 #pragma unroll
-            for (int jj = 0; jj < PBW; ++jj) {
-                if (tid == p0 + jj) {
-                    double d = r[jj];
+                for (int jj = 0; jj < PBW; ++jj) {
+                    double d = __shfl_sync(0xffffffffu, r[jj], l0 + jj);
                     if (!(d > 0.0)) {
-                        atomicCAS(info, 0, op.front + 1);
+                        if (lane == l0 + jj)
+                            atomicCAS(info, 0, op.front + 1);
                         d = 1.0;
                     }
                     d = sqrt(d);
-                    r[jj] = d;
-                    piv = 1.0 / d;      // one division per column; the rows below multiply
-                }
-                __syncthreads();
-                const bool below = act && i > p0 + jj;
-                if (below) {
-                    r[jj] = r[jj] * piv;
-                    if (i < p0 + PBW)
-                        colbuf[i - p0] = r[jj];
-                }
-                __syncthreads();
-                if (below) {
-                    const double l = r[jj];
+                    const double pv = 1.0 / d;      // one division per column; the rows below multiply
+                    const bool below = inblk && lane > l0 + jj;
+                    if (lane == l0 + jj) {
+                        r[jj] = d;
+                        pinv[jj] = pv;
+                    } else if (below)
+                        r[jj] = r[jj] * pv;
 #pragma unroll
-                    for (int kk = jj + 1; kk < PBW; ++kk)
-                        r[kk] -= l * colbuf[kk];
+                    for (int kk = 0; kk < PBW; ++kk) {
+                        if (kk <= jj)
+                            continue;   // (fixed bounds: the loops unroll completely and r[] stays in registers)
+                        const double c = __shfl_sync(0xffffffffu, r[jj], l0 + kk);   // L[p0 + kk][p0 + jj]
+                        if (below)
+                            r[kk] -= r[jj] * c;
+                    }
+                }
+                if (inblk) {
+#pragma unroll
+                    for (int kk = 0; kk < PBW; ++kk)
+                        Lb[lane - l0][kk] = r[kk];
+                }
+            }
+            __syncthreads();
+            // (b) the rows below the block: X L11^T = R by substitution against the finished block (broadcast reads),
+            //     the same operations in the same order as a right-looking sweep, without its two barriers per column
+            if (act && i >= p0 + PBW) {
+#pragma unroll
+                for (int jj = 0; jj < PBW; ++jj) {
+                    double v = r[jj];
+#pragma unroll
+                    for (int kk = 0; kk < PBW; ++kk)
+                        if (kk < jj)
+                            v -= r[kk] * Lb[jj][kk];
+                    r[jj] = v * pinv[jj];
                 }
             }
             if (act) {
@@ -152,11 +196,9 @@ __global__ void __launch_bounds__(DIAG_THREADS, CTAS_PER_SM) diag_kernel(const D
             }
             __syncthreads();
         }
-        for (int idx = tid; idx < w * w; idx += DIAG_THREADS) {
-            const int i = idx / w, j = idx - i * w;
-            if (j <= i)
+        for (int i = warp; i < w; i += DIAG_THREADS / 32)
+            for (int j = lane; j <= i; j += 32)
                 op.D[i * ld + j] = S[tri(i, j)];
-        }
     }
     if (op.W == nullptr && op.Wt == nullptr)
         return;
@@ -219,13 +261,13 @@ __global__ void __launch_bounds__(DIAG_THREADS, CTAS_PER_SM) diag_kernel(const D
         }
         __syncthreads();
     }
-    for (int idx = tid; idx < w * w; idx += DIAG_THREADS) {
-        const int i = idx / w, j = idx - i * w;
-        if (op.W)
-            op.W[i * op.ldw + j] = (j <= i) ? S[tri(i, j)] : 0.0;     // W[i][j] (row-major, lower)
-        if (op.Wt)
-            op.Wt[i * op.ldwt + j] = (j >= i) ? S[tri(j, i)] : 0.0;   // Wt[i][j] = W[j][i] (upper)
-    }
+    for (int i = warp; i < w; i += DIAG_THREADS / 32)
+        for (int j = lane; j < w; j += 32) {
+            if (op.W)
+                op.W[i * op.ldw + j] = (j <= i) ? S[tri(i, j)] : 0.0;     // W[i][j] (row-major, lower)
+            if (op.Wt)
+                op.Wt[i * op.ldwt + j] = (j >= i) ? S[tri(j, i)] : 0.0;   // Wt[i][j] = W[j][i] (upper)
+        }
 }
 
 // ---- multi-GPU: finished regions of a replicated front pushed into every peer's replica ----------------------
@@ -366,6 +408,47 @@ __global__ void __launch_bounds__(TRIMV_THREADS) trimv_kernel(const TrimvOp* __r
     const TrimvOp op = ops[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double* __restrict__ x = op.x;
+    if (op.wide) {
+        // wide fronts (k >= TRIMV_WIDE_K: few fronts per level, long rows): up to 8 rows per CTA, the 256 threads stride
+        // across the columns — 8 loads in flight per thread and k / 8 CTAs per front, where the row-group form below left
+        // most of the GPU idle (a 3 400-wide top front: 53 CTAs, 60 GB/s)
+        __shared__ double red[TRIMV_THREADS / 32][TRIMV_WIDE_ROWS];
+        const int gr = op.row0, nr = op.nrows;
+        const int c_lo = op.upper ? gr : 0;
+        const int c_hi = op.upper ? op.k : gr + nr;        // exclusive
+        double acc[TRIMV_WIDE_ROWS];
+#pragma unroll
+        for (int r = 0; r < TRIMV_WIDE_ROWS; ++r)
+            acc[r] = 0.0;
+        for (int c = (c_lo & ~31) + (int)threadIdx.x; c < c_hi; c += TRIMV_THREADS) {
+            if (c < c_lo)
+                continue;
+            const double xv = x[c];
+#pragma unroll
+            for (int r = 0; r < TRIMV_WIDE_ROWS; ++r) {
+                const bool in = r < nr && (op.upper ? c >= gr + r : c <= gr + r);
+                if (in)
+                    acc[r] += op.A[(int64_t)r * op.ld + c] * xv;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < TRIMV_WIDE_ROWS; ++r) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+            if (lane == 0)
+                red[warp][r] = acc[r];
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < nr) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < TRIMV_THREADS / 32; ++w)
+                s += red[w][threadIdx.x];
+            op.y[gr + threadIdx.x] = s;
+        }
+        return;
+    }
     for (int g0 = 4 * warp; g0 < op.nrows; g0 += 4 * (TRIMV_THREADS / 32)) {
         const int gr = op.row0 + g0;                       // first row (front numbering) of the group
         const int nr = op.nrows - g0 < 4 ? op.nrows - g0 : 4;
@@ -468,47 +551,77 @@ __global__ void __launch_bounds__(256) transpose_kernel(const TransposeOp* __res
 
 // ---- selected-inverse gather ---------------------------------------------------------------
 // 16 x 16-station tiles (48 x 48 doubles) staged through shared memory so that both the lower block
-// and its mirror image are written with coalesced rows.
+// and its mirror image are written with coalesced rows.  Read: one 3 x 3 station block per thread (256 blocks per
+// tile), so the index arithmetic — two row-map look-ups and one 64-bit address — is done once per block; write: one
+// tile row per warp and pass.  (The first version indexed element by element and was bound by its integer
+// arithmetic: ncu showed 69 % issue-slot use at 10 % of the DRAM bandwidth, profiles/r2_gather_ncu_summary.txt.)
 constexpr int GT = 16;            // stations per tile edge
 constexpr int GE = 3 * GT;        // doubles per tile edge
 __global__ void __launch_bounds__(256) gather_kernel(const GatherOp* __restrict__ ops, const GatherTile* __restrict__ tiles, int ntiles)
 {
     __shared__ double T[GE][GE + 1];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bi = tid >> 4, bj = tid & 15;            // this thread's station block of the tile
+    const int c0 = lane, c1 = lane + 32;               // the two tile columns this lane writes (c1 < 48 for lanes 0..15)
+    const int cs0 = c0 / 3, cs1 = c1 / 3;              // their stations
+    int cur = -1;
+    GatherOp op;
     // the planner lists exactly the tiles on or below the diagonal of every op; the CTAs stride through the list
     for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
         const GatherTile gt = tiles[tl];
-        const GatherOp op = ops[gt.op];
+        if (gt.op != cur) {                            // (uniform) consecutive tiles mostly belong to one op
+            op = ops[gt.op];
+            cur = gt.op;
+        }
         const int ni = op.nb - op.jb, nj = op.je - op.jb;
         const int i0 = gt.ti * GT, j0 = gt.tj * GT;      // station offsets relative to jb
-        for (int e = threadIdx.x; e < GE * GE; e += 256) {
-            const int ar = e / GE, bc = e - ar * GE;
-            const int ii = i0 + ar / 3, jj = j0 + bc / 3;
-            int a = ar % 3, b = bc % 3;
-            double v = 0.0;
+        {
+            const int ii = i0 + bi, jj = j0 + bj;
+            double v[9];
+#pragma unroll
+            for (int e = 0; e < 9; ++e)
+                v[e] = 0.0;
             if (ii < ni && jj < nj && jj <= ii) {
-                if (ii == jj && a < b) {
-                    const int t = a;
-                    a = b;
-                    b = t;
+                const double* __restrict__ z = op.Z + 3ll * op.rowmap[ii] * op.ld + 3ll * op.rowmap[jj];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b)
+                        v[3 * a + b] = z[a * op.ld + b];
+                if (ii == jj) {                        // a diagonal block: the panel holds its lower triangle only
+                    v[1] = v[3];
+                    v[2] = v[6];
+                    v[5] = v[7];
                 }
-                v = op.Z[(3ll * op.rowmap[ii] + a) * op.ld + 3ll * op.rowmap[jj] + b];
             }
-            T[ar][bc] = v;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b)
+                    T[3 * bi + a][3 * bj + b] = v[3 * a + b];
         }
         __syncthreads();
         // lower part: rows of G along i, contiguous along j
-        for (int e = threadIdx.x; e < GE * GE; e += 256) {
-            const int ar = e / GE, bc = e - ar * GE;
-            const int ii = i0 + ar / 3, jj = j0 + bc / 3;
-            if (ii < ni && jj < nj && jj <= ii)
-                op.G[(3ll * (op.jb + ii) + ar % 3) * op.ldg + 3 * (op.jb + jj) + bc % 3] = T[ar][bc];
+        for (int rr = warp; rr < GE; rr += 8) {
+            const int ii = i0 + rr / 3;
+            if (ii >= ni)
+                break;
+            double* __restrict__ g = op.G + (3ll * (op.jb + i0) + rr) * op.ldg + 3 * (op.jb + j0);
+            if (j0 + cs0 < nj && j0 + cs0 <= ii)
+                g[c0] = T[rr][c0];
+            if (c1 < GE && j0 + cs1 < nj && j0 + cs1 <= ii)
+                g[c1] = T[rr][c1];
         }
         // mirror: rows of G along j, contiguous along i
-        for (int e = threadIdx.x; e < GE * GE; e += 256) {
-            const int bc = e / GE, ar = e - bc * GE;
-            const int ii = i0 + ar / 3, jj = j0 + bc / 3;
-            if (ii < ni && jj < nj && jj <= ii)
-                op.G[(3ll * (op.jb + jj) + bc % 3) * op.ldg + 3 * (op.jb + ii) + ar % 3] = T[ar][bc];
+        for (int cc = warp; cc < GE; cc += 8) {
+            const int jj = j0 + cc / 3;
+            if (jj >= nj)
+                break;
+            double* __restrict__ g = op.G + (3ll * (op.jb + j0) + cc) * op.ldg + 3 * (op.jb + i0);
+            if (i0 + cs0 < ni && jj <= i0 + cs0)
+                g[c0] = T[c0][cc];
+            if (c1 < GE && i0 + cs1 < ni && jj <= i0 + cs1)
+                g[c1] = T[c1][cc];
         }
         __syncthreads();
     }

@@ -600,8 +600,9 @@ struct Builder {
     //   backward (top-down):   y1 -= L21^T x[boundary rows];   x1 = Wt y1
     void add_trimv(std::vector<TrimvOp>& tb, uint32_t fi, bool upper)
     {
-        const int ROWS = 64;
         const Front& f = s.fronts[fi];
+        const bool wide = (int)f.k >= TRIMV_WIDE_K;
+        const int ROWS = wide ? TRIMV_WIDE_ROWS : 64;
         const uint32_t ldw = ldw_of(f);
         const double* A = upper ? Wtof(fi) : Wof(fi);
         for (int r0 = 0; r0 < (int)f.k; r0 += ROWS) {
@@ -612,6 +613,7 @@ struct Builder {
             t.nrows = std::min<int>(ROWS, (int)f.k - r0);
             t.k = (int32_t)f.k;
             t.upper = upper ? 1 : 0;
+            t.wide = wide ? 1 : 0;
             t.x = (upper ? b.y : b.x) + 3 * (size_t)f.own_begin;
             t.y = (upper ? b.x : b.y) + 3 * (size_t)f.own_begin;
             tb.push_back(t);
