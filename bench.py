@@ -56,7 +56,7 @@ def workload_name(key, cfg):
 def ncu_traffic(*kernels):
     """DRAM bytes per launch of the named kernel(s), summed, from the committed ncu capture of this workload
     (dram__bytes_read.sum + dram__bytes_write.sum, C4 on one GPU)."""
-    for name in ("r2_ncu_dram_traffic_c4.json", "r1_ncu_dram_traffic_c4.json"):
+    for name in ("r2b_ncu_dram_traffic_c4.json", "r2_ncu_dram_traffic_c4.json", "r1_ncu_dram_traffic_c4.json"):
         p = os.path.join(ROOT, "profiles", name)
         try:
             k = json.load(open(p))["kernels"]

@@ -36,6 +36,44 @@ def test_dense_front_block_doubling(oracle, hostsim_path):
     assert info.nfronts == 1
 
 
+@pytest.mark.parametrize("tile", [64, 128])
+def test_gemm_tile_shapes_plan(oracle, hostsim_path, tile):
+    """The planner's tile lists for either shape of the tile GEMM (the stand-in kernel walks exactly the listed tiles with
+    the launch's shape): dissection with multi-tile fronts, a chain, a dense front wider than several pivot tiles — incl.
+    the in-place pivot-panel product, which must stay in one column tile."""
+    parity.check_against_oracle(oracle, hostsim_path, 1000, 3000, 7, leaf_stations=24, gemm_tile=tile)
+    parity.check_against_oracle(oracle, hostsim_path, 300, 900, 9, blocks=lambda n: parity.chain_blocks(n, 40), gemm_tile=tile)
+    parity.check_against_oracle(oracle, hostsim_path, 250, 750, 23, ordering=engine.ORDER_DENSE, gemm_tile=tile)
+
+
+def test_gemm_tile_option_is_validated(hostsim_path):
+    stn, msr, _, _ = synth.gnss_network(40, 120, 3)
+    adj = engine.Adjustment(stn, msr, lib_path=hostsim_path, gemm_tile=96)
+    with pytest.raises(engine.AdjustmentError) as e:
+        adj.prepare()
+    assert "gemm_tile" in str(e.value)
+
+
+def test_gemm_flags_reference_semantics(hostsim_path):
+    """gadj_test_gemm_ex on the stand-in kernel: the flag semantics the GPU test of the same name holds the CUDA kernel to."""
+    ACCUM, NEG, LOWER, KLO_ROW, KHI_ROW, DUAL = 1, 2, 4, 16, 64, 128
+    rng = np.random.default_rng(5)
+    adj = engine.Adjustment(lib_path=hostsim_path)
+    for tile in (64, 128):
+        A, B, C0 = rng.standard_normal((150, 70)), rng.standard_normal((150, 70)), rng.standard_normal((150, 150))
+        C, _, _ = adj.test_gemm_ex(A, B, C0, flags=ACCUM | NEG | LOWER, tile=tile)
+        ref = C0 - A @ B.T
+        ref[np.triu_indices(150, 1)] = C0[np.triu_indices(150, 1)]
+        assert np.abs(C - ref).max() < 1e-12
+        A = np.triu(rng.standard_normal((130, 130)))
+        B = rng.standard_normal((90, 130))
+        C, Ct, _ = adj.test_gemm_ex(A, B, flags=KLO_ROW | DUAL, tile=tile)
+        assert np.abs(C - A @ B.T).max() < 1e-12 and np.abs(Ct - C.T).max() == 0.0
+        C, _, _ = adj.test_gemm_ex(np.tril(A.T), B, flags=KHI_ROW, tile=tile)
+        assert np.abs(C - np.tril(A.T) @ B.T).max() < 1e-12
+    adj.close()
+
+
 def test_chain_blocks_match_oracle(oracle, hostsim_path):
     # a .seg-style chain of blocks (phased adjustment) is rigorous: same answer as simultaneous
     info = parity.check_against_oracle(oracle, hostsim_path, 300, 900, 9, blocks=lambda n: parity.chain_blocks(n, 40))
