@@ -22,7 +22,8 @@
 // Roofline: FP64 tensor pipe.  Per tile and 16-deep K step: 2*128*128*16 = 524k flop against
 // 32 KB of TMA traffic (16 flop/B from L2; panels are read ~once from HBM per launch).
 // Measured DMMA issue ceiling from registers: 36.4 TFLOP/s (tools/probes/dmma_pred_probe.cu); cuBLAS DGEMM 35.4;
-// this kernel 35.5 at 4096^3 and 29.3 (algorithmic flops) over a whole C4 iteration.
+// this kernel 35.5 at 4096^3 and 28.6 (executed useful flops: 0.81 of the sustained DGEMM rate) over a whole C4 iteration
+// with the planner's per-launch choice of tile shape (25.8 with 128 x 128 tiles only).
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -88,6 +89,13 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
+}
+// FP64 add into global memory, result not needed.  (atomicAdd on a pointer read from a descriptor is a generic-space
+// atomic: the compiler emits a shared / global space check and both code paths around every one of the up to 4 096 adds
+// of a scatter tile; the targets are always panels in global memory.)
+__device__ __forceinline__ void red_add_f64(double* p, double v)
+{
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
 }
 __device__ __forceinline__ double lds_f64(uint32_t addr)
 {
@@ -324,7 +332,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB)
                 if (cbase[cc] == nullptr || (lower && r + tri_off < col0 + cl))
                     continue;
                 const double v = lds_f64(rbase + (uint32_t)((((cl >> 2) ^ sw) << 5) + ((cl & 3) << 3)));
-                atomicAdd(cbase[cc] + (3ll * rmap[cc][si] + rc) * cld[cc], alpha * v);
+                red_add_f64(cbase[cc] + (3ll * rmap[cc][si] + rc) * cld[cc], alpha * v);
             }
         }
         if (LOADER == 0) {
