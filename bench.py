@@ -484,7 +484,8 @@ def run_engine(args):
                                 sharding=(f"{world} ranks, subtrees of the dissection tree; {info.top_fronts} top fronts replicated, their "
                                           f"tiles shared out among the ranks; all-reduce, stores into the peers' replicas and barriers in our "
                                           f"own kernels over NVLink peer mappings (cut at level {info.cut_level})") if world > 1 else "none",
-                                panel_gb=info.panel_bytes / 1e9, prepare_s=prepare_s),
+                                panel_gb=info.panel_bytes / 1e9, prepare_s=prepare_s,
+                                gemm_tiles="64x64 (3 CTAs/SM) or 128x128 (1 CTA/SM), chosen per launch by the planner"),
                     e2e=dict(value=e2e_ms, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
                     e2e_first_iteration_ms=prepare_s * 1e3 + first_iteration_ms,
                     device_ms_per_step=device_ms,

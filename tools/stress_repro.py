@@ -17,10 +17,13 @@ from tests import parity  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "C3"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 tag = sys.argv[3] if len(sys.argv) > 3 else "a"
+only = sys.argv[4] if len(sys.argv) > 4 else "both"      # "nd", "chain" or "both"
 stn, msr, truth, _ = synth.config_network(name)
 thr = float(np.float32(0.0005))
 bad = []
 for label, kw, blocks in (("nd", dict(leaf_stations=96), None), ("chain", dict(), parity.chain_blocks(len(stn), 1000))):
+    if only not in ("both", label):
+        continue
     s, m = stn.copy(), msr.copy()
     adj = engine.Adjustment(s, m, **kw)
     if blocks is not None:
