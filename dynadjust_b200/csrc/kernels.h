@@ -20,7 +20,8 @@ constexpr int TILE_M = 128;
 constexpr int TILE_N = 128;
 constexpr int TILE_K = 16;   // doubles per TMA box row (= 128 bytes, SWIZZLE_128B)
 // Tile shape of a GEMM launch (all tiles of a launch have the same shape; GemmTile::tm / tn and the ops' tensor-map
-// boxes are in its units): 128 x 128 for the large fronts, 64 x 64 for launches made of small fronts (plan.cpp picks).
+// boxes are in its units): 64 x 64 wherever it costs no more padded work, 128 x 128 for launches of long products
+// (K >= ~2000), shared / pushed tiles of the top fronts and wide in-place products (plan.cpp, choose_shape).
 enum TileShape : int32_t { TILE_SHAPE_128 = 0, TILE_SHAPE_64 = 1 };
 constexpr int tile_dim(int shape) { return shape == TILE_SHAPE_64 ? 64 : TILE_M; }
 constexpr int NB = 128;      // pivot block width of the blocked factorisation

@@ -4,7 +4,7 @@ For each mode: prepare, warm up, one profiled iteration (per-launch CSV: index, 
 timed iterations, and the results against the 128 x 128 run (largest coordinate difference, largest relative
 difference of the station variance blocks) plus the normal-equation identity on every station.
 
-    python tools/tile_experiment.py [C4] [leaf] [modes, e.g. 128,64,0,0:1.3]   -> gpurun_out/tile_<mode>.csv, tile_experiment.json
+    python tools/tile_experiment.py [C4] [leaf] [modes, e.g. 128,64,0,0:256]   -> gpurun_out/tile_<mode>.csv, tile_experiment.json
 A mode "0:<steps>" runs the planner's choice with GADJ_TILE_LONG_K=<steps> (16-deep K steps from which 128-wide tiles are kept).
 """
 import json
@@ -29,10 +29,10 @@ stn0, msr0, _, _ = synth.config_network(cfg)
 results = {}
 ref = None
 for mode in modes:
-    tile, _, margin = mode.partition(":")
+    tile, _, long_k = mode.partition(":")
     os.environ.pop("GADJ_TILE_LONG_K", None)
-    if margin:
-        os.environ["GADJ_TILE_LONG_K"] = margin
+    if long_k:
+        os.environ["GADJ_TILE_LONG_K"] = long_k
     stn, msr = stn0.copy(), msr0.copy()
     adj = engine.Adjustment(stn, msr, leaf_stations=leaf, gemm_tile=int(tile))
     t = time.time()
