@@ -74,6 +74,20 @@ def test_gemm_flags_reference_semantics(hostsim_path):
     adj.close()
 
 
+SLOW = pytest.mark.skipif(not os.environ.get("GADJ_SLOW_TESTS"), reason="minutes of dense CPU oracle: set GADJ_SLOW_TESTS=1")
+
+
+@SLOW
+def test_dense_oracle_at_5000_mixed_stations(oracle, hostsim_path):
+    """The largest size the dense oracle (explicit inverse of the 15 000 x 15 000 normals) finishes in minutes: 5 000
+    stations, 15 000 GNSS baselines + 4 000 slope distances + 3 000 levelled height differences, 169 fronts on 8 levels;
+    north_star tolerances (1e-9 m; sigma-zero 1e-7 with local-frame rows, see test_gpu_parity.py).  3 minutes on 8 cores;
+    the same check on the device is tests/test_gpu_parity.py::test_dense_oracle_at_5000_mixed_stations."""
+    info = parity.check_against_oracle(oracle, hostsim_path, 5000, 15000, 101, n_distances=4000, n_levels=3000,
+                                       leaf_stations=64, tol_sigma0=1e-7)
+    assert info.nfronts > 100
+
+
 def test_chain_blocks_match_oracle(oracle, hostsim_path):
     # a .seg-style chain of blocks (phased adjustment) is rigorous: same answer as simultaneous
     info = parity.check_against_oracle(oracle, hostsim_path, 300, 900, 9, blocks=lambda n: parity.chain_blocks(n, 40))
