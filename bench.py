@@ -462,7 +462,11 @@ def run_engine(args):
                         peak_source="cuBLAS DGEMM 8192^3 sustained (back to back ~2 s) measured in this run; MEASURED_PEAKS.json has no FP64 entry",
                         peak_burst=peak_burst, executed_gemm_flops_per_step=executed,
                         algorithmic_flops_per_step=alg_flops, rank0_algorithmic_flops_per_step=rank_flops,
-                        whole_step_frac=alg_flops / world / (ms_step * 1e9) / peak_sustained,
+                        # the whole step against the same peak: this rank's executed useful GEMM flops over the step time
+                        # (everything that is not a GEMM — pivot tiles, gather, substitutions, assembly — counts as lost time);
+                        # symbolic_step_frac: the symbolic count (pivot-tile flops and the full k^2 r terms included) per rank
+                        whole_step_frac=executed / (ms_step * 1e9) / peak_sustained,
+                        symbolic_step_frac=alg_flops / world / (ms_step * 1e9) / peak_sustained,
                         kernel_ms_per_step=gemm_ms, kernel_share_of_step=gemm_ms / ms_step,
                         launches_per_step=prof.gemm_launches / args.steps)
         if wl.get("dense"):
